@@ -1,0 +1,218 @@
+/* b200lp.h — C ABI of the B200-native local-planner rollout-and-score path.
+ *
+ * This is the drop-in boundary for dddmr_navigation's local planner hot path. Every entry
+ * point replaces a piece of the reference's in-process C++ interface (paths relative to the
+ * reference tree, src/dddmr_local_planner/ = LP/):
+ *
+ *   b200lp_create            <- plugin parameter loading: TrajectoryGeneratorTheory::onInitialize
+ *                               (LP/trajectory_generators/theories/dd_simple_trajectory_generator_theory.cpp:43-234,
+ *                                omni_simple…cpp:43-256, dd_rotate_inplace_theory.cpp:43-227) and
+ *                               ScoringModel::onInitialize + the per-generator critic list
+ *                               (LP/mpc_critics/src/mpc_critics_ros.cpp:60-82).
+ *   b200lp_set_cloud         <- ModelSharedData::pcl_perception_ assignment + updateData() kd-tree build
+ *                               (LP/local_planner/src/local_planner.cpp:582,586;
+ *                                LP/mpc_critics/include/mpc_critics/model_shared_data.h:74-81).
+ *   b200lp_set_plan          <- prune_plan_ hand-over to generator and critic shared data
+ *                               (local_planner.cpp:530,583; model_shared_data.h:83-91).
+ *   b200lp_plan              <- initializeTheories_wi_Shared_data() + the rollout loop + getBestTrajectory()
+ *                               (local_planner.cpp:535-587; LP/trajectory_generators/src/stacked_generator.cpp:67-111;
+ *                                LP/mpc_critics/src/stacked_scoring_model.cpp:75-93; local_planner.cpp:447-480).
+ *   b200lp_plan_batch        <- the same cycle for many independent robots (fleet sharding; no reference analogue,
+ *                               one reference process serves one robot).
+ *   b200lp_read_trajectories <- what the reference keeps in std::vector<base_trajectory::Trajectory>
+ *                               (LP/base_trajectory/include/base_trajectory/trajectory.h:47-126) — read back for
+ *                               RViz publishing (local_planner.cpp:554,569) and for parity tests.
+ *   b200lp_count_radius      <- diagnostic: |radiusSearch(pose, 1.0)| per pose (LP/mpc_critics/models/collision_model.cpp:122),
+ *                               the n_r1 figure the roofline accounting is defined on.
+ *
+ * Conventions: extern "C"; plain pointers and sizes; every function returns 0 on success and a
+ * negative B200LP_E_* code on failure, with text from b200lp_last_error(); the caller owns every
+ * input buffer and may free it on return; a ctx owns its device memory and one CUDA stream, is
+ * bound to one device and is NOT re-entrant (the reference serialises the same calls under its
+ * perception and critics mutexes, local_planner.cpp:498,577). There is no CPU fallback: without a
+ * usable CUDA device b200lp_create fails with B200LP_E_CUDA.
+ */
+#ifndef B200LP_H_
+#define B200LP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200LP_ABI_VERSION 1
+
+/* status codes */
+#define B200LP_OK 0
+#define B200LP_E_INVALID (-1) /* bad argument / parameter set outside the supported envelope */
+#define B200LP_E_CUDA (-2)    /* CUDA runtime error or no device */
+#define B200LP_E_STATE (-3)   /* call order violated (e.g. read before plan) */
+#define B200LP_E_NOMEM (-4)
+
+/* trajectory generator theories (LP/trajectory_generators/trajectory_generators.xml) */
+#define B200LP_THEORY_DD_SIMPLE 0         /* trajectory_generators::DDSimpleTrajectoryGeneratorTheory */
+#define B200LP_THEORY_OMNI_SIMPLE 1       /* trajectory_generators::OmniSimpleTrajectoryGeneratorTheory */
+#define B200LP_THEORY_DD_ROTATE_INPLACE 2 /* trajectory_generators::DDRotateInplaceTheory */
+
+/* critics (LP/mpc_critics/mpc_critics.xml) */
+#define B200LP_CRITIC_COLLISION 0          /* mpc_critics::CollisionModel */
+#define B200LP_CRITIC_COLLISION_MIN_MAX 1  /* mpc_critics::CollisionMinMaxModel */
+#define B200LP_CRITIC_STICK_PATH 2         /* mpc_critics::StickPathModel */
+#define B200LP_CRITIC_PURE_PURSUIT 3       /* mpc_critics::PurePursuitModel */
+#define B200LP_CRITIC_TOWARD_GLOBAL_PLAN 4 /* mpc_critics::TowardGlobalPlanModel */
+#define B200LP_CRITIC_SHORTEST_ANGLE 5     /* mpc_critics::ShortestAngleModel */
+#define B200LP_CRITIC_TWIRLING 6           /* mpc_critics::TwirlingModel */
+#define B200LP_MAX_CRITICS 8
+
+/* Upper bound on poses per trajectory (num_steps). The reference has none; the shipped parameter
+ * sets produce <= 252 (rotate in place). b200lp_create rejects parameter sets that could exceed it. */
+#define B200LP_MAX_STEPS 512
+/* Upper bound on prune-plan poses per robot. */
+#define B200LP_MAX_PLAN 1024
+
+typedef struct b200lp_ctx b200lp_ctx;
+
+/* DDTrajectoryGeneratorLimits / OmniTrajectoryGeneratorLimits
+ * (LP/trajectory_generators/include/trajectory_generators/dd_simple_trajectory_generator_limits.h:40-109,
+ *  omni_simple_trajectory_generator_limits.h:40-125); rotation_speed from dd_rotate_inplace_theory.cpp:127. */
+typedef struct b200lp_limits {
+  double max_vel_x, min_vel_x;
+  double max_vel_y, min_vel_y;         /* omni only */
+  double max_vel_trans, min_vel_trans; /* omni only */
+  double max_vel_theta, min_vel_theta;
+  double acc_lim_x, acc_lim_y, acc_lim_theta;
+  double deceleration_ratio;
+  double max_motor_shaft_rpm, wheel_diameter, gear_ratio, robot_radius;
+  double rotation_speed; /* rotate-in-place only */
+  int32_t use_motor_constraint;
+  int32_t reserved_;
+} b200lp_limits;
+
+/* DDTrajectoryGeneratorParams / OmniTrajectoryGeneratorParams
+ * (…/dd_simple_trajectory_generator_params.h:42-76, omni_simple_trajectory_generator_params.h:42-80).
+ * The *_sample fields are doubles truncated to int exactly as the reference passes them to
+ * VelocityIterator (velocity_iterator.h:44). */
+typedef struct b200lp_params {
+  int32_t theory; /* B200LP_THEORY_* */
+  int32_t reserved_;
+  double controller_frequency;
+  double sim_time;
+  double linear_x_sample, linear_y_sample, angular_z_sample;
+  double sim_granularity, angular_sim_granularity;
+} b200lp_params;
+
+/* One entry of the generator's ordered critic list (YAML plugins: order, mpc_critics_ros.cpp:63-82). */
+typedef struct b200lp_critic {
+  int32_t kind; /* B200LP_CRITIC_* */
+  int32_t reserved_;
+  double weight;             /* ScoringModel::weight_ */
+  double translation_weight; /* PurePursuitModel only */
+  double orientation_weight; /* PurePursuitModel only */
+} b200lp_critic;
+
+/* Voxel-grid configuration of the lethal cloud (no reference analogue: replaces KdTreeFLANN).
+ * Zero-initialise for defaults. */
+typedef struct b200lp_grid_config {
+  float cell_xy;      /* cell edge in x and y, metres (default 0.25) */
+  float cell_z;       /* cell height, metres (default 0.25) */
+  uint32_t max_cells; /* cap on the dense cell count; cells are coarsened to fit (default 1<<26) */
+  uint32_t reserved_;
+} b200lp_grid_config;
+
+/* Per-cycle inputs the reference copies into the shared-data structs (local_planner.cpp:528-533,579-583). */
+typedef struct b200lp_query {
+  double pose[7];            /* robot_pose_: translation x,y,z then rotation x,y,z,w (map -> base_link) */
+  double twist[3];           /* robot_state_.twist.twist: linear.x, linear.y, angular.z */
+  double max_speed_override; /* current_allowed_max_linear_speed_ (<= 0: ignored) */
+  double heading_deviation;  /* ModelSharedData::heading_deviation_ (ShortestAngleModel) */
+} b200lp_query;
+
+/* What Local_Planner::getBestTrajectory leaves in best_traj plus cycle counters. */
+typedef struct b200lp_result {
+  int32_t best_id;   /* index into the generated-trajectory list; -1 = all rejected (ALL_TRAJECTORIES_FAIL) */
+  int32_t n_samples; /* |sample_params_| after initialise() */
+  int32_t n_traj;    /* trajectories generateTrajectory() accepted (= |trajectories_|) */
+  int32_t n_collided;/* trajectories whose cost_ is a collision critic's -1 */
+  int64_t n_poses;   /* sum of num_steps over generated trajectories */
+  double best_cost;  /* best_traj.cost_ (-1 when best_id < 0) */
+  double xv, yv, thetav; /* best_traj.{xv_,yv_,thetav_} */
+} b200lp_result;
+
+/* Optional per-trajectory read-back. Any pointer may be NULL. Arrays are indexed by trajectory id
+ * (0..n_traj-1) of robot `robot` of the last plan / plan_batch call. */
+typedef struct b200lp_traj_view {
+  int32_t* sample_index;  /* [n_traj] index of the velocity sample that produced the trajectory */
+  float* vel;             /* [n_traj*3] xv, yv, thetav as the float sample */
+  int32_t* num_steps;     /* [n_traj] */
+  double* time_delta;     /* [n_traj] Trajectory::time_delta_ */
+  double* cost;           /* [n_traj] Trajectory::cost_ after StackedScoringModel::scoreTrajectory */
+  double* critic_scores;  /* [n_traj*n_critics] value each critic returned; NaN = not evaluated (after an early-out) */
+  int32_t* first_hit_pose;/* [n_traj] first pose index a collision critic rejected at, -1 = none / not evaluated */
+} b200lp_traj_view;
+
+/* Optional per-pose read-back of ONE trajectory (recomputed on the device on demand). */
+typedef struct b200lp_pose_view {
+  double* pose;     /* [num_steps*7] PoseStamped position xyz + orientation xyzw */
+  float* pcl_pose;  /* [num_steps*3] Trajectory::getPCLPoint */
+  float* cuboid;    /* [num_steps*8*3] Trajectory::getCuboid vertices, order blb,brb,blt,flb,brt,frt,flt,frb */
+  float* aabb;      /* [num_steps*6] Trajectory::getCuboidMinMax min xyz, max xyz */
+  uint8_t* collide; /* [num_steps] 1 if the pose collides under the first collision critic of the stack
+                       (evaluated for every pose, no early exit) */
+  int32_t* n_r1;    /* [num_steps] |radiusSearch(pose, 1.0)| */
+} b200lp_pose_view;
+
+const char* b200lp_last_error(const b200lp_ctx* ctx); /* ctx may be NULL: last create() error of this thread */
+int b200lp_abi_version(void);
+
+int b200lp_create(b200lp_ctx** out, int device, const b200lp_limits* limits, const b200lp_params* params,
+                  const float* cuboid_xyz /* 8*3, order blb,brb,blt,flb,brt,frt,flt,frb */,
+                  const b200lp_critic* critics, int n_critics, const b200lp_grid_config* grid /* may be NULL */);
+void b200lp_destroy(b200lp_ctx* ctx);
+
+/* Upload the aggregated observation cloud and (re)build the voxel grid. `pts` is host memory,
+ * n points of `stride_bytes` each (32 = pcl::PointXYZI, 16 = pcl::PointXYZ), x,y,z = first three floats. */
+int b200lp_set_cloud(b200lp_ctx* ctx, const void* pts, size_t n, size_t stride_bytes);
+/* Same, `pts` already resident on ctx's device (e.g. produced by a device-side perception stage). */
+int b200lp_set_cloud_device(b200lp_ctx* ctx, const void* dev_pts, size_t n, size_t stride_bytes);
+
+/* Prune plan of the single-robot path: n poses of 7 doubles (position xyz, orientation xyzw). */
+int b200lp_set_plan(b200lp_ctx* ctx, const double* xyz_qxyzw, size_t n);
+
+/* One local-plan cycle for one robot. */
+int b200lp_plan(b200lp_ctx* ctx, const b200lp_query* q, b200lp_result* out);
+
+/* Sample-sharded cycle: this ctx scores only the contiguous sample range of shard `rank` of `count`
+ * (samples [rank*S/count, (rank+1)*S/count)); ids and counters in `out` stay global / local resp.:
+ * best_id is the GLOBAL trajectory id, n_traj/n_poses/n_collided count the local shard. The caller
+ * reduces (best_cost, best_id) across shards: min cost, ties -> largest id (local_planner.cpp:460). */
+int b200lp_plan_shard(b200lp_ctx* ctx, const b200lp_query* q, int rank, int count, b200lp_result* out);
+
+/* Fleet cycle: n_robots independent queries on the shared cloud. Robot i's prune plan is
+ * plans[plan_offsets[i] .. plan_offsets[i+1]) (7 doubles per pose). */
+int b200lp_plan_batch(b200lp_ctx* ctx, const b200lp_query* qs, size_t n_robots, const double* plans,
+                      const int64_t* plan_offsets /* n_robots+1 */, b200lp_result* outs);
+
+int b200lp_read_trajectories(b200lp_ctx* ctx, size_t robot, const b200lp_traj_view* view);
+int b200lp_read_poses(b200lp_ctx* ctx, size_t robot, int32_t traj_id, const b200lp_pose_view* view);
+
+/* Roofline accounting helper: sum over all scored poses of the last plan call of
+ * |{cloud points with float d^2 < 1.0 to the pose}| (the reference's radiusSearch candidate set). */
+int b200lp_count_radius(b200lp_ctx* ctx, int64_t* sum_n_r1, int64_t* n_poses);
+
+/* Device-timeline instrumentation: milliseconds the last call spent in each stage, measured with
+ * CUDA events on ctx's stream. Any pointer may be NULL. */
+int b200lp_last_timing(const b200lp_ctx* ctx, float* ms_upload, float* ms_grid_build, float* ms_plan_kernels,
+                       float* ms_readback);
+/* Number of kernels this library launched on ctx's stream since creation. */
+int64_t b200lp_launch_count(const b200lp_ctx* ctx);
+/* Grid geometry of the current cloud (for tests / docs). dims = nx,ny,nz; origin xyz; cell xy,z. */
+int b200lp_grid_info(const b200lp_ctx* ctx, int32_t dims[3], float origin[3], float cell[2], int64_t* n_points_kept);
+/* The CUDA stream (cudaStream_t as void*) all work of ctx is enqueued on. */
+void* b200lp_stream(const b200lp_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200LP_H_ */

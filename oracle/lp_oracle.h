@@ -1,0 +1,69 @@
+/* lp_oracle.h — C ABI of the CPU oracle (TEST INFRASTRUCTURE, not product code).
+ *
+ * The oracle restates, on the CPU and in the reference's own arithmetic, the local-planner
+ * rollout-and-score path of dddmr_navigation. Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load it. PARITY UNPINNED: the reference
+ * ships no tests or golden vectors for this path and cannot be built in this image (needs
+ * ROS 2 Humble, PCL 1.15, FLANN, Eigen, tf2), so the oracle is pinned only to (a) glibc sinf/cosf,
+ * exhaustively, (b) hand-derived micro-cases, (c) the reference's vendored nanoflann as an
+ * independent radius-search index (oracle/_ref build). See DESIGN.md §3.
+ *
+ * It reuses the product's public POD structs (include/b200lp.h) so tests feed both sides the
+ * same bytes.
+ */
+#ifndef LP_ORACLE_H_
+#define LP_ORACLE_H_
+#include "../include/b200lp.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LPORACLE_MATH_SHARED 0 /* dddmr_navigation_b200/csrc/lp_math.h — what the GPU evaluates */
+#define LPORACLE_MATH_LIBM 1   /* glibc libm — what the reference binary calls */
+
+#define LPORACLE_INDEX_BRUTE 0     /* scan the whole cloud per query */
+#define LPORACLE_INDEX_GRID 1      /* uniform 1 m bucket grid (exact) */
+#define LPORACLE_INDEX_NANOFLANN 2 /* reference's vendored nanoflann 1.5.1 kd-tree; only in oracle/_ref builds */
+
+typedef struct lporacle_ctx lporacle_ctx;
+
+int lporacle_has_nanoflann(void);
+int lporacle_create(lporacle_ctx** out, const b200lp_limits* limits, const b200lp_params* params,
+                    const float* cuboid_xyz, const b200lp_critic* critics, int n_critics, int math_mode,
+                    int index_mode);
+void lporacle_destroy(lporacle_ctx* ctx);
+const char* lporacle_last_error(const lporacle_ctx* ctx);
+int lporacle_set_cloud(lporacle_ctx* ctx, const void* pts, size_t n, size_t stride_bytes);
+int lporacle_set_plan(lporacle_ctx* ctx, const double* xyz_qxyzw, size_t n);
+/* Score only samples whose index % stride == phase (bounded-sample CPU baseline). Default 1, 0. */
+int lporacle_set_sample_stride(lporacle_ctx* ctx, int stride, int phase);
+/* One cycle: (re)build the spatial index like ModelSharedData::updateData, roll out, score, argmin.
+ * n_threads > 1 splits the trajectories over std::threads (a courtesy upper bound; the reference
+ * is single-threaded). seconds_index / seconds_rollout / seconds_score may be NULL. */
+int lporacle_plan(lporacle_ctx* ctx, const b200lp_query* q, int n_threads, b200lp_result* out,
+                  double* seconds_index, double* seconds_rollout, double* seconds_score);
+int lporacle_read_trajectories(lporacle_ctx* ctx, const b200lp_traj_view* view);
+int lporacle_read_poses(lporacle_ctx* ctx, int32_t traj_id, const b200lp_pose_view* view);
+int lporacle_count_radius(lporacle_ctx* ctx, int64_t* sum_n_r1, int64_t* n_poses);
+
+/* Velocity samples exactly as initialise() leaves them in sample_params_ (xv,yv,thetav floats).
+ * Returns the count; fills up to cap samples. */
+int lporacle_samples(lporacle_ctx* ctx, const b200lp_query* q, float* out_xyz, int cap);
+
+/* scalar math probes for tests/test_math.py (mode = LPORACLE_MATH_*) */
+float lporacle_sinf(int mode, float x);
+float lporacle_cosf(int mode, float x);
+double lporacle_sin(int mode, double x);
+double lporacle_cos(int mode, double x);
+double lporacle_asin(int mode, double x);
+double lporacle_atan2(int mode, double y, double x);
+double lporacle_fmod(int mode, double x, double y);
+/* vectorised mismatch counter: compares shared vs libm sinf and cosf over the float bit patterns
+ * [lo, hi) with the given step (sign bit cleared and set); returns the number of mismatches. */
+int64_t lporacle_sincosf_mismatches(uint32_t lo, uint32_t hi, uint32_t step);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,173 @@
+"""ctypes wrapper of the CPU oracle (oracle/lp_oracle.cpp). TEST INFRASTRUCTURE — see oracle/lp_oracle.h.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+The class mirrors dddmr_navigation_b200.planner.LocalPlanner method for method so parity tests read
+symmetrically.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from dddmr_navigation_b200 import abi
+from dddmr_navigation_b200.config import PlannerConfig
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "liblporacle.so")
+LIB_REF = os.path.join(HERE, "_ref", "liblporacle_ref.so")
+
+MATH_SHARED, MATH_LIBM = 0, 1
+INDEX_BRUTE, INDEX_GRID, INDEX_NANOFLANN = 0, 1, 2
+
+_P = C.c_void_p
+_SYMS = {
+    "lporacle_has_nanoflann": (C.c_int, []),
+    "lporacle_create": (C.c_int, [C.POINTER(_P), C.POINTER(abi.Limits), C.POINTER(abi.Params), C.POINTER(C.c_float),
+                                  C.POINTER(abi.Critic), C.c_int, C.c_int, C.c_int]),
+    "lporacle_destroy": (None, [_P]),
+    "lporacle_last_error": (C.c_char_p, [_P]),
+    "lporacle_set_cloud": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t]),
+    "lporacle_set_plan": (C.c_int, [_P, C.POINTER(C.c_double), C.c_size_t]),
+    "lporacle_set_sample_stride": (C.c_int, [_P, C.c_int, C.c_int]),
+    "lporacle_plan": (C.c_int, [_P, C.POINTER(abi.Query), C.c_int, C.POINTER(abi.Result), C.POINTER(C.c_double),
+                                C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "lporacle_read_trajectories": (C.c_int, [_P, C.POINTER(abi.TrajView)]),
+    "lporacle_read_poses": (C.c_int, [_P, C.c_int32, C.POINTER(abi.PoseView)]),
+    "lporacle_count_radius": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "lporacle_samples": (C.c_int, [_P, C.POINTER(abi.Query), C.POINTER(C.c_float), C.c_int]),
+    "lporacle_sinf": (C.c_float, [C.c_int, C.c_float]),
+    "lporacle_cosf": (C.c_float, [C.c_int, C.c_float]),
+    "lporacle_sin": (C.c_double, [C.c_int, C.c_double]),
+    "lporacle_cos": (C.c_double, [C.c_int, C.c_double]),
+    "lporacle_asin": (C.c_double, [C.c_int, C.c_double]),
+    "lporacle_atan2": (C.c_double, [C.c_int, C.c_double, C.c_double]),
+    "lporacle_fmod": (C.c_double, [C.c_int, C.c_double, C.c_double]),
+    "lporacle_sincosf_mismatches": (C.c_int64, [C.c_uint32, C.c_uint32, C.c_uint32]),
+}
+_libs = {}
+
+
+def build(force: bool = False) -> None:
+    """Compile the oracle (and oracle/_ref when /root/reference is present) with oracle/Makefile."""
+    if force or not os.path.exists(LIB):
+        subprocess.run(["make", "-C", HERE, "-B" if force else "-s"], check=True, capture_output=True)
+    else:
+        subprocess.run(["make", "-C", HERE, "-s"], check=True, capture_output=True)
+
+
+def load(ref: bool = False):
+    key = "ref" if ref else "own"
+    if key in _libs:
+        return _libs[key]
+    path = LIB_REF if ref else LIB
+    if not os.path.exists(path):
+        build()
+    lib = C.CDLL(path)
+    for name, (res, args) in _SYMS.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _libs[key] = lib
+    return lib
+
+
+def have_ref() -> bool:
+    return os.path.exists(LIB_REF)
+
+
+class OraclePlanner:
+    """CPU restatement of one generator + its critic stack (same surface as LocalPlanner)."""
+
+    def __init__(self, config: PlannerConfig, math_mode: int = MATH_SHARED, index_mode: int = INDEX_GRID):
+        self.lib = load(ref=(index_mode == INDEX_NANOFLANN))
+        self.config = config
+        self._L, self._Pm = config.limits(), config.params()
+        self._cub = config.cuboid()
+        self._crit, self.n_critics = config.critic_array()
+        h = _P()
+        rc = self.lib.lporacle_create(C.byref(h), C.byref(self._L), C.byref(self._Pm),
+                                      self._cub.ctypes.data_as(C.POINTER(C.c_float)), self._crit, self.n_critics,
+                                      math_mode, index_mode)
+        if rc != 0:
+            raise RuntimeError(f"lporacle_create failed: {rc}")
+        self.h = h
+        self.last = None
+        self.timing = (0.0, 0.0, 0.0)
+
+    def close(self):
+        if self.h:
+            self.lib.lporacle_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_cloud(self, pts: np.ndarray):
+        pts = np.ascontiguousarray(pts, dtype=np.float32)
+        assert pts.ndim == 2 and pts.shape[1] in (3, 4, 8)
+        stride = pts.shape[1] * 4
+        if pts.shape[1] == 3:  # repack to 16-byte stride
+            p4 = np.zeros((pts.shape[0], 4), np.float32)
+            p4[:, :3] = pts
+            pts, stride = p4, 16
+        rc = self.lib.lporacle_set_cloud(self.h, pts.ctypes.data_as(_P), pts.shape[0], stride)
+        assert rc == 0
+
+    def set_plan(self, plan: np.ndarray):
+        plan = np.ascontiguousarray(plan, dtype=np.float64).reshape(-1, 7)
+        rc = self.lib.lporacle_set_plan(self.h, plan.ctypes.data_as(C.POINTER(C.c_double)), plan.shape[0])
+        assert rc == 0
+
+    def set_sample_stride(self, stride: int, phase: int = 0):
+        assert self.lib.lporacle_set_sample_stride(self.h, stride, phase) == 0
+
+    def plan(self, q: abi.Query, n_threads: int = 1) -> abi.Result:
+        r = abi.Result()
+        t = [C.c_double(), C.c_double(), C.c_double()]
+        rc = self.lib.lporacle_plan(self.h, C.byref(q), n_threads, C.byref(r), C.byref(t[0]), C.byref(t[1]),
+                                    C.byref(t[2]))
+        assert rc == 0
+        self.last = r
+        self.timing = tuple(x.value for x in t)
+        return r
+
+    def samples(self, q: abi.Query) -> np.ndarray:
+        n = self.lib.lporacle_samples(self.h, C.byref(q), None, 0)
+        out = np.zeros((max(n, 1), 3), np.float32)
+        self.lib.lporacle_samples(self.h, C.byref(q), out.ctypes.data_as(C.POINTER(C.c_float)), n)
+        return out[:n]
+
+    def read_trajectories(self) -> dict:
+        n = self.last.n_traj
+        nc = max(1, self.n_critics)
+        d = {
+            "sample_index": np.zeros(n, np.int32), "vel": np.zeros((n, 3), np.float32),
+            "num_steps": np.zeros(n, np.int32), "time_delta": np.zeros(n, np.float64),
+            "cost": np.zeros(n, np.float64), "critic_scores": np.zeros((n, nc), np.float64),
+            "first_hit_pose": np.zeros(n, np.int32),
+        }
+        v = abi.TrajView(*[d[k].ctypes.data_as(t) for k, t in abi.TrajView._fields_])
+        assert self.lib.lporacle_read_trajectories(self.h, C.byref(v)) == 0
+        d["critic_scores"] = d["critic_scores"][:, :self.n_critics]
+        return d
+
+    def read_poses(self, traj_id: int, num_steps: int) -> dict:
+        n = num_steps
+        d = {
+            "pose": np.zeros((n, 7), np.float64), "pcl_pose": np.zeros((n, 3), np.float32),
+            "cuboid": np.zeros((n, 8, 3), np.float32), "aabb": np.zeros((n, 6), np.float32),
+            "collide": np.zeros(n, np.uint8), "n_r1": np.zeros(n, np.int32),
+        }
+        v = abi.PoseView(*[d[k].ctypes.data_as(t) for k, t in abi.PoseView._fields_])
+        assert self.lib.lporacle_read_poses(self.h, traj_id, C.byref(v)) == 0
+        return d
+
+    def count_radius(self):
+        s, n = C.c_int64(), C.c_int64()
+        assert self.lib.lporacle_count_radius(self.h, C.byref(s), C.byref(n)) == 0
+        return s.value, n.value
