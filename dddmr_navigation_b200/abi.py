@@ -107,6 +107,7 @@ SYMBOLS = {
     "b200lp_plan_shard": (C.c_int, [_P, C.POINTER(Query), C.c_int, C.c_int, C.POINTER(Result)]),
     "b200lp_plan_batch": (C.c_int, [_P, C.POINTER(Query), C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_int64),
                                     C.POINTER(Result)]),
+    "b200lp_traj_count": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "b200lp_read_trajectories": (C.c_int, [_P, C.c_size_t, C.POINTER(TrajView)]),
     "b200lp_read_poses": (C.c_int, [_P, C.c_size_t, C.c_int32, C.POINTER(PoseView)]),
     "b200lp_count_radius": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

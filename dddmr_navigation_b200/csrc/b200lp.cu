@@ -1,0 +1,625 @@
+// b200lp.cu — C ABI (include/b200lp.h) over the sm_100a kernels in lp_kernels.cuh.
+//
+// Build (see __graft_entry__.build):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+// -fmad=false is part of the numeric contract (lp_device.cuh). There is no CPU path in this file.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/b200lp.h"
+#include "lp_kernels.cuh"
+
+using namespace lp;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = std::max(n, (size_t)16);
+    cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+template <class T>
+struct PinBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = std::max(n, (size_t)16);
+    cudaError_t e = cudaMallocHost((void**)&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+}  // namespace
+
+struct b200lp_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  std::string err;
+  Consts C{};
+  b200lp_grid_config gcfg{};
+  int64_t launches = 0;
+
+  // cloud / grid
+  GridDev grid{};
+  size_t raw_stride = 0;
+  DevBuf<char> d_raw;
+  DevBuf<float4> d_pts;
+  DevBuf<uint32_t> d_cell_start, d_fill, d_keys, d_block_sums;
+  DevBuf<BoundsDev> d_bounds;
+  DevBuf<uint32_t> d_total;
+  PinBuf<BoundsDev> h_bounds;
+  bool have_cloud = false;
+  float cell_xy_used = 0.f, cell_z_used = 0.f;
+
+  // plan (single-robot path) — host copy, uploaded with every query
+  std::vector<double> plan_host;
+
+  // per-cycle state
+  size_t n_robots = 0;
+  int t_cap = 0;
+  int shard_rank = 0, shard_count = 1;
+  DevBuf<RobotIn> d_robots;
+  DevBuf<RobotMeta> d_meta;
+  DevBuf<double> d_plan7;
+  DevBuf<float4> d_plan_pts;
+  DevBuf<float4> d_rec_vel;
+  DevBuf<int> d_rec_steps, d_rec_sample, d_first_hit;
+  DevBuf<double> d_rec_dt, d_cost, d_scores;
+  DevBuf<BlockBest> d_partial;
+  DevBuf<unsigned> d_block_counter;
+  DevBuf<b200lp_result> d_results;
+  DevBuf<unsigned long long> d_count;
+  PinBuf<RobotIn> h_robots;
+  PinBuf<double> h_plan7;
+  PinBuf<b200lp_result> h_results;
+  PinBuf<RobotMeta> h_meta;
+  PinBuf<unsigned long long> h_count;
+  std::vector<RobotMeta> meta_host;
+  bool have_cycle = false;
+
+  // timing of the last call
+  float ms_upload = 0.f, ms_grid = 0.f, ms_plan = 0.f, ms_readback = 0.f;
+
+  int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    err = buf;
+    return code;
+  }
+};
+
+#define CK(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e__ = (call);                                                                          \
+    if (e__ != cudaSuccess) return ctx->fail(B200LP_E_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+namespace {
+
+int grid_blocks(size_t n, int threads, int sm_count) {
+  const size_t want = (n + threads - 1) / threads;
+  return (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)sm_count * 16));
+}
+
+int sm_count_of(int device) {
+  int n = 148;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
+  return n;
+}
+
+// largest num_steps a parameter set can produce (see traj_precheck)
+double max_steps_bound(const b200lp_limits& L, const b200lp_params& P) {
+  const double eps = 1e-4;
+  if (P.theory == B200LP_THEORY_DD_ROTATE_INPLACE) return std::ceil(6.28 / P.angular_sim_granularity) + 1;
+  double vmax;
+  if (P.theory == B200LP_THEORY_DD_SIMPLE) vmax = L.max_vel_x;
+  else vmax = L.max_vel_trans;
+  if (vmax < 0) return INFINITY;  // the reference disables the speed check; unbounded
+  const double a = (vmax + eps) * P.sim_time / P.sim_granularity;
+  const double b = (L.max_vel_theta + eps) * P.sim_time / P.angular_sim_granularity;
+  return std::ceil(std::max(a, b)) + 1;
+}
+
+int axis_count(double sample) { return std::max(2, (int)sample) + 1; }
+
+int traj_cap(const b200lp_params& P) {
+  if (!(P.linear_x_sample * P.angular_z_sample > 0)) return 1;
+  if (P.theory == B200LP_THEORY_DD_ROTATE_INPLACE) return 2;
+  long long n = (long long)axis_count(P.linear_x_sample) * axis_count(P.angular_z_sample);
+  if (P.theory == B200LP_THEORY_OMNI_SIMPLE) n *= axis_count(P.linear_y_sample);
+  return (int)std::min<long long>(n, 1ll << 30);
+}
+
+int build_grid(b200lp_ctx* ctx, size_t n, size_t stride) {
+  const int sms = sm_count_of(ctx->device);
+  GridDev& g = ctx->grid;
+  g.n_raw = (uint32_t)n;
+  g.n_kept = 0;
+  g.nx = g.ny = g.nz = 1;
+  g.org[0] = g.org[1] = g.org[2] = 0.f;
+  g.inv_xy = g.inv_z = 1.f;
+  g.cmax = 1.f;
+  float cxy = ctx->gcfg.cell_xy > 0.f ? ctx->gcfg.cell_xy : 0.25f;
+  float cz = ctx->gcfg.cell_z > 0.f ? ctx->gcfg.cell_z : 0.25f;
+  const uint32_t max_cells = ctx->gcfg.max_cells ? ctx->gcfg.max_cells : (1u << 26);
+
+  CK(ctx->d_bounds.reserve(1));
+  CK(ctx->h_bounds.reserve(1));
+  CK(ctx->d_total.reserve(1));
+  BoundsDev init;
+  for (int a = 0; a < 3; ++a) {
+    init.mn[a] = 0xffffffffu;
+    init.mx[a] = 0u;
+  }
+  init.n_finite = 0;
+  init.pad = 0;
+  *ctx->h_bounds.p = init;
+  CK(cudaMemcpyAsync(ctx->d_bounds.p, ctx->h_bounds.p, sizeof(BoundsDev), cudaMemcpyHostToDevice, ctx->stream));
+  if (n) {
+    bounds_kernel<<<grid_blocks(n, 256, sms), 256, 0, ctx->stream>>>(ctx->d_raw.p, n, stride, ctx->d_bounds.p);
+    ++ctx->launches;
+  }
+  CK(cudaMemcpyAsync(ctx->h_bounds.p, ctx->d_bounds.p, sizeof(BoundsDev), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const BoundsDev b = *ctx->h_bounds.p;
+  size_t n_cells = 1;
+  if (b.n_finite) {
+    float mn[3], mx[3];
+    for (int a = 0; a < 3; ++a) {
+      mn[a] = ord2f(b.mn[a]);
+      mx[a] = ord2f(b.mx[a]);
+    }
+    for (;;) {
+      const double nx = std::floor(((double)mx[0] - mn[0]) / cxy) + 1, ny = std::floor(((double)mx[1] - mn[1]) / cxy) + 1,
+                   nz = std::floor(((double)mx[2] - mn[2]) / cz) + 1;
+      if (nx * ny * nz <= (double)max_cells && nx < 2e9 && ny < 2e9 && nz < 2e9) {
+        g.nx = (int)nx;
+        g.ny = (int)ny;
+        g.nz = (int)nz;
+        break;
+      }
+      cxy *= 1.25f;
+      cz *= 1.25f;
+    }
+    g.org[0] = mn[0];
+    g.org[1] = mn[1];
+    g.org[2] = mn[2];
+    g.inv_xy = 1.0f / cxy;
+    g.inv_z = 1.0f / cz;
+    float cm = 1.f;
+    for (int a = 0; a < 3; ++a) cm = std::max(cm, std::max(std::fabs(mn[a]), std::fabs(mx[a])));
+    g.cmax = cm;
+    g.n_kept = b.n_finite;
+    n_cells = (size_t)g.nx * g.ny * g.nz;
+  }
+  ctx->cell_xy_used = cxy;
+  ctx->cell_z_used = cz;
+  const int nb = (int)((n_cells + kScanItems - 1) / kScanItems);
+  CK(ctx->d_cell_start.reserve(n_cells + 1));
+  CK(ctx->d_fill.reserve(n_cells + 1));
+  CK(ctx->d_block_sums.reserve(nb));
+  CK(ctx->d_keys.reserve(n));
+  CK(ctx->d_pts.reserve(std::max<size_t>(g.n_kept, 1)));
+  CK(cudaMemsetAsync(ctx->d_cell_start.p, 0, (n_cells + 1) * sizeof(uint32_t), ctx->stream));
+  g.pts = ctx->d_pts.p;
+  g.cell_start = ctx->d_cell_start.p;
+  if (g.n_kept) {
+    hist_kernel<<<grid_blocks(n, 256, sms), 256, 0, ctx->stream>>>(ctx->d_raw.p, n, stride, g, ctx->d_cell_start.p,
+                                                                   ctx->d_keys.p);
+    scan_block_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_cell_start.p, n_cells, ctx->d_block_sums.p);
+    scan_sums_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_block_sums.p, nb, ctx->d_total.p);
+    scan_add_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_cell_start.p, n_cells, ctx->d_block_sums.p, ctx->d_total.p);
+    CK(cudaMemcpyAsync(ctx->d_fill.p, ctx->d_cell_start.p, n_cells * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
+                       ctx->stream));
+    scatter_kernel<<<grid_blocks(n, 256, sms), 256, 0, ctx->stream>>>(ctx->d_raw.p, n, stride, ctx->d_keys.p,
+                                                                      ctx->d_fill.p, ctx->d_pts.p);
+    ctx->launches += 5;
+  }
+  CK(cudaGetLastError());
+  ctx->have_cloud = true;
+  return B200LP_OK;
+}
+
+int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_result* outs) {
+  // inputs are already staged in h_robots / h_plan7 (pinned); total plan poses in plan_total
+  const int t_cap = traj_cap(ctx->C.par);
+  const size_t T = n_robots * (size_t)t_cap;
+  size_t plan_total = 0;
+  for (size_t i = 0; i < n_robots; ++i) plan_total = std::max<size_t>(plan_total, ctx->h_robots.p[i].plan_off + ctx->h_robots.p[i].plan_n);
+  const int nc = std::max(1, ctx->C.n_critics);
+  const int gx = (t_cap + kWarpsPerCta - 1) / kWarpsPerCta;
+  CK(ctx->d_robots.reserve(n_robots));
+  CK(ctx->d_meta.reserve(n_robots));
+  CK(ctx->d_plan7.reserve(std::max<size_t>(plan_total * 7, 7)));
+  CK(ctx->d_plan_pts.reserve(std::max<size_t>(plan_total, 1)));
+  CK(ctx->d_rec_vel.reserve(T));
+  CK(ctx->d_rec_steps.reserve(T));
+  CK(ctx->d_rec_sample.reserve(T));
+  CK(ctx->d_first_hit.reserve(T));
+  CK(ctx->d_rec_dt.reserve(T));
+  CK(ctx->d_cost.reserve(T));
+  CK(ctx->d_scores.reserve(T * nc));
+  CK(ctx->d_partial.reserve(n_robots * gx));
+  CK(ctx->d_results.reserve(n_robots));
+  CK(ctx->h_results.reserve(n_robots));
+  CK(ctx->h_meta.reserve(n_robots));
+  if (ctx->d_block_counter.cap < n_robots) {
+    CK(ctx->d_block_counter.reserve(n_robots));
+    CK(cudaMemsetAsync(ctx->d_block_counter.p, 0, ctx->d_block_counter.cap * sizeof(unsigned), ctx->stream));
+  }
+  if (!ctx->have_cloud) {  // no cloud yet: an empty one (collision critics return 0.0, size() < 5)
+    int rc = build_grid(ctx, 0, 16);
+    if (rc) return rc;
+  }
+  ctx->n_robots = n_robots;
+  ctx->t_cap = t_cap;
+  ctx->shard_rank = rank;
+  ctx->shard_count = count;
+
+  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_robots.p, ctx->h_robots.p, n_robots * sizeof(RobotIn), cudaMemcpyHostToDevice, ctx->stream));
+  if (plan_total)
+    CK(cudaMemcpyAsync(ctx->d_plan7.p, ctx->h_plan7.p, plan_total * 7 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  prep_kernel<<<(unsigned)n_robots, 1024, 0, ctx->stream>>>(ctx->C, ctx->d_robots.p, t_cap, rank, count, ctx->d_rec_vel.p,
+                                                            ctx->d_rec_steps.p, ctx->d_rec_dt.p, ctx->d_rec_sample.p,
+                                                            ctx->d_meta.p, ctx->d_plan7.p, ctx->d_plan_pts.p);
+  plan_kernel<<<dim3(gx, (unsigned)n_robots), kThreads, 0, ctx->stream>>>(
+      ctx->C, ctx->grid, ctx->d_robots.p, ctx->d_meta.p, t_cap, ctx->d_rec_vel.p, ctx->d_rec_steps.p, ctx->d_rec_dt.p,
+      ctx->d_plan_pts.p, ctx->d_plan7.p, ctx->d_cost.p, ctx->d_scores.p, ctx->d_first_hit.p, ctx->d_partial.p,
+      ctx->d_block_counter.p, ctx->d_results.p);
+  ctx->launches += 2;
+  CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_results.p, ctx->d_results.p, n_robots * sizeof(b200lp_result), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_meta.p, ctx->d_meta.p, n_robots * sizeof(RobotMeta), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  ctx->meta_host.assign(ctx->h_meta.p, ctx->h_meta.p + n_robots);
+  for (size_t i = 0; i < n_robots; ++i) {
+    if (ctx->meta_host[i].error)
+      return ctx->fail(B200LP_E_INVALID, "robot %zu: a trajectory exceeds B200LP_MAX_STEPS=%d poses or the trajectory list overflowed",
+                       i, B200LP_MAX_STEPS);
+    outs[i] = ctx->h_results.p[i];
+  }
+  ctx->have_cycle = true;
+  cudaEventElapsedTime(&ctx->ms_upload, ctx->ev[0], ctx->ev[1]);
+  cudaEventElapsedTime(&ctx->ms_plan, ctx->ev[1], ctx->ev[2]);
+  cudaEventElapsedTime(&ctx->ms_readback, ctx->ev[2], ctx->ev[3]);
+  return B200LP_OK;
+}
+
+void fill_robot(RobotIn* r, const b200lp_query* q, int64_t plan_off, int32_t plan_n) {
+  memcpy(r->pose, q->pose, sizeof(r->pose));
+  memcpy(r->twist, q->twist, sizeof(r->twist));
+  r->max_speed_override = q->max_speed_override;
+  r->heading_deviation = q->heading_deviation;
+  r->plan_off = plan_off;
+  r->plan_n = plan_n;
+  r->pad = 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200lp_abi_version(void) { return B200LP_ABI_VERSION; }
+
+const char* b200lp_last_error(const b200lp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int b200lp_create(b200lp_ctx** out, int device, const b200lp_limits* limits, const b200lp_params* params,
+                  const float* cuboid_xyz, const b200lp_critic* critics, int n_critics, const b200lp_grid_config* grid) {
+  auto bad = [&](const char* msg) {
+    g_create_error = msg;
+    return B200LP_E_INVALID;
+  };
+  if (!out || !limits || !params || !cuboid_xyz) return bad("null argument");
+  if (n_critics < 0 || n_critics > B200LP_MAX_CRITICS || (n_critics && !critics)) return bad("bad critic list");
+  if (params->theory < 0 || params->theory > B200LP_THEORY_DD_ROTATE_INPLACE) return bad("unknown theory");
+  for (int k = 0; k < n_critics; ++k)
+    if (critics[k].kind < 0 || critics[k].kind > B200LP_CRITIC_TWIRLING) return bad("unknown critic kind");
+  if (!(params->controller_frequency > 0) || !(params->sim_time > 0) || !(params->sim_granularity > 0) ||
+      !(params->angular_sim_granularity > 0))
+    return bad("controller_frequency, sim_time and the granularities must be positive");
+  if (params->theory == B200LP_THEORY_DD_ROTATE_INPLACE && !(std::fabs(limits->rotation_speed) > 0))
+    return bad("rotation_speed must be non-zero");
+  if (!(max_steps_bound(*limits, *params) <= (double)B200LP_MAX_STEPS))
+    return bad("parameter set can produce more than B200LP_MAX_STEPS poses per trajectory");
+  if (!(limits->max_vel_theta * params->sim_time < 100.0)) return bad("max_vel_theta*sim_time must stay below 100 rad");
+  if ((int)params->linear_x_sample > kMaxAxis - 2 || (int)params->angular_z_sample > kMaxAxis - 2 ||
+      (params->theory == B200LP_THEORY_OMNI_SIMPLE && (int)params->linear_y_sample > kMaxAxis - 2))
+    return bad("too many samples per velocity axis");
+  if ((long long)axis_count(params->linear_x_sample) * axis_count(params->angular_z_sample) *
+          (params->theory == B200LP_THEORY_OMNI_SIMPLE ? axis_count(params->linear_y_sample) : 1) > (1ll << 24))
+    return bad("more than 2^24 velocity samples");
+
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no usable CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)";
+    return B200LP_E_CUDA;
+  }
+  if (device < 0 || device >= ndev) return bad("device index out of range");
+  b200lp_ctx* ctx = new (std::nothrow) b200lp_ctx();
+  if (!ctx) return B200LP_E_NOMEM;
+  ctx->device = device;
+  auto cuda_fail = [&](cudaError_t err, const char* what) {
+    g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
+    delete ctx;
+    return B200LP_E_CUDA;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+  for (auto& ev : ctx->ev)
+    if ((e = cudaEventCreate(&ev)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+  ctx->C.lim = *limits;
+  ctx->C.par = *params;
+  memcpy(ctx->C.cuboid, cuboid_xyz, sizeof(ctx->C.cuboid));
+  ctx->C.n_critics = n_critics;
+  for (int k = 0; k < n_critics; ++k) {
+    ctx->C.critics[k].kind = critics[k].kind;
+    ctx->C.critics[k].pad = 0;
+    ctx->C.critics[k].weight = critics[k].weight;
+    ctx->C.critics[k].tw = critics[k].translation_weight;
+    ctx->C.critics[k].ow = critics[k].orientation_weight;
+  }
+  if (grid) ctx->gcfg = *grid;
+  *out = ctx;
+  return B200LP_OK;
+}
+
+void b200lp_destroy(b200lp_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  ctx->d_raw.release(); ctx->d_pts.release(); ctx->d_cell_start.release(); ctx->d_fill.release();
+  ctx->d_keys.release(); ctx->d_block_sums.release(); ctx->d_bounds.release(); ctx->d_total.release();
+  ctx->h_bounds.release(); ctx->d_robots.release(); ctx->d_meta.release(); ctx->d_plan7.release();
+  ctx->d_plan_pts.release(); ctx->d_rec_vel.release(); ctx->d_rec_steps.release(); ctx->d_rec_sample.release();
+  ctx->d_first_hit.release(); ctx->d_rec_dt.release(); ctx->d_cost.release(); ctx->d_scores.release();
+  ctx->d_partial.release(); ctx->d_block_counter.release(); ctx->d_results.release(); ctx->d_count.release();
+  ctx->h_robots.release(); ctx->h_plan7.release(); ctx->h_results.release(); ctx->h_meta.release();
+  ctx->h_count.release();
+  for (auto& ev : ctx->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+static int set_cloud_common(b200lp_ctx* ctx, const void* pts, size_t n, size_t stride, bool on_device) {
+  if (!ctx) return B200LP_E_INVALID;
+  if ((n && !pts) || stride < 12 || (stride & 3)) return ctx->fail(B200LP_E_INVALID, "set_cloud: bad pointer or stride");
+  if (n > 0xfffffff0ull) return ctx->fail(B200LP_E_INVALID, "set_cloud: more than 2^32 points");
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->d_raw.reserve(std::max<size_t>(n * stride, 16)));
+  ctx->raw_stride = stride;
+  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  if (n) CK(cudaMemcpyAsync(ctx->d_raw.p, pts, n * stride, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  int rc = build_grid(ctx, n, stride);
+  if (rc) return rc;
+  CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaEventElapsedTime(&ctx->ms_upload, ctx->ev[0], ctx->ev[1]);
+  cudaEventElapsedTime(&ctx->ms_grid, ctx->ev[1], ctx->ev[2]);
+  ctx->ms_plan = ctx->ms_readback = 0.f;
+  ctx->have_cycle = false;
+  return B200LP_OK;
+}
+
+int b200lp_set_cloud(b200lp_ctx* ctx, const void* pts, size_t n, size_t stride_bytes) {
+  return set_cloud_common(ctx, pts, n, stride_bytes, false);
+}
+int b200lp_set_cloud_device(b200lp_ctx* ctx, const void* dev_pts, size_t n, size_t stride_bytes) {
+  return set_cloud_common(ctx, dev_pts, n, stride_bytes, true);
+}
+
+int b200lp_set_plan(b200lp_ctx* ctx, const double* p, size_t n) {
+  if (!ctx) return B200LP_E_INVALID;
+  if (n && !p) return ctx->fail(B200LP_E_INVALID, "set_plan: null plan");
+  if (n > B200LP_MAX_PLAN) return ctx->fail(B200LP_E_INVALID, "set_plan: more than B200LP_MAX_PLAN poses");
+  ctx->plan_host.assign(p, p + n * 7);
+  return B200LP_OK;
+}
+
+int b200lp_plan_shard(b200lp_ctx* ctx, const b200lp_query* q, int rank, int count, b200lp_result* out) {
+  if (!ctx) return B200LP_E_INVALID;
+  if (!q || !out || count < 1 || rank < 0 || rank >= count) return ctx->fail(B200LP_E_INVALID, "plan: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  const size_t np = ctx->plan_host.size() / 7;
+  CK(ctx->h_robots.reserve(1));
+  CK(ctx->h_plan7.reserve(std::max<size_t>(np * 7, 7)));
+  fill_robot(ctx->h_robots.p, q, 0, (int32_t)np);
+  if (np) memcpy(ctx->h_plan7.p, ctx->plan_host.data(), np * 7 * sizeof(double));
+  return run_cycle(ctx, 1, rank, count, out);
+}
+
+int b200lp_plan(b200lp_ctx* ctx, const b200lp_query* q, b200lp_result* out) { return b200lp_plan_shard(ctx, q, 0, 1, out); }
+
+int b200lp_plan_batch(b200lp_ctx* ctx, const b200lp_query* qs, size_t n_robots, const double* plans,
+                      const int64_t* plan_offsets, b200lp_result* outs) {
+  if (!ctx) return B200LP_E_INVALID;
+  if (!qs || !outs || !n_robots || !plan_offsets) return ctx->fail(B200LP_E_INVALID, "plan_batch: bad argument");
+  if (n_robots > 65535) return ctx->fail(B200LP_E_INVALID, "plan_batch: more than 65535 robots per call");
+  CK(cudaSetDevice(ctx->device));
+  const int64_t total = plan_offsets[n_robots];
+  if (total < 0 || (total && !plans)) return ctx->fail(B200LP_E_INVALID, "plan_batch: bad plan table");
+  CK(ctx->h_robots.reserve(n_robots));
+  CK(ctx->h_plan7.reserve(std::max<size_t>((size_t)total * 7, 7)));
+  for (size_t i = 0; i < n_robots; ++i) {
+    const int64_t a = plan_offsets[i], b = plan_offsets[i + 1];
+    if (a < 0 || b < a || b > total || b - a > B200LP_MAX_PLAN) return ctx->fail(B200LP_E_INVALID, "plan_batch: bad plan offsets for robot %zu", i);
+    fill_robot(ctx->h_robots.p + i, qs + i, a, (int32_t)(b - a));
+  }
+  if (total) memcpy(ctx->h_plan7.p, plans, (size_t)total * 7 * sizeof(double));
+  return run_cycle(ctx, n_robots, 0, 1, outs);
+}
+
+int b200lp_traj_count(const b200lp_ctx* ctx, size_t robot, int32_t* n_traj_global, int32_t* t_begin, int32_t* t_end) {
+  if (!ctx || !ctx->have_cycle || robot >= ctx->n_robots) return B200LP_E_STATE;
+  const RobotMeta& m = ctx->meta_host[robot];
+  if (n_traj_global) *n_traj_global = m.n_traj;
+  if (t_begin) *t_begin = m.t_begin;
+  if (t_end) *t_end = m.t_end;
+  return B200LP_OK;
+}
+
+int b200lp_read_trajectories(b200lp_ctx* ctx, size_t robot, const b200lp_traj_view* v) {
+  if (!ctx) return B200LP_E_INVALID;
+  if (!v) return ctx->fail(B200LP_E_INVALID, "read_trajectories: null view");
+  if (!ctx->have_cycle || robot >= ctx->n_robots) return ctx->fail(B200LP_E_STATE, "read_trajectories: no plan result for that robot");
+  CK(cudaSetDevice(ctx->device));
+  const RobotMeta& m = ctx->meta_host[robot];
+  const size_t n = (size_t)m.n_traj, off = robot * (size_t)ctx->t_cap;
+  const int nc = ctx->C.n_critics;
+  if (!n) return B200LP_OK;
+  std::vector<float4> vel;
+  if (v->vel) {
+    vel.resize(n);
+    CK(cudaMemcpyAsync(vel.data(), ctx->d_rec_vel.p + off, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (v->sample_index) CK(cudaMemcpyAsync(v->sample_index, ctx->d_rec_sample.p + off, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (v->num_steps) CK(cudaMemcpyAsync(v->num_steps, ctx->d_rec_steps.p + off, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (v->time_delta) CK(cudaMemcpyAsync(v->time_delta, ctx->d_rec_dt.p + off, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (v->cost) CK(cudaMemcpyAsync(v->cost, ctx->d_cost.p + off, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (v->first_hit_pose) CK(cudaMemcpyAsync(v->first_hit_pose, ctx->d_first_hit.p + off, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (v->critic_scores && nc) CK(cudaMemcpyAsync(v->critic_scores, ctx->d_scores.p + off * nc, n * nc * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (v->vel)
+    for (size_t i = 0; i < n; ++i) {
+      v->vel[i * 3] = vel[i].x;
+      v->vel[i * 3 + 1] = vel[i].y;
+      v->vel[i * 3 + 2] = vel[i].z;
+    }
+  // trajectories outside a sample shard were not scored in this launch: mark them
+  if (m.t_begin > 0 || m.t_end < m.n_traj) {
+    const double nan = std::nan("");
+    for (size_t i = 0; i < n; ++i) {
+      if ((int)i >= m.t_begin && (int)i < m.t_end) continue;
+      if (v->cost) v->cost[i] = nan;
+      if (v->first_hit_pose) v->first_hit_pose[i] = -1;
+      if (v->critic_scores)
+        for (int k = 0; k < nc; ++k) v->critic_scores[i * nc + k] = nan;
+    }
+  }
+  return B200LP_OK;
+}
+
+int b200lp_read_poses(b200lp_ctx* ctx, size_t robot, int32_t id, const b200lp_pose_view* v) {
+  if (!ctx) return B200LP_E_INVALID;
+  if (!v) return ctx->fail(B200LP_E_INVALID, "read_poses: null view");
+  if (!ctx->have_cycle || robot >= ctx->n_robots) return ctx->fail(B200LP_E_STATE, "read_poses: no plan result for that robot");
+  const RobotMeta& m = ctx->meta_host[robot];
+  if (id < 0 || id >= m.n_traj) return ctx->fail(B200LP_E_INVALID, "read_poses: trajectory id out of range");
+  CK(cudaSetDevice(ctx->device));
+  int n = 0;
+  CK(cudaMemcpyAsync(&n, ctx->d_rec_steps.p + robot * (size_t)ctx->t_cap + id, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  // scratch layout in one allocation
+  const size_t b_pose = 0, b_pcl = b_pose + (size_t)n * 56, b_cub = b_pcl + (size_t)n * 12, b_aabb = b_cub + (size_t)n * 96,
+               b_nr1 = b_aabb + (size_t)n * 24, b_col = b_nr1 + (size_t)n * 4, total = b_col + (size_t)n;
+  char* d = nullptr;
+  CK(cudaMalloc((void**)&d, std::max<size_t>(total, 16)));
+  poses_kernel<<<1, 32, 0, ctx->stream>>>(ctx->C, ctx->grid, ctx->d_robots.p, (int)robot, ctx->t_cap, id, ctx->d_rec_vel.p,
+                                          ctx->d_rec_steps.p, ctx->d_rec_dt.p, (double*)(d + b_pose), (float*)(d + b_pcl),
+                                          (float*)(d + b_cub), (float*)(d + b_aabb), (unsigned char*)(d + b_col),
+                                          (int*)(d + b_nr1));
+  ++ctx->launches;
+  std::vector<char> h(std::max<size_t>(total, 16));
+  cudaError_t e = cudaMemcpyAsync(h.data(), d, total, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return ctx->fail(B200LP_E_CUDA, "read_poses: %s", cudaGetErrorString(e));
+  if (v->pose) memcpy(v->pose, h.data() + b_pose, (size_t)n * 56);
+  if (v->pcl_pose) memcpy(v->pcl_pose, h.data() + b_pcl, (size_t)n * 12);
+  if (v->cuboid) memcpy(v->cuboid, h.data() + b_cub, (size_t)n * 96);
+  if (v->aabb) memcpy(v->aabb, h.data() + b_aabb, (size_t)n * 24);
+  if (v->n_r1) memcpy(v->n_r1, h.data() + b_nr1, (size_t)n * 4);
+  if (v->collide) memcpy(v->collide, h.data() + b_col, (size_t)n);
+  return B200LP_OK;
+}
+
+int b200lp_count_radius(b200lp_ctx* ctx, int64_t* sum_n_r1, int64_t* n_poses) {
+  if (!ctx) return B200LP_E_INVALID;
+  if (!ctx->have_cycle) return ctx->fail(B200LP_E_STATE, "count_radius: no plan result");
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->d_count.reserve(2));
+  CK(ctx->h_count.reserve(2));
+  CK(cudaMemsetAsync(ctx->d_count.p, 0, 16, ctx->stream));
+  const int gx = (ctx->t_cap + kWarpsPerCta - 1) / kWarpsPerCta;
+  count_radius_kernel<<<dim3(gx, (unsigned)ctx->n_robots), kThreads, 0, ctx->stream>>>(
+      ctx->C, ctx->grid, ctx->d_robots.p, ctx->d_meta.p, ctx->t_cap, ctx->d_rec_vel.p, ctx->d_rec_steps.p, ctx->d_rec_dt.p,
+      ctx->d_count.p);
+  ++ctx->launches;
+  CK(cudaMemcpyAsync(ctx->h_count.p, ctx->d_count.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  if (sum_n_r1) *sum_n_r1 = (int64_t)ctx->h_count.p[0];
+  if (n_poses) *n_poses = (int64_t)ctx->h_count.p[1];
+  return B200LP_OK;
+}
+
+int b200lp_last_timing(const b200lp_ctx* ctx, float* ms_upload, float* ms_grid_build, float* ms_plan_kernels,
+                       float* ms_readback) {
+  if (!ctx) return B200LP_E_INVALID;
+  if (ms_upload) *ms_upload = ctx->ms_upload;
+  if (ms_grid_build) *ms_grid_build = ctx->ms_grid;
+  if (ms_plan_kernels) *ms_plan_kernels = ctx->ms_plan;
+  if (ms_readback) *ms_readback = ctx->ms_readback;
+  return B200LP_OK;
+}
+
+int64_t b200lp_launch_count(const b200lp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int b200lp_grid_info(const b200lp_ctx* ctx, int32_t dims[3], float origin[3], float cell[2], int64_t* n_points_kept) {
+  if (!ctx || !ctx->have_cloud) return B200LP_E_STATE;
+  if (dims) { dims[0] = ctx->grid.nx; dims[1] = ctx->grid.ny; dims[2] = ctx->grid.nz; }
+  if (origin) { origin[0] = ctx->grid.org[0]; origin[1] = ctx->grid.org[1]; origin[2] = ctx->grid.org[2]; }
+  if (cell) { cell[0] = ctx->cell_xy_used; cell[1] = ctx->cell_z_used; }
+  if (n_points_kept) *n_points_kept = ctx->grid.n_kept;
+  return B200LP_OK;
+}
+
+void* b200lp_stream(const b200lp_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+}  // extern "C"

@@ -1,0 +1,513 @@
+// lp_device.cuh — device-side building blocks of the rollout-and-score path (sm_100a).
+//
+// Arithmetic contract: this translation unit is compiled with -fmad=false; every float/double
+// expression below evaluates exactly like the CPU oracle's (oracle/lp_oracle.cpp), which restates the
+// reference. The ONLY fused multiply-adds are the explicit __fmaf_rn calls of the conservative
+// pre-test in sweep_points(), whose outcome is re-decided by the exact test before it can matter.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b200lp.h"
+#include "lp_math.h"
+
+namespace lp {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kThreads = kWarpsPerCta * 32;
+constexpr int kGroup = 4;       // consecutive poses swept against one candidate stream
+constexpr int kMaxAxis = 2048;  // cap on samples per velocity axis (incl. the inserted zero)
+constexpr int kPlanSmem = 256;  // prune-plan points staged in shared memory
+constexpr unsigned kFull = 0xffffffffu;
+
+// per-warp pose stash (structure of arrays: [field][lane])
+enum Field {
+  F_CX = 0, F_CY, F_CZ,                     // cuboid centre (collision_model.cpp:86-95)
+  F_AXX, F_AXY, F_AXZ,                      // unit x axis
+  F_AYX, F_AYY, F_AYZ,                      // unit y axis
+  F_AZX, F_AZY, F_AZZ,                      // unit z axis
+  F_HX, F_HY, F_HZ,                         // half extents (exactly representable in float)
+  F_PX, F_PY, F_PZ,                         // Trajectory::getPCLPoint
+  F_MNX, F_MNY, F_MNZ, F_MXX, F_MXY, F_MXZ, // Trajectory::getCuboidMinMax
+  F_LOX, F_LOY, F_LOZ, F_HIX, F_HIY, F_HIZ, // candidate box: (AABB +- margin) ∩ (pose +- (1+margin))
+  F_COUNT
+};
+
+struct GridDev {
+  const float4* pts;           // cell-sorted points: x,y,z, w = original index bits
+  const uint32_t* cell_start;  // n_cells + 1 offsets into pts
+  float org[3];
+  float inv_xy, inv_z;
+  int nx, ny, nz;
+  uint32_t n_kept;  // finite points in pts
+  uint32_t n_raw;   // raw cloud size: the reference's `points.size() < 5` rule uses this
+  float cmax;       // max |coordinate| of the grid bounds (scales the pre-test slack)
+};
+
+struct CriticDev {
+  int kind;
+  int pad;
+  double weight, tw, ow;
+};
+
+struct Consts {
+  b200lp_limits lim;
+  b200lp_params par;
+  float cuboid[8][3];
+  int n_critics;
+  int pad;
+  CriticDev critics[B200LP_MAX_CRITICS];
+};
+
+struct RobotIn {
+  double pose[7];
+  double twist[3];
+  double max_speed_override;
+  double heading_deviation;
+  int64_t plan_off;
+  int32_t plan_n;
+  int32_t pad;
+};
+
+struct RobotMeta {
+  int32_t n_samples;  // |sample_params_|
+  int32_t n_traj;     // all valid trajectories of the robot (global id space)
+  int32_t t_begin, t_end;  // id range this launch scores (sample shard)
+  int32_t error;      // 1 = num_steps exceeded B200LP_MAX_STEPS
+  int32_t pad;
+  long long n_poses;  // sum num_steps over [t_begin, t_end)
+};
+
+struct BlockBest {
+  unsigned long long cost_bits;  // ~0 = none
+  int32_t id;
+  int32_t n_collided;
+};
+
+// ---------------------------------------------------------------------------------------------
+// double-precision pose algebra (mirrors oracle: quat_to_matrix, affine_mul, affine_inverse, matrix_to_quat)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void quat_to_matrix(double x, double y, double z, double w, double* R /*9 row-major*/) {
+  const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
+  const double twx = tx * w, twy = ty * w, twz = tz * w;
+  const double txx = tx * x, txy = ty * x, txz = tz * x;
+  const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  R[0] = 1.0 - (tyy + tzz); R[1] = txy - twz;         R[2] = txz + twy;
+  R[3] = txy + twz;         R[4] = 1.0 - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy;         R[7] = tyz + twx;         R[8] = 1.0 - (txx + tyy);
+}
+
+__device__ __forceinline__ void matrix_to_quat(const double* m, double* q /*x,y,z,w*/) {
+  double t = (m[0] + m[4]) + m[8];
+  if (t > 0.0) {
+    t = lpm::dsqrt(t + 1.0);
+    q[3] = 0.5 * t;
+    t = 0.5 / t;
+    q[0] = (m[7] - m[5]) * t;
+    q[1] = (m[2] - m[6]) * t;
+    q[2] = (m[3] - m[1]) * t;
+  } else {
+    int i = 0;
+    if (m[4] > m[0]) i = 1;
+    if (m[8] > m[i * 4]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = lpm::dsqrt(((m[i * 4] - m[j * 4]) - m[k * 4]) + 1.0);
+    double qq[4];
+    qq[i] = 0.5 * t;
+    t = 0.5 / t;
+    qq[3] = (m[k * 3 + j] - m[j * 3 + k]) * t;
+    qq[j] = (m[j * 3 + i] + m[i * 3 + j]) * t;
+    qq[k] = (m[k * 3 + i] + m[i * 3 + k]) * t;
+    q[0] = qq[0]; q[1] = qq[1]; q[2] = qq[2]; q[3] = qq[3];
+  }
+}
+
+__device__ __forceinline__ double cof3(const double* m, int i, int j) {
+  const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+  return m[i1 * 3 + j1] * m[i2 * 3 + j2] - m[i1 * 3 + j2] * m[i2 * 3 + j1];
+}
+
+// PurePursuitModel::scoreTrajectory body (pure_pursuit_model.cpp:86-113) for a trajectory end pose given
+// as affine (L,t) and the plan end pose as affine (gL,gt).
+__device__ __noinline__ double pure_pursuit_value(const double* L, const double* t, const double* gL,
+                                                  const double* gt, double tw, double ow) {
+  // PoseStamped orientation = Quaterniond(L); the critic turns it back into a matrix
+  double q[4];
+  matrix_to_quat(L, q);
+  double A[9];
+  quat_to_matrix(q[0], q[1], q[2], q[3], A);
+  // inverse (Affine mode)
+  const double c00 = cof3(A, 0, 0), c10 = cof3(A, 1, 0), c20 = cof3(A, 2, 0);
+  const double det = (c00 * A[0] + c10 * A[3]) + c20 * A[6];
+  const double invdet = 1.0 / det;
+  double I[9];
+  I[0] = c00 * invdet; I[1] = c10 * invdet; I[2] = c20 * invdet;
+  I[3] = cof3(A, 0, 1) * invdet; I[4] = cof3(A, 1, 1) * invdet; I[5] = cof3(A, 2, 1) * invdet;
+  I[6] = cof3(A, 0, 2) * invdet; I[7] = cof3(A, 1, 2) * invdet; I[8] = cof3(A, 2, 2) * invdet;
+  double it[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) it[i] = -((I[i * 3] * t[0] + I[i * 3 + 1] * t[1]) + I[i * 3 + 2] * t[2]);
+  // diff = inv * goal
+  double D[9], dt[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) D[i * 3 + j] = (I[i * 3] * gL[j] + I[i * 3 + 1] * gL[3 + j]) + I[i * 3 + 2] * gL[6 + j];
+    dt[i] = ((I[i * 3] * gt[0] + I[i * 3 + 1] * gt[1]) + I[i * 3 + 2] * gt[2]) + it[i];
+  }
+  matrix_to_quat(D, q);
+  const double d = ((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]) + q[3] * q[3];
+  const double s = 2.0 / d;
+  const double ys = q[1] * s, zs = q[2] * s;
+  const double wy = q[3] * ys, wz = q[3] * zs;
+  const double xy = q[0] * ys, xz = q[0] * zs;
+  const double yy = q[1] * ys, zz = q[2] * zs;
+  const double m00 = 1.0 - (yy + zz), m10 = xy + wz, m20 = xz - wy;
+  double yaw;
+  if (lpm::dabs(m20) >= 1.0) {
+    yaw = 0.0;
+  } else {
+    const double pitch = -lpm::asin(m20);
+    const double cp = lpm::cos(pitch);
+    yaw = lpm::atan2(m10 / cp, m00 / cp);
+  }
+  {
+    const double v = yaw + 3.1416;
+    const double r = lpm::fmod_pos(lpm::dabs(v), 3.1416);
+    yaw = v < 0.0 ? -r : r;
+  }
+  const double distance = lpm::dsqrt((dt[0] * dt[0] + dt[1] * dt[1]) + dt[2] * dt[2]);
+  return tw * distance + ow * yaw;
+}
+
+// ---------------------------------------------------------------------------------------------
+// grid helpers
+// ---------------------------------------------------------------------------------------------
+// Cell coordinate of a world coordinate. The SAME function bins points at build time and maps query
+// boxes to cell ranges; float subtraction, multiplication and floor are monotone, so a point with
+// v >= lo can never land in a cell below cell(lo).
+__device__ __forceinline__ float cell_f(float v, float org, float inv) { return floorf((v - org) * inv); }
+__device__ __forceinline__ int cell_clamped(float v, float org, float inv, int n) {
+  const float f = cell_f(v, org, inv);
+  return (int)fminf(fmaxf(f, 0.0f), (float)(n - 1));
+}
+
+// slack of the conservative pre-test and of the candidate box, both scaled by the map extent
+__device__ __forceinline__ float pretest_delta(const GridDev& g) { return 4e-6f + 1e-6f * g.cmax; }
+__device__ __forceinline__ float box_margin(const GridDev& g) { return 1e-3f + 1e-5f * g.cmax; }
+
+// ---------------------------------------------------------------------------------------------
+// rollout: one warp, 32 consecutive steps. State (x,y,th) is carried in every lane.
+// DD simple / rotate: dd_simple…cpp:457-464; omni: omni_simple…cpp:498-505.
+// On return lane k holds pose base+k (after step base+k) in (px,py,pth).
+// ---------------------------------------------------------------------------------------------
+struct Carry {
+  float x, y, th;
+};
+
+__device__ __forceinline__ void rollout32(Carry& c, int lane, int theory, float vx, float vy, float w, double dt,
+                                          float& px, float& py, float& pth) {
+  // heading chain: th' = (float)(th + w*dt); w*dt is loop invariant
+  const double wdt = (double)w * dt;
+  float th_old_mine = 0.f, th_new_mine = 0.f;
+  float th = c.th;
+#pragma unroll 8
+  for (int k = 0; k < 32; ++k) {
+    const float tn = (float)((double)th + wdt);
+    if (k == lane) {
+      th_old_mine = th;
+      th_new_mine = tn;
+    }
+    th = tn;
+  }
+  c.th = th;
+  // per-step increments, one step per lane
+  double ex, ey;
+  if (theory == B200LP_THEORY_OMNI_SIMPLE) {
+    const double a = 1.57079632679489661923 + (double)th_old_mine;  // M_PI_2 + pos[2]
+    ex = ((double)(vx * lpm::cosf(th_old_mine)) + (double)vy * lpm::cos(a)) * dt;
+    ey = ((double)(vx * lpm::sinf(th_old_mine)) + (double)vy * lpm::sin(a)) * dt;
+  } else {
+    ex = (double)(vx * lpm::cosf(th_old_mine)) * dt;
+    ey = (double)(vx * lpm::sinf(th_old_mine)) * dt;
+  }
+  // position chains
+  float x = c.x, y = c.y;
+  float xm = 0.f, ym = 0.f;
+#pragma unroll 8
+  for (int k = 0; k < 32; ++k) {
+    const double exk = __shfl_sync(kFull, ex, k);
+    const double eyk = __shfl_sync(kFull, ey, k);
+    x = (float)((double)x + exk);
+    y = (float)((double)y + eyk);
+    if (k == lane) {
+      xm = x;
+      ym = y;
+    }
+  }
+  c.x = x;
+  c.y = y;
+  px = xm;
+  py = ym;
+  pth = th_new_mine;
+}
+
+// World transform of one pose: G = pos_af3 * [Rz(th), (x,y,0)] (dd_simple…cpp:416-433).
+// Terms that multiply an exact zero of the planar transform are dropped: a + (±0) == a.
+__device__ __forceinline__ void pose_affine(const double* R0, const double* t0, float x, float y, float th,
+                                            double* L, double* t) {
+  const double ang = (double)th;
+  const double s = lpm::sin(ang), co = lpm::cos(ang);
+  const double r22 = (1.0 - co) + co;
+  const double xd = (double)x, yd = (double)y;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double a = R0[i * 3], b = R0[i * 3 + 1], cc = R0[i * 3 + 2];
+    L[i * 3 + 0] = a * co + b * s;
+    L[i * 3 + 1] = a * (-s) + b * co;
+    L[i * 3 + 2] = cc * r22;
+    t[i] = (a * xd + b * yd) + t0[i];
+  }
+}
+
+// Everything CollisionModel derives per pose from the transformed cuboid, written to the warp stash.
+__device__ __forceinline__ void pose_geometry(const Consts& C, const GridDev& g, const double* L, const double* t,
+                                              float* stash /* [F_COUNT][32] */, int lane, bool live,
+                                              float* verts_out /* optional 24 floats, may be nullptr */) {
+  float v[8][3];
+  float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
+  float mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const double x = (double)C.cuboid[k][0], y = (double)C.cuboid[k][1], z = (double)C.cuboid[k][2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      v[k][a] = (float)(((L[a * 3] * x + L[a * 3 + 1] * y) + L[a * 3 + 2] * z) + t[a]);
+      mn[a] = fminf(mn[a], v[k][a]);
+      mx[a] = fmaxf(mx[a], v[k][a]);
+    }
+  }
+  if (verts_out) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+      for (int a = 0; a < 3; ++a) verts_out[k * 3 + a] = v[k][a];
+  }
+  float c[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float s = v[0][a];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) s = s + v[k][a];
+    c[a] = s / 8.0f;
+  }
+  const int other[3] = {3, 1, 2};
+  float ax[3][3], half[3];
+#pragma unroll
+  for (int e = 0; e < 3; ++e) {
+    float d[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) d[a] = v[other[e]][a] - v[0][a];
+    const float len = lpm::fsqrt((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]);
+    half[e] = len * 0.5f;  // == sqrtf(..)/2. (exact)
+    // (float)((double)d / (2.*half)) == correctly rounded float quotient d/len (double rounding is
+    // innocuous for division when the wide format has >= 2p+2 bits)
+#pragma unroll
+    for (int a = 0; a < 3; ++a) ax[e][a] = __fdiv_rn(d[a], len);
+  }
+  const float p[3] = {(float)t[0], (float)t[1], (float)t[2]};
+  const float m = box_margin(g);
+  if (!live) {  // lanes past num_steps: an empty candidate box and an unsatisfiable half extent
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      half[a] = -1.0f;
+      mn[a] = 3.402823466e+38f;
+      mx[a] = -3.402823466e+38f;
+    }
+  }
+  stash[F_CX * 32 + lane] = c[0]; stash[F_CY * 32 + lane] = c[1]; stash[F_CZ * 32 + lane] = c[2];
+  stash[F_AXX * 32 + lane] = ax[0][0]; stash[F_AXY * 32 + lane] = ax[0][1]; stash[F_AXZ * 32 + lane] = ax[0][2];
+  stash[F_AYX * 32 + lane] = ax[1][0]; stash[F_AYY * 32 + lane] = ax[1][1]; stash[F_AYZ * 32 + lane] = ax[1][2];
+  stash[F_AZX * 32 + lane] = ax[2][0]; stash[F_AZY * 32 + lane] = ax[2][1]; stash[F_AZZ * 32 + lane] = ax[2][2];
+  stash[F_HX * 32 + lane] = half[0]; stash[F_HY * 32 + lane] = half[1]; stash[F_HZ * 32 + lane] = half[2];
+  stash[F_PX * 32 + lane] = p[0]; stash[F_PY * 32 + lane] = p[1]; stash[F_PZ * 32 + lane] = p[2];
+  stash[F_MNX * 32 + lane] = mn[0]; stash[F_MNY * 32 + lane] = mn[1]; stash[F_MNZ * 32 + lane] = mn[2];
+  stash[F_MXX * 32 + lane] = mx[0]; stash[F_MXY * 32 + lane] = mx[1]; stash[F_MXZ * 32 + lane] = mx[2];
+  // candidate box: every point that can pass BOTH exact tests lies inside it
+  const float r = 1.0f + m;
+  stash[F_LOX * 32 + lane] = fmaxf(mn[0] - m, p[0] - r); stash[F_HIX * 32 + lane] = fminf(mx[0] + m, p[0] + r);
+  stash[F_LOY * 32 + lane] = fmaxf(mn[1] - m, p[1] - r); stash[F_HIY * 32 + lane] = fminf(mx[1] + m, p[1] + r);
+  stash[F_LOZ * 32 + lane] = fmaxf(mn[2] - m, p[2] - r); stash[F_HIZ * 32 + lane] = fminf(mx[2] + m, p[2] + r);
+}
+
+// exact tests, reference arithmetic ---------------------------------------------------------------
+// FLANN L2_Simple<float>: ((dx*dx) + dy*dy) + dz*dz, strict < 1.0f
+__device__ __forceinline__ float l2_simple(float qx, float qy, float qz, float px, float py, float pz) {
+  float d = qx - px;
+  float r = d * d;
+  d = qy - py;
+  r = r + d * d;
+  d = qz - pz;
+  r = r + d * d;
+  return r;
+}
+
+// CollisionModel point-in-cuboid (collision_model.cpp:124-139) for stash column `col`
+__device__ __forceinline__ bool exact_in_box(const float* stash, int col, float px, float py, float pz) {
+  const float dx = px - stash[F_CX * 32 + col], dy = py - stash[F_CY * 32 + col], dz = pz - stash[F_CZ * 32 + col];
+  const float xv = fabsf((dx * stash[F_AXX * 32 + col] + dy * stash[F_AXY * 32 + col]) + dz * stash[F_AXZ * 32 + col]);
+  const float yv = fabsf((dx * stash[F_AYX * 32 + col] + dy * stash[F_AYY * 32 + col]) + dz * stash[F_AYZ * 32 + col]);
+  const float zv = fabsf((dx * stash[F_AZX * 32 + col] + dy * stash[F_AZY * 32 + col]) + dz * stash[F_AZZ * 32 + col]);
+  return xv <= stash[F_HX * 32 + col] && yv <= stash[F_HY * 32 + col] && zv <= stash[F_HZ * 32 + col];
+}
+
+// CollisionMinMaxModel containment (collision_min_max_model.cpp:74-77)
+__device__ __forceinline__ bool exact_in_aabb(const float* stash, int col, float px, float py, float pz) {
+  return px >= stash[F_MNX * 32 + col] && px <= stash[F_MXX * 32 + col] && py >= stash[F_MNY * 32 + col] &&
+         py <= stash[F_MXY * 32 + col] && pz >= stash[F_MNZ * 32 + col] && pz <= stash[F_MXZ * 32 + col];
+}
+
+__device__ __forceinline__ bool exact_in_radius(const float* stash, int col, float px, float py, float pz) {
+  return l2_simple(stash[F_PX * 32 + col], stash[F_PY * 32 + col], stash[F_PZ * 32 + col], px, py, pz) < 1.0f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The obstacle query for kGroup consecutive poses (stash columns col0 .. col0+3).
+// Returns a 4-bit mask (warp-uniform): bit g set iff pose col0+g collides.
+//   minmax == false: CollisionModel; minmax == true: CollisionMinMaxModel.
+// Candidate set: the cell rows overlapping the union of the poses' candidate boxes. A row is the run
+// of x-adjacent cells [ix0, ix1] at fixed (iy, iz); cell-sorted storage makes it ONE contiguous range
+// of float4, which the warp streams with coalesced 512-byte loads.
+// ---------------------------------------------------------------------------------------------
+template <bool kMinMax>
+__device__ __forceinline__ unsigned sweep_points(const GridDev& g, const float* stash, int col0, int lane) {
+  // union candidate box (dead lanes contribute an empty box)
+  float lo[3], hi[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    lo[a] = 3.402823466e+38f;
+    hi[a] = -3.402823466e+38f;
+  }
+#pragma unroll
+  for (int q = 0; q < kGroup; ++q) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float l = stash[(F_LOX + a) * 32 + col0 + q], h = stash[(F_HIX + a) * 32 + col0 + q];
+      if (l <= h) {
+        lo[a] = fminf(lo[a], l);
+        hi[a] = fmaxf(hi[a], h);
+      }
+    }
+  }
+  if (!(lo[0] <= hi[0] && lo[1] <= hi[1] && lo[2] <= hi[2])) return 0u;
+  // cell ranges; empty when the box misses the grid
+  const float fx0 = cell_f(lo[0], g.org[0], g.inv_xy), fx1 = cell_f(hi[0], g.org[0], g.inv_xy);
+  const float fy0 = cell_f(lo[1], g.org[1], g.inv_xy), fy1 = cell_f(hi[1], g.org[1], g.inv_xy);
+  const float fz0 = cell_f(lo[2], g.org[2], g.inv_z), fz1 = cell_f(hi[2], g.org[2], g.inv_z);
+  if (fx1 < 0.f || fy1 < 0.f || fz1 < 0.f || fx0 > (float)(g.nx - 1) || fy0 > (float)(g.ny - 1) ||
+      fz0 > (float)(g.nz - 1))
+    return 0u;
+  const int ix0 = (int)fmaxf(fx0, 0.f), ix1 = (int)fminf(fx1, (float)(g.nx - 1));
+  const int iy0 = (int)fmaxf(fy0, 0.f), iy1 = (int)fminf(fy1, (float)(g.ny - 1));
+  const int iz0 = (int)fmaxf(fz0, 0.f), iz1 = (int)fminf(fz1, (float)(g.nz - 1));
+  const int nyr = iy1 - iy0 + 1;
+  const int nrows = nyr * (iz1 - iz0 + 1);
+
+  // pre-test coefficients of the 4 poses, in registers
+  float ax[kGroup][3], ay[kGroup][3], az[kGroup][3], kk[kGroup][3], hb[kGroup][3];
+  const float delta = pretest_delta(g);
+#pragma unroll
+  for (int q = 0; q < kGroup; ++q) {
+    const int col = col0 + q;
+    if (kMinMax) {
+      // exact compares need no slack: reuse ax/ay as min/max
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        ax[q][a] = stash[(F_MNX + a) * 32 + col];
+        ay[q][a] = stash[(F_MXX + a) * 32 + col];
+        az[q][a] = 0.f; kk[q][a] = 0.f; hb[q][a] = 0.f;
+      }
+    } else {
+      const float cx = stash[F_CX * 32 + col], cy = stash[F_CY * 32 + col], cz = stash[F_CZ * 32 + col];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        ax[q][a] = stash[(F_AXX + a) * 32 + col];
+        ay[q][a] = stash[(F_AYX + a) * 32 + col];
+        az[q][a] = stash[(F_AZX + a) * 32 + col];
+      }
+      kk[q][0] = (float)(((double)cx * ax[q][0] + (double)cy * ax[q][1]) + (double)cz * ax[q][2]);
+      kk[q][1] = (float)(((double)cx * ay[q][0] + (double)cy * ay[q][1]) + (double)cz * ay[q][2]);
+      kk[q][2] = (float)(((double)cx * az[q][0] + (double)cy * az[q][1]) + (double)cz * az[q][2]);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const float h = stash[(F_HX + a) * 32 + col];
+        hb[q][a] = (h < 0.f) ? -1.0f : __fadd_ru(h, delta);
+      }
+    }
+  }
+
+  unsigned hit = 0u;  // per-lane, exact hits
+  for (int r0 = 0; r0 < nrows; r0 += 32) {
+    const int r = r0 + lane;
+    uint32_t beg = 0, end = 0;
+    if (r < nrows) {
+      const int iy = iy0 + r % nyr, iz = iz0 + r / nyr;
+      const size_t base = ((size_t)iz * g.ny + iy) * (size_t)g.nx;
+      beg = __ldg(g.cell_start + base + ix0);
+      end = __ldg(g.cell_start + base + ix1 + 1);
+    }
+    unsigned rows = __ballot_sync(kFull, beg < end);
+    while (rows) {
+      const int src = __ffs(rows) - 1;
+      rows &= rows - 1;
+      const uint32_t b = __shfl_sync(kFull, beg, src), e = __shfl_sync(kFull, end, src);
+      for (uint32_t j = b + lane; j < e; j += 32) {
+        const float4 p = __ldg(g.pts + j);
+        unsigned pre = 0u;
+#pragma unroll
+        for (int q = 0; q < kGroup; ++q) {
+          bool in;
+          if (kMinMax) {
+            in = p.x >= ax[q][0] && p.x <= ay[q][0] && p.y >= ax[q][1] && p.y <= ay[q][1] && p.z >= ax[q][2] &&
+                 p.z <= ay[q][2];
+          } else {
+            // conservative superset of the exact test: |v' - v| <= delta
+            const float vx = __fmaf_rn(p.x, ax[q][0], __fmaf_rn(p.y, ax[q][1], __fmaf_rn(p.z, ax[q][2], -kk[q][0])));
+            const float vy = __fmaf_rn(p.x, ay[q][0], __fmaf_rn(p.y, ay[q][1], __fmaf_rn(p.z, ay[q][2], -kk[q][1])));
+            const float vz = __fmaf_rn(p.x, az[q][0], __fmaf_rn(p.y, az[q][1], __fmaf_rn(p.z, az[q][2], -kk[q][2])));
+            in = fabsf(vx) <= hb[q][0] && fabsf(vy) <= hb[q][1] && fabsf(vz) <= hb[q][2];
+          }
+          pre |= in ? (1u << q) : 0u;
+        }
+        if (pre) {  // rare: decide with the reference's own arithmetic
+#pragma unroll
+          for (int q = 0; q < kGroup; ++q) {
+            if (pre & (1u << q)) {
+              const int col = col0 + q;
+              const bool in = kMinMax ? exact_in_aabb(stash, col, p.x, p.y, p.z) : exact_in_box(stash, col, p.x, p.y, p.z);
+              if (in && exact_in_radius(stash, col, p.x, p.y, p.z)) hit |= 1u << q;
+            }
+          }
+        }
+      }
+      // the lowest pose of the group already collides: nothing later can precede it
+      if (__any_sync(kFull, hit & 1u)) return __reduce_or_sync(kFull, hit);
+    }
+  }
+  return __reduce_or_sync(kFull, hit);
+}
+
+// nearestKSearch(K=1) against the prune-plan cloud: min float squared distance
+// (stick_path_model.cpp:61-68, toward_global_plan_model.cpp:62-71)
+__device__ __forceinline__ float plan_nn_d2(const float4* plan, int n, float qx, float qy, float qz) {
+  float best = 3.402823466e+38f;
+#pragma unroll 4
+  for (int i = 0; i < n; ++i) {
+    const float4 p = plan[i];
+    const float d = l2_simple(qx, qy, qz, p.x, p.y, p.z);
+    best = fminf(best, d);
+  }
+  return best;
+}
+
+}  // namespace lp

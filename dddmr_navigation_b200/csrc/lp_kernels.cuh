@@ -1,0 +1,872 @@
+// lp_kernels.cuh — the sm_100a kernels of the rollout-and-score path.
+//
+//   grid build : bounds_kernel -> hist_kernel -> scan (3 kernels) -> scatter_kernel
+//   plan cycle : prep_kernel (velocity sampling + trajectory list) -> plan_kernel (fused rollout,
+//                obstacle query, critics, block argmin, last-block final argmin)
+//   read-back  : poses_kernel, count_radius_kernel (diagnostics / parity / roofline accounting)
+#pragma once
+#include "lp_device.cuh"
+
+namespace lp {
+
+// =============================================================================================
+// grid build
+// =============================================================================================
+__device__ __forceinline__ unsigned f2ord(float f) {  // order-preserving float -> uint
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ord2f(unsigned o) {
+  const unsigned u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(u);
+#else
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+#endif
+}
+
+struct BoundsDev {
+  unsigned mn[3], mx[3];  // ordered-uint encoded
+  unsigned n_finite;
+  unsigned pad;
+};
+
+__device__ __forceinline__ float3 load_xyz(const char* raw, size_t i, size_t stride) {
+  if ((stride & 15) == 0) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(raw + i * stride));
+    return make_float3(v.x, v.y, v.z);
+  }
+  const float* p = reinterpret_cast<const float*>(raw + i * stride);
+  return make_float3(__ldg(p), __ldg(p + 1), __ldg(p + 2));
+}
+
+__device__ __forceinline__ bool finite3(float3 v) {
+  return isfinite(v.x) && isfinite(v.y) && isfinite(v.z);
+}
+
+__global__ void __launch_bounds__(256) bounds_kernel(const char* __restrict__ raw, size_t n, size_t stride,
+                                                     BoundsDev* __restrict__ b) {
+  float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
+  float mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+  unsigned cnt = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float3 v = load_xyz(raw, i, stride);
+    if (finite3(v)) {
+      ++cnt;
+      mn[0] = fminf(mn[0], v.x); mx[0] = fmaxf(mx[0], v.x);
+      mn[1] = fminf(mn[1], v.y); mx[1] = fmaxf(mx[1], v.y);
+      mn[2] = fminf(mn[2], v.z); mx[2] = fmaxf(mx[2], v.z);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(kFull, mn[a], o));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(kFull, mx[a], o));
+    }
+    cnt += __shfl_xor_sync(kFull, cnt, o);
+  }
+  if ((threadIdx.x & 31) == 0 && cnt) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      atomicMin(&b->mn[a], f2ord(mn[a]));
+      atomicMax(&b->mx[a], f2ord(mx[a]));
+    }
+    atomicAdd(&b->n_finite, cnt);
+  }
+}
+
+__device__ __forceinline__ uint32_t cell_key(const GridDev& g, float3 v) {
+  const int cx = cell_clamped(v.x, g.org[0], g.inv_xy, g.nx);
+  const int cy = cell_clamped(v.y, g.org[1], g.inv_xy, g.ny);
+  const int cz = cell_clamped(v.z, g.org[2], g.inv_z, g.nz);
+  return (uint32_t)(((size_t)cz * g.ny + cy) * (size_t)g.nx + cx);
+}
+
+// histogram of points per cell; remembers each point's key so the scatter pass does not recompute it
+__global__ void __launch_bounds__(256) hist_kernel(const char* __restrict__ raw, size_t n, size_t stride, GridDev g,
+                                                   uint32_t* __restrict__ counts, uint32_t* __restrict__ keys) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float3 v = load_xyz(raw, i, stride);
+    uint32_t key = 0xffffffffu;
+    if (finite3(v)) {
+      key = cell_key(g, v);
+      atomicAdd(counts + key, 1u);
+    }
+    keys[i] = key;
+  }
+}
+
+// exclusive scan of counts[0..n) in place, three kernels, 2048 items per block
+constexpr int kScanItems = 2048;
+__global__ void __launch_bounds__(256) scan_block_kernel(uint32_t* __restrict__ data, size_t n,
+                                                         uint32_t* __restrict__ block_sums) {
+  __shared__ uint32_t s_warp[8];
+  const size_t base = (size_t)blockIdx.x * kScanItems + (size_t)threadIdx.x * 8;
+  uint32_t v[8];
+  uint32_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    v[k] = (base + k < n) ? data[base + k] : 0u;
+    sum += v[k];
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  uint32_t woff = 0;
+  for (int w = 0; w < warp; ++w) woff += s_warp[w];
+  uint32_t run = woff + incl - sum;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (base + k < n) data[base + k] = run;
+    run += v[k];
+  }
+  if (threadIdx.x == 255) block_sums[blockIdx.x] = woff + incl;
+}
+
+__global__ void __launch_bounds__(1024) scan_sums_kernel(uint32_t* __restrict__ block_sums, int nb,
+                                                         uint32_t* __restrict__ total_out) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < nb; base += 1024) {
+    const int i = base + threadIdx.x;
+    const uint32_t v = (i < nb) ? block_sums[i] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(kFull, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int w = 0; w < warp; ++w) woff += s_warp[w];
+    const uint32_t carry = s_carry;
+    if (i < nb) block_sums[i] = carry + woff + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = carry + woff + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total_out = s_carry;
+}
+
+__global__ void __launch_bounds__(256) scan_add_kernel(uint32_t* __restrict__ data, size_t n,
+                                                       const uint32_t* __restrict__ block_sums,
+                                                       const uint32_t* __restrict__ total) {
+  const uint32_t off = block_sums[blockIdx.x];
+  const size_t base = (size_t)blockIdx.x * kScanItems + (size_t)threadIdx.x * 8;
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (base + k < n) data[base + k] += off;
+  if (blockIdx.x == 0 && threadIdx.x == 0) data[n] = *total;  // cell_start[n_cells]
+}
+
+// counting-sort scatter. `fill` holds a copy of the exclusive offsets and is consumed by atomics, so the
+// order of points inside a cell is arbitrary; every consumer is an any-hit or a count.
+__global__ void __launch_bounds__(256) scatter_kernel(const char* __restrict__ raw, size_t n, size_t stride,
+                                                      const uint32_t* __restrict__ keys, uint32_t* __restrict__ fill,
+                                                      float4* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t key = keys[i];
+    if (key == 0xffffffffu) continue;
+    const float3 v = load_xyz(raw, i, stride);
+    const uint32_t slot = atomicAdd(fill + key, 1u);
+    out[slot] = make_float4(v.x, v.y, v.z, __uint_as_float((uint32_t)i));
+  }
+}
+
+// =============================================================================================
+// prep: velocity sampling (initialise()) and the generated-trajectory list (generateTrajectory's
+// early rejects, num_steps, dt), one CTA per robot.
+// =============================================================================================
+// trajectory_generators::VelocityIterator (velocity_iterator.h:44-69); values are rounded to float where
+// the reference stores them into an Eigen::Vector3f (dd_simple…cpp:282-286).
+__device__ int velocity_iterator_dev(double mn, double mx, int n, float* out) {
+  int cnt = 0;
+  if (mn == mx) {
+    out[cnt++] = (float)mn;
+    return cnt;
+  }
+  n = max(2, n);
+  const double step = (mx - mn) / (double)max(1, n - 1);
+  double next = mn;
+  for (int j = 0; j < n - 1; ++j) {
+    const double cur = next;
+    next += step;
+    if (cnt < kMaxAxis) out[cnt] = (float)cur;
+    ++cnt;
+    if (cur < 0 && next > 0) {
+      if (cnt < kMaxAxis) out[cnt] = 0.0f;
+      ++cnt;
+    }
+  }
+  if (cnt < kMaxAxis) out[cnt] = (float)mx;
+  ++cnt;
+  return min(cnt, kMaxAxis);
+}
+
+__device__ __forceinline__ bool motor_ok(const b200lp_limits& L, float v0, float v2) {
+  const double vr = (double)v0 + L.robot_radius * (double)v2;
+  const double vl = (double)v0 - L.robot_radius * (double)v2;
+  const double rpm_r = vr * L.gear_ratio * 60. / 3.1415926 / L.wheel_diameter;
+  const double rpm_l = vl * L.gear_ratio * 60. / 3.1415926 / L.wheel_diameter;
+  return !(lpm::dabs(rpm_r) >= L.max_motor_shaft_rpm || lpm::dabs(rpm_l) >= L.max_motor_shaft_rpm);
+}
+
+// generateTrajectory prologue (dd_simple…cpp:355-388, omni…cpp:386-424, dd_rotate_inplace…cpp:329-351).
+// returns false when the reference returns false before simulating.
+__device__ __forceinline__ bool traj_precheck(const Consts& C, const RobotIn& q, float v0, float v1, float v2,
+                                              int* num_steps, double* dt, int* err) {
+  const b200lp_limits& L = C.lim;
+  const b200lp_params& P = C.par;
+  const double eps = 1e-4;
+  double vmag, sim_time = P.sim_time;
+  const double aw = (double)fabsf(v2);
+  if (P.theory == B200LP_THEORY_DD_SIMPLE) {
+    vmag = (double)fabsf(v0);
+    if ((L.min_vel_x >= 0 && vmag + eps < L.min_vel_x) && (L.min_vel_theta >= 0 && aw + eps < L.min_vel_theta)) return false;
+    if (L.max_vel_x >= 0 && vmag - eps > L.max_vel_x) return false;
+  } else if (P.theory == B200LP_THEORY_OMNI_SIMPLE) {
+    vmag = (double)(float)lpm::dsqrt((double)v0 * (double)v0 + (double)v1 * (double)v1);  // hypotf
+    if ((L.min_vel_trans >= 0 && vmag + eps < L.min_vel_trans) && (L.min_vel_theta >= 0 && aw + eps < L.min_vel_theta))
+      return false;
+    if (L.max_vel_trans >= 0 && vmag - eps > L.max_vel_trans) return false;
+    if (q.max_speed_override > 0.0 && vmag - eps > q.max_speed_override) return false;
+  } else {
+    vmag = (double)fabsf(v0);
+    sim_time = 6.28 / aw;
+  }
+  const double sim_time_distance = vmag * sim_time;
+  const double sim_time_angle = aw * sim_time;
+  const double a = sim_time_distance / P.sim_granularity, b = sim_time_angle / P.angular_sim_granularity;
+  const double steps_d = ceil((a < b) ? b : a);  // std::max(a,b)
+  if (!(steps_d <= (double)B200LP_MAX_STEPS)) {  // also catches NaN/inf
+    *err = 1;
+    return false;
+  }
+  const int n = (int)steps_d;
+  if (n == 0) return false;
+  *num_steps = n;
+  *dt = sim_time / n;
+  return true;
+}
+
+__global__ void __launch_bounds__(1024) prep_kernel(Consts C, const RobotIn* __restrict__ robots, int t_cap,
+                                                    int shard_rank, int shard_count, float4* __restrict__ rec_vel,
+                                                    int* __restrict__ rec_steps, double* __restrict__ rec_dt,
+                                                    int* __restrict__ rec_sample, RobotMeta* __restrict__ meta,
+                                                    const double* __restrict__ plan7, float4* __restrict__ plan_pts) {
+  __shared__ float s_x[kMaxAxis], s_y[kMaxAxis], s_th[kMaxAxis];
+  __shared__ int s_n[3];
+  __shared__ int s_wkeep[32], s_wvalid[32];
+  __shared__ int s_cnt_lo, s_cnt_hi, s_err;
+  __shared__ unsigned long long s_poses;
+  const int robot = blockIdx.x;
+  const RobotIn q = robots[robot];
+  const b200lp_limits& L = C.lim;
+  const b200lp_params& P = C.par;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // pcl_prune_plan_: float-cast plan positions (model_shared_data.h:83-91)
+  for (int i = tid; i < q.plan_n; i += blockDim.x) {
+    const double* p = plan7 + (q.plan_off + i) * 7;
+    plan_pts[q.plan_off + i] = make_float4((float)p[0], (float)p[1], (float)p[2], 0.f);
+  }
+  if (tid == 0) {
+    s_cnt_lo = 0; s_cnt_hi = 0; s_err = 0; s_poses = 0ull;
+    s_n[0] = s_n[1] = s_n[2] = 0;
+  }
+  __syncthreads();
+
+  const bool sampling_on = P.linear_x_sample * P.angular_z_sample > 0;
+  if (sampling_on && P.theory != B200LP_THEORY_DD_ROTATE_INPLACE && lane == 0 && warp < 3) {
+    // window (dd_simple…cpp:255-277; omni…cpp:277-303); Vector3f stores round to float
+    const double max_vel_th = L.max_vel_theta, min_vel_th = -1.0 * max_vel_th;
+    const float acc0 = (float)L.acc_lim_x, acc1 = (float)L.acc_lim_y, acc2 = (float)L.acc_lim_theta;
+    const double sim_period = 1.0 / P.controller_frequency;
+    const double tx = q.twist[0], ty = q.twist[1], tw = q.twist[2];
+    double min_vel_x = L.min_vel_x, max_vel_x = L.max_vel_x;
+    float mx0, mn0, mx1 = 0.f, mn1 = 0.f, mx2, mn2;
+    if (P.theory == B200LP_THEORY_DD_SIMPLE) {
+      if (q.max_speed_override > 0.0) max_vel_x = fmin(max_vel_x, q.max_speed_override);
+      mx0 = (float)fmin(max_vel_x, tx + (double)acc0 * sim_period);
+      mx2 = (float)fmin(max_vel_th, tw + (double)acc2 * sim_period);
+      mn0 = (float)fmax(min_vel_x, tx / L.deceleration_ratio);
+      mn2 = (float)fmax(min_vel_th, tw - (double)acc2 * sim_period);
+      if (mx0 < mn0) {
+        mn0 = (float)(tx / L.deceleration_ratio);
+        mx0 = (float)(tx / L.deceleration_ratio);
+      }
+    } else {
+      const double min_vel_y = L.min_vel_y, max_vel_y = L.max_vel_y;
+      mx0 = (float)fmin(max_vel_x, tx + (double)acc0 * sim_period);
+      mx1 = (float)fmin(max_vel_y, ty + (double)acc1 * sim_period);
+      mx2 = (float)fmin(max_vel_th, tw + (double)acc2 * sim_period);
+      mn0 = (float)fmax(min_vel_x, tx - (double)acc0 * sim_period);
+      mn1 = (float)fmax(min_vel_y, ty - (double)acc1 * sim_period);
+      mn2 = (float)fmax(min_vel_th, tw - (double)acc2 * sim_period);
+      if (tx >= max_vel_x / L.deceleration_ratio) mn0 = (float)fmax(min_vel_x, tx / L.deceleration_ratio);
+      else if (tx <= min_vel_x / L.deceleration_ratio) mx0 = (float)fmin(max_vel_x, tx / L.deceleration_ratio);
+      if (ty >= max_vel_y / L.deceleration_ratio) mn1 = (float)fmax(min_vel_y, ty / L.deceleration_ratio);
+      else if (ty <= min_vel_y / L.deceleration_ratio) mx1 = (float)fmin(max_vel_y, ty / L.deceleration_ratio);
+    }
+    if (warp == 0) s_n[0] = velocity_iterator_dev((double)mn0, (double)mx0, (int)P.linear_x_sample, s_x);
+    if (warp == 1) {
+      if (P.theory == B200LP_THEORY_OMNI_SIMPLE) s_n[1] = velocity_iterator_dev((double)mn1, (double)mx1, (int)P.linear_y_sample, s_y);
+      else { s_y[0] = 0.f; s_n[1] = 1; }
+    }
+    if (warp == 2) s_n[2] = velocity_iterator_dev((double)mn2, (double)mx2, (int)P.angular_z_sample, s_th);
+  }
+  __syncthreads();
+
+  int n_raw;
+  const int nys = s_n[1], nths = s_n[2];
+  if (!sampling_on) n_raw = 0;
+  else if (P.theory == B200LP_THEORY_DD_ROTATE_INPLACE) n_raw = 2;
+  else n_raw = s_n[0] * nys * nths;
+  const long long lo = (long long)n_raw * shard_rank / shard_count;
+  const long long hi = (long long)n_raw * (shard_rank + 1) / shard_count;
+
+  int base_keep = 0, base_valid = 0;
+  int cnt_lo = 0, cnt_hi = 0, err = 0;
+  unsigned long long poses = 0ull;
+  for (int s0 = 0; s0 < n_raw; s0 += blockDim.x) {
+    const int s = s0 + tid;
+    bool keep = false, valid = false;
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+    int steps = 0;
+    double dt = 0.0;
+    if (s < n_raw) {
+      if (P.theory == B200LP_THEORY_DD_ROTATE_INPLACE) {
+        v2 = (s == 0) ? (float)L.rotation_speed : (float)(-1.0 * L.rotation_speed);
+        keep = motor_ok(L, v0, v2);
+      } else {
+        const int ith = s % nths, iy = (s / nths) % nys, ix = s / (nths * nys);
+        v0 = s_x[ix]; v1 = s_y[iy]; v2 = s_th[ith];
+        keep = (P.theory == B200LP_THEORY_OMNI_SIMPLE) || !L.use_motor_constraint || motor_ok(L, v0, v2);
+      }
+      if (keep) valid = traj_precheck(C, q, v0, v1, v2, &steps, &dt, &err);
+    }
+    const unsigned mk = __ballot_sync(kFull, keep), mv = __ballot_sync(kFull, valid);
+    if (lane == 0) {
+      s_wkeep[warp] = __popc(mk);
+      s_wvalid[warp] = __popc(mv);
+    }
+    __syncthreads();
+    int offk = 0, offv = 0, totk = 0, totv = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      const int a = s_wkeep[w], b = s_wvalid[w];
+      if (w < warp) { offk += a; offv += b; }
+      totk += a; totv += b;
+    }
+    const unsigned lt = (1u << lane) - 1u;
+    if (valid) {
+      const int sample_index = base_keep + offk + __popc(mk & lt);
+      const int id = base_valid + offv + __popc(mv & lt);
+      if (id < t_cap) {
+        const size_t o = (size_t)robot * t_cap + id;
+        rec_vel[o] = make_float4(v0, v1, v2, 0.f);
+        rec_steps[o] = steps;
+        rec_dt[o] = dt;
+        rec_sample[o] = sample_index;
+      }
+      if (s < lo) ++cnt_lo;
+      if (s < hi) ++cnt_hi;
+      if (s >= lo && s < hi) poses += (unsigned long long)steps;
+    }
+    base_keep += totk;
+    base_valid += totv;
+    __syncthreads();
+  }
+  // block totals
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt_lo += __shfl_xor_sync(kFull, cnt_lo, o);
+    cnt_hi += __shfl_xor_sync(kFull, cnt_hi, o);
+    err |= __shfl_xor_sync(kFull, err, o);
+    poses += __shfl_xor_sync(kFull, poses, o);
+  }
+  if (lane == 0) {
+    atomicAdd(&s_cnt_lo, cnt_lo);
+    atomicAdd(&s_cnt_hi, cnt_hi);
+    atomicOr(&s_err, err);
+    atomicAdd(&s_poses, poses);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    RobotMeta m;
+    m.n_samples = base_keep;
+    m.n_traj = base_valid;
+    m.t_begin = s_cnt_lo;
+    m.t_end = s_cnt_hi;
+    m.error = s_err | (base_valid > t_cap ? 2 : 0);
+    m.pad = 0;
+    m.n_poses = (long long)s_poses;
+    meta[robot] = m;
+  }
+}
+
+// =============================================================================================
+// plan: one warp per trajectory; 8 trajectories per CTA; grid = (ceil(t_cap/8), robots)
+// =============================================================================================
+__device__ __forceinline__ bool better(unsigned long long ca, int ia, unsigned long long cb, int ib) {
+  // getBestTrajectory: `cost <= minimum_cost` while scanning in id order => min cost, ties -> largest id
+  return ca < cb || (ca == cb && ia > ib);
+}
+
+struct CtaShared {
+  float stash[kWarpsPerCta][F_COUNT * 32];
+  double R0[9], t0[3], gL[9], gt[3];
+  float4 plan[kPlanSmem];
+  BlockBest best[kWarpsPerCta];
+  int is_last;
+};
+
+__global__ void __launch_bounds__(kThreads, 2)
+plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, const RobotMeta* __restrict__ meta, int t_cap,
+            const float4* __restrict__ rec_vel, const int* __restrict__ rec_steps, const double* __restrict__ rec_dt,
+            const float4* __restrict__ plan_pts, const double* __restrict__ plan7, double* __restrict__ out_cost,
+            double* __restrict__ out_scores, int* __restrict__ out_first_hit, BlockBest* __restrict__ partial,
+            unsigned* __restrict__ block_counter, b200lp_result* __restrict__ results) {
+  __shared__ CtaShared S;
+  const int robot = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const RobotMeta m = meta[robot];
+  const int n_local = m.t_end - m.t_begin;
+  const bool cta_has_work = (int)blockIdx.x * kWarpsPerCta < n_local;
+  const RobotIn& q = robots[robot];
+  const int plan_n = q.plan_n;
+  const float4* plan = plan_pts + q.plan_off;
+
+  if (cta_has_work) {
+    if (threadIdx.x == 0) {
+      // tf2::transformToEigen(robot_pose_) (dd_simple…cpp:355)
+      quat_to_matrix(q.pose[3], q.pose[4], q.pose[5], q.pose[6], S.R0);
+      S.t0[0] = q.pose[0]; S.t0[1] = q.pose[1]; S.t0[2] = q.pose[2];
+    }
+    if (threadIdx.x == 32 && plan_n > 0) {
+      const double* e = plan7 + (q.plan_off + plan_n - 1) * 7;  // prune_plan_.poses.back()
+      quat_to_matrix(e[3], e[4], e[5], e[6], S.gL);
+      S.gt[0] = e[0]; S.gt[1] = e[1]; S.gt[2] = e[2];
+    }
+    if (plan_n <= kPlanSmem)
+      for (int i = threadIdx.x; i < plan_n; i += kThreads) S.plan[i] = plan[i];
+  }
+  __syncthreads();
+  if (plan_n <= kPlanSmem) plan = S.plan;
+
+  const int local = blockIdx.x * kWarpsPerCta + warp;
+  const int id = m.t_begin + local;
+  unsigned long long my_cost_bits = ~0ull;
+  int my_collided = 0;
+
+  if (local < n_local) {
+    const size_t rec = (size_t)robot * t_cap + id;
+    const float4 vel = rec_vel[rec];
+    const int n = rec_steps[rec];
+    const double dt = rec_dt[rec];
+    float* stash = S.stash[warp];
+
+    // ---- critic stack analysis (warp-uniform) ------------------------------------------------
+    const int nc = C.n_critics;
+    double val[B200LP_MAX_CRITICS];  // NaN = not evaluated
+    int hit_pose[B200LP_MAX_CRITICS];
+    bool need_stick = false, need_last_nn = false, need_pp = false;
+    bool early_ok = true;       // may a collision hit end the rollout?
+    int stop_at = nc;           // critics >= stop_at are never evaluated (an earlier one is known negative)
+    const double thetav = (double)vel.z;
+    {
+      bool rollout_dep_seen = false;
+#pragma unroll
+      for (int k = 0; k < B200LP_MAX_CRITICS; ++k) {
+        val[k] = lpm::u2d(0x7ff8000000000000ull);
+        hit_pose[k] = -1;
+        if (k >= nc || k >= stop_at) continue;
+        const CriticDev& cr = C.critics[k];
+        switch (cr.kind) {
+          case B200LP_CRITIC_COLLISION:
+          case B200LP_CRITIC_COLLISION_MIN_MAX:
+            if (g.n_raw < 5) val[k] = 0.0;  // collision_model.cpp:53-55
+            else if (rollout_dep_seen) early_ok = false;
+            break;
+          case B200LP_CRITIC_STICK_PATH:
+            if (plan_n < 3) val[k] = 10.0;
+            else { need_stick = true; rollout_dep_seen = true; }
+            break;
+          case B200LP_CRITIC_TOWARD_GLOBAL_PLAN:
+            if (plan_n < 3) val[k] = 10.0;
+            else { need_last_nn = true; rollout_dep_seen = true; }
+            break;
+          case B200LP_CRITIC_PURE_PURSUIT:
+            if (plan_n == 0 || n < 2) val[k] = -4.0;
+            else { need_pp = true; rollout_dep_seen = true; }
+            break;
+          case B200LP_CRITIC_SHORTEST_ANGLE:
+            if (q.heading_deviation >= 0) val[k] = (thetav >= 0) ? cr.weight : cr.weight * 2;
+            else val[k] = (thetav >= 0) ? cr.weight * 2 : cr.weight;
+            break;
+          case B200LP_CRITIC_TWIRLING:
+            val[k] = lpm::dabs(thetav) * cr.weight;
+            break;
+        }
+        if (val[k] < 0) stop_at = k + 1;  // known-negative up front: later critics are never reached
+      }
+    }
+    // which collision critics still have to run
+    unsigned coll_active = 0u;
+#pragma unroll
+    for (int k = 0; k < B200LP_MAX_CRITICS; ++k)
+      if (k < nc && k < stop_at && g.n_raw >= 5 &&
+          (C.critics[k].kind == B200LP_CRITIC_COLLISION || C.critics[k].kind == B200LP_CRITIC_COLLISION_MIN_MAX))
+        coll_active |= 1u << k;
+    const int first_coll = coll_active ? (__ffs(coll_active) - 1) : -1;
+    const bool any_rollout_work = coll_active || need_stick || need_last_nn || need_pp;
+
+    // ---- rollout + query, 32 poses at a time ---------------------------------------------------
+    Carry carry = {0.f, 0.f, 0.f};
+    double stick_sum = 0.0;
+    float last_nn = 0.f;
+    double pp_val = 0.0;
+    bool done = !any_rollout_work;
+    for (int base = 0; base < n && !done; base += 32) {
+      float px, py, pth;
+      rollout32(carry, lane, C.par.theory, vel.x, vel.y, vel.z, dt, px, py, pth);
+      const int k = base + lane;
+      const bool live = k < n;
+      double L[9], t[3];
+      pose_affine(S.R0, S.t0, px, py, pth, L, t);
+      if (need_pp && k == n - 1) {
+        double tw = 0.0, ow = 0.0;
+#pragma unroll
+        for (int c = 0; c < B200LP_MAX_CRITICS; ++c)
+          if (c < nc && C.critics[c].kind == B200LP_CRITIC_PURE_PURSUIT && lpm::d2u(val[c]) == 0x7ff8000000000000ull) {
+            tw = C.critics[c].tw; ow = C.critics[c].ow;
+          }
+        pp_val = pure_pursuit_value(L, t, S.gL, S.gt, tw, ow);
+      }
+      pose_geometry(C, g, L, t, stash, lane, live, nullptr);
+      __syncwarp();
+
+      // obstacle query, groups of kGroup consecutive poses
+      const int n_here = min(32, n - base);
+#pragma unroll
+      for (int kc = 0; kc < B200LP_MAX_CRITICS; ++kc) {
+        if (kc >= nc || !(coll_active & (1u << kc))) continue;
+        const bool minmax = C.critics[kc].kind == B200LP_CRITIC_COLLISION_MIN_MAX;
+        for (int col0 = 0; col0 < n_here; col0 += kGroup) {
+          const unsigned h = minmax ? sweep_points<true>(g, stash, col0, lane) : sweep_points<false>(g, stash, col0, lane);
+          if (h) {
+            hit_pose[kc] = base + col0 + (__ffs(h) - 1);
+            coll_active &= ~(1u << kc);
+            break;
+          }
+        }
+      }
+      // A hit of the FIRST collision critic of the stack ends the trajectory (the reference returns -1
+      // there) when nothing that precedes it in the stack depends on the rollout. A later collision
+      // critic hitting first only retires that critic: the earlier one must still run to the end.
+      if (early_ok && first_coll >= 0) {
+#pragma unroll
+        for (int kc = 0; kc < B200LP_MAX_CRITICS; ++kc)
+          if (kc == first_coll && hit_pose[kc] >= 0) done = true;
+      }
+      if (done) break;
+
+      if (need_stick || need_last_nn) {
+        float d2 = 0.f;
+        if (live) d2 = plan_nn_d2(plan, plan_n, stash[F_PX * 32 + lane], stash[F_PY * 32 + lane], stash[F_PZ * 32 + lane]);
+        const float sq = lpm::fsqrt(d2);
+        if (need_stick) {
+          // normalized_distance += sqrt(d2), in pose order, in double (stick_path_model.cpp:68)
+          for (int j = 0; j < n_here; ++j) stick_sum += (double)__shfl_sync(kFull, sq, j);
+        }
+        if (n - 1 - base < 32 && n - 1 >= base) last_nn = __shfl_sync(kFull, sq, n - 1 - base);
+      }
+      __syncwarp();
+    }
+    if (need_pp) pp_val = __shfl_sync(kFull, pp_val, (n - 1) & 31);
+
+    // ---- StackedScoringModel::scoreTrajectory (stacked_scoring_model.cpp:75-93) -----------------
+    double cost = 0.0;
+    int first_hit = -1;
+    bool stopped = false;
+#pragma unroll
+    for (int k = 0; k < B200LP_MAX_CRITICS; ++k) {
+      if (k >= nc) continue;
+      if (stopped) {
+        val[k] = lpm::u2d(0x7ff8000000000000ull);
+        continue;
+      }
+      const CriticDev& cr = C.critics[k];
+      const bool unknown = lpm::d2u(val[k]) == 0x7ff8000000000000ull;
+      if (unknown) {
+        switch (cr.kind) {
+          case B200LP_CRITIC_COLLISION:
+          case B200LP_CRITIC_COLLISION_MIN_MAX:
+            val[k] = (hit_pose[k] >= 0) ? -1.0 : 0.0;
+            if (hit_pose[k] >= 0 && first_hit < 0) first_hit = hit_pose[k];
+            break;
+          case B200LP_CRITIC_STICK_PATH: val[k] = stick_sum / (double)plan_n; break;
+          case B200LP_CRITIC_TOWARD_GLOBAL_PLAN: val[k] = (double)last_nn * cr.weight; break;
+          case B200LP_CRITIC_PURE_PURSUIT: val[k] = pp_val; break;
+          default: break;
+        }
+      }
+      if (val[k] < 0) {
+        cost = val[k];
+        stopped = true;
+      } else {
+        cost += val[k];
+      }
+    }
+    if (lane == 0) {
+      out_cost[rec] = cost;
+      out_first_hit[rec] = first_hit;
+#pragma unroll
+      for (int k = 0; k < B200LP_MAX_CRITICS; ++k)
+        if (k < nc) out_scores[rec * nc + k] = val[k];
+    }
+    if (cost >= 0.0 && cost <= 9999999.0) my_cost_bits = lpm::d2u(cost);  // local_planner.cpp:450,460
+    my_collided = first_hit >= 0 ? 1 : 0;
+  }
+
+  // ---- block argmin: per-warp results -> warp-shuffle reduce -> one partial per CTA ---------------
+  if (lane == 0) {
+    S.best[warp].cost_bits = my_cost_bits;
+    S.best[warp].id = id;
+    S.best[warp].n_collided = my_collided;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long cb = ~0ull;
+    int bi = -1, ncoll = 0;
+    if (lane < kWarpsPerCta) {
+      cb = S.best[lane].cost_bits;
+      bi = S.best[lane].id;
+      ncoll = S.best[lane].n_collided;
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      const unsigned long long ocb = __shfl_xor_sync(kFull, cb, o);
+      const int obi = __shfl_xor_sync(kFull, bi, o);
+      ncoll += __shfl_xor_sync(kFull, ncoll, o);
+      if (ocb != ~0ull && (cb == ~0ull || better(ocb, obi, cb, bi))) { cb = ocb; bi = obi; }
+    }
+    if (lane == 0) {
+      BlockBest b;
+      b.cost_bits = cb;
+      b.id = (cb == ~0ull) ? -1 : bi;
+      b.n_collided = ncoll;
+      partial[(size_t)robot * gridDim.x + blockIdx.x] = b;
+      __threadfence();
+      const unsigned ticket = atomicAdd(block_counter + robot, 1u);
+      S.is_last = (ticket == gridDim.x - 1) ? 1 : 0;
+    }
+  }
+  __syncthreads();
+  if (!S.is_last) return;
+
+  // ---- last CTA of this robot: final argmin over the CTA partials (local_planner.cpp:447-480) ------
+  __threadfence();
+  unsigned long long cb = ~0ull;
+  int bi = -1, ncoll = 0;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += kThreads) {
+    const BlockBest b = partial[(size_t)robot * gridDim.x + i];
+    ncoll += b.n_collided;
+    if (b.cost_bits != ~0ull && (cb == ~0ull || better(b.cost_bits, b.id, cb, bi))) { cb = b.cost_bits; bi = b.id; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long ocb = __shfl_xor_sync(kFull, cb, o);
+    const int obi = __shfl_xor_sync(kFull, bi, o);
+    ncoll += __shfl_xor_sync(kFull, ncoll, o);
+    if (ocb != ~0ull && (cb == ~0ull || better(ocb, obi, cb, bi))) { cb = ocb; bi = obi; }
+  }
+  __syncthreads();  // S.best is reused below
+  if (lane == 0) {
+    S.best[warp].cost_bits = cb;
+    S.best[warp].id = bi;
+    S.best[warp].n_collided = ncoll;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    cb = ~0ull; bi = -1; ncoll = 0;
+    for (int w = 0; w < kWarpsPerCta; ++w) {
+      const BlockBest b = S.best[w];
+      ncoll += b.n_collided;
+      if (b.cost_bits != ~0ull && (cb == ~0ull || better(b.cost_bits, b.id, cb, bi))) { cb = b.cost_bits; bi = b.id; }
+    }
+    b200lp_result r;
+    r.best_id = (cb == ~0ull) ? -1 : bi;
+    r.n_samples = m.n_samples;
+    r.n_traj = n_local;
+    r.n_collided = ncoll;
+    r.n_poses = m.n_poses;
+    r.best_cost = (cb == ~0ull) ? -1.0 : lpm::u2d(cb);
+    r.xv = r.yv = r.thetav = 0.0;
+    if (cb != ~0ull) {
+      const float4 v = rec_vel[(size_t)robot * t_cap + bi];
+      r.xv = (double)v.x;
+      r.yv = (C.par.theory == B200LP_THEORY_OMNI_SIMPLE) ? (double)v.y : 0.0;
+      r.thetav = (double)v.z;
+    }
+    results[robot] = r;
+    block_counter[robot] = 0u;  // ready for the next launch
+  }
+}
+
+// =============================================================================================
+// read-back / diagnostics
+// =============================================================================================
+// lane-per-pose scan of every cell overlapping the 1 m ball: n_r1 and (optionally) the exact collision flag
+__device__ __forceinline__ void ball_scan(const GridDev& g, const float* stash, int col, int mode /*-1 none,0 box,1 minmax*/,
+                                          int* n_r1, int* collide) {
+  int cnt = 0, hit = 0;
+  const float qx = stash[F_PX * 32 + col], qy = stash[F_PY * 32 + col], qz = stash[F_PZ * 32 + col];
+  const float r = 1.0f + 1e-3f + 1e-5f * g.cmax;
+  const float fx0 = cell_f(qx - r, g.org[0], g.inv_xy), fx1 = cell_f(qx + r, g.org[0], g.inv_xy);
+  const float fy0 = cell_f(qy - r, g.org[1], g.inv_xy), fy1 = cell_f(qy + r, g.org[1], g.inv_xy);
+  const float fz0 = cell_f(qz - r, g.org[2], g.inv_z), fz1 = cell_f(qz + r, g.org[2], g.inv_z);
+  if (!(fx1 < 0.f || fy1 < 0.f || fz1 < 0.f || fx0 > (float)(g.nx - 1) || fy0 > (float)(g.ny - 1) ||
+        fz0 > (float)(g.nz - 1)) && g.n_kept > 0) {
+    const int ix0 = (int)fmaxf(fx0, 0.f), ix1 = (int)fminf(fx1, (float)(g.nx - 1));
+    const int iy0 = (int)fmaxf(fy0, 0.f), iy1 = (int)fminf(fy1, (float)(g.ny - 1));
+    const int iz0 = (int)fmaxf(fz0, 0.f), iz1 = (int)fminf(fz1, (float)(g.nz - 1));
+    for (int iz = iz0; iz <= iz1; ++iz)
+      for (int iy = iy0; iy <= iy1; ++iy) {
+        const size_t base = ((size_t)iz * g.ny + iy) * (size_t)g.nx;
+        const uint32_t b = g.cell_start[base + ix0], e = g.cell_start[base + ix1 + 1];
+        for (uint32_t j = b; j < e; ++j) {
+          const float4 p = g.pts[j];
+          if (l2_simple(qx, qy, qz, p.x, p.y, p.z) < 1.0f) {
+            ++cnt;
+            if (mode == 0 && exact_in_box(stash, col, p.x, p.y, p.z)) hit = 1;
+            if (mode == 1 && exact_in_aabb(stash, col, p.x, p.y, p.z)) hit = 1;
+          }
+        }
+      }
+  }
+  *n_r1 = cnt;
+  *collide = hit;
+}
+
+// one warp recomputes one trajectory and writes every per-pose quantity the reference's Trajectory holds
+__global__ void __launch_bounds__(32) poses_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, int robot,
+                                                   int t_cap, int id, const float4* __restrict__ rec_vel,
+                                                   const int* __restrict__ rec_steps, const double* __restrict__ rec_dt,
+                                                   double* __restrict__ o_pose, float* __restrict__ o_pcl,
+                                                   float* __restrict__ o_cuboid, float* __restrict__ o_aabb,
+                                                   unsigned char* __restrict__ o_collide, int* __restrict__ o_nr1) {
+  __shared__ float stash[F_COUNT * 32];
+  __shared__ double R0[9], t0[3];
+  const int lane = threadIdx.x;
+  const RobotIn& q = robots[robot];
+  if (lane == 0) {
+    quat_to_matrix(q.pose[3], q.pose[4], q.pose[5], q.pose[6], R0);
+    t0[0] = q.pose[0]; t0[1] = q.pose[1]; t0[2] = q.pose[2];
+  }
+  __syncwarp();
+  const size_t rec = (size_t)robot * t_cap + id;
+  const float4 vel = rec_vel[rec];
+  const int n = rec_steps[rec];
+  const double dt = rec_dt[rec];
+  int mode = -1;
+  for (int k = C.n_critics - 1; k >= 0; --k) {
+    if (C.critics[k].kind == B200LP_CRITIC_COLLISION) mode = 0;
+    if (C.critics[k].kind == B200LP_CRITIC_COLLISION_MIN_MAX) mode = 1;
+  }
+  Carry carry = {0.f, 0.f, 0.f};
+  for (int base = 0; base < n; base += 32) {
+    float px, py, pth;
+    rollout32(carry, lane, C.par.theory, vel.x, vel.y, vel.z, dt, px, py, pth);
+    const int k = base + lane;
+    const bool live = k < n;
+    double L[9], t[3];
+    pose_affine(R0, t0, px, py, pth, L, t);
+    float verts[24];
+    pose_geometry(C, g, L, t, stash, lane, live, verts);
+    __syncwarp();
+    if (live) {
+      double qd[4];
+      matrix_to_quat(L, qd);  // tf2::eigenToTransform (dd_simple…cpp:434)
+      o_pose[k * 7 + 0] = t[0]; o_pose[k * 7 + 1] = t[1]; o_pose[k * 7 + 2] = t[2];
+      o_pose[k * 7 + 3] = qd[0]; o_pose[k * 7 + 4] = qd[1]; o_pose[k * 7 + 5] = qd[2]; o_pose[k * 7 + 6] = qd[3];
+      for (int a = 0; a < 3; ++a) {
+        o_pcl[k * 3 + a] = stash[(F_PX + a) * 32 + lane];
+        o_aabb[k * 6 + a] = stash[(F_MNX + a) * 32 + lane];
+        o_aabb[k * 6 + 3 + a] = stash[(F_MXX + a) * 32 + lane];
+      }
+      for (int j = 0; j < 24; ++j) o_cuboid[k * 24 + j] = verts[j];
+      int nr1 = 0, col = 0;
+      if (g.n_raw >= 5) ball_scan(g, stash, lane, mode, &nr1, &col);
+      o_nr1[k] = nr1;
+      o_collide[k] = (unsigned char)col;
+    }
+    __syncwarp();
+  }
+}
+
+// sum over all poses of the launch's trajectory range of |radiusSearch(pose, 1.0)|
+__global__ void __launch_bounds__(kThreads) count_radius_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots,
+                                                                const RobotMeta* __restrict__ meta, int t_cap,
+                                                                const float4* __restrict__ rec_vel,
+                                                                const int* __restrict__ rec_steps,
+                                                                const double* __restrict__ rec_dt,
+                                                                unsigned long long* __restrict__ out /* [2]: sum, poses */) {
+  __shared__ float s_stash[kWarpsPerCta][F_COUNT * 32];
+  __shared__ double R0[9], t0[3];
+  const int robot = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const RobotMeta m = meta[robot];
+  const RobotIn& q = robots[robot];
+  if (threadIdx.x == 0) {
+    quat_to_matrix(q.pose[3], q.pose[4], q.pose[5], q.pose[6], R0);
+    t0[0] = q.pose[0]; t0[1] = q.pose[1]; t0[2] = q.pose[2];
+  }
+  __syncthreads();
+  const int local = blockIdx.x * kWarpsPerCta + warp;
+  if (local >= m.t_end - m.t_begin) return;
+  const size_t rec = (size_t)robot * t_cap + m.t_begin + local;
+  const float4 vel = rec_vel[rec];
+  const int n = rec_steps[rec];
+  const double dt = rec_dt[rec];
+  float* stash = s_stash[warp];
+  Carry carry = {0.f, 0.f, 0.f};
+  unsigned long long sum = 0ull;
+  for (int base = 0; base < n; base += 32) {
+    float px, py, pth;
+    rollout32(carry, lane, C.par.theory, vel.x, vel.y, vel.z, dt, px, py, pth);
+    double L[9], t[3];
+    pose_affine(R0, t0, px, py, pth, L, t);
+    stash[F_PX * 32 + lane] = (float)t[0];
+    stash[F_PY * 32 + lane] = (float)t[1];
+    stash[F_PZ * 32 + lane] = (float)t[2];
+    __syncwarp();
+    if (base + lane < n && g.n_raw >= 5) {
+      int nr1, col;
+      ball_scan(g, stash, lane, -1, &nr1, &col);
+      sum += (unsigned long long)nr1;
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(kFull, sum, o);
+  if (lane == 0) {
+    atomicAdd(out, sum);
+    atomicAdd(out + 1, (unsigned long long)n);
+  }
+}
+
+}  // namespace lp

@@ -1,0 +1,227 @@
+"""Host-side mirror of the reference's local-planner cycle on top of the C ABI (include/b200lp.h).
+
+:class:`LocalPlanner` is the thin, literal wrapper (one method per C entry point).
+:class:`Local_Planner` keeps the reference's operator names and return codes for the hot path —
+``setPlan`` / ``computeVelocityCommand`` returning a ``PlannerState`` and a ``Trajectory``
+(src/dddmr_local_planner/local_planner/include/local_planner/local_planner.h:72-82,
+src/dddmr_sys_core/include/dddmr_sys_core/dddmr_enum_states.h:46-54) — so tests and callers read like
+the reference. Everything numeric happens in libb200lp.so on the GPU; nothing here computes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import abi
+from .config import PlannerConfig, make_query
+
+_P = C.c_void_p
+
+
+class PlannerState(enum.IntEnum):
+    """dddmr_sys_core::PlannerState (dddmr_enum_states.h:46-54) — the values the hot path can produce."""
+    TF_FAIL = 0
+    PRUNE_PLAN_FAIL = 1
+    ALL_TRAJECTORIES_FAIL = 2
+    TRAJECTORY_FOUND = 3
+    PATH_BLOCKED_WAIT = 4
+    PATH_BLOCKED_REPLANNING = 5
+    PERCEPTION_MALFUNCTION = 6
+
+
+@dataclass
+class Trajectory:
+    """The fields of base_trajectory::Trajectory the caller consumes (trajectory.h:62-66)."""
+    xv_: float = 0.0
+    yv_: float = 0.0
+    thetav_: float = 0.0
+    cost_: float = -1.0
+    time_delta_: float = 0.0
+    id: int = -1
+
+
+def _cloud_bytes(pts: np.ndarray):
+    """Accept (N,3) xyz, (N,4) PointXYZ layout or (N,8) PointXYZI layout float32; returns (array, stride)."""
+    pts = np.ascontiguousarray(pts, dtype=np.float32)
+    if pts.ndim != 2 or pts.shape[1] not in (3, 4, 8):
+        raise ValueError("cloud must be (N,3), (N,4) [pcl::PointXYZ] or (N,8) [pcl::PointXYZI] float32")
+    return pts, pts.shape[1] * 4
+
+
+class LocalPlanner:
+    """One generator + its critic stack on one GPU (a b200lp_ctx)."""
+
+    def __init__(self, config: PlannerConfig | None = None, device: int = 0, lib_path: str | None = None):
+        self.lib = abi.load_library(lib_path)
+        self.config = config or PlannerConfig()
+        self._L, self._Pm = self.config.limits(), self.config.params()
+        self._cub = self.config.cuboid()
+        self._crit, self.n_critics = self.config.critic_array()
+        self._grid = self.config.grid_config()
+        h = _P()
+        rc = self.lib.b200lp_create(C.byref(h), device, C.byref(self._L), C.byref(self._Pm),
+                                    self._cub.ctypes.data_as(C.POINTER(C.c_float)), self._crit, self.n_critics,
+                                    C.byref(self._grid))
+        if rc != 0:
+            raise abi.B200LPError(rc, (self.lib.b200lp_last_error(None) or b"").decode())
+        self.h = h
+        self.last = None
+        self._n_robots = 0
+        self._results = None
+
+    # -- lifetime -------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b200lp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise abi.B200LPError(rc, (self.lib.b200lp_last_error(self.h) or b"").decode())
+
+    # -- inputs ---------------------------------------------------------------------------------
+    def set_cloud(self, pts: np.ndarray):
+        pts, stride = _cloud_bytes(pts)
+        self._ck(self.lib.b200lp_set_cloud(self.h, pts.ctypes.data_as(_P), pts.shape[0], stride))
+
+    def set_cloud_device(self, dev_ptr: int, n: int, stride: int):
+        self._ck(self.lib.b200lp_set_cloud_device(self.h, _P(dev_ptr), n, stride))
+
+    def set_plan(self, plan: np.ndarray):
+        plan = np.ascontiguousarray(plan, dtype=np.float64).reshape(-1, 7)
+        self._ck(self.lib.b200lp_set_plan(self.h, plan.ctypes.data_as(C.POINTER(C.c_double)), plan.shape[0]))
+
+    # -- cycle ----------------------------------------------------------------------------------
+    def plan(self, q: abi.Query) -> abi.Result:
+        r = abi.Result()
+        self._ck(self.lib.b200lp_plan(self.h, C.byref(q), C.byref(r)))
+        self.last, self._n_robots = r, 1
+        self._results = [r]
+        return r
+
+    def plan_shard(self, q: abi.Query, rank: int, count: int) -> abi.Result:
+        r = abi.Result()
+        self._ck(self.lib.b200lp_plan_shard(self.h, C.byref(q), rank, count, C.byref(r)))
+        self.last, self._n_robots = r, 1
+        self._results = [r]
+        return r
+
+    def plan_batch(self, queries, plans, plan_offsets):
+        """queries: ctypes array of abi.Query; plans: (sum,7) float64; plan_offsets: (n+1,) int64."""
+        n = len(queries)
+        plans = np.ascontiguousarray(plans, dtype=np.float64).reshape(-1, 7)
+        offs = np.ascontiguousarray(plan_offsets, dtype=np.int64)
+        assert offs.shape == (n + 1,)
+        res = (abi.Result * n)()
+        self._ck(self.lib.b200lp_plan_batch(self.h, queries, n, plans.ctypes.data_as(C.POINTER(C.c_double)),
+                                            offs.ctypes.data_as(C.POINTER(C.c_int64)), res))
+        self._n_robots = n
+        self._results = res
+        self.last = res[0]
+        return res
+
+    # -- read-back ------------------------------------------------------------------------------
+    def read_trajectories(self, robot: int = 0) -> dict:
+        n = self.traj_count(robot)[0]  # arrays span the robot's whole id space, also after a sharded run
+        nc = max(1, self.n_critics)
+        d = {
+            "sample_index": np.zeros(n, np.int32), "vel": np.zeros((n, 3), np.float32),
+            "num_steps": np.zeros(n, np.int32), "time_delta": np.zeros(n, np.float64),
+            "cost": np.zeros(n, np.float64), "critic_scores": np.zeros((n, nc), np.float64),
+            "first_hit_pose": np.zeros(n, np.int32),
+        }
+        if self.n_critics == 0:
+            d["critic_scores"] = np.zeros((n, 0), np.float64)
+        v = abi.TrajView(*[d[k].ctypes.data_as(t) if d[k].size else None for k, t in abi.TrajView._fields_])
+        self._ck(self.lib.b200lp_read_trajectories(self.h, robot, C.byref(v)))
+        return d
+
+    def traj_count(self, robot: int = 0):
+        """-> (n_traj_global, t_begin, t_end) of the last cycle."""
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        self._ck(self.lib.b200lp_traj_count(self.h, robot, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def read_poses(self, traj_id: int, num_steps: int, robot: int = 0) -> dict:
+        n = num_steps
+        d = {
+            "pose": np.zeros((n, 7), np.float64), "pcl_pose": np.zeros((n, 3), np.float32),
+            "cuboid": np.zeros((n, 8, 3), np.float32), "aabb": np.zeros((n, 6), np.float32),
+            "collide": np.zeros(n, np.uint8), "n_r1": np.zeros(n, np.int32),
+        }
+        v = abi.PoseView(*[d[k].ctypes.data_as(t) for k, t in abi.PoseView._fields_])
+        self._ck(self.lib.b200lp_read_poses(self.h, robot, traj_id, C.byref(v)))
+        return d
+
+    def count_radius(self):
+        s, n = C.c_int64(), C.c_int64()
+        self._ck(self.lib.b200lp_count_radius(self.h, C.byref(s), C.byref(n)))
+        return s.value, n.value
+
+    def last_timing(self) -> dict:
+        a, b, c, d = C.c_float(), C.c_float(), C.c_float(), C.c_float()
+        self.lib.b200lp_last_timing(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+        return {"ms_upload": a.value, "ms_grid_build": b.value, "ms_plan_kernels": c.value, "ms_readback": d.value}
+
+    def launch_count(self) -> int:
+        return int(self.lib.b200lp_launch_count(self.h))
+
+    def grid_info(self) -> dict:
+        dims = (C.c_int32 * 3)()
+        org = (C.c_float * 3)()
+        cell = (C.c_float * 2)()
+        kept = C.c_int64()
+        self._ck(self.lib.b200lp_grid_info(self.h, dims, org, cell, C.byref(kept)))
+        return {"dims": tuple(dims), "origin": tuple(org), "cell": tuple(cell), "n_points_kept": kept.value}
+
+    def stream(self) -> int:
+        return int(self.lib.b200lp_stream(self.h) or 0)
+
+
+class Local_Planner:
+    """The reference's Local_Planner surface for the hot path (local_planner.h:72-82).
+
+    The caller supplies what the reference pulls from ROS at the top of computeVelocityCommand: the robot pose
+    (tf map->base_link), the odometry twist, the aggregated observation cloud and the prune plan.
+    """
+
+    def __init__(self, config: PlannerConfig | None = None, device: int = 0):
+        self.planner = LocalPlanner(config, device)
+        self._have_plan = False
+        self.robot_pose = None
+        self.robot_twist = None
+        self.current_allowed_max_linear_speed_ = -1.0
+        self.heading_deviation_ = 0.0
+
+    def setPlan(self, prune_plan: np.ndarray):
+        """prune plan, (n,7) position + orientation xyzw — prunePlan()'s output (local_planner.cpp:374-445)."""
+        self.planner.set_plan(prune_plan)
+        self._have_plan = True
+
+    def setObservation(self, cloud: np.ndarray):
+        """aggregate_observation_ (perception_3d/src/stacked_perception.cpp:128-140)."""
+        self.planner.set_cloud(cloud)
+
+    def setRobotState(self, pose7, twist3):
+        self.robot_pose = [float(v) for v in pose7]
+        self.robot_twist = [float(v) for v in twist3]
+
+    def computeVelocityCommand(self, traj_gen_name: str = "differential_drive_simple"):
+        """-> (PlannerState, Trajectory). Mirrors local_planner.cpp:482-621 for the states the path decides."""
+        if self.robot_pose is None:
+            return PlannerState.TF_FAIL, Trajectory()
+        q = make_query(self.robot_pose, self.robot_twist, self.current_allowed_max_linear_speed_, self.heading_deviation_)
+        r = self.planner.plan(q)
+        best = Trajectory(r.xv, r.yv, r.thetav, r.best_cost, 0.0, r.best_id)
+        if r.best_id < 0:
+            return PlannerState.ALL_TRAJECTORIES_FAIL, best
+        return PlannerState.TRAJECTORY_FOUND, best

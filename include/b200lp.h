@@ -19,6 +19,7 @@
  *                                LP/mpc_critics/src/stacked_scoring_model.cpp:75-93; local_planner.cpp:447-480).
  *   b200lp_plan_batch        <- the same cycle for many independent robots (fleet sharding; no reference analogue,
  *                               one reference process serves one robot).
+ *   b200lp_traj_count /
  *   b200lp_read_trajectories <- what the reference keeps in std::vector<base_trajectory::Trajectory>
  *                               (LP/base_trajectory/include/base_trajectory/trajectory.h:47-126) — read back for
  *                               RViz publishing (local_planner.cpp:554,569) and for parity tests.
@@ -194,6 +195,9 @@ int b200lp_plan_shard(b200lp_ctx* ctx, const b200lp_query* q, int rank, int coun
 int b200lp_plan_batch(b200lp_ctx* ctx, const b200lp_query* qs, size_t n_robots, const double* plans,
                       const int64_t* plan_offsets /* n_robots+1 */, b200lp_result* outs);
 
+/* Size of robot's trajectory-id space in the last cycle (= n_traj of an unsharded run) and the id range
+ * [t_begin, t_end) the last call actually scored (the whole space unless b200lp_plan_shard was used). */
+int b200lp_traj_count(const b200lp_ctx* ctx, size_t robot, int32_t* n_traj_global, int32_t* t_begin, int32_t* t_end);
 int b200lp_read_trajectories(b200lp_ctx* ctx, size_t robot, const b200lp_traj_view* view);
 int b200lp_read_poses(b200lp_ctx* ctx, size_t robot, int32_t traj_id, const b200lp_pose_view* view);
 

@@ -1,0 +1,280 @@
+"""GPU parity: the sm_100a path (through the C ABI) against the CPU oracle on identical inputs.
+
+Bar (BASELINE.json north_star): bit-exact num_steps, sample validity / trajectory-id mapping, collision
+outcome (first colliding pose), selected trajectory id; per-critic float scores within 1e-4 relative.
+Against the oracle's "shared" math mode the floats are required to be IDENTICAL (same functions, no FMA);
+against its "libm" mode (glibc, what the reference binary calls) the 1e-4 tolerance applies.
+"""
+import copy
+import math
+
+import numpy as np
+import pytest
+
+from dddmr_navigation_b200 import LocalPlanner, Local_Planner, PlannerConfig, PlannerState, abi, make_query, synth
+from dddmr_navigation_b200.config import (DD_ROTATE_INPLACE_DEFAULT, OMNI_SIMPLE_CRITICS, OMNI_SIMPLE_DEFAULT,
+                                          ROTATE_CRITICS)
+from oracle import lporacle as O
+from tests.helpers import (assert_result_equal, assert_same_array, assert_trajectories_equal, reference_argmin,
+                           run_pair)
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(cfg, math_mode=O.MATH_SHARED, index_mode=O.INDEX_GRID):
+    return LocalPlanner(cfg), O.OraclePlanner(cfg, math_mode, index_mode)
+
+
+def _full_compare(gpu, ora, r_g, r_o, n_pose_trajs=6, exact=True):
+    assert_result_equal(r_g, r_o, exact_cost=exact)
+    tg, to = gpu.read_trajectories(), ora.read_trajectories()
+    assert_trajectories_equal(tg, to, exact=exact)
+    n = r_o.n_traj
+    if n == 0:
+        return tg
+    ids = sorted(set(np.linspace(0, n - 1, min(n, n_pose_trajs)).astype(int).tolist()))
+    for i in ids:
+        ns = int(to["num_steps"][i])
+        pg, po = gpu.read_poses(i, ns), ora.read_poses(i, ns)
+        for k in po:
+            if exact or k in ("collide", "n_r1"):
+                assert_same_array(pg[k], po[k], f"traj {i} {k}")
+            else:
+                np.testing.assert_allclose(pg[k], po[k], rtol=1e-4, atol=1e-9, err_msg=f"traj {i} {k}")
+    return tg
+
+
+def test_playground_fixture_bit_exact():
+    sc = synth.playground()
+    gpu, ora = _pair(sc.config)
+    r_g, r_o = run_pair(gpu, ora, sc.cloud, sc.plan, sc.pose, sc.twist)
+    assert r_o.n_traj == 55 and r_o.n_poses == 2363
+    _full_compare(gpu, ora, r_g, r_o, n_pose_trajs=55)
+
+
+def test_playground_vs_libm_oracle():
+    sc = synth.playground()
+    gpu, ora = _pair(sc.config, O.MATH_LIBM, O.INDEX_BRUTE)
+    r_g, r_o = run_pair(gpu, ora, sc.cloud, sc.plan, sc.pose, sc.twist)
+    _full_compare(gpu, ora, r_g, r_o, exact=False)
+
+
+def test_c1_ramp_full():
+    sc = synth.c1_ramp()
+    gpu, ora = _pair(sc.config)
+    r_g, r_o = run_pair(gpu, ora, sc.cloud, sc.plan, sc.pose, sc.twist)
+    assert r_o.n_traj == 520 and r_o.n_collided > 0.3 * 520
+    tg = _full_compare(gpu, ora, r_g, r_o, n_pose_trajs=12)
+    assert r_g.best_id == reference_argmin(tg["cost"])
+    s_g, n_g = gpu.count_radius()
+    s_o, n_o = ora.count_radius()
+    assert (s_g, n_g) == (s_o, n_o)
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref (nanoflann build) not present")
+def test_c1_ramp_vs_reference_nanoflann_libm():
+    sc = synth.c1_ramp()
+    gpu, ora = _pair(sc.config, O.MATH_LIBM, O.INDEX_NANOFLANN)
+    r_g, r_o = run_pair(gpu, ora, sc.cloud, sc.plan, sc.pose, sc.twist)
+    _full_compare(gpu, ora, r_g, r_o, n_pose_trajs=4, exact=False)
+
+
+SMALL_CASES = []
+
+
+def _cfg(gen_over=None, critics=None, gen_base=None):
+    from dddmr_navigation_b200.config import DD_SIMPLE_CRITICS, DD_SIMPLE_DEFAULT
+    g = copy.deepcopy(gen_base or DD_SIMPLE_DEFAULT)
+    g.update(gen_over or {})
+    return PlannerConfig(generator=g, critics=copy.deepcopy(critics if critics is not None else DD_SIMPLE_CRITICS))
+
+
+def _straight_plan(n=30, step=0.1, yaw=0.0, z=0.0, start=(-0.3, 0.0)):
+    q = synth.quat_from_rpy(0, 0, yaw)
+    return np.array([[start[0] + i * step * math.cos(yaw), start[1] + i * step * math.sin(yaw), z, *q] for i in range(n)])
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_random_small_scenes_dd(seed):
+    rng = np.random.default_rng(seed)
+    cfg = _cfg({"linear_x_sample": 7.0, "angular_z_sample": 9.0, "sim_time": float(rng.uniform(1.0, 3.0))})
+    cloud = synth.small_scene(seed)
+    yaw = float(rng.uniform(-3.1, 3.1))
+    pose = [float(rng.uniform(-0.3, 0.3)), float(rng.uniform(-0.3, 0.3)), 0.0, *synth.quat_from_rpy(0.02, -0.03, yaw)]
+    twist = [float(rng.uniform(0.0, 1.0)), 0.0, float(rng.uniform(-0.5, 0.5))]
+    gpu, ora = _pair(cfg)
+    r_g, r_o = run_pair(gpu, ora, cloud, _straight_plan(yaw=yaw), pose, twist)
+    _full_compare(gpu, ora, r_g, r_o)
+
+
+def test_big_cuboid_radius_filter_matters():
+    # corners of the 1.2 x 0.8 x 1.0 footprint are > 1 m from base_link: points inside the cuboid but with
+    # d^2 >= 1 must NOT collide (collision_model.cpp:122)
+    cfg = _cfg({"cuboid": synth.big_cuboid(), "linear_x_sample": 6.0, "angular_z_sample": 8.0, "sim_time": 2.0})
+    cloud = synth.small_scene(11, n_points=6000, extent=3.0)
+    gpu, ora = _pair(cfg)
+    r_g, r_o = run_pair(gpu, ora, cloud, _straight_plan(), [0, 0, 0, 0, 0, 0, 1], [0.8, 0, 0.1])
+    _full_compare(gpu, ora, r_g, r_o, n_pose_trajs=10)
+
+
+def test_collision_min_max_and_reordered_stack():
+    critics = [
+        {"plugin": "mpc_critics::StickPathModel", "weight": 0.1},
+        {"plugin": "mpc_critics::CollisionMinMaxModel", "weight": 1.0},
+        {"plugin": "mpc_critics::TwirlingModel", "weight": 0.3},
+        {"plugin": "mpc_critics::CollisionModel", "weight": 1.0},
+        {"plugin": "mpc_critics::TowardGlobalPlanModel", "weight": 2.0},
+        {"plugin": "mpc_critics::ShortestAngleModel", "weight": 0.5},
+        {"plugin": "mpc_critics::PurePursuitModel", "translation_weight": 0.7, "orientation_weight": 0.2},
+    ]
+    cfg = _cfg({"linear_x_sample": 5.0, "angular_z_sample": 7.0}, critics)
+    cloud = synth.small_scene(5, n_points=4000, extent=3.0)
+    gpu, ora = _pair(cfg)
+    r_g, r_o = run_pair(gpu, ora, cloud, _straight_plan(), [0, 0, 0, 0, 0, 0, 1], [0.5, 0, -0.1], heading_dev=-0.4)
+    _full_compare(gpu, ora, r_g, r_o, n_pose_trajs=8)
+
+
+def test_edge_cases_cloud_and_plan_sizes():
+    cfg = _cfg({"linear_x_sample": 4.0, "angular_z_sample": 5.0})
+    gpu, ora = _pair(cfg)
+    four = synth.to_xyzi(np.array([[0.5, 0, 0.2]] * 4, np.float32))       # < 5 points: collision critic returns 0
+    five = synth.to_xyzi(np.array([[0.5, 0, 0.2]] * 5, np.float32))
+    nanpts = synth.to_xyzi(np.array([[np.nan, 0, 0.2]] * 3 + [[5, 5, 5]] * 3, np.float32))
+    for cloud in (four, five, nanpts, synth.to_xyzi(np.zeros((0, 3), np.float32))):
+        for plan in (_straight_plan(), _straight_plan(n=2), np.zeros((0, 7))):   # plan < 3 -> 10.0; empty -> -4
+            r_g, r_o = run_pair(gpu, ora, cloud, plan, [0, 0, 0, 0, 0, 0, 1], [0.3, 0, 0.0])
+            _full_compare(gpu, ora, r_g, r_o, n_pose_trajs=3)
+    assert r_o.best_id == -1  # empty plan: pure pursuit rejects everything (pure_pursuit_model.cpp:62-64)
+
+
+def test_speed_override_motor_constraint_and_degenerate_window():
+    cfg = _cfg({"linear_x_sample": 6.0, "angular_z_sample": 6.0, "use_motor_constraint": True, "gear_ratio": 30.0,
+                "max_motor_shaft_rpm": 2500.0})
+    gpu, ora = _pair(cfg)
+    cloud = synth.small_scene(7)
+    for twist, ov in (([0.9, 0, 0.2], 0.3), ([0.02, 0, 0.0], -1.0), ([0.5, 0, -0.55], 0.45)):
+        r_g, r_o = run_pair(gpu, ora, cloud, _straight_plan(), [0, 0, 0, 0, 0, 0, 1], twist, max_speed=ov)
+        _full_compare(gpu, ora, r_g, r_o, n_pose_trajs=4)
+
+
+def test_omni_theory():
+    cfg = PlannerConfig(generator=copy.deepcopy(OMNI_SIMPLE_DEFAULT), critics=copy.deepcopy(OMNI_SIMPLE_CRITICS))
+    gpu, ora = _pair(cfg)
+    cloud = synth.small_scene(9, n_points=4000)
+    r_g, r_o = run_pair(gpu, ora, cloud, _straight_plan(), [0.1, -0.1, 0, *synth.quat_from_rpy(0, 0, 0.4)], [0.3, 0.1, 0.1])
+    assert r_o.n_traj > 100
+    _full_compare(gpu, ora, r_g, r_o, n_pose_trajs=8)
+
+
+def test_rotate_inplace_theory():
+    cfg = PlannerConfig(generator=copy.deepcopy(DD_ROTATE_INPLACE_DEFAULT), critics=copy.deepcopy(ROTATE_CRITICS))
+    gpu, ora = _pair(cfg)
+    cloud = synth.small_scene(13, n_points=2000, extent=1.5)
+    for hd in (0.5, -0.5):
+        r_g, r_o = run_pair(gpu, ora, cloud, _straight_plan(), [0, 0, 0, 0, 0, 0, 1], [0.0, 0, 0.0], heading_dev=hd)
+        assert r_o.n_traj == 2 and r_o.n_poses == 2 * 126
+        _full_compare(gpu, ora, r_g, r_o, n_pose_trajs=2)
+
+
+def test_tie_goes_to_last_index():
+    # no cloud, no plan-dependent critics: symmetric +-w samples cost the same; `<=` keeps the LAST (local_planner.cpp:460)
+    cfg = _cfg({"linear_x_sample": 3.0, "angular_z_sample": 4.0}, [{"plugin": "mpc_critics::TwirlingModel", "weight": 1.0}])
+    gpu, ora = _pair(cfg)
+    r_g, r_o = run_pair(gpu, ora, synth.to_xyzi(np.zeros((0, 3), np.float32)), _straight_plan(), [0, 0, 0, 0, 0, 0, 1], [0.5, 0, 0.0])
+    t = ora.read_trajectories()
+    zero_w = np.where(t["cost"] == t["cost"].min())[0]
+    assert len(zero_w) > 1 and r_o.best_id == zero_w[-1]
+    _full_compare(gpu, ora, r_g, r_o)
+
+
+def test_reference_named_surface():
+    sc = synth.playground()
+    lp = Local_Planner(sc.config)
+    lp.setObservation(sc.cloud)
+    lp.setPlan(sc.plan)
+    lp.setRobotState(sc.pose, sc.twist)
+    state, best = lp.computeVelocityCommand("differential_drive_simple")
+    assert state == PlannerState.TRAJECTORY_FOUND and best.id == 51 and best.xv_ == 0.5
+    lp.setPlan(np.zeros((0, 7)))
+    state, best = lp.computeVelocityCommand("differential_drive_simple")
+    assert state == PlannerState.ALL_TRAJECTORIES_FAIL and best.cost_ == -1.0
+
+
+def test_sample_shard_union_equals_whole():
+    sc = synth.c1_ramp()
+    gpu, ora = _pair(sc.config)
+    r_g, r_o = run_pair(gpu, ora, sc.cloud, sc.plan, sc.pose, sc.twist)
+    whole = gpu.read_trajectories()
+    for count in (2, 3, 8):
+        best = (None, -1)
+        cost = np.full(r_o.n_traj, np.nan)
+        n_poses = n_traj = 0
+        for rank in range(count):
+            r = gpu.plan_shard(make_query(sc.pose, sc.twist), rank, count)
+            n_g, b, e = gpu.traj_count()
+            assert n_g == r_o.n_traj
+            t = gpu.read_trajectories()
+            cost[b:e] = t["cost"][b:e]
+            assert np.all(np.isnan(t["cost"][:b])) and np.all(np.isnan(t["cost"][e:]))
+            n_poses += r.n_poses
+            n_traj += r.n_traj
+            if r.best_id >= 0 and (best[0] is None or r.best_cost < best[0] or (r.best_cost == best[0] and r.best_id > best[1])):
+                best = (r.best_cost, r.best_id)
+        assert n_poses == r_o.n_poses and n_traj == r_o.n_traj
+        assert_same_array(cost, whole["cost"], f"shard x{count} cost")
+        assert best[1] == r_o.best_id and best[0] == r_o.best_cost
+
+
+def test_fleet_batch_equals_individual_plans():
+    sc = synth.c1_ramp(n_points=50_000)
+    cfg = sc.config
+    gpu = LocalPlanner(cfg)
+    gpu.set_cloud(sc.cloud)
+    n = 12
+    poses, twists, plans, offs = synth.fleet_queries(n, region=(2.0, 20.0, -6.0, 6.0))
+    qs = (abi.Query * n)()
+    for i in range(n):
+        qs[i] = make_query(poses[i], twists[i])
+    res = gpu.plan_batch(qs, plans, offs)
+    batch = [(res[i].as_dict(), gpu.read_trajectories(i)) for i in range(n)]
+    ora = O.OraclePlanner(cfg)
+    ora.set_cloud(sc.cloud)
+    for i in range(n):
+        ora.set_plan(plans[offs[i]:offs[i + 1]])
+        r_o = ora.plan(qs[i])
+        assert batch[i][0] == r_o.as_dict(), f"robot {i}"
+        assert_trajectories_equal(batch[i][1], ora.read_trajectories())
+
+
+def test_c2_full_size_properties_and_sampled_oracle():
+    """BASELINE config C2 at full size (16.5 k trajectories, 2 M points): size-independent properties on the
+    whole result + exact comparison with the oracle on every 64th sample."""
+    sc = synth.c2_dense()
+    gpu = LocalPlanner(sc.config)
+    gpu.set_cloud(sc.cloud)
+    gpu.set_plan(sc.plan)
+    q = make_query(sc.pose, sc.twist)
+    r = gpu.plan(q)
+    t = gpu.read_trajectories()
+    assert r.n_samples == 128 * 129 and r.n_traj == len(t["cost"])
+    assert r.n_poses == int(t["num_steps"].sum())
+    assert r.n_collided == int((t["first_hit_pose"] >= 0).sum())
+    assert r.best_id == reference_argmin(t["cost"]) and r.best_cost == t["cost"][r.best_id]
+    # idempotence: a second cycle on the same inputs returns the same bits
+    r2 = gpu.plan(q)
+    assert r2.as_dict() == r.as_dict()
+    assert_same_array(gpu.read_trajectories()["cost"], t["cost"], "second cycle cost")
+    stride = 64
+    ora = O.OraclePlanner(sc.config)
+    ora.set_cloud(sc.cloud)
+    ora.set_plan(sc.plan)
+    ora.set_sample_stride(stride)
+    ora.plan(q, n_threads=8)
+    to = ora.read_trajectories()
+    sel = to["sample_index"]
+    lut = {int(s): i for i, s in enumerate(t["sample_index"])}
+    idx = np.array([lut[int(s)] for s in sel])
+    for k in ("num_steps", "time_delta", "cost", "first_hit_pose", "critic_scores", "vel"):
+        assert_same_array(t[k][idx], to[k], f"C2 sampled {k}")
+    grid = gpu.grid_info()
+    assert grid["n_points_kept"] == 2_000_000
