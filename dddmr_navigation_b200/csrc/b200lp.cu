@@ -116,6 +116,7 @@ struct b200lp_ctx {
 
   // timing of the last call
   float ms_upload = 0.f, ms_grid = 0.f, ms_plan = 0.f, ms_readback = 0.f;
+  float ms_k_prep = 0.f, ms_k_plan = 0.f;
 
   int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -304,6 +305,7 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   prep_kernel<<<(unsigned)n_robots, 1024, 0, ctx->stream>>>(ctx->C, ctx->d_robots.p, t_cap, rank, count, ctx->d_rec_vel.p,
                                                             ctx->d_rec_steps.p, ctx->d_rec_dt.p, ctx->d_rec_sample.p,
                                                             ctx->d_meta.p, ctx->d_plan7.p, ctx->d_plan_pts.p);
+  CK(cudaEventRecord(ctx->ev[4], ctx->stream));
   plan_kernel<<<dim3(gx, (unsigned)n_robots), kThreads, 0, ctx->stream>>>(
       ctx->C, ctx->grid, ctx->d_robots.p, ctx->d_meta.p, t_cap, ctx->d_rec_vel.p, ctx->d_rec_steps.p, ctx->d_rec_dt.p,
       ctx->d_plan_pts.p, ctx->d_plan7.p, ctx->d_cost.p, ctx->d_scores.p, ctx->d_first_hit.p, ctx->d_partial.p,
@@ -326,6 +328,8 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   cudaEventElapsedTime(&ctx->ms_upload, ctx->ev[0], ctx->ev[1]);
   cudaEventElapsedTime(&ctx->ms_plan, ctx->ev[1], ctx->ev[2]);
   cudaEventElapsedTime(&ctx->ms_readback, ctx->ev[2], ctx->ev[3]);
+  cudaEventElapsedTime(&ctx->ms_k_prep, ctx->ev[1], ctx->ev[4]);
+  cudaEventElapsedTime(&ctx->ms_k_plan, ctx->ev[4], ctx->ev[2]);
   return B200LP_OK;
 }
 
@@ -606,6 +610,13 @@ int b200lp_last_timing(const b200lp_ctx* ctx, float* ms_upload, float* ms_grid_b
   if (ms_grid_build) *ms_grid_build = ctx->ms_grid;
   if (ms_plan_kernels) *ms_plan_kernels = ctx->ms_plan;
   if (ms_readback) *ms_readback = ctx->ms_readback;
+  return B200LP_OK;
+}
+
+int b200lp_last_kernel_ms(const b200lp_ctx* ctx, float* ms_prep_kernel, float* ms_plan_kernel) {
+  if (!ctx) return B200LP_E_INVALID;
+  if (ms_prep_kernel) *ms_prep_kernel = ctx->ms_k_prep;
+  if (ms_plan_kernel) *ms_plan_kernel = ctx->ms_k_plan;
   return B200LP_OK;
 }
 

@@ -172,6 +172,15 @@ class LocalPlanner:
         self.lib.b200lp_last_timing(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
         return {"ms_upload": a.value, "ms_grid_build": b.value, "ms_plan_kernels": c.value, "ms_readback": d.value}
 
+    def last_kernel_ms(self) -> dict:
+        a, b = C.c_float(), C.c_float()
+        self.lib.b200lp_last_kernel_ms(self.h, C.byref(a), C.byref(b))
+        return {"prep_kernel": a.value, "plan_kernel": b.value}
+
+    def set_cloud_ptr(self, host_ptr: int, n: int, stride: int):
+        """set_cloud from a raw host address (e.g. a pinned buffer)."""
+        self._ck(self.lib.b200lp_set_cloud(self.h, _P(host_ptr), n, stride))
+
     def launch_count(self) -> int:
         return int(self.lib.b200lp_launch_count(self.h))
 

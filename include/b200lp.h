@@ -209,6 +209,9 @@ int b200lp_count_radius(b200lp_ctx* ctx, int64_t* sum_n_r1, int64_t* n_poses);
  * CUDA events on ctx's stream. Any pointer may be NULL. */
 int b200lp_last_timing(const b200lp_ctx* ctx, float* ms_upload, float* ms_grid_build, float* ms_plan_kernels,
                        float* ms_readback);
+/* Per-kernel split of ms_plan_kernels for the last plan call: the sampling/trajectory-list kernel and the
+ * fused rollout+query+critics+argmin kernel (the one the roofline is reported for). */
+int b200lp_last_kernel_ms(const b200lp_ctx* ctx, float* ms_prep_kernel, float* ms_plan_kernel);
 /* Number of kernels this library launched on ctx's stream since creation. */
 int64_t b200lp_launch_count(const b200lp_ctx* ctx);
 /* Grid geometry of the current cloud (for tests / docs). dims = nx,ny,nz; origin xyz; cell xy,z. */

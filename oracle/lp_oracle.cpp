@@ -807,9 +807,9 @@ int lporacle_plan(lporacle_ctx* c, const b200lp_query* q, int n_threads, b200lp_
     for (int k = 0; k < n_threads; ++k)
       th.emplace_back([&]() {
         for (;;) {
-          const size_t b = next.fetch_add(16);
+          const size_t b = next.fetch_add(2);
           if (b >= c->trajs.size()) break;
-          for (size_t i = b; i < std::min(b + 16, c->trajs.size()); ++i) score_trajectory(*c, c->trajs[i]);
+          for (size_t i = b; i < std::min(b + 2, c->trajs.size()); ++i) score_trajectory(*c, c->trajs[i]);
         }
       });
     for (auto& x : th) x.join();
