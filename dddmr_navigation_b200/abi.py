@@ -1,7 +1,7 @@
 """ctypes mirror of include/b200lp.h (the C ABI) and the loader of libb200lp.so.
 
 The structs here are the single Python definition of the ABI's POD types; the CPU oracle's wrapper
-(oracle/lporacle.py, test infrastructure) reuses them so tests hand both sides the same bytes.
+(test infrastructure, under oracle/) reuses them so tests hand both sides the same bytes.
 
 There is no CPU fallback: :func:`load_library` raises if the CUDA library has not been built.
 """

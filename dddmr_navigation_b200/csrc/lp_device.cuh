@@ -1,7 +1,7 @@
 // lp_device.cuh — device-side building blocks of the rollout-and-score path (sm_100a).
 //
 // Arithmetic contract: this translation unit is compiled with -fmad=false; every float/double
-// expression below evaluates exactly like the CPU oracle's (oracle/lp_oracle.cpp), which restates the
+// expression below evaluates exactly like the CPU oracle's (test infrastructure under oracle/), which restates the
 // reference. The ONLY fused multiply-adds are the explicit __fmaf_rn calls of the conservative
 // pre-test in sweep_points(), whose outcome is re-decided by the exact test before it can matter.
 #pragma once

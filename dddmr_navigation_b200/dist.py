@@ -1,0 +1,62 @@
+"""Multi-GPU plumbing of the path: one process per GPU, torch.distributed for the exchange.
+
+Two shardings exist and only one of them has a collective:
+
+* sample sharding (BASELINE config C4): every rank scores the contiguous slice of the velocity-sample grid that
+  ``b200lp_plan_shard(rank, count)`` selects and owns a local best ``(cost, global trajectory id)``. The global
+  best is found with ONE small all-reduce: a zero-initialised int64 vector of 2*W entries in which rank r fills
+  only slots [2r, 2r+1] with (bit pattern of its cost, id); the sum over ranks is an exact all-gather of 16 B per
+  rank. Every rank then applies the reference's rule — minimum cost, ties to the LARGEST id
+  (local_planner.cpp:460 keeps the last trajectory with `<=`) — so all ranks agree without a second exchange.
+* fleet sharding (config C5): robots are independent, ranks own disjoint robot ranges, no collective.
+"""
+from __future__ import annotations
+
+import struct
+
+NONE_BITS = (1 << 63) - 1  # "no feasible trajectory": larger than the bits of any cost <= 9999999
+
+
+def cost_to_bits(cost: float, best_id: int) -> int:
+    """Non-negative doubles order like their bit patterns (sign bit clear), so int64 compares are exact."""
+    if best_id < 0 or not (cost >= 0.0):
+        return NONE_BITS
+    return struct.unpack("<q", struct.pack("<d", float(cost)))[0]
+
+
+def bits_to_cost(bits: int) -> float:
+    return struct.unpack("<d", struct.pack("<q", int(bits)))[0]
+
+
+def pick_best(pairs):
+    """pairs: iterable of (cost_bits, id). Reference rule: min cost, ties -> largest id. -> (cost, id) or (-1.0, -1)."""
+    best_bits, best_id = NONE_BITS, -1
+    for bits, tid in pairs:
+        if bits == NONE_BITS or tid < 0:
+            continue
+        if bits < best_bits or (bits == best_bits and tid > best_id):
+            best_bits, best_id = int(bits), int(tid)
+    if best_id < 0:
+        return -1.0, -1
+    return bits_to_cost(best_bits), best_id
+
+
+def allreduce_best(local_cost: float, local_id: int, device=None, group=None):
+    """The single collective of the sample-sharded path. Works on NCCL (CUDA tensors) and gloo (CPU tensors)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    buf = torch.zeros(2 * world, dtype=torch.int64, device=device)
+    buf[2 * rank] = cost_to_bits(local_cost, local_id)
+    buf[2 * rank + 1] = int(local_id)
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    vals = buf.cpu().tolist()
+    return pick_best((vals[2 * r], vals[2 * r + 1]) for r in range(world))
+
+
+def shard_range(n: int, rank: int, count: int):
+    """[lo, hi) of n units for shard `rank` of `count` — the same split b200lp_plan_shard applies to the sample grid
+    and the one fleet sharding applies to robots."""
+    return n * rank // count, n * (rank + 1) // count
