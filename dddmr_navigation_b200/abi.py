@@ -110,6 +110,8 @@ SYMBOLS = {
     "b200lp_traj_count": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "b200lp_read_trajectories": (C.c_int, [_P, C.c_size_t, C.POINTER(TrajView)]),
     "b200lp_read_poses": (C.c_int, [_P, C.c_size_t, C.c_int32, C.POINTER(PoseView)]),
+    "b200lp_read_pose_batch": (C.c_int, [_P, C.c_size_t, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(PoseView),
+                                         C.c_size_t]),
     "b200lp_count_radius": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "b200lp_last_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
                                      C.POINTER(C.c_float)]),

@@ -109,6 +109,34 @@ class PlannerConfig:
                 critics.append(d)
         return cls(generator=gen, critics=critics)
 
+    def to_ros_yaml(self, generator_name: str = "differential_drive_simple") -> str:
+        """The same configuration as the text of a ROS 2 params file in the reference's layout (two nodes,
+        `trajectory_generators` and `mpc_critics`) — what the C++ host layer's plugin loaders read."""
+        def scalar(v):
+            if isinstance(v, bool):
+                return "true" if v else "false"
+            if isinstance(v, str):
+                return f'"{v}"'
+            return repr(float(v))
+        out = ["trajectory_generators:", "  ros__parameters:", f'    plugins: ["{generator_name}"]', f"    {generator_name}:"]
+        for k, v in self.generator.items():
+            if k == "cuboid":
+                out.append("      cuboid:")
+                for name, xyz in v.items():
+                    out.append(f"        {name}: [{', '.join(repr(float(c)) for c in xyz)}]")
+            else:
+                out.append(f"      {k}: {scalar(v)}")
+        names = [c.get("name", f"critic{i}") for i, c in enumerate(self.critics)]
+        out += ["", "mpc_critics:", "  ros__parameters:", "    plugins: [" + ", ".join(f'"{n}"' for n in names) + "]"]
+        for n, c in zip(names, self.critics):
+            out.append(f"    {n}:")
+            out.append(f'      plugin: "{c["plugin"]}"')
+            out.append(f"      trajectory_generator: {generator_name}")
+            for k, v in c.items():
+                if k not in ("name", "plugin", "trajectory_generator"):
+                    out.append(f"      {k}: {scalar(v)}")
+        return "\n".join(out) + "\n"
+
     # ---- conversion to ABI structs -----------------------------------------------------------
     def _g(self, key):
         return self.generator.get(key, _CODE_DEFAULTS[key])

@@ -106,6 +106,7 @@ struct b200lp_ctx {
   DevBuf<unsigned> d_block_counter;
   DevBuf<b200lp_result> d_results;
   DevBuf<unsigned long long> d_count;
+  DevBuf<char> d_scratch;
   PinBuf<RobotIn> h_robots;
   PinBuf<double> h_plan7;
   PinBuf<b200lp_result> h_results;
@@ -421,7 +422,7 @@ void b200lp_destroy(b200lp_ctx* ctx) {
   ctx->h_bounds.release(); ctx->d_robots.release(); ctx->d_meta.release(); ctx->d_plan7.release();
   ctx->d_plan_pts.release(); ctx->d_rec_vel.release(); ctx->d_rec_steps.release(); ctx->d_rec_sample.release();
   ctx->d_first_hit.release(); ctx->d_rec_dt.release(); ctx->d_cost.release(); ctx->d_scores.release();
-  ctx->d_partial.release(); ctx->d_block_counter.release(); ctx->d_results.release(); ctx->d_count.release();
+  ctx->d_partial.release(); ctx->d_block_counter.release(); ctx->d_results.release(); ctx->d_count.release(); ctx->d_scratch.release();
   ctx->h_robots.release(); ctx->h_plan7.release(); ctx->h_results.release(); ctx->h_meta.release();
   ctx->h_count.release();
   for (auto& ev : ctx->ev)
@@ -549,38 +550,59 @@ int b200lp_read_trajectories(b200lp_ctx* ctx, size_t robot, const b200lp_traj_vi
   return B200LP_OK;
 }
 
+int b200lp_read_pose_batch(b200lp_ctx* ctx, size_t robot, int32_t t0, int32_t t1, int64_t* pose_offsets,
+                           const b200lp_pose_view* v, size_t capacity_poses) {
+  if (!ctx) return B200LP_E_INVALID;
+  if (!v) return ctx->fail(B200LP_E_INVALID, "read_pose_batch: null view");
+  if (!ctx->have_cycle || robot >= ctx->n_robots) return ctx->fail(B200LP_E_STATE, "read_pose_batch: no plan result for that robot");
+  const RobotMeta& m = ctx->meta_host[robot];
+  if (t0 < 0 || t1 < t0 || t1 > m.n_traj) return ctx->fail(B200LP_E_INVALID, "read_pose_batch: trajectory range out of bounds");
+  const size_t nt = (size_t)(t1 - t0);
+  if (pose_offsets) pose_offsets[0] = 0;
+  if (!nt) return B200LP_OK;
+  CK(cudaSetDevice(ctx->device));
+  // exclusive prefix sum of num_steps -> output row of every trajectory
+  std::vector<int> steps(nt);
+  CK(cudaMemcpyAsync(steps.data(), ctx->d_rec_steps.p + robot * (size_t)ctx->t_cap + t0, nt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  std::vector<long long> off(nt + 1);
+  off[0] = 0;
+  for (size_t i = 0; i < nt; ++i) off[i + 1] = off[i] + steps[i];
+  const size_t n = (size_t)off[nt];
+  if (pose_offsets)
+    for (size_t i = 0; i <= nt; ++i) pose_offsets[i] = off[i];
+  if (n > capacity_poses) return ctx->fail(B200LP_E_INVALID, "read_pose_batch: %zu poses exceed the view capacity %zu", n, capacity_poses);
+  if (!n) return B200LP_OK;
+  // scratch layout in one allocation (8-byte fields first)
+  const size_t b_off = 0, b_pose = b_off + (nt + 1) * 8, b_pcl = b_pose + (v->pose ? n * 56 : 0),
+               b_cub = b_pcl + (v->pcl_pose ? n * 12 : 0), b_aabb = b_cub + (v->cuboid ? n * 96 : 0),
+               b_nr1 = b_aabb + (v->aabb ? n * 24 : 0), b_col = b_nr1 + (v->n_r1 ? n * 4 : 0),
+               total = b_col + (v->collide ? n : 0);
+  CK(ctx->d_scratch.reserve(total));
+  char* d = ctx->d_scratch.p;
+  CK(cudaMemcpyAsync(d + b_off, off.data(), (nt + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  poses_kernel<<<(unsigned)nt, 32, 0, ctx->stream>>>(
+      ctx->C, ctx->grid, ctx->d_robots.p, (int)robot, ctx->t_cap, t0, (const long long*)(d + b_off), ctx->d_rec_vel.p,
+      ctx->d_rec_steps.p, ctx->d_rec_dt.p, v->pose ? (double*)(d + b_pose) : nullptr, v->pcl_pose ? (float*)(d + b_pcl) : nullptr,
+      v->cuboid ? (float*)(d + b_cub) : nullptr, v->aabb ? (float*)(d + b_aabb) : nullptr,
+      v->collide ? (unsigned char*)(d + b_col) : nullptr, v->n_r1 ? (int*)(d + b_nr1) : nullptr);
+  ++ctx->launches;
+  if (v->pose) CK(cudaMemcpyAsync(v->pose, d + b_pose, n * 56, cudaMemcpyDeviceToHost, ctx->stream));
+  if (v->pcl_pose) CK(cudaMemcpyAsync(v->pcl_pose, d + b_pcl, n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+  if (v->cuboid) CK(cudaMemcpyAsync(v->cuboid, d + b_cub, n * 96, cudaMemcpyDeviceToHost, ctx->stream));
+  if (v->aabb) CK(cudaMemcpyAsync(v->aabb, d + b_aabb, n * 24, cudaMemcpyDeviceToHost, ctx->stream));
+  if (v->n_r1) CK(cudaMemcpyAsync(v->n_r1, d + b_nr1, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (v->collide) CK(cudaMemcpyAsync(v->collide, d + b_col, n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  return B200LP_OK;
+}
+
 int b200lp_read_poses(b200lp_ctx* ctx, size_t robot, int32_t id, const b200lp_pose_view* v) {
   if (!ctx) return B200LP_E_INVALID;
-  if (!v) return ctx->fail(B200LP_E_INVALID, "read_poses: null view");
   if (!ctx->have_cycle || robot >= ctx->n_robots) return ctx->fail(B200LP_E_STATE, "read_poses: no plan result for that robot");
-  const RobotMeta& m = ctx->meta_host[robot];
-  if (id < 0 || id >= m.n_traj) return ctx->fail(B200LP_E_INVALID, "read_poses: trajectory id out of range");
-  CK(cudaSetDevice(ctx->device));
-  int n = 0;
-  CK(cudaMemcpyAsync(&n, ctx->d_rec_steps.p + robot * (size_t)ctx->t_cap + id, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  // scratch layout in one allocation
-  const size_t b_pose = 0, b_pcl = b_pose + (size_t)n * 56, b_cub = b_pcl + (size_t)n * 12, b_aabb = b_cub + (size_t)n * 96,
-               b_nr1 = b_aabb + (size_t)n * 24, b_col = b_nr1 + (size_t)n * 4, total = b_col + (size_t)n;
-  char* d = nullptr;
-  CK(cudaMalloc((void**)&d, std::max<size_t>(total, 16)));
-  poses_kernel<<<1, 32, 0, ctx->stream>>>(ctx->C, ctx->grid, ctx->d_robots.p, (int)robot, ctx->t_cap, id, ctx->d_rec_vel.p,
-                                          ctx->d_rec_steps.p, ctx->d_rec_dt.p, (double*)(d + b_pose), (float*)(d + b_pcl),
-                                          (float*)(d + b_cub), (float*)(d + b_aabb), (unsigned char*)(d + b_col),
-                                          (int*)(d + b_nr1));
-  ++ctx->launches;
-  std::vector<char> h(std::max<size_t>(total, 16));
-  cudaError_t e = cudaMemcpyAsync(h.data(), d, total, cudaMemcpyDeviceToHost, ctx->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d);
-  if (e != cudaSuccess) return ctx->fail(B200LP_E_CUDA, "read_poses: %s", cudaGetErrorString(e));
-  if (v->pose) memcpy(v->pose, h.data() + b_pose, (size_t)n * 56);
-  if (v->pcl_pose) memcpy(v->pcl_pose, h.data() + b_pcl, (size_t)n * 12);
-  if (v->cuboid) memcpy(v->cuboid, h.data() + b_cub, (size_t)n * 96);
-  if (v->aabb) memcpy(v->aabb, h.data() + b_aabb, (size_t)n * 24);
-  if (v->n_r1) memcpy(v->n_r1, h.data() + b_nr1, (size_t)n * 4);
-  if (v->collide) memcpy(v->collide, h.data() + b_col, (size_t)n);
-  return B200LP_OK;
+  if (id < 0 || id >= ctx->meta_host[robot].n_traj) return ctx->fail(B200LP_E_INVALID, "read_poses: trajectory id out of range");
+  return b200lp_read_pose_batch(ctx, robot, id, id + 1, nullptr, v, (size_t)B200LP_MAX_STEPS);
 }
 
 int b200lp_count_radius(b200lp_ctx* ctx, int64_t* sum_n_r1, int64_t* n_poses) {

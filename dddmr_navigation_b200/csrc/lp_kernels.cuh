@@ -762,9 +762,11 @@ __device__ __forceinline__ void ball_scan(const GridDev& g, const float* stash, 
   *collide = hit;
 }
 
-// one warp recomputes one trajectory and writes every per-pose quantity the reference's Trajectory holds
+// one warp (= one CTA) recomputes one trajectory and writes every per-pose quantity the reference's
+// Trajectory holds; CTA b handles trajectory id0 + b and writes its poses at row pose_off[b]
 __global__ void __launch_bounds__(32) poses_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, int robot,
-                                                   int t_cap, int id, const float4* __restrict__ rec_vel,
+                                                   int t_cap, int id0, const long long* __restrict__ pose_off,
+                                                   const float4* __restrict__ rec_vel,
                                                    const int* __restrict__ rec_steps, const double* __restrict__ rec_dt,
                                                    double* __restrict__ o_pose, float* __restrict__ o_pcl,
                                                    float* __restrict__ o_cuboid, float* __restrict__ o_aabb,
@@ -772,6 +774,8 @@ __global__ void __launch_bounds__(32) poses_kernel(Consts C, GridDev g, const Ro
   __shared__ float stash[F_COUNT * 32];
   __shared__ double R0[9], t0[3];
   const int lane = threadIdx.x;
+  const int id = id0 + blockIdx.x;
+  const long long row0 = pose_off[blockIdx.x];
   const RobotIn& q = robots[robot];
   if (lane == 0) {
     quat_to_matrix(q.pose[3], q.pose[4], q.pose[5], q.pose[6], R0);
@@ -791,28 +795,35 @@ __global__ void __launch_bounds__(32) poses_kernel(Consts C, GridDev g, const Ro
   for (int base = 0; base < n; base += 32) {
     float px, py, pth;
     rollout32(carry, lane, C.par.theory, vel.x, vel.y, vel.z, dt, px, py, pth);
-    const int k = base + lane;
-    const bool live = k < n;
+    const bool live = base + lane < n;
+    const long long k = row0 + base + lane;
     double L[9], t[3];
     pose_affine(R0, t0, px, py, pth, L, t);
     float verts[24];
     pose_geometry(C, g, L, t, stash, lane, live, verts);
     __syncwarp();
     if (live) {
-      double qd[4];
-      matrix_to_quat(L, qd);  // tf2::eigenToTransform (dd_simple…cpp:434)
-      o_pose[k * 7 + 0] = t[0]; o_pose[k * 7 + 1] = t[1]; o_pose[k * 7 + 2] = t[2];
-      o_pose[k * 7 + 3] = qd[0]; o_pose[k * 7 + 4] = qd[1]; o_pose[k * 7 + 5] = qd[2]; o_pose[k * 7 + 6] = qd[3];
-      for (int a = 0; a < 3; ++a) {
-        o_pcl[k * 3 + a] = stash[(F_PX + a) * 32 + lane];
-        o_aabb[k * 6 + a] = stash[(F_MNX + a) * 32 + lane];
-        o_aabb[k * 6 + 3 + a] = stash[(F_MXX + a) * 32 + lane];
+      if (o_pose) {
+        double qd[4];
+        matrix_to_quat(L, qd);  // tf2::eigenToTransform (dd_simple…cpp:434)
+        o_pose[k * 7 + 0] = t[0]; o_pose[k * 7 + 1] = t[1]; o_pose[k * 7 + 2] = t[2];
+        o_pose[k * 7 + 3] = qd[0]; o_pose[k * 7 + 4] = qd[1]; o_pose[k * 7 + 5] = qd[2]; o_pose[k * 7 + 6] = qd[3];
       }
-      for (int j = 0; j < 24; ++j) o_cuboid[k * 24 + j] = verts[j];
-      int nr1 = 0, col = 0;
-      if (g.n_raw >= 5) ball_scan(g, stash, lane, mode, &nr1, &col);
-      o_nr1[k] = nr1;
-      o_collide[k] = (unsigned char)col;
+      for (int a = 0; a < 3; ++a) {
+        if (o_pcl) o_pcl[k * 3 + a] = stash[(F_PX + a) * 32 + lane];
+        if (o_aabb) {
+          o_aabb[k * 6 + a] = stash[(F_MNX + a) * 32 + lane];
+          o_aabb[k * 6 + 3 + a] = stash[(F_MXX + a) * 32 + lane];
+        }
+      }
+      if (o_cuboid)
+        for (int j = 0; j < 24; ++j) o_cuboid[k * 24 + j] = verts[j];
+      if (o_nr1 || o_collide) {
+        int nr1 = 0, col = 0;
+        if (g.n_raw >= 5) ball_scan(g, stash, lane, mode, &nr1, &col);
+        if (o_nr1) o_nr1[k] = nr1;
+        if (o_collide) o_collide[k] = (unsigned char)col;
+      }
     }
     __syncwarp();
   }

@@ -26,10 +26,10 @@ class PlannerState(enum.IntEnum):
     TF_FAIL = 0
     PRUNE_PLAN_FAIL = 1
     ALL_TRAJECTORIES_FAIL = 2
-    TRAJECTORY_FOUND = 3
-    PATH_BLOCKED_WAIT = 4
-    PATH_BLOCKED_REPLANNING = 5
-    PERCEPTION_MALFUNCTION = 6
+    PERCEPTION_MALFUNCTION = 3
+    TRAJECTORY_FOUND = 4
+    PATH_BLOCKED_WAIT = 5
+    PATH_BLOCKED_REPLANNING = 6
 
 
 @dataclass
@@ -160,6 +160,29 @@ class LocalPlanner:
         }
         v = abi.PoseView(*[d[k].ctypes.data_as(t) for k, t in abi.PoseView._fields_])
         self._ck(self.lib.b200lp_read_poses(self.h, robot, traj_id, C.byref(v)))
+        return d
+
+    def read_pose_batch(self, t_begin: int = 0, t_end: int | None = None, robot: int = 0, fields=None) -> dict:
+        """Per-pose quantities of trajectories [t_begin, t_end) in one launch; "offsets" maps a trajectory to its rows."""
+        if t_end is None:
+            t_end = self.traj_count(robot)[0]
+        nt = t_end - t_begin
+        offs = np.zeros(nt + 1, np.int64)
+        empty = abi.PoseView()
+        rc = self.lib.b200lp_read_pose_batch(self.h, robot, t_begin, t_end, offs.ctypes.data_as(C.POINTER(C.c_int64)),
+                                             C.byref(empty), 0)
+        n = int(offs[-1])
+        if rc != 0 and n == 0:
+            self._ck(rc)
+        shapes = {"pose": ((n, 7), np.float64), "pcl_pose": ((n, 3), np.float32), "cuboid": ((n, 8, 3), np.float32),
+                  "aabb": ((n, 6), np.float32), "collide": ((n,), np.uint8), "n_r1": ((n,), np.int32)}
+        want = list(fields) if fields is not None else list(shapes)
+        d = {k: np.zeros(*shapes[k]) for k in want}
+        v = abi.PoseView(*[d[k].ctypes.data_as(t) if k in d and d[k].size else None for k, t in abi.PoseView._fields_])
+        if n:
+            self._ck(self.lib.b200lp_read_pose_batch(self.h, robot, t_begin, t_end, offs.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                     C.byref(v), n))
+        d["offsets"] = offs
         return d
 
     def count_radius(self):

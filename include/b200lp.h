@@ -200,6 +200,13 @@ int b200lp_plan_batch(b200lp_ctx* ctx, const b200lp_query* qs, size_t n_robots, 
 int b200lp_traj_count(const b200lp_ctx* ctx, size_t robot, int32_t* n_traj_global, int32_t* t_begin, int32_t* t_end);
 int b200lp_read_trajectories(b200lp_ctx* ctx, size_t robot, const b200lp_traj_view* view);
 int b200lp_read_poses(b200lp_ctx* ctx, size_t robot, int32_t traj_id, const b200lp_pose_view* view);
+/* The same for trajectories [t_begin, t_end) in ONE launch — what the generator adapters use to materialise
+ * base_trajectory::Trajectory objects for the reference's PoseArray publishers (local_planner.cpp:554,569).
+ * Trajectory t's poses occupy rows pose_offsets[t - t_begin] .. pose_offsets[t - t_begin + 1) of every view array;
+ * pose_offsets (t_end - t_begin + 1 entries, may be NULL) is written by the call. Fails with B200LP_E_INVALID when
+ * the range holds more than capacity_poses poses (pose_offsets is still filled, so the caller can size and retry). */
+int b200lp_read_pose_batch(b200lp_ctx* ctx, size_t robot, int32_t t_begin, int32_t t_end, int64_t* pose_offsets,
+                           const b200lp_pose_view* view, size_t capacity_poses);
 
 /* Roofline accounting helper: sum over all scored poses of the last plan call of
  * |{cloud points with float d^2 < 1.0 to the pose}| (the reference's radiusSearch candidate set). */

@@ -1,0 +1,150 @@
+"""The C++ host layer (dddmr_navigation_b200/host): the reference's plugin interfaces over the C ABI.
+
+tests/cpp/plugin_cycle drives a cycle exactly like Local_Planner::computeVelocityCommand (local_planner.cpp:482-621):
+Trajectory_Generators_ROS / MPC_Critics_ROS load the plugins named in a ROS params YAML, the generator hands out
+base_trajectory::Trajectory objects one at a time, StackedScoringModel sums the critics with its negative early-out
+and getBestTrajectory keeps the last minimum. The GPU tests compare everything that caller sees with the CPU oracle.
+"""
+from __future__ import annotations
+
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from dddmr_navigation_b200 import PlannerConfig, make_query, synth
+from dddmr_navigation_b200 import config as cfgmod
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "tests", "cpp", "plugin_cycle")
+
+
+@pytest.fixture(scope="module")
+def driver():
+    import __graft_entry__ as g
+    g.build_host()
+    assert os.path.exists(BIN)
+    return BIN
+
+
+def _write_case(tmp, cfg, gen, cloud, plan, pose, twist, max_speed=-1.0, heading_dev=0.0):
+    yaml = os.path.join(tmp, "params.yaml")
+    with open(yaml, "w") as f:
+        f.write(cfg.to_ros_yaml(gen))
+    cloud = np.ascontiguousarray(cloud, np.float32)
+    if cloud.shape[1] != 8:  # PointXYZI layout: x y z pad intensity pad pad pad
+        c8 = np.zeros((cloud.shape[0], 8), np.float32)
+        c8[:, :3] = cloud[:, :3]
+        c8[:, 3] = 1.0
+        cloud = c8
+    plan = np.ascontiguousarray(plan, np.float64).reshape(-1, 7)
+    sc = os.path.join(tmp, "scenario.bin")
+    with open(sc, "wb") as f:
+        f.write(struct.pack("<qq", cloud.shape[0], plan.shape[0]))
+        f.write(cloud.tobytes())
+        f.write(plan.tobytes())
+        f.write(np.asarray(list(pose) + list(twist) + [max_speed, heading_dev], np.float64).tobytes())
+    return yaml, sc
+
+
+def _run(driver, yaml, sc, prefix, gen, mode):
+    p = subprocess.run([driver, yaml, sc, prefix, gen, mode], capture_output=True, text=True, timeout=600)
+    return p
+
+
+def _load(prefix):
+    s = {}
+    for line in open(prefix + ".summary.txt"):
+        k, v = line.strip().split("=")
+        s[k] = float(v)
+    traj = np.fromfile(prefix + ".traj.f64", np.float64).reshape(-1, 6)
+    return s, traj, {"pose": np.fromfile(prefix + ".pose.f64", np.float64).reshape(-1, 7),
+                     "pcl_pose": np.fromfile(prefix + ".pcl.f32", np.float32).reshape(-1, 3),
+                     "cuboid": np.fromfile(prefix + ".cuboid.f32", np.float32).reshape(-1, 8, 3),
+                     "aabb": np.fromfile(prefix + ".aabb.f32", np.float32).reshape(-1, 6)}
+
+
+def test_host_layer_builds_and_fails_loudly_without_a_device(driver, tmp_path):
+    """No GPU here: the plugins load from the reference-format YAML, then the first cycle must raise b200lp::Error —
+    there is no CPU path behind the plugin interfaces."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    sc = synth.playground()
+    yaml, scb = _write_case(str(tmp_path), sc.config, "differential_drive_simple", sc.cloud, sc.plan, sc.pose, sc.twist)
+    p = _run(driver, yaml, scb, str(tmp_path / "out"), "differential_drive_simple", "early")
+    assert p.returncode == 10, (p.returncode, p.stderr)
+    assert "no usable CUDA device" in p.stderr and "no CPU fallback" in p.stderr
+
+
+def test_unknown_plugin_type_is_an_error(driver, tmp_path):
+    sc = synth.playground()
+    cfg = PlannerConfig(generator=dict(sc.config.generator, plugin="trajectory_generators::NoSuchTheory"), critics=sc.config.critics)
+    yaml, scb = _write_case(str(tmp_path), cfg, "g", sc.cloud, sc.plan, sc.pose, sc.twist)
+    p = _run(driver, yaml, scb, str(tmp_path / "out"), "g", "early")
+    assert p.returncode == 11 and "no plugin registered" in p.stderr
+
+
+def _variant(generator, critics, twist, n_points=4000, seed=11):
+    """small random scene around the origin with another generator / critic stack"""
+    import copy
+    import dataclasses
+    sc = synth.playground()
+    cfg = PlannerConfig(generator=copy.deepcopy(generator), critics=copy.deepcopy(critics))
+    cloud = synth.to_xyzi(synth.small_scene(seed, n_points)[:, :3])
+    return dataclasses.replace(sc, config=cfg, cloud=cloud, twist=list(twist))
+
+
+CASES = {
+    "playground": lambda: (synth.playground(), "differential_drive_simple", 0.0),
+    "c1_ramp_small": lambda: (synth.c1_ramp(n_points=20_000), "differential_drive_simple", 0.0),
+    "omni": lambda: (_variant(cfgmod.OMNI_SIMPLE_DEFAULT, cfgmod.OMNI_SIMPLE_CRITICS, (0.3, 0.1, 0.05)), "omni_drive_simple", 0.0),
+    "rotate_shortest": lambda: (_variant(cfgmod.DD_ROTATE_INPLACE_DEFAULT, cfgmod.ROTATE_CRITICS, (0.0, 0.0, 0.0)),
+                                "differential_drive_rotate_shortest_angle", -0.7),
+}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", sorted(CASES))
+@pytest.mark.parametrize("mode", ["early", "late"])
+def test_plugin_cycle_matches_oracle(driver, tmp_path, case, mode):
+    from oracle import lporacle as O
+    sc, gen, hdev = CASES[case]()
+    yaml, scb = _write_case(str(tmp_path), sc.config, gen, sc.cloud, sc.plan, sc.pose, sc.twist, -1.0, hdev)
+    prefix = str(tmp_path / "out")
+    p = _run(driver, yaml, scb, prefix, gen, mode)
+    assert p.returncode == 0, p.stderr
+    s, traj, poses = _load(prefix)
+
+    ora = O.OraclePlanner(sc.config, O.MATH_SHARED, O.INDEX_GRID)
+    ora.set_cloud(sc.cloud)
+    ora.set_plan(sc.plan)
+    r = ora.plan(make_query(sc.pose, sc.twist, -1.0, hdev))
+    t = ora.read_trajectories()
+
+    # what the reference caller sees: list length, per-trajectory velocities / time_delta / summed cost, best pick
+    assert int(s["n_traj"]) == r.n_traj == traj.shape[0]
+    assert np.array_equal(traj[:, 0], t["cost"])                       # StackedScoringModel sum, bit for bit
+    assert np.array_equal(traj[:, 1], t["vel"][:, 0].astype(np.float64))
+    assert np.array_equal(traj[:, 3], t["vel"][:, 2].astype(np.float64))
+    assert np.array_equal(traj[:, 4], t["time_delta"])
+    assert np.array_equal(traj[:, 5].astype(np.int32), t["num_steps"])
+    assert int(s["best_id"]) == r.best_id == int(s["device_best_id"]) == int(s["best_id2"])
+    assert int(s["state"]) == int(s["state2"]) == (4 if r.best_id >= 0 else 2)  # TRAJECTORY_FOUND / ALL_TRAJECTORIES_FAIL
+    if r.best_id >= 0:
+        assert s["best_cost"] == r.best_cost and s["best_xv"] == r.xv and s["best_thetav"] == r.thetav
+    # the patched caller needs one launch per cycle; the unpatched one re-launches when the critics bring the cloud
+    # (a heading deviation first seen through the critics' shared data costs the first cycle one re-launch)
+    assert int(s["launches_first"]) == (1 if mode == "early" and hdev == 0.0 else 2)
+    assert int(s["launches_second"]) == (1 if mode == "early" else 2)
+
+    # every pose / cuboid / AABB the Trajectory objects hold
+    off = np.concatenate([[0], np.cumsum(t["num_steps"])])
+    assert poses["pose"].shape[0] == off[-1]
+    for tid in range(r.n_traj):
+        po = ora.read_poses(tid, int(t["num_steps"][tid]))
+        a, b = off[tid], off[tid + 1]
+        for k in ("pose", "pcl_pose", "cuboid", "aabb"):
+            assert np.array_equal(poses[k][a:b], po[k]), (case, tid, k)
