@@ -70,7 +70,7 @@ struct PinBuf {
 struct b200lp_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::string err;
   Consts C{};
   b200lp_grid_config gcfg{};
@@ -102,8 +102,11 @@ struct b200lp_ctx {
   DevBuf<float4> d_rec_vel;
   DevBuf<int> d_rec_steps, d_rec_sample, d_first_hit;
   DevBuf<double> d_rec_dt, d_cost, d_scores;
-  DevBuf<BlockBest> d_partial;
-  DevBuf<unsigned> d_block_counter;
+  DevBuf<unsigned> d_tickets;            // prep_kernel chunk tickets, one per robot (self-resetting)
+  DevBuf<PrepAgg> d_aggs;                // prep_kernel look-back aggregates
+  DevBuf<unsigned long long> d_work;     // plan_kernel work counter (reset by argmin_kernel)
+  unsigned epoch = 0;                    // launch number, the "published" flag value of d_aggs
+  int plan_ctas_per_sm = 0, sm_count = 0;
   DevBuf<b200lp_result> d_results;
   DevBuf<unsigned long long> d_count;
   DevBuf<char> d_scratch;
@@ -117,7 +120,7 @@ struct b200lp_ctx {
 
   // timing of the last call
   float ms_upload = 0.f, ms_grid = 0.f, ms_plan = 0.f, ms_readback = 0.f;
-  float ms_k_prep = 0.f, ms_k_plan = 0.f;
+  float ms_k_prep = 0.f, ms_k_plan = 0.f, ms_k_argmin = 0.f;
 
   int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -269,7 +272,9 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   size_t plan_total = 0;
   for (size_t i = 0; i < n_robots; ++i) plan_total = std::max<size_t>(plan_total, ctx->h_robots.p[i].plan_off + ctx->h_robots.p[i].plan_n);
   const int nc = std::max(1, ctx->C.n_critics);
-  const int gx = (t_cap + kWarpsPerCta - 1) / kWarpsPerCta;
+  const int n_chunks = (t_cap + kPrepThreads - 1) / kPrepThreads;
+  // upper bound on the trajectories of one robot inside one sample shard
+  const int cap_local = (int)std::min<long long>(t_cap, ((long long)t_cap + count - 1) / count + 1);
   CK(ctx->d_robots.reserve(n_robots));
   CK(ctx->d_meta.reserve(n_robots));
   CK(ctx->d_plan7.reserve(std::max<size_t>(plan_total * 7, 7)));
@@ -281,13 +286,26 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   CK(ctx->d_rec_dt.reserve(T));
   CK(ctx->d_cost.reserve(T));
   CK(ctx->d_scores.reserve(T * nc));
-  CK(ctx->d_partial.reserve(n_robots * gx));
   CK(ctx->d_results.reserve(n_robots));
   CK(ctx->h_results.reserve(n_robots));
   CK(ctx->h_meta.reserve(n_robots));
-  if (ctx->d_block_counter.cap < n_robots) {
-    CK(ctx->d_block_counter.reserve(n_robots));
-    CK(cudaMemsetAsync(ctx->d_block_counter.p, 0, ctx->d_block_counter.cap * sizeof(unsigned), ctx->stream));
+  if (ctx->d_tickets.cap < n_robots) {
+    CK(ctx->d_tickets.reserve(n_robots));
+    CK(cudaMemsetAsync(ctx->d_tickets.p, 0, ctx->d_tickets.cap * sizeof(unsigned), ctx->stream));
+  }
+  if (ctx->d_aggs.cap < n_robots * (size_t)n_chunks) {
+    CK(ctx->d_aggs.reserve(n_robots * (size_t)n_chunks));
+    CK(cudaMemsetAsync(ctx->d_aggs.p, 0, ctx->d_aggs.cap * sizeof(PrepAgg), ctx->stream));
+    ctx->epoch = 0;
+  }
+  if (!ctx->d_work.p) {
+    CK(ctx->d_work.reserve(1));
+    CK(cudaMemsetAsync(ctx->d_work.p, 0, sizeof(unsigned long long), ctx->stream));
+  }
+  if (!ctx->plan_ctas_per_sm) {
+    ctx->sm_count = sm_count_of(ctx->device);
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->plan_ctas_per_sm, plan_kernel, kThreads, 0));
+    if (ctx->plan_ctas_per_sm < 1) return ctx->fail(B200LP_E_CUDA, "plan_kernel does not fit on an SM");
   }
   if (!ctx->have_cloud) {  // no cloud yet: an empty one (collision critics return 0.0, size() < 5)
     int rc = build_grid(ctx, 0, 16);
@@ -297,21 +315,31 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   ctx->t_cap = t_cap;
   ctx->shard_rank = rank;
   ctx->shard_count = count;
+  if (++ctx->epoch == 0u) ctx->epoch = 1u;
+
+  const unsigned long long work = (unsigned long long)n_robots * (unsigned long long)cap_local;
+  const unsigned plan_grid = (unsigned)std::max<unsigned long long>(
+      1ull, std::min<unsigned long long>((work + kWarpsPerCta - 1) / kWarpsPerCta,
+                                         (unsigned long long)ctx->sm_count * ctx->plan_ctas_per_sm));
 
   CK(cudaEventRecord(ctx->ev[0], ctx->stream));
   CK(cudaMemcpyAsync(ctx->d_robots.p, ctx->h_robots.p, n_robots * sizeof(RobotIn), cudaMemcpyHostToDevice, ctx->stream));
   if (plan_total)
     CK(cudaMemcpyAsync(ctx->d_plan7.p, ctx->h_plan7.p, plan_total * 7 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-  prep_kernel<<<(unsigned)n_robots, 1024, 0, ctx->stream>>>(ctx->C, ctx->d_robots.p, t_cap, rank, count, ctx->d_rec_vel.p,
-                                                            ctx->d_rec_steps.p, ctx->d_rec_dt.p, ctx->d_rec_sample.p,
-                                                            ctx->d_meta.p, ctx->d_plan7.p, ctx->d_plan_pts.p);
+  prep_kernel<<<dim3((unsigned)n_chunks, (unsigned)n_robots), kPrepThreads, 0, ctx->stream>>>(
+      ctx->C, ctx->d_robots.p, t_cap, rank, count, ctx->epoch, ctx->d_tickets.p, ctx->d_aggs.p, ctx->d_rec_vel.p,
+      ctx->d_rec_steps.p, ctx->d_rec_dt.p, ctx->d_rec_sample.p, ctx->d_meta.p, ctx->d_plan7.p, ctx->d_plan_pts.p);
   CK(cudaEventRecord(ctx->ev[4], ctx->stream));
-  plan_kernel<<<dim3(gx, (unsigned)n_robots), kThreads, 0, ctx->stream>>>(
-      ctx->C, ctx->grid, ctx->d_robots.p, ctx->d_meta.p, t_cap, ctx->d_rec_vel.p, ctx->d_rec_steps.p, ctx->d_rec_dt.p,
-      ctx->d_plan_pts.p, ctx->d_plan7.p, ctx->d_cost.p, ctx->d_scores.p, ctx->d_first_hit.p, ctx->d_partial.p,
-      ctx->d_block_counter.p, ctx->d_results.p);
-  ctx->launches += 2;
+  plan_kernel<<<plan_grid, kThreads, 0, ctx->stream>>>(
+      ctx->C, ctx->grid, ctx->d_robots.p, ctx->d_meta.p, (int)n_robots, t_cap, cap_local, ctx->d_rec_vel.p,
+      ctx->d_rec_steps.p, ctx->d_rec_dt.p, ctx->d_plan_pts.p, ctx->d_plan7.p, ctx->d_cost.p, ctx->d_scores.p,
+      ctx->d_first_hit.p, ctx->d_work.p);
+  CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+  argmin_kernel<<<(unsigned)n_robots, kArgminThreads, 0, ctx->stream>>>(ctx->C, ctx->d_meta.p, t_cap, ctx->d_rec_vel.p,
+                                                                        ctx->d_cost.p, ctx->d_first_hit.p,
+                                                                        ctx->d_results.p, ctx->d_work.p);
+  ctx->launches += 3;
   CK(cudaEventRecord(ctx->ev[2], ctx->stream));
   CK(cudaMemcpyAsync(ctx->h_results.p, ctx->d_results.p, n_robots * sizeof(b200lp_result), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(ctx->h_meta.p, ctx->d_meta.p, n_robots * sizeof(RobotMeta), cudaMemcpyDeviceToHost, ctx->stream));
@@ -330,7 +358,8 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   cudaEventElapsedTime(&ctx->ms_plan, ctx->ev[1], ctx->ev[2]);
   cudaEventElapsedTime(&ctx->ms_readback, ctx->ev[2], ctx->ev[3]);
   cudaEventElapsedTime(&ctx->ms_k_prep, ctx->ev[1], ctx->ev[4]);
-  cudaEventElapsedTime(&ctx->ms_k_plan, ctx->ev[4], ctx->ev[2]);
+  cudaEventElapsedTime(&ctx->ms_k_plan, ctx->ev[4], ctx->ev[5]);
+  cudaEventElapsedTime(&ctx->ms_k_argmin, ctx->ev[5], ctx->ev[2]);
   return B200LP_OK;
 }
 
@@ -422,7 +451,7 @@ void b200lp_destroy(b200lp_ctx* ctx) {
   ctx->h_bounds.release(); ctx->d_robots.release(); ctx->d_meta.release(); ctx->d_plan7.release();
   ctx->d_plan_pts.release(); ctx->d_rec_vel.release(); ctx->d_rec_steps.release(); ctx->d_rec_sample.release();
   ctx->d_first_hit.release(); ctx->d_rec_dt.release(); ctx->d_cost.release(); ctx->d_scores.release();
-  ctx->d_partial.release(); ctx->d_block_counter.release(); ctx->d_results.release(); ctx->d_count.release(); ctx->d_scratch.release();
+  ctx->d_tickets.release(); ctx->d_aggs.release(); ctx->d_work.release(); ctx->d_results.release(); ctx->d_count.release(); ctx->d_scratch.release();
   ctx->h_robots.release(); ctx->h_plan7.release(); ctx->h_results.release(); ctx->h_meta.release();
   ctx->h_count.release();
   for (auto& ev : ctx->ev)

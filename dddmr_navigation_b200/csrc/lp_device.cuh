@@ -13,9 +13,10 @@
 
 namespace lp {
 
-constexpr int kWarpsPerCta = 8;
+constexpr int kWarpsPerCta = 4;
 constexpr int kThreads = kWarpsPerCta * 32;
 constexpr int kGroup = 4;       // consecutive poses swept against one candidate stream
+constexpr int kPreStride = 5;   // float4 per pose in the pre-test stash (4 used + 1 pad: conflict-free 80-byte stride)
 constexpr int kMaxAxis = 2048;  // cap on samples per velocity axis (incl. the inserted zero)
 constexpr int kPlanSmem = 256;  // prune-plan points staged in shared memory
 constexpr unsigned kFull = 0xffffffffu;
@@ -29,8 +30,13 @@ enum Field {
   F_HX, F_HY, F_HZ,                         // half extents (exactly representable in float)
   F_PX, F_PY, F_PZ,                         // Trajectory::getPCLPoint
   F_MNX, F_MNY, F_MNZ, F_MXX, F_MXY, F_MXZ, // Trajectory::getCuboidMinMax
-  F_LOX, F_LOY, F_LOZ, F_HIX, F_HIY, F_HIZ, // candidate box: (AABB +- margin) ∩ (pose +- (1+margin))
   F_COUNT
+};
+
+// Cell range of a pose's candidate box = (AABB +- margin) ∩ (pose +- (1+margin)), clamped to the grid.
+// Every point that can pass BOTH exact tests of that pose lies in these cells. Empty: x0 > x1.
+struct CellBox {
+  int x0, x1, y0, y1, z0, z1;
 };
 
 struct GridDev {
@@ -129,8 +135,9 @@ __device__ __forceinline__ double cof3(const double* m, int i, int j) {
 
 // PurePursuitModel::scoreTrajectory body (pure_pursuit_model.cpp:86-113) for a trajectory end pose given
 // as affine (L,t) and the plan end pose as affine (gL,gt).
-__device__ __noinline__ double pure_pursuit_value(const double* L, const double* t, const double* gL,
-                                                  const double* gt, double tw, double ow) {
+// Writes the translation distance and the wrapped yaw; the critic's value is tw * distance + ow * yaw.
+__device__ __noinline__ void pure_pursuit_terms(const double* L, const double* t, const double* gL, const double* gt,
+                                                double* distance_out, double* yaw_out) {
   // PoseStamped orientation = Quaterniond(L); the critic turns it back into a matrix
   double q[4];
   matrix_to_quat(L, q);
@@ -176,8 +183,8 @@ __device__ __noinline__ double pure_pursuit_value(const double* L, const double*
     const double r = lpm::fmod_pos(lpm::dabs(v), 3.1416);
     yaw = v < 0.0 ? -r : r;
   }
-  const double distance = lpm::dsqrt((dt[0] * dt[0] + dt[1] * dt[1]) + dt[2] * dt[2]);
-  return tw * distance + ow * yaw;
+  *distance_out = lpm::dsqrt((dt[0] * dt[0] + dt[1] * dt[1]) + dt[2] * dt[2]);
+  *yaw_out = yaw;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -270,10 +277,14 @@ __device__ __forceinline__ void pose_affine(const double* R0, const double* t0, 
   }
 }
 
-// Everything CollisionModel derives per pose from the transformed cuboid, written to the warp stash.
+// Everything CollisionModel derives per pose from the transformed cuboid, written to the warp stash:
+//  * stash (SoA [field][lane]): the reference's own quantities, read by the exact tests and the path critics;
+//  * pre (AoS, kPreStride float4 per lane, may be nullptr): coefficients of the conservative pre-test of
+//    sweep_points — (axis, -k) per box axis with k = fl(centre . axis), and the half extents rounded up by delta;
+//  * *cb (may be nullptr): the cell range of the pose's candidate box.
 __device__ __forceinline__ void pose_geometry(const Consts& C, const GridDev& g, const double* L, const double* t,
-                                              float* stash /* [F_COUNT][32] */, int lane, bool live,
-                                              float* verts_out /* optional 24 floats, may be nullptr */) {
+                                              float* stash /* [F_COUNT][32] */, float4* pre, CellBox* cb, int lane,
+                                              bool live, float* verts_out /* optional 24 floats, may be nullptr */) {
   float v[8][3];
   float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
   float mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
@@ -333,11 +344,51 @@ __device__ __forceinline__ void pose_geometry(const Consts& C, const GridDev& g,
   stash[F_PX * 32 + lane] = p[0]; stash[F_PY * 32 + lane] = p[1]; stash[F_PZ * 32 + lane] = p[2];
   stash[F_MNX * 32 + lane] = mn[0]; stash[F_MNY * 32 + lane] = mn[1]; stash[F_MNZ * 32 + lane] = mn[2];
   stash[F_MXX * 32 + lane] = mx[0]; stash[F_MXY * 32 + lane] = mx[1]; stash[F_MXZ * 32 + lane] = mx[2];
-  // candidate box: every point that can pass BOTH exact tests lies inside it
-  const float r = 1.0f + m;
-  stash[F_LOX * 32 + lane] = fmaxf(mn[0] - m, p[0] - r); stash[F_HIX * 32 + lane] = fminf(mx[0] + m, p[0] + r);
-  stash[F_LOY * 32 + lane] = fmaxf(mn[1] - m, p[1] - r); stash[F_HIY * 32 + lane] = fminf(mx[1] + m, p[1] + r);
-  stash[F_LOZ * 32 + lane] = fmaxf(mn[2] - m, p[2] - r); stash[F_HIZ * 32 + lane] = fminf(mx[2] + m, p[2] + r);
+  if (pre) {
+    const float delta = pretest_delta(g);
+    float hb[3];
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+      const float k = (float)(((double)c[0] * ax[e][0] + (double)c[1] * ax[e][1]) + (double)c[2] * ax[e][2]);
+      pre[lane * kPreStride + e] = make_float4(ax[e][0], ax[e][1], ax[e][2], -k);
+      hb[e] = (half[e] < 0.f) ? -1.0f : __fadd_ru(half[e], delta);
+    }
+    pre[lane * kPreStride + 3] = make_float4(hb[0], hb[1], hb[2], 0.f);
+  }
+  if (cb) {
+    // candidate box: every point that can pass BOTH exact tests lies inside it
+    const float r = 1.0f + m;
+    float lo[3], hi[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      lo[a] = fmaxf(mn[a] - m, p[a] - r);
+      hi[a] = fminf(mx[a] + m, p[a] + r);
+    }
+    const float fx0 = cell_f(lo[0], g.org[0], g.inv_xy), fx1 = cell_f(hi[0], g.org[0], g.inv_xy);
+    const float fy0 = cell_f(lo[1], g.org[1], g.inv_xy), fy1 = cell_f(hi[1], g.org[1], g.inv_xy);
+    const float fz0 = cell_f(lo[2], g.org[2], g.inv_z), fz1 = cell_f(hi[2], g.org[2], g.inv_z);
+    const bool empty = !(lo[0] <= hi[0] && lo[1] <= hi[1] && lo[2] <= hi[2]) || fx1 < 0.f || fy1 < 0.f || fz1 < 0.f ||
+                       fx0 > (float)(g.nx - 1) || fy0 > (float)(g.ny - 1) || fz0 > (float)(g.nz - 1) || g.n_kept == 0;
+    if (empty) {
+      cb->x0 = cb->y0 = cb->z0 = 0x7fffffff;
+      cb->x1 = cb->y1 = cb->z1 = -1;
+    } else {
+      cb->x0 = (int)fmaxf(fx0, 0.f); cb->x1 = (int)fminf(fx1, (float)(g.nx - 1));
+      cb->y0 = (int)fmaxf(fy0, 0.f); cb->y1 = (int)fminf(fy1, (float)(g.ny - 1));
+      cb->z0 = (int)fmaxf(fz0, 0.f); cb->z1 = (int)fminf(fz1, (float)(g.nz - 1));
+    }
+  }
+}
+
+// union of the cell boxes of each aligned group of kGroup lanes (empty boxes are neutral); every lane of a group
+// ends up with the group's box
+__device__ __forceinline__ void group_union(CellBox& b) {
+#pragma unroll
+  for (int o = 1; o < kGroup; o <<= 1) {
+    b.x0 = min(b.x0, __shfl_xor_sync(kFull, b.x0, o)); b.x1 = max(b.x1, __shfl_xor_sync(kFull, b.x1, o));
+    b.y0 = min(b.y0, __shfl_xor_sync(kFull, b.y0, o)); b.y1 = max(b.y1, __shfl_xor_sync(kFull, b.y1, o));
+    b.z0 = min(b.z0, __shfl_xor_sync(kFull, b.z0, o)); b.z1 = max(b.z1, __shfl_xor_sync(kFull, b.z1, o));
+  }
 }
 
 // exact tests, reference arithmetic ---------------------------------------------------------------
@@ -372,126 +423,90 @@ __device__ __forceinline__ bool exact_in_radius(const float* stash, int col, flo
 }
 
 // ---------------------------------------------------------------------------------------------
-// The obstacle query for kGroup consecutive poses (stash columns col0 .. col0+3).
-// Returns a 4-bit mask (warp-uniform): bit g set iff pose col0+g collides.
+// The obstacle query for kGroup consecutive poses (stash columns col0 .. col0+3) whose united cell box is `ub`
+// (warp-uniform). Returns a 4-bit mask (warp-uniform) whose LOWEST set bit g is exact: pose col0+g is the first
+// pose of the group that collides (higher bits may be missing once a lower pose is known to collide).
 //   minmax == false: CollisionModel; minmax == true: CollisionMinMaxModel.
-// Candidate set: the cell rows overlapping the union of the poses' candidate boxes. A row is the run
-// of x-adjacent cells [ix0, ix1] at fixed (iy, iz); cell-sorted storage makes it ONE contiguous range
-// of float4, which the warp streams with coalesced 512-byte loads.
+// Candidate set: the cell rows overlapping the box. A row is the run of x-adjacent cells [x0, x1] at fixed
+// (iy, iz); cell-sorted storage makes it ONE contiguous range of float4, which the warp streams with coalesced
+// 512-byte loads.
 // ---------------------------------------------------------------------------------------------
 template <bool kMinMax>
-__device__ __forceinline__ unsigned sweep_points(const GridDev& g, const float* stash, int col0, int lane) {
-  // union candidate box (dead lanes contribute an empty box)
-  float lo[3], hi[3];
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    lo[a] = 3.402823466e+38f;
-    hi[a] = -3.402823466e+38f;
-  }
-#pragma unroll
-  for (int q = 0; q < kGroup; ++q) {
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const float l = stash[(F_LOX + a) * 32 + col0 + q], h = stash[(F_HIX + a) * 32 + col0 + q];
-      if (l <= h) {
-        lo[a] = fminf(lo[a], l);
-        hi[a] = fmaxf(hi[a], h);
-      }
-    }
-  }
-  if (!(lo[0] <= hi[0] && lo[1] <= hi[1] && lo[2] <= hi[2])) return 0u;
-  // cell ranges; empty when the box misses the grid
-  const float fx0 = cell_f(lo[0], g.org[0], g.inv_xy), fx1 = cell_f(hi[0], g.org[0], g.inv_xy);
-  const float fy0 = cell_f(lo[1], g.org[1], g.inv_xy), fy1 = cell_f(hi[1], g.org[1], g.inv_xy);
-  const float fz0 = cell_f(lo[2], g.org[2], g.inv_z), fz1 = cell_f(hi[2], g.org[2], g.inv_z);
-  if (fx1 < 0.f || fy1 < 0.f || fz1 < 0.f || fx0 > (float)(g.nx - 1) || fy0 > (float)(g.ny - 1) ||
-      fz0 > (float)(g.nz - 1))
-    return 0u;
-  const int ix0 = (int)fmaxf(fx0, 0.f), ix1 = (int)fminf(fx1, (float)(g.nx - 1));
-  const int iy0 = (int)fmaxf(fy0, 0.f), iy1 = (int)fminf(fy1, (float)(g.ny - 1));
-  const int iz0 = (int)fmaxf(fz0, 0.f), iz1 = (int)fminf(fz1, (float)(g.nz - 1));
-  const int nyr = iy1 - iy0 + 1;
-  const int nrows = nyr * (iz1 - iz0 + 1);
+__device__ __forceinline__ unsigned sweep_points(const GridDev& g, const float* stash, const float4* pre, int col0,
+                                                 int lane, const CellBox& ub) {
+  if (ub.x0 > ub.x1) return 0u;
+  const int nyr = ub.y1 - ub.y0 + 1;
+  const int nrows = nyr * (ub.z1 - ub.z0 + 1);
 
   // pre-test coefficients of the 4 poses, in registers
-  float ax[kGroup][3], ay[kGroup][3], az[kGroup][3], kk[kGroup][3], hb[kGroup][3];
-  const float delta = pretest_delta(g);
+  float4 ca[kGroup], cb[kGroup], cc[kGroup], ch[kGroup];
 #pragma unroll
   for (int q = 0; q < kGroup; ++q) {
     const int col = col0 + q;
-    if (kMinMax) {
-      // exact compares need no slack: reuse ax/ay as min/max
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        ax[q][a] = stash[(F_MNX + a) * 32 + col];
-        ay[q][a] = stash[(F_MXX + a) * 32 + col];
-        az[q][a] = 0.f; kk[q][a] = 0.f; hb[q][a] = 0.f;
-      }
+    if (kMinMax) {  // exact compares need no slack
+      ca[q] = make_float4(stash[F_MNX * 32 + col], stash[F_MNY * 32 + col], stash[F_MNZ * 32 + col], 0.f);
+      cb[q] = make_float4(stash[F_MXX * 32 + col], stash[F_MXY * 32 + col], stash[F_MXZ * 32 + col], 0.f);
+      cc[q] = ch[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     } else {
-      const float cx = stash[F_CX * 32 + col], cy = stash[F_CY * 32 + col], cz = stash[F_CZ * 32 + col];
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        ax[q][a] = stash[(F_AXX + a) * 32 + col];
-        ay[q][a] = stash[(F_AYX + a) * 32 + col];
-        az[q][a] = stash[(F_AZX + a) * 32 + col];
-      }
-      kk[q][0] = (float)(((double)cx * ax[q][0] + (double)cy * ax[q][1]) + (double)cz * ax[q][2]);
-      kk[q][1] = (float)(((double)cx * ay[q][0] + (double)cy * ay[q][1]) + (double)cz * ay[q][2]);
-      kk[q][2] = (float)(((double)cx * az[q][0] + (double)cy * az[q][1]) + (double)cz * az[q][2]);
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        const float h = stash[(F_HX + a) * 32 + col];
-        hb[q][a] = (h < 0.f) ? -1.0f : __fadd_ru(h, delta);
-      }
+      ca[q] = pre[col * kPreStride + 0];
+      cb[q] = pre[col * kPreStride + 1];
+      cc[q] = pre[col * kPreStride + 2];
+      ch[q] = pre[col * kPreStride + 3];
     }
   }
 
-  unsigned hit = 0u;  // per-lane, exact hits
+  unsigned hit = 0u;     // per-lane, exact hits
+  unsigned alive = 0xfu; // poses still worth testing: those below the lowest pose known to collide (warp-uniform)
   for (int r0 = 0; r0 < nrows; r0 += 32) {
     const int r = r0 + lane;
     uint32_t beg = 0, end = 0;
     if (r < nrows) {
-      const int iy = iy0 + r % nyr, iz = iz0 + r / nyr;
+      const int iy = ub.y0 + r % nyr, iz = ub.z0 + r / nyr;
       const size_t base = ((size_t)iz * g.ny + iy) * (size_t)g.nx;
-      beg = __ldg(g.cell_start + base + ix0);
-      end = __ldg(g.cell_start + base + ix1 + 1);
+      beg = __ldg(g.cell_start + base + ub.x0);
+      end = __ldg(g.cell_start + base + ub.x1 + 1);
     }
     unsigned rows = __ballot_sync(kFull, beg < end);
     while (rows) {
       const int src = __ffs(rows) - 1;
       rows &= rows - 1;
       const uint32_t b = __shfl_sync(kFull, beg, src), e = __shfl_sync(kFull, end, src);
-      for (uint32_t j = b + lane; j < e; j += 32) {
-        const float4 p = __ldg(g.pts + j);
-        unsigned pre = 0u;
-#pragma unroll
-        for (int q = 0; q < kGroup; ++q) {
-          bool in;
-          if (kMinMax) {
-            in = p.x >= ax[q][0] && p.x <= ay[q][0] && p.y >= ax[q][1] && p.y <= ay[q][1] && p.z >= ax[q][2] &&
-                 p.z <= ay[q][2];
-          } else {
-            // conservative superset of the exact test: |v' - v| <= delta
-            const float vx = __fmaf_rn(p.x, ax[q][0], __fmaf_rn(p.y, ax[q][1], __fmaf_rn(p.z, ax[q][2], -kk[q][0])));
-            const float vy = __fmaf_rn(p.x, ay[q][0], __fmaf_rn(p.y, ay[q][1], __fmaf_rn(p.z, ay[q][2], -kk[q][1])));
-            const float vz = __fmaf_rn(p.x, az[q][0], __fmaf_rn(p.y, az[q][1], __fmaf_rn(p.z, az[q][2], -kk[q][2])));
-            in = fabsf(vx) <= hb[q][0] && fabsf(vy) <= hb[q][1] && fabsf(vz) <= hb[q][2];
-          }
-          pre |= in ? (1u << q) : 0u;
-        }
-        if (pre) {  // rare: decide with the reference's own arithmetic
+      for (uint32_t j0 = b; j0 < e; j0 += 32) {  // warp-uniform trip count
+        const uint32_t j = j0 + lane;
+        unsigned pm = 0u;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < e) {
+          p = __ldg(g.pts + j);
 #pragma unroll
           for (int q = 0; q < kGroup; ++q) {
-            if (pre & (1u << q)) {
+            bool in;
+            if (kMinMax) {
+              in = p.x >= ca[q].x && p.x <= cb[q].x && p.y >= ca[q].y && p.y <= cb[q].y && p.z >= ca[q].z && p.z <= cb[q].z;
+            } else {
+              // conservative superset of the exact test: |v' - v| <= delta
+              const float vx = __fmaf_rn(p.x, ca[q].x, __fmaf_rn(p.y, ca[q].y, __fmaf_rn(p.z, ca[q].z, ca[q].w)));
+              const float vy = __fmaf_rn(p.x, cb[q].x, __fmaf_rn(p.y, cb[q].y, __fmaf_rn(p.z, cb[q].z, cb[q].w)));
+              const float vz = __fmaf_rn(p.x, cc[q].x, __fmaf_rn(p.y, cc[q].y, __fmaf_rn(p.z, cc[q].z, cc[q].w)));
+              in = fabsf(vx) <= ch[q].x && fabsf(vy) <= ch[q].y && fabsf(vz) <= ch[q].z;
+            }
+            pm |= in ? (1u << q) : 0u;
+          }
+          pm &= alive;
+        }
+        if (__any_sync(kFull, pm != 0u)) {  // rare: decide with the reference's own arithmetic
+#pragma unroll 1
+          for (int q = 0; q < kGroup; ++q) {
+            if (pm & (1u << q)) {
               const int col = col0 + q;
               const bool in = kMinMax ? exact_in_aabb(stash, col, p.x, p.y, p.z) : exact_in_box(stash, col, p.x, p.y, p.z);
               if (in && exact_in_radius(stash, col, p.x, p.y, p.z)) hit |= 1u << q;
             }
           }
+          const unsigned wh = __reduce_or_sync(kFull, hit);
+          if (wh & 1u) return wh;  // the lowest pose of the group collides: nothing can precede it
+          if (wh) alive = (wh & (0u - wh)) - 1u;
         }
       }
-      // the lowest pose of the group already collides: nothing later can precede it
-      if (__any_sync(kFull, hit & 1u)) return __reduce_or_sync(kFull, hit);
     }
   }
   return __reduce_or_sync(kFull, hit);

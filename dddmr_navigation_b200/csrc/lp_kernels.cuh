@@ -263,32 +263,55 @@ __device__ __forceinline__ bool traj_precheck(const Consts& C, const RobotIn& q,
   return true;
 }
 
-__global__ void __launch_bounds__(1024) prep_kernel(Consts C, const RobotIn* __restrict__ robots, int t_cap,
-                                                    int shard_rank, int shard_count, float4* __restrict__ rec_vel,
-                                                    int* __restrict__ rec_steps, double* __restrict__ rec_dt,
-                                                    int* __restrict__ rec_sample, RobotMeta* __restrict__ meta,
-                                                    const double* __restrict__ plan7, float4* __restrict__ plan_pts) {
+// Per-(robot, chunk) aggregate of the decoupled look-back that orders the trajectory list across CTAs.
+struct PrepAgg {
+  int keep, valid;     // samples kept by the motor constraint / trajectories that passed the prologue
+  int cnt_lo, cnt_hi;  // valid samples below the shard's first / end sample
+  long long poses;     // sum of num_steps inside the shard
+  int err;
+  unsigned flag;       // == launch epoch once the fields above are visible
+};
+
+constexpr int kPrepThreads = 256;  // samples per chunk
+
+// grid = (n_chunks, robots). Chunk ids are handed out by a per-robot ticket, so a CTA only ever waits for
+// chunks that are already running; every CTA publishes its aggregate BEFORE it looks back.
+__global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const RobotIn* __restrict__ robots, int t_cap,
+                                                             int shard_rank, int shard_count, unsigned epoch,
+                                                             unsigned* __restrict__ tickets, PrepAgg* aggs,
+                                                             float4* __restrict__ rec_vel, int* __restrict__ rec_steps,
+                                                             double* __restrict__ rec_dt, int* __restrict__ rec_sample,
+                                                             RobotMeta* __restrict__ meta,
+                                                             const double* __restrict__ plan7,
+                                                             float4* __restrict__ plan_pts) {
   __shared__ float s_x[kMaxAxis], s_y[kMaxAxis], s_th[kMaxAxis];
   __shared__ int s_n[3];
-  __shared__ int s_wkeep[32], s_wvalid[32];
-  __shared__ int s_cnt_lo, s_cnt_hi, s_err;
+  __shared__ int s_wkeep[kPrepThreads / 32], s_wvalid[kPrepThreads / 32];
+  __shared__ int s_chunk;
+  __shared__ int s_red[6];
   __shared__ unsigned long long s_poses;
-  const int robot = blockIdx.x;
+  const int robot = blockIdx.y;
+  const int n_chunks = gridDim.x;
   const RobotIn q = robots[robot];
   const b200lp_limits& L = C.lim;
   const b200lp_params& P = C.par;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  // pcl_prune_plan_: float-cast plan positions (model_shared_data.h:83-91)
-  for (int i = tid; i < q.plan_n; i += blockDim.x) {
-    const double* p = plan7 + (q.plan_off + i) * 7;
-    plan_pts[q.plan_off + i] = make_float4((float)p[0], (float)p[1], (float)p[2], 0.f);
-  }
   if (tid == 0) {
-    s_cnt_lo = 0; s_cnt_hi = 0; s_err = 0; s_poses = 0ull;
+    s_chunk = (int)atomicAdd(tickets + robot, 1u);
     s_n[0] = s_n[1] = s_n[2] = 0;
+    s_red[0] = s_red[1] = s_red[2] = s_red[3] = s_red[4] = s_red[5] = 0;
+    s_poses = 0ull;
   }
   __syncthreads();
+  const int chunk = s_chunk;
+
+  // pcl_prune_plan_: float-cast plan positions (model_shared_data.h:83-91)
+  if (chunk == 0)
+    for (int i = tid; i < q.plan_n; i += blockDim.x) {
+      const double* p = plan7 + (q.plan_off + i) * 7;
+      plan_pts[q.plan_off + i] = make_float4((float)p[0], (float)p[1], (float)p[2], 0.f);
+    }
 
   const bool sampling_on = P.linear_x_sample * P.angular_z_sample > 0;
   if (sampling_on && P.theory != B200LP_THEORY_DD_ROTATE_INPLACE && lane == 0 && warp < 3) {
@@ -339,58 +362,30 @@ __global__ void __launch_bounds__(1024) prep_kernel(Consts C, const RobotIn* __r
   const long long lo = (long long)n_raw * shard_rank / shard_count;
   const long long hi = (long long)n_raw * (shard_rank + 1) / shard_count;
 
-  int base_keep = 0, base_valid = 0;
-  int cnt_lo = 0, cnt_hi = 0, err = 0;
-  unsigned long long poses = 0ull;
-  for (int s0 = 0; s0 < n_raw; s0 += blockDim.x) {
-    const int s = s0 + tid;
-    bool keep = false, valid = false;
-    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
-    int steps = 0;
-    double dt = 0.0;
-    if (s < n_raw) {
-      if (P.theory == B200LP_THEORY_DD_ROTATE_INPLACE) {
-        v2 = (s == 0) ? (float)L.rotation_speed : (float)(-1.0 * L.rotation_speed);
-        keep = motor_ok(L, v0, v2);
-      } else {
-        const int ith = s % nths, iy = (s / nths) % nys, ix = s / (nths * nys);
-        v0 = s_x[ix]; v1 = s_y[iy]; v2 = s_th[ith];
-        keep = (P.theory == B200LP_THEORY_OMNI_SIMPLE) || !L.use_motor_constraint || motor_ok(L, v0, v2);
-      }
-      if (keep) valid = traj_precheck(C, q, v0, v1, v2, &steps, &dt, &err);
+  // ---- this chunk's samples: one per thread ----
+  const int s = chunk * kPrepThreads + tid;
+  bool keep = false, valid = false;
+  float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+  int steps = 0, err = 0;
+  double dt = 0.0;
+  if (s < n_raw) {
+    if (P.theory == B200LP_THEORY_DD_ROTATE_INPLACE) {
+      v2 = (s == 0) ? (float)L.rotation_speed : (float)(-1.0 * L.rotation_speed);
+      keep = motor_ok(L, v0, v2);
+    } else {
+      const int ith = s % nths, iy = (s / nths) % nys, ix = s / (nths * nys);
+      v0 = s_x[ix]; v1 = s_y[iy]; v2 = s_th[ith];
+      keep = (P.theory == B200LP_THEORY_OMNI_SIMPLE) || !L.use_motor_constraint || motor_ok(L, v0, v2);
     }
-    const unsigned mk = __ballot_sync(kFull, keep), mv = __ballot_sync(kFull, valid);
-    if (lane == 0) {
-      s_wkeep[warp] = __popc(mk);
-      s_wvalid[warp] = __popc(mv);
-    }
-    __syncthreads();
-    int offk = 0, offv = 0, totk = 0, totv = 0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
-      const int a = s_wkeep[w], b = s_wvalid[w];
-      if (w < warp) { offk += a; offv += b; }
-      totk += a; totv += b;
-    }
-    const unsigned lt = (1u << lane) - 1u;
-    if (valid) {
-      const int sample_index = base_keep + offk + __popc(mk & lt);
-      const int id = base_valid + offv + __popc(mv & lt);
-      if (id < t_cap) {
-        const size_t o = (size_t)robot * t_cap + id;
-        rec_vel[o] = make_float4(v0, v1, v2, 0.f);
-        rec_steps[o] = steps;
-        rec_dt[o] = dt;
-        rec_sample[o] = sample_index;
-      }
-      if (s < lo) ++cnt_lo;
-      if (s < hi) ++cnt_hi;
-      if (s >= lo && s < hi) poses += (unsigned long long)steps;
-    }
-    base_keep += totk;
-    base_valid += totv;
-    __syncthreads();
+    if (keep) valid = traj_precheck(C, q, v0, v1, v2, &steps, &dt, &err);
   }
-  // block totals
+  const unsigned mk = __ballot_sync(kFull, keep), mv = __ballot_sync(kFull, valid);
+  if (lane == 0) {
+    s_wkeep[warp] = __popc(mk);
+    s_wvalid[warp] = __popc(mv);
+  }
+  int cnt_lo = (valid && s < lo) ? 1 : 0, cnt_hi = (valid && s < hi) ? 1 : 0;
+  unsigned long long poses = (valid && s >= lo && s < hi) ? (unsigned long long)steps : 0ull;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     cnt_lo += __shfl_xor_sync(kFull, cnt_lo, o);
@@ -399,146 +394,233 @@ __global__ void __launch_bounds__(1024) prep_kernel(Consts C, const RobotIn* __r
     poses += __shfl_xor_sync(kFull, poses, o);
   }
   if (lane == 0) {
-    atomicAdd(&s_cnt_lo, cnt_lo);
-    atomicAdd(&s_cnt_hi, cnt_hi);
-    atomicOr(&s_err, err);
+    atomicAdd(&s_red[0], cnt_lo);
+    atomicAdd(&s_red[1], cnt_hi);
+    atomicOr(&s_red[2], err);
     atomicAdd(&s_poses, poses);
   }
   __syncthreads();
-  if (tid == 0) {
+  int offk = 0, offv = 0, totk = 0, totv = 0;
+#pragma unroll
+  for (int w = 0; w < kPrepThreads / 32; ++w) {
+    const int a = s_wkeep[w], b = s_wvalid[w];
+    if (w < warp) { offk += a; offv += b; }
+    totk += a; totv += b;
+  }
+  PrepAgg* my_aggs = aggs + (size_t)robot * n_chunks;
+  if (tid == 0) {  // publish this chunk's aggregate
+    PrepAgg* a = my_aggs + chunk;
+    a->keep = totk; a->valid = totv;
+    a->cnt_lo = s_red[0]; a->cnt_hi = s_red[1];
+    a->poses = (long long)s_poses;
+    a->err = s_red[2];
+    __threadfence();
+    *(volatile unsigned*)&a->flag = epoch;
+  }
+  // ---- look back over every earlier chunk ----
+  int pk = 0, pv = 0, plo = 0, phi = 0, perr = 0;
+  long long pposes = 0;
+  for (int c = tid; c < chunk; c += kPrepThreads) {
+    const PrepAgg* a = my_aggs + c;
+    while (*(volatile const unsigned*)&a->flag != epoch) __nanosleep(20);
+    __threadfence();
+    pk += *(volatile const int*)&a->keep; pv += *(volatile const int*)&a->valid;
+    plo += *(volatile const int*)&a->cnt_lo; phi += *(volatile const int*)&a->cnt_hi;
+    pposes += *(volatile const long long*)&a->poses;
+    perr |= *(volatile const int*)&a->err;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    pk += __shfl_xor_sync(kFull, pk, o); pv += __shfl_xor_sync(kFull, pv, o);
+    plo += __shfl_xor_sync(kFull, plo, o); phi += __shfl_xor_sync(kFull, phi, o);
+    pposes += __shfl_xor_sync(kFull, pposes, o);
+    perr |= __shfl_xor_sync(kFull, perr, o);
+  }
+  __syncthreads();  // s_red / s_poses were consumed by thread 0 above; reuse them for the prefix
+  if (tid == 0) { s_red[0] = s_red[1] = s_red[3] = s_red[4] = 0; s_poses = 0ull; }
+  __syncthreads();
+  if (lane == 0 && chunk > 0) {
+    atomicAdd(&s_red[0], pk); atomicAdd(&s_red[1], pv);
+    atomicAdd(&s_red[3], plo); atomicAdd(&s_red[4], phi);
+    atomicOr(&s_red[5], perr);
+    atomicAdd(&s_poses, (unsigned long long)pposes);
+  }
+  __syncthreads();
+  const int base_keep = s_red[0], base_valid = s_red[1];
+
+  const unsigned lt = (1u << lane) - 1u;
+  if (valid) {
+    const int sample_index = base_keep + offk + __popc(mk & lt);
+    const int id = base_valid + offv + __popc(mv & lt);
+    if (id < t_cap) {
+      const size_t o = (size_t)robot * t_cap + id;
+      rec_vel[o] = make_float4(v0, v1, v2, 0.f);
+      rec_steps[o] = steps;
+      rec_dt[o] = dt;
+      rec_sample[o] = sample_index;
+    }
+  }
+  if (chunk == n_chunks - 1 && tid == 0) {  // the last ticket: every chunk of this robot has started
+    const PrepAgg* a = my_aggs + chunk;
     RobotMeta m;
-    m.n_samples = base_keep;
-    m.n_traj = base_valid;
-    m.t_begin = s_cnt_lo;
-    m.t_end = s_cnt_hi;
-    m.error = s_err | (base_valid > t_cap ? 2 : 0);
+    m.n_samples = base_keep + totk;
+    m.n_traj = base_valid + totv;
+    m.t_begin = s_red[3] + a->cnt_lo;
+    m.t_end = s_red[4] + a->cnt_hi;
+    m.error = (s_red[5] | a->err) | (m.n_traj > t_cap ? 2 : 0);
     m.pad = 0;
-    m.n_poses = (long long)s_poses;
+    m.n_poses = (long long)s_poses + a->poses;
     meta[robot] = m;
+    tickets[robot] = 0u;  // ready for the next launch
   }
 }
 
 // =============================================================================================
-// plan: one warp per trajectory; 8 trajectories per CTA; grid = (ceil(t_cap/8), robots)
+// plan: persistent warps, one trajectory per work item (robot, local trajectory index), handed out by a
+// global counter; grid = min(work, SMs x resident CTAs). Each warp rolls the trajectory out 32 poses at a
+// time, queries the grid, evaluates the critic stack and writes cost / per-critic scores / first-hit pose.
+// argmin_kernel then picks the best trajectory per robot.
 // =============================================================================================
 __device__ __forceinline__ bool better(unsigned long long ca, int ia, unsigned long long cb, int ib) {
   // getBestTrajectory: `cost <= minimum_cost` while scanning in id order => min cost, ties -> largest id
   return ca < cb || (ca == cb && ia > ib);
 }
 
-struct CtaShared {
-  float stash[kWarpsPerCta][F_COUNT * 32];
+struct WarpCtx {
   double R0[9], t0[3], gL[9], gt[3];
-  float4 plan[kPlanSmem];
-  BlockBest best[kWarpsPerCta];
-  int is_last;
 };
 
-__global__ void __launch_bounds__(kThreads, 2)
-plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, const RobotMeta* __restrict__ meta, int t_cap,
-            const float4* __restrict__ rec_vel, const int* __restrict__ rec_steps, const double* __restrict__ rec_dt,
-            const float4* __restrict__ plan_pts, const double* __restrict__ plan7, double* __restrict__ out_cost,
-            double* __restrict__ out_scores, int* __restrict__ out_first_hit, BlockBest* __restrict__ partial,
-            unsigned* __restrict__ block_counter, b200lp_result* __restrict__ results) {
-  __shared__ CtaShared S;
-  const int robot = blockIdx.y;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const RobotMeta m = meta[robot];
-  const int n_local = m.t_end - m.t_begin;
-  const bool cta_has_work = (int)blockIdx.x * kWarpsPerCta < n_local;
-  const RobotIn& q = robots[robot];
-  const int plan_n = q.plan_n;
-  const float4* plan = plan_pts + q.plan_off;
+struct CtaShared {
+  float stash[kWarpsPerCta][F_COUNT * 32];
+  float4 pre[kWarpsPerCta][32 * kPreStride];
+  WarpCtx wc[kWarpsPerCta];
+  float4 plan[kPlanSmem];
+};
 
-  if (cta_has_work) {
-    if (threadIdx.x == 0) {
-      // tf2::transformToEigen(robot_pose_) (dd_simple…cpp:355)
-      quat_to_matrix(q.pose[3], q.pose[4], q.pose[5], q.pose[6], S.R0);
-      S.t0[0] = q.pose[0]; S.t0[1] = q.pose[1]; S.t0[2] = q.pose[2];
-    }
-    if (threadIdx.x == 32 && plan_n > 0) {
-      const double* e = plan7 + (q.plan_off + plan_n - 1) * 7;  // prune_plan_.poses.back()
-      quat_to_matrix(e[3], e[4], e[5], e[6], S.gL);
-      S.gt[0] = e[0]; S.gt[1] = e[1]; S.gt[2] = e[2];
-    }
-    if (plan_n <= kPlanSmem)
-      for (int i = threadIdx.x; i < plan_n; i += kThreads) S.plan[i] = plan[i];
+__global__ void __launch_bounds__(kThreads, 4)
+plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, const RobotMeta* __restrict__ meta, int n_robots,
+            int t_cap, int cap_local, const float4* __restrict__ rec_vel, const int* __restrict__ rec_steps,
+            const double* __restrict__ rec_dt, const float4* __restrict__ plan_pts, const double* __restrict__ plan7,
+            double* __restrict__ out_cost, double* __restrict__ out_scores, int* __restrict__ out_first_hit,
+            unsigned long long* __restrict__ work_counter) {
+  __shared__ CtaShared S;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* stash = S.stash[warp];
+  float4* pre = S.pre[warp];
+  WarpCtx& W = S.wc[warp];
+  const unsigned long long total = (unsigned long long)n_robots * (unsigned long long)cap_local;
+  const int nc = C.n_critics;
+
+  // single-robot launches stage the prune plan in shared memory once per CTA
+  const bool plan_staged = n_robots == 1 && robots[0].plan_n <= kPlanSmem;
+  if (plan_staged) {
+    const float4* gp = plan_pts + robots[0].plan_off;
+    for (int i = threadIdx.x; i < robots[0].plan_n; i += kThreads) S.plan[i] = gp[i];
   }
   __syncthreads();
-  if (plan_n <= kPlanSmem) plan = S.plan;
 
-  const int local = blockIdx.x * kWarpsPerCta + warp;
-  const int id = m.t_begin + local;
-  unsigned long long my_cost_bits = ~0ull;
-  int my_collided = 0;
-
-  if (local < n_local) {
+  int cur_robot = -1, t_begin = 0, n_local = 0, plan_n = 0;
+  double heading_deviation = 0.0;
+  const float4* plan = nullptr;
+  for (;;) {
+    unsigned long long w = 0ull;
+    if (lane == 0) w = atomicAdd(work_counter, 1ull);
+    w = __shfl_sync(kFull, w, 0);
+    if (w >= total) break;
+    const int robot = (int)(w / (unsigned long long)cap_local);
+    const int local = (int)(w - (unsigned long long)robot * (unsigned long long)cap_local);
+    if (robot != cur_robot) {
+      cur_robot = robot;
+      const RobotIn& q = robots[robot];
+      t_begin = meta[robot].t_begin;
+      n_local = meta[robot].t_end - t_begin;
+      plan_n = q.plan_n;
+      heading_deviation = q.heading_deviation;
+      plan = plan_staged ? S.plan : plan_pts + q.plan_off;
+      __syncwarp();
+      if (lane == 0) {
+        // tf2::transformToEigen(robot_pose_) (dd_simple…cpp:355)
+        quat_to_matrix(q.pose[3], q.pose[4], q.pose[5], q.pose[6], W.R0);
+        W.t0[0] = q.pose[0]; W.t0[1] = q.pose[1]; W.t0[2] = q.pose[2];
+      }
+      if (lane == 1 && plan_n > 0) {
+        const double* e = plan7 + (q.plan_off + plan_n - 1) * 7;  // prune_plan_.poses.back()
+        quat_to_matrix(e[3], e[4], e[5], e[6], W.gL);
+        W.gt[0] = e[0]; W.gt[1] = e[1]; W.gt[2] = e[2];
+      }
+      __syncwarp();
+    }
+    if (local >= n_local) continue;
+    const int id = t_begin + local;
     const size_t rec = (size_t)robot * t_cap + id;
     const float4 vel = rec_vel[rec];
     const int n = rec_steps[rec];
     const double dt = rec_dt[rec];
-    float* stash = S.stash[warp];
 
     // ---- critic stack analysis (warp-uniform) ------------------------------------------------
-    const int nc = C.n_critics;
-    double val[B200LP_MAX_CRITICS];  // NaN = not evaluated
-    int hit_pose[B200LP_MAX_CRITICS];
-    bool need_stick = false, need_last_nn = false, need_pp = false;
-    bool early_ok = true;       // may a collision hit end the rollout?
-    int stop_at = nc;           // critics >= stop_at are never evaluated (an earlier one is known negative)
+    // A critic's value may be known before the rollout (collision_model.cpp:53-55, stick_path_model.cpp:53-55,
+    // pure_pursuit_model.cpp:62-84, shortest_angle_model.cpp:51-69, twirling_model.cpp:51-55).
     const double thetav = (double)vel.z;
+    auto upfront = [&](const CriticDev& cr, double& v) -> bool {
+      switch (cr.kind) {
+        case B200LP_CRITIC_COLLISION:
+        case B200LP_CRITIC_COLLISION_MIN_MAX:
+          if (g.n_raw < 5) { v = 0.0; return true; }
+          return false;
+        case B200LP_CRITIC_STICK_PATH:
+        case B200LP_CRITIC_TOWARD_GLOBAL_PLAN:
+          if (plan_n < 3) { v = 10.0; return true; }
+          return false;
+        case B200LP_CRITIC_PURE_PURSUIT:
+          if (plan_n == 0 || n < 2) { v = -4.0; return true; }
+          return false;
+        case B200LP_CRITIC_SHORTEST_ANGLE:
+          if (heading_deviation >= 0) v = (thetav >= 0) ? cr.weight : cr.weight * 2;
+          else v = (thetav >= 0) ? cr.weight * 2 : cr.weight;
+          return true;
+        case B200LP_CRITIC_TWIRLING:
+          v = lpm::dabs(thetav) * cr.weight;
+          return true;
+      }
+      return false;
+    };
+    bool need_box = false, need_mm = false, need_stick = false, need_last_nn = false, need_pp = false;
+    bool early_ok = true;      // may a collision hit end the rollout?
+    int first_coll_kind = -1;  // kind of the stack's first live collision critic: 0 box, 1 min-max
     {
       bool rollout_dep_seen = false;
-#pragma unroll
-      for (int k = 0; k < B200LP_MAX_CRITICS; ++k) {
-        val[k] = lpm::u2d(0x7ff8000000000000ull);
-        hit_pose[k] = -1;
-        if (k >= nc || k >= stop_at) continue;
+#pragma unroll 1
+      for (int k = 0; k < nc; ++k) {
         const CriticDev& cr = C.critics[k];
+        double v;
+        if (upfront(cr, v)) {
+          if (v < 0) break;  // known-negative up front: later critics are never reached
+          continue;
+        }
         switch (cr.kind) {
           case B200LP_CRITIC_COLLISION:
-          case B200LP_CRITIC_COLLISION_MIN_MAX:
-            if (g.n_raw < 5) val[k] = 0.0;  // collision_model.cpp:53-55
-            else if (rollout_dep_seen) early_ok = false;
+          case B200LP_CRITIC_COLLISION_MIN_MAX: {
+            const bool mm = cr.kind == B200LP_CRITIC_COLLISION_MIN_MAX;
+            if (rollout_dep_seen) early_ok = false;
+            if (mm) need_mm = true; else need_box = true;
+            if (first_coll_kind < 0) first_coll_kind = mm ? 1 : 0;
             break;
-          case B200LP_CRITIC_STICK_PATH:
-            if (plan_n < 3) val[k] = 10.0;
-            else { need_stick = true; rollout_dep_seen = true; }
-            break;
-          case B200LP_CRITIC_TOWARD_GLOBAL_PLAN:
-            if (plan_n < 3) val[k] = 10.0;
-            else { need_last_nn = true; rollout_dep_seen = true; }
-            break;
-          case B200LP_CRITIC_PURE_PURSUIT:
-            if (plan_n == 0 || n < 2) val[k] = -4.0;
-            else { need_pp = true; rollout_dep_seen = true; }
-            break;
-          case B200LP_CRITIC_SHORTEST_ANGLE:
-            if (q.heading_deviation >= 0) val[k] = (thetav >= 0) ? cr.weight : cr.weight * 2;
-            else val[k] = (thetav >= 0) ? cr.weight * 2 : cr.weight;
-            break;
-          case B200LP_CRITIC_TWIRLING:
-            val[k] = lpm::dabs(thetav) * cr.weight;
-            break;
+          }
+          case B200LP_CRITIC_STICK_PATH: need_stick = true; rollout_dep_seen = true; break;
+          case B200LP_CRITIC_TOWARD_GLOBAL_PLAN: need_last_nn = true; rollout_dep_seen = true; break;
+          case B200LP_CRITIC_PURE_PURSUIT: need_pp = true; rollout_dep_seen = true; break;
+          default: break;
         }
-        if (val[k] < 0) stop_at = k + 1;  // known-negative up front: later critics are never reached
       }
     }
-    // which collision critics still have to run
-    unsigned coll_active = 0u;
-#pragma unroll
-    for (int k = 0; k < B200LP_MAX_CRITICS; ++k)
-      if (k < nc && k < stop_at && g.n_raw >= 5 &&
-          (C.critics[k].kind == B200LP_CRITIC_COLLISION || C.critics[k].kind == B200LP_CRITIC_COLLISION_MIN_MAX))
-        coll_active |= 1u << k;
-    const int first_coll = coll_active ? (__ffs(coll_active) - 1) : -1;
-    const bool any_rollout_work = coll_active || need_stick || need_last_nn || need_pp;
+    const bool any_rollout_work = need_box || need_mm || need_stick || need_last_nn || need_pp;
 
     // ---- rollout + query, 32 poses at a time ---------------------------------------------------
     Carry carry = {0.f, 0.f, 0.f};
     double stick_sum = 0.0;
     float last_nn = 0.f;
-    double pp_val = 0.0;
+    double pp_dist = 0.0, pp_yaw = 0.0;
+    int hit_box = -1, hit_mm = -1;  // first colliding pose per collision-critic kind
     bool done = !any_rollout_work;
     for (int base = 0; base < n && !done; base += 32) {
       float px, py, pth;
@@ -546,30 +628,29 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, const Robot
       const int k = base + lane;
       const bool live = k < n;
       double L[9], t[3];
-      pose_affine(S.R0, S.t0, px, py, pth, L, t);
-      if (need_pp && k == n - 1) {
-        double tw = 0.0, ow = 0.0;
-#pragma unroll
-        for (int c = 0; c < B200LP_MAX_CRITICS; ++c)
-          if (c < nc && C.critics[c].kind == B200LP_CRITIC_PURE_PURSUIT && lpm::d2u(val[c]) == 0x7ff8000000000000ull) {
-            tw = C.critics[c].tw; ow = C.critics[c].ow;
-          }
-        pp_val = pure_pursuit_value(L, t, S.gL, S.gt, tw, ow);
-      }
-      pose_geometry(C, g, L, t, stash, lane, live, nullptr);
+      pose_affine(W.R0, W.t0, px, py, pth, L, t);
+      if (need_pp && k == n - 1) pure_pursuit_terms(L, t, W.gL, W.gt, &pp_dist, &pp_yaw);
+      CellBox cbx;
+      pose_geometry(C, g, L, t, stash, pre, &cbx, lane, live, nullptr);
+      group_union(cbx);
       __syncwarp();
 
-      // obstacle query, groups of kGroup consecutive poses
+      // obstacle query, groups of kGroup consecutive poses, once per collision-critic kind still undecided
       const int n_here = min(32, n - base);
-#pragma unroll
-      for (int kc = 0; kc < B200LP_MAX_CRITICS; ++kc) {
-        if (kc >= nc || !(coll_active & (1u << kc))) continue;
-        const bool minmax = C.critics[kc].kind == B200LP_CRITIC_COLLISION_MIN_MAX;
+#pragma unroll 1
+      for (int kind = 0; kind < 2; ++kind) {
+        if (kind == 0 ? !(need_box && hit_box < 0) : !(need_mm && hit_mm < 0)) continue;
+#pragma unroll 1
         for (int col0 = 0; col0 < n_here; col0 += kGroup) {
-          const unsigned h = minmax ? sweep_points<true>(g, stash, col0, lane) : sweep_points<false>(g, stash, col0, lane);
+          CellBox ub;
+          ub.x0 = __shfl_sync(kFull, cbx.x0, col0); ub.x1 = __shfl_sync(kFull, cbx.x1, col0);
+          ub.y0 = __shfl_sync(kFull, cbx.y0, col0); ub.y1 = __shfl_sync(kFull, cbx.y1, col0);
+          ub.z0 = __shfl_sync(kFull, cbx.z0, col0); ub.z1 = __shfl_sync(kFull, cbx.z1, col0);
+          const unsigned h = kind ? sweep_points<true>(g, stash, pre, col0, lane, ub)
+                                  : sweep_points<false>(g, stash, pre, col0, lane, ub);
           if (h) {
-            hit_pose[kc] = base + col0 + (__ffs(h) - 1);
-            coll_active &= ~(1u << kc);
+            const int hp = base + col0 + (__ffs(h) - 1);
+            if (kind) hit_mm = hp; else hit_box = hp;
             break;
           }
         }
@@ -577,12 +658,7 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, const Robot
       // A hit of the FIRST collision critic of the stack ends the trajectory (the reference returns -1
       // there) when nothing that precedes it in the stack depends on the rollout. A later collision
       // critic hitting first only retires that critic: the earlier one must still run to the end.
-      if (early_ok && first_coll >= 0) {
-#pragma unroll
-        for (int kc = 0; kc < B200LP_MAX_CRITICS; ++kc)
-          if (kc == first_coll && hit_pose[kc] >= 0) done = true;
-      }
-      if (done) break;
+      if (early_ok && first_coll_kind >= 0 && (first_coll_kind ? hit_mm : hit_box) >= 0) break;
 
       if (need_stick || need_last_nn) {
         float d2 = 0.f;
@@ -596,96 +672,73 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, const Robot
       }
       __syncwarp();
     }
-    if (need_pp) pp_val = __shfl_sync(kFull, pp_val, (n - 1) & 31);
+    if (need_pp) {
+      pp_dist = __shfl_sync(kFull, pp_dist, (n - 1) & 31);
+      pp_yaw = __shfl_sync(kFull, pp_yaw, (n - 1) & 31);
+    }
 
     // ---- StackedScoringModel::scoreTrajectory (stacked_scoring_model.cpp:75-93) -----------------
     double cost = 0.0;
     int first_hit = -1;
     bool stopped = false;
-#pragma unroll
-    for (int k = 0; k < B200LP_MAX_CRITICS; ++k) {
-      if (k >= nc) continue;
-      if (stopped) {
-        val[k] = lpm::u2d(0x7ff8000000000000ull);
-        continue;
-      }
+#pragma unroll 1
+    for (int k = 0; k < nc; ++k) {
       const CriticDev& cr = C.critics[k];
-      const bool unknown = lpm::d2u(val[k]) == 0x7ff8000000000000ull;
-      if (unknown) {
-        switch (cr.kind) {
-          case B200LP_CRITIC_COLLISION:
-          case B200LP_CRITIC_COLLISION_MIN_MAX:
-            val[k] = (hit_pose[k] >= 0) ? -1.0 : 0.0;
-            if (hit_pose[k] >= 0 && first_hit < 0) first_hit = hit_pose[k];
-            break;
-          case B200LP_CRITIC_STICK_PATH: val[k] = stick_sum / (double)plan_n; break;
-          case B200LP_CRITIC_TOWARD_GLOBAL_PLAN: val[k] = (double)last_nn * cr.weight; break;
-          case B200LP_CRITIC_PURE_PURSUIT: val[k] = pp_val; break;
-          default: break;
+      double v = lpm::u2d(0x7ff8000000000000ull);  // NaN = not evaluated (an earlier critic rejected the trajectory)
+      if (!stopped) {
+        if (!upfront(cr, v)) {
+          switch (cr.kind) {
+            case B200LP_CRITIC_COLLISION:
+            case B200LP_CRITIC_COLLISION_MIN_MAX: {
+              const int hp = cr.kind == B200LP_CRITIC_COLLISION ? hit_box : hit_mm;
+              v = (hp >= 0) ? -1.0 : 0.0;
+              if (hp >= 0 && first_hit < 0) first_hit = hp;
+              break;
+            }
+            case B200LP_CRITIC_STICK_PATH: v = stick_sum / (double)plan_n; break;
+            case B200LP_CRITIC_TOWARD_GLOBAL_PLAN: v = (double)last_nn * cr.weight; break;
+            case B200LP_CRITIC_PURE_PURSUIT: v = cr.tw * pp_dist + cr.ow * pp_yaw; break;
+            default: break;
+          }
+        }
+        if (v < 0) {
+          cost = v;
+          stopped = true;
+        } else {
+          cost += v;
         }
       }
-      if (val[k] < 0) {
-        cost = val[k];
-        stopped = true;
-      } else {
-        cost += val[k];
-      }
+      if (lane == 0) out_scores[rec * nc + k] = v;
     }
     if (lane == 0) {
       out_cost[rec] = cost;
       out_first_hit[rec] = first_hit;
-#pragma unroll
-      for (int k = 0; k < B200LP_MAX_CRITICS; ++k)
-        if (k < nc) out_scores[rec * nc + k] = val[k];
     }
-    if (cost >= 0.0 && cost <= 9999999.0) my_cost_bits = lpm::d2u(cost);  // local_planner.cpp:450,460
-    my_collided = first_hit >= 0 ? 1 : 0;
+    __syncwarp();
   }
+}
 
-  // ---- block argmin: per-warp results -> warp-shuffle reduce -> one partial per CTA ---------------
-  if (lane == 0) {
-    S.best[warp].cost_bits = my_cost_bits;
-    S.best[warp].id = id;
-    S.best[warp].n_collided = my_collided;
-  }
-  __syncthreads();
-  if (warp == 0) {
-    unsigned long long cb = ~0ull;
-    int bi = -1, ncoll = 0;
-    if (lane < kWarpsPerCta) {
-      cb = S.best[lane].cost_bits;
-      bi = S.best[lane].id;
-      ncoll = S.best[lane].n_collided;
-    }
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
-      const unsigned long long ocb = __shfl_xor_sync(kFull, cb, o);
-      const int obi = __shfl_xor_sync(kFull, bi, o);
-      ncoll += __shfl_xor_sync(kFull, ncoll, o);
-      if (ocb != ~0ull && (cb == ~0ull || better(ocb, obi, cb, bi))) { cb = ocb; bi = obi; }
-    }
-    if (lane == 0) {
-      BlockBest b;
-      b.cost_bits = cb;
-      b.id = (cb == ~0ull) ? -1 : bi;
-      b.n_collided = ncoll;
-      partial[(size_t)robot * gridDim.x + blockIdx.x] = b;
-      __threadfence();
-      const unsigned ticket = atomicAdd(block_counter + robot, 1u);
-      S.is_last = (ticket == gridDim.x - 1) ? 1 : 0;
-    }
-  }
-  __syncthreads();
-  if (!S.is_last) return;
-
-  // ---- last CTA of this robot: final argmin over the CTA partials (local_planner.cpp:447-480) ------
-  __threadfence();
+// Local_Planner::getBestTrajectory (local_planner.cpp:447-480) over the costs plan_kernel wrote: one CTA per robot.
+constexpr int kArgminThreads = 256;
+__global__ void __launch_bounds__(kArgminThreads)
+argmin_kernel(Consts C, const RobotMeta* __restrict__ meta, int t_cap, const float4* __restrict__ rec_vel,
+              const double* __restrict__ cost, const int* __restrict__ first_hit, b200lp_result* __restrict__ results,
+              unsigned long long* __restrict__ work_counter) {
+  __shared__ BlockBest s_best[kArgminThreads / 32];
+  const int robot = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const RobotMeta m = meta[robot];
+  if (blockIdx.x == 0 && threadIdx.x == 0) *work_counter = 0ull;  // ready for the next plan_kernel launch
   unsigned long long cb = ~0ull;
   int bi = -1, ncoll = 0;
-  for (int i = threadIdx.x; i < (int)gridDim.x; i += kThreads) {
-    const BlockBest b = partial[(size_t)robot * gridDim.x + i];
-    ncoll += b.n_collided;
-    if (b.cost_bits != ~0ull && (cb == ~0ull || better(b.cost_bits, b.id, cb, bi))) { cb = b.cost_bits; bi = b.id; }
+  for (int id = m.t_begin + threadIdx.x; id < m.t_end; id += kArgminThreads) {
+    const size_t rec = (size_t)robot * t_cap + id;
+    const double c = cost[rec];
+    ncoll += first_hit[rec] >= 0 ? 1 : 0;
+    if (c >= 0.0 && c <= 9999999.0) {  // local_planner.cpp:450,460
+      const unsigned long long bits = lpm::d2u(c);
+      if (cb == ~0ull || better(bits, id, cb, bi)) { cb = bits; bi = id; }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -694,24 +747,23 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, const Robot
     ncoll += __shfl_xor_sync(kFull, ncoll, o);
     if (ocb != ~0ull && (cb == ~0ull || better(ocb, obi, cb, bi))) { cb = ocb; bi = obi; }
   }
-  __syncthreads();  // S.best is reused below
   if (lane == 0) {
-    S.best[warp].cost_bits = cb;
-    S.best[warp].id = bi;
-    S.best[warp].n_collided = ncoll;
+    s_best[warp].cost_bits = cb;
+    s_best[warp].id = bi;
+    s_best[warp].n_collided = ncoll;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     cb = ~0ull; bi = -1; ncoll = 0;
-    for (int w = 0; w < kWarpsPerCta; ++w) {
-      const BlockBest b = S.best[w];
+    for (int w = 0; w < kArgminThreads / 32; ++w) {
+      const BlockBest b = s_best[w];
       ncoll += b.n_collided;
       if (b.cost_bits != ~0ull && (cb == ~0ull || better(b.cost_bits, b.id, cb, bi))) { cb = b.cost_bits; bi = b.id; }
     }
     b200lp_result r;
     r.best_id = (cb == ~0ull) ? -1 : bi;
     r.n_samples = m.n_samples;
-    r.n_traj = n_local;
+    r.n_traj = m.t_end - m.t_begin;
     r.n_collided = ncoll;
     r.n_poses = m.n_poses;
     r.best_cost = (cb == ~0ull) ? -1.0 : lpm::u2d(cb);
@@ -723,7 +775,6 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, const Robot
       r.thetav = (double)v.z;
     }
     results[robot] = r;
-    block_counter[robot] = 0u;  // ready for the next launch
   }
 }
 
@@ -800,7 +851,7 @@ __global__ void __launch_bounds__(32) poses_kernel(Consts C, GridDev g, const Ro
     double L[9], t[3];
     pose_affine(R0, t0, px, py, pth, L, t);
     float verts[24];
-    pose_geometry(C, g, L, t, stash, lane, live, verts);
+    pose_geometry(C, g, L, t, stash, nullptr, nullptr, lane, live, verts);
     __syncwarp();
     if (live) {
       if (o_pose) {

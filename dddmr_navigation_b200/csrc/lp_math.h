@@ -26,8 +26,12 @@
 
 #if defined(__CUDACC__)
 #define LPM_HD __host__ __device__ __forceinline__
+// the big double routines are called from a few sites only: one out-of-line copy keeps the kernels' code
+// inside the instruction cache (same arithmetic either way)
+#define LPM_HD_BIG static __host__ __device__ __noinline__
 #else
 #define LPM_HD static inline
+#define LPM_HD_BIG static inline
 #endif
 
 namespace lpm {
@@ -113,8 +117,8 @@ LPM_HD double reduce_fast(double x, int* np) {
   return x - n * hpi;
 }
 
-LPM_HD double sin(double x);
-LPM_HD double cos(double x);
+LPM_HD_BIG double sin(double x);
+LPM_HD_BIG double cos(double x);
 
 LPM_HD float sinf(float y) {
   double x = y;
@@ -196,7 +200,7 @@ LPM_HD int rem_pio2(double x, double* y0, double* y1) {
   return (int)fn;
 }
 
-LPM_HD double sin(double x) {
+LPM_HD_BIG double sin(double x) {
   if (dabs(x) <= 0.78539816339744827900) {
     if (dabs(x) < 7.450580596923828125e-9 /* 2^-27 */) return x;
     return ksin(x, 0.0, 0);
@@ -211,7 +215,7 @@ LPM_HD double sin(double x) {
   }
 }
 
-LPM_HD double cos(double x) {
+LPM_HD_BIG double cos(double x) {
   if (dabs(x) <= 0.78539816339744827900) {
     if (dabs(x) < 7.450580596923828125e-9) return 1.0;
     return kcos(x, 0.0);
@@ -230,7 +234,7 @@ LPM_HD double cos(double x) {
 // asin / atan / atan2 (msun e_asin.c, s_atan.c, e_atan2.c forms). Finite inputs only: the
 // critic feeds matrix entries of a finite rotation.
 // ----------------------------------------------------------------------------------------
-LPM_HD double asin(double x) {
+LPM_HD_BIG double asin(double x) {
   const double pio2_hi = 1.57079632679489655800e+00, pio2_lo = 6.12323399573676603587e-17,
                pio4_hi = 7.85398163397448278999e-01;
   const double pS0 = 1.66666666666666657415e-01, pS1 = -3.25565818622400915405e-01,
@@ -269,7 +273,7 @@ LPM_HD double asin(double x) {
   return (x > 0.0) ? t : -t;
 }
 
-LPM_HD double atan(double x) {
+LPM_HD_BIG double atan(double x) {
   const double aT0 = 3.33333333333329318027e-01, aT1 = -1.99999999998764832476e-01,
                aT2 = 1.42857142725034663711e-01, aT3 = -1.11111104054623557880e-01,
                aT4 = 9.09088713343650656196e-02, aT5 = -7.69187620504482999495e-02,
@@ -316,7 +320,7 @@ LPM_HD double atan(double x) {
   return neg ? -z : z;
 }
 
-LPM_HD double atan2(double y, double x) {
+LPM_HD_BIG double atan2(double y, double x) {
   const double pi = 3.1415926535897931160E+00, pi_lo = 1.2246467991473531772E-16,
                pi_o_2 = 1.5707963267948965580E+00;
   const bool sx = (d2u(x) >> 63) != 0, sy = (d2u(y) >> 63) != 0;
