@@ -102,6 +102,10 @@ struct b200lp_ctx {
   DevBuf<float4> d_rec_vel;
   DevBuf<int> d_rec_steps, d_rec_sample, d_first_hit;
   DevBuf<double> d_rec_dt, d_cost, d_scores;
+  DevBuf<long long> d_rec_pose_off;      // row of every trajectory in d_poses
+  DevBuf<float4> d_poses;                // forward-simulated (x, y, th) of every pose of the cycle, robot frame
+  DevBuf<double2> d_rec_pp;              // pure-pursuit (distance, yaw) of every trajectory's last pose
+  long long pose_stride = 0;             // rows of d_poses reserved per robot
   DevBuf<unsigned> d_tickets;            // prep_kernel chunk tickets, one per robot (self-resetting)
   DevBuf<PrepAgg> d_aggs;                // prep_kernel look-back aggregates
   DevBuf<unsigned long long> d_work;     // plan_kernel work counter (reset by argmin_kernel)
@@ -289,6 +293,17 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   CK(ctx->d_results.reserve(n_robots));
   CK(ctx->h_results.reserve(n_robots));
   CK(ctx->h_meta.reserve(n_robots));
+  // the forward simulation of every scored trajectory is materialised once per cycle (16 B per pose)
+  const long long pose_stride = (long long)cap_local * (long long)max_steps_bound(ctx->C.lim, ctx->C.par);
+  if ((double)pose_stride * (double)n_robots * 16.0 > 64e9)
+    return ctx->fail(B200LP_E_NOMEM, "plan: %zu robots x %d trajectories x %d poses need more than 64 GB of pose storage",
+                     n_robots, cap_local, (int)max_steps_bound(ctx->C.lim, ctx->C.par));
+  CK(ctx->d_poses.reserve((size_t)pose_stride * n_robots));
+  CK(ctx->d_rec_pose_off.reserve(T));
+  int want_pp = 0;
+  for (int k = 0; k < ctx->C.n_critics; ++k) want_pp |= ctx->C.critics[k].kind == B200LP_CRITIC_PURE_PURSUIT;
+  CK(ctx->d_rec_pp.reserve(want_pp ? T : 1));
+  ctx->pose_stride = pose_stride;
   if (ctx->d_tickets.cap < n_robots) {
     CK(ctx->d_tickets.reserve(n_robots));
     CK(cudaMemsetAsync(ctx->d_tickets.p, 0, ctx->d_tickets.cap * sizeof(unsigned), ctx->stream));
@@ -329,12 +344,13 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   prep_kernel<<<dim3((unsigned)n_chunks, (unsigned)n_robots), kPrepThreads, 0, ctx->stream>>>(
       ctx->C, ctx->d_robots.p, t_cap, rank, count, ctx->epoch, ctx->d_tickets.p, ctx->d_aggs.p, ctx->d_rec_vel.p,
-      ctx->d_rec_steps.p, ctx->d_rec_dt.p, ctx->d_rec_sample.p, ctx->d_meta.p, ctx->d_plan7.p, ctx->d_plan_pts.p);
+      ctx->d_rec_steps.p, ctx->d_rec_dt.p, ctx->d_rec_sample.p, ctx->d_meta.p, ctx->d_plan7.p, ctx->d_plan_pts.p,
+      ctx->d_rec_pose_off.p, ctx->d_poses.p, pose_stride, ctx->d_rec_pp.p, want_pp);
   CK(cudaEventRecord(ctx->ev[4], ctx->stream));
   plan_kernel<<<plan_grid, kThreads, 0, ctx->stream>>>(
       ctx->C, ctx->grid, ctx->d_robots.p, ctx->d_meta.p, (int)n_robots, t_cap, cap_local, ctx->d_rec_vel.p,
-      ctx->d_rec_steps.p, ctx->d_rec_dt.p, ctx->d_plan_pts.p, ctx->d_plan7.p, ctx->d_cost.p, ctx->d_scores.p,
-      ctx->d_first_hit.p, ctx->d_work.p);
+      ctx->d_rec_steps.p, ctx->d_rec_pose_off.p, ctx->d_poses.p, ctx->d_rec_pp.p, ctx->d_plan_pts.p, ctx->d_cost.p,
+      ctx->d_scores.p, ctx->d_first_hit.p, ctx->d_work.p);
   CK(cudaEventRecord(ctx->ev[5], ctx->stream));
   argmin_kernel<<<(unsigned)n_robots, kArgminThreads, 0, ctx->stream>>>(ctx->C, ctx->d_meta.p, t_cap, ctx->d_rec_vel.p,
                                                                         ctx->d_cost.p, ctx->d_first_hit.p,
@@ -349,7 +365,7 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   ctx->meta_host.assign(ctx->h_meta.p, ctx->h_meta.p + n_robots);
   for (size_t i = 0; i < n_robots; ++i) {
     if (ctx->meta_host[i].error)
-      return ctx->fail(B200LP_E_INVALID, "robot %zu: a trajectory exceeds B200LP_MAX_STEPS=%d poses or the trajectory list overflowed",
+      return ctx->fail(B200LP_E_INVALID, "robot %zu: a trajectory exceeds B200LP_MAX_STEPS=%d poses or the trajectory / pose list overflowed",
                        i, B200LP_MAX_STEPS);
     outs[i] = ctx->h_results.p[i];
   }
@@ -451,7 +467,7 @@ void b200lp_destroy(b200lp_ctx* ctx) {
   ctx->h_bounds.release(); ctx->d_robots.release(); ctx->d_meta.release(); ctx->d_plan7.release();
   ctx->d_plan_pts.release(); ctx->d_rec_vel.release(); ctx->d_rec_steps.release(); ctx->d_rec_sample.release();
   ctx->d_first_hit.release(); ctx->d_rec_dt.release(); ctx->d_cost.release(); ctx->d_scores.release();
-  ctx->d_tickets.release(); ctx->d_aggs.release(); ctx->d_work.release(); ctx->d_results.release(); ctx->d_count.release(); ctx->d_scratch.release();
+  ctx->d_rec_pose_off.release(); ctx->d_poses.release(); ctx->d_rec_pp.release(); ctx->d_tickets.release(); ctx->d_aggs.release(); ctx->d_work.release(); ctx->d_results.release(); ctx->d_count.release(); ctx->d_scratch.release();
   ctx->h_robots.release(); ctx->h_plan7.release(); ctx->h_results.release(); ctx->h_meta.release();
   ctx->h_count.release();
   for (auto& ev : ctx->ev)

@@ -193,28 +193,26 @@ __global__ void __launch_bounds__(256) scatter_kernel(const char* __restrict__ r
 // =============================================================================================
 // trajectory_generators::VelocityIterator (velocity_iterator.h:44-69); values are rounded to float where
 // the reference stores them into an Eigen::Vector3f (dd_simple…cpp:282-286).
+// One lane runs it; the only serial dependency is the `next += step` chain (b200lp_create bounds n so that
+// every index below stays inside out[kMaxAxis]).
 __device__ int velocity_iterator_dev(double mn, double mx, int n, float* out) {
-  int cnt = 0;
   if (mn == mx) {
-    out[cnt++] = (float)mn;
-    return cnt;
+    out[0] = (float)mn;
+    return 1;
   }
   n = max(2, n);
   const double step = (mx - mn) / (double)max(1, n - 1);
   double next = mn;
+  int cnt = 0;
   for (int j = 0; j < n - 1; ++j) {
     const double cur = next;
     next += step;
-    if (cnt < kMaxAxis) out[cnt] = (float)cur;
-    ++cnt;
-    if (cur < 0 && next > 0) {
-      if (cnt < kMaxAxis) out[cnt] = 0.0f;
-      ++cnt;
-    }
+    out[cnt] = (float)cur;
+    out[cnt + 1] = 0.0f;  // kept only when the window crosses zero here, else overwritten by the next value
+    cnt += (cur < 0 && next > 0) ? 2 : 1;
   }
-  if (cnt < kMaxAxis) out[cnt] = (float)mx;
-  ++cnt;
-  return min(cnt, kMaxAxis);
+  out[cnt] = (float)mx;
+  return min(cnt + 1, kMaxAxis);
 }
 
 __device__ __forceinline__ bool motor_ok(const b200lp_limits& L, float v0, float v2) {
@@ -283,8 +281,13 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
                                                              double* __restrict__ rec_dt, int* __restrict__ rec_sample,
                                                              RobotMeta* __restrict__ meta,
                                                              const double* __restrict__ plan7,
-                                                             float4* __restrict__ plan_pts) {
+                                                             float4* __restrict__ plan_pts,
+                                                             long long* __restrict__ rec_pose_off,
+                                                             float4* __restrict__ pose_rows, long long pose_stride,
+                                                             double2* __restrict__ rec_pp, int want_pp) {
   __shared__ float s_x[kMaxAxis], s_y[kMaxAxis], s_th[kMaxAxis];
+  __shared__ double s_R0[9], s_t0[3], s_gL[9], s_gt[3];
+  __shared__ unsigned long long s_wposes[kPrepThreads / 32];
   __shared__ int s_n[3];
   __shared__ int s_wkeep[kPrepThreads / 32], s_wvalid[kPrepThreads / 32];
   __shared__ int s_chunk;
@@ -306,6 +309,16 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
   __syncthreads();
   const int chunk = s_chunk;
 
+  if (tid == 64) {
+    // tf2::transformToEigen(robot_pose_) (dd_simple…cpp:355)
+    quat_to_matrix(q.pose[3], q.pose[4], q.pose[5], q.pose[6], s_R0);
+    s_t0[0] = q.pose[0]; s_t0[1] = q.pose[1]; s_t0[2] = q.pose[2];
+  }
+  if (tid == 96 && q.plan_n > 0) {
+    const double* e = plan7 + (q.plan_off + q.plan_n - 1) * 7;  // prune_plan_.poses.back()
+    quat_to_matrix(e[3], e[4], e[5], e[6], s_gL);
+    s_gt[0] = e[0]; s_gt[1] = e[1]; s_gt[2] = e[2];
+  }
   // pcl_prune_plan_: float-cast plan positions (model_shared_data.h:83-91)
   if (chunk == 0)
     for (int i = tid; i < q.plan_n; i += blockDim.x) {
@@ -385,7 +398,17 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
     s_wvalid[warp] = __popc(mv);
   }
   int cnt_lo = (valid && s < lo) ? 1 : 0, cnt_hi = (valid && s < hi) ? 1 : 0;
-  unsigned long long poses = (valid && s >= lo && s < hi) ? (unsigned long long)steps : 0ull;
+  const bool in_shard = valid && s >= lo && s < hi;
+  const unsigned long long my_poses = in_shard ? (unsigned long long)steps : 0ull;
+  unsigned long long poses = my_poses;
+  // inclusive warp scan of the shard's pose counts -> row of every trajectory in the pose array
+  unsigned long long pscan = my_poses;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long tv = __shfl_up_sync(kFull, pscan, o);
+    if (lane >= o) pscan += tv;
+  }
+  if (lane == 31) s_wposes[warp] = pscan;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     cnt_lo += __shfl_xor_sync(kFull, cnt_lo, o);
@@ -401,10 +424,11 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
   }
   __syncthreads();
   int offk = 0, offv = 0, totk = 0, totv = 0;
+  unsigned long long offp = 0ull;
 #pragma unroll
   for (int w = 0; w < kPrepThreads / 32; ++w) {
     const int a = s_wkeep[w], b = s_wvalid[w];
-    if (w < warp) { offk += a; offv += b; }
+    if (w < warp) { offk += a; offv += b; offp += s_wposes[w]; }
     totk += a; totv += b;
   }
   PrepAgg* my_aggs = aggs + (size_t)robot * n_chunks;
@@ -449,15 +473,49 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
   const int base_keep = s_red[0], base_valid = s_red[1];
 
   const unsigned lt = (1u << lane) - 1u;
+  const long long pose_row = (long long)robot * pose_stride + (long long)(s_poses + offp + pscan - my_poses);
+  size_t rec = 0;
+  bool roll = false;
   if (valid) {
     const int sample_index = base_keep + offk + __popc(mk & lt);
     const int id = base_valid + offv + __popc(mv & lt);
     if (id < t_cap) {
-      const size_t o = (size_t)robot * t_cap + id;
-      rec_vel[o] = make_float4(v0, v1, v2, 0.f);
-      rec_steps[o] = steps;
-      rec_dt[o] = dt;
-      rec_sample[o] = sample_index;
+      rec = (size_t)robot * t_cap + id;
+      rec_vel[rec] = make_float4(v0, v1, v2, 0.f);
+      rec_steps[rec] = steps;
+      rec_dt[rec] = dt;
+      rec_sample[rec] = sample_index;
+      rec_pose_off[rec] = pose_row;
+      roll = in_shard && (long long)(s_poses + offp + pscan) <= pose_stride;
+    }
+  }
+  // ---- forward simulation of this thread's trajectory (computeNewPositions, dd_simple…cpp:457-464,
+  // omni_simple…cpp:498-505): x,y,th in the robot frame after every step, then the pure-pursuit terms
+  // of the last pose ----
+  if (roll) {
+    float x = 0.f, y = 0.f, th = 0.f;
+    const double wdt = (double)v2 * dt;  // loop invariant of th' = (float)(th + w*dt)
+    float4* out = pose_rows + pose_row;
+    for (int k = 0; k < steps; ++k) {
+      double ex, ey;
+      if (P.theory == B200LP_THEORY_OMNI_SIMPLE) {
+        const double a = 1.57079632679489661923 + (double)th;  // M_PI_2 + pos[2]
+        ex = ((double)(v0 * lpm::cosf(th)) + (double)v1 * lpm::cos(a)) * dt;
+        ey = ((double)(v0 * lpm::sinf(th)) + (double)v1 * lpm::sin(a)) * dt;
+      } else {
+        ex = (double)(v0 * lpm::cosf(th)) * dt;
+        ey = (double)(v0 * lpm::sinf(th)) * dt;
+      }
+      x = (float)((double)x + ex);
+      y = (float)((double)y + ey);
+      th = (float)((double)th + wdt);
+      out[k] = make_float4(x, y, th, 0.f);
+    }
+    if (want_pp && q.plan_n > 0 && steps >= 2) {
+      double Lm[9], tv[3], dist, yaw;
+      pose_affine(s_R0, s_t0, x, y, th, Lm, tv);
+      pure_pursuit_terms(Lm, tv, s_gL, s_gt, &dist, &yaw);
+      rec_pp[rec] = make_double2(dist, yaw);
     }
   }
   if (chunk == n_chunks - 1 && tid == 0) {  // the last ticket: every chunk of this robot has started
@@ -467,7 +525,7 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
     m.n_traj = base_valid + totv;
     m.t_begin = s_red[3] + a->cnt_lo;
     m.t_end = s_red[4] + a->cnt_hi;
-    m.error = (s_red[5] | a->err) | (m.n_traj > t_cap ? 2 : 0);
+    m.error = (s_red[5] | a->err) | (m.n_traj > t_cap ? 2 : 0) | ((long long)s_poses + a->poses > pose_stride ? 4 : 0);
     m.pad = 0;
     m.n_poses = (long long)s_poses + a->poses;
     meta[robot] = m;
@@ -487,7 +545,7 @@ __device__ __forceinline__ bool better(unsigned long long ca, int ia, unsigned l
 }
 
 struct WarpCtx {
-  double R0[9], t0[3], gL[9], gt[3];
+  double R0[9], t0[3];
 };
 
 struct CtaShared {
@@ -500,8 +558,9 @@ struct CtaShared {
 __global__ void __launch_bounds__(kThreads, 4)
 plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, const RobotMeta* __restrict__ meta, int n_robots,
             int t_cap, int cap_local, const float4* __restrict__ rec_vel, const int* __restrict__ rec_steps,
-            const double* __restrict__ rec_dt, const float4* __restrict__ plan_pts, const double* __restrict__ plan7,
-            double* __restrict__ out_cost, double* __restrict__ out_scores, int* __restrict__ out_first_hit,
+            const long long* __restrict__ rec_pose_off, const float4* __restrict__ poses,
+            const double2* __restrict__ rec_pp, const float4* __restrict__ plan_pts, double* __restrict__ out_cost,
+            double* __restrict__ out_scores, int* __restrict__ out_first_hit,
             unsigned long long* __restrict__ work_counter) {
   __shared__ CtaShared S;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -543,11 +602,6 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, const Robot
         quat_to_matrix(q.pose[3], q.pose[4], q.pose[5], q.pose[6], W.R0);
         W.t0[0] = q.pose[0]; W.t0[1] = q.pose[1]; W.t0[2] = q.pose[2];
       }
-      if (lane == 1 && plan_n > 0) {
-        const double* e = plan7 + (q.plan_off + plan_n - 1) * 7;  // prune_plan_.poses.back()
-        quat_to_matrix(e[3], e[4], e[5], e[6], W.gL);
-        W.gt[0] = e[0]; W.gt[1] = e[1]; W.gt[2] = e[2];
-      }
       __syncwarp();
     }
     if (local >= n_local) continue;
@@ -555,7 +609,7 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, const Robot
     const size_t rec = (size_t)robot * t_cap + id;
     const float4 vel = rec_vel[rec];
     const int n = rec_steps[rec];
-    const double dt = rec_dt[rec];
+    const float4* traj_poses = poses + rec_pose_off[rec];  // prep_kernel's forward simulation
 
     // ---- critic stack analysis (warp-uniform) ------------------------------------------------
     // A critic's value may be known before the rollout (collision_model.cpp:53-55, stick_path_model.cpp:53-55,
@@ -616,20 +670,16 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, const Robot
     const bool any_rollout_work = need_box || need_mm || need_stick || need_last_nn || need_pp;
 
     // ---- rollout + query, 32 poses at a time ---------------------------------------------------
-    Carry carry = {0.f, 0.f, 0.f};
     double stick_sum = 0.0;
     float last_nn = 0.f;
-    double pp_dist = 0.0, pp_yaw = 0.0;
     int hit_box = -1, hit_mm = -1;  // first colliding pose per collision-critic kind
-    bool done = !any_rollout_work;
+    const bool done = !any_rollout_work;
     for (int base = 0; base < n && !done; base += 32) {
-      float px, py, pth;
-      rollout32(carry, lane, C.par.theory, vel.x, vel.y, vel.z, dt, px, py, pth);
       const int k = base + lane;
       const bool live = k < n;
+      const float4 pz = live ? __ldg(traj_poses + k) : make_float4(0.f, 0.f, 0.f, 0.f);
       double L[9], t[3];
-      pose_affine(W.R0, W.t0, px, py, pth, L, t);
-      if (need_pp && k == n - 1) pure_pursuit_terms(L, t, W.gL, W.gt, &pp_dist, &pp_yaw);
+      pose_affine(W.R0, W.t0, pz.x, pz.y, pz.z, L, t);
       CellBox cbx;
       pose_geometry(C, g, L, t, stash, pre, &cbx, lane, live, nullptr);
       group_union(cbx);
@@ -672,9 +722,11 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, const Robot
       }
       __syncwarp();
     }
+    double pp_dist = 0.0, pp_yaw = 0.0;
     if (need_pp) {
-      pp_dist = __shfl_sync(kFull, pp_dist, (n - 1) & 31);
-      pp_yaw = __shfl_sync(kFull, pp_yaw, (n - 1) & 31);
+      const double2 pp = rec_pp[rec];
+      pp_dist = pp.x;
+      pp_yaw = pp.y;
     }
 
     // ---- StackedScoringModel::scoreTrajectory (stacked_scoring_model.cpp:75-93) -----------------
