@@ -87,12 +87,52 @@ def make_workload(name: str, rank: int):
 
 
 class ClockSampler:
+    """SM clock + throttle reasons DURING the timed region: an NVML polling thread (10 ms period); falls back to the
+    recipe's `nvidia-smi --query-gpu=... -lms` subprocess when pynvml is unavailable."""
+
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
         self.proc = None
         self.path = f"/tmp/b200lp_clocks_{os.getpid()}.csv"
+        self.thread = None
+        self.samples = []
+
+    def _nvml_loop(self, pynvml, handle):
+        R = pynvml
+        names = [("hw_slowdown", getattr(R, "nvmlClocksEventReasonHwSlowdown", getattr(R, "nvmlClocksThrottleReasonHwSlowdown", 0x8))),
+                 ("hw_thermal_slowdown", getattr(R, "nvmlClocksEventReasonHwThermalSlowdown", getattr(R, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40))),
+                 ("sw_thermal_slowdown", getattr(R, "nvmlClocksEventReasonSwThermalSlowdown", getattr(R, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20))),
+                 ("sw_power_cap", getattr(R, "nvmlClocksEventReasonSwPowerCap", getattr(R, "nvmlClocksThrottleReasonSwPowerCap", 0x4)))]
+        get_reasons = getattr(R, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(R, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop:
+            try:
+                sm = R.nvmlDeviceGetClockInfo(handle, R.NVML_CLOCK_SM)
+                mask = int(get_reasons(handle))
+                self.samples.append((float(sm), [n for n, bit in names if mask & int(bit)]))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def start(self):
+        try:
+            import threading
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu])
+                except Exception:
+                    idx = self.gpu
+            handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            self._stop = False
+            self.thread = threading.Thread(target=self._nvml_loop, args=(pynvml, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -105,6 +145,13 @@ class ClockSampler:
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.thread is not None:
+            self._stop = True
+            self.thread.join(timeout=2)
+            if self.samples:
+                out.update(sm_mhz=statistics.median([s for s, _ in self.samples]), sm_max_mhz=self.sm_max, samples=len(self.samples),
+                           reasons=sorted({r for _, rs in self.samples for r in rs}))
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -245,7 +292,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
-    dev_ms, plan_k_ms, prep_k_ms, wall_ms = [], [], [], []
+    dev_ms, plan_k_ms, prep_k_ms, argmin_k_ms, wall_ms = [], [], [], [], []
     for _ in range(args.steps):
         flush_l2()
         t0 = time.perf_counter()
@@ -255,6 +302,7 @@ def main():
         km = lp.last_kernel_ms()
         plan_k_ms.append(km["plan_kernel"])
         prep_k_ms.append(km["prep_kernel"])
+        argmin_k_ms.append(km["argmin_kernel"])
     barrier()
     launches = lp.launch_count() - launches0
     t_dev = sum(dev_ms) / 1e3
@@ -327,7 +375,8 @@ def main():
                              "ms_per_step": sum(wall_ms) / len(wall_ms), "p50_ms": statistics.median(wall_ms),
                              "what": "b200lp_plan only (query+plan upload, kernels, result read-back), host wall clock, rank 0"},
         "gpu_launches": int(launches),
-        "kernel_ms": {"prep_kernel": sum(prep_k_ms) / len(prep_k_ms), "plan_kernel": k_ms, "grid_build_total": grid_ms},
+        "kernel_ms": {"prep_kernel": sum(prep_k_ms) / len(prep_k_ms), "plan_kernel": k_ms,
+                      "argmin_kernel": sum(argmin_k_ms) / len(argmin_k_ms), "grid_build_total": grid_ms},
         "roofline": roofline,
         "result": {"best_id": int(r.best_id), "best_cost": float(r.best_cost), "n_collided": int(r.n_collided)},
     }

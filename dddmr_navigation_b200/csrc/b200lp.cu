@@ -81,7 +81,7 @@ struct b200lp_ctx {
   size_t raw_stride = 0;
   DevBuf<char> d_raw;
   DevBuf<float4> d_pts;
-  DevBuf<uint32_t> d_cell_start, d_fill, d_keys, d_block_sums;
+  DevBuf<uint32_t> d_cell_start, d_fill, d_keys, d_block_sums, d_sat;
   DevBuf<BoundsDev> d_bounds;
   DevBuf<uint32_t> d_total;
   PinBuf<BoundsDev> h_bounds;
@@ -106,6 +106,8 @@ struct b200lp_ctx {
   DevBuf<float4> d_poses;                // forward-simulated (x, y, th) of every pose of the cycle, robot frame
   DevBuf<double2> d_rec_pp;              // pure-pursuit (distance, yaw) of every trajectory's last pose
   long long pose_stride = 0;             // rows of d_poses reserved per robot
+  DevBuf<BlockBest> d_partial;           // argmin_kernel CTA partials
+  DevBuf<unsigned> d_tickets2;           // argmin_kernel last-CTA tickets, one per robot (self-resetting)
   DevBuf<unsigned> d_tickets;            // prep_kernel chunk tickets, one per robot (self-resetting)
   DevBuf<PrepAgg> d_aggs;                // prep_kernel look-back aggregates
   DevBuf<unsigned long long> d_work;     // plan_kernel work counter (reset by argmin_kernel)
@@ -249,9 +251,13 @@ int build_grid(b200lp_ctx* ctx, size_t n, size_t stride) {
   CK(ctx->d_block_sums.reserve(nb));
   CK(ctx->d_keys.reserve(n));
   CK(ctx->d_pts.reserve(std::max<size_t>(g.n_kept, 1)));
+  const size_t n_sat = ((size_t)g.nx + 1) * ((size_t)g.ny + 1) * ((size_t)g.nz + 1);
+  CK(ctx->d_sat.reserve(n_sat));
   CK(cudaMemsetAsync(ctx->d_cell_start.p, 0, (n_cells + 1) * sizeof(uint32_t), ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_sat.p, 0, n_sat * sizeof(uint32_t), ctx->stream));
   g.pts = ctx->d_pts.p;
   g.cell_start = ctx->d_cell_start.p;
+  g.sat = ctx->d_sat.p;
   if (g.n_kept) {
     hist_kernel<<<grid_blocks(n, 256, sms), 256, 0, ctx->stream>>>(ctx->d_raw.p, n, stride, g, ctx->d_cell_start.p,
                                                                    ctx->d_keys.p);
@@ -262,7 +268,10 @@ int build_grid(b200lp_ctx* ctx, size_t n, size_t stride) {
                        ctx->stream));
     scatter_kernel<<<grid_blocks(n, 256, sms), 256, 0, ctx->stream>>>(ctx->d_raw.p, n, stride, ctx->d_keys.p,
                                                                       ctx->d_fill.p, ctx->d_pts.p);
-    ctx->launches += 5;
+    const size_t ny_threads = ((size_t)g.nx + 1) * (size_t)g.nz, nz_threads = ((size_t)g.nx + 1) * ((size_t)g.ny + 1);
+    sat_y_kernel<<<(unsigned)((ny_threads + 255) / 256), 256, 0, ctx->stream>>>(g, ctx->d_sat.p);
+    sat_z_kernel<<<(unsigned)((nz_threads + 255) / 256), 256, 0, ctx->stream>>>(g, ctx->d_sat.p);
+    ctx->launches += 7;
   }
   CK(cudaGetLastError());
   ctx->have_cloud = true;
@@ -304,6 +313,12 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   for (int k = 0; k < ctx->C.n_critics; ++k) want_pp |= ctx->C.critics[k].kind == B200LP_CRITIC_PURE_PURSUIT;
   CK(ctx->d_rec_pp.reserve(want_pp ? T : 1));
   ctx->pose_stride = pose_stride;
+  const int argmin_ctas = (int)std::max(1, std::min(kArgminMaxCtas, (cap_local + 2047) / 2048));
+  CK(ctx->d_partial.reserve(n_robots * (size_t)kArgminMaxCtas));
+  if (ctx->d_tickets2.cap < n_robots) {
+    CK(ctx->d_tickets2.reserve(n_robots));
+    CK(cudaMemsetAsync(ctx->d_tickets2.p, 0, ctx->d_tickets2.cap * sizeof(unsigned), ctx->stream));
+  }
   if (ctx->d_tickets.cap < n_robots) {
     CK(ctx->d_tickets.reserve(n_robots));
     CK(cudaMemsetAsync(ctx->d_tickets.p, 0, ctx->d_tickets.cap * sizeof(unsigned), ctx->stream));
@@ -352,9 +367,9 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
       ctx->d_rec_steps.p, ctx->d_rec_pose_off.p, ctx->d_poses.p, ctx->d_rec_pp.p, ctx->d_plan_pts.p, ctx->d_cost.p,
       ctx->d_scores.p, ctx->d_first_hit.p, ctx->d_work.p);
   CK(cudaEventRecord(ctx->ev[5], ctx->stream));
-  argmin_kernel<<<(unsigned)n_robots, kArgminThreads, 0, ctx->stream>>>(ctx->C, ctx->d_meta.p, t_cap, ctx->d_rec_vel.p,
-                                                                        ctx->d_cost.p, ctx->d_first_hit.p,
-                                                                        ctx->d_results.p, ctx->d_work.p);
+  argmin_kernel<<<dim3((unsigned)argmin_ctas, (unsigned)n_robots), kArgminThreads, 0, ctx->stream>>>(
+      ctx->C, ctx->d_meta.p, t_cap, ctx->d_rec_vel.p, ctx->d_cost.p, ctx->d_first_hit.p, ctx->d_partial.p,
+      ctx->d_tickets2.p, ctx->d_results.p, ctx->d_work.p);
   ctx->launches += 3;
   CK(cudaEventRecord(ctx->ev[2], ctx->stream));
   CK(cudaMemcpyAsync(ctx->h_results.p, ctx->d_results.p, n_robots * sizeof(b200lp_result), cudaMemcpyDeviceToHost, ctx->stream));
@@ -463,11 +478,11 @@ void b200lp_destroy(b200lp_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   ctx->d_raw.release(); ctx->d_pts.release(); ctx->d_cell_start.release(); ctx->d_fill.release();
-  ctx->d_keys.release(); ctx->d_block_sums.release(); ctx->d_bounds.release(); ctx->d_total.release();
+  ctx->d_keys.release(); ctx->d_block_sums.release(); ctx->d_sat.release(); ctx->d_bounds.release(); ctx->d_total.release();
   ctx->h_bounds.release(); ctx->d_robots.release(); ctx->d_meta.release(); ctx->d_plan7.release();
   ctx->d_plan_pts.release(); ctx->d_rec_vel.release(); ctx->d_rec_steps.release(); ctx->d_rec_sample.release();
   ctx->d_first_hit.release(); ctx->d_rec_dt.release(); ctx->d_cost.release(); ctx->d_scores.release();
-  ctx->d_rec_pose_off.release(); ctx->d_poses.release(); ctx->d_rec_pp.release(); ctx->d_tickets.release(); ctx->d_aggs.release(); ctx->d_work.release(); ctx->d_results.release(); ctx->d_count.release(); ctx->d_scratch.release();
+  ctx->d_rec_pose_off.release(); ctx->d_poses.release(); ctx->d_rec_pp.release(); ctx->d_partial.release(); ctx->d_tickets2.release(); ctx->d_tickets.release(); ctx->d_aggs.release(); ctx->d_work.release(); ctx->d_results.release(); ctx->d_count.release(); ctx->d_scratch.release();
   ctx->h_robots.release(); ctx->h_plan7.release(); ctx->h_results.release(); ctx->h_meta.release();
   ctx->h_count.release();
   for (auto& ev : ctx->ev)
@@ -680,10 +695,11 @@ int b200lp_last_timing(const b200lp_ctx* ctx, float* ms_upload, float* ms_grid_b
   return B200LP_OK;
 }
 
-int b200lp_last_kernel_ms(const b200lp_ctx* ctx, float* ms_prep_kernel, float* ms_plan_kernel) {
+int b200lp_last_kernel_ms(const b200lp_ctx* ctx, float* ms_prep_kernel, float* ms_plan_kernel, float* ms_argmin_kernel) {
   if (!ctx) return B200LP_E_INVALID;
   if (ms_prep_kernel) *ms_prep_kernel = ctx->ms_k_prep;
   if (ms_plan_kernel) *ms_plan_kernel = ctx->ms_k_plan;
+  if (ms_argmin_kernel) *ms_argmin_kernel = ctx->ms_k_argmin;
   return B200LP_OK;
 }
 

@@ -42,6 +42,7 @@ struct CellBox {
 struct GridDev {
   const float4* pts;           // cell-sorted points: x,y,z, w = original index bits
   const uint32_t* cell_start;  // n_cells + 1 offsets into pts
+  const uint32_t* sat;         // summed-volume table, (nz+1)(ny+1)(nx+1): points with cell < (X,Y,Z) componentwise
   float org[3];
   float inv_xy, inv_z;
   int nx, ny, nz;
@@ -369,13 +370,25 @@ __device__ __forceinline__ void pose_geometry(const Consts& C, const GridDev& g,
     const float fz0 = cell_f(lo[2], g.org[2], g.inv_z), fz1 = cell_f(hi[2], g.org[2], g.inv_z);
     const bool empty = !(lo[0] <= hi[0] && lo[1] <= hi[1] && lo[2] <= hi[2]) || fx1 < 0.f || fy1 < 0.f || fz1 < 0.f ||
                        fx0 > (float)(g.nx - 1) || fy0 > (float)(g.ny - 1) || fz0 > (float)(g.nz - 1) || g.n_kept == 0;
-    if (empty) {
-      cb->x0 = cb->y0 = cb->z0 = 0x7fffffff;
-      cb->x1 = cb->y1 = cb->z1 = -1;
-    } else {
-      cb->x0 = (int)fmaxf(fx0, 0.f); cb->x1 = (int)fminf(fx1, (float)(g.nx - 1));
-      cb->y0 = (int)fmaxf(fy0, 0.f); cb->y1 = (int)fminf(fy1, (float)(g.ny - 1));
-      cb->z0 = (int)fmaxf(fz0, 0.f); cb->z1 = (int)fminf(fz1, (float)(g.nz - 1));
+    cb->x0 = cb->y0 = cb->z0 = 0x7fffffff;
+    cb->x1 = cb->y1 = cb->z1 = -1;
+    if (!empty) {
+      const int x0 = (int)fmaxf(fx0, 0.f), x1 = (int)fminf(fx1, (float)(g.nx - 1));
+      const int y0 = (int)fmaxf(fy0, 0.f), y1 = (int)fminf(fy1, (float)(g.ny - 1));
+      const int z0 = (int)fmaxf(fz0, 0.f), z1 = (int)fminf(fz1, (float)(g.nz - 1));
+      // number of cloud points in those cells (inclusion-exclusion on the summed-volume table, exact in
+      // modular u32 arithmetic): most poses drive through free space and are culled right here
+      const size_t sx = (size_t)(g.nx + 1), sy = (size_t)(g.ny + 1) * sx;
+      const uint32_t* s0 = g.sat + (size_t)z0 * sy;
+      const uint32_t* s1 = g.sat + (size_t)(z1 + 1) * sy;
+      const size_t a0 = (size_t)y0 * sx, a1 = (size_t)(y1 + 1) * sx;
+      const uint32_t hi = (__ldg(s1 + a1 + x1 + 1) - __ldg(s1 + a1 + x0)) - (__ldg(s1 + a0 + x1 + 1) - __ldg(s1 + a0 + x0));
+      const uint32_t lo = (__ldg(s0 + a1 + x1 + 1) - __ldg(s0 + a1 + x0)) - (__ldg(s0 + a0 + x1 + 1) - __ldg(s0 + a0 + x0));
+      if (hi - lo != 0u) {
+        cb->x0 = x0; cb->x1 = x1;
+        cb->y0 = y0; cb->y1 = y1;
+        cb->z0 = z0; cb->z1 = z1;
+      }
     }
   }
 }
@@ -437,6 +450,7 @@ __device__ __forceinline__ unsigned sweep_points(const GridDev& g, const float* 
   if (ub.x0 > ub.x1) return 0u;
   const int nyr = ub.y1 - ub.y0 + 1;
   const int nrows = nyr * (ub.z1 - ub.z0 + 1);
+  const float inv_nyr = 1.0f / (float)nyr;
 
   // pre-test coefficients of the 4 poses, in registers
   float4 ca[kGroup], cb[kGroup], cc[kGroup], ch[kGroup];
@@ -461,7 +475,12 @@ __device__ __forceinline__ unsigned sweep_points(const GridDev& g, const float* 
     const int r = r0 + lane;
     uint32_t beg = 0, end = 0;
     if (r < nrows) {
-      const int iy = ub.y0 + r % nyr, iz = ub.z0 + r / nyr;
+      // r / nyr and r % nyr without the integer-division sequence: float estimate, then one correction step
+      int qz = (int)((float)r * inv_nyr);
+      int ry = r - qz * nyr;
+      if (ry < 0) { --qz; ry += nyr; }
+      else if (ry >= nyr) { ++qz; ry -= nyr; }
+      const int iy = ub.y0 + ry, iz = ub.z0 + qz;
       const size_t base = ((size_t)iz * g.ny + iy) * (size_t)g.nx;
       beg = __ldg(g.cell_start + base + ub.x0);
       end = __ldg(g.cell_start + base + ub.x1 + 1);

@@ -69,13 +69,31 @@ __global__ void __launch_bounds__(256) bounds_kernel(const char* __restrict__ ra
     }
     cnt += __shfl_xor_sync(kFull, cnt, o);
   }
-  if ((threadIdx.x & 31) == 0 && cnt) {
+  // one set of global atomics per CTA (same-address atomics serialise in L2)
+  __shared__ float s_mn[8][3], s_mx[8][3];
+  __shared__ unsigned s_cnt[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      atomicMin(&b->mn[a], f2ord(mn[a]));
-      atomicMax(&b->mx[a], f2ord(mx[a]));
+    for (int a = 0; a < 3; ++a) { s_mn[warp][a] = mn[a]; s_mx[warp][a] = mx[a]; }
+    s_cnt[warp] = cnt;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned total = 0;
+    for (int w = 0; w < 8; ++w) {
+      total += s_cnt[w];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { mn[a] = fminf(mn[a], s_mn[w][a]); mx[a] = fmaxf(mx[a], s_mx[w][a]); }
     }
-    atomicAdd(&b->n_finite, cnt);
+    if (total) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        atomicMin(&b->mn[a], f2ord(mn[a]));
+        atomicMax(&b->mx[a], f2ord(mx[a]));
+      }
+      atomicAdd(&b->n_finite, total);
+    }
   }
 }
 
@@ -184,6 +202,32 @@ __global__ void __launch_bounds__(256) scatter_kernel(const char* __restrict__ r
     const float3 v = load_xyz(raw, i, stride);
     const uint32_t slot = atomicAdd(fill + key, 1u);
     out[slot] = make_float4(v.x, v.y, v.z, __uint_as_float((uint32_t)i));
+  }
+}
+
+// Summed-volume table of the per-cell point counts: sat[Z][Y][X] = points with cell (x,y,z) < (X,Y,Z)
+// componentwise, dims (nz+1)(ny+1)(nx+1), zero-initialised by the caller. The x prefix comes straight from
+// cell_start; sat_y_kernel accumulates along y, sat_z_kernel along z. Consecutive threads walk consecutive X.
+__global__ void __launch_bounds__(256) sat_y_kernel(GridDev g, uint32_t* __restrict__ sat) {
+  const size_t nxp = (size_t)g.nx + 1;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nxp * (size_t)g.nz) return;
+  const int X = (int)(i % nxp), z = (int)(i / nxp);
+  uint32_t run = 0u;
+  for (int y = 0; y < g.ny; ++y) {
+    const size_t row = ((size_t)z * g.ny + y) * (size_t)g.nx;
+    run += g.cell_start[row + X] - g.cell_start[row];
+    sat[((size_t)(z + 1) * (g.ny + 1) + (y + 1)) * nxp + X] = run;
+  }
+}
+__global__ void __launch_bounds__(256) sat_z_kernel(GridDev g, uint32_t* __restrict__ sat) {
+  const size_t plane = ((size_t)g.nx + 1) * ((size_t)g.ny + 1);
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= plane) return;
+  uint32_t run = 0u;
+  for (int Z = 1; Z <= g.nz; ++Z) {
+    run += sat[(size_t)Z * plane + i];
+    sat[(size_t)Z * plane + i] = run;
   }
 }
 
@@ -555,7 +599,10 @@ struct CtaShared {
   float4 plan[kPlanSmem];
 };
 
-__global__ void __launch_bounds__(kThreads, 4)
+#ifndef B200LP_PLAN_MIN_CTAS
+#define B200LP_PLAN_MIN_CTAS 5
+#endif
+__global__ void __launch_bounds__(kThreads, B200LP_PLAN_MIN_CTAS)
 plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, const RobotMeta* __restrict__ meta, int n_robots,
             int t_cap, int cap_local, const float4* __restrict__ rec_vel, const int* __restrict__ rec_steps,
             const long long* __restrict__ rec_pose_off, const float4* __restrict__ poses,
@@ -581,11 +628,13 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, const Robot
   int cur_robot = -1, t_begin = 0, n_local = 0, plan_n = 0;
   double heading_deviation = 0.0;
   const float4* plan = nullptr;
+  // work items are fetched one ahead, so the atomic's round trip overlaps the previous trajectory
+  unsigned long long pending = 0ull;
+  if (lane == 0) pending = atomicAdd(work_counter, 1ull);
   for (;;) {
-    unsigned long long w = 0ull;
-    if (lane == 0) w = atomicAdd(work_counter, 1ull);
-    w = __shfl_sync(kFull, w, 0);
+    const unsigned long long w = __shfl_sync(kFull, pending, 0);
     if (w >= total) break;
+    if (lane == 0) pending = atomicAdd(work_counter, 1ull);
     const int robot = (int)(w / (unsigned long long)cap_local);
     const int local = (int)(w - (unsigned long long)robot * (unsigned long long)cap_local);
     if (robot != cur_robot) {
@@ -604,8 +653,10 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, const Robot
       }
       __syncwarp();
     }
-    if (local >= n_local) continue;
-    const int id = t_begin + local;
+    if (local >= n_local) continue;  // padding of the (robot, local) work space
+    // hand trajectories out from the END of the list: the sample grid is ordered by rising linear speed, so the
+    // longest rollouts start first and the kernel's tail is made of short ones
+    const int id = t_begin + (n_local - 1 - local);
     const size_t rec = (size_t)robot * t_cap + id;
     const float4 vel = rec_vel[rec];
     const int n = rec_steps[rec];
@@ -770,63 +821,112 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, const Robot
   }
 }
 
-// Local_Planner::getBestTrajectory (local_planner.cpp:447-480) over the costs plan_kernel wrote: one CTA per robot.
+// Local_Planner::getBestTrajectory (local_planner.cpp:447-480) over the costs plan_kernel wrote.
+// grid = (B, robots): B CTAs split a robot's trajectory range, the last one to finish (ticket) merges the B
+// partials and writes b200lp_result. The (cost bits, id) order is total, so any merge tree gives the reference's
+// sequential `<=` scan result.
 constexpr int kArgminThreads = 256;
-__global__ void __launch_bounds__(kArgminThreads)
-argmin_kernel(Consts C, const RobotMeta* __restrict__ meta, int t_cap, const float4* __restrict__ rec_vel,
-              const double* __restrict__ cost, const int* __restrict__ first_hit, b200lp_result* __restrict__ results,
-              unsigned long long* __restrict__ work_counter) {
-  __shared__ BlockBest s_best[kArgminThreads / 32];
-  const int robot = blockIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const RobotMeta m = meta[robot];
-  if (blockIdx.x == 0 && threadIdx.x == 0) *work_counter = 0ull;  // ready for the next plan_kernel launch
-  unsigned long long cb = ~0ull;
-  int bi = -1, ncoll = 0;
-  for (int id = m.t_begin + threadIdx.x; id < m.t_end; id += kArgminThreads) {
-    const size_t rec = (size_t)robot * t_cap + id;
-    const double c = cost[rec];
-    ncoll += first_hit[rec] >= 0 ? 1 : 0;
-    if (c >= 0.0 && c <= 9999999.0) {  // local_planner.cpp:450,460
-      const unsigned long long bits = lpm::d2u(c);
-      if (cb == ~0ull || better(bits, id, cb, bi)) { cb = bits; bi = id; }
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const unsigned long long ocb = __shfl_xor_sync(kFull, cb, o);
-    const int obi = __shfl_xor_sync(kFull, bi, o);
-    ncoll += __shfl_xor_sync(kFull, ncoll, o);
+constexpr int kArgminMaxCtas = 64;
+
+struct Best {
+  unsigned long long cb;  // cost bits, ~0 = none
+  int bi, ncoll;
+  __device__ __forceinline__ void take(unsigned long long ocb, int obi) {
     if (ocb != ~0ull && (cb == ~0ull || better(ocb, obi, cb, bi))) { cb = ocb; bi = obi; }
   }
+  __device__ __forceinline__ void warp_reduce() {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long ocb = __shfl_xor_sync(kFull, cb, o);
+      const int obi = __shfl_xor_sync(kFull, bi, o);
+      ncoll += __shfl_xor_sync(kFull, ncoll, o);
+      take(ocb, obi);
+    }
+  }
+};
+
+__global__ void __launch_bounds__(kArgminThreads)
+argmin_kernel(Consts C, const RobotMeta* __restrict__ meta, int t_cap, const float4* __restrict__ rec_vel,
+              const double* __restrict__ cost, const int* __restrict__ first_hit, BlockBest* partial,
+              unsigned* __restrict__ tickets, b200lp_result* __restrict__ results,
+              unsigned long long* __restrict__ work_counter) {
+  __shared__ BlockBest s_best[kArgminThreads / 32];
+  __shared__ int s_last;
+  const int robot = blockIdx.y, B = gridDim.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const RobotMeta m = meta[robot];
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *work_counter = 0ull;  // ready for the next plan_kernel
+  const int n_local = m.t_end - m.t_begin;
+  const int per = (n_local + B - 1) / B;
+  const int lo = m.t_begin + (int)blockIdx.x * per, hi = min(m.t_end, lo + per);
+  Best b = {~0ull, -1, 0};
+  for (int id0 = lo + (int)threadIdx.x; id0 < hi; id0 += kArgminThreads * 4) {
+    double c[4];
+    int fh[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {  // independent loads first
+      const int id = id0 + u * kArgminThreads;
+      const size_t rec = (size_t)robot * t_cap + id;
+      c[u] = id < hi ? cost[rec] : -1.0;
+      fh[u] = id < hi ? first_hit[rec] : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      b.ncoll += fh[u] >= 0 ? 1 : 0;
+      if (c[u] >= 0.0 && c[u] <= 9999999.0) b.take(lpm::d2u(c[u]), id0 + u * kArgminThreads);  // local_planner.cpp:450,460
+    }
+  }
+  b.warp_reduce();
   if (lane == 0) {
-    s_best[warp].cost_bits = cb;
-    s_best[warp].id = bi;
-    s_best[warp].n_collided = ncoll;
+    s_best[warp].cost_bits = b.cb;
+    s_best[warp].id = b.bi;
+    s_best[warp].n_collided = b.ncoll;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    cb = ~0ull; bi = -1; ncoll = 0;
-    for (int w = 0; w < kArgminThreads / 32; ++w) {
-      const BlockBest b = s_best[w];
-      ncoll += b.n_collided;
-      if (b.cost_bits != ~0ull && (cb == ~0ull || better(b.cost_bits, b.id, cb, bi))) { cb = b.cost_bits; bi = b.id; }
+  if (warp == 0) {
+    b.cb = ~0ull; b.bi = -1; b.ncoll = 0;
+    if (lane < kArgminThreads / 32) { b.cb = s_best[lane].cost_bits; b.bi = s_best[lane].id; b.ncoll = s_best[lane].n_collided; }
+    b.warp_reduce();
+    if (lane == 0) {
+      s_last = 1;
+      if (B > 1) {
+        BlockBest pb;
+        pb.cost_bits = b.cb; pb.id = b.bi; pb.n_collided = b.ncoll;
+        partial[(size_t)robot * B + blockIdx.x] = pb;
+        __threadfence();
+        s_last = atomicAdd(tickets + robot, 1u) == (unsigned)(B - 1) ? 1 : 0;
+      }
     }
+  }
+  __syncthreads();
+  if (!s_last || warp != 0) return;
+  if (B > 1) {  // merge the CTA partials
+    __threadfence();
+    b.cb = ~0ull; b.bi = -1; b.ncoll = 0;
+    for (int i = lane; i < B; i += 32) {
+      const volatile BlockBest* pb = &partial[(size_t)robot * B + i];
+      b.ncoll += pb->n_collided;
+      b.take(pb->cost_bits, pb->id);
+    }
+    b.warp_reduce();
+  }
+  if (lane == 0) {
     b200lp_result r;
-    r.best_id = (cb == ~0ull) ? -1 : bi;
+    r.best_id = (b.cb == ~0ull) ? -1 : b.bi;
     r.n_samples = m.n_samples;
-    r.n_traj = m.t_end - m.t_begin;
-    r.n_collided = ncoll;
+    r.n_traj = n_local;
+    r.n_collided = b.ncoll;
     r.n_poses = m.n_poses;
-    r.best_cost = (cb == ~0ull) ? -1.0 : lpm::u2d(cb);
+    r.best_cost = (b.cb == ~0ull) ? -1.0 : lpm::u2d(b.cb);
     r.xv = r.yv = r.thetav = 0.0;
-    if (cb != ~0ull) {
-      const float4 v = rec_vel[(size_t)robot * t_cap + bi];
+    if (b.cb != ~0ull) {
+      const float4 v = rec_vel[(size_t)robot * t_cap + b.bi];
       r.xv = (double)v.x;
       r.yv = (C.par.theory == B200LP_THEORY_OMNI_SIMPLE) ? (double)v.y : 0.0;
       r.thetav = (double)v.z;
     }
     results[robot] = r;
+    if (B > 1) tickets[robot] = 0u;  // ready for the next launch
   }
 }
 

@@ -196,9 +196,9 @@ class LocalPlanner:
         return {"ms_upload": a.value, "ms_grid_build": b.value, "ms_plan_kernels": c.value, "ms_readback": d.value}
 
     def last_kernel_ms(self) -> dict:
-        a, b = C.c_float(), C.c_float()
-        self.lib.b200lp_last_kernel_ms(self.h, C.byref(a), C.byref(b))
-        return {"prep_kernel": a.value, "plan_kernel": b.value}
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        self.lib.b200lp_last_kernel_ms(self.h, C.byref(a), C.byref(b), C.byref(c))
+        return {"prep_kernel": a.value, "plan_kernel": b.value, "argmin_kernel": c.value}
 
     def set_cloud_ptr(self, host_ptr: int, n: int, stride: int):
         """set_cloud from a raw host address (e.g. a pinned buffer)."""

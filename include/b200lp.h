@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define B200LP_ABI_VERSION 1
+#define B200LP_ABI_VERSION 2
 
 /* status codes */
 #define B200LP_OK 0
@@ -216,9 +216,10 @@ int b200lp_count_radius(b200lp_ctx* ctx, int64_t* sum_n_r1, int64_t* n_poses);
  * CUDA events on ctx's stream. Any pointer may be NULL. */
 int b200lp_last_timing(const b200lp_ctx* ctx, float* ms_upload, float* ms_grid_build, float* ms_plan_kernels,
                        float* ms_readback);
-/* Per-kernel split of ms_plan_kernels for the last plan call: the sampling/trajectory-list kernel and the
- * fused rollout+query+critics+argmin kernel (the one the roofline is reported for). */
-int b200lp_last_kernel_ms(const b200lp_ctx* ctx, float* ms_prep_kernel, float* ms_plan_kernel);
+/* Per-kernel split of ms_plan_kernels for the last plan call: prep_kernel (velocity sampling, trajectory list,
+ * forward simulation), plan_kernel (pose geometry + obstacle query + critics; the one the roofline is reported
+ * for) and argmin_kernel (best trajectory per robot). */
+int b200lp_last_kernel_ms(const b200lp_ctx* ctx, float* ms_prep_kernel, float* ms_plan_kernel, float* ms_argmin_kernel);
 /* Number of kernels this library launched on ctx's stream since creation. */
 int64_t b200lp_launch_count(const b200lp_ctx* ctx);
 /* Grid geometry of the current cloud (for tests / docs). dims = nx,ny,nz; origin xyz; cell xy,z. */
