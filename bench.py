@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — trajectory-poses scored per second on the BASELINE.json workload.
 
-    python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--workload C2|C1|C3]
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--workload C2|C1|C3|C4|C5]
 
 A "step" is one local-plan cycle of the hot path (sampling -> rollout -> obstacle query -> critics -> argmin)
 for one robot on the named synthetic workload (default C2: 128 x 129 = 16.5 k trajectories x <= 60 poses,
@@ -20,6 +20,9 @@ poses = sum of num_steps over the generated trajectories (exactly what the oracl
 
 N > 1 (torchrun, one rank per GPU): fleet sharding, weak scaling — every rank plans for its own robot on its
 own replica of the map; no collective on the data path. value = poses of all ranks / max-over-ranks time.
+--workload C5 is the batched-fleet configuration (512 robots per GPU on the 8 M-point map, weak scaling, no
+collective); --workload C4 is the sample-sharded one (131 k trajectories split over the ranks, strong scaling,
+one NCCL all-reduce of 16*W bytes per cycle, step time = host-observed kernels + exchange).
 --impl reference times the CPU restatement with all host threads (rank 0 only).
 """
 from __future__ import annotations
@@ -62,28 +65,44 @@ def load_traffic(workload):
     return None
 
 
-def make_workload(name: str, rank: int):
+FLEET_ROBOTS_PER_GPU = 512  # C5: 4096 robots over 8 GPUs
+
+
+def make_workload(name: str, rank: int, world: int = 1):
+    """-> dict(sc, desc, mode, and per-mode inputs). Modes: "single" (one robot, one plan() per step),
+    "shard" (C4: one robot, sample grid split over the ranks, NCCL argmin exchange), "fleet" (C5: plan_batch)."""
     from dddmr_navigation_b200 import synth
+    w = {"mode": "single"}
     if name == "C1":
         sc = synth.c1_ramp()
         desc = "C1: DD simple + default critics, 520 trajectories x <=40 poses, 200k-point 10deg ramp map"
     elif name == "C3":
         sc = synth.c3_multilevel()
         desc = "C3: 16.5k trajectories x <=60 poses, 1.2x0.8x1.0 m footprint, 8M-point 3-floor map with ramps"
+    elif name == "C4":
+        sc = synth.c3_multilevel(samples=(361.0, 361.0))
+        desc = "C4: 131k trajectories (361x362 samples) x <=60 poses on the 8M-point 3-floor map, sample grid split contiguously over the ranks"
+        w["mode"] = "shard"
+    elif name == "C5":
+        base = synth.c3_multilevel(samples=(20.0, 25.0))
+        c1 = synth.c1_ramp(n_points=1000)
+        sc = synth.Scenario("C5", c1.config, base.cloud, base.pose, base.twist, base.plan)
+        n_total = FLEET_ROBOTS_PER_GPU * world
+        poses, twists, plans, offs = synth.fleet_queries(n_total, region=(-28.0, 28.0, -20.0, 20.0), levels=(0.0, 3.0, 6.0),
+                                                         cloud=base.cloud)
+        lo, hi = rank * FLEET_ROBOTS_PER_GPU, (rank + 1) * FLEET_ROBOTS_PER_GPU
+        w.update(mode="fleet", fleet=(poses[lo:hi], twists[lo:hi], plans[offs[lo]:offs[hi]], offs[lo:hi + 1] - offs[lo]))
+        desc = (f"C5: fleet planning, {FLEET_ROBOTS_PER_GPU} robots per GPU ({n_total} in total) x 520 trajectories x <=40 poses "
+                "on the shared 8M-point 3-floor map (replicated per GPU)")
     else:
         sc = synth.c2_dense()
         desc = "C2: 16.5k trajectories x <=60 poses, 1.2x0.8x1.0 m footprint, 2M-point single-floor lethal cloud"
     pose, twist, plan = list(sc.pose), list(sc.twist), sc.plan
-    if rank > 0 and name in ("C1", "C2"):
-        # fleet sharding: every rank plans for a different robot; same position, heading turned by rank*45deg
-        yaw = rank * math.pi / 4
-        q = synth.quat_from_rpy(0.0, 0.0, yaw)
-        if name == "C2":
-            pose = [0.0, 0.0, 0.0, *q]
-            plan = synth._plan_polyline((-0.5 * math.cos(yaw), -0.5 * math.sin(yaw)), yaw, 80, 0.05, 50, 25.0, lambda x, y: 0.0)
-    elif rank > 0 and name == "C3" and sc.extra_poses:
-        pose, twist, plan = sc.extra_poses[(rank - 1) % len(sc.extra_poses)]
-    return sc, pose, twist, plan, desc
+    # N > 1 in "single" mode: every rank serves its own robot, and all robots issue the SAME query (the named
+    # configuration), so the work per GPU is exactly the N=1 work — a clean weak-scaling measurement. Fleets of
+    # different robots are the C5 workload.
+    w.update(sc=sc, pose=pose, twist=twist, plan=plan, desc=desc)
+    return w
 
 
 class ClockSampler:
@@ -198,7 +217,8 @@ def run_reference(args, rank, world):
         return 0
     from dddmr_navigation_b200 import make_query
     from oracle import lporacle as O
-    sc, pose, twist, plan, desc = make_workload(args.workload, 0)
+    wl = make_workload(args.workload if args.workload in ("C1", "C2", "C3") else "C3", 0)
+    sc, pose, twist, plan, desc = wl["sc"], wl["pose"], wl["twist"], wl["plan"], wl["desc"]
     use_ref = O.have_ref()
     ora = O.OraclePlanner(sc.config, O.MATH_LIBM, O.INDEX_NANOFLANN if use_ref else O.INDEX_GRID)
     ora.set_cloud(sc.cloud)
@@ -237,7 +257,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3"])
+    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--ref-stride", type=int, default=1, help="--impl reference / cpu_baseline: score every k-th sample")
     ap.add_argument("--cpu-baseline-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -268,7 +288,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sc, pose, twist, plan, desc = make_workload(args.workload, rank)
+    wl = make_workload(args.workload, rank, world)
+    sc, pose, twist, plan, desc, mode = wl["sc"], wl["pose"], wl["twist"], wl["plan"], wl["desc"], wl["mode"]
     pin_t, cloud = pinned_copy(sc.cloud)
     n_pts, stride = cloud.shape[0], cloud.shape[1] * 4
     plan = np.ascontiguousarray(plan, np.float64)
@@ -280,14 +301,43 @@ def main():
         flush.zero_()
         torch.cuda.synchronize()
 
+    if mode == "fleet":
+        from dddmr_navigation_b200 import abi
+        f_poses, f_twists, f_plans, f_offs = wl["fleet"]
+        qs = (abi.Query * len(f_poses))()
+        for i in range(len(f_poses)):
+            qs[i] = make_query(f_poses[i], f_twists[i])
+        f_plans = np.ascontiguousarray(f_plans, np.float64)
+        f_offs = np.ascontiguousarray(f_offs, np.int64)
+
+    def cycle():
+        """One step of the hot path on resident inputs -> (poses scored on this rank, result summary)."""
+        if mode == "fleet":
+            res = lp.plan_batch(qs, f_plans, f_offs)
+            return sum(int(r.n_poses) for r in res), res[0]
+        if mode == "shard":
+            r = lp.plan_shard(q, rank, world)
+            if world > 1:
+                from dddmr_navigation_b200.dist import allreduce_best
+                cost, bid = allreduce_best(r.best_cost, r.best_id, device=torch.device("cuda", local_rank))
+                r.best_cost, r.best_id = cost, bid
+            return int(r.n_poses), r
+        r = lp.plan(q)
+        return int(r.n_poses), r
+
+    def upload():
+        lp.set_cloud_ptr(cloud.ctypes.data, n_pts, stride)
+        tm = lp.last_timing()
+        if mode != "fleet":
+            lp.set_plan(plan)
+        return tm
+
     # ---------------- device-resident arm: kernels only ----------------
-    lp.set_cloud_ptr(cloud.ctypes.data, n_pts, stride)
-    lp.set_plan(plan)
+    upload()
     grid_ms = lp.last_timing()["ms_grid_build"]
     for _ in range(args.warmup):
         flush_l2()
-        r = lp.plan(q)
-    poses_per_step = int(r.n_poses)
+        poses_per_step, r = cycle()
     launches0 = lp.launch_count()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -296,7 +346,7 @@ def main():
     for _ in range(args.steps):
         flush_l2()
         t0 = time.perf_counter()
-        r = lp.plan(q)
+        poses_per_step, r = cycle()
         wall_ms.append(1e3 * (time.perf_counter() - t0))
         dev_ms.append(lp.last_timing()["ms_plan_kernels"])
         km = lp.last_kernel_ms()
@@ -305,32 +355,34 @@ def main():
         argmin_k_ms.append(km["argmin_kernel"])
     barrier()
     launches = lp.launch_count() - launches0
-    t_dev = sum(dev_ms) / 1e3
+    # the sample-sharded cycle ends with a collective: its step time is the host-observed one (kernels + exchange)
+    t_dev = (sum(wall_ms) if mode == "shard" and world > 1 else sum(dev_ms)) / 1e3
 
     # ---------------- e2e arm: host buffers through the C ABI, every step ----------------
     for _ in range(2):
-        lp.set_cloud_ptr(cloud.ctypes.data, n_pts, stride)
-        lp.set_plan(plan)
-        lp.plan(q)
+        upload()
+        cycle()
     barrier()
     e2e_ms, e2e_stage = [], {"ms_upload": 0.0, "ms_grid_build": 0.0, "ms_plan": 0.0}
     for _ in range(args.steps):
         flush_l2()
         t0 = time.perf_counter()
-        lp.set_cloud_ptr(cloud.ctypes.data, n_pts, stride)
-        tm = lp.last_timing()
-        lp.set_plan(plan)
-        r2 = lp.plan(q)
+        tm = upload()
+        _, r2 = cycle()
         e2e_ms.append(1e3 * (time.perf_counter() - t0))
         e2e_stage["ms_upload"] += tm["ms_upload"]
         e2e_stage["ms_grid_build"] += tm["ms_grid_build"]
         e2e_stage["ms_plan"] += lp.last_timing()["ms_plan_kernels"]
-        assert r2.as_dict() == r.as_dict()
+        assert (r2.best_id, r2.best_cost) == (r.best_id, r.best_cost)
     barrier()
     clocks = sampler.stop()
     t_e2e = sum(e2e_ms) / 1e3
-    h2d = n_pts * stride + plan.nbytes + ctypes.sizeof(q)
-    d2h = 56 + 32 + 32  # result + meta + grid bounds
+    if mode == "fleet":
+        h2d = n_pts * stride + f_plans.nbytes + len(qs) * ctypes.sizeof(abi.Query)
+        d2h = len(qs) * (56 + 32) + 32
+    else:
+        h2d = n_pts * stride + plan.nbytes + ctypes.sizeof(q)
+        d2h = 56 + 32 + 32  # result + meta + grid bounds
 
     # ---------------- reductions over ranks (max time, summed poses) ----------------
     poses_total = poses_per_step * args.steps
@@ -360,11 +412,15 @@ def main():
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "strong" if mode == "shard" else "weak",
+        "vs_baseline": None,
         "dtype": "f32+f64", "data": "synthetic",
         "config": {"workload": desc, "trajectories": int(r.n_traj), "poses_per_step": poses_per_step, "cloud_points": n_pts,
                    "cloud_stride_bytes": stride, "timing": "CUDA events on the library stream; L2 flushed (256 MiB memset) between steps",
-                   "parallelism": "1 robot per GPU, map replicated (fleet sharding)" if world > 1 else "single GPU",
+                   "parallelism": ({"single": "1 robot per GPU issuing the named query, map replicated (fleet sharding, no collective)",
+                                    "fleet": f"{FLEET_ROBOTS_PER_GPU} robots per GPU, map replicated (fleet sharding, no collective)",
+                                    "shard": "sample grid split over the ranks, one 16*W-byte all-reduce per cycle (NCCL)"}[mode]
+                                   if world > 1 or mode != "single" else "single GPU"),
                    "grid": lp.grid_info()},
         "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -383,7 +439,8 @@ def main():
 
     # ---------------- p50 cycle latency on the reference's own CPU-runnable case (C1), rank 0 ----------------
     if rank == 0 and world == 1 and args.latency_cycles > 0:
-        sc1, pose1, twist1, plan1, _ = make_workload("C1", 0)
+        w1 = make_workload("C1", 0)
+        sc1, pose1, twist1, plan1 = w1["sc"], w1["pose"], w1["twist"], w1["plan"]
         lp1 = LocalPlanner(sc1.config, device=local_rank)
         lp1.set_cloud(sc1.cloud)
         lp1.set_plan(plan1)
@@ -401,7 +458,7 @@ def main():
         lp1.close()
 
     # ---------------- CPU baseline on this box's host cores (rank 0, N=1) ----------------
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and mode == "single":
         from oracle import lporacle as O
         use_ref = O.have_ref()
         ora = O.OraclePlanner(sc.config, O.MATH_LIBM, O.INDEX_NANOFLANN if use_ref else O.INDEX_GRID)

@@ -48,9 +48,10 @@ def allreduce_best(local_cost: float, local_id: int, device=None, group=None):
 
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    buf = torch.zeros(2 * world, dtype=torch.int64, device=device)
-    buf[2 * rank] = cost_to_bits(local_cost, local_id)
-    buf[2 * rank + 1] = int(local_id)
+    vals = [0] * (2 * world)
+    vals[2 * rank] = cost_to_bits(local_cost, local_id)
+    vals[2 * rank + 1] = int(local_id)
+    buf = torch.tensor(vals, dtype=torch.int64, device=device)  # one H2D copy
     dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
     vals = buf.cpu().tolist()
     return pick_best((vals[2 * r], vals[2 * r + 1]) for r in range(world))

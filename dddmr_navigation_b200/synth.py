@@ -296,16 +296,40 @@ def c3_multilevel(n_points=8_000_000, seed=SEED0 + 3, samples=(128.0, 128.0)) ->
 # ---------------------------------------------------------------------------------------------------
 # C5: a fleet of robots on free ground of a map (poses, twists, 60-point plans), C1 sampling
 # ---------------------------------------------------------------------------------------------------
-def fleet_queries(n_robots: int, seed=SEED0 + 5, region=(-28.0, 28.0, -20.0, 20.0), levels=(0.0,)):
-    """-> (poses (n,7), twists (n,3), plans (n*60,7), offsets (n+1,)). Uniform over the region and the floors."""
+def fleet_queries(n_robots: int, seed=SEED0 + 5, region=(-28.0, 28.0, -20.0, 20.0), levels=(0.0,), cloud=None, clearance=1.0):
+    """-> (poses (n,7), twists (n,3), plans (n*60,7), offsets (n+1,)). Uniform over the region and the floors; with
+    `cloud` given, robots are re-drawn until no lethal point lies within `clearance` metres (0.5 m occupancy cells per
+    floor, a point counts for the floor whose ground it is at most 2.5 m above)."""
     rng = np.random.default_rng(seed)
+    occ = None
+    if cloud is not None:
+        cs = 0.5
+        nx, ny = int(math.ceil((region[1] - region[0]) / cs)) + 8, int(math.ceil((region[3] - region[2]) / cs)) + 8
+        ox, oy = region[0] - 4 * cs, region[2] - 4 * cs
+        occ = np.zeros((len(levels), nx, ny), bool)
+        xyz = np.asarray(cloud)[:, :3]
+        ix = np.floor((xyz[:, 0] - ox) / cs).astype(np.int64)
+        iy = np.floor((xyz[:, 1] - oy) / cs).astype(np.int64)
+        ok = (ix >= 0) & (ix < nx) & (iy >= 0) & (iy < ny)
+        for li, zl in enumerate(levels):
+            m = ok & (xyz[:, 2] >= zl) & (xyz[:, 2] < zl + 2.5)
+            occ[li, ix[m], iy[m]] = True
+        rad = int(math.ceil(clearance / cs))
+
+        def free(x, y, li):
+            cx, cy = int((x - ox) // cs), int((y - oy) // cs)
+            return not occ[li, max(cx - rad, 0):cx + rad + 1, max(cy - rad, 0):cy + rad + 1].any()
     poses = np.zeros((n_robots, 7))
     twists = np.zeros((n_robots, 3))
     plans = np.zeros((n_robots * 60, 7))
     offs = np.arange(n_robots + 1, dtype=np.int64) * 60
     for i in range(n_robots):
-        x, y = rng.uniform(region[0], region[1]), rng.uniform(region[2], region[3])
-        z = float(levels[rng.integers(0, len(levels))])
+        for _ in range(1000):
+            x, y = rng.uniform(region[0], region[1]), rng.uniform(region[2], region[3])
+            li = int(rng.integers(0, len(levels)))
+            if occ is None or free(x, y, li):
+                break
+        z = float(levels[li])
         yaw = rng.uniform(-math.pi, math.pi)
         q = quat_from_rpy(0.0, 0.0, yaw)
         poses[i] = [x, y, z, *q]

@@ -7,6 +7,7 @@ against its "libm" mode (glibc, what the reference binary calls) the 1e-4 tolera
 """
 import copy
 import math
+import os
 
 import numpy as np
 import pytest
@@ -278,3 +279,140 @@ def test_c2_full_size_properties_and_sampled_oracle():
         assert_same_array(t[k][idx], to[k], f"C2 sampled {k}")
     grid = gpu.grid_info()
     assert grid["n_points_kept"] == 2_000_000
+
+
+def _sampled_oracle_check(sc, pose, twist, plan, gpu, stride, tag):
+    q = make_query(pose, twist)
+    gpu.set_plan(plan)
+    r = gpu.plan(q)
+    t = gpu.read_trajectories()
+    assert r.n_poses == int(t["num_steps"].sum())
+    assert r.n_collided == int((t["first_hit_pose"] >= 0).sum())
+    assert r.best_id == reference_argmin(t["cost"])
+    ora = O.OraclePlanner(sc.config)
+    ora.set_cloud(sc.cloud)
+    ora.set_plan(plan)
+    ora.set_sample_stride(stride)
+    ora.plan(q, n_threads=8)
+    to = ora.read_trajectories()
+    lut = {int(s): i for i, s in enumerate(t["sample_index"])}
+    idx = np.array([lut[int(s)] for s in to["sample_index"]])
+    for k in ("num_steps", "time_delta", "cost", "first_hit_pose", "critic_scores", "vel"):
+        assert_same_array(t[k][idx], to[k], f"{tag} sampled {k}")
+    return r, t
+
+
+def test_c3_multilevel_full_size_all_stations():
+    """BASELINE config C3 (8 M points, three floors joined by 12 degree ramps): mid-floor, ramp entry and ramp exit
+    (the pitched start pose whose trajectories cross the floor transition), every 96th sample against the oracle."""
+    sc = synth.c3_multilevel()
+    gpu = LocalPlanner(sc.config)
+    gpu.set_cloud(sc.cloud)
+    assert gpu.grid_info()["n_points_kept"] == 8_000_000
+    stations = [(sc.pose, sc.twist, sc.plan)] + list(sc.extra_poses)
+    seen_hit = seen_free = False
+    for i, (pose, twist, plan) in enumerate(stations):
+        r, t = _sampled_oracle_check(sc, pose, twist, plan, gpu, 96, f"C3 station {i}")
+        seen_hit |= r.n_collided > 0
+        seen_free |= r.best_id >= 0
+    assert seen_hit and seen_free
+
+
+def test_c4_sample_shards_at_full_size():
+    """BASELINE config C4 sampling (361 x 362 = 131 k samples) on the C3 map: the union of 8 contiguous sample shards
+    reproduces the unsharded cycle bit for bit, and the reference argmin rule over the shard winners picks the same id."""
+    sc = synth.c3_multilevel(n_points=2_000_000, samples=(361.0, 361.0))
+    gpu = LocalPlanner(sc.config)
+    gpu.set_cloud(sc.cloud)
+    gpu.set_plan(sc.plan)
+    q = make_query(sc.pose, sc.twist)
+    r = gpu.plan(q)
+    whole = gpu.read_trajectories()
+    assert r.n_samples == 361 * 362  # the linear window stays positive (no inserted zero), the angular one straddles it
+    from dddmr_navigation_b200.dist import cost_to_bits, pick_best
+    count = 8
+    cost = np.full(r.n_traj, np.nan)
+    pairs, n_poses = [], 0
+    for rank in range(count):
+        rs = gpu.plan_shard(q, rank, count)
+        _, b, e = gpu.traj_count()
+        cost[b:e] = gpu.read_trajectories()["cost"][b:e]
+        pairs.append((cost_to_bits(rs.best_cost, rs.best_id), rs.best_id))
+        n_poses += rs.n_poses
+    assert n_poses == r.n_poses
+    assert_same_array(cost, whole["cost"], "C4 shard union cost")
+    best_cost, best_id = pick_best(pairs)
+    assert best_id == r.best_id and best_cost == r.best_cost
+
+
+def test_c5_fleet_batch_on_the_multilevel_map():
+    """BASELINE config C5 shape (C1 sampling, robots on all three floors of the shared map) at 96 robots: the batch equals
+    per-robot cycles, and 8 of them are checked against the oracle in full."""
+    base = synth.c3_multilevel(n_points=2_000_000)
+    cfg = synth.c1_ramp(n_points=1000).config
+    n = 96
+    poses, twists, plans, offs = synth.fleet_queries(n, levels=(0.0, 3.0, 6.0), cloud=base.cloud)
+    gpu = LocalPlanner(cfg)
+    gpu.set_cloud(base.cloud)
+    qs = (abi.Query * n)()
+    for i in range(n):
+        qs[i] = make_query(poses[i], twists[i])
+    res = gpu.plan_batch(qs, plans, offs)
+    batch = [(res[i].as_dict(), gpu.read_trajectories(i)) for i in range(n)]
+    assert sum(1 for d, _ in batch if d["best_id"] >= 0) > n // 2  # robots stand on free ground
+    single = LocalPlanner(cfg)
+    single.set_cloud(base.cloud)
+    ora = O.OraclePlanner(cfg)
+    ora.set_cloud(base.cloud)
+    for i in range(n):
+        single.set_plan(plans[offs[i]:offs[i + 1]])
+        r1 = single.plan(qs[i])
+        assert r1.as_dict() == batch[i][0], f"robot {i}"
+        assert_trajectories_equal(single.read_trajectories(), batch[i][1])
+        if i % 12 == 0:
+            ora.set_plan(plans[offs[i]:offs[i + 1]])
+            r_o = ora.plan(qs[i])
+            assert batch[i][0] == r_o.as_dict(), f"robot {i} vs oracle"
+            assert_trajectories_equal(batch[i][1], ora.read_trajectories())
+
+
+def _nccl_shard_worker(rank, world, port, out_q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from dddmr_navigation_b200.dist import allreduce_best
+    sc = synth.c1_ramp()
+    gpu = LocalPlanner(sc.config, device=rank)
+    gpu.set_cloud(sc.cloud)
+    gpu.set_plan(sc.plan)
+    r = gpu.plan_shard(make_query(sc.pose, sc.twist), rank, world)
+    cost, bid = allreduce_best(r.best_cost, r.best_id, device=torch.device("cuda", rank))
+    out_q.put((rank, cost, bid, r.n_poses))
+    dist.destroy_process_group()
+
+
+def test_sample_sharding_over_nccl_two_gpus():
+    """The real multi-GPU path of config C4: one process per GPU, plan_shard + the single NCCL all-reduce."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import multiprocessing as mp
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    out_q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_shard_worker, args=(r, 2, port, out_q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(out_q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    sc = synth.c1_ramp()
+    gpu, ora = _pair(sc.config)
+    r_g, r_o = run_pair(gpu, ora, sc.cloud, sc.plan, sc.pose, sc.twist)
+    assert got[0][1:3] == got[1][1:3] == (r_o.best_cost, r_o.best_id)
+    assert got[0][3] + got[1][3] == r_o.n_poses
