@@ -269,7 +269,7 @@ int build_grid(b200lp_ctx* ctx, size_t n, size_t stride) {
     scatter_kernel<<<grid_blocks(n, 256, sms), 256, 0, ctx->stream>>>(ctx->d_raw.p, n, stride, ctx->d_keys.p,
                                                                       ctx->d_fill.p, ctx->d_pts.p);
     const size_t ny_threads = ((size_t)g.nx + 1) * (size_t)g.nz, nz_threads = ((size_t)g.nx + 1) * ((size_t)g.ny + 1);
-    sat_y_kernel<<<(unsigned)((ny_threads + 255) / 256), 256, 0, ctx->stream>>>(g, ctx->d_sat.p);
+    sat_y_kernel<<<(unsigned)((ny_threads * 32 + 255) / 256), 256, 0, ctx->stream>>>(g, ctx->d_sat.p);
     sat_z_kernel<<<(unsigned)((nz_threads + 255) / 256), 256, 0, ctx->stream>>>(g, ctx->d_sat.p);
     ctx->launches += 7;
   }

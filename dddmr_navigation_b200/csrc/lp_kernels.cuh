@@ -208,16 +208,28 @@ __global__ void __launch_bounds__(256) scatter_kernel(const char* __restrict__ r
 // Summed-volume table of the per-cell point counts: sat[Z][Y][X] = points with cell (x,y,z) < (X,Y,Z)
 // componentwise, dims (nz+1)(ny+1)(nx+1), zero-initialised by the caller. The x prefix comes straight from
 // cell_start; sat_y_kernel accumulates along y, sat_z_kernel along z. Consecutive threads walk consecutive X.
+// one warp per (X, z): the lanes scan 32 consecutive y at a time
 __global__ void __launch_bounds__(256) sat_y_kernel(GridDev g, uint32_t* __restrict__ sat) {
   const size_t nxp = (size_t)g.nx + 1;
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nxp * (size_t)g.nz) return;
-  const int X = (int)(i % nxp), z = (int)(i / nxp);
-  uint32_t run = 0u;
-  for (int y = 0; y < g.ny; ++y) {
-    const size_t row = ((size_t)z * g.ny + y) * (size_t)g.nx;
-    run += g.cell_start[row + X] - g.cell_start[row];
-    sat[((size_t)(z + 1) * (g.ny + 1) + (y + 1)) * nxp + X] = run;
+  const size_t wid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= nxp * (size_t)g.nz) return;
+  const int X = (int)(wid % nxp), z = (int)(wid / nxp);
+  uint32_t carry = 0u;
+  for (int y0 = 0; y0 < g.ny; y0 += 32) {
+    const int y = y0 + lane;
+    uint32_t v = 0u;
+    if (y < g.ny) {
+      const size_t row = ((size_t)z * g.ny + y) * (size_t)g.nx;
+      v = g.cell_start[row + X] - g.cell_start[row];
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(kFull, v, o);
+      if (lane >= o) v += t;
+    }
+    if (y < g.ny) sat[((size_t)(z + 1) * (g.ny + 1) + (y + 1)) * nxp + X] = carry + v;
+    carry += __shfl_sync(kFull, v, 31);
   }
 }
 __global__ void __launch_bounds__(256) sat_z_kernel(GridDev g, uint32_t* __restrict__ sat) {
@@ -314,7 +326,13 @@ struct PrepAgg {
   unsigned flag;       // == launch epoch once the fields above are visible
 };
 
-constexpr int kPrepThreads = 256;  // samples per chunk
+#ifndef B200LP_PREP_THREADS
+#define B200LP_PREP_THREADS 256
+#endif
+constexpr int kPrepThreads = B200LP_PREP_THREADS;  // samples per chunk
+constexpr int kPrepWarps = kPrepThreads / 32;
+// serial per-CTA jobs (three velocity axes, two pose matrices) are spread over different warps where possible
+__device__ __forceinline__ bool prep_job(int job, int tid) { return tid == (job % kPrepWarps) * 32 + job / kPrepWarps; }
 
 // grid = (n_chunks, robots). Chunk ids are handed out by a per-robot ticket, so a CTA only ever waits for
 // chunks that are already running; every CTA publishes its aggregate BEFORE it looks back.
@@ -353,12 +371,12 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
   __syncthreads();
   const int chunk = s_chunk;
 
-  if (tid == 64) {
+  if (prep_job(3, tid)) {
     // tf2::transformToEigen(robot_pose_) (dd_simple…cpp:355)
     quat_to_matrix(q.pose[3], q.pose[4], q.pose[5], q.pose[6], s_R0);
     s_t0[0] = q.pose[0]; s_t0[1] = q.pose[1]; s_t0[2] = q.pose[2];
   }
-  if (tid == 96 && q.plan_n > 0) {
+  if (prep_job(4, tid) && q.plan_n > 0) {
     const double* e = plan7 + (q.plan_off + q.plan_n - 1) * 7;  // prune_plan_.poses.back()
     quat_to_matrix(e[3], e[4], e[5], e[6], s_gL);
     s_gt[0] = e[0]; s_gt[1] = e[1]; s_gt[2] = e[2];
@@ -371,7 +389,7 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
     }
 
   const bool sampling_on = P.linear_x_sample * P.angular_z_sample > 0;
-  if (sampling_on && P.theory != B200LP_THEORY_DD_ROTATE_INPLACE && lane == 0 && warp < 3) {
+  if (sampling_on && P.theory != B200LP_THEORY_DD_ROTATE_INPLACE && (prep_job(0, tid) || prep_job(1, tid) || prep_job(2, tid))) {
     // window (dd_simple…cpp:255-277; omni…cpp:277-303); Vector3f stores round to float
     const double max_vel_th = L.max_vel_theta, min_vel_th = -1.0 * max_vel_th;
     const float acc0 = (float)L.acc_lim_x, acc1 = (float)L.acc_lim_y, acc2 = (float)L.acc_lim_theta;
@@ -402,12 +420,12 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
       if (ty >= max_vel_y / L.deceleration_ratio) mn1 = (float)fmax(min_vel_y, ty / L.deceleration_ratio);
       else if (ty <= min_vel_y / L.deceleration_ratio) mx1 = (float)fmin(max_vel_y, ty / L.deceleration_ratio);
     }
-    if (warp == 0) s_n[0] = velocity_iterator_dev((double)mn0, (double)mx0, (int)P.linear_x_sample, s_x);
-    if (warp == 1) {
+    if (prep_job(0, tid)) s_n[0] = velocity_iterator_dev((double)mn0, (double)mx0, (int)P.linear_x_sample, s_x);
+    if (prep_job(1, tid)) {
       if (P.theory == B200LP_THEORY_OMNI_SIMPLE) s_n[1] = velocity_iterator_dev((double)mn1, (double)mx1, (int)P.linear_y_sample, s_y);
       else { s_y[0] = 0.f; s_n[1] = 1; }
     }
-    if (warp == 2) s_n[2] = velocity_iterator_dev((double)mn2, (double)mx2, (int)P.angular_z_sample, s_th);
+    if (prep_job(2, tid)) s_n[2] = velocity_iterator_dev((double)mn2, (double)mx2, (int)P.angular_z_sample, s_th);
   }
   __syncthreads();
 
@@ -536,24 +554,49 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
   // ---- forward simulation of this thread's trajectory (computeNewPositions, dd_simple…cpp:457-464,
   // omni_simple…cpp:498-505): x,y,th in the robot frame after every step, then the pure-pursuit terms
   // of the last pose ----
+#ifdef B200LP_DBG_NOROLL
+  roll = false;
+#endif
   if (roll) {
     float x = 0.f, y = 0.f, th = 0.f;
     const double wdt = (double)v2 * dt;  // loop invariant of th' = (float)(th + w*dt)
     float4* out = pose_rows + pose_row;
-    for (int k = 0; k < steps; ++k) {
-      double ex, ey;
-      if (P.theory == B200LP_THEORY_OMNI_SIMPLE) {
-        const double a = 1.57079632679489661923 + (double)th;  // M_PI_2 + pos[2]
-        ex = ((double)(v0 * lpm::cosf(th)) + (double)v1 * lpm::cos(a)) * dt;
-        ey = ((double)(v0 * lpm::sinf(th)) + (double)v1 * lpm::sin(a)) * dt;
-      } else {
-        ex = (double)(v0 * lpm::cosf(th)) * dt;
-        ey = (double)(v0 * lpm::sinf(th)) * dt;
+    // Blocks of 4 steps: the heading chain th' = (float)(th + w*dt) is the only dependency the expensive
+    // sin/cos evaluations have, so it runs ahead and the four evaluations overlap in the FP64 pipe.
+    constexpr int kU = 4;
+    for (int k0 = 0; k0 < steps; k0 += kU) {
+      float tho[kU], thn[kU];
+      double ex[kU], ey[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        tho[u] = th;
+        th = (float)((double)th + wdt);
+        thn[u] = th;
       }
-      x = (float)((double)x + ex);
-      y = (float)((double)y + ey);
-      th = (float)((double)th + wdt);
-      out[k] = make_float4(x, y, th, 0.f);
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        float sn, cs;
+        lpm::sincosf(tho[u], &sn, &cs);
+        if (P.theory == B200LP_THEORY_OMNI_SIMPLE) {
+          const double a = 1.57079632679489661923 + (double)tho[u];  // M_PI_2 + pos[2]
+          ex[u] = ((double)(v0 * cs) + (double)v1 * lpm::cos(a)) * dt;
+          ey[u] = ((double)(v0 * sn) + (double)v1 * lpm::sin(a)) * dt;
+        } else {
+          ex[u] = (double)(v0 * cs) * dt;
+          ey[u] = (double)(v0 * sn) * dt;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        x = (float)((double)x + ex[u]);
+        y = (float)((double)y + ey[u]);
+        if (k0 + u < steps) out[k0 + u] = make_float4(x, y, thn[u], 0.f);
+      }
+    }
+    // the block loop may run past the last step: restore the state after step `steps - 1`
+    {
+      const float4 last = out[steps - 1];
+      x = last.x; y = last.y; th = last.z;
     }
     if (want_pp && q.plan_n > 0 && steps >= 2) {
       double Lm[9], tv[3], dist, yaw;

@@ -120,36 +120,49 @@ LPM_HD double reduce_fast(double x, int* np) {
 LPM_HD_BIG double sin(double x);
 LPM_HD_BIG double cos(double x);
 
-LPM_HD float sinf(float y) {
+// sinf and cosf of the same argument from ONE range reduction. glibc evaluates, for n = round(y / (pi/2)):
+//   sinf: n even -> sine polynomial of (x*s, x^2), n odd -> cosine polynomial with the sign table (n & 2)
+//   cosf: the same with n ^ 1
+// where negating every coefficient of the cosine polynomial negates its value exactly. Its |y| < pi/4 shortcut is the
+// n = 0 case of the general path (reduce_fast returns x unchanged), so one straight-line evaluation of both
+// polynomials yields both results bit for bit; only the tiny-argument returns and the |y| >= 120 fallback remain.
+LPM_HD void sincosf(float y, float* sn, float* cs) {
+  const uint32_t top = abstop12(y);
   double x = y;
-  if (abstop12(y) < 0x3f4u /* abstop12(pi/4) */) {
-    double s = x * x;
-    if (abstop12(y) < 0x398u /* abstop12(2^-12) */) return y;
-    return sinf_poly(x, s, false, 0);
-  } else if (abstop12(y) < 0x42fu /* abstop12(120.0f) */) {
-    int n;
-    x = reduce_fast(x, &n);
-    double s = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
-    return sinf_poly(x * s, x * x, (n & 2) != 0, n);
+  if (top >= 0x42fu /* abstop12(120.0f) */) {
+    // outside the planner's contract (the C ABI rejects such parameter sets); glibc switches to a 192-bit
+    // reduction here, we round the double routines.
+    *sn = (float)lpm::sin(x);
+    *cs = (float)lpm::cos(x);
+    return;
   }
-  // |y| >= 120: outside the planner's contract (the C ABI rejects such parameter sets);
-  // glibc switches to a 192-bit reduction here, we round the double routine.
-  return (float)lpm::sin(x);
+  int n;
+  const double xr = reduce_fast(x, &n);
+  const double sg = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
+  const double x2 = xr * xr;
+  const float sp = sinf_poly(xr * sg, x2, false, 0);
+  const float cp = sinf_poly(xr * sg, x2, false, 1);
+  const float cpn = (n & 2) ? -cp : cp;
+  float s = (n & 1) ? cpn : sp;
+  float c = (n & 1) ? sp : cpn;
+  if (top < 0x398u /* abstop12(2^-12) */) {
+    s = y;
+    c = 1.0f;
+  }
+  *sn = s;
+  *cs = c;
+}
+
+LPM_HD float sinf(float y) {
+  float s, c;
+  sincosf(y, &s, &c);
+  return s;
 }
 
 LPM_HD float cosf(float y) {
-  double x = y;
-  if (abstop12(y) < 0x3f4u) {
-    double x2 = x * x;
-    if (abstop12(y) < 0x398u) return 1.0f;
-    return sinf_poly(x, x2, false, 1);
-  } else if (abstop12(y) < 0x42fu) {
-    int n;
-    x = reduce_fast(x, &n);
-    double s = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
-    return sinf_poly(x * s, x * x, (n & 2) != 0, n ^ 1);
-  }
-  return (float)lpm::cos(x);
+  float s, c;
+  sincosf(y, &s, &c);
+  return c;
 }
 
 // ----------------------------------------------------------------------------------------
