@@ -190,8 +190,8 @@ int build_grid(b200lp_ctx* ctx, size_t n, size_t stride) {
   g.org[0] = g.org[1] = g.org[2] = 0.f;
   g.inv_xy = g.inv_z = 1.f;
   g.cmax = 1.f;
-  float cxy = ctx->gcfg.cell_xy > 0.f ? ctx->gcfg.cell_xy : 0.25f;
-  float cz = ctx->gcfg.cell_z > 0.f ? ctx->gcfg.cell_z : 0.25f;
+  float cxy = ctx->gcfg.cell_xy > 0.f ? ctx->gcfg.cell_xy : 0.2f;
+  float cz = ctx->gcfg.cell_z > 0.f ? ctx->gcfg.cell_z : 0.4f;
   const uint32_t max_cells = ctx->gcfg.max_cells ? ctx->gcfg.max_cells : (1u << 26);
 
   CK(ctx->d_bounds.reserve(1));

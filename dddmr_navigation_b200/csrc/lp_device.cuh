@@ -15,7 +15,10 @@ namespace lp {
 
 constexpr int kWarpsPerCta = 4;
 constexpr int kThreads = kWarpsPerCta * 32;
-constexpr int kGroup = 4;       // consecutive poses swept against one candidate stream
+#ifndef B200LP_GROUP
+#define B200LP_GROUP 4
+#endif
+constexpr int kGroup = B200LP_GROUP;  // consecutive poses swept against one candidate stream (power of two)
 constexpr int kPreStride = 5;   // float4 per pose in the pre-test stash (4 used + 1 pad: conflict-free 80-byte stride)
 constexpr int kMaxAxis = 2048;  // cap on samples per velocity axis (incl. the inserted zero)
 constexpr int kPlanSmem = 256;  // prune-plan points staged in shared memory
@@ -470,7 +473,7 @@ __device__ __forceinline__ unsigned sweep_points(const GridDev& g, const float* 
   }
 
   unsigned hit = 0u;     // per-lane, exact hits
-  unsigned alive = 0xfu; // poses still worth testing: those below the lowest pose known to collide (warp-uniform)
+  unsigned alive = (1u << kGroup) - 1u; // poses still worth testing: those below the lowest pose known to collide (warp-uniform)
   for (int r0 = 0; r0 < nrows; r0 += 32) {
     const int r = r0 + lane;
     uint32_t beg = 0, end = 0;

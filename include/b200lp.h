@@ -116,8 +116,8 @@ typedef struct b200lp_critic {
 /* Voxel-grid configuration of the lethal cloud (no reference analogue: replaces KdTreeFLANN).
  * Zero-initialise for defaults. */
 typedef struct b200lp_grid_config {
-  float cell_xy;      /* cell edge in x and y, metres (default 0.25) */
-  float cell_z;       /* cell height, metres (default 0.25) */
+  float cell_xy;      /* cell edge in x and y, metres (default 0.2) */
+  float cell_z;       /* cell height, metres (default 0.4) */
   uint32_t max_cells; /* cap on the dense cell count; cells are coarsened to fit (default 1<<26) */
   uint32_t reserved_;
 } b200lp_grid_config;

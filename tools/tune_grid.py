@@ -17,7 +17,7 @@ for name in (sys.argv[1:] or ["C2"]):
     sc = MAKERS[name]()
     q = make_query(sc.pose, sc.twist)
     ref = None
-    for cxy, cz in [(0.25, 0.25), (0.25, 0.5), (0.25, 1.0), (0.5, 0.25), (0.5, 0.5), (0.5, 1.0), (0.35, 0.35), (0.2, 0.2), (0.25, 2.5), (1.0, 1.0)]:
+    for cxy, cz in [(0.25, 0.25), (0.25, 0.5), (0.25, 1.0), (0.2, 0.2), (0.2, 0.4), (0.15, 0.15), (0.15, 0.3), (0.125, 0.25), (0.1, 0.2), (0.1, 0.1), (0.35, 0.35), (0.5, 0.5)]:
         cfg = dataclasses.replace(sc.config, cell_xy=cxy, cell_z=cz)
         lp = LocalPlanner(cfg, device=0)
         lp.set_cloud(sc.cloud)
