@@ -13,7 +13,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libb200lp.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # status codes
 OK, E_INVALID, E_CUDA, E_STATE, E_NOMEM = 0, -1, -2, -3, -4
@@ -92,6 +92,21 @@ class PoseView(C.Structure):
                 ("aabb", C.POINTER(C.c_float)), ("collide", C.POINTER(C.c_uint8)), ("n_r1", C.POINTER(C.c_int32))]
 
 
+class PruneInfo(C.Structure):
+    _fields_ = [("status", C.c_int32), ("nearest_index", C.c_int32), ("n_prune", C.c_int32), ("n_backward", C.c_int32)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class Blocked(C.Structure):
+    _fields_ = [("n_blocked", C.c_int32), ("n_checked", C.c_int32), ("n_total", C.c_int32), ("opinion", C.c_int32),
+                ("ratio", C.c_double)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 # every symbol include/b200lp.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -112,6 +127,10 @@ SYMBOLS = {
     "b200lp_read_poses": (C.c_int, [_P, C.c_size_t, C.c_int32, C.POINTER(PoseView)]),
     "b200lp_read_pose_batch": (C.c_int, [_P, C.c_size_t, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(PoseView),
                                          C.c_size_t]),
+    "b200lp_set_global_plan": (C.c_int, [_P, C.POINTER(C.c_double), C.c_size_t]),
+    "b200lp_prune_plan": (C.c_int, [_P, C.POINTER(C.c_double), C.c_double, C.c_double, C.POINTER(PruneInfo)]),
+    "b200lp_read_prune_plan": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_float), C.c_size_t]),
+    "b200lp_path_blocked": (C.c_int, [_P, C.c_double, C.POINTER(Blocked)]),
     "b200lp_count_radius": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "b200lp_last_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
                                      C.POINTER(C.c_float)]),

@@ -90,6 +90,17 @@ struct b200lp_ctx {
 
   // plan (single-robot path) — host copy, uploaded with every query
   std::vector<double> plan_host;
+  // ... unless b200lp_prune_plan produced it on the device (then d_plan7 already holds plan_n_device poses)
+  bool plan_on_device = false;
+  int plan_n_device = 0;
+  DevBuf<double> d_gplan7;  // Local_Planner::global_plan_
+  size_t n_gplan = 0;
+  DevBuf<float4> d_prune_pcl;  // pcl_prune_plan_ (x, y, z, intensity tag)
+  DevBuf<PruneMeta> d_prune_meta;
+  PinBuf<PruneMeta> h_prune_meta;
+  DevBuf<int> d_blocked;
+  PinBuf<int> h_blocked;
+  bool have_prune = false;
 
   // per-cycle state
   size_t n_robots = 0;
@@ -278,7 +289,7 @@ int build_grid(b200lp_ctx* ctx, size_t n, size_t stride) {
   return B200LP_OK;
 }
 
-int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_result* outs) {
+int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_result* outs, bool plan_resident = false) {
   // inputs are already staged in h_robots / h_plan7 (pinned); total plan poses in plan_total
   const int t_cap = traj_cap(ctx->C.par);
   const size_t T = n_robots * (size_t)t_cap;
@@ -290,7 +301,7 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   const int cap_local = (int)std::min<long long>(t_cap, ((long long)t_cap + count - 1) / count + 1);
   CK(ctx->d_robots.reserve(n_robots));
   CK(ctx->d_meta.reserve(n_robots));
-  CK(ctx->d_plan7.reserve(std::max<size_t>(plan_total * 7, 7)));
+  if (!plan_resident) CK(ctx->d_plan7.reserve(std::max<size_t>(plan_total * 7, 7)));  // (a resident plan must not move)
   CK(ctx->d_plan_pts.reserve(std::max<size_t>(plan_total, 1)));
   CK(ctx->d_rec_vel.reserve(T));
   CK(ctx->d_rec_steps.reserve(T));
@@ -354,7 +365,7 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
 
   CK(cudaEventRecord(ctx->ev[0], ctx->stream));
   CK(cudaMemcpyAsync(ctx->d_robots.p, ctx->h_robots.p, n_robots * sizeof(RobotIn), cudaMemcpyHostToDevice, ctx->stream));
-  if (plan_total)
+  if (plan_total && !plan_resident)
     CK(cudaMemcpyAsync(ctx->d_plan7.p, ctx->h_plan7.p, plan_total * 7 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   prep_kernel<<<dim3((unsigned)n_chunks, (unsigned)n_robots), kPrepThreads, 0, ctx->stream>>>(
@@ -482,7 +493,7 @@ void b200lp_destroy(b200lp_ctx* ctx) {
   ctx->h_bounds.release(); ctx->d_robots.release(); ctx->d_meta.release(); ctx->d_plan7.release();
   ctx->d_plan_pts.release(); ctx->d_rec_vel.release(); ctx->d_rec_steps.release(); ctx->d_rec_sample.release();
   ctx->d_first_hit.release(); ctx->d_rec_dt.release(); ctx->d_cost.release(); ctx->d_scores.release();
-  ctx->d_rec_pose_off.release(); ctx->d_poses.release(); ctx->d_rec_pp.release(); ctx->d_partial.release(); ctx->d_tickets2.release(); ctx->d_tickets.release(); ctx->d_aggs.release(); ctx->d_work.release(); ctx->d_results.release(); ctx->d_count.release(); ctx->d_scratch.release();
+  ctx->d_rec_pose_off.release(); ctx->d_poses.release(); ctx->d_rec_pp.release(); ctx->d_gplan7.release(); ctx->d_prune_pcl.release(); ctx->d_prune_meta.release(); ctx->h_prune_meta.release(); ctx->d_blocked.release(); ctx->h_blocked.release(); ctx->d_partial.release(); ctx->d_tickets2.release(); ctx->d_tickets.release(); ctx->d_aggs.release(); ctx->d_work.release(); ctx->d_results.release(); ctx->d_count.release(); ctx->d_scratch.release();
   ctx->h_robots.release(); ctx->h_plan7.release(); ctx->h_results.release(); ctx->h_meta.release();
   ctx->h_count.release();
   for (auto& ev : ctx->ev)
@@ -524,6 +535,7 @@ int b200lp_set_plan(b200lp_ctx* ctx, const double* p, size_t n) {
   if (n && !p) return ctx->fail(B200LP_E_INVALID, "set_plan: null plan");
   if (n > B200LP_MAX_PLAN) return ctx->fail(B200LP_E_INVALID, "set_plan: more than B200LP_MAX_PLAN poses");
   ctx->plan_host.assign(p, p + n * 7);
+  ctx->plan_on_device = false;
   return B200LP_OK;
 }
 
@@ -531,12 +543,13 @@ int b200lp_plan_shard(b200lp_ctx* ctx, const b200lp_query* q, int rank, int coun
   if (!ctx) return B200LP_E_INVALID;
   if (!q || !out || count < 1 || rank < 0 || rank >= count) return ctx->fail(B200LP_E_INVALID, "plan: bad argument");
   CK(cudaSetDevice(ctx->device));
-  const size_t np = ctx->plan_host.size() / 7;
+  const bool resident = ctx->plan_on_device;
+  const size_t np = resident ? (size_t)ctx->plan_n_device : ctx->plan_host.size() / 7;
   CK(ctx->h_robots.reserve(1));
   CK(ctx->h_plan7.reserve(std::max<size_t>(np * 7, 7)));
   fill_robot(ctx->h_robots.p, q, 0, (int32_t)np);
-  if (np) memcpy(ctx->h_plan7.p, ctx->plan_host.data(), np * 7 * sizeof(double));
-  return run_cycle(ctx, 1, rank, count, out);
+  if (np && !resident) memcpy(ctx->h_plan7.p, ctx->plan_host.data(), np * 7 * sizeof(double));
+  return run_cycle(ctx, 1, rank, count, out, resident);
 }
 
 int b200lp_plan(b200lp_ctx* ctx, const b200lp_query* q, b200lp_result* out) { return b200lp_plan_shard(ctx, q, 0, 1, out); }
@@ -557,6 +570,7 @@ int b200lp_plan_batch(b200lp_ctx* ctx, const b200lp_query* qs, size_t n_robots, 
     fill_robot(ctx->h_robots.p + i, qs + i, a, (int32_t)(b - a));
   }
   if (total) memcpy(ctx->h_plan7.p, plans, (size_t)total * 7 * sizeof(double));
+  ctx->plan_on_device = false;  // the fleet call brings its own plans; a device-side prune plan does not survive it
   return run_cycle(ctx, n_robots, 0, 1, outs);
 }
 
@@ -663,6 +677,94 @@ int b200lp_read_poses(b200lp_ctx* ctx, size_t robot, int32_t id, const b200lp_po
   if (!ctx->have_cycle || robot >= ctx->n_robots) return ctx->fail(B200LP_E_STATE, "read_poses: no plan result for that robot");
   if (id < 0 || id >= ctx->meta_host[robot].n_traj) return ctx->fail(B200LP_E_INVALID, "read_poses: trajectory id out of range");
   return b200lp_read_pose_batch(ctx, robot, id, id + 1, nullptr, v, (size_t)B200LP_MAX_STEPS);
+}
+
+int b200lp_set_global_plan(b200lp_ctx* ctx, const double* p, size_t n) {
+  if (!ctx) return B200LP_E_INVALID;
+  if (!p) return ctx->fail(B200LP_E_INVALID, "set_global_plan: null plan");
+  if (n < 3) return ctx->fail(B200LP_E_INVALID, "set_global_plan: size of global plan is smaller than 3");  // local_planner.cpp:324-327
+  if (n > 0x7fffffffull / 7) return ctx->fail(B200LP_E_INVALID, "set_global_plan: plan too long");
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->d_gplan7.reserve(n * 7));
+  CK(cudaMemcpyAsync(ctx->d_gplan7.p, p, n * 7 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));  // the caller may free its buffer on return
+  ctx->n_gplan = n;
+  return B200LP_OK;
+}
+
+int b200lp_prune_plan(b200lp_ctx* ctx, const double robot_xyz[3], double forward_distance, double backward_distance,
+                      b200lp_prune_info* out) {
+  if (!ctx) return B200LP_E_INVALID;
+  if (!robot_xyz || !out) return ctx->fail(B200LP_E_INVALID, "prune_plan: null argument");
+  if (ctx->n_gplan < 3) {  // prunePlan's first early return (:376-377): nothing changes
+    out->status = 1; out->nearest_index = -1;
+    out->n_prune = ctx->plan_on_device ? ctx->plan_n_device : (int32_t)(ctx->plan_host.size() / 7);
+    out->n_backward = 0;
+    return B200LP_OK;
+  }
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->d_plan7.reserve((size_t)B200LP_MAX_PLAN * 7));
+  CK(ctx->d_prune_pcl.reserve(B200LP_MAX_PLAN));
+  CK(ctx->d_prune_meta.reserve(1));
+  CK(ctx->h_prune_meta.reserve(1));
+  prune_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d_gplan7.p, (int)ctx->n_gplan, robot_xyz[0], robot_xyz[1], robot_xyz[2],
+                                           forward_distance, backward_distance, B200LP_MAX_PLAN, ctx->d_plan7.p,
+                                           ctx->d_prune_pcl.p, ctx->d_prune_meta.p);
+  ++ctx->launches;
+  CK(cudaMemcpyAsync(ctx->h_prune_meta.p, ctx->d_prune_meta.p, sizeof(PruneMeta), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  const PruneMeta m = *ctx->h_prune_meta.p;
+  if (m.overflow) return ctx->fail(B200LP_E_INVALID, "prune_plan: %d poses exceed B200LP_MAX_PLAN=%d", m.info.n_prune, B200LP_MAX_PLAN);
+  *out = m.info;
+  if (m.info.status == 2) out->n_prune = 0;
+  ctx->plan_on_device = true;
+  ctx->plan_n_device = out->n_prune;
+  ctx->have_prune = true;
+  return B200LP_OK;
+}
+
+int b200lp_read_prune_plan(b200lp_ctx* ctx, double* poses7, float* pcl_xyzi, size_t capacity) {
+  if (!ctx) return B200LP_E_INVALID;
+  if (!ctx->have_prune || !ctx->plan_on_device) return ctx->fail(B200LP_E_STATE, "read_prune_plan: no device-side prune plan");
+  const size_t n = (size_t)ctx->plan_n_device;
+  if (n > capacity) return ctx->fail(B200LP_E_INVALID, "read_prune_plan: %zu poses exceed the capacity %zu", n, capacity);
+  if (!n) return B200LP_OK;
+  CK(cudaSetDevice(ctx->device));
+  if (poses7) CK(cudaMemcpyAsync(poses7, ctx->d_plan7.p, n * 56, cudaMemcpyDeviceToHost, ctx->stream));
+  if (pcl_xyzi) CK(cudaMemcpyAsync(pcl_xyzi, ctx->d_prune_pcl.p, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return B200LP_OK;
+}
+
+int b200lp_path_blocked(b200lp_ctx* ctx, double check_radius, b200lp_blocked* out) {
+  if (!ctx) return B200LP_E_INVALID;
+  if (!out) return ctx->fail(B200LP_E_INVALID, "path_blocked: null argument");
+  if (!ctx->have_prune || !ctx->plan_on_device) return ctx->fail(B200LP_E_STATE, "path_blocked: no device-side prune plan");
+  if (!ctx->have_cloud) return ctx->fail(B200LP_E_STATE, "path_blocked: no cloud");
+  b200lp_blocked B{};
+  B.n_total = ctx->plan_n_device;
+  // selfMark's guard: `points.size() <= 5 || pcl_prune_plan_.points.size() <= 0` => ratio 0 (path_blocked_strategy.cpp:62-64)
+  if (!(ctx->grid.n_raw <= 5 || B.n_total <= 0)) {
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->d_blocked.reserve(2));
+    CK(ctx->h_blocked.reserve(2));
+    CK(cudaMemsetAsync(ctx->d_blocked.p, 0, 2 * sizeof(int), ctx->stream));
+    const float r2 = (float)(check_radius * check_radius);  // what pcl::KdTreeFLANN::radiusSearch hands to FLANN
+    blocked_kernel<<<(unsigned)((B.n_total * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+        ctx->grid, ctx->d_prune_pcl.p, B.n_total, (float)std::fabs(check_radius), r2, ctx->d_blocked.p, ctx->d_blocked.p + 1);
+    ++ctx->launches;
+    CK(cudaMemcpyAsync(ctx->h_blocked.p, ctx->d_blocked.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    B.n_blocked = ctx->h_blocked.p[0];
+    B.n_checked = ctx->h_blocked.p[1];
+    const float orig = (float)B.n_total, blocked = (float)B.n_blocked;  // :91-93: float division, then * 100.0 in double
+    B.ratio = (blocked) / (orig) * 100.0;
+  }
+  B.opinion = B.ratio > 0.0 ? 1 : 0;
+  *out = B;
+  return B200LP_OK;
 }
 
 int b200lp_count_radius(b200lp_ctx* ctx, int64_t* sum_n_r1, int64_t* n_poses) {

@@ -974,6 +974,129 @@ argmin_kernel(Consts C, const RobotMeta* __restrict__ meta, int t_cap, const flo
 }
 
 // =============================================================================================
+// the steps either side of the path
+// =============================================================================================
+struct PruneMeta {
+  b200lp_prune_info info;
+  int32_t overflow, pad;
+};
+
+// Local_Planner::prunePlan (local_planner.cpp:374-445), one CTA. The prune plan is two contiguous index ranges of the
+// global plan: [nn - nb + 1, nn] (the backward walk, reversed at :418) followed by [nn, nn + nf - 1].
+__global__ void __launch_bounds__(256) prune_kernel(const double* __restrict__ g7, int n, double rx, double ry, double rz,
+                                                    double forward_distance, double backward_distance, int cap,
+                                                    double* __restrict__ plan7, float4* __restrict__ pcl,
+                                                    PruneMeta* __restrict__ meta) {
+  __shared__ float s_d[8];
+  __shared__ int s_i[8];
+  __shared__ int s_nn, s_nb, s_nf, s_status;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // nearestKSearch(robot_pose, 1): float positions, L2_Simple, lowest index among equal distances
+  const float qx = (float)rx, qy = (float)ry, qz = (float)rz;
+  float best = 3.402823466e+38f;
+  int bi = 0x7fffffff;
+  for (int i = tid; i < n; i += 256) {
+    const float d = l2_simple(qx, qy, qz, (float)g7[i * 7], (float)g7[i * 7 + 1], (float)g7[i * 7 + 2]);
+    if (d < best) { best = d; bi = i; }  // ascending i per thread: strict < keeps the lowest index
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float od = __shfl_xor_sync(kFull, best, o);
+    const int oi = __shfl_xor_sync(kFull, bi, o);
+    if (od < best || (od == best && oi < bi)) { best = od; bi = oi; }
+  }
+  if (lane == 0) { s_d[warp] = best; s_i[warp] = bi; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; ++w)
+      if (s_d[w] < best || (s_d[w] == best && s_i[w] < bi)) { best = s_d[w]; bi = s_i[w]; }
+    int status = 0, nb = 0, nf = 0;
+    if ((double)lpm::fsqrt(best) > 1.0) {
+      status = 2;  // deviated from the plan: the prune plan stays cleared
+    } else {
+      const int nn = bi;
+      auto dist = [&](int a, int b) {  // getDistanceBTWPoseStamp
+        const double dx = g7[a * 7] - g7[b * 7], dy = g7[a * 7 + 1] - g7[b * 7 + 1], dz = g7[a * 7 + 2] - g7[b * 7 + 2];
+        return lpm::dsqrt((dx * dx + dy * dy) + dz * dz);
+      };
+      int last = nn;
+      for (int i = nn; i >= 0; --i) {
+        ++nb;
+        if (i < nn) backward_distance -= dist(last, i);
+        last = i;
+        if (backward_distance < 0) break;
+      }
+      for (int i = nn; i < n; ++i) {
+        ++nf;
+        if (i > nn) forward_distance -= dist(last, i);
+        last = i;
+        if (forward_distance < 0) break;
+      }
+    }
+    s_nn = bi; s_nb = nb; s_nf = nf; s_status = status;
+    PruneMeta m;
+    m.info.status = status;
+    m.info.nearest_index = bi;
+    m.info.n_prune = nb + nf;
+    m.info.n_backward = nb;
+    m.overflow = (nb + nf > cap) ? 1 : 0;
+    m.pad = 0;
+    *meta = m;
+  }
+  __syncthreads();
+  const int nn = s_nn, nb = s_nb, nf = s_nf;
+  if (s_status != 0 || nb + nf > cap) return;
+  for (int k = tid; k < nb + nf; k += 256) {
+    // prune_plan_.poses order
+    const int src = k < nb ? nn - nb + 1 + k : nn + (k - nb);
+#pragma unroll
+    for (int a = 0; a < 7; ++a) plan7[k * 7 + a] = g7[src * 7 + a];
+    // pcl_prune_plan_ order: the backward walk as pushed (nn, nn-1, ...), then the forward walk; intensity tags :407,:424-429
+    const int src2 = k < nb ? nn - k : nn + (k - nb);
+    const float tag = k < nb ? -1.f : (src2 == 0 ? 0.f : 1.f);
+    pcl[k] = make_float4((float)g7[src2 * 7], (float)g7[src2 * 7 + 1], (float)g7[src2 * 7 + 2], tag);
+  }
+}
+
+// PathBlockedStrategy::selfMark (path_blocked_strategy.cpp:56-100): one warp per prune-plan point; the lanes scan the
+// cell rows overlapping the check ball for ANY point with float d^2 < r^2.
+__global__ void __launch_bounds__(256) blocked_kernel(GridDev g, const float4* __restrict__ pcl, int n, float r, float r2,
+                                                      int* __restrict__ n_blocked, int* __restrict__ n_checked) {
+  const int lane = threadIdx.x & 31;
+  const int i = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (i >= n) return;
+  const float4 q = pcl[i];
+  if (q.w < 0.f) return;  // backward poses are skipped
+  if (lane == 0) atomicAdd(n_checked, 1);
+  if (g.n_kept == 0) return;
+  // cells that can hold a point with d^2 < r^2: |p - q| < r per axis, padded for the float rounding of d^2
+  const float rr = r * 1.0001f + 1e-3f + 1e-5f * g.cmax;
+  const float fx0 = cell_f(q.x - rr, g.org[0], g.inv_xy), fx1 = cell_f(q.x + rr, g.org[0], g.inv_xy);
+  const float fy0 = cell_f(q.y - rr, g.org[1], g.inv_xy), fy1 = cell_f(q.y + rr, g.org[1], g.inv_xy);
+  const float fz0 = cell_f(q.z - rr, g.org[2], g.inv_z), fz1 = cell_f(q.z + rr, g.org[2], g.inv_z);
+  if (fx1 < 0.f || fy1 < 0.f || fz1 < 0.f || fx0 > (float)(g.nx - 1) || fy0 > (float)(g.ny - 1) || fz0 > (float)(g.nz - 1)) return;
+  const int x0 = (int)fmaxf(fx0, 0.f), x1 = (int)fminf(fx1, (float)(g.nx - 1));
+  const int y0 = (int)fmaxf(fy0, 0.f), y1 = (int)fminf(fy1, (float)(g.ny - 1));
+  const int z0 = (int)fmaxf(fz0, 0.f), z1 = (int)fminf(fz1, (float)(g.nz - 1));
+  bool hit = false;
+  for (int iz = z0; iz <= z1 && !hit; ++iz)
+    for (int iy = y0; iy <= y1 && !hit; ++iy) {
+      const size_t base = ((size_t)iz * g.ny + iy) * (size_t)g.nx;
+      const uint32_t b = g.cell_start[base + x0], e = g.cell_start[base + x1 + 1];
+      for (uint32_t j0 = b; j0 < e && !hit; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        bool in = false;
+        if (j < e) {
+          const float4 p = __ldg(g.pts + j);
+          in = l2_simple(q.x, q.y, q.z, p.x, p.y, p.z) < r2;
+        }
+        hit = __any_sync(kFull, in);
+      }
+    }
+  if (hit && lane == 0) atomicAdd(n_blocked, 1);
+}
+
+// =============================================================================================
 // read-back / diagnostics
 // =============================================================================================
 // lane-per-pose scan of every cell overlapping the 1 m ball: n_r1 and (optionally) the exact collision flag

@@ -59,6 +59,13 @@ class Session {
   void beginCycle(const geometry_msgs::msg::TransformStamped& robot_pose, const nav_msgs::msg::Odometry& robot_state,
                   const nav_msgs::msg::Path& prune_plan, double current_allowed_max_linear_speed);
 
+  // ---- the steps either side of the cycle ----
+  void setGlobalPlan(const std::vector<double>& poses7);  // Local_Planner::setPlan
+  // Local_Planner::prunePlan on the device; fills poses7 (prune_plan_.poses) and pcl_xyzi (pcl_prune_plan_, x y z tag)
+  b200lp_prune_info prunePlan(const double robot_xyz[3], double forward_distance, double backward_distance,
+                              std::vector<double>& poses7, std::vector<float>& pcl_xyzi);
+  b200lp_blocked pathBlocked(double check_radius);  // PathBlockedStrategy::selfMark
+
   // ---- generator side ----
   int trajectoryCount();
   void fillTrajectory(int id, base_trajectory::Trajectory& traj, bool with_points);
@@ -96,6 +103,8 @@ class Session {
   bool cloud_uploaded_ = false;
   b200lp_query query_{};
   std::vector<double> plan7_;
+  std::vector<double> plan7_device_;  // what the device-side prune plan holds; launch() skips the upload when equal
+  bool plan_resident_ = false;
   bool in_cycle_ = false, launched_ = false, points_loaded_ = false;
   std::uint64_t cycle_ = 0;
   int launches_this_cycle_ = 0;

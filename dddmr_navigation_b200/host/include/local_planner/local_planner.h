@@ -2,8 +2,10 @@
 // Local_Planner::computeVelocityCommand (src/dddmr_local_planner/local_planner/src/local_planner.cpp:482-621) and
 // getBestTrajectory (:447-480), driving the generator and critic plugin stacks through their reference interfaces.
 // Everything ROS supplies in the reference (tf pose, odometry, the perception stack's aggregated cloud, the pruned
-// global plan) is set by the embedding code through the setters below; publishers, tf, prunePlan() and the
-// perception opinions are outside the path (SURVEY.md §8f lists prunePlan / path-blocked as the next rows).
+// global plan) is set by the embedding code through the setters below; publishers and tf are outside the path.
+// setPlan() / prunePlan() (:322-343, :374-445) and the path-blocked opinion of perception_3d::PathBlockedStrategy
+// (dddmr_perception_3d/plugins/path_blocked_strategy.cpp:56-100, consumed at local_planner.cpp:597-607) — SURVEY.md
+// §8(f) rows 1 and 2 — run on the device through the same session.
 #ifndef B200LP_LOCAL_PLANNER_H_
 #define B200LP_LOCAL_PLANNER_H_
 #include <memory>
@@ -15,10 +17,26 @@
 #include "trajectory_generators/trajectory_generators_ros.h"
 
 namespace perception_3d {
-// the two members of perception_3d::SharedData the cycle reads (perception_3d/include/perception_3d/shared_data.h:79,85)
+// the members of perception_3d::SharedData the cycle reads (perception_3d/include/perception_3d/shared_data.h:59,79,85)
 struct SharedData {
   pcl::PointCloud<pcl::PointXYZI>::Ptr aggregate_observation_;
+  pcl::PointCloud<pcl::PointXYZI> pcl_prune_plan_;
   double current_allowed_max_linear_speed_ = -1.0;
+};
+enum PerceptionOpinion { PASS = 0, PATH_BLOCKED_WAIT = 1, PATH_BLOCKED_REPLANNING = 2 };  // perception_3d/sensor.h
+
+// perception_3d::PathBlockedStrategy (plugins/path_blocked_strategy.cpp): the `check_radius` parameter and selfMark(),
+// answered by the device against the voxel grid of the cloud the critics query.
+class PathBlockedStrategy {
+ public:
+  explicit PathBlockedStrategy(double check_radius) : check_radius_(check_radius) {}
+  void selfMark(const std::string& traj_gen_name);
+  PerceptionOpinion getOpinion() const { return opinion_; }
+  double getBlockedRatio() const { return prune_plan_blocked_ratio_; }
+
+ private:
+  double check_radius_ = 0.0, prune_plan_blocked_ratio_ = 0.0;
+  PerceptionOpinion opinion_ = PASS;
 };
 }  // namespace perception_3d
 
@@ -34,7 +52,16 @@ class Local_Planner {
   // inputs the reference pulls from ROS at the top of the cycle
   void setGlobalPose(const geometry_msgs::msg::TransformStamped& trans_gbl2b) { trans_gbl2b_ = trans_gbl2b; got_pose_ = true; }
   void cbOdom(const nav_msgs::msg::Odometry& msg) { robot_state_ = msg; got_odom_ = true; }
-  void setPrunePlan(const nav_msgs::msg::Path& prune_plan) { prune_plan_ = prune_plan; }  // prunePlan()'s output
+  void setPrunePlan(const nav_msgs::msg::Path& prune_plan) { prune_plan_ = prune_plan; }  // a prune plan made elsewhere
+
+  // Local_Planner::setPlan (:322-343) and prunePlan (:374-445): the global plan lives on the device, pruning runs
+  // there, prune_plan_ / pcl_prune_plan_ are read back for the reference's other consumers (publishers, perception).
+  void setPlan(const std::vector<geometry_msgs::msg::PoseStamped>& orig_global_plan, const std::string& traj_gen_name);
+  void prunePlan(double forward_distance, double backward_distance, const std::string& traj_gen_name);
+  const nav_msgs::msg::Path& getPrunePlan() const { return prune_plan_; }
+  const pcl::PointCloud<pcl::PointXYZI>& getPCLPrunePlan() const { return pcl_prune_plan_; }
+  // optional path-blocked strategy: its opinion is looped after scoring like local_planner.cpp:597-607
+  void setPathBlockedStrategy(const std::shared_ptr<perception_3d::PathBlockedStrategy>& s) { path_blocked_ = s; }
 
   dddmr_sys_core::PlannerState computeVelocityCommand(std::string traj_gen_name, base_trajectory::Trajectory& best_traj);
   void getBestTrajectory(std::string traj_gen_name, base_trajectory::Trajectory& best_traj);
@@ -53,6 +80,9 @@ class Local_Planner {
   geometry_msgs::msg::TransformStamped trans_gbl2b_;
   nav_msgs::msg::Odometry robot_state_;
   nav_msgs::msg::Path prune_plan_;
+  pcl::PointCloud<pcl::PointXYZI> pcl_prune_plan_;
+  std::vector<geometry_msgs::msg::PoseStamped> global_plan_;
+  std::shared_ptr<perception_3d::PathBlockedStrategy> path_blocked_;
   bool got_odom_ = false, got_pose_ = false, early_observation_ = true;
 };
 

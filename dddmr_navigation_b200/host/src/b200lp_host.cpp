@@ -252,6 +252,7 @@ void Session::ensureContext() {
   }
   config_dirty_ = false;
   cloud_uploaded_ = false;
+  plan_resident_ = false;
 }
 
 void Session::uploadCloud(const pcl::PointCloud<pcl::PointXYZI>::ConstPtr& cloud) {
@@ -294,11 +295,53 @@ void Session::beginCycle(const geometry_msgs::msg::TransformStamped& robot_pose,
   ++cycle_;
 }
 
+void Session::setGlobalPlan(const std::vector<double>& poses7) {
+  std::lock_guard<std::mutex> lk(mu_);
+  ensureContext();
+  const int rc = b200lp_set_global_plan(ctx_, poses7.data(), poses7.size() / 7);
+  if (rc != B200LP_OK) raise(rc, "b200lp_set_global_plan");
+}
+
+b200lp_prune_info Session::prunePlan(const double robot_xyz[3], double forward_distance, double backward_distance,
+                                     std::vector<double>& poses7, std::vector<float>& pcl_xyzi) {
+  std::lock_guard<std::mutex> lk(mu_);
+  ensureContext();
+  b200lp_prune_info info{};
+  int rc = b200lp_prune_plan(ctx_, robot_xyz, forward_distance, backward_distance, &info);
+  if (rc != B200LP_OK) raise(rc, "b200lp_prune_plan");
+  if (info.status == 1) return info;  // the reference returns before touching the prune plan
+  poses7.assign((size_t)info.n_prune * 7, 0.0);
+  pcl_xyzi.assign((size_t)info.n_prune * 4, 0.f);
+  if (info.n_prune) {
+    rc = b200lp_read_prune_plan(ctx_, poses7.data(), pcl_xyzi.data(), (size_t)info.n_prune);
+    if (rc != B200LP_OK) raise(rc, "b200lp_read_prune_plan");
+  }
+  plan7_device_ = poses7;
+  plan_resident_ = true;
+  launched_ = false;
+  return info;
+}
+
+b200lp_blocked Session::pathBlocked(double check_radius) {
+  std::lock_guard<std::mutex> lk(mu_);
+  ensureContext();
+  if (!cloud_uploaded_) uploadCloud(cloud_);
+  b200lp_blocked b{};
+  const int rc = b200lp_path_blocked(ctx_, check_radius, &b);
+  if (rc != B200LP_OK) raise(rc, "b200lp_path_blocked");
+  return b;
+}
+
 void Session::launch() {
   ensureContext();
   if (!cloud_uploaded_) uploadCloud(cloud_);  // after a context rebuild (or never set: the empty cloud)
-  int rc = b200lp_set_plan(ctx_, plan7_.empty() ? nullptr : plan7_.data(), plan7_.size() / 7);
-  if (rc != B200LP_OK) raise(rc, "b200lp_set_plan");
+  int rc = B200LP_OK;
+  // the device-side prune plan stays where it is when the generator was handed exactly that plan
+  if (!(plan_resident_ && plan7_ == plan7_device_)) {
+    rc = b200lp_set_plan(ctx_, plan7_.empty() ? nullptr : plan7_.data(), plan7_.size() / 7);
+    if (rc != B200LP_OK) raise(rc, "b200lp_set_plan");
+    plan_resident_ = false;
+  }
   rc = b200lp_plan(ctx_, &query_, &result_);
   if (rc != B200LP_OK) raise(rc, "b200lp_plan");
   const size_t n = (size_t)result_.n_traj, nc = critics_.size();
@@ -576,6 +619,14 @@ struct RegisterPlugins {
 // =====================================================================================================
 // the cycle driver (the caller of the path)
 // =====================================================================================================
+namespace perception_3d {
+void PathBlockedStrategy::selfMark(const std::string& traj_gen_name) {
+  const b200lp_blocked b = b200lp::Session::forGenerator(traj_gen_name)->pathBlocked(check_radius_);
+  prune_plan_blocked_ratio_ = b.ratio;
+  opinion_ = b.opinion ? PATH_BLOCKED_WAIT : PASS;
+}
+}  // namespace perception_3d
+
 namespace local_planner {
 
 void Local_Planner::initial(const std::shared_ptr<perception_3d::SharedData>& perception_3d,
@@ -584,6 +635,40 @@ void Local_Planner::initial(const std::shared_ptr<perception_3d::SharedData>& pe
   perception_3d_ = perception_3d;
   mpc_critics_ros_ = mpc_critics;
   trajectory_generators_ros_ = trajectory_generators;
+}
+
+void Local_Planner::setPlan(const std::vector<geometry_msgs::msg::PoseStamped>& orig_global_plan, const std::string& traj_gen_name) {
+  if (orig_global_plan.size() < 3) return;  // "Size of global plan is smaller than 3." (:324-327)
+  global_plan_ = orig_global_plan;
+  std::vector<double> g7;
+  g7.reserve(global_plan_.size() * 7);
+  for (const auto& ps : global_plan_) {
+    const auto& p = ps.pose;
+    const double row[7] = {p.position.x, p.position.y, p.position.z, p.orientation.x, p.orientation.y, p.orientation.z, p.orientation.w};
+    g7.insert(g7.end(), row, row + 7);
+  }
+  b200lp::Session::forGenerator(traj_gen_name)->setGlobalPlan(g7);
+}
+
+void Local_Planner::prunePlan(double forward_distance, double backward_distance, const std::string& traj_gen_name) {
+  if (global_plan_.size() < 3) return;  // :376-377
+  const double xyz[3] = {trans_gbl2b_.transform.translation.x, trans_gbl2b_.transform.translation.y, trans_gbl2b_.transform.translation.z};
+  std::vector<double> p7;
+  std::vector<float> pcl4;
+  const b200lp_prune_info info = b200lp::Session::forGenerator(traj_gen_name)->prunePlan(xyz, forward_distance, backward_distance, p7, pcl4);
+  if (info.status == 1) return;
+  prune_plan_.poses.clear();  // :379-380
+  pcl_prune_plan_.points.clear();
+  for (int i = 0; i < info.n_prune; ++i) {
+    geometry_msgs::msg::PoseStamped ps;
+    ps.pose.position.x = p7[i * 7]; ps.pose.position.y = p7[i * 7 + 1]; ps.pose.position.z = p7[i * 7 + 2];
+    ps.pose.orientation.x = p7[i * 7 + 3]; ps.pose.orientation.y = p7[i * 7 + 4]; ps.pose.orientation.z = p7[i * 7 + 5]; ps.pose.orientation.w = p7[i * 7 + 6];
+    prune_plan_.poses.push_back(ps);
+    pcl::PointXYZI pt;
+    pt.x = pcl4[i * 4]; pt.y = pcl4[i * 4 + 1]; pt.z = pcl4[i * 4 + 2]; pt.intensity = pcl4[i * 4 + 3];
+    pcl_prune_plan_.points.push_back(pt);
+  }
+  if (perception_3d_) perception_3d_->pcl_prune_plan_ = pcl_prune_plan_;  // :518
 }
 
 void Local_Planner::getBestTrajectory(std::string traj_gen_name, base_trajectory::Trajectory& best_traj) {
@@ -628,6 +713,12 @@ dddmr_sys_core::PlannerState Local_Planner::computeVelocityCommand(std::string t
     mc->prune_plan_ = prune_plan_;
     mpc_critics_ros_->updateSharedData();
     getBestTrajectory(traj_gen_name, best_traj);
+  }
+  // :597-607 — loop the perception opinions (here: the optional path-blocked strategy)
+  if (path_blocked_) {
+    path_blocked_->selfMark(traj_gen_name);
+    if (path_blocked_->getOpinion() == perception_3d::PATH_BLOCKED_WAIT) return dddmr_sys_core::PATH_BLOCKED_WAIT;
+    if (path_blocked_->getOpinion() == perception_3d::PATH_BLOCKED_REPLANNING) return dddmr_sys_core::PATH_BLOCKED_REPLANNING;
   }
   return best_traj.cost_ < 0 ? dddmr_sys_core::ALL_TRAJECTORIES_FAIL : dddmr_sys_core::TRAJECTORY_FOUND;
 }

@@ -100,6 +100,33 @@ class LocalPlanner:
         plan = np.ascontiguousarray(plan, dtype=np.float64).reshape(-1, 7)
         self._ck(self.lib.b200lp_set_plan(self.h, plan.ctypes.data_as(C.POINTER(C.c_double)), plan.shape[0]))
 
+    # -- the steps either side of the cycle ------------------------------------------
+    def set_global_plan(self, plan: np.ndarray):
+        """Local_Planner::setPlan (local_planner.cpp:322-343): (n,7) position + orientation xyzw, n >= 3."""
+        plan = np.ascontiguousarray(plan, dtype=np.float64).reshape(-1, 7)
+        self._ck(self.lib.b200lp_set_global_plan(self.h, plan.ctypes.data_as(C.POINTER(C.c_double)), plan.shape[0]))
+
+    def prune_plan(self, robot_xyz, forward_distance: float, backward_distance: float) -> abi.PruneInfo:
+        """Local_Planner::prunePlan (local_planner.cpp:374-445) on the device; the result becomes the cycle's prune plan."""
+        info = abi.PruneInfo()
+        xyz = (C.c_double * 3)(*[float(v) for v in robot_xyz])
+        self._ck(self.lib.b200lp_prune_plan(self.h, xyz, float(forward_distance), float(backward_distance), C.byref(info)))
+        return info
+
+    def read_prune_plan(self, n: int):
+        """-> (prune_plan_.poses (n,7) float64, pcl_prune_plan_ (n,4) float32 x,y,z,intensity in its own order)."""
+        poses = np.zeros((n, 7), np.float64)
+        pcl = np.zeros((n, 4), np.float32)
+        self._ck(self.lib.b200lp_read_prune_plan(self.h, poses.ctypes.data_as(C.POINTER(C.c_double)),
+                                                 pcl.ctypes.data_as(C.POINTER(C.c_float)), n))
+        return poses, pcl
+
+    def path_blocked(self, check_radius: float) -> abi.Blocked:
+        """perception_3d::PathBlockedStrategy::selfMark (path_blocked_strategy.cpp:56-100) of the device-side prune plan."""
+        b = abi.Blocked()
+        self._ck(self.lib.b200lp_path_blocked(self.h, float(check_radius), C.byref(b)))
+        return b
+
     # -- cycle ----------------------------------------------------------------------------------
     def plan(self, q: abi.Query) -> abi.Result:
         r = abi.Result()

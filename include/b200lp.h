@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define B200LP_ABI_VERSION 2
+#define B200LP_ABI_VERSION 3
 
 /* status codes */
 #define B200LP_OK 0
@@ -207,6 +207,41 @@ int b200lp_read_poses(b200lp_ctx* ctx, size_t robot, int32_t traj_id, const b200
  * the range holds more than capacity_poses poses (pose_offsets is still filled, so the caller can size and retry). */
 int b200lp_read_pose_batch(b200lp_ctx* ctx, size_t robot, int32_t t_begin, int32_t t_end, int64_t* pose_offsets,
                            const b200lp_pose_view* view, size_t capacity_poses);
+
+/* ---- the steps either side of the path -------------------------------------------------------- */
+/* What Local_Planner::prunePlan decided (LP/local_planner/src/local_planner.cpp:374-445). */
+typedef struct b200lp_prune_info {
+  int32_t status;        /* 0 = pruned; 1 = global plan has < 3 poses: the reference returns before touching the prune
+                            plan, the previous one stays in effect; 2 = robot farther than 1 m from the plan: the reference
+                            has already cleared the prune plan (:379-380) when it returns, so it is now EMPTY */
+  int32_t nearest_index; /* global-plan index nearest to the robot (-1 when status == 1) */
+  int32_t n_prune;       /* poses of the prune plan now in effect (the nearest pose appears twice, as upstream) */
+  int32_t n_backward;    /* how many of them are tagged backward (pcl_prune_plan_ intensity -1) */
+} b200lp_prune_info;
+/* What perception_3d::PathBlockedStrategy::selfMark decided (dddmr_perception_3d/plugins/path_blocked_strategy.cpp:56-100). */
+typedef struct b200lp_blocked {
+  int32_t n_blocked; /* forward prune-plan points with a cloud point inside check_radius (strict float d^2 < r^2) */
+  int32_t n_checked; /* points with intensity >= 0 */
+  int32_t n_total;   /* |pcl_prune_plan_| */
+  int32_t opinion;   /* 0 = perception_3d::PASS, 1 = PATH_BLOCKED_WAIT (ratio > 0) */
+  double ratio;      /* prune_plan_blocked_ratio_ = (float)n_blocked / (float)n_total * 100.0 */
+} b200lp_blocked;
+
+/* Local_Planner::setPlan (local_planner.cpp:322-343): keep the global plan on the device. n >= 3 as upstream
+ * (smaller plans are rejected with B200LP_E_INVALID and the previous plan stays). */
+int b200lp_set_global_plan(b200lp_ctx* ctx, const double* xyz_qxyzw, size_t n);
+/* Local_Planner::prunePlan on the device: nearest global-plan pose to the robot (float L2, lowest index on exact
+ * ties), walk backward / forward until the distances are used up. On status 0 and 2 the result BECOMES the prune plan
+ * of the following b200lp_plan / b200lp_plan_shard calls without leaving the device (it replaces b200lp_set_plan). */
+int b200lp_prune_plan(b200lp_ctx* ctx, const double robot_xyz[3], double forward_distance, double backward_distance,
+                      b200lp_prune_info* out);
+/* Read the device-side prune plan back: poses7 = prune_plan_.poses (backward part reversed, then forward part),
+ * pcl_xyzi = pcl_prune_plan_ in ITS order (backward part as walked, then forward part; w = intensity tag).
+ * Either pointer may be NULL; capacity in poses. */
+int b200lp_read_prune_plan(b200lp_ctx* ctx, double* poses7, float* pcl_xyzi, size_t capacity);
+/* PathBlockedStrategy::selfMark of the device-side prune plan against the current cloud (the same voxel grid the
+ * critics query). Requires a successful b200lp_prune_plan. */
+int b200lp_path_blocked(b200lp_ctx* ctx, double check_radius, b200lp_blocked* out);
 
 /* Roofline accounting helper: sum over all scored poses of the last plan call of
  * |{cloud points with float d^2 < 1.0 to the pose}| (the reference's radiusSearch candidate set). */

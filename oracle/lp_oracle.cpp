@@ -911,6 +911,86 @@ int lporacle_count_radius(lporacle_ctx* c, int64_t* sum, int64_t* n_poses) {
   return B200LP_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// SURVEY.md §8(f) rows next to the path
+// ---------------------------------------------------------------------------------------------
+// Local_Planner::prunePlan (LP/local_planner/src/local_planner.cpp:374-445) on the plan handed to setPlan (:322-343).
+// nearestKSearch(K=1) over pcl::PointXYZ (float-cast positions, L2_Simple); equal distances resolve to the LOWEST index
+// (a kd-tree's choice among exact ties is traversal dependent; the restatement fixes it).
+int lporacle_prune_plan(const double* g7, size_t n, const double robot_xyz[3], double forward_distance,
+                        double backward_distance, double* out_poses7, float* out_pcl_xyzi, size_t capacity,
+                        b200lp_prune_info* info) {
+  b200lp_prune_info I{};
+  I.status = 0; I.nearest_index = -1; I.n_prune = 0; I.n_backward = 0;
+  auto done = [&](int rc) { if (info) *info = I; return rc; };
+  if (n < 3) { I.status = 1; return done(B200LP_OK); }              // :376-377
+  const float q[3] = {(float)robot_xyz[0], (float)robot_xyz[1], (float)robot_xyz[2]};  // :385-388
+  float best = 0.f; long nn = -1;
+  for (size_t i = 0; i < n; ++i) {
+    const Pt p = {(float)g7[i * 7], (float)g7[i * 7 + 1], (float)g7[i * 7 + 2]};       // :333-339
+    const float d = l2_simple(q, p);
+    if (nn < 0 || d < best) { best = d; nn = (long)i; }
+  }
+  I.nearest_index = (int32_t)nn;
+  // :396-400 (sqrt(float) is sqrtf); the prune plan was cleared at :379-380 and stays empty
+  if ((double)sqrtf(best) > 1.0) { I.status = 2; return done(B200LP_OK); }
+  auto dist = [&](long a, long b) {  // getDistanceBTWPoseStamp (:346-352)
+    const double dx = g7[a * 7] - g7[b * 7], dy = g7[a * 7 + 1] - g7[b * 7 + 1], dz = g7[a * 7 + 2] - g7[b * 7 + 2];
+    return sqrt(dx * dx + dy * dy + dz * dz);
+  };
+  std::vector<long> back, fwd;
+  long last = nn;
+  for (long i = nn; i >= 0; --i) {            // :403-416
+    back.push_back(i);
+    if (i < nn) backward_distance -= dist(last, i);
+    last = i;
+    if (backward_distance < 0) break;
+  }
+  for (long i = nn; i < (long)n; ++i) {       // :420-438
+    fwd.push_back(i);
+    if (i > nn) forward_distance -= dist(last, i);
+    last = i;
+    if (forward_distance < 0) break;
+  }
+  I.n_backward = (int32_t)back.size();
+  I.n_prune = (int32_t)(back.size() + fwd.size());
+  if ((size_t)I.n_prune > capacity) return done(B200LP_E_INVALID);
+  size_t k = 0;
+  if (out_poses7) {  // prune_plan_.poses: backward part reversed (:418), then the forward part
+    for (size_t j = back.size(); j-- > 0;) memcpy(out_poses7 + 7 * k++, g7 + 7 * back[j], 56);
+    for (long i : fwd) memcpy(out_poses7 + 7 * k++, g7 + 7 * i, 56);
+  }
+  k = 0;
+  if (out_pcl_xyzi) {  // pcl_prune_plan_: push order, NOT reversed; intensity tags :407,:424-429
+    for (long i : back) { float* o = out_pcl_xyzi + 4 * k++; o[0] = (float)g7[i * 7]; o[1] = (float)g7[i * 7 + 1]; o[2] = (float)g7[i * 7 + 2]; o[3] = -1.f; }
+    for (long i : fwd) { float* o = out_pcl_xyzi + 4 * k++; o[0] = (float)g7[i * 7]; o[1] = (float)g7[i * 7 + 1]; o[2] = (float)g7[i * 7 + 2]; o[3] = (i == 0) ? 0.f : 1.f; }
+  }
+  return done(B200LP_OK);
+}
+
+// perception_3d::PathBlockedStrategy::selfMark (src/dddmr_perception_3d/plugins/path_blocked_strategy.cpp:56-100)
+// against the cloud last given to lporacle_set_cloud. Brute force: exact by construction.
+int lporacle_path_blocked(lporacle_ctx* c, const float* pcl_xyzi, size_t n, double check_radius, b200lp_blocked* out) {
+  if (!c || !out) return B200LP_E_INVALID;
+  b200lp_blocked B{};
+  B.n_total = (int32_t)n;
+  if (!(c->cloud.size() <= 5 || n == 0)) {  // :62-64
+    const float r2 = (float)(check_radius * check_radius);  // pcl::KdTreeFLANN::radiusSearch -> FLANN radius^2 as float
+    for (size_t i = 0; i < n; ++i) {
+      if (pcl_xyzi[4 * i + 3] < 0) continue;  // :79-80 backward poses are skipped
+      ++B.n_checked;
+      const float q[3] = {pcl_xyzi[4 * i], pcl_xyzi[4 * i + 1], pcl_xyzi[4 * i + 2]};
+      for (const Pt& p : c->cloud)
+        if (l2_simple(q, p) < r2) { ++B.n_blocked; break; }
+    }
+    const float orig = (float)n, blocked = (float)B.n_blocked;  // :91-93 float division, then * 100.0 in double
+    B.ratio = (blocked) / (orig) * 100.0;
+  }
+  B.opinion = B.ratio > 0.0 ? 1 : 0;  // PATH_BLOCKED_WAIT : PASS (:96-97)
+  *out = B;
+  return B200LP_OK;
+}
+
 float lporacle_sinf(int mode, float x) { return (mode ? kLibm : kShared).sinf_(x); }
 float lporacle_cosf(int mode, float x) { return (mode ? kLibm : kShared).cosf_(x); }
 double lporacle_sin(int mode, double x) { return (mode ? kLibm : kShared).sin_(x); }

@@ -47,6 +47,12 @@ int lporacle_read_trajectories(lporacle_ctx* ctx, const b200lp_traj_view* view);
 int lporacle_read_poses(lporacle_ctx* ctx, int32_t traj_id, const b200lp_pose_view* view);
 int lporacle_count_radius(lporacle_ctx* ctx, int64_t* sum_n_r1, int64_t* n_poses);
 
+/* Local_Planner::prunePlan and PathBlockedStrategy::selfMark restated (see lp_oracle.cpp). */
+int lporacle_prune_plan(const double* global_plan7, size_t n, const double robot_xyz[3], double forward_distance,
+                        double backward_distance, double* out_poses7, float* out_pcl_xyzi, size_t capacity,
+                        b200lp_prune_info* info);
+int lporacle_path_blocked(lporacle_ctx* ctx, const float* pcl_xyzi, size_t n, double check_radius, b200lp_blocked* out);
+
 /* Velocity samples exactly as initialise() leaves them in sample_params_ (xv,yv,thetav floats).
  * Returns the count; fills up to cap samples. */
 int lporacle_samples(lporacle_ctx* ctx, const b200lp_query* q, float* out_xyz, int cap);

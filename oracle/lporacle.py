@@ -37,6 +37,9 @@ _SYMS = {
     "lporacle_read_trajectories": (C.c_int, [_P, C.POINTER(abi.TrajView)]),
     "lporacle_read_poses": (C.c_int, [_P, C.c_int32, C.POINTER(abi.PoseView)]),
     "lporacle_count_radius": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "lporacle_prune_plan": (C.c_int, [C.POINTER(C.c_double), C.c_size_t, C.POINTER(C.c_double), C.c_double, C.c_double,
+                                      C.POINTER(C.c_double), C.POINTER(C.c_float), C.c_size_t, C.POINTER(abi.PruneInfo)]),
+    "lporacle_path_blocked": (C.c_int, [_P, C.POINTER(C.c_float), C.c_size_t, C.c_double, C.POINTER(abi.Blocked)]),
     "lporacle_samples": (C.c_int, [_P, C.POINTER(abi.Query), C.POINTER(C.c_float), C.c_int]),
     "lporacle_sinf": (C.c_float, [C.c_int, C.c_float]),
     "lporacle_cosf": (C.c_float, [C.c_int, C.c_float]),
@@ -171,3 +174,28 @@ class OraclePlanner:
         s, n = C.c_int64(), C.c_int64()
         assert self.lib.lporacle_count_radius(self.h, C.byref(s), C.byref(n)) == 0
         return s.value, n.value
+
+    def path_blocked(self, pcl_xyzi, check_radius: float) -> abi.Blocked:
+        """PathBlockedStrategy::selfMark restated, against the cloud given to set_cloud."""
+        pcl = np.ascontiguousarray(pcl_xyzi, np.float32).reshape(-1, 4)
+        b = abi.Blocked()
+        assert self.lib.lporacle_path_blocked(self.h, pcl.ctypes.data_as(C.POINTER(C.c_float)), pcl.shape[0],
+                                              float(check_radius), C.byref(b)) == 0
+        return b
+
+
+def prune_plan(global_plan, robot_xyz, forward_distance, backward_distance, capacity=abi.MAX_PLAN):
+    """Local_Planner::prunePlan restated (lp_oracle.cpp). -> (PruneInfo, poses (n,7), pcl (n,4))."""
+    lib = load()
+    g = np.ascontiguousarray(global_plan, np.float64).reshape(-1, 7)
+    poses = np.zeros((capacity, 7), np.float64)
+    pcl = np.zeros((capacity, 4), np.float32)
+    info = abi.PruneInfo()
+    xyz = (C.c_double * 3)(*[float(v) for v in robot_xyz])
+    rc = lib.lporacle_prune_plan(g.ctypes.data_as(C.POINTER(C.c_double)), g.shape[0], xyz, float(forward_distance),
+                                 float(backward_distance), poses.ctypes.data_as(C.POINTER(C.c_double)),
+                                 pcl.ctypes.data_as(C.POINTER(C.c_float)), capacity, C.byref(info))
+    if rc != 0:
+        raise RuntimeError(f"lporacle_prune_plan: {rc}")
+    n = info.n_prune if info.status == 0 else 0
+    return info, poses[:n], pcl[:n]

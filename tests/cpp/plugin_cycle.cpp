@@ -1,7 +1,9 @@
 // plugin_cycle.cpp — drives ONE local-plan cycle through the reference's plugin interfaces (host layer mirrors) the way
 // Local_Planner::computeVelocityCommand does (local_planner.cpp:482-621), and dumps what the caller sees so pytest can
 // compare it with the CPU oracle. Usage:
-//   plugin_cycle <params.yaml> <scenario.bin> <out_prefix> <generator_name> <early|late>
+//   plugin_cycle <params.yaml> <scenario.bin> <out_prefix> <generator_name> <early|late> [prune <fwd> <bwd> <check_radius>]
+// With `prune`, the scenario's plan is the GLOBAL plan: Local_Planner::setPlan + prunePlan run on the device and a
+// PathBlockedStrategy gives its opinion after scoring; .prune.f64 / .prunepcl.f32 are dumped too.
 // scenario.bin: int64 n_points, int64 n_plan, float32 points[n][8] (PointXYZI), float64 plan[m][7], float64 pose[7],
 //               float64 twist[3], float64 max_speed, float64 heading_deviation
 // outputs:      <out_prefix>.summary.txt (key=value), .traj.f64 (n x 6: cost,xv,yv,thetav,time_delta,n_points),
@@ -82,7 +84,16 @@ int main(int argc, char** argv) {
     mc->getSharedDataPtr()->heading_deviation_ = tail[11];
     lp.setGlobalPose(pose);
     lp.cbOdom(odom);
-    lp.setPrunePlan(plan);
+    const bool prune = argc >= 10 && std::string(argv[6]) == "prune";
+    std::shared_ptr<perception_3d::PathBlockedStrategy> blocked;
+    if (prune) {
+      lp.setPlan(plan.poses, gen);
+      lp.prunePlan(std::atof(argv[7]), std::atof(argv[8]), gen);
+      blocked = std::make_shared<perception_3d::PathBlockedStrategy>(std::atof(argv[9]));
+      lp.setPathBlockedStrategy(blocked);
+    } else {
+      lp.setPrunePlan(plan);
+    }
 
     // ---- two cycles: the second one must reproduce the first (cached state is per cycle) ----
     base_trajectory::Trajectory best;
@@ -116,6 +127,16 @@ int main(int argc, char** argv) {
     dump(out + ".pcl.f32", pcl3);
     dump(out + ".cuboid.f32", cub);
     dump(out + ".aabb.f32", aabb);
+    if (prune) {
+      std::vector<double> pp;
+      std::vector<float> pc;
+      for (const auto& ps : lp.getPrunePlan().poses)
+        pp.insert(pp.end(), {ps.pose.position.x, ps.pose.position.y, ps.pose.position.z, ps.pose.orientation.x,
+                             ps.pose.orientation.y, ps.pose.orientation.z, ps.pose.orientation.w});
+      for (const auto& pt : lp.getPCLPrunePlan().points) pc.insert(pc.end(), {pt.x, pt.y, pt.z, pt.intensity});
+      dump(out + ".prune.f64", pp);
+      dump(out + ".prunepcl.f32", pc);
+    }
     const b200lp_result& r = session->result();
     std::ofstream s(out + ".summary.txt");
     s.precision(17);
@@ -124,6 +145,7 @@ int main(int argc, char** argv) {
       << "\nn_traj=" << lp.trajectories_->size() << "\nlaunches_first=" << launches_first
       << "\nlaunches_second=" << launches_second << "\ndevice_best_id=" << r.best_id << "\ndevice_best_cost=" << r.best_cost
       << "\ndevice_n_samples=" << r.n_samples << "\ndevice_n_poses=" << r.n_poses << "\n";
+    if (prune) s << "blocked_ratio=" << blocked->getBlockedRatio() << "\nblocked_opinion=" << (int)blocked->getOpinion() << "\n";
     b200lp::Session::resetAll();
   } catch (const b200lp::Error& e) {
     std::fprintf(stderr, "b200lp::Error(%d): %s\n", e.code(), e.what());

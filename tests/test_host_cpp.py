@@ -148,3 +148,37 @@ def test_plugin_cycle_matches_oracle(driver, tmp_path, case, mode):
         a, b = off[tid], off[tid + 1]
         for k in ("pose", "pcl_pose", "cuboid", "aabb"):
             assert np.array_equal(poses[k][a:b], po[k]), (case, tid, k)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("radius,expect_blocked", [(0.05, False), (2.5, True)])
+def test_plugin_cycle_with_device_prune_plan_and_path_blocked_opinion(driver, tmp_path, radius, expect_blocked):
+    """SURVEY.md §8(f) rows 1-2 through the host layer: Local_Planner::setPlan + prunePlan and the PathBlockedStrategy
+    opinion, all on the device; the generator scores against the device-side prune plan (one launch per cycle)."""
+    from oracle import lporacle as O
+    sc = synth.c1_ramp(n_points=20_000)
+    last, prev = sc.plan[-1], sc.plan[-2]
+    ext = np.repeat(last[None, :], 80, 0)
+    ext[:, :3] += (last[:3] - prev[:3])[None, :] * np.arange(1, 81)[:, None]
+    gplan = np.concatenate([sc.plan, ext])
+    gen = "differential_drive_simple"
+    yaml, scb = _write_case(str(tmp_path), sc.config, gen, sc.cloud, gplan, sc.pose, sc.twist)
+    prefix = str(tmp_path / "out")
+    p = subprocess.run([driver, yaml, scb, prefix, gen, "early", "prune", "3.0", "1.0", str(radius)], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr
+    s, traj, _ = _load(prefix)
+    info, o_poses, o_pcl = O.prune_plan(gplan, sc.pose[:3], 3.0, 1.0)
+    assert info.status == 0
+    assert np.array_equal(np.fromfile(prefix + ".prune.f64", np.float64).reshape(-1, 7), o_poses)
+    assert np.array_equal(np.fromfile(prefix + ".prunepcl.f32", np.float32).reshape(-1, 4), o_pcl)
+    ora = O.OraclePlanner(sc.config, O.MATH_SHARED, O.INDEX_GRID)
+    ora.set_cloud(sc.cloud)
+    ora.set_plan(o_poses)
+    r = ora.plan(make_query(sc.pose, sc.twist))
+    assert np.array_equal(traj[:, 0], ora.read_trajectories()["cost"])
+    assert int(s["best_id"]) == r.best_id
+    b = ora.path_blocked(o_pcl, radius)
+    assert s["blocked_ratio"] == b.ratio and int(s["blocked_opinion"]) == b.opinion == (1 if expect_blocked else 0)
+    # PATH_BLOCKED_WAIT = 5 overrides the trajectory verdict (local_planner.cpp:597-607)
+    assert int(s["state"]) == (5 if expect_blocked else (4 if r.best_id >= 0 else 2))
+    assert int(s["launches_first"]) == 1 and int(s["launches_second"]) == 1
