@@ -761,52 +761,69 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, const Robot
         }
       }
     }
-    const bool any_rollout_work = need_box || need_mm || need_stick || need_last_nn || need_pp;
-
-    // ---- rollout + query, 32 poses at a time ---------------------------------------------------
-    double stick_sum = 0.0;
-    float last_nn = 0.f;
+    // ---- pass 1: cuboids + obstacle query, 32 poses at a time ----------------------------------------
     int hit_box = -1, hit_mm = -1;  // first colliding pose per collision-critic kind
-    const bool done = !any_rollout_work;
-    for (int base = 0; base < n && !done; base += 32) {
-      const int k = base + lane;
-      const bool live = k < n;
-      const float4 pz = live ? __ldg(traj_poses + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-      double L[9], t[3];
-      pose_affine(W.R0, W.t0, pz.x, pz.y, pz.z, L, t);
-      CellBox cbx;
-      pose_geometry(C, g, L, t, stash, pre, &cbx, lane, live, nullptr);
-      group_union(cbx);
-      __syncwarp();
+    bool rejected = false;           // the stack's first collision critic hit and ends the evaluation
+    if (need_box || need_mm) {
+      for (int base = 0; base < n; base += 32) {
+        const int k = base + lane;
+        const bool live = k < n;
+        const float4 pz = live ? __ldg(traj_poses + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        double L[9], t[3];
+        pose_affine(W.R0, W.t0, pz.x, pz.y, pz.z, L, t);
+        CellBox cbx;
+        pose_geometry(C, g, L, t, stash, pre, &cbx, lane, live, nullptr);
+        group_union(cbx);
+        __syncwarp();
 
-      // obstacle query, groups of kGroup consecutive poses, once per collision-critic kind still undecided
-      const int n_here = min(32, n - base);
+        // groups of kGroup consecutive poses, once per collision-critic kind still undecided
+        const int n_here = min(32, n - base);
 #pragma unroll 1
-      for (int kind = 0; kind < 2; ++kind) {
-        if (kind == 0 ? !(need_box && hit_box < 0) : !(need_mm && hit_mm < 0)) continue;
+        for (int kind = 0; kind < 2; ++kind) {
+          if (kind == 0 ? !(need_box && hit_box < 0) : !(need_mm && hit_mm < 0)) continue;
 #pragma unroll 1
-        for (int col0 = 0; col0 < n_here; col0 += kGroup) {
-          CellBox ub;
-          ub.x0 = __shfl_sync(kFull, cbx.x0, col0); ub.x1 = __shfl_sync(kFull, cbx.x1, col0);
-          ub.y0 = __shfl_sync(kFull, cbx.y0, col0); ub.y1 = __shfl_sync(kFull, cbx.y1, col0);
-          ub.z0 = __shfl_sync(kFull, cbx.z0, col0); ub.z1 = __shfl_sync(kFull, cbx.z1, col0);
-          const unsigned h = kind ? sweep_points<true>(g, stash, pre, col0, lane, ub)
-                                  : sweep_points<false>(g, stash, pre, col0, lane, ub);
-          if (h) {
-            const int hp = base + col0 + (__ffs(h) - 1);
-            if (kind) hit_mm = hp; else hit_box = hp;
-            break;
+          for (int col0 = 0; col0 < n_here; col0 += kGroup) {
+            CellBox ub;
+            ub.x0 = __shfl_sync(kFull, cbx.x0, col0); ub.x1 = __shfl_sync(kFull, cbx.x1, col0);
+            ub.y0 = __shfl_sync(kFull, cbx.y0, col0); ub.y1 = __shfl_sync(kFull, cbx.y1, col0);
+            ub.z0 = __shfl_sync(kFull, cbx.z0, col0); ub.z1 = __shfl_sync(kFull, cbx.z1, col0);
+            const unsigned h = kind ? sweep_points<true>(g, stash, pre, col0, lane, ub)
+                                    : sweep_points<false>(g, stash, pre, col0, lane, ub);
+            if (h) {
+              const int hp = base + col0 + (__ffs(h) - 1);
+              if (kind) hit_mm = hp; else hit_box = hp;
+              break;
+            }
           }
         }
+        __syncwarp();
+        // A hit of the FIRST collision critic of the stack ends the trajectory (the reference returns -1
+        // there) when nothing that precedes it in the stack depends on the rollout. A later collision
+        // critic hitting first only retires that critic: the earlier one must still run to the end.
+        if (early_ok && first_coll_kind >= 0 && (first_coll_kind ? hit_mm : hit_box) >= 0) {
+          rejected = true;
+          break;
+        }
+        if (!(need_box && hit_box < 0) && !(need_mm && hit_mm < 0)) break;  // every collision critic is decided
       }
-      // A hit of the FIRST collision critic of the stack ends the trajectory (the reference returns -1
-      // there) when nothing that precedes it in the stack depends on the rollout. A later collision
-      // critic hitting first only retires that critic: the earlier one must still run to the end.
-      if (early_ok && first_coll_kind >= 0 && (first_coll_kind ? hit_mm : hit_box) >= 0) break;
+    }
 
-      if (need_stick || need_last_nn) {
+    // ---- pass 2: path critics, only for trajectories the collision critic did not already reject ----
+    double stick_sum = 0.0;
+    float last_nn = 0.f;
+    if (!rejected && (need_stick || need_last_nn)) {
+      for (int base = 0; base < n; base += 32) {
+        const int k = base + lane;
+        const int n_here = min(32, n - base);
         float d2 = 0.f;
-        if (live) d2 = plan_nn_d2(plan, plan_n, stash[F_PX * 32 + lane], stash[F_PY * 32 + lane], stash[F_PZ * 32 + lane]);
+        if (k < n) {
+          const float4 pz = __ldg(traj_poses + k);
+          // Trajectory::getPCLPoint: the translation of pos_af3 * [Rz(th), (x,y,0)] (same expression as pose_affine)
+          float pw[3];
+#pragma unroll
+          for (int a = 0; a < 3; ++a) pw[a] = (float)((W.R0[a * 3] * (double)pz.x + W.R0[a * 3 + 1] * (double)pz.y) + W.t0[a]);
+          d2 = plan_nn_d2(plan, plan_n, pw[0], pw[1], pw[2]);
+        }
         const float sq = lpm::fsqrt(d2);
         if (need_stick) {
           // normalized_distance += sqrt(d2), in pose order, in double (stick_path_model.cpp:68)
@@ -814,7 +831,6 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, const Robot
         }
         if (n - 1 - base < 32 && n - 1 >= base) last_nn = __shfl_sync(kFull, sq, n - 1 - base);
       }
-      __syncwarp();
     }
     double pp_dist = 0.0, pp_yaw = 0.0;
     if (need_pp) {
