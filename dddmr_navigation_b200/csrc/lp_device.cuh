@@ -268,7 +268,8 @@ __device__ __forceinline__ void rollout32(Carry& c, int lane, int theory, float 
 __device__ __forceinline__ void pose_affine(const double* R0, const double* t0, float x, float y, float th,
                                             double* L, double* t) {
   const double ang = (double)th;
-  const double s = lpm::sin(ang), co = lpm::cos(ang);
+  double s, co;
+  lpm::sincos(ang, &s, &co);
   const double r22 = (1.0 - co) + co;
   const double xd = (double)x, yd = (double)y;
 #pragma unroll

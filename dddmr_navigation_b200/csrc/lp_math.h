@@ -243,6 +243,25 @@ LPM_HD_BIG double cos(double x) {
   }
 }
 
+// sin and cos of the same argument from one reduction: exactly the values lpm::sin / lpm::cos return
+LPM_HD_BIG void sincos(double x, double* sn, double* cs) {
+  if (dabs(x) <= 0.78539816339744827900) {
+    const bool tiny = dabs(x) < 7.450580596923828125e-9;
+    *sn = tiny ? x : ksin(x, 0.0, 0);
+    *cs = tiny ? 1.0 : kcos(x, 0.0);
+    return;
+  }
+  double y0, y1;
+  const int n = rem_pio2(x, &y0, &y1);
+  const double s = ksin(y0, y1, 1), c = kcos(y0, y1);
+  switch (n & 3) {
+    case 0: *sn = s; *cs = c; break;
+    case 1: *sn = c; *cs = -s; break;
+    case 2: *sn = -s; *cs = -c; break;
+    default: *sn = -c; *cs = s; break;
+  }
+}
+
 // ----------------------------------------------------------------------------------------
 // asin / atan / atan2 (msun e_asin.c, s_atan.c, e_atan2.c forms). Finite inputs only: the
 // critic feeds matrix entries of a finite rotation.
