@@ -15,15 +15,16 @@ poses = sum of num_steps over the generated trajectories (exactly what the oracl
                    cycle, model_shared_data.h:78-81), uploads plan + query and reads the result back.
   roofline         fused plan kernel: algorithmic bytes (16 B x n_r1(pose) + 64 B per pose) / its
                    CUDA-event duration, against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
-  cpu_baseline     the CPU oracle with the reference's vendored nanoflann kd-tree and glibc libm, single thread,
-                   timed on this box's host cores (N=1, rank 0 only).
+  cpu_baseline     the reference's OWN theory/critic sources (oracle/_ref/liblpref.so, built from /root/reference against
+                   stand-ins for its third-party headers), single thread as upstream, one or two full cycles of the
+                   same workload on this box's host cores (N=1, rank 0 only); the oracle port when that .so is absent.
 
 N > 1 (torchrun, one rank per GPU): fleet sharding, weak scaling — every rank plans for its own robot on its
 own replica of the map; no collective on the data path. value = poses of all ranks / max-over-ranks time.
 --workload C5 is the batched-fleet configuration (512 robots per GPU on the 8 M-point map, weak scaling, no
 collective); --workload C4 is the sample-sharded one (131 k trajectories split over the ranks, strong scaling,
 one NCCL all-reduce of 16*W bytes per cycle, step time = host-observed kernels + exchange).
---impl reference times the CPU restatement with all host threads (rank 0 only).
+--impl reference times the reference's own sources (same .so) on a thinned velocity sampling of the workload (rank 0 only).
 """
 from __future__ import annotations
 
@@ -211,40 +212,68 @@ def pinned_copy(arr: np.ndarray):
     return t, t.numpy()
 
 
+REF_SAMPLES = (64.0, 64.0)  # --impl reference: velocity samples per axis of the bounded sample (C2 itself is 128 x 128)
+
+
 def run_reference(args, rank, world):
-    """CPU arm: the oracle restatement (reference's nanoflann kd-tree + glibc), all host threads."""
+    """CPU arm. With oracle/_ref/liblpref.so present (built from the reference's OWN theory / critic sources, see
+    oracle/Makefile) it times that code — single-threaded, as the reference is — on the named map and parameters with the
+    velocity sampling thinned to REF_SAMPLES so that K steps end within minutes. Otherwise it times the oracle port on all
+    host threads."""
     if rank != 0:
         return 0
+    import dataclasses
     from dddmr_navigation_b200 import make_query
     from oracle import lporacle as O
-    wl = make_workload(args.workload if args.workload in ("C1", "C2", "C3") else "C3", 0)
+    name = args.workload if args.workload in ("C1", "C2", "C3") else "C3"
+    wl = make_workload(name, 0)
     sc, pose, twist, plan, desc = wl["sc"], wl["pose"], wl["twist"], wl["plan"], wl["desc"]
-    use_ref = O.have_ref()
-    ora = O.OraclePlanner(sc.config, O.MATH_LIBM, O.INDEX_NANOFLANN if use_ref else O.INDEX_GRID)
-    ora.set_cloud(sc.cloud)
-    ora.set_plan(plan)
-    threads = os.cpu_count() or 1
-    stride = args.ref_stride
-    ora.set_sample_stride(stride)
     q = make_query(pose, twist)
+    if O.have_reference_sources():
+        gen = dict(sc.config.generator)
+        thinned = name != "C1"
+        if thinned:
+            gen.update(linear_x_sample=REF_SAMPLES[0], angular_z_sample=REF_SAMPLES[1])
+        cfg = dataclasses.replace(sc.config, generator=gen)
+        ref = O.ReferencePlanner(cfg)
+        ref.set_plan(plan)
+        threads, kind = 1, "reference"
+
+        def step():
+            ref.set_cloud(sc.cloud)  # the cloud object is new every cycle upstream; the kd-tree is rebuilt in updateData()
+            return ref.plan(q)
+        sample = ((f"the reference's own C++ (oracle/_ref/liblpref.so: theories, critics, stacked models compiled from /root/reference "
+                   f"against stand-ins for Eigen/PCL/tf2/rclcpp, vendored nanoflann kd-tree), 1 thread as upstream; "
+                   + (f"velocity sampling thinned from the workload's to {int(REF_SAMPLES[0])} x {int(REF_SAMPLES[1])} samples, "
+                      if thinned else "the full workload, ")
+                   + "kd-tree over the full cloud rebuilt every step"))
+    else:
+        use_ref = O.have_ref()
+        ora = O.OraclePlanner(sc.config, O.MATH_LIBM, O.INDEX_NANOFLANN if use_ref else O.INDEX_GRID)
+        ora.set_cloud(sc.cloud)
+        ora.set_plan(plan)
+        threads, kind = os.cpu_count() or 1, "port"
+        ora.set_sample_stride(args.ref_stride)
+
+        def step():
+            return ora.plan(q, threads)
+        sample = (f"oracle port, every {args.ref_stride}-th velocity sample, all host threads, kd-tree rebuilt every step; "
+                  f"index={'reference-vendored nanoflann 1.5.1' if use_ref else 'oracle bucket grid'}, glibc libm")
     for _ in range(min(args.warmup, 1)):
-        ora.plan(q, threads)
+        step()
     t0 = time.perf_counter()
     poses = 0
     for _ in range(args.steps):
-        r = ora.plan(q, threads)
+        r = step()
         poses += r.n_poses
     dt = time.perf_counter() - t0
     value = poses / dt
-    base = {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": (f"every {stride}-th velocity sample of the workload ({r.n_traj} trajectories, {r.n_poses} poses per step), "
-                       f"kd-tree over the full cloud rebuilt every step as the reference does; "
-                       f"index={'reference-vendored nanoflann 1.5.1 (oracle/_ref)' if use_ref else 'oracle bucket grid'}, glibc libm; "
-                       "the literal reference binary cannot be built here (needs ROS 2/PCL/FLANN/Eigen/tf2)")}
+    sample += f" ({r.n_traj} trajectories, {r.n_poses} poses per step)"
+    base = {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-            "config": {"workload": desc, "sample_stride": stride, "threads": threads},
+            "config": {"workload": desc, "threads": threads},
             "cpu_baseline": base,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -460,31 +489,54 @@ def main():
     # ---------------- CPU baseline on this box's host cores (rank 0, N=1) ----------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline and mode == "single":
         from oracle import lporacle as O
-        use_ref = O.have_ref()
-        ora = O.OraclePlanner(sc.config, O.MATH_LIBM, O.INDEX_NANOFLANN if use_ref else O.INDEX_GRID)
-        ora.set_cloud(sc.cloud)
-        ora.set_plan(plan)
-        stride_s = max(1, args.ref_stride)
-        ora.set_sample_stride(stride_s)
-        t0 = time.perf_counter()
-        cp = 0
-        for _ in range(args.cpu_baseline_steps):
-            ro = ora.plan(q, 1)
-            cp += ro.n_poses
-        dt = time.perf_counter() - t0
-        if stride_s == 1:
-            assert ro.best_id == r.best_id, (ro.best_id, r.best_id)  # same best trajectory as the libm/nanoflann CPU path
-        line["cpu_baseline"] = {
-            "value": cp / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": (f"{args.cpu_baseline_steps} full cycles of the same workload"
-                       + ("" if stride_s == 1 else f" restricted to every {stride_s}-th velocity sample")
-                       + f" ({ro.n_poses} poses each), kd-tree over the full cloud rebuilt every cycle like the reference; "
-                       f"index={'reference-vendored nanoflann 1.5.1 (oracle/_ref)' if use_ref else 'oracle bucket grid'}, glibc libm, "
-                       f"1 thread (the reference path is single-threaded); host has {os.cpu_count()} cores"),
-            "ms_per_cycle": 1e3 * dt / args.cpu_baseline_steps,
-            "stages_s_last_cycle": {"index_build": ora.timing[0], "rollout": ora.timing[1], "score": ora.timing[2]},
-            "best_id_matches_gpu": bool(stride_s != 1 or ro.best_id == r.best_id),
-        }
+        if O.have_reference_sources() and max(1, args.ref_stride) == 1:
+            # the reference's own sources, the FULL workload, one thread (as upstream); ~10 s per cycle at C2
+            ref = O.ReferencePlanner(sc.config)
+            ref.set_plan(plan)
+            n_cycles = max(1, min(args.cpu_baseline_steps, 2))
+            t0 = time.perf_counter()
+            cp = 0
+            for _ in range(n_cycles):
+                ref.set_cloud(sc.cloud)
+                ro = ref.plan(q)
+                cp += ro.n_poses
+            dt = time.perf_counter() - t0
+            assert ro.best_id == r.best_id, (ro.best_id, r.best_id)  # the GPU picks the trajectory the reference's own code picks
+            line["cpu_baseline"] = {
+                "value": cp / dt, "unit": UNIT, "cores": 1, "kind": "reference",
+                "sample": (f"{n_cycles} full cycle(s) of the same workload ({ro.n_poses} poses each) through the reference's own C++ "
+                           "(oracle/_ref/liblpref.so: its theory / critic / stacked-model sources compiled from /root/reference against "
+                           "stand-ins for Eigen/PCL/tf2/rclcpp, its vendored nanoflann as kd-tree), kd-tree rebuilt every cycle, "
+                           f"1 thread (the reference path is single-threaded); host has {os.cpu_count()} cores"),
+                "ms_per_cycle": 1e3 * dt / n_cycles,
+                "best_id_matches_gpu": bool(ro.best_id == r.best_id), "best_cost_matches_gpu_1e-4": bool(abs(ro.best_cost - r.best_cost) <= 1e-4 * abs(ro.best_cost)),
+            }
+        else:
+            use_ref = O.have_ref()
+            ora = O.OraclePlanner(sc.config, O.MATH_LIBM, O.INDEX_NANOFLANN if use_ref else O.INDEX_GRID)
+            ora.set_cloud(sc.cloud)
+            ora.set_plan(plan)
+            stride_s = max(1, args.ref_stride)
+            ora.set_sample_stride(stride_s)
+            t0 = time.perf_counter()
+            cp = 0
+            for _ in range(args.cpu_baseline_steps):
+                ro = ora.plan(q, 1)
+                cp += ro.n_poses
+            dt = time.perf_counter() - t0
+            if stride_s == 1:
+                assert ro.best_id == r.best_id, (ro.best_id, r.best_id)
+            line["cpu_baseline"] = {
+                "value": cp / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": (f"{args.cpu_baseline_steps} full cycles of the same workload"
+                           + ("" if stride_s == 1 else f" restricted to every {stride_s}-th velocity sample")
+                           + f" ({ro.n_poses} poses each) through the oracle port, kd-tree rebuilt every cycle; "
+                           f"index={'reference-vendored nanoflann 1.5.1 (oracle/_ref)' if use_ref else 'oracle bucket grid'}, glibc libm, "
+                           f"1 thread; host has {os.cpu_count()} cores"),
+                "ms_per_cycle": 1e3 * dt / args.cpu_baseline_steps,
+                "stages_s_last_cycle": {"index_build": ora.timing[0], "rollout": ora.timing[1], "score": ora.timing[2]},
+                "best_id_matches_gpu": bool(stride_s != 1 or ro.best_id == r.best_id),
+            }
 
     if rank == 0:
         print(json.dumps(line), flush=True)

@@ -3,7 +3,8 @@
 // TEST INFRASTRUCTURE ONLY. Nothing under dddmr_navigation_b200/ may call into this file; only
 // tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs load it.
 //
-// PARITY UNPINNED (see lp_oracle.h): every function below cites the reference lines it restates
+// PARITY: pinned to the reference's own sources run here (oracle/_ref/liblpref.so, tests/test_reference_sources.py);
+// third-party arithmetic (Eigen / PCL / FLANN / tf2) unpinned — see lp_oracle.h. Every function below cites the reference lines it restates
 // (paths relative to /root/reference/src/dddmr_local_planner/, shortened to TG/, MC/, BT/, LP/ as in
 // SURVEY.md). Arithmetic that lives in un-vendored third-party code (Eigen 3.4, PCL 1.15, FLANN
 // 1.9.1, tf2 Humble) follows the numeric contract of SURVEY.md Appendix A.

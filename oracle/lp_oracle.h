@@ -2,11 +2,19 @@
  *
  * The oracle restates, on the CPU and in the reference's own arithmetic, the local-planner
  * rollout-and-score path of dddmr_navigation. Only tests/, __graft_entry__.smoke() and
- * bench.py's cpu_baseline / --impl reference legs may load it. PARITY UNPINNED: the reference
- * ships no tests or golden vectors for this path and cannot be built in this image (needs
- * ROS 2 Humble, PCL 1.15, FLANN, Eigen, tf2), so the oracle is pinned only to (a) glibc sinf/cosf,
- * exhaustively, (b) hand-derived micro-cases, (c) the reference's vendored nanoflann as an
- * independent radius-search index (oracle/_ref build). See DESIGN.md §3.
+ * bench.py's cpu_baseline / --impl reference legs may load it.
+ *
+ * PARITY STATUS: the reference ships no tests or golden vectors for this path and its own build
+ * (colcon + ROS 2 Humble, PCL 1.15, FLANN, Eigen, tf2) cannot run in this image. What the oracle IS
+ * pinned to: the reference's OWN sources for this path — three theories, StackedGenerator,
+ * base_trajectory::Trajectory, seven critics, StackedScoringModel — compiled where they lie under
+ * /root/reference into oracle/_ref/liblpref.so against stand-ins for the third-party headers they
+ * include (oracle/ref_shims/) with the reference's vendored nanoflann as kd-tree;
+ * tests/test_reference_sources.py requires IDENTICAL bits from that code and from this restatement
+ * (libm mode) for every trajectory, pose, cuboid, AABB, critic value, cost and the selected id, on
+ * the playground / C1 / C2 scenes, all theories, edge cases and 48 randomised scenes. What stays
+ * UNPINNED: the arithmetic inside Eigen / PCL / FLANN / tf2 themselves (which
+ * both sides follow), plus glibc sinf/cosf which lp_math.h matches exhaustively. See DESIGN.md §2.
  *
  * It reuses the product's public POD structs (include/b200lp.h) so tests feed both sides the
  * same bytes.

@@ -199,3 +199,94 @@ def prune_plan(global_plan, robot_xyz, forward_distance, backward_distance, capa
         raise RuntimeError(f"lporacle_prune_plan: {rc}")
     n = info.n_prune if info.status == 0 else 0
     return info, poses[:n], pcl[:n]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# oracle/_ref/liblpref.so: the REFERENCE's own theory / critic / stacked-model sources compiled where they lie under
+# /root/reference against the third-party stand-ins of oracle/ref_shims/ (oracle/Makefile target `lpref`). Used by
+# tests/test_reference_sources.py to pin the restatement above to the reference's real control flow.
+# ---------------------------------------------------------------------------------------------------------------------
+LIB_LPREF = os.path.join(HERE, "_ref", "liblpref.so")
+_LPREF_SYMS = {
+    "lpref_last_error": (C.c_char_p, [_P]),
+    "lpref_create": (C.c_int, [C.POINTER(_P), C.POINTER(abi.Limits), C.POINTER(abi.Params), C.POINTER(C.c_float),
+                               C.POINTER(abi.Critic), C.c_int]),
+    "lpref_destroy": (None, [_P]),
+    "lpref_set_cloud": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t]),
+    "lpref_set_plan": (C.c_int, [_P, C.POINTER(C.c_double), C.c_size_t]),
+    "lpref_plan": (C.c_int, [_P, C.POINTER(abi.Query), C.POINTER(abi.Result)]),
+    "lpref_read_trajectories": (C.c_int, [_P, C.POINTER(abi.TrajView)]),
+    "lpref_read_poses": (C.c_int, [_P, C.c_int32, C.POINTER(abi.PoseView)]),
+}
+_lpref = None
+
+
+def have_reference_sources() -> bool:
+    return os.path.exists(LIB_LPREF)
+
+
+def load_lpref():
+    global _lpref
+    if _lpref is None:
+        lib = C.CDLL(LIB_LPREF)
+        for name, (res, args) in _LPREF_SYMS.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lpref = lib
+    return _lpref
+
+
+class ReferencePlanner:
+    """The reference's real C++ (DD/omni/rotate theories, seven critics, StackedGenerator, StackedScoringModel,
+    base_trajectory::Trajectory) behind the same surface as OraclePlanner."""
+
+    def __init__(self, config: PlannerConfig):
+        self.lib = load_lpref()
+        self.config = config
+        self._L, self._Pm = config.limits(), config.params()
+        self._cub = config.cuboid()
+        self._crit, self.n_critics = config.critic_array()
+        h = _P()
+        rc = self.lib.lpref_create(C.byref(h), C.byref(self._L), C.byref(self._Pm), self._cub.ctypes.data_as(C.POINTER(C.c_float)),
+                                   self._crit, self.n_critics)
+        assert rc == 0, rc
+        self.h = h
+        self.last = None
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.lpref_destroy(self.h)
+            self.h = None
+
+    def set_cloud(self, pts):
+        pts = np.ascontiguousarray(pts, np.float32)
+        assert self.lib.lpref_set_cloud(self.h, pts.ctypes.data_as(_P), pts.shape[0], pts.shape[1] * 4) == 0
+
+    def set_plan(self, plan):
+        plan = np.ascontiguousarray(plan, np.float64).reshape(-1, 7)
+        assert self.lib.lpref_set_plan(self.h, plan.ctypes.data_as(C.POINTER(C.c_double)), plan.shape[0]) == 0
+
+    def plan(self, q: abi.Query) -> abi.Result:
+        r = abi.Result()
+        rc = self.lib.lpref_plan(self.h, C.byref(q), C.byref(r))
+        assert rc == 0, (rc, self.lib.lpref_last_error(self.h))
+        self.last = r
+        return r
+
+    def read_trajectories(self) -> dict:
+        n, nc = self.last.n_traj, max(1, self.n_critics)
+        d = {"sample_index": np.zeros(n, np.int32), "vel": np.zeros((n, 3), np.float32), "num_steps": np.zeros(n, np.int32),
+             "time_delta": np.zeros(n, np.float64), "cost": np.zeros(n, np.float64),
+             "critic_scores": np.zeros((n, nc if self.n_critics else 0), np.float64), "first_hit_pose": np.zeros(n, np.int32)}
+        v = abi.TrajView(*[d[k].ctypes.data_as(t) if d[k].size else None for k, t in abi.TrajView._fields_])
+        assert self.lib.lpref_read_trajectories(self.h, C.byref(v)) == 0
+        return d
+
+    def read_poses(self, traj_id: int, num_steps: int) -> dict:
+        n = num_steps
+        d = {"pose": np.zeros((n, 7), np.float64), "pcl_pose": np.zeros((n, 3), np.float32),
+             "cuboid": np.zeros((n, 8, 3), np.float32), "aabb": np.zeros((n, 6), np.float32)}
+        v = abi.PoseView(d["pose"].ctypes.data_as(C.POINTER(C.c_double)), d["pcl_pose"].ctypes.data_as(C.POINTER(C.c_float)),
+                         d["cuboid"].ctypes.data_as(C.POINTER(C.c_float)), d["aabb"].ctypes.data_as(C.POINTER(C.c_float)), None, None)
+        assert self.lib.lpref_read_poses(self.h, traj_id, C.byref(v)) == 0
+        return d

@@ -1,0 +1,102 @@
+"""Pins the oracle to the REFERENCE'S OWN C++.
+
+oracle/_ref/liblpref.so is built (oracle/Makefile, target `lpref`) from the reference's unmodified sources where they lie
+under /root/reference — the three trajectory-generator theories, StackedGenerator, base_trajectory::Trajectory, the seven
+critics, StackedScoringModel — against stand-ins (oracle/ref_shims/) for the third-party headers they include (Eigen,
+PCL, tf2, rclcpp, pluginlib: not installed in this image) and the reference's vendored nanoflann as the kd-tree. These
+tests run that code and the restatement (oracle/lp_oracle.cpp, libm math mode) on identical inputs and require IDENTICAL
+bits for everything the reference exposes: the trajectory list, velocities, time_delta, number of poses, every pose,
+cuboid vertex and AABB, every critic's return value, the accumulated cost and the selected trajectory.
+
+What this pins: the reference's control flow, operand types (float vs double), evaluation order, early returns, loop
+bounds, tie-breaks. What it cannot pin: the arithmetic INSIDE Eigen / PCL / FLANN / tf2, which both sides take from SURVEY.md
+Appendix A.
+"""
+import copy
+import math
+
+import numpy as np
+import pytest
+
+from dddmr_navigation_b200 import PlannerConfig, make_query, synth
+from dddmr_navigation_b200.config import (DD_ROTATE_INPLACE_DEFAULT, DD_SIMPLE_DEFAULT, OMNI_SIMPLE_CRITICS,
+                                          OMNI_SIMPLE_DEFAULT, ROTATE_CRITICS)
+from oracle import lporacle as O
+from tests.helpers import assert_same_array
+
+pytestmark = pytest.mark.skipif(not O.have_reference_sources(), reason="oracle/_ref/liblpref.so not built (needs /root/reference)")
+
+FIELDS = ("vel", "num_steps", "time_delta", "cost", "critic_scores")
+
+
+def _compare(cfg, cloud, plan, pose, twist, max_speed=-1.0, hdev=0.0, pose_trajs=6, tag=""):
+    ref = O.ReferencePlanner(cfg)
+    ora = O.OraclePlanner(cfg, O.MATH_LIBM, O.INDEX_BRUTE if len(cloud) < 30_000 else O.INDEX_GRID)
+    q = make_query(pose, twist, max_speed, hdev)
+    for p in (ref, ora):
+        p.set_cloud(cloud)
+        p.set_plan(plan)
+    r_r, r_o = ref.plan(q), ora.plan(q)
+    for f in ("best_id", "n_traj", "n_collided", "n_poses", "best_cost", "xv", "yv", "thetav"):
+        assert getattr(r_r, f) == getattr(r_o, f), (tag, f, getattr(r_r, f), getattr(r_o, f))
+    t_r, t_o = ref.read_trajectories(), ora.read_trajectories()
+    for k in FIELDS:
+        assert_same_array(t_o[k], t_r[k], f"{tag} {k}")
+    n = r_o.n_traj
+    ids = sorted(set(int(i) for i in np.linspace(0, max(n - 1, 0), pose_trajs))) if n else []
+    for tid in ids:
+        steps = int(t_o["num_steps"][tid])
+        p_r, p_o = ref.read_poses(tid, steps), ora.read_poses(tid, steps)
+        for k in ("pose", "pcl_pose", "cuboid", "aabb"):
+            assert_same_array(p_o[k], p_r[k], f"{tag} traj {tid} {k}")
+    return r_o
+
+
+def test_playground_scenario():
+    sc = synth.playground()
+    r = _compare(sc.config, sc.cloud, sc.plan, sc.pose, sc.twist, pose_trajs=55, tag="playground")
+    assert r.best_id == 51 and r.n_collided == 17
+
+
+def test_c1_ramp_pitched_pose():
+    sc = synth.c1_ramp(n_points=20_000)
+    r = _compare(sc.config, sc.cloud, sc.plan, sc.pose, sc.twist, pose_trajs=12, tag="c1")
+    assert r.n_collided > 0 and r.best_id >= 0
+
+
+def test_big_cuboid_on_the_c2_scene():
+    sc = synth.c2_dense(n_points=100_000, samples=(12.0, 14.0))
+    r = _compare(sc.config, sc.cloud, sc.plan, sc.pose, sc.twist, pose_trajs=8, tag="c2")
+    assert 0 < r.n_collided < r.n_traj
+
+
+def test_omni_and_rotate_theories():
+    cloud = synth.small_scene(9, n_points=4000)
+    plan = np.array([[-0.3 + 0.1 * i, 0.0, 0.0, 0, 0, 0, 1.0] for i in range(30)])
+    cfg = PlannerConfig(generator=copy.deepcopy(OMNI_SIMPLE_DEFAULT), critics=copy.deepcopy(OMNI_SIMPLE_CRITICS))
+    r = _compare(cfg, cloud, plan, [0.1, -0.1, 0, *synth.quat_from_rpy(0, 0, 0.4)], [0.3, 0.1, 0.1], tag="omni")
+    assert r.n_traj > 100
+    cfg = PlannerConfig(generator=copy.deepcopy(DD_ROTATE_INPLACE_DEFAULT), critics=copy.deepcopy(ROTATE_CRITICS))
+    for hd in (0.5, -0.5):
+        r = _compare(cfg, synth.small_scene(13, n_points=2000, extent=1.5), plan, [0, 0, 0, 0, 0, 0, 1], [0, 0, 0], hdev=hd, tag="rotate")
+        assert r.n_traj == 2 and r.n_poses == 2 * 126
+
+
+def test_edge_cases_small_clouds_and_short_plans():
+    cfg = PlannerConfig(generator=dict(copy.deepcopy(DD_SIMPLE_DEFAULT), linear_x_sample=4.0, angular_z_sample=5.0))
+    four = synth.to_xyzi(np.array([[0.5, 0, 0.2]] * 4, np.float32))
+    five = synth.to_xyzi(np.array([[0.5, 0, 0.2]] * 5, np.float32))
+    line = np.array([[-0.3 + 0.1 * i, 0.0, 0.0, 0, 0, 0, 1.0] for i in range(30)])
+    for ci, cloud in enumerate((four, five)):
+        for pi, plan in enumerate((line, line[:2], np.zeros((0, 7)))):
+            _compare(cfg, cloud, plan, [0, 0, 0, 0, 0, 0, 1], [0.3, 0, 0.0], tag=f"edge {ci}/{pi}")
+
+
+@pytest.mark.parametrize("seed", range(48))
+def test_randomised_scenes(seed):
+    """The scene generator of tests/test_fuzz_gpu.py (random theory, critic stack, cuboid, tilted pose, plan length), minus
+    the non-finite cloud points (the kd-tree stand-in, like FLANN, is not defined on NaN coordinates)."""
+    from tests.test_fuzz_gpu import _scene
+    cfg, cloud, plan, pose, twist, max_speed, hdev = _scene(seed)
+    cloud = cloud[np.isfinite(cloud[:, :3]).all(axis=1)]
+    _compare(cfg, cloud, plan, pose, twist, max_speed, hdev, pose_trajs=4, tag=f"fuzz {seed}")
