@@ -100,3 +100,54 @@ def test_randomised_scenes(seed):
     cfg, cloud, plan, pose, twist, max_speed, hdev = _scene(seed)
     cloud = cloud[np.isfinite(cloud[:, :3]).all(axis=1)]
     _compare(cfg, cloud, plan, pose, twist, max_speed, hdev, pose_trajs=4, tag=f"fuzz {seed}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["playground", "c1", "c2_small", "omni", "fuzz3", "fuzz8", "fuzz17", "fuzz30"])
+def test_gpu_against_the_reference_sources(case):
+    """The sm_100a path against the reference's own C++ directly (north_star bar): identical trajectory list, pose
+    counts, collision outcomes and selected id; per-critic scores and cost within 1e-4 relative (the reference calls
+    glibc's double sin/cos/asin/atan2, the device lp_math.h's, <= 1 ulp apart)."""
+    from dddmr_navigation_b200 import LocalPlanner
+    hdev, ms = 0.0, -1.0
+    if case == "playground":
+        sc = synth.playground(); cfg, cloud, plan, pose, twist = sc.config, sc.cloud, sc.plan, sc.pose, sc.twist
+    elif case == "c1":
+        sc = synth.c1_ramp(n_points=50_000); cfg, cloud, plan, pose, twist = sc.config, sc.cloud, sc.plan, sc.pose, sc.twist
+    elif case == "c2_small":
+        sc = synth.c2_dense(n_points=200_000, samples=(16.0, 18.0)); cfg, cloud, plan, pose, twist = sc.config, sc.cloud, sc.plan, sc.pose, sc.twist
+    elif case == "omni":
+        cfg = PlannerConfig(generator=copy.deepcopy(OMNI_SIMPLE_DEFAULT), critics=copy.deepcopy(OMNI_SIMPLE_CRITICS))
+        cloud = synth.small_scene(9, n_points=4000)
+        plan = np.array([[-0.3 + 0.1 * i, 0.0, 0.0, 0, 0, 0, 1.0] for i in range(30)])
+        pose, twist = [0.1, -0.1, 0, *synth.quat_from_rpy(0, 0, 0.4)], [0.3, 0.1, 0.1]
+    else:
+        from tests.test_fuzz_gpu import _scene
+        cfg, cloud, plan, pose, twist, ms, hdev = _scene(int(case[4:]))
+        cloud = cloud[np.isfinite(cloud[:, :3]).all(axis=1)]
+    gpu, ref = LocalPlanner(cfg), O.ReferencePlanner(cfg)
+    q = make_query(pose, twist, ms, hdev)
+    for p in (gpu, ref):
+        p.set_cloud(cloud)
+        p.set_plan(plan)
+    r_g, r_r = gpu.plan(q), ref.plan(q)
+    assert (r_g.best_id, r_g.n_traj, r_g.n_collided, r_g.n_poses) == (r_r.best_id, r_r.n_traj, r_r.n_collided, r_r.n_poses)
+    t_g, t_r = gpu.read_trajectories(), ref.read_trajectories()
+    assert_same_array(t_g["num_steps"], t_r["num_steps"], "num_steps")
+    assert_same_array(t_g["vel"], t_r["vel"], "vel")
+    assert_same_array(t_g["time_delta"], t_r["time_delta"], "time_delta")
+    for k in ("cost", "critic_scores"):
+        a, b = t_g[k], t_r[k]
+        assert np.array_equal(np.isnan(a), np.isnan(b)), k
+        m = ~np.isnan(a)
+        assert np.array_equal(a[m] < 0, b[m] < 0), k  # rejections (collision -1, pure pursuit -4) are discrete
+        assert np.all(np.abs(a[m] - b[m]) <= 1e-4 * np.maximum(np.abs(b[m]), 1e-12)), k  # 1e-4 relative (BASELINE.json north_star)
+    if r_r.best_id >= 0:
+        assert abs(r_g.best_cost - r_r.best_cost) <= 1e-4 * abs(r_r.best_cost)
+    n = r_r.n_traj
+    for tid in sorted(set(int(i) for i in np.linspace(0, max(n - 1, 0), 4))) if n else []:
+        steps = int(t_r["num_steps"][tid])
+        p_g, p_r = gpu.read_poses(tid, steps), ref.read_poses(tid, steps)
+        for k in ("pcl_pose", "cuboid", "aabb"):   # float outputs of double arithmetic: equal unless a 1-ulp libm difference straddles a float rounding
+            assert np.allclose(p_g[k], p_r[k], rtol=1e-6, atol=1e-6), (tid, k)
+        assert np.allclose(p_g["pose"], p_r["pose"], rtol=1e-12, atol=1e-12), tid
