@@ -217,6 +217,7 @@ _LPREF_SYMS = {
     "lpref_plan": (C.c_int, [_P, C.POINTER(abi.Query), C.POINTER(abi.Result)]),
     "lpref_read_trajectories": (C.c_int, [_P, C.POINTER(abi.TrajView)]),
     "lpref_read_poses": (C.c_int, [_P, C.c_int32, C.POINTER(abi.PoseView)]),
+    "lpref_path_blocked": (C.c_int, [_P, C.c_size_t, C.c_size_t, C.POINTER(C.c_float), C.c_size_t, C.c_double, C.POINTER(C.c_int32)]),
 }
 _lpref = None
 
@@ -290,3 +291,16 @@ class ReferencePlanner:
                          d["cuboid"].ctypes.data_as(C.POINTER(C.c_float)), d["aabb"].ctypes.data_as(C.POINTER(C.c_float)), None, None)
         assert self.lib.lpref_read_poses(self.h, traj_id, C.byref(v)) == 0
         return d
+
+
+def reference_path_blocked_opinion(cloud, pcl_xyzi, check_radius: float) -> int:
+    """perception_3d::PathBlockedStrategy::selfMark — the reference's own code — on (cloud, pcl_prune_plan_): its opinion
+    (0 PASS, 1 PATH_BLOCKED_WAIT)."""
+    lib = load_lpref()
+    cloud = np.ascontiguousarray(cloud, np.float32)
+    pcl = np.ascontiguousarray(pcl_xyzi, np.float32).reshape(-1, 4)
+    out = C.c_int32(-1)
+    rc = lib.lpref_path_blocked(cloud.ctypes.data_as(_P), cloud.shape[0], cloud.shape[1] * 4, pcl.ctypes.data_as(C.POINTER(C.c_float)),
+                                pcl.shape[0], float(check_radius), C.byref(out))
+    assert rc == 0, rc
+    return out.value

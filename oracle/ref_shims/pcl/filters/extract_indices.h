@@ -1,0 +1,1 @@
+#include "../../lpref_pcl.hpp"

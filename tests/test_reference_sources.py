@@ -151,3 +151,35 @@ def test_gpu_against_the_reference_sources(case):
         for k in ("pcl_pose", "cuboid", "aabb"):   # float outputs of double arithmetic: equal unless a 1-ulp libm difference straddles a float rounding
             assert np.allclose(p_g[k], p_r[k], rtol=1e-6, atol=1e-6), (tid, k)
         assert np.allclose(p_g["pose"], p_r["pose"], rtol=1e-12, atol=1e-12), tid
+
+
+def test_path_blocked_strategy_opinion_matches_the_reference_plugin():
+    """the restated selfMark against the reference's own PathBlockedStrategy plugin."""
+    rng = np.random.default_rng(7)
+    sc = synth.c1_ramp(n_points=20_000)
+    ora = O.OraclePlanner(sc.config, O.MATH_SHARED, O.INDEX_BRUTE)
+    seen = set()
+    for trial in range(24):
+        n = int(rng.choice([3, 4, 5, 6, 40, 400, 20_000]))
+        cloud = sc.cloud[rng.choice(len(sc.cloud), size=n, replace=False)]
+        info, poses, pcl = O.prune_plan(sc.plan, sc.pose[:3], float(rng.uniform(0.2, 3.0)), float(rng.uniform(0.0, 1.0)))
+        radius = float(rng.choice([0.05, 0.3, 0.8, 2.0]))
+        if trial % 2 == 0 and n > 5:  # drop one cloud point somewhere around a random (forward or backward) plan point
+            k = int(rng.integers(0, len(pcl)))
+            d = rng.normal(size=3)
+            cloud = cloud.copy()
+            cloud[0, :3] = pcl[k, :3] + d / np.linalg.norm(d) * rng.uniform(0.0, 2.0 * radius)
+        ora.set_cloud(cloud)
+        b = ora.path_blocked(pcl, radius)
+        assert b.opinion == O.reference_path_blocked_opinion(cloud, pcl, radius), (trial, n, radius, b.as_dict())
+        seen.add(b.opinion)
+    assert seen == {0, 1}
+    # <= 5 cloud points or an empty prune plan: PASS whatever the geometry (path_blocked_strategy.cpp:62-64)
+    five = np.repeat(np.array([[pcl[-1, 0], pcl[-1, 1], pcl[-1, 2]]], np.float32), 5, 0)
+    assert O.reference_path_blocked_opinion(synth.to_xyzi(five), pcl, 1.0) == 0
+    ora.set_cloud(synth.to_xyzi(five))
+    assert ora.path_blocked(pcl, 1.0).opinion == 0
+    six = np.repeat(five[:1], 6, 0)
+    assert O.reference_path_blocked_opinion(synth.to_xyzi(six), pcl, 1.0) == 1
+    ora.set_cloud(synth.to_xyzi(six))
+    assert ora.path_blocked(pcl, 1.0).opinion == 1
