@@ -318,13 +318,14 @@ __device__ __forceinline__ bool traj_precheck(const Consts& C, const RobotIn& q,
 }
 
 // Per-(robot, chunk) aggregate of the decoupled look-back that orders the trajectory list across CTAs.
-struct PrepAgg {
+struct alignas(16) PrepAgg {  // 32 bytes: read back with two 16-byte volatile loads
   int keep, valid;     // samples kept by the motor constraint / trajectories that passed the prologue
   int cnt_lo, cnt_hi;  // valid samples below the shard's first / end sample
   long long poses;     // sum of num_steps inside the shard
   int err;
   unsigned flag;       // == launch epoch once the fields above are visible
 };
+static_assert(sizeof(PrepAgg) == 32, "PrepAgg layout");
 
 #ifndef B200LP_PREP_THREADS
 #define B200LP_PREP_THREADS 256
@@ -508,12 +509,16 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
   long long pposes = 0;
   for (int c = tid; c < chunk; c += kPrepThreads) {
     const PrepAgg* a = my_aggs + c;
-    while (*(volatile const unsigned*)&a->flag != epoch) __nanosleep(20);
+    // the poll must be a volatile access: an empty loop around a plain intrinsic load has no side effect the compiler
+    // is obliged to keep
+    while (*(volatile const unsigned*)&a->flag != epoch) {}
     __threadfence();
-    pk += *(volatile const int*)&a->keep; pv += *(volatile const int*)&a->valid;
-    plo += *(volatile const int*)&a->cnt_lo; phi += *(volatile const int*)&a->cnt_hi;
-    pposes += *(volatile const long long*)&a->poses;
-    perr |= *(volatile const int*)&a->err;
+    const uint4 w0 = __ldcv(reinterpret_cast<const uint4*>(a));      // keep, valid, cnt_lo, cnt_hi
+    const uint4 w1 = __ldcv(reinterpret_cast<const uint4*>(a) + 1);  // poses (lo, hi), err, flag
+    pk += (int)w0.x; pv += (int)w0.y;
+    plo += (int)w0.z; phi += (int)w0.w;
+    pposes += (long long)(((unsigned long long)w1.y << 32) | (unsigned long long)w1.x);
+    perr |= (int)w1.z;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
