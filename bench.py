@@ -439,6 +439,16 @@ def main():
                          "sets would stream; the voxel-grid prune touches far fewer and re-reads them from L1/L2, so the "
                          "kernel is issue/latency-bound, not DRAM-bound — see profiles/ for dram bytes and pipe utilisation")}
 
+    gi = lp.grid_info()
+    n_cells = gi["dims"][0] * gi["dims"][1] * gi["dims"][2]
+    grid_bytes = n_pts * 48 + 4 * n_cells  # read the PointXYZI-stride input, write 16 B cell-sorted float4, offsets
+    grid_ms_e2e = e2e_stage["ms_grid_build"] / args.steps
+    roofline_grid = {"bound": "hbm", "achieved": grid_bytes / (grid_ms_e2e * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": grid_bytes / (grid_ms_e2e * 1e-3) / 1e9 / peak, "algorithmic_bytes": grid_bytes, "ms": grid_ms_e2e,
+                     "note": ("whole grid build of one set_cloud (bounds, histogram, 3-kernel scan, scatter, two summed-volume passes, "
+                              "two memsets and one host round trip for the grid dimensions); at this size it is launch/latency-bound, "
+                              "and it sits behind a PCIe upload ~8x longer")}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "strong" if mode == "shard" else "weak",
@@ -463,6 +473,7 @@ def main():
         "kernel_ms": {"prep_kernel": sum(prep_k_ms) / len(prep_k_ms), "plan_kernel": k_ms,
                       "argmin_kernel": sum(argmin_k_ms) / len(argmin_k_ms), "grid_build_total": grid_ms},
         "roofline": roofline,
+        "roofline_grid_build": roofline_grid,
         "result": {"best_id": int(r.best_id), "best_cost": float(r.best_cost), "n_collided": int(r.n_collided)},
     }
 

@@ -559,9 +559,6 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
   // ---- forward simulation of this thread's trajectory (computeNewPositions, dd_simple…cpp:457-464,
   // omni_simple…cpp:498-505): x,y,th in the robot frame after every step, then the pure-pursuit terms
   // of the last pose ----
-#ifdef B200LP_DBG_NOROLL
-  roll = false;
-#endif
   if (roll) {
     float x = 0.f, y = 0.f, th = 0.f;
     const double wdt = (double)v2 * dt;  // loop invariant of th' = (float)(th + w*dt)
