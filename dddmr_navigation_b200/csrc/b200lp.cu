@@ -81,7 +81,10 @@ struct b200lp_ctx {
   size_t raw_stride = 0;
   DevBuf<char> d_raw;
   DevBuf<float4> d_pts;
-  DevBuf<uint32_t> d_cell_start, d_fill, d_keys, d_block_sums, d_sat;
+  DevBuf<uint32_t> d_cell_start, d_fill, d_block_sums, d_sat;
+  DevBuf<float4> d_packed;  // the raw cloud as 16-byte records (x, y, z, original index)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t chunk_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   DevBuf<BoundsDev> d_bounds;
   DevBuf<uint32_t> d_total;
   PinBuf<BoundsDev> h_bounds;
@@ -192,7 +195,16 @@ int traj_cap(const b200lp_params& P) {
   return (int)std::min<long long>(n, 1ll << 30);
 }
 
-int build_grid(b200lp_ctx* ctx, size_t n, size_t stride) {
+#ifndef B200LP_UPLOAD_CHUNKS
+#define B200LP_UPLOAD_CHUNKS 4
+#endif
+constexpr int kUploadChunks = B200LP_UPLOAD_CHUNKS;  // <= 8 (chunk_ev)
+
+// Brings the cloud to the device and builds the voxel grid + summed-volume table.
+//   src == nullptr : the raw cloud is already in d_raw (or n == 0)
+//   otherwise      : `src` (host, or device when on_device) is copied in kUploadChunks pieces on the copy stream while
+//                    bounds_pack_kernel works through the pieces that have arrived on the main stream.
+int build_grid(b200lp_ctx* ctx, const void* src, size_t n, size_t stride, bool on_device) {
   const int sms = sm_count_of(ctx->device);
   GridDev& g = ctx->grid;
   g.n_raw = (uint32_t)n;
@@ -208,6 +220,7 @@ int build_grid(b200lp_ctx* ctx, size_t n, size_t stride) {
   CK(ctx->d_bounds.reserve(1));
   CK(ctx->h_bounds.reserve(1));
   CK(ctx->d_total.reserve(1));
+  CK(ctx->d_packed.reserve(std::max<size_t>(n, 1)));
   BoundsDev init;
   for (int a = 0; a < 3; ++a) {
     init.mn[a] = 0xffffffffu;
@@ -216,13 +229,29 @@ int build_grid(b200lp_ctx* ctx, size_t n, size_t stride) {
   init.n_finite = 0;
   init.pad = 0;
   *ctx->h_bounds.p = init;
+  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
   CK(cudaMemcpyAsync(ctx->d_bounds.p, ctx->h_bounds.p, sizeof(BoundsDev), cudaMemcpyHostToDevice, ctx->stream));
   if (n) {
-    bounds_kernel<<<grid_blocks(n, 256, sms), 256, 0, ctx->stream>>>(ctx->d_raw.p, n, stride, ctx->d_bounds.p);
-    ++ctx->launches;
+    const int chunks = (src && n >= (size_t)kUploadChunks * 65536) ? kUploadChunks : 1;
+    if (src) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[0], 0));  // the copy may not overtake earlier work on d_raw
+    for (int c = 0; c < chunks; ++c) {
+      const size_t i0 = n * c / chunks, i1 = n * (c + 1) / chunks;
+      if (src) {
+        CK(cudaMemcpyAsync(ctx->d_raw.p + i0 * stride, (const char*)src + i0 * stride, (i1 - i0) * stride,
+                           on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[c], 0));
+      }
+      if (c == chunks - 1) CK(cudaEventRecord(ctx->ev[1], ctx->stream));  // everything has arrived
+      bounds_pack_kernel<<<grid_blocks(i1 - i0, 256, sms), 256, 0, ctx->stream>>>(ctx->d_raw.p, i0, i1, stride, ctx->d_packed.p,
+                                                                                  ctx->d_bounds.p);
+      ++ctx->launches;
+    }
+  } else {
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   }
   CK(cudaMemcpyAsync(ctx->h_bounds.p, ctx->d_bounds.p, sizeof(BoundsDev), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));  // the host needs the bounds to size the grid; the caller's buffer is free from here on
   const BoundsDev b = *ctx->h_bounds.p;
   size_t n_cells = 1;
   if (b.n_finite) {
@@ -260,7 +289,6 @@ int build_grid(b200lp_ctx* ctx, size_t n, size_t stride) {
   CK(ctx->d_cell_start.reserve(n_cells + 1));
   CK(ctx->d_fill.reserve(n_cells + 1));
   CK(ctx->d_block_sums.reserve(nb));
-  CK(ctx->d_keys.reserve(n));
   CK(ctx->d_pts.reserve(std::max<size_t>(g.n_kept, 1)));
   const size_t n_sat = ((size_t)g.nx + 1) * ((size_t)g.ny + 1) * ((size_t)g.nz + 1);
   CK(ctx->d_sat.reserve(n_sat));
@@ -270,15 +298,12 @@ int build_grid(b200lp_ctx* ctx, size_t n, size_t stride) {
   g.cell_start = ctx->d_cell_start.p;
   g.sat = ctx->d_sat.p;
   if (g.n_kept) {
-    hist_kernel<<<grid_blocks(n, 256, sms), 256, 0, ctx->stream>>>(ctx->d_raw.p, n, stride, g, ctx->d_cell_start.p,
-                                                                   ctx->d_keys.p);
+    hist_kernel<<<grid_blocks(n, 256, sms), 256, 0, ctx->stream>>>(ctx->d_packed.p, n, g, ctx->d_cell_start.p);
     scan_block_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_cell_start.p, n_cells, ctx->d_block_sums.p);
     scan_sums_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_block_sums.p, nb, ctx->d_total.p);
-    scan_add_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_cell_start.p, n_cells, ctx->d_block_sums.p, ctx->d_total.p);
-    CK(cudaMemcpyAsync(ctx->d_fill.p, ctx->d_cell_start.p, n_cells * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
-                       ctx->stream));
-    scatter_kernel<<<grid_blocks(n, 256, sms), 256, 0, ctx->stream>>>(ctx->d_raw.p, n, stride, ctx->d_keys.p,
-                                                                      ctx->d_fill.p, ctx->d_pts.p);
+    scan_add_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_cell_start.p, n_cells, ctx->d_block_sums.p, ctx->d_total.p,
+                                                 ctx->d_fill.p);
+    scatter_kernel<<<grid_blocks(n, 256, sms), 256, 0, ctx->stream>>>(ctx->d_packed.p, n, g, ctx->d_fill.p, ctx->d_pts.p);
     const size_t ny_threads = ((size_t)g.nx + 1) * (size_t)g.nz, nz_threads = ((size_t)g.nx + 1) * ((size_t)g.ny + 1);
     sat_y_kernel<<<(unsigned)((ny_threads * 32 + 255) / 256), 256, 0, ctx->stream>>>(g, ctx->d_sat.p);
     sat_z_kernel<<<(unsigned)((nz_threads + 255) / 256), 256, 0, ctx->stream>>>(g, ctx->d_sat.p);
@@ -349,7 +374,7 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
     if (ctx->plan_ctas_per_sm < 1) return ctx->fail(B200LP_E_CUDA, "plan_kernel does not fit on an SM");
   }
   if (!ctx->have_cloud) {  // no cloud yet: an empty one (collision critics return 0.0, size() < 5)
-    int rc = build_grid(ctx, 0, 16);
+    int rc = build_grid(ctx, nullptr, 0, 16, false);
     if (rc) return rc;
   }
   ctx->n_robots = n_robots;
@@ -466,8 +491,11 @@ int b200lp_create(b200lp_ctx** out, int device, const b200lp_limits* limits, con
   };
   if ((e = cudaSetDevice(device)) != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+  if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
   for (auto& ev : ctx->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+  for (auto& ev : ctx->chunk_ev)
+    if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
   ctx->C.lim = *limits;
   ctx->C.par = *params;
   memcpy(ctx->C.cuboid, cuboid_xyz, sizeof(ctx->C.cuboid));
@@ -489,7 +517,7 @@ void b200lp_destroy(b200lp_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   ctx->d_raw.release(); ctx->d_pts.release(); ctx->d_cell_start.release(); ctx->d_fill.release();
-  ctx->d_keys.release(); ctx->d_block_sums.release(); ctx->d_sat.release(); ctx->d_bounds.release(); ctx->d_total.release();
+  ctx->d_packed.release(); ctx->d_block_sums.release(); ctx->d_sat.release(); ctx->d_bounds.release(); ctx->d_total.release();
   ctx->h_bounds.release(); ctx->d_robots.release(); ctx->d_meta.release(); ctx->d_plan7.release();
   ctx->d_plan_pts.release(); ctx->d_rec_vel.release(); ctx->d_rec_steps.release(); ctx->d_rec_sample.release();
   ctx->d_first_hit.release(); ctx->d_rec_dt.release(); ctx->d_cost.release(); ctx->d_scores.release();
@@ -498,6 +526,9 @@ void b200lp_destroy(b200lp_ctx* ctx) {
   ctx->h_count.release();
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
+  for (auto& ev : ctx->chunk_ev)
+    if (ev) cudaEventDestroy(ev);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -509,13 +540,12 @@ static int set_cloud_common(b200lp_ctx* ctx, const void* pts, size_t n, size_t s
   CK(cudaSetDevice(ctx->device));
   CK(ctx->d_raw.reserve(std::max<size_t>(n * stride, 16)));
   ctx->raw_stride = stride;
-  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-  if (n) CK(cudaMemcpyAsync(ctx->d_raw.p, pts, n * stride, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-  int rc = build_grid(ctx, n, stride);
+  int rc = build_grid(ctx, n ? pts : nullptr, n, stride, on_device);  // records ev[0] (start) and ev[1] (cloud arrived)
   if (rc) return rc;
   CK(cudaEventRecord(ctx->ev[2], ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  // ms_upload: start -> last chunk on the device (bounds_pack_kernel of the earlier chunks runs underneath);
+  // ms_grid_build: everything after that, i.e. what the grid adds to the upload
   cudaEventElapsedTime(&ctx->ms_upload, ctx->ev[0], ctx->ev[1]);
   cudaEventElapsedTime(&ctx->ms_grid, ctx->ev[1], ctx->ev[2]);
   ctx->ms_plan = ctx->ms_readback = 0.f;

@@ -46,13 +46,17 @@ __device__ __forceinline__ bool finite3(float3 v) {
   return isfinite(v.x) && isfinite(v.y) && isfinite(v.z);
 }
 
-__global__ void __launch_bounds__(256) bounds_kernel(const char* __restrict__ raw, size_t n, size_t stride,
-                                                     BoundsDev* __restrict__ b) {
+// Pass 1 over points [i0, i1) of the raw cloud (launched per upload chunk, so it overlaps the rest of the upload):
+// pack x,y,z + the original index into 16-byte float4 records — every later pass reads these, fully coalesced, instead
+// of the 32-byte-stride PointXYZI input — and reduce the bounds of the finite points.
+__global__ void __launch_bounds__(256) bounds_pack_kernel(const char* __restrict__ raw, size_t i0, size_t i1, size_t stride,
+                                                          float4* __restrict__ packed, BoundsDev* __restrict__ b) {
   float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
   float mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
   unsigned cnt = 0;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+  for (size_t i = i0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (size_t)gridDim.x * blockDim.x) {
     const float3 v = load_xyz(raw, i, stride);
+    packed[i] = make_float4(v.x, v.y, v.z, __uint_as_float((uint32_t)i));
     if (finite3(v)) {
       ++cnt;
       mn[0] = fminf(mn[0], v.x); mx[0] = fmaxf(mx[0], v.x);
@@ -104,17 +108,14 @@ __device__ __forceinline__ uint32_t cell_key(const GridDev& g, float3 v) {
   return (uint32_t)(((size_t)cz * g.ny + cy) * (size_t)g.nx + cx);
 }
 
-// histogram of points per cell; remembers each point's key so the scatter pass does not recompute it
-__global__ void __launch_bounds__(256) hist_kernel(const char* __restrict__ raw, size_t n, size_t stride, GridDev g,
-                                                   uint32_t* __restrict__ counts, uint32_t* __restrict__ keys) {
+// histogram of points per cell (the key is three subtract-multiply-floors: cheaper to recompute in the scatter pass than
+// to store and re-read)
+__global__ void __launch_bounds__(256) hist_kernel(const float4* __restrict__ packed, size_t n, GridDev g,
+                                                   uint32_t* __restrict__ counts) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const float3 v = load_xyz(raw, i, stride);
-    uint32_t key = 0xffffffffu;
-    if (finite3(v)) {
-      key = cell_key(g, v);
-      atomicAdd(counts + key, 1u);
-    }
-    keys[i] = key;
+    const float4 p = __ldg(packed + i);
+    const float3 v = make_float3(p.x, p.y, p.z);
+    if (finite3(v)) atomicAdd(counts + cell_key(g, v), 1u);
   }
 }
 
@@ -180,28 +181,32 @@ __global__ void __launch_bounds__(1024) scan_sums_kernel(uint32_t* __restrict__ 
   if (threadIdx.x == 0) *total_out = s_carry;
 }
 
+// adds the block offsets and leaves a second copy of the offsets in `fill` (the scatter pass's slot counters)
 __global__ void __launch_bounds__(256) scan_add_kernel(uint32_t* __restrict__ data, size_t n,
                                                        const uint32_t* __restrict__ block_sums,
-                                                       const uint32_t* __restrict__ total) {
+                                                       const uint32_t* __restrict__ total, uint32_t* __restrict__ fill) {
   const uint32_t off = block_sums[blockIdx.x];
   const size_t base = (size_t)blockIdx.x * kScanItems + (size_t)threadIdx.x * 8;
 #pragma unroll
   for (int k = 0; k < 8; ++k)
-    if (base + k < n) data[base + k] += off;
+    if (base + k < n) {
+      const uint32_t v = data[base + k] + off;
+      data[base + k] = v;
+      fill[base + k] = v;
+    }
   if (blockIdx.x == 0 && threadIdx.x == 0) data[n] = *total;  // cell_start[n_cells]
 }
 
 // counting-sort scatter. `fill` holds a copy of the exclusive offsets and is consumed by atomics, so the
 // order of points inside a cell is arbitrary; every consumer is an any-hit or a count.
-__global__ void __launch_bounds__(256) scatter_kernel(const char* __restrict__ raw, size_t n, size_t stride,
-                                                      const uint32_t* __restrict__ keys, uint32_t* __restrict__ fill,
-                                                      float4* __restrict__ out) {
+__global__ void __launch_bounds__(256) scatter_kernel(const float4* __restrict__ packed, size_t n, GridDev g,
+                                                      uint32_t* __restrict__ fill, float4* __restrict__ out) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const uint32_t key = keys[i];
-    if (key == 0xffffffffu) continue;
-    const float3 v = load_xyz(raw, i, stride);
-    const uint32_t slot = atomicAdd(fill + key, 1u);
-    out[slot] = make_float4(v.x, v.y, v.z, __uint_as_float((uint32_t)i));
+    const float4 p = __ldg(packed + i);
+    const float3 v = make_float3(p.x, p.y, p.z);
+    if (!finite3(v)) continue;
+    const uint32_t slot = atomicAdd(fill + cell_key(g, v), 1u);
+    out[slot] = p;
   }
 }
 
