@@ -71,6 +71,8 @@ struct b200lp_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t cev[3] = {nullptr, nullptr, nullptr};  // set_cloud: start, cloud arrived, grid built
+  bool cloud_timing_pending = false;
   std::string err;
   Consts C{};
   b200lp_grid_config gcfg{};
@@ -229,11 +231,11 @@ int build_grid(b200lp_ctx* ctx, const void* src, size_t n, size_t stride, bool o
   init.n_finite = 0;
   init.pad = 0;
   *ctx->h_bounds.p = init;
-  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  CK(cudaEventRecord(ctx->cev[0], ctx->stream));
   CK(cudaMemcpyAsync(ctx->d_bounds.p, ctx->h_bounds.p, sizeof(BoundsDev), cudaMemcpyHostToDevice, ctx->stream));
   if (n) {
     const int chunks = (src && n >= (size_t)kUploadChunks * 65536) ? kUploadChunks : 1;
-    if (src) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[0], 0));  // the copy may not overtake earlier work on d_raw
+    if (src) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->cev[0], 0));  // the copy may not overtake earlier work on d_raw
     for (int c = 0; c < chunks; ++c) {
       const size_t i0 = n * c / chunks, i1 = n * (c + 1) / chunks;
       if (src) {
@@ -242,13 +244,13 @@ int build_grid(b200lp_ctx* ctx, const void* src, size_t n, size_t stride, bool o
         CK(cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream));
         CK(cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[c], 0));
       }
-      if (c == chunks - 1) CK(cudaEventRecord(ctx->ev[1], ctx->stream));  // everything has arrived
+      if (c == chunks - 1) CK(cudaEventRecord(ctx->cev[1], ctx->stream));  // everything has arrived
       bounds_pack_kernel<<<grid_blocks(i1 - i0, 256, sms), 256, 0, ctx->stream>>>(ctx->d_raw.p, i0, i1, stride, ctx->d_packed.p,
                                                                                   ctx->d_bounds.p);
       ++ctx->launches;
     }
   } else {
-    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CK(cudaEventRecord(ctx->cev[1], ctx->stream));
   }
   CK(cudaMemcpyAsync(ctx->h_bounds.p, ctx->d_bounds.p, sizeof(BoundsDev), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));  // the host needs the bounds to size the grid; the caller's buffer is free from here on
@@ -312,6 +314,16 @@ int build_grid(b200lp_ctx* ctx, const void* src, size_t n, size_t stride, bool o
   CK(cudaGetLastError());
   ctx->have_cloud = true;
   return B200LP_OK;
+}
+
+// set_cloud returns as soon as the host buffer has been consumed; its device timeline is read back lazily
+void resolve_cloud_timing(b200lp_ctx* ctx) {
+  if (!ctx->cloud_timing_pending) return;
+  if (cudaEventSynchronize(ctx->cev[2]) == cudaSuccess) {
+    cudaEventElapsedTime(&ctx->ms_upload, ctx->cev[0], ctx->cev[1]);
+    cudaEventElapsedTime(&ctx->ms_grid, ctx->cev[1], ctx->cev[2]);
+  }
+  ctx->cloud_timing_pending = false;
 }
 
 int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_result* outs, bool plan_resident = false) {
@@ -421,7 +433,7 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
     outs[i] = ctx->h_results.p[i];
   }
   ctx->have_cycle = true;
-  cudaEventElapsedTime(&ctx->ms_upload, ctx->ev[0], ctx->ev[1]);
+  resolve_cloud_timing(ctx);  // the stream is idle: the set_cloud events have completed
   cudaEventElapsedTime(&ctx->ms_plan, ctx->ev[1], ctx->ev[2]);
   cudaEventElapsedTime(&ctx->ms_readback, ctx->ev[2], ctx->ev[3]);
   cudaEventElapsedTime(&ctx->ms_k_prep, ctx->ev[1], ctx->ev[4]);
@@ -496,6 +508,8 @@ int b200lp_create(b200lp_ctx** out, int device, const b200lp_limits* limits, con
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
   for (auto& ev : ctx->chunk_ev)
     if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+  for (auto& ev : ctx->cev)
+    if ((e = cudaEventCreate(&ev)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
   ctx->C.lim = *limits;
   ctx->C.par = *params;
   memcpy(ctx->C.cuboid, cuboid_xyz, sizeof(ctx->C.cuboid));
@@ -528,6 +542,8 @@ void b200lp_destroy(b200lp_ctx* ctx) {
     if (ev) cudaEventDestroy(ev);
   for (auto& ev : ctx->chunk_ev)
     if (ev) cudaEventDestroy(ev);
+  for (auto& ev : ctx->cev)
+    if (ev) cudaEventDestroy(ev);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -540,15 +556,16 @@ static int set_cloud_common(b200lp_ctx* ctx, const void* pts, size_t n, size_t s
   CK(cudaSetDevice(ctx->device));
   CK(ctx->d_raw.reserve(std::max<size_t>(n * stride, 16)));
   ctx->raw_stride = stride;
-  int rc = build_grid(ctx, n ? pts : nullptr, n, stride, on_device);  // records ev[0] (start) and ev[1] (cloud arrived)
+  ctx->cloud_timing_pending = false;
+  int rc = build_grid(ctx, n ? pts : nullptr, n, stride, on_device);  // records cev[0] (start) and cev[1] (cloud arrived)
   if (rc) return rc;
-  CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  // ms_upload: start -> last chunk on the device (bounds_pack_kernel of the earlier chunks runs underneath);
-  // ms_grid_build: everything after that, i.e. what the grid adds to the upload
-  cudaEventElapsedTime(&ctx->ms_upload, ctx->ev[0], ctx->ev[1]);
-  cudaEventElapsedTime(&ctx->ms_grid, ctx->ev[1], ctx->ev[2]);
-  ctx->ms_plan = ctx->ms_readback = 0.f;
+  CK(cudaEventRecord(ctx->cev[2], ctx->stream));
+  // No synchronisation here: the caller's buffer was consumed before build_grid's host round trip for the bounds, and
+  // the histogram / scan / scatter / summed-volume kernels still in flight are ordered before everything later on this
+  // stream. ms_upload (start -> last piece on the device, bounds_pack_kernel of the earlier pieces underneath) and
+  // ms_grid_build (what the grid adds after that) are read back when somebody asks (b200lp_last_timing) or the next
+  // cycle has drained the stream anyway.
+  ctx->cloud_timing_pending = true;
   ctx->have_cycle = false;
   return B200LP_OK;
 }
@@ -820,6 +837,7 @@ int b200lp_count_radius(b200lp_ctx* ctx, int64_t* sum_n_r1, int64_t* n_poses) {
 int b200lp_last_timing(const b200lp_ctx* ctx, float* ms_upload, float* ms_grid_build, float* ms_plan_kernels,
                        float* ms_readback) {
   if (!ctx) return B200LP_E_INVALID;
+  resolve_cloud_timing(const_cast<b200lp_ctx*>(ctx));
   if (ms_upload) *ms_upload = ctx->ms_upload;
   if (ms_grid_build) *ms_grid_build = ctx->ms_grid;
   if (ms_plan_kernels) *ms_plan_kernels = ctx->ms_plan;

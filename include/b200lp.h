@@ -247,8 +247,9 @@ int b200lp_path_blocked(b200lp_ctx* ctx, double check_radius, b200lp_blocked* ou
  * |{cloud points with float d^2 < 1.0 to the pose}| (the reference's radiusSearch candidate set). */
 int b200lp_count_radius(b200lp_ctx* ctx, int64_t* sum_n_r1, int64_t* n_poses);
 
-/* Device-timeline instrumentation: milliseconds the last call spent in each stage, measured with
- * CUDA events on ctx's stream. Any pointer may be NULL. */
+/* Device-timeline instrumentation, CUDA events on ctx's stream: ms_upload / ms_grid_build of the last
+ * b200lp_set_cloud* (which returns once the caller's buffer is consumed, with the grid kernels still in
+ * flight — asking here waits for them), ms_plan_kernels / ms_readback of the last plan call. Any pointer may be NULL. */
 int b200lp_last_timing(const b200lp_ctx* ctx, float* ms_upload, float* ms_grid_build, float* ms_plan_kernels,
                        float* ms_readback);
 /* Per-kernel split of ms_plan_kernels for the last plan call: prep_kernel (velocity sampling, trajectory list,
