@@ -78,6 +78,17 @@ def _scene(seed):
     pyaw = yaw + float(rng.uniform(-0.5, 0.5))
     plan = np.array([[pose[0] - 0.3 * math.cos(pyaw) + 0.05 * i * math.cos(pyaw), pose[1] - 0.3 * math.sin(pyaw) + 0.05 * i * math.sin(pyaw),
                       pose[2] + 0.002 * i, *synth.quat_from_rpy(0.0, float(rng.uniform(-0.1, 0.1)), pyaw)] for i in range(n_plan)]).reshape(-1, 7)
+    if seed % 5 == 0:
+        # the same scene far from the map origin: float coordinates get coarse (6e-5 m at 1 km), the conservative pre-test
+        # and the candidate-box margins have to scale with the map extent
+        off = np.array([rng.uniform(500, 3000), -rng.uniform(500, 3000), rng.uniform(-50, 120)])
+        cloud = cloud.copy()
+        fin = np.isfinite(cloud[:, :3]).all(axis=1)
+        cloud[fin, :3] = (cloud[fin, :3].astype(np.float64) + off).astype(np.float32)
+        pose = [pose[0] + off[0], pose[1] + off[1], pose[2] + off[2], *pose[3:]]
+        if len(plan):
+            plan = plan.copy()
+            plan[:, :3] += off
     return cfg, cloud, plan, pose, twist, float(rng.choice([-1.0, 0.4])), float(rng.uniform(-1.0, 1.0))
 
 
