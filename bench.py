@@ -205,6 +205,21 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_numa_node(gpu_index: int):
+    """Pin this process to the CPUs NVML calls ideal for its GPU, so that the pinned upload buffers are allocated on the
+    GPU's own NUMA node (8 ranks uploading 64 MB each per step otherwise fight over one socket's memory and links)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[gpu_index]) if vis else gpu_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return sorted(os.sched_getaffinity(0))
+    except Exception as e:  # affinity is an optimisation, never a requirement
+        return f"unavailable ({type(e).__name__})"
+
+
 def pinned_copy(arr: np.ndarray):
     """Page-locked host copy of arr (torch allocates; numpy views it)."""
     import torch
@@ -308,6 +323,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)  # before any pinned allocation: the upload buffers should sit next to the GPU
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -461,6 +477,7 @@ def main():
                                     "shard": "sample grid split over the ranks, one 16*W-byte all-reduce per cycle (NCCL)"}[mode]
                                    if world > 1 or mode != "single" else "single GPU"),
                    "grid": lp.grid_info()},
+        "cpu_affinity": (f"{len(numa)} CPUs local to the GPU: {numa[0]}-{numa[-1]}" if isinstance(numa, list) and numa else str(numa)),
         "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * t_e2e / args.steps,
