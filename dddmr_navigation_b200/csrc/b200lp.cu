@@ -362,7 +362,7 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   CK(ctx->d_rec_pp.reserve(want_pp ? T : 1));
   ctx->pose_stride = pose_stride;
   const int argmin_ctas = (int)std::max(1, std::min(kArgminMaxCtas, (cap_local + 2047) / 2048));
-  CK(ctx->d_partial.reserve(n_robots * (size_t)kArgminMaxCtas));
+  CK(ctx->d_partial.reserve(std::max(n_robots * (size_t)kArgminMaxCtas, (size_t)16384)));  // >= the persistent plan grid (SMs x resident CTAs)
   if (ctx->d_tickets2.cap < n_robots) {
     CK(ctx->d_tickets2.reserve(n_robots));
     CK(cudaMemsetAsync(ctx->d_tickets2.p, 0, ctx->d_tickets2.cap * sizeof(unsigned), ctx->stream));
@@ -413,12 +413,15 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   plan_kernel<<<plan_grid, kThreads, 0, ctx->stream>>>(
       ctx->C, ctx->grid, ctx->d_robots.p, ctx->d_meta.p, (int)n_robots, t_cap, cap_local, ctx->d_rec_vel.p,
       ctx->d_rec_steps.p, ctx->d_rec_pose_off.p, ctx->d_poses.p, ctx->d_rec_pp.p, ctx->d_plan_pts.p, ctx->d_cost.p,
-      ctx->d_scores.p, ctx->d_first_hit.p, ctx->d_work.p);
+      ctx->d_scores.p, ctx->d_first_hit.p, ctx->d_work.p, ctx->d_partial.p, ctx->d_tickets2.p, ctx->d_results.p);
   CK(cudaEventRecord(ctx->ev[5], ctx->stream));
-  argmin_kernel<<<dim3((unsigned)argmin_ctas, (unsigned)n_robots), kArgminThreads, 0, ctx->stream>>>(
-      ctx->C, ctx->d_meta.p, t_cap, ctx->d_rec_vel.p, ctx->d_cost.p, ctx->d_first_hit.p, ctx->d_partial.p,
-      ctx->d_tickets2.p, ctx->d_results.p, ctx->d_work.p);
-  ctx->launches += 3;
+  if (n_robots > 1) {  // a single robot's argmin is folded into plan_kernel
+    argmin_kernel<<<dim3((unsigned)argmin_ctas, (unsigned)n_robots), kArgminThreads, 0, ctx->stream>>>(
+        ctx->C, ctx->d_meta.p, t_cap, ctx->d_rec_vel.p, ctx->d_cost.p, ctx->d_first_hit.p, ctx->d_partial.p,
+        ctx->d_tickets2.p, ctx->d_results.p, ctx->d_work.p);
+    ++ctx->launches;
+  }
+  ctx->launches += 2;
   CK(cudaEventRecord(ctx->ev[2], ctx->stream));
   CK(cudaMemcpyAsync(ctx->h_results.p, ctx->d_results.p, n_robots * sizeof(b200lp_result), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(ctx->h_meta.p, ctx->d_meta.p, n_robots * sizeof(RobotMeta), cudaMemcpyDeviceToHost, ctx->stream));

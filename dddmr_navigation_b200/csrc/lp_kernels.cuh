@@ -642,6 +642,24 @@ struct WarpCtx {
   double R0[9], t0[3];
 };
 
+struct Best {
+  unsigned long long cb;  // cost bits, ~0 = none
+  int bi, ncoll;
+  __device__ __forceinline__ void take(unsigned long long ocb, int obi) {
+    if (ocb != ~0ull && (cb == ~0ull || better(ocb, obi, cb, bi))) { cb = ocb; bi = obi; }
+  }
+  __device__ __forceinline__ void warp_reduce() {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long ocb = __shfl_xor_sync(kFull, cb, o);
+      const int obi = __shfl_xor_sync(kFull, bi, o);
+      ncoll += __shfl_xor_sync(kFull, ncoll, o);
+      take(ocb, obi);
+    }
+  }
+};
+
+
 struct CtaShared {
   float stash[kWarpsPerCta][F_COUNT * 32];
   float4 pre[kWarpsPerCta][32 * kPreStride];
@@ -658,7 +676,8 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, const Robot
             const long long* __restrict__ rec_pose_off, const float4* __restrict__ poses,
             const double2* __restrict__ rec_pp, const float4* __restrict__ plan_pts, double* __restrict__ out_cost,
             double* __restrict__ out_scores, int* __restrict__ out_first_hit,
-            unsigned long long* __restrict__ work_counter) {
+            unsigned long long* __restrict__ work_counter, BlockBest* partial, unsigned* __restrict__ tickets,
+            b200lp_result* __restrict__ results) {
   __shared__ CtaShared S;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* stash = S.stash[warp];
@@ -675,6 +694,10 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, const Robot
   }
   __syncthreads();
 
+  // Single-robot launches fold Local_Planner::getBestTrajectory into this kernel (warp -> CTA -> last CTA by ticket);
+  // fleets run argmin_kernel afterwards. The (cost bits, id) order is total, so the merge tree does not matter.
+  const bool fused_argmin = n_robots == 1;
+  Best wb = {~0ull, -1, 0};
   int cur_robot = -1, t_begin = 0, n_local = 0, plan_n = 0;
   double heading_deviation = 0.0;
   const float4* plan = nullptr;
@@ -883,33 +906,85 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, const Robot
       out_cost[rec] = cost;
       out_first_hit[rec] = first_hit;
     }
+    if (fused_argmin) {
+      wb.ncoll += first_hit >= 0 ? 1 : 0;
+      if (cost >= 0.0 && cost <= 9999999.0) wb.take(lpm::d2u(cost), id);  // local_planner.cpp:450,460
+    }
     __syncwarp();
+  }
+  if (!fused_argmin) return;
+
+  // ---- getBestTrajectory for the single robot of this launch --------------------------------------------------
+  __shared__ BlockBest s_best[kWarpsPerCta];
+  __shared__ int s_last;
+  if (lane == 0) {
+    s_best[warp].cost_bits = wb.cb;
+    s_best[warp].id = wb.bi;
+    s_best[warp].n_collided = wb.ncoll;
+  }
+  __syncthreads();
+  Best b = {~0ull, -1, 0};
+  if (warp == 0) {
+    if (lane < kWarpsPerCta) { b.cb = s_best[lane].cost_bits; b.bi = s_best[lane].id; b.ncoll = s_best[lane].n_collided; }
+    b.warp_reduce();
+    if (lane == 0) {
+      BlockBest pb;
+      pb.cost_bits = b.cb; pb.id = b.bi; pb.n_collided = b.ncoll;
+      partial[blockIdx.x] = pb;
+      __threadfence();
+      s_last = atomicAdd(tickets, 1u) == gridDim.x - 1 ? 1 : 0;
+    }
+  }
+  __syncthreads();
+  if (!s_last) return;
+  // the last CTA: every other CTA has stored its partial and left the work loop; all its threads merge the partials
+  __threadfence();
+  b.cb = ~0ull; b.bi = -1; b.ncoll = 0;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += kThreads) {
+    const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(partial + i));  // cost bits (lo, hi), id, n_collided
+    b.ncoll += (int)raw.w;
+    b.take(((unsigned long long)raw.y << 32) | (unsigned long long)raw.x, (int)raw.z);
+  }
+  b.warp_reduce();
+  if (lane == 0) {
+    s_best[warp].cost_bits = b.cb;
+    s_best[warp].id = b.bi;
+    s_best[warp].n_collided = b.ncoll;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    b.cb = ~0ull; b.bi = -1; b.ncoll = 0;
+    for (int w = 0; w < kWarpsPerCta; ++w) {
+      b.ncoll += s_best[w].n_collided;
+      b.take(s_best[w].cost_bits, s_best[w].id);
+    }
+    const RobotMeta m = meta[0];
+    b200lp_result r;
+    r.best_id = (b.cb == ~0ull) ? -1 : b.bi;
+    r.n_samples = m.n_samples;
+    r.n_traj = m.t_end - m.t_begin;
+    r.n_collided = b.ncoll;
+    r.n_poses = m.n_poses;
+    r.best_cost = (b.cb == ~0ull) ? -1.0 : lpm::u2d(b.cb);
+    r.xv = r.yv = r.thetav = 0.0;
+    if (b.cb != ~0ull) {
+      const float4 v = rec_vel[b.bi];
+      r.xv = (double)v.x;
+      r.yv = (C.par.theory == B200LP_THEORY_OMNI_SIMPLE) ? (double)v.y : 0.0;
+      r.thetav = (double)v.z;
+    }
+    results[0] = r;
+    *tickets = 0u;          // ready for the next launch
+    *work_counter = 0ull;
   }
 }
 
-// Local_Planner::getBestTrajectory (local_planner.cpp:447-480) over the costs plan_kernel wrote.
+// Local_Planner::getBestTrajectory (local_planner.cpp:447-480) over the costs plan_kernel wrote (fleet launches).
 // grid = (B, robots): B CTAs split a robot's trajectory range, the last one to finish (ticket) merges the B
 // partials and writes b200lp_result. The (cost bits, id) order is total, so any merge tree gives the reference's
 // sequential `<=` scan result.
 constexpr int kArgminThreads = 256;
 constexpr int kArgminMaxCtas = 64;
-
-struct Best {
-  unsigned long long cb;  // cost bits, ~0 = none
-  int bi, ncoll;
-  __device__ __forceinline__ void take(unsigned long long ocb, int obi) {
-    if (ocb != ~0ull && (cb == ~0ull || better(ocb, obi, cb, bi))) { cb = ocb; bi = obi; }
-  }
-  __device__ __forceinline__ void warp_reduce() {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const unsigned long long ocb = __shfl_xor_sync(kFull, cb, o);
-      const int obi = __shfl_xor_sync(kFull, bi, o);
-      ncoll += __shfl_xor_sync(kFull, ncoll, o);
-      take(ocb, obi);
-    }
-  }
-};
 
 __global__ void __launch_bounds__(kArgminThreads)
 argmin_kernel(Consts C, const RobotMeta* __restrict__ meta, int t_cap, const float4* __restrict__ rec_vel,
