@@ -136,6 +136,9 @@ struct b200lp_ctx {
   PinBuf<double> h_plan7;
   PinBuf<b200lp_result> h_results;
   PinBuf<RobotMeta> h_meta;
+  PinBuf<DirectOut> h_direct;            // single-robot cycles: result block the kernel writes into host memory
+  unsigned long long direct_seq = 0;
+  bool cycle_timing_pending = false, cycle_timing_direct = false;
   PinBuf<unsigned long long> h_count;
   std::vector<RobotMeta> meta_host;
   bool have_cycle = false;
@@ -326,6 +329,20 @@ void resolve_cloud_timing(b200lp_ctx* ctx) {
   ctx->cloud_timing_pending = false;
 }
 
+void resolve_cycle_timing(b200lp_ctx* ctx) {
+  resolve_cloud_timing(ctx);
+  if (!ctx->cycle_timing_pending) return;
+  if (cudaEventSynchronize(ctx->ev[2]) == cudaSuccess) {
+    cudaEventElapsedTime(&ctx->ms_plan, ctx->ev[1], ctx->ev[2]);
+    ctx->ms_readback = 0.f;
+    if (!ctx->cycle_timing_direct) cudaEventElapsedTime(&ctx->ms_readback, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&ctx->ms_k_prep, ctx->ev[1], ctx->ev[4]);
+    cudaEventElapsedTime(&ctx->ms_k_plan, ctx->ev[4], ctx->ev[5]);
+    cudaEventElapsedTime(&ctx->ms_k_argmin, ctx->ev[5], ctx->ev[2]);
+  }
+  ctx->cycle_timing_pending = false;
+}
+
 int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_result* outs, bool plan_resident = false) {
   // inputs are already staged in h_robots / h_plan7 (pinned); total plan poses in plan_total
   const int t_cap = traj_cap(ctx->C.par);
@@ -394,6 +411,15 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   ctx->shard_rank = rank;
   ctx->shard_count = count;
   if (++ctx->epoch == 0u) ctx->epoch = 1u;
+  const bool direct = n_robots == 1;
+  if (direct) {
+    if (!ctx->h_direct.p) {
+      CK(ctx->h_direct.reserve(1));
+      memset(ctx->h_direct.p, 0, sizeof(DirectOut));
+    }
+    ++ctx->direct_seq;
+  }
+  ctx->cycle_timing_pending = false;  // nobody asked for the previous cycle's timeline; its events are re-recorded now
 
   const unsigned long long work = (unsigned long long)n_robots * (unsigned long long)cap_local;
   const unsigned plan_grid = (unsigned)std::max<unsigned long long>(
@@ -413,7 +439,8 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   plan_kernel<<<plan_grid, kThreads, 0, ctx->stream>>>(
       ctx->C, ctx->grid, ctx->d_robots.p, ctx->d_meta.p, (int)n_robots, t_cap, cap_local, ctx->d_rec_vel.p,
       ctx->d_rec_steps.p, ctx->d_rec_pose_off.p, ctx->d_poses.p, ctx->d_rec_pp.p, ctx->d_plan_pts.p, ctx->d_cost.p,
-      ctx->d_scores.p, ctx->d_first_hit.p, ctx->d_work.p, ctx->d_partial.p, ctx->d_tickets2.p, ctx->d_results.p);
+      ctx->d_scores.p, ctx->d_first_hit.p, ctx->d_work.p, ctx->d_partial.p, ctx->d_tickets2.p, ctx->d_results.p,
+      direct ? ctx->h_direct.p : nullptr, ctx->direct_seq);
   CK(cudaEventRecord(ctx->ev[5], ctx->stream));
   if (n_robots > 1) {  // a single robot's argmin is folded into plan_kernel
     argmin_kernel<<<dim3((unsigned)argmin_ctas, (unsigned)n_robots), kArgminThreads, 0, ctx->stream>>>(
@@ -423,11 +450,30 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   }
   ctx->launches += 2;
   CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-  CK(cudaMemcpyAsync(ctx->h_results.p, ctx->d_results.p, n_robots * sizeof(b200lp_result), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->h_meta.p, ctx->d_meta.p, n_robots * sizeof(RobotMeta), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  CK(cudaGetLastError());
+  if (direct) {
+    // the kernel's last CTA writes the result block into pinned host memory and raises seq: no copies, no stream sync
+    CK(cudaGetLastError());
+    volatile unsigned long long* flag = &ctx->h_direct.p->seq;
+    unsigned spins = 0;
+    while (*flag != ctx->direct_seq) {
+      __builtin_ia32_pause();
+      if ((++spins & 0xfffu) == 0u) {  // every few microseconds: is the stream dead or done without raising the flag?
+        const cudaError_t qe = cudaStreamQuery(ctx->stream);
+        if (qe == cudaErrorNotReady) continue;
+        if (qe != cudaSuccess) return ctx->fail(B200LP_E_CUDA, "plan: %s", cudaGetErrorString(qe));
+        if (*flag != ctx->direct_seq) return ctx->fail(B200LP_E_CUDA, "plan: the kernels finished without publishing a result");
+      }
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    ctx->h_results.p[0] = ctx->h_direct.p->r;
+    ctx->h_meta.p[0] = ctx->h_direct.p->m;
+  } else {
+    CK(cudaMemcpyAsync(ctx->h_results.p, ctx->d_results.p, n_robots * sizeof(b200lp_result), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_meta.p, ctx->d_meta.p, n_robots * sizeof(RobotMeta), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+  }
   ctx->meta_host.assign(ctx->h_meta.p, ctx->h_meta.p + n_robots);
   for (size_t i = 0; i < n_robots; ++i) {
     if (ctx->meta_host[i].error)
@@ -436,12 +482,8 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
     outs[i] = ctx->h_results.p[i];
   }
   ctx->have_cycle = true;
-  resolve_cloud_timing(ctx);  // the stream is idle: the set_cloud events have completed
-  cudaEventElapsedTime(&ctx->ms_plan, ctx->ev[1], ctx->ev[2]);
-  cudaEventElapsedTime(&ctx->ms_readback, ctx->ev[2], ctx->ev[3]);
-  cudaEventElapsedTime(&ctx->ms_k_prep, ctx->ev[1], ctx->ev[4]);
-  cudaEventElapsedTime(&ctx->ms_k_plan, ctx->ev[4], ctx->ev[5]);
-  cudaEventElapsedTime(&ctx->ms_k_argmin, ctx->ev[5], ctx->ev[2]);
+  ctx->cycle_timing_pending = true;  // the device timeline is read back when somebody asks for it
+  ctx->cycle_timing_direct = direct;
   return B200LP_OK;
 }
 
@@ -540,7 +582,7 @@ void b200lp_destroy(b200lp_ctx* ctx) {
   ctx->d_first_hit.release(); ctx->d_rec_dt.release(); ctx->d_cost.release(); ctx->d_scores.release();
   ctx->d_rec_pose_off.release(); ctx->d_poses.release(); ctx->d_rec_pp.release(); ctx->d_gplan7.release(); ctx->d_prune_pcl.release(); ctx->d_prune_meta.release(); ctx->h_prune_meta.release(); ctx->d_blocked.release(); ctx->h_blocked.release(); ctx->d_partial.release(); ctx->d_tickets2.release(); ctx->d_tickets.release(); ctx->d_aggs.release(); ctx->d_work.release(); ctx->d_results.release(); ctx->d_count.release(); ctx->d_scratch.release();
   ctx->h_robots.release(); ctx->h_plan7.release(); ctx->h_results.release(); ctx->h_meta.release();
-  ctx->h_count.release();
+  ctx->h_count.release(); ctx->h_direct.release();
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
   for (auto& ev : ctx->chunk_ev)
@@ -840,7 +882,7 @@ int b200lp_count_radius(b200lp_ctx* ctx, int64_t* sum_n_r1, int64_t* n_poses) {
 int b200lp_last_timing(const b200lp_ctx* ctx, float* ms_upload, float* ms_grid_build, float* ms_plan_kernels,
                        float* ms_readback) {
   if (!ctx) return B200LP_E_INVALID;
-  resolve_cloud_timing(const_cast<b200lp_ctx*>(ctx));
+  resolve_cycle_timing(const_cast<b200lp_ctx*>(ctx));
   if (ms_upload) *ms_upload = ctx->ms_upload;
   if (ms_grid_build) *ms_grid_build = ctx->ms_grid;
   if (ms_plan_kernels) *ms_plan_kernels = ctx->ms_plan;
@@ -850,6 +892,7 @@ int b200lp_last_timing(const b200lp_ctx* ctx, float* ms_upload, float* ms_grid_b
 
 int b200lp_last_kernel_ms(const b200lp_ctx* ctx, float* ms_prep_kernel, float* ms_plan_kernel, float* ms_argmin_kernel) {
   if (!ctx) return B200LP_E_INVALID;
+  resolve_cycle_timing(const_cast<b200lp_ctx*>(ctx));
   if (ms_prep_kernel) *ms_prep_kernel = ctx->ms_k_prep;
   if (ms_plan_kernel) *ms_plan_kernel = ctx->ms_k_plan;
   if (ms_argmin_kernel) *ms_argmin_kernel = ctx->ms_k_argmin;

@@ -88,6 +88,14 @@ struct RobotMeta {
   long long n_poses;  // sum num_steps over [t_begin, t_end)
 };
 
+// Result block of a single-robot cycle in mapped pinned host memory: the last CTA of plan_kernel stores it straight into
+// host memory and raises `seq`, the host spins on `seq` instead of enqueueing two copies and synchronising the stream.
+struct DirectOut {
+  b200lp_result r;
+  RobotMeta m;
+  unsigned long long seq;
+};
+
 struct BlockBest {
   unsigned long long cost_bits;  // ~0 = none
   int32_t id;

@@ -677,7 +677,7 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, const Robot
             const double2* __restrict__ rec_pp, const float4* __restrict__ plan_pts, double* __restrict__ out_cost,
             double* __restrict__ out_scores, int* __restrict__ out_first_hit,
             unsigned long long* __restrict__ work_counter, BlockBest* partial, unsigned* __restrict__ tickets,
-            b200lp_result* __restrict__ results) {
+            b200lp_result* __restrict__ results, DirectOut* direct, unsigned long long direct_seq) {
   __shared__ CtaShared S;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* stash = S.stash[warp];
@@ -976,6 +976,12 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, const Robot
     results[0] = r;
     *tickets = 0u;          // ready for the next launch
     *work_counter = 0ull;
+    if (direct) {  // hand the result to the spinning host thread
+      direct->r = r;
+      direct->m = m;
+      __threadfence_system();
+      *(volatile unsigned long long*)&direct->seq = direct_seq;
+    }
   }
 }
 
