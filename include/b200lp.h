@@ -31,7 +31,10 @@
  * input buffer and may free it on return; a ctx owns its device memory and one CUDA stream, is
  * bound to one device and is NOT re-entrant (the reference serialises the same calls under its
  * perception and critics mutexes, local_planner.cpp:498,577). There is no CPU fallback: without a
- * usable CUDA device b200lp_create fails with B200LP_E_CUDA.
+ * usable CUDA device b200lp_create fails with B200LP_E_CUDA. Calls return when their RESULT is on the
+ * host, not necessarily when the stream is idle: b200lp_set_cloud returns once the caller's buffer is
+ * consumed (grid kernels still in flight), b200lp_plan once the kernel has written the result into
+ * pinned host memory; everything later on the ctx is ordered behind that work on the same stream.
  */
 #ifndef B200LP_H_
 #define B200LP_H_
