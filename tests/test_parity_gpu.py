@@ -441,3 +441,37 @@ def test_first_cycle_of_a_fresh_process_is_already_right():
         line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")][0].split()
         assert [int(line[1]), int(line[2]), int(line[3]), int(line[4])] == [r_o.n_samples, r_o.n_traj, r_o.n_poses, r_o.best_id]
         assert float(line[5]) == r_o.best_cost
+
+
+def test_api_edges_device_cloud_errors_and_reuse():
+    """C-ABI behaviour around the path: a cloud that already lives on the device, 16-byte PointXYZ stride, call-order and
+    argument errors (negative status + message, no crash), and one ctx reused across clouds of very different size."""
+    import ctypes as C
+    import torch
+    sc = synth.c1_ramp(n_points=20_000)
+    gpu, ora = _pair(sc.config)
+    r_g, r_o = run_pair(gpu, ora, sc.cloud, sc.plan, sc.pose, sc.twist)
+    # the same cloud handed over as a device buffer, PointXYZ (16-byte) layout
+    xyz4 = np.ascontiguousarray(sc.cloud[:, :4])
+    dev = torch.from_numpy(xyz4).cuda()
+    gpu.set_cloud_device(dev.data_ptr(), dev.shape[0], 16)
+    assert gpu.plan(make_query(sc.pose, sc.twist)).as_dict() == r_o.as_dict()
+    # errors: bad stride, too long a plan, read-back before any cycle, out-of-range trajectory id
+    lib = gpu.lib
+    assert lib.b200lp_set_cloud(gpu.h, xyz4.ctypes.data_as(C.c_void_p), 10, 10) == abi.E_INVALID
+    assert b"stride" in lib.b200lp_last_error(gpu.h)
+    long_plan = np.zeros((abi.MAX_PLAN + 1, 7))
+    assert lib.b200lp_set_plan(gpu.h, long_plan.ctypes.data_as(C.POINTER(C.c_double)), long_plan.shape[0]) == abi.E_INVALID
+    fresh = LocalPlanner(sc.config)
+    v = abi.TrajView()
+    assert fresh.lib.b200lp_read_trajectories(fresh.h, 0, C.byref(v)) == abi.E_STATE
+    pv = abi.PoseView()
+    assert lib.b200lp_read_poses(gpu.h, 0, 10**6, C.byref(pv)) == abi.E_INVALID
+    assert lib.b200lp_path_blocked(gpu.h, 0.5, C.byref(abi.Blocked())) == abi.E_STATE  # no device-side prune plan yet
+    # the ctx survives the errors and a sequence of very different clouds (buffers grow and are reused)
+    for n in (7, 200_000, 0, 3000, 20_000):
+        cloud = synth.c1_ramp(n_points=max(n, 1000)).cloud[:n] if n else synth.to_xyzi(np.zeros((0, 3), np.float32))
+        gpu.set_cloud(cloud)
+        ora.set_cloud(cloud)
+        q = make_query(sc.pose, sc.twist)
+        assert gpu.plan(q).as_dict() == ora.plan(q).as_dict(), n
