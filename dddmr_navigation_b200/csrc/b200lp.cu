@@ -238,14 +238,18 @@ int build_grid(b200lp_ctx* ctx, const void* src, size_t n, size_t stride, bool o
   CK(cudaMemcpyAsync(ctx->d_bounds.p, ctx->h_bounds.p, sizeof(BoundsDev), cudaMemcpyHostToDevice, ctx->stream));
   if (n) {
     const int chunks = (src && n >= (size_t)kUploadChunks * 65536) ? kUploadChunks : 1;
-    if (src) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->cev[0], 0));  // the copy may not overtake earlier work on d_raw
+    // one piece: plain copy on the main stream; several: on the copy stream, each piece handed over by an event
+    cudaStream_t cs = chunks > 1 ? ctx->copy_stream : ctx->stream;
+    if (src && chunks > 1) CK(cudaStreamWaitEvent(cs, ctx->cev[0], 0));  // the copy may not overtake earlier work on d_raw
     for (int c = 0; c < chunks; ++c) {
       const size_t i0 = n * c / chunks, i1 = n * (c + 1) / chunks;
       if (src) {
         CK(cudaMemcpyAsync(ctx->d_raw.p + i0 * stride, (const char*)src + i0 * stride, (i1 - i0) * stride,
-                           on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->copy_stream));
-        CK(cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream));
-        CK(cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[c], 0));
+                           on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, cs));
+        if (chunks > 1) {
+          CK(cudaEventRecord(ctx->chunk_ev[c], cs));
+          CK(cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[c], 0));
+        }
       }
       if (c == chunks - 1) CK(cudaEventRecord(ctx->cev[1], ctx->stream));  // everything has arrived
       bounds_pack_kernel<<<grid_blocks(i1 - i0, 256, sms), 256, 0, ctx->stream>>>(ctx->d_raw.p, i0, i1, stride, ctx->d_packed.p,

@@ -12,7 +12,10 @@ for name in (sys.argv[1:] or ["C2"]):
     for lib in sorted(glob.glob(os.path.join(ROOT, "tools", "variants", "*.so"))):
         lp = LocalPlanner(sc.config, device=0, lib_path=lib)
         wall, up, gr = [], [], []
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
         for i in range(15):
+            if os.environ.get("FLUSH"):
+                flush.zero_(); torch.cuda.synchronize()
             t0 = time.perf_counter()
             lp.set_cloud_ptr(cloud.ctypes.data, cloud.shape[0], cloud.shape[1] * 4)
             dt = time.perf_counter() - t0
