@@ -13,7 +13,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libb200lp.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # status codes
 OK, E_INVALID, E_CUDA, E_STATE, E_NOMEM = 0, -1, -2, -3, -4
@@ -41,6 +41,7 @@ CRITIC_BY_PLUGIN = {
 MAX_CRITICS = 8
 MAX_STEPS = 512
 MAX_PLAN = 1024
+MAX_SENSORS = 8
 
 
 class Limits(C.Structure):
@@ -107,6 +108,20 @@ class Blocked(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class SensorParams(C.Structure):
+    """What MultiLayerSpinningLidar reads for cbSensor (multilayer_spinning_lidar.cpp:64-131)."""
+    _fields_ = [("perception_window_size", C.c_double), ("marking_height", C.c_double), ("leaf_size", C.c_float),
+                ("is_local_planner", C.c_int32)]
+
+
+class ObservationInfo(C.Structure):
+    _fields_ = [("n_scan", C.c_int64), ("n_window", C.c_int64), ("n_points", C.c_int64), ("ms_device", C.c_float),
+                ("n_launches", C.c_int32)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 # every symbol include/b200lp.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -131,6 +146,10 @@ SYMBOLS = {
     "b200lp_prune_plan": (C.c_int, [_P, C.POINTER(C.c_double), C.c_double, C.c_double, C.POINTER(PruneInfo)]),
     "b200lp_read_prune_plan": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_float), C.c_size_t]),
     "b200lp_path_blocked": (C.c_int, [_P, C.c_double, C.POINTER(Blocked)]),
+    "b200lp_sensor_observation": (C.c_int, [_P, C.c_int, _P, C.c_size_t, C.c_size_t, C.POINTER(C.c_double),
+                                            C.POINTER(C.c_double), C.POINTER(SensorParams), C.POINTER(ObservationInfo)]),
+    "b200lp_read_observation": (C.c_int, [_P, C.c_int, _P, C.c_size_t, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "b200lp_aggregate_observations": (C.c_int, [_P, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_size_t)]),
     "b200lp_count_radius": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "b200lp_last_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
                                      C.POINTER(C.c_float)]),

@@ -16,6 +16,7 @@
 
 #include "../../include/b200lp.h"
 #include "lp_kernels.cuh"
+#include "lp_observe.cuh"
 
 using namespace lp;
 
@@ -106,6 +107,16 @@ struct b200lp_ctx {
   DevBuf<int> d_blocked;
   PinBuf<int> h_blocked;
   bool have_prune = false;
+
+  // observation producer
+  DevBuf<char> d_scan;                          // the uploaded lidar scan
+  DevBuf<float4> d_obs_a, d_obs_b;              // sort ping-pong: (x, y, z in base_link, voxel key)
+  DevBuf<uint32_t> d_obs_hist, d_obs_sums, d_obs_heads, d_obs_counts;
+  PinBuf<uint32_t> h_obs_counts;
+  DevBuf<float4> d_obs_out[B200LP_MAX_SENSORS];  // Sensor::sensor_current_observation_ per sensor, pcl::PointXYZ layout
+  size_t n_obs_out[B200LP_MAX_SENSORS] = {0, 0, 0, 0, 0, 0, 0, 0};
+  bool have_obs[B200LP_MAX_SENSORS] = {false, false, false, false, false, false, false, false};
+  cudaEvent_t oev[2] = {nullptr, nullptr};
 
   // per-cycle state
   size_t n_robots = 0;
@@ -559,6 +570,8 @@ int b200lp_create(b200lp_ctx** out, int device, const b200lp_limits* limits, con
     if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
   for (auto& ev : ctx->cev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+  for (auto& ev : ctx->oev)
+    if ((e = cudaEventCreate(&ev)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
   ctx->C.lim = *limits;
   ctx->C.par = *params;
   memcpy(ctx->C.cuboid, cuboid_xyz, sizeof(ctx->C.cuboid));
@@ -587,6 +600,11 @@ void b200lp_destroy(b200lp_ctx* ctx) {
   ctx->d_rec_pose_off.release(); ctx->d_poses.release(); ctx->d_rec_pp.release(); ctx->d_gplan7.release(); ctx->d_prune_pcl.release(); ctx->d_prune_meta.release(); ctx->h_prune_meta.release(); ctx->d_blocked.release(); ctx->h_blocked.release(); ctx->d_partial.release(); ctx->d_tickets2.release(); ctx->d_tickets.release(); ctx->d_aggs.release(); ctx->d_work.release(); ctx->d_results.release(); ctx->d_count.release(); ctx->d_scratch.release();
   ctx->h_robots.release(); ctx->h_plan7.release(); ctx->h_results.release(); ctx->h_meta.release();
   ctx->h_count.release(); ctx->h_direct.release();
+  ctx->d_scan.release(); ctx->d_obs_a.release(); ctx->d_obs_b.release(); ctx->d_obs_hist.release(); ctx->d_obs_sums.release();
+  ctx->d_obs_heads.release(); ctx->d_obs_counts.release(); ctx->h_obs_counts.release();
+  for (auto& b : ctx->d_obs_out) b.release();
+  for (auto& ev : ctx->oev)
+    if (ev) cudaEventDestroy(ev);
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
   for (auto& ev : ctx->chunk_ev)
@@ -860,6 +878,167 @@ int b200lp_path_blocked(b200lp_ctx* ctx, double check_radius, b200lp_blocked* ou
   }
   B.opinion = B.ratio > 0.0 ? 1 : 0;
   *out = B;
+  return B200LP_OK;
+}
+
+// tf2::transformToEigen(TransformStamped) = Translation3d * Quaterniond(w, x, y, z) as a row-major 3x4 (no normalisation,
+// Eigen's toRotationMatrix operation order; the same expression as lp::quat_to_matrix on the device and the oracle)
+static void transform_to_rows(const double p[7], double m[12]) {
+  const double x = p[3], y = p[4], z = p[5], w = p[6];
+  const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
+  const double twx = tx * w, twy = ty * w, twz = tz * w;
+  const double txx = tx * x, txy = ty * x, txz = tz * x;
+  const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  m[0] = 1.0 - (tyy + tzz); m[1] = txy - twz;         m[2] = txz + twy;          m[3] = p[0];
+  m[4] = txy + twz;         m[5] = 1.0 - (txx + tzz); m[6] = tyz - twx;          m[7] = p[1];
+  m[8] = txz - twy;         m[9] = tyz + twx;         m[10] = 1.0 - (txx + tyy); m[11] = p[2];
+}
+
+int b200lp_sensor_observation(b200lp_ctx* ctx, int sensor, const void* scan, size_t n, size_t stride,
+                              const double base_from_sensor[7], const double global_from_base[7],
+                              const b200lp_sensor_params* sp, b200lp_observation_info* info) {
+  if (!ctx) return B200LP_E_INVALID;
+  if (sensor < 0 || sensor >= B200LP_MAX_SENSORS) return ctx->fail(B200LP_E_INVALID, "sensor_observation: sensor index out of range");
+  if (!sp || !base_from_sensor || !global_from_base || (n && !scan) || stride < 12 || (stride & 3))
+    return ctx->fail(B200LP_E_INVALID, "sensor_observation: bad argument");
+  if (n > 0x7fffffffull) return ctx->fail(B200LP_E_INVALID, "sensor_observation: more than 2^31 points");
+  ObsDev P{};
+  transform_to_rows(base_from_sensor, P.m1);
+  transform_to_rows(global_from_base, P.m2);
+  P.apply_m2 = sp->is_local_planner ? 1 : 0;
+  const float leaf = sp->leaf_size > 0.f ? sp->leaf_size : 0.1f;
+  P.inv_leaf = 1.0f / leaf;  // pcl::VoxelGrid::setLeafSize: inverse_leaf_size_ = Array4f::Ones() / leaf_size_.array()
+  // pcl::PassThrough::setFilterLimits(const float&, const float&): the doubles are narrowed at the call (:242, :249)
+  P.lo[0] = P.lo[1] = (float)(-sp->perception_window_size);
+  P.hi[0] = P.hi[1] = (float)(sp->perception_window_size);
+  P.lo[2] = 0.0f;
+  P.hi[2] = (float)(sp->marking_height);
+  double cells = 1.0;
+  uint32_t ext[3];
+  for (int a = 0; a < 3; ++a) {
+    const float flo = std::floor(P.lo[a] * P.inv_leaf), fhi = std::floor(P.hi[a] * P.inv_leaf);
+    if (!(std::fabs(flo) < 8388608.f) || !(std::fabs(fhi) < 8388608.f))
+      return ctx->fail(B200LP_E_INVALID, "sensor_observation: window / leaf out of range");
+    P.lb[a] = (int)flo;
+    ext[a] = fhi >= flo ? (uint32_t)((int)fhi - (int)flo + 1) : 1u;
+    cells *= (double)ext[a];
+  }
+  if (cells > (double)(1u << 27))
+    return ctx->fail(B200LP_E_INVALID, "sensor_observation: the pass-through window holds %.0f voxels of %.3f m (limit 2^27)", cells, leaf);
+  P.d0 = ext[0];
+  P.d1 = ext[1];
+  int key_bits = 1;
+  while (((uint64_t)1 << key_bits) < (uint64_t)cells) ++key_bits;
+  const int passes = (key_bits + kObsMaxBits - 1) / kObsMaxBits;
+  const int bits = (key_bits + passes - 1) / passes;
+
+  CK(cudaSetDevice(ctx->device));
+  ctx->have_obs[sensor] = false;
+  ctx->n_obs_out[sensor] = 0;
+  b200lp_observation_info I{};
+  I.n_scan = (int64_t)n;
+  if (n) {
+    const unsigned nb = (unsigned)((n + kObsTile - 1) / kObsTile);
+    const size_t hist_n = ((size_t)1 << bits) * nb;
+    const unsigned nbk = (unsigned)((hist_n + kScanItems - 1) / kScanItems);
+    const unsigned nbh = (unsigned)((n + kObsHeadTile - 1) / kObsHeadTile);
+    CK(ctx->d_scan.reserve(n * stride));
+    CK(ctx->d_obs_a.reserve(n));
+    CK(ctx->d_obs_b.reserve(n));
+    CK(ctx->d_obs_hist.reserve(hist_n));
+    CK(ctx->d_obs_sums.reserve(nbk));
+    CK(ctx->d_obs_heads.reserve(nbh));
+    CK(ctx->d_obs_counts.reserve(2));
+    CK(ctx->h_obs_counts.reserve(2));
+    CK(ctx->d_obs_out[sensor].reserve(n));
+    cudaStream_t st = ctx->stream;
+    CK(cudaEventRecord(ctx->oev[0], st));
+    CK(cudaMemcpyAsync(ctx->d_scan.p, scan, n * stride, cudaMemcpyHostToDevice, st));
+    obs_key_kernel<<<nb, kObsThreads, 0, st>>>(ctx->d_scan.p, n, stride, P, bits, ctx->d_obs_a.p, ctx->d_obs_hist.p);
+    float4 *src = ctx->d_obs_a.p, *dst = ctx->d_obs_b.p;
+    int launches = 1;
+    for (int p = 0; p < passes; ++p) {
+      if (p) {
+        obs_hist_kernel<<<nb, kObsThreads, 0, st>>>(src, ctx->d_obs_counts.p, p * bits, bits, ctx->d_obs_hist.p);
+        ++launches;
+      }
+      scan_block_kernel<<<nbk, 256, 0, st>>>(ctx->d_obs_hist.p, hist_n, ctx->d_obs_sums.p);
+      scan_sums_kernel<<<1, 1024, 0, st>>>(ctx->d_obs_sums.p, (int)nbk, ctx->d_obs_counts.p);  // total = points in the window
+      obs_scatter_kernel<<<nb, kObsThreads, 0, st>>>(src, n, ctx->d_obs_counts.p, p == 0 ? 1 : 0, p * bits, bits, ctx->d_obs_hist.p,
+                                                     ctx->d_obs_sums.p, dst);
+      launches += 3;
+      std::swap(src, dst);
+    }
+    obs_heads_kernel<<<nbh, kObsThreads, 0, st>>>(src, ctx->d_obs_counts.p, ctx->d_obs_heads.p);
+    obs_centroid_kernel<<<nbh, kObsThreads, 0, st>>>(src, ctx->d_obs_counts.p, ctx->d_obs_heads.p, P, ctx->d_obs_out[sensor].p);
+    launches += 2;
+    ctx->launches += launches;
+    I.n_launches = launches;
+    CK(cudaMemcpyAsync(ctx->h_obs_counts.p, ctx->d_obs_counts.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(ctx->oev[1], st));
+    CK(cudaStreamSynchronize(st));  // the caller may free the scan on return, and needs the point count
+    CK(cudaGetLastError());
+    I.n_window = ctx->h_obs_counts.p[0];
+    I.n_points = ctx->h_obs_counts.p[1];
+    cudaEventElapsedTime(&I.ms_device, ctx->oev[0], ctx->oev[1]);
+  }
+  ctx->n_obs_out[sensor] = (size_t)I.n_points;
+  ctx->have_obs[sensor] = true;
+  if (info) *info = I;
+  return B200LP_OK;
+}
+
+int b200lp_read_observation(b200lp_ctx* ctx, int sensor, void* out, size_t capacity, size_t stride, size_t* n_points) {
+  if (!ctx) return B200LP_E_INVALID;
+  if (sensor < 0 || sensor >= B200LP_MAX_SENSORS) return ctx->fail(B200LP_E_INVALID, "read_observation: sensor index out of range");
+  if (!ctx->have_obs[sensor]) return ctx->fail(B200LP_E_STATE, "read_observation: sensor %d has no observation", sensor);
+  if (stride != 16 && stride != 32) return ctx->fail(B200LP_E_INVALID, "read_observation: stride must be 16 (PointXYZ) or 32 (PointXYZI)");
+  const size_t n = ctx->n_obs_out[sensor];
+  if (n_points) *n_points = n;
+  if (n > capacity) return ctx->fail(B200LP_E_INVALID, "read_observation: %zu points exceed the capacity %zu", n, capacity);
+  if (!n) return B200LP_OK;
+  if (!out) return ctx->fail(B200LP_E_INVALID, "read_observation: null buffer");
+  CK(cudaSetDevice(ctx->device));
+  if (stride == 16) {
+    CK(cudaMemcpyAsync(out, ctx->d_obs_out[sensor].p, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  } else {
+    CK(ctx->d_scratch.reserve(n * 32));
+    obs_expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_obs_out[sensor].p, n, (float4*)ctx->d_scratch.p);
+    ++ctx->launches;
+    CK(cudaMemcpyAsync(out, ctx->d_scratch.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  return B200LP_OK;
+}
+
+int b200lp_aggregate_observations(b200lp_ctx* ctx, const int32_t* sensors, int n_sensors, size_t* n_total) {
+  if (!ctx) return B200LP_E_INVALID;
+  if (n_sensors < 0 || n_sensors > B200LP_MAX_SENSORS || (n_sensors && !sensors))
+    return ctx->fail(B200LP_E_INVALID, "aggregate_observations: bad sensor list");
+  size_t total = 0;
+  for (int k = 0; k < n_sensors; ++k) {
+    if (sensors[k] < 0 || sensors[k] >= B200LP_MAX_SENSORS) return ctx->fail(B200LP_E_INVALID, "aggregate_observations: sensor index out of range");
+    if (!ctx->have_obs[sensors[k]]) return ctx->fail(B200LP_E_STATE, "aggregate_observations: sensor %d has no observation", sensors[k]);
+    total += ctx->n_obs_out[sensors[k]];
+  }
+  if (total > 0xfffffff0ull) return ctx->fail(B200LP_E_INVALID, "aggregate_observations: more than 2^32 points");
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->d_raw.reserve(std::max<size_t>(total * 16, 16)));
+  ctx->raw_stride = 16;
+  ctx->cloud_timing_pending = false;
+  size_t off = 0;
+  for (int k = 0; k < n_sensors; ++k) {  // `*aggregate += *plugin->getObservation()` in plugin order
+    const size_t m = ctx->n_obs_out[sensors[k]];
+    if (m) CK(cudaMemcpyAsync(ctx->d_raw.p + off * 16, ctx->d_obs_out[sensors[k]].p, m * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+    off += m;
+  }
+  int rc = build_grid(ctx, nullptr, total, 16, false);
+  if (rc) return rc;
+  CK(cudaEventRecord(ctx->cev[2], ctx->stream));
+  ctx->cloud_timing_pending = true;
+  ctx->have_cycle = false;
+  if (n_total) *n_total = total;
   return B200LP_OK;
 }
 

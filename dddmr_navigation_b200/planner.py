@@ -127,6 +127,35 @@ class LocalPlanner:
         self._ck(self.lib.b200lp_path_blocked(self.h, float(check_radius), C.byref(b)))
         return b
 
+    def sensor_observation(self, sensor: int, scan: np.ndarray, base_from_sensor, global_from_base, window: float,
+                           marking_height: float, leaf: float = 0.1, is_local_planner: bool = True) -> abi.ObservationInfo:
+        """perception_3d::MultiLayerSpinningLidar::cbSensor (multilayer_spinning_lidar.cpp:232-269) on one scan:
+        transform -> pass-through -> voxel filter -> transform; the observation stays on the device.
+        scan: (n,3|4|8) float32 in the sensor frame; the transforms are (x,y,z, qx,qy,qz,qw)."""
+        pts, stride = _cloud_bytes(scan)
+        sp = abi.SensorParams(float(window), float(marking_height), float(leaf), int(bool(is_local_planner)))
+        b2s = (C.c_double * 7)(*[float(v) for v in base_from_sensor])
+        g2b = (C.c_double * 7)(*[float(v) for v in global_from_base])
+        info = abi.ObservationInfo()
+        self._ck(self.lib.b200lp_sensor_observation(self.h, int(sensor), pts.ctypes.data_as(_P), pts.shape[0], stride, b2s, g2b,
+                                                    C.byref(sp), C.byref(info)))
+        return info
+
+    def read_observation(self, sensor: int, n: int, stride: int = 16) -> np.ndarray:
+        """Sensor::sensor_current_observation_ of `sensor`: (n,4) x,y,z,1 for stride 16, (n,8) PointXYZI rows for 32."""
+        out = np.zeros((max(n, 1), stride // 4), np.float32)
+        got = C.c_size_t()
+        self._ck(self.lib.b200lp_read_observation(self.h, int(sensor), out.ctypes.data_as(_P), n, stride, C.byref(got)))
+        return out[:got.value]
+
+    def aggregate_observations(self, sensors) -> int:
+        """StackedPerception::aggregateObservations (stacked_perception.cpp:128-140) on the device: the concatenation
+        becomes the critics' cloud."""
+        ids = (C.c_int32 * len(sensors))(*[int(v) for v in sensors])
+        total = C.c_size_t()
+        self._ck(self.lib.b200lp_aggregate_observations(self.h, ids, len(sensors), C.byref(total)))
+        return total.value
+
     # -- cycle ----------------------------------------------------------------------------------
     def plan(self, q: abi.Query) -> abi.Result:
         r = abi.Result()

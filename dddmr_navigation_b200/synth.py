@@ -359,3 +359,49 @@ def small_scene(seed: int, n_points: int = 3000, extent: float = 4.0, cuboid=Non
         blocks.append(b)
         have += len(b)
     return _finish_cloud(rng, blocks, n_points)
+
+
+# ---------------------------------------------------------------------------------------------------
+# lidar scans for the observation producer
+# ---------------------------------------------------------------------------------------------------
+def lidar_scan(n_beams: int = 32, n_azimuth: int = 1024, seed: int = SEED0 + 6, sensor_height: float = 0.6,
+               room=(16.0, 12.0, 2.8), n_pillars: int = 12, dropout: float = 0.02, noise: float = 0.01):
+    """One revolution of a multilayer spinning lidar in a box room with cylindrical pillars, as the (N,4) float32
+    pcl::PointXYZ rows (sensor frame) that pcl::fromROSMsg hands to MultiLayerSpinningLidar::cbSensor
+    (multilayer_spinning_lidar.cpp:178-183). Returns without a hit are NaN rows (a non-dense cloud), a few are +inf.
+    -> (scan, base_from_sensor (7,), global_from_base (7,))."""
+    rng = np.random.default_rng(seed)
+    el = np.deg2rad(np.linspace(-25.0, 15.0, n_beams))
+    az = np.linspace(-np.pi, np.pi, n_azimuth, endpoint=False)
+    A, E = np.meshgrid(az, el)
+    d = np.stack([np.cos(E) * np.cos(A), np.cos(E) * np.sin(A), np.sin(E)], -1).reshape(-1, 3)
+    hx, hy, hz = room[0] / 2, room[1] / 2, room[2]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = np.full(d.shape[0], np.inf)
+        for axis, lo, hi in ((0, -hx, hx), (1, -hy, hy), (2, -sensor_height, hz - sensor_height)):
+            for plane in (lo, hi):
+                tp = plane / d[:, axis]
+                t = np.where((tp > 0) & (tp < t), tp, t)
+        for _ in range(n_pillars):
+            cx, cy = rng.uniform(-hx + 1, hx - 1), rng.uniform(-hy + 1, hy - 1)
+            if math.hypot(cx, cy) < 1.0:
+                continue
+            r = rng.uniform(0.1, 0.4)
+            a = d[:, 0] ** 2 + d[:, 1] ** 2
+            b = -2 * (d[:, 0] * cx + d[:, 1] * cy)
+            c = cx * cx + cy * cy - r * r
+            disc = b * b - 4 * a * c
+            tp = (-b - np.sqrt(np.where(disc >= 0, disc, np.nan))) / (2 * a)
+            t = np.where((tp > 0) & (tp < t), tp, t)
+    t = t + rng.normal(0.0, noise, t.shape)
+    pts = (d * t[:, None]).astype(np.float32)
+    drop = rng.random(pts.shape[0]) < dropout
+    pts[drop] = np.nan
+    pts[rng.random(pts.shape[0]) < dropout / 20] = np.inf
+    scan = np.zeros((pts.shape[0], 4), np.float32)
+    scan[:, :3] = pts
+    scan[:, 3] = 1.0
+    # sensor mounted 0.25 m ahead of base_link, sensor_height up, yawed 2 deg and rolled 1 deg; robot somewhere in the map
+    b2s = np.array([0.25, 0.0, sensor_height, *quat_from_rpy(math.radians(1.0), 0.0, math.radians(2.0))], np.float64)
+    g2b = np.array([12.5, -3.75, 0.02, *quat_from_rpy(0.0, math.radians(-3.0), math.radians(40.0))], np.float64)
+    return scan, b2s, g2b

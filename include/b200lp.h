@@ -23,6 +23,11 @@
  *   b200lp_read_trajectories <- what the reference keeps in std::vector<base_trajectory::Trajectory>
  *                               (LP/base_trajectory/include/base_trajectory/trajectory.h:47-126) — read back for
  *                               RViz publishing (local_planner.cpp:554,569) and for parity tests.
+ *   b200lp_sensor_observation /
+ *   b200lp_aggregate_observations <- the producer of that cloud: MultiLayerSpinningLidar::cbSensor's transform -> pass-through ->
+ *                               0.1 m voxel filter -> transform (dddmr_perception_3d/plugins/multilayer_spinning_lidar.cpp:232-269)
+ *                               and StackedPerception::aggregateObservations (dddmr_perception_3d/src/stacked_perception.cpp:128-140);
+ *                               the observation stays on the device and becomes the critics' cloud without a host round trip.
  *   b200lp_count_radius      <- diagnostic: |radiusSearch(pose, 1.0)| per pose (LP/mpc_critics/models/collision_model.cpp:122),
  *                               the n_r1 figure the roofline accounting is defined on.
  *
@@ -46,7 +51,7 @@
 extern "C" {
 #endif
 
-#define B200LP_ABI_VERSION 3
+#define B200LP_ABI_VERSION 4
 
 /* status codes */
 #define B200LP_OK 0
@@ -245,6 +250,41 @@ int b200lp_read_prune_plan(b200lp_ctx* ctx, double* poses7, float* pcl_xyzi, siz
 /* PathBlockedStrategy::selfMark of the device-side prune plan against the current cloud (the same voxel grid the
  * critics query). Requires a successful b200lp_prune_plan. */
 int b200lp_path_blocked(b200lp_ctx* ctx, double check_radius, b200lp_blocked* out);
+
+/* ---- the observation producer in front of the path --------------------------------------- */
+#define B200LP_MAX_SENSORS 8
+/* Parameters MultiLayerSpinningLidar reads for cbSensor (multilayer_spinning_lidar.cpp:64-131). */
+typedef struct b200lp_sensor_params {
+  double perception_window_size; /* pass-through limits of x and y in base_link: [-w, w] (:242, :246) */
+  double marking_height;         /* pass-through limits of z in base_link: [0, marking_height] (:249) */
+  float leaf_size;               /* pcl::VoxelGrid leaf, 0.1f upstream (:254); 0 selects 0.1f */
+  int32_t is_local_planner;      /* non-zero: the observation is moved to the global frame (:264-268) */
+} b200lp_sensor_params;
+typedef struct b200lp_observation_info {
+  int64_t n_scan;   /* points handed in */
+  int64_t n_window; /* points left by the three pass-through filters (non-finite points are removed there too) */
+  int64_t n_points; /* voxels = points of the observation */
+  float ms_device;  /* CUDA-event time of the device work of this call (upload included) */
+  int32_t n_launches;
+} b200lp_observation_info;
+/* MultiLayerSpinningLidar::cbSensor on one scan (after pcl::fromROSMsg / stitching): `scan` is host memory, n points of
+ * stride_bytes each (16 = pcl::PointXYZ), x,y,z = first three floats, in the sensor frame. base_from_sensor =
+ * trans_b2s_, global_from_base = trans_gbl2b_ (translation xyz, rotation xyzw: geometry_msgs Transform order).
+ * The result is sensor `sensor`'s current observation (Sensor::sensor_current_observation_), kept on the device.
+ * Voxels leave in ascending voxel-index order like pcl::VoxelGrid; inside a voxel the points are added in scan order
+ * (PCL adds them in the order an unstable sort of the voxel indices leaves them).
+ * B200LP_E_INVALID when the window holds more than 2^27 voxels of that leaf. */
+int b200lp_sensor_observation(b200lp_ctx* ctx, int sensor, const void* scan, size_t n, size_t stride_bytes,
+                              const double base_from_sensor[7], const double global_from_base[7],
+                              const b200lp_sensor_params* params, b200lp_observation_info* info /* may be NULL */);
+/* Read sensor's current observation back (for the reference's current_observation publisher, :273-278, and for parity
+ * tests): stride_bytes 16 = pcl::PointXYZ (x, y, z, 1), 32 = pcl::PointXYZI (+ intensity 0). Returns B200LP_E_INVALID
+ * when it holds more than capacity_points. */
+int b200lp_read_observation(b200lp_ctx* ctx, int sensor, void* out, size_t capacity_points, size_t stride_bytes,
+                            size_t* n_points);
+/* StackedPerception::aggregateObservations: concatenate the current observations of `sensors` (plugin order) on the
+ * device and make the result the critics' cloud (what b200lp_set_cloud does with a host cloud). */
+int b200lp_aggregate_observations(b200lp_ctx* ctx, const int32_t* sensors, int n_sensors, size_t* n_total /* may be NULL */);
 
 /* Roofline accounting helper: sum over all scored poses of the last plan call of
  * |{cloud points with float d^2 < 1.0 to the pose}| (the reference's radiusSearch candidate set). */

@@ -992,6 +992,117 @@ int lporacle_path_blocked(lporacle_ctx* c, const float* pcl_xyzi, size_t n, doub
   return B200LP_OK;
 }
 
+// perception_3d::MultiLayerSpinningLidar::cbSensor from the first transform to the local-planner observation
+// (src/dddmr_perception_3d/plugins/multilayer_spinning_lidar.cpp:232-269), with the PCL 1.15 filters it calls restated
+// from their published algorithms (PCL is not vendored under /root/reference: this part of the parity is UNPINNED):
+//   pcl::transformPointCloud(cloud, cloud, Affine3d)  common/impl/transforms.hpp  
+//   pcl::PassThrough<PointXYZ>::applyFilterIndices    filters/impl/passthrough.hpp
+//   pcl::VoxelGrid<PointXYZ>::applyFilter             filters/impl/voxel_grid.hpp
+//   pcl::CentroidPoint<PointXYZ> / AccumulatorXYZ     common/impl/accumulators.hpp
+// order_mode 0: the points of a voxel are added in scan order (a stable sort of the voxel indices) — the order the device
+// path defines; 1: in the order libstdc++'s std::sort leaves them (unstable, like PCL's boost spreadsort / std::sort), to
+// measure how far an unstable order moves a centroid. Voxel set, voxel order and counts do not depend on the mode.
+// out_xyz1: capacity x 4 floats (pcl::PointXYZ layout, data[3] = 1). Returns B200LP_E_INVALID if the capacity is too small.
+int lporacle_sensor_observation(const void* scan, size_t n, size_t stride, const double base_from_sensor[7],
+                                const double global_from_base[7], const b200lp_sensor_params* sp, int order_mode,
+                                float* out_xyz1, size_t capacity, b200lp_observation_info* info) {
+  if (!sp || !info || (n && !scan)) return B200LP_E_INVALID;
+  struct P3 { float x, y, z; };
+  std::vector<P3> cloud(n);
+  for (size_t i = 0; i < n; ++i) memcpy(&cloud[i], (const char*)scan + i * stride, 12);
+  auto transform = [](std::vector<P3>& c, const Affine& a) {  // :232-233, :266-267
+    for (P3& p : c) {
+      const double x = p.x, y = p.y, z = p.z;
+      p.x = (float)(((a.L[0][0] * x + a.L[0][1] * y) + a.L[0][2] * z) + a.t[0]);
+      p.y = (float)(((a.L[1][0] * x + a.L[1][1] * y) + a.L[1][2] * z) + a.t[1]);
+      p.z = (float)(((a.L[2][0] * x + a.L[2][1] * y) + a.L[2][2] * z) + a.t[2]);
+    }
+  };
+  transform(cloud, pose_to_affine(base_from_sensor));  // tf2::transformToEigen(trans_b2s_)
+  // three pcl::PassThrough runs (:240-251): x and y share the limits set once, z gets its own
+  auto pass = [](std::vector<P3>& c, int field, float lo, float hi) {
+    std::vector<P3> out;
+    out.reserve(c.size());
+    for (const P3& p : c) {
+      if (!std::isfinite(p.x) || !std::isfinite(p.y) || !std::isfinite(p.z)) continue;
+      const float v = field == 0 ? p.x : field == 1 ? p.y : p.z;
+      if (!std::isfinite(v)) continue;
+      if (v < lo || v > hi) continue;
+      out.push_back(p);
+    }
+    c.swap(out);
+  };
+  const float wlo = (float)(-sp->perception_window_size), whi = (float)(sp->perception_window_size);
+  pass(cloud, 0, wlo, whi);
+  pass(cloud, 1, wlo, whi);
+  pass(cloud, 2, 0.0f, (float)(sp->marking_height));
+  info->n_scan = (int64_t)n;
+  info->n_window = (int64_t)cloud.size();
+  info->ms_device = 0.f;
+  info->n_launches = 0;
+  // pcl::VoxelGrid (:253-256)
+  const float leaf = sp->leaf_size > 0.f ? sp->leaf_size : 0.1f;
+  const float inv = 1.0f / leaf;  // inverse_leaf_size_ = Ones / leaf_size_
+  std::vector<P3> out;
+  if (!cloud.empty()) {
+    float mn[3] = {std::numeric_limits<float>::max(), std::numeric_limits<float>::max(), std::numeric_limits<float>::max()};
+    float mx[3] = {-mn[0], -mn[1], -mn[2]};
+    for (const P3& p : cloud) {  // getMinMax3D
+      mn[0] = std::min(mn[0], p.x); mx[0] = std::max(mx[0], p.x);
+      mn[1] = std::min(mn[1], p.y); mx[1] = std::max(mx[1], p.y);
+      mn[2] = std::min(mn[2], p.z); mx[2] = std::max(mx[2], p.z);
+    }
+    const int64_t dx = (int64_t)((mx[0] - mn[0]) * inv) + 1, dy = (int64_t)((mx[1] - mn[1]) * inv) + 1,
+                  dz = (int64_t)((mx[2] - mn[2]) * inv) + 1;
+    if (dx * dy * dz > (int64_t)std::numeric_limits<int32_t>::max()) {
+      out = cloud;  // "Leaf size is too small for the input dataset": output = *input_
+    } else {
+      int min_b[3], max_b[3], div_b[3];
+      for (int a = 0; a < 3; ++a) {
+        min_b[a] = (int)std::floor(mn[a] * inv);
+        max_b[a] = (int)std::floor(mx[a] * inv);
+        div_b[a] = max_b[a] - min_b[a] + 1;
+      }
+      const int mul[3] = {1, div_b[0], div_b[0] * div_b[1]};
+      struct Ix { unsigned idx; unsigned pt; };
+      std::vector<Ix> iv;
+      iv.reserve(cloud.size());
+      for (size_t i = 0; i < cloud.size(); ++i) {
+        const int ijk0 = (int)(std::floor(cloud[i].x * inv) - (float)min_b[0]);
+        const int ijk1 = (int)(std::floor(cloud[i].y * inv) - (float)min_b[1]);
+        const int ijk2 = (int)(std::floor(cloud[i].z * inv) - (float)min_b[2]);
+        iv.push_back({(unsigned)(ijk0 * mul[0] + ijk1 * mul[1] + ijk2 * mul[2]), (unsigned)i});
+      }
+      auto less = [](const Ix& a, const Ix& b) { return a.idx < b.idx; };
+      if (order_mode == 1) std::sort(iv.begin(), iv.end(), less);
+      else std::stable_sort(iv.begin(), iv.end(), less);
+      for (size_t i = 0; i < iv.size();) {
+        size_t j = i;
+        float sx = 0.0f, sy = 0.0f, sz = 0.0f;  // AccumulatorXYZ: xyz = Zero; xyz += point
+        while (j < iv.size() && iv[j].idx == iv[i].idx) {
+          sx += cloud[iv[j].pt].x;
+          sy += cloud[iv[j].pt].y;
+          sz += cloud[iv[j].pt].z;
+          ++j;
+        }
+        const float fn = (float)(j - i);  // xyz / n
+        out.push_back({sx / fn, sy / fn, sz / fn});
+        i = j;
+      }
+    }
+  }
+  if (sp->is_local_planner) transform(out, pose_to_affine(global_from_base));  // :264-268
+  info->n_points = (int64_t)out.size();
+  if (out.size() > capacity) return B200LP_E_INVALID;
+  for (size_t i = 0; i < out.size(); ++i) {
+    out_xyz1[4 * i] = out[i].x;
+    out_xyz1[4 * i + 1] = out[i].y;
+    out_xyz1[4 * i + 2] = out[i].z;
+    out_xyz1[4 * i + 3] = 1.0f;
+  }
+  return B200LP_OK;
+}
+
 float lporacle_sinf(int mode, float x) { return (mode ? kLibm : kShared).sinf_(x); }
 float lporacle_cosf(int mode, float x) { return (mode ? kLibm : kShared).cosf_(x); }
 double lporacle_sin(int mode, double x) { return (mode ? kLibm : kShared).sin_(x); }

@@ -61,6 +61,13 @@ int lporacle_prune_plan(const double* global_plan7, size_t n, const double robot
                         b200lp_prune_info* info);
 int lporacle_path_blocked(lporacle_ctx* ctx, const float* pcl_xyzi, size_t n, double check_radius, b200lp_blocked* out);
 
+/* MultiLayerSpinningLidar::cbSensor's transform -> pass-through -> voxel filter -> transform,
+ * PCL's filters restated from their published algorithms (UNPINNED: PCL is not vendored under /root/reference).
+ * order_mode 0 = points of a voxel added in scan order (the device's order), 1 = in std::sort's (unstable) order. */
+int lporacle_sensor_observation(const void* scan, size_t n, size_t stride_bytes, const double base_from_sensor[7],
+                                const double global_from_base[7], const b200lp_sensor_params* params, int order_mode,
+                                float* out_xyz1, size_t capacity, b200lp_observation_info* info);
+
 /* Velocity samples exactly as initialise() leaves them in sample_params_ (xv,yv,thetav floats).
  * Returns the count; fills up to cap samples. */
 int lporacle_samples(lporacle_ctx* ctx, const b200lp_query* q, float* out_xyz, int cap);

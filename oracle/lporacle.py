@@ -40,6 +40,9 @@ _SYMS = {
     "lporacle_prune_plan": (C.c_int, [C.POINTER(C.c_double), C.c_size_t, C.POINTER(C.c_double), C.c_double, C.c_double,
                                       C.POINTER(C.c_double), C.POINTER(C.c_float), C.c_size_t, C.POINTER(abi.PruneInfo)]),
     "lporacle_path_blocked": (C.c_int, [_P, C.POINTER(C.c_float), C.c_size_t, C.c_double, C.POINTER(abi.Blocked)]),
+    "lporacle_sensor_observation": (C.c_int, [_P, C.c_size_t, C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                              C.POINTER(abi.SensorParams), C.c_int, C.POINTER(C.c_float), C.c_size_t,
+                                              C.POINTER(abi.ObservationInfo)]),
     "lporacle_samples": (C.c_int, [_P, C.POINTER(abi.Query), C.POINTER(C.c_float), C.c_int]),
     "lporacle_sinf": (C.c_float, [C.c_int, C.c_float]),
     "lporacle_cosf": (C.c_float, [C.c_int, C.c_float]),
@@ -199,6 +202,25 @@ def prune_plan(global_plan, robot_xyz, forward_distance, backward_distance, capa
         raise RuntimeError(f"lporacle_prune_plan: {rc}")
     n = info.n_prune if info.status == 0 else 0
     return info, poses[:n], pcl[:n]
+
+
+def sensor_observation(scan, base_from_sensor, global_from_base, window, marking_height, leaf=0.1, is_local_planner=True,
+                       order_mode=0):
+    """MultiLayerSpinningLidar::cbSensor's filter chain restated (lp_oracle.cpp). -> (ObservationInfo, (n,4) float32)."""
+    lib = load()
+    pts = np.ascontiguousarray(scan, np.float32)
+    if pts.ndim != 2 or pts.shape[1] not in (3, 4, 8):
+        raise ValueError("scan must be (n,3|4|8) float32")
+    sp = abi.SensorParams(float(window), float(marking_height), float(leaf), int(bool(is_local_planner)))
+    b2s = (C.c_double * 7)(*[float(v) for v in base_from_sensor])
+    g2b = (C.c_double * 7)(*[float(v) for v in global_from_base])
+    out = np.zeros((max(pts.shape[0], 1), 4), np.float32)
+    info = abi.ObservationInfo()
+    rc = lib.lporacle_sensor_observation(pts.ctypes.data_as(_P), pts.shape[0], pts.shape[1] * 4, b2s, g2b, C.byref(sp),
+                                         int(order_mode), out.ctypes.data_as(C.POINTER(C.c_float)), out.shape[0], C.byref(info))
+    if rc != 0:
+        raise RuntimeError(f"lporacle_sensor_observation: {rc}")
+    return info, out[:info.n_points]
 
 
 # ---------------------------------------------------------------------------------------------------------------------

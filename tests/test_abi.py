@@ -42,7 +42,8 @@ def test_ctypes_structs_match_the_c_layout(tmp_path):
     names = {"b200lp_limits": abi.Limits, "b200lp_params": abi.Params, "b200lp_critic": abi.Critic,
              "b200lp_grid_config": abi.GridConfig, "b200lp_query": abi.Query, "b200lp_result": abi.Result,
              "b200lp_traj_view": abi.TrajView, "b200lp_pose_view": abi.PoseView,
-             "b200lp_prune_info": abi.PruneInfo, "b200lp_blocked": abi.Blocked}
+             "b200lp_prune_info": abi.PruneInfo, "b200lp_blocked": abi.Blocked,
+             "b200lp_sensor_params": abi.SensorParams, "b200lp_observation_info": abi.ObservationInfo}
     prog = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     for cname, cls in names.items():
         prog.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
