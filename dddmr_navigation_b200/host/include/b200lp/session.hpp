@@ -66,6 +66,17 @@ class Session {
                               std::vector<double>& poses7, std::vector<float>& pcl_xyzi);
   b200lp_blocked pathBlocked(double check_radius);  // PathBlockedStrategy::selfMark
 
+  // ---- the observation producer in front of the cycle ----
+  // MultiLayerSpinningLidar::cbSensor's filter chain on the device; the result stays there as sensor `sensor`'s observation
+  b200lp_observation_info sensorObservation(int sensor, const pcl::PointCloud<pcl::PointXYZ>& scan,
+                                            const geometry_msgs::msg::TransformStamped& trans_b2s,
+                                            const geometry_msgs::msg::TransformStamped& trans_gbl2b, const b200lp_sensor_params& sp);
+  void readObservation(int sensor, pcl::PointCloud<pcl::PointXYZI>& out);  // Sensor::getObservation for host-side consumers
+  // StackedPerception::aggregateObservations: the sensors' observations are concatenated ON THE DEVICE and become the
+  // critics' cloud; `aggregate` receives the host copy other consumers read and is this cloud's identity from here on
+  // (handing the same object to setObservation / the critics' shared data does not upload anything again).
+  void aggregateObservations(const std::vector<int>& sensors, const pcl::PointCloud<pcl::PointXYZI>::Ptr& aggregate);
+
   // ---- generator side ----
   int trajectoryCount();
   void fillTrajectory(int id, base_trajectory::Trajectory& traj, bool with_points);
@@ -101,6 +112,7 @@ class Session {
 
   pcl::PointCloud<pcl::PointXYZI>::ConstPtr cloud_;  // kept alive: pointer identity is the freshness token
   bool cloud_uploaded_ = false;
+  bool cloud_from_device_ = false;  // cloud_ is the host copy of a device-side aggregate: the device already holds it
   b200lp_query query_{};
   std::vector<double> plan7_;
   std::vector<double> plan7_device_;  // what the device-side prune plan holds; launch() skips the upload when equal

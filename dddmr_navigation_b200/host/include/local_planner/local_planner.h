@@ -25,6 +25,48 @@ struct SharedData {
 };
 enum PerceptionOpinion { PASS = 0, PATH_BLOCKED_WAIT = 1, PATH_BLOCKED_REPLANNING = 2 };  // perception_3d/sensor.h
 
+// perception_3d::MultiLayerSpinningLidar reduced to the producer of the local planner's observation: the filter chain of
+// cbSensor (dddmr_perception_3d/plugins/multilayer_spinning_lidar.cpp:232-269; what pcl::fromROSMsg / the stitcher leave in
+// pcl_msg and the two tf lookups are handed in) runs on the device of the generator's session, and the observation stays
+// there; getObservation() (Sensor::getObservation) reads it back for host-side consumers. SURVEY.md §8(f) row 4.
+class MultiLayerSpinningLidar {
+ public:
+  MultiLayerSpinningLidar(const std::string& name, const std::string& traj_gen_name, int slot, double perception_window_size,
+                          double marking_height, bool is_local_planner)
+      : name_(name), traj_gen_name_(traj_gen_name), slot_(slot), perception_window_size_(perception_window_size),
+        marking_height_(marking_height), is_local_planner_(is_local_planner),
+        sensor_current_observation_(new pcl::PointCloud<pcl::PointXYZI>) {}
+  void cbSensor(const pcl::PointCloud<pcl::PointXYZ>& pcl_msg, const geometry_msgs::msg::TransformStamped& trans_b2s,
+                const geometry_msgs::msg::TransformStamped& trans_gbl2b);
+  pcl::PointCloud<pcl::PointXYZI>::Ptr getObservation();
+  const std::string& getName() const { return name_; }
+  const std::string& generatorName() const { return traj_gen_name_; }
+  int slot() const { return slot_; }
+  const b200lp_observation_info& lastInfo() const { return last_info_; }
+
+ private:
+  std::string name_, traj_gen_name_;
+  int slot_;
+  double perception_window_size_, marking_height_;
+  bool is_local_planner_, observation_stale_ = false;
+  pcl::PointCloud<pcl::PointXYZI>::Ptr sensor_current_observation_;
+  b200lp_observation_info last_info_{};
+};
+
+// perception_3d::StackedPerception::aggregateObservations (src/stacked_perception.cpp:128-140): the plugins' observations
+// are concatenated in plugin order — on the device, where the result is the critics' cloud of the next cycle; the host
+// copy lands in SharedData::aggregate_observation_ for the reference's other readers.
+class StackedPerception {
+ public:
+  explicit StackedPerception(const std::shared_ptr<SharedData>& shared_data) : shared_data_(shared_data) {}
+  void addPluginToVector(const std::shared_ptr<MultiLayerSpinningLidar>& plugin) { plugins_.push_back(plugin); }
+  void aggregateObservations();
+
+ private:
+  std::shared_ptr<SharedData> shared_data_;
+  std::vector<std::shared_ptr<MultiLayerSpinningLidar>> plugins_;
+};
+
 // perception_3d::PathBlockedStrategy (plugins/path_blocked_strategy.cpp): the `check_radius` parameter and selfMark(),
 // answered by the device against the voxel grid of the cloud the critics query.
 class PathBlockedStrategy {

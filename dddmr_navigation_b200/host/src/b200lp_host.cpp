@@ -261,12 +261,72 @@ void Session::uploadCloud(const pcl::PointCloud<pcl::PointXYZI>::ConstPtr& cloud
   const int rc = b200lp_set_cloud(ctx_, n ? (const void*)cloud->points.data() : nullptr, n, sizeof(pcl::PointXYZI));
   if (rc != B200LP_OK) raise(rc, "b200lp_set_cloud");
   cloud_uploaded_ = true;
+  cloud_from_device_ = false;
 }
 
 void Session::setObservation(const pcl::PointCloud<pcl::PointXYZI>::ConstPtr& cloud) {
   std::lock_guard<std::mutex> lk(mu_);
   ensureContext();
-  uploadCloud(cloud);
+  // the host copy of a device-side aggregate (aggregateObservations) is already where the kernels read it
+  if (!(cloud_from_device_ && cloud_uploaded_ && cloud && cloud.get() == cloud_.get())) uploadCloud(cloud);
+  launched_ = false;
+}
+
+namespace {
+void transform_to_array(const geometry_msgs::msg::TransformStamped& t, double out[7]) {
+  const auto& tr = t.transform;
+  const double v[7] = {tr.translation.x, tr.translation.y, tr.translation.z, tr.rotation.x, tr.rotation.y, tr.rotation.z, tr.rotation.w};
+  std::memcpy(out, v, sizeof(v));
+}
+}  // namespace
+
+b200lp_observation_info Session::sensorObservation(int sensor, const pcl::PointCloud<pcl::PointXYZ>& scan,
+                                                   const geometry_msgs::msg::TransformStamped& trans_b2s,
+                                                   const geometry_msgs::msg::TransformStamped& trans_gbl2b,
+                                                   const b200lp_sensor_params& sp) {
+  std::lock_guard<std::mutex> lk(mu_);
+  ensureContext();
+  double b2s[7], g2b[7];
+  transform_to_array(trans_b2s, b2s);
+  transform_to_array(trans_gbl2b, g2b);
+  b200lp_observation_info info{};
+  const int rc = b200lp_sensor_observation(ctx_, sensor, scan.points.empty() ? nullptr : (const void*)scan.points.data(),
+                                           scan.points.size(), sizeof(pcl::PointXYZ), b2s, g2b, &sp, &info);
+  if (rc != B200LP_OK) raise(rc, "b200lp_sensor_observation");
+  return info;
+}
+
+void Session::readObservation(int sensor, pcl::PointCloud<pcl::PointXYZI>& out) {
+  std::lock_guard<std::mutex> lk(mu_);
+  ensureContext();
+  size_t n = 0;
+  int rc = b200lp_read_observation(ctx_, sensor, nullptr, 0, sizeof(pcl::PointXYZI), &n);
+  if (rc != B200LP_OK && n == 0) raise(rc, "b200lp_read_observation");
+  out.points.assign(n, pcl::PointXYZI());
+  out.width = (uint32_t)n;
+  if (n) {
+    rc = b200lp_read_observation(ctx_, sensor, out.points.data(), n, sizeof(pcl::PointXYZI), &n);
+    if (rc != B200LP_OK) raise(rc, "b200lp_read_observation");
+  }
+}
+
+void Session::aggregateObservations(const std::vector<int>& sensors, const pcl::PointCloud<pcl::PointXYZI>::Ptr& aggregate) {
+  if (!aggregate) throw Error(B200LP_E_INVALID, "b200lp::Session::aggregateObservations: null aggregate cloud");
+  aggregate->points.clear();
+  for (int s : sensors) {  // the host copy, sensor by sensor (`*aggregate += *plugin->getObservation()`)
+    pcl::PointCloud<pcl::PointXYZI> one;
+    readObservation(s, one);
+    *aggregate += one;
+  }
+  std::lock_guard<std::mutex> lk(mu_);
+  std::vector<int32_t> ids(sensors.begin(), sensors.end());
+  size_t total = 0;
+  const int rc = b200lp_aggregate_observations(ctx_, ids.data(), (int)ids.size(), &total);
+  if (rc != B200LP_OK) raise(rc, "b200lp_aggregate_observations");
+  if (total != aggregate->points.size()) throw Error(B200LP_E_STATE, "b200lp::Session::aggregateObservations: host copy and device aggregate differ in size");
+  cloud_ = aggregate;
+  cloud_uploaded_ = true;
+  cloud_from_device_ = true;
   launched_ = false;
 }
 
@@ -620,6 +680,34 @@ struct RegisterPlugins {
 // the cycle driver (the caller of the path)
 // =====================================================================================================
 namespace perception_3d {
+void MultiLayerSpinningLidar::cbSensor(const pcl::PointCloud<pcl::PointXYZ>& pcl_msg,
+                                       const geometry_msgs::msg::TransformStamped& trans_b2s,
+                                       const geometry_msgs::msg::TransformStamped& trans_gbl2b) {
+  b200lp_sensor_params sp{};
+  sp.perception_window_size = perception_window_size_;
+  sp.marking_height = marking_height_;
+  sp.leaf_size = 0.1f;  // sor.setLeafSize(0.1f, 0.1f, 0.1f) (:254)
+  sp.is_local_planner = is_local_planner_ ? 1 : 0;
+  last_info_ = b200lp::Session::forGenerator(traj_gen_name_)->sensorObservation(slot_, pcl_msg, trans_b2s, trans_gbl2b, sp);
+  observation_stale_ = true;
+}
+
+pcl::PointCloud<pcl::PointXYZI>::Ptr MultiLayerSpinningLidar::getObservation() {
+  if (observation_stale_) {
+    b200lp::Session::forGenerator(traj_gen_name_)->readObservation(slot_, *sensor_current_observation_);
+    observation_stale_ = false;
+  }
+  return sensor_current_observation_;
+}
+
+void StackedPerception::aggregateObservations() {
+  shared_data_->aggregate_observation_.reset(new pcl::PointCloud<pcl::PointXYZI>);  // :130
+  if (plugins_.empty()) return;
+  std::vector<int> slots;
+  for (const auto& p : plugins_) slots.push_back(p->slot());
+  b200lp::Session::forGenerator(plugins_.front()->generatorName())->aggregateObservations(slots, shared_data_->aggregate_observation_);
+}
+
 void PathBlockedStrategy::selfMark(const std::string& traj_gen_name) {
   const b200lp_blocked b = b200lp::Session::forGenerator(traj_gen_name)->pathBlocked(check_radius_);
   prune_plan_blocked_ratio_ = b.ratio;

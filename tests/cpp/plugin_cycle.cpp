@@ -2,6 +2,11 @@
 // Local_Planner::computeVelocityCommand does (local_planner.cpp:482-621), and dumps what the caller sees so pytest can
 // compare it with the CPU oracle. Usage:
 //   plugin_cycle <params.yaml> <scenario.bin> <out_prefix> <generator_name> <early|late> [prune <fwd> <bwd> <check_radius>]
+//   plugin_cycle <params.yaml> <scenario.bin> <out_prefix> <generator_name> <early|late> scan <scans.bin> <window> <marking_height>
+// With `scan`, the scenario's cloud is ignored: the lidar scans of scans.bin (int64 n_sensors; per sensor int64 n,
+// float64 base_from_sensor[7], float32 points[n][4] in the sensor frame) go through the MultiLayerSpinningLidar::cbSensor
+// mirrors and StackedPerception::aggregateObservations before every cycle; .obs.f32 (n x 8) is the
+// host copy of the aggregate.
 // With `prune`, the scenario's plan is the GLOBAL plan: Local_Planner::setPlan + prunePlan run on the device and a
 // PathBlockedStrategy gives its opinion after scoring; .prune.f64 / .prunepcl.f32 are dumped too.
 // scenario.bin: int64 n_points, int64 n_plan, float32 points[n][8] (PointXYZI), float64 plan[m][7], float64 pose[7],
@@ -84,6 +89,40 @@ int main(int argc, char** argv) {
     mc->getSharedDataPtr()->heading_deviation_ = tail[11];
     lp.setGlobalPose(pose);
     lp.cbOdom(odom);
+    const bool scan_mode = argc >= 10 && std::string(argv[6]) == "scan";
+    std::vector<std::shared_ptr<perception_3d::MultiLayerSpinningLidar>> lidars;
+    std::vector<pcl::PointCloud<pcl::PointXYZ>> scans;
+    std::vector<geometry_msgs::msg::TransformStamped> mounts;
+    perception_3d::StackedPerception stacked(perception);
+    auto observe = [&] {  // what the sensor callbacks + the perception loop do between two planner cycles
+      for (size_t k = 0; k < lidars.size(); ++k) lidars[k]->cbSensor(scans[k], mounts[k], pose);
+      stacked.aggregateObservations();
+    };
+    if (scan_mode) {
+      const std::string sb = slurp(argv[7]);
+      const char* q = sb.data();
+      int64_t n_sensors;
+      std::memcpy(&n_sensors, q, 8); q += 8;
+      for (int64_t k = 0; k < n_sensors; ++k) {
+        int64_t n;
+        double m[7];
+        std::memcpy(&n, q, 8); q += 8;
+        std::memcpy(m, q, 56); q += 56;
+        pcl::PointCloud<pcl::PointXYZ> sc_k;
+        sc_k.points.resize((size_t)n);
+        std::memcpy((void*)sc_k.points.data(), q, (size_t)n * 16); q += n * 16;
+        sc_k.is_dense = false;
+        scans.push_back(sc_k);
+        geometry_msgs::msg::TransformStamped t;
+        t.transform.translation.x = m[0]; t.transform.translation.y = m[1]; t.transform.translation.z = m[2];
+        t.transform.rotation.x = m[3]; t.transform.rotation.y = m[4]; t.transform.rotation.z = m[5]; t.transform.rotation.w = m[6];
+        mounts.push_back(t);
+        lidars.push_back(std::make_shared<perception_3d::MultiLayerSpinningLidar>("lidar" + std::to_string(k), gen, (int)k,
+                                                                                 std::atof(argv[8]), std::atof(argv[9]), true));
+        stacked.addPluginToVector(lidars.back());
+      }
+      observe();
+    }
     const bool prune = argc >= 10 && std::string(argv[6]) == "prune";
     std::shared_ptr<perception_3d::PathBlockedStrategy> blocked;
     if (prune) {
@@ -101,7 +140,8 @@ int main(int argc, char** argv) {
     auto session = b200lp::Session::forGenerator(gen);
     const int launches_first = session->launchesThisCycle();
     // aggregateObservations() builds a fresh cloud object every cycle (stacked_perception.cpp:128-140)
-    perception->aggregate_observation_.reset(new pcl::PointCloud<pcl::PointXYZI>(*perception->aggregate_observation_));
+    if (scan_mode) observe();
+    else perception->aggregate_observation_.reset(new pcl::PointCloud<pcl::PointXYZI>(*perception->aggregate_observation_));
     base_trajectory::Trajectory best2;
     const dddmr_sys_core::PlannerState state2 = lp.computeVelocityCommand(gen, best2);
     const int launches_second = session->launchesThisCycle();
@@ -127,6 +167,12 @@ int main(int argc, char** argv) {
     dump(out + ".pcl.f32", pcl3);
     dump(out + ".cuboid.f32", cub);
     dump(out + ".aabb.f32", aabb);
+    if (scan_mode) {
+      std::vector<float> ob;
+      for (const auto& pt : perception->aggregate_observation_->points)
+        ob.insert(ob.end(), {pt.x, pt.y, pt.z, pt.pad_, pt.intensity, pt.pad2_[0], pt.pad2_[1], pt.pad2_[2]});
+      dump(out + ".obs.f32", ob);
+    }
     if (prune) {
       std::vector<double> pp;
       std::vector<float> pc;
@@ -145,6 +191,11 @@ int main(int argc, char** argv) {
       << "\nn_traj=" << lp.trajectories_->size() << "\nlaunches_first=" << launches_first
       << "\nlaunches_second=" << launches_second << "\ndevice_best_id=" << r.best_id << "\ndevice_best_cost=" << r.best_cost
       << "\ndevice_n_samples=" << r.n_samples << "\ndevice_n_poses=" << r.n_poses << "\n";
+    if (scan_mode) {
+      s << "n_observation=" << perception->aggregate_observation_->points.size() << "\n";
+      for (size_t k = 0; k < lidars.size(); ++k)
+        s << "sensor" << k << "_n_points=" << lidars[k]->lastInfo().n_points << "\nsensor" << k << "_n_window=" << lidars[k]->lastInfo().n_window << "\n";
+    }
     if (prune) s << "blocked_ratio=" << blocked->getBlockedRatio() << "\nblocked_opinion=" << (int)blocked->getOpinion() << "\n";
     b200lp::Session::resetAll();
   } catch (const b200lp::Error& e) {

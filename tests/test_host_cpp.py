@@ -182,3 +182,44 @@ def test_plugin_cycle_with_device_prune_plan_and_path_blocked_opinion(driver, tm
     # PATH_BLOCKED_WAIT = 5 overrides the trajectory verdict (local_planner.cpp:597-607)
     assert int(s["state"]) == (5 if expect_blocked else (4 if r.best_id >= 0 else 2))
     assert int(s["launches_first"]) == 1 and int(s["launches_second"]) == 1
+
+
+@pytest.mark.gpu
+def test_plugin_cycle_fed_by_the_device_side_observation_producer(driver, tmp_path):
+    """SURVEY.md §8(f) row 4 through the host layer: two MultiLayerSpinningLidar mirrors run cbSensor's filter chain on
+    the device, StackedPerception::aggregateObservations concatenates there, and the cycle scores against that cloud with
+    one launch and no cloud upload; the host copy in SharedData::aggregate_observation_ equals the oracle's restatement."""
+    from oracle import lporacle as O
+    sc = synth.playground()
+    gen = "differential_drive_simple"
+    yaml, scb = _write_case(str(tmp_path), sc.config, gen, np.zeros((0, 8), np.float32), sc.plan, sc.pose, sc.twist)
+    scans, expect = [], []
+    for seed, mount in ((21, 0.25), (22, -0.2)):
+        scan, b2s, _ = synth.lidar_scan(n_beams=32, n_azimuth=1024, seed=seed, room=(16.0, 12.0, 2.5), n_pillars=12)
+        b2s = b2s.copy()
+        b2s[0] = mount
+        b2s[2] -= 0.15
+        scans.append((scan, b2s))
+        expect.append(O.sensor_observation(scan, b2s, np.asarray(sc.pose, np.float64), 6.0, 1.2)[1])
+    sb = str(tmp_path / "scans.bin")
+    with open(sb, "wb") as f:
+        f.write(struct.pack("<q", len(scans)))
+        for scan, b2s in scans:
+            f.write(struct.pack("<q", scan.shape[0]))
+            f.write(np.asarray(b2s, np.float64).tobytes())
+            f.write(np.ascontiguousarray(scan, np.float32).tobytes())
+    prefix = str(tmp_path / "out")
+    p = subprocess.run([driver, yaml, scb, prefix, gen, "early", "scan", sb, "6.0", "1.2"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr
+    s, traj, _ = _load(prefix)
+    host = np.concatenate(expect)
+    obs = np.fromfile(prefix + ".obs.f32", np.float32).reshape(-1, 8)
+    assert int(s["n_observation"]) == host.shape[0] and int(s["sensor0_n_points"]) == expect[0].shape[0]
+    assert np.array_equal(obs[:, :4].view(np.uint32), host.view(np.uint32)) and not obs[:, 4:].any()
+    ora = O.OraclePlanner(sc.config, O.MATH_SHARED, O.INDEX_GRID)
+    ora.set_cloud(host)
+    ora.set_plan(sc.plan)
+    r = ora.plan(make_query(sc.pose, sc.twist))
+    assert np.array_equal(traj[:, 0], ora.read_trajectories()["cost"])
+    assert int(s["best_id"]) == r.best_id == int(s["best_id2"]) and 0 < r.n_collided < r.n_traj
+    assert int(s["launches_first"]) == 1 and int(s["launches_second"]) == 1
