@@ -4,6 +4,7 @@
 //   plan cycle : prep_kernel (velocity sampling + trajectory list) -> plan_kernel (fused rollout,
 //                obstacle query, critics, block argmin, last-block final argmin)
 //   read-back  : poses_kernel, count_radius_kernel (diagnostics / parity / roofline accounting)
+//   either side: prune_kernel, blocked_kernel here; the lidar observation producer in lp_observe.cuh
 #pragma once
 #include "lp_device.cuh"
 
