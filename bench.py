@@ -426,10 +426,10 @@ def main():
     clocks = sampler.stop()
     t_e2e = sum(e2e_ms) / 1e3
     if mode == "fleet":
-        h2d = n_pts * stride + f_plans.nbytes + len(qs) * ctypes.sizeof(abi.Query)
+        h2d = lp.last_upload()["h2d_bytes"] + f_plans.nbytes + len(qs) * ctypes.sizeof(abi.Query)
         d2h = len(qs) * (56 + 32) + 32
     else:
-        h2d = n_pts * stride + plan.nbytes + ctypes.sizeof(q)
+        h2d = lp.last_upload()["h2d_bytes"] + plan.nbytes + ctypes.sizeof(q)
         d2h = 56 + 32 + 32  # result + meta + grid bounds
 
     # ---------------- reductions over ranks (max time, summed poses) ----------------
@@ -485,7 +485,9 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * t_e2e / args.steps,
                 "stages_ms_per_step": {k: v / args.steps for k, v in e2e_stage.items()},
-                "what": "set_cloud (pinned PointXYZI upload + grid build) + set_plan + plan, host wall clock, every step"},
+                "host_cloud_bytes_per_step": n_pts * stride, "host_pack_threads": lp.last_upload()["pack_threads"],
+                "what": ("set_cloud (PointXYZI cloud in pinned host memory -> packed to 12 B/point by host_pack_threads host threads -> "
+                         "upload + grid build) + set_plan + plan, host wall clock, every step")},
         "e2e_map_resident": {"value": poses_per_step * args.steps / (sum(wall_ms) / 1e3), "unit": UNIT,
                              "ms_per_step": sum(wall_ms) / len(wall_ms), "p50_ms": statistics.median(wall_ms),
                              "what": "b200lp_plan only (query+plan upload, kernels, result read-back), host wall clock, rank 0"},

@@ -131,6 +131,7 @@ SYMBOLS = {
                                 C.POINTER(Critic), C.c_int, C.POINTER(GridConfig)]),
     "b200lp_destroy": (None, [_P]),
     "b200lp_set_cloud": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t]),
+    "b200lp_last_upload": (C.c_int, [_P, C.POINTER(C.c_size_t), C.POINTER(C.c_int32)]),
     "b200lp_set_cloud_device": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t]),
     "b200lp_set_plan": (C.c_int, [_P, C.POINTER(C.c_double), C.c_size_t]),
     "b200lp_plan": (C.c_int, [_P, C.POINTER(Query), C.POINTER(Result)]),

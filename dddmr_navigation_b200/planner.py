@@ -260,6 +260,12 @@ class LocalPlanner:
         """set_cloud from a raw host address (e.g. a pinned buffer)."""
         self._ck(self.lib.b200lp_set_cloud(self.h, _P(host_ptr), n, stride))
 
+    def last_upload(self) -> dict:
+        """Bytes the last set_cloud copied host -> device and the host threads that packed them (0: copied as is)."""
+        b, t = C.c_size_t(), C.c_int32()
+        self._ck(self.lib.b200lp_last_upload(self.h, C.byref(b), C.byref(t)))
+        return {"h2d_bytes": b.value, "pack_threads": t.value}
+
     def launch_count(self) -> int:
         return int(self.lib.b200lp_launch_count(self.h))
 
