@@ -81,8 +81,29 @@ struct PinBuf {
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kPackChunks = 8;
 
-inline void pack_xyz(const char* src, size_t stride, float* dst, size_t i0, size_t i1) {
+struct alignas(64) HostBounds {  // one per packing thread (own cache line)
+  float mn[4], mx[4];
+  size_t n_finite;
+  void reset() {
+    for (int a = 0; a < 4; ++a) { mn[a] = 3.402823466e+38f; mx[a] = -3.402823466e+38f; }
+    n_finite = 0;
+  }
+};
+
+// Packs points [i0, i1) and folds the bounds of the finite ones into hb — the same reduction bounds_pack_kernel does on
+// the device for clouds that are not packed on the host (min / max of floats: exact in any order).
+inline void pack_xyz(const char* src, size_t stride, float* dst, size_t i0, size_t i1, HostBounds& hb) {
   size_t i = i0;
+  __m128 mn = _mm_loadu_ps(hb.mn), mx = _mm_loadu_ps(hb.mx);
+  size_t cnt = hb.n_finite;
+  const __m128 zero = _mm_setzero_ps();
+  auto fold = [&](__m128 p) {  // lanes x, y, z of one point; lane 3 is padding and is ignored everywhere
+    if ((_mm_movemask_ps(_mm_cmpeq_ps(_mm_sub_ps(p, p), zero)) & 7) == 7) {
+      mn = _mm_min_ps(mn, p);
+      mx = _mm_max_ps(mx, p);
+      ++cnt;
+    }
+  };
   if (((uintptr_t)(dst + i * 3) & 15) == 0) {
     for (; i + 4 <= i1; i += 4) {  // 4 points -> 3 x 16 bytes, written around the cache (the DMA engine is the only reader)
       const char* sp = src + i * stride;
@@ -97,6 +118,15 @@ inline void pack_xyz(const char* src, size_t stride, float* dst, size_t i0, size
       _mm_stream_ps(o, o0);
       _mm_stream_ps(o + 4, o1);
       _mm_stream_ps(o + 8, o2);
+      // x - x is 0 for finite x and NaN otherwise: one test for the four points, the per-point path only when it fails
+      const __m128 nf = _mm_add_ps(_mm_add_ps(_mm_sub_ps(a, a), _mm_sub_ps(b, b)), _mm_add_ps(_mm_sub_ps(c, c), _mm_sub_ps(d, d)));
+      if ((_mm_movemask_ps(_mm_cmpeq_ps(nf, zero)) & 7) == 7) {
+        mn = _mm_min_ps(_mm_min_ps(mn, a), _mm_min_ps(_mm_min_ps(b, c), d));
+        mx = _mm_max_ps(_mm_max_ps(mx, a), _mm_max_ps(_mm_max_ps(b, c), d));
+        cnt += 4;
+      } else {
+        fold(a); fold(b); fold(c); fold(d);
+      }
     }
   }
   for (; i < i1; ++i) {
@@ -105,14 +135,19 @@ inline void pack_xyz(const char* src, size_t stride, float* dst, size_t i0, size
     o[0] = sp[0];
     o[1] = sp[1];
     o[2] = sp[2];
+    fold(_mm_set_ps(0.f, sp[2], sp[1], sp[0]));
   }
   _mm_sfence();
+  _mm_storeu_ps(hb.mn, mn);
+  _mm_storeu_ps(hb.mx, mx);
+  hb.n_finite = cnt;
 }
 
 class PackPool {
  public:
   explicit PackPool(int threads) : T_(threads) {
     for (int c = 0; c < kPackChunks; ++c) done_[c].store(0);
+    bounds_.resize((size_t)T_);
     for (int w = 0; w < T_; ++w) th_.emplace_back([this, w] { run(w); });
   }
   ~PackPool() {
@@ -140,6 +175,16 @@ class PackPool {
   void wait_chunk(int c) const {  // a chunk takes tens of microseconds: spin
     while (done_[c].load(std::memory_order_acquire) != T_) __builtin_ia32_pause();
   }
+  // bounds of the finite points of the whole cloud; valid once the last chunk has been waited for
+  HostBounds bounds() const {
+    HostBounds r;
+    r.reset();
+    for (const HostBounds& b : bounds_) {
+      for (int a = 0; a < 3; ++a) { r.mn[a] = std::min(r.mn[a], b.mn[a]); r.mx[a] = std::max(r.mx[a], b.mx[a]); }
+      r.n_finite += b.n_finite;
+    }
+    return r;
+  }
 
  private:
   void run(int w) {
@@ -151,10 +196,11 @@ class PackPool {
         seen = gen_;
         if (stop_) return;
       }
+      bounds_[(size_t)w].reset();
       for (int c = 0; c < kPackChunks; ++c) {
         const size_t c0 = bound(c), c1 = bound(c + 1), len = c1 - c0;
         const size_t a = c0 + ((len * (size_t)w / T_) & ~(size_t)3), b = w == T_ - 1 ? c1 : c0 + ((len * (size_t)(w + 1) / T_) & ~(size_t)3);
-        if (b > a) pack_xyz(src_, stride_, dst_, a, b);
+        if (b > a) pack_xyz(src_, stride_, dst_, a, b, bounds_[(size_t)w]);
         done_[c].fetch_add(1, std::memory_order_release);
       }
     }
@@ -169,6 +215,7 @@ class PackPool {
   size_t stride_ = 0, n_ = 0;
   float* dst_ = nullptr;
   std::atomic<int> done_[kPackChunks];
+  std::vector<HostBounds> bounds_;
 };
 
 int pack_threads_wanted() {
@@ -331,103 +378,15 @@ int traj_cap(const b200lp_params& P) {
 #endif
 constexpr int kUploadChunks = B200LP_UPLOAD_CHUNKS;  // <= 8 (chunk_ev)
 
-// Brings the cloud to the device and builds the voxel grid + summed-volume table.
-//   src == nullptr : the raw cloud is already in d_raw (or n == 0)
-//   otherwise      : `src` (host, or device when on_device) is copied in kUploadChunks pieces on the copy stream while
-//                    bounds_pack_kernel works through the pieces that have arrived on the main stream.
-int build_grid(b200lp_ctx* ctx, const void* src, size_t n, size_t stride, bool on_device) {
-  const int sms = sm_count_of(ctx->device);
+// Grid geometry from the bounds of the finite points: cell sizes (coarsened until the dense grid fits max_cells), dims,
+// origin. Returns the number of cells.
+size_t size_grid(b200lp_ctx* ctx, const float mn[3], const float mx[3], size_t n_finite) {
   GridDev& g = ctx->grid;
-  g.n_raw = (uint32_t)n;
-  g.n_kept = 0;
-  g.nx = g.ny = g.nz = 1;
-  g.org[0] = g.org[1] = g.org[2] = 0.f;
-  g.inv_xy = g.inv_z = 1.f;
-  g.cmax = 1.f;
   float cxy = ctx->gcfg.cell_xy > 0.f ? ctx->gcfg.cell_xy : 0.2f;
   float cz = ctx->gcfg.cell_z > 0.f ? ctx->gcfg.cell_z : 0.4f;
   const uint32_t max_cells = ctx->gcfg.max_cells ? ctx->gcfg.max_cells : (1u << 26);
-
-  CK(ctx->d_bounds.reserve(1));
-  CK(ctx->h_bounds.reserve(1));
-  CK(ctx->d_total.reserve(1));
-  CK(ctx->d_packed.reserve(std::max<size_t>(n, 1)));
-  BoundsDev init;
-  for (int a = 0; a < 3; ++a) {
-    init.mn[a] = 0xffffffffu;
-    init.mx[a] = 0u;
-  }
-  init.n_finite = 0;
-  init.pad = 0;
-  *ctx->h_bounds.p = init;
-  CK(cudaEventRecord(ctx->cev[0], ctx->stream));
-  CK(cudaMemcpyAsync(ctx->d_bounds.p, ctx->h_bounds.p, sizeof(BoundsDev), cudaMemcpyHostToDevice, ctx->stream));
-  ctx->pack_threads_used = 0;
-  // large host clouds with padding between the points: pack on the host, upload 12 bytes per point (see PackPool)
-  bool packing = false;
-  if (src && !on_device && stride >= 16 && n * stride >= ((size_t)8 << 20)) {
-    if (!ctx->pack_pool) {
-      const int t = pack_threads_wanted();
-      if (t > 0) ctx->pack_pool = new (std::nothrow) PackPool(t);
-    }
-    packing = ctx->pack_pool != nullptr && ctx->h_stage.reserve(n * 3) == cudaSuccess;
-  }
-  if (packing) {
-    PackPool& pool = *ctx->pack_pool;
-    pool.start((const char*)src, stride, ctx->h_stage.p, n);
-    ctx->pack_threads_used = pool.threads();
-    stride = 12;  // what d_raw holds from here on
-    ctx->raw_stride = 12;
-    cudaError_t pe = cudaStreamWaitEvent(ctx->copy_stream, ctx->cev[0], 0);
-    for (int c = 0; c < kPackChunks; ++c) {
-      const size_t i0 = pool.bound(c), i1 = pool.bound(c + 1);
-      pool.wait_chunk(c);  // also on the error path: the workers read the caller's buffer until the last chunk is packed
-      if (pe != cudaSuccess) continue;
-      if (i1 > i0) {
-        pe = cudaMemcpyAsync(ctx->d_raw.p + i0 * 12, ctx->h_stage.p + i0 * 3, (i1 - i0) * 12, cudaMemcpyHostToDevice, ctx->copy_stream);
-        if (pe == cudaSuccess) pe = cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream);
-        if (pe == cudaSuccess) pe = cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[c], 0);
-      }
-      if (pe == cudaSuccess && c == kPackChunks - 1) pe = cudaEventRecord(ctx->cev[1], ctx->stream);  // everything has arrived
-      if (pe == cudaSuccess && i1 > i0) {
-        bounds_pack_kernel<<<grid_blocks(i1 - i0, 256, sms), 256, 0, ctx->stream>>>(ctx->d_raw.p, i0, i1, 12, ctx->d_packed.p, ctx->d_bounds.p);
-        ++ctx->launches;
-      }
-    }
-    if (pe != cudaSuccess) return ctx->fail(B200LP_E_CUDA, "set_cloud (packing upload): %s", cudaGetErrorString(pe));
-  } else if (n) {
-    const int chunks = (src && n >= (size_t)kUploadChunks * 65536) ? kUploadChunks : 1;
-    // one piece: plain copy on the main stream; several: on the copy stream, each piece handed over by an event
-    cudaStream_t cs = chunks > 1 ? ctx->copy_stream : ctx->stream;
-    if (src && chunks > 1) CK(cudaStreamWaitEvent(cs, ctx->cev[0], 0));  // the copy may not overtake earlier work on d_raw
-    for (int c = 0; c < chunks; ++c) {
-      const size_t i0 = n * c / chunks, i1 = n * (c + 1) / chunks;
-      if (src) {
-        CK(cudaMemcpyAsync(ctx->d_raw.p + i0 * stride, (const char*)src + i0 * stride, (i1 - i0) * stride,
-                           on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, cs));
-        if (chunks > 1) {
-          CK(cudaEventRecord(ctx->chunk_ev[c], cs));
-          CK(cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[c], 0));
-        }
-      }
-      if (c == chunks - 1) CK(cudaEventRecord(ctx->cev[1], ctx->stream));  // everything has arrived
-      bounds_pack_kernel<<<grid_blocks(i1 - i0, 256, sms), 256, 0, ctx->stream>>>(ctx->d_raw.p, i0, i1, stride, ctx->d_packed.p,
-                                                                                  ctx->d_bounds.p);
-      ++ctx->launches;
-    }
-  } else {
-    CK(cudaEventRecord(ctx->cev[1], ctx->stream));
-  }
-  CK(cudaMemcpyAsync(ctx->h_bounds.p, ctx->d_bounds.p, sizeof(BoundsDev), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));  // the host needs the bounds to size the grid; the caller's buffer is free from here on
-  const BoundsDev b = *ctx->h_bounds.p;
   size_t n_cells = 1;
-  if (b.n_finite) {
-    float mn[3], mx[3];
-    for (int a = 0; a < 3; ++a) {
-      mn[a] = ord2f(b.mn[a]);
-      mx[a] = ord2f(b.mx[a]);
-    }
+  if (n_finite) {
     for (;;) {
       const double nx = std::floor(((double)mx[0] - mn[0]) / cxy) + 1, ny = std::floor(((double)mx[1] - mn[1]) / cxy) + 1,
                    nz = std::floor(((double)mx[2] - mn[2]) / cz) + 1;
@@ -448,11 +407,122 @@ int build_grid(b200lp_ctx* ctx, const void* src, size_t n, size_t stride, bool o
     float cm = 1.f;
     for (int a = 0; a < 3; ++a) cm = std::max(cm, std::max(std::fabs(mn[a]), std::fabs(mx[a])));
     g.cmax = cm;
-    g.n_kept = b.n_finite;
+    g.n_kept = (uint32_t)n_finite;
     n_cells = (size_t)g.nx * g.ny * g.nz;
   }
   ctx->cell_xy_used = cxy;
   ctx->cell_z_used = cz;
+  return n_cells;
+}
+
+// Brings the cloud to the device and builds the voxel grid + summed-volume table.
+//   src == nullptr : the raw cloud is already in d_raw (or n == 0)
+//   otherwise      : `src` (host, or device when on_device) is copied in pieces on the copy stream, overlapped with the
+//                    first pass over the pieces that have arrived on the main stream. Two ways:
+//     packing upload (large padded host clouds): host threads pack x,y,z into pinned staging AND reduce the bounds, so the
+//       grid is sized on the host without a device round trip, hist_kernel runs per piece under the rest of the upload,
+//       and the call returns when the caller's buffer has been read — nothing waits for the device;
+//     plain upload: bounds_pack_kernel per piece (bounds + 16-byte records on the device), one host round trip for the
+//       bounds, then the histogram over the whole cloud.
+int build_grid(b200lp_ctx* ctx, const void* src, size_t n, size_t stride, bool on_device) {
+  const int sms = sm_count_of(ctx->device);
+  GridDev& g = ctx->grid;
+  g.n_raw = (uint32_t)n;
+  g.n_kept = 0;
+  g.nx = g.ny = g.nz = 1;
+  g.org[0] = g.org[1] = g.org[2] = 0.f;
+  g.inv_xy = g.inv_z = 1.f;
+  g.cmax = 1.f;
+  CK(ctx->d_total.reserve(1));
+  CK(cudaEventRecord(ctx->cev[0], ctx->stream));
+  ctx->pack_threads_used = 0;
+  // large host clouds with padding between the points: pack on the host, upload 12 bytes per point (see PackPool)
+  bool packing = false;
+  if (src && !on_device && stride >= 16 && n * stride >= ((size_t)8 << 20)) {
+    if (!ctx->pack_pool) {
+      const int t = pack_threads_wanted();
+      if (t > 0) ctx->pack_pool = new (std::nothrow) PackPool(t);
+    }
+    // the staging buffer may still be feeding the copies of the previous cloud
+    packing = ctx->pack_pool != nullptr && cudaStreamSynchronize(ctx->copy_stream) == cudaSuccess &&
+              ctx->h_stage.reserve(n * 3) == cudaSuccess;
+  }
+  const char* rec = nullptr;  // what the histogram / scatter passes read, and its stride
+  size_t rec_stride = 0;
+  size_t n_cells = 1;
+  bool hist_per_chunk = false;
+  size_t chunk_bound[kPackChunks + 1] = {0};
+  if (packing) {
+    PackPool& pool = *ctx->pack_pool;
+    pool.start((const char*)src, stride, ctx->h_stage.p, n);
+    ctx->pack_threads_used = pool.threads();
+    ctx->raw_stride = 12;  // what d_raw holds from here on
+    cudaError_t pe = cudaStreamWaitEvent(ctx->copy_stream, ctx->cev[0], 0);  // the copies may not overtake earlier work on d_raw
+    for (int c = 0; c < kPackChunks; ++c) {
+      const size_t i0 = pool.bound(c), i1 = pool.bound(c + 1);
+      chunk_bound[c] = i0;
+      chunk_bound[c + 1] = i1;
+      pool.wait_chunk(c);  // also on the error path: the workers read the caller's buffer until the last chunk is packed
+      if (pe != cudaSuccess || i1 == i0) continue;
+      pe = cudaMemcpyAsync(ctx->d_raw.p + i0 * 12, ctx->h_stage.p + i0 * 3, (i1 - i0) * 12, cudaMemcpyHostToDevice, ctx->copy_stream);
+      if (pe == cudaSuccess) pe = cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream);
+    }
+    if (pe != cudaSuccess) return ctx->fail(B200LP_E_CUDA, "set_cloud (packing upload): %s", cudaGetErrorString(pe));
+    // the caller's buffer is free from here on, and the bounds are already on the host
+    const HostBounds hb = pool.bounds();
+    n_cells = size_grid(ctx, hb.mn, hb.mx, hb.n_finite);
+    rec = ctx->d_raw.p;
+    rec_stride = 12;
+    hist_per_chunk = true;
+  } else {
+    CK(ctx->d_bounds.reserve(1));
+    CK(ctx->h_bounds.reserve(1));
+    CK(ctx->d_packed.reserve(std::max<size_t>(n, 1)));
+    BoundsDev init;
+    for (int a = 0; a < 3; ++a) {
+      init.mn[a] = 0xffffffffu;
+      init.mx[a] = 0u;
+    }
+    init.n_finite = 0;
+    init.pad = 0;
+    *ctx->h_bounds.p = init;
+    CK(cudaMemcpyAsync(ctx->d_bounds.p, ctx->h_bounds.p, sizeof(BoundsDev), cudaMemcpyHostToDevice, ctx->stream));
+    if (n) {
+      const int chunks = (src && n >= (size_t)kUploadChunks * 65536) ? kUploadChunks : 1;
+      // one piece: plain copy on the main stream; several: on the copy stream, each piece handed over by an event
+      cudaStream_t cs = chunks > 1 ? ctx->copy_stream : ctx->stream;
+      if (src && chunks > 1) CK(cudaStreamWaitEvent(cs, ctx->cev[0], 0));  // the copy may not overtake earlier work on d_raw
+      for (int c = 0; c < chunks; ++c) {
+        const size_t i0 = n * c / chunks, i1 = n * (c + 1) / chunks;
+        if (src) {
+          CK(cudaMemcpyAsync(ctx->d_raw.p + i0 * stride, (const char*)src + i0 * stride, (i1 - i0) * stride,
+                             on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, cs));
+          if (chunks > 1) {
+            CK(cudaEventRecord(ctx->chunk_ev[c], cs));
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[c], 0));
+          }
+        }
+        if (c == chunks - 1) CK(cudaEventRecord(ctx->cev[1], ctx->stream));  // everything has arrived
+        bounds_pack_kernel<<<grid_blocks(i1 - i0, 256, sms), 256, 0, ctx->stream>>>(ctx->d_raw.p, i0, i1, stride, ctx->d_packed.p,
+                                                                                    ctx->d_bounds.p);
+        ++ctx->launches;
+      }
+    } else {
+      CK(cudaEventRecord(ctx->cev[1], ctx->stream));
+    }
+    CK(cudaMemcpyAsync(ctx->h_bounds.p, ctx->d_bounds.p, sizeof(BoundsDev), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));  // the host needs the bounds to size the grid; the caller's buffer is free from here on
+    const BoundsDev b = *ctx->h_bounds.p;
+    float mn[3] = {0.f, 0.f, 0.f}, mx[3] = {0.f, 0.f, 0.f};
+    if (b.n_finite)
+      for (int a = 0; a < 3; ++a) {
+        mn[a] = ord2f(b.mn[a]);
+        mx[a] = ord2f(b.mx[a]);
+      }
+    n_cells = size_grid(ctx, mn, mx, b.n_finite);
+    rec = (const char*)ctx->d_packed.p;
+    rec_stride = 16;
+  }
   const int nb = (int)((n_cells + kScanItems - 1) / kScanItems);
   CK(ctx->d_cell_start.reserve(n_cells + 1));
   CK(ctx->d_fill.reserve(n_cells + 1));
@@ -465,17 +535,30 @@ int build_grid(b200lp_ctx* ctx, const void* src, size_t n, size_t stride, bool o
   g.pts = ctx->d_pts.p;
   g.cell_start = ctx->d_cell_start.p;
   g.sat = ctx->d_sat.p;
+  if (hist_per_chunk) {  // every piece is counted as soon as it has landed; only the last one is not hidden by the upload
+    for (int c = 0; c < kPackChunks; ++c) {
+      const size_t i0 = chunk_bound[c], i1 = chunk_bound[c + 1];
+      if (i1 > i0) CK(cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[c], 0));
+      if (c == kPackChunks - 1) CK(cudaEventRecord(ctx->cev[1], ctx->stream));  // everything has arrived
+      if (i1 > i0 && g.n_kept) {
+        hist_kernel<<<grid_blocks(i1 - i0, 256, sms), 256, 0, ctx->stream>>>(rec, rec_stride, i0, i1, g, ctx->d_cell_start.p);
+        ++ctx->launches;
+      }
+    }
+  } else if (g.n_kept) {
+    hist_kernel<<<grid_blocks(n, 256, sms), 256, 0, ctx->stream>>>(rec, rec_stride, 0, n, g, ctx->d_cell_start.p);
+    ++ctx->launches;
+  }
   if (g.n_kept) {
-    hist_kernel<<<grid_blocks(n, 256, sms), 256, 0, ctx->stream>>>(ctx->d_packed.p, n, g, ctx->d_cell_start.p);
     scan_block_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_cell_start.p, n_cells, ctx->d_block_sums.p);
     scan_sums_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_block_sums.p, nb, ctx->d_total.p);
     scan_add_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_cell_start.p, n_cells, ctx->d_block_sums.p, ctx->d_total.p,
                                                  ctx->d_fill.p);
-    scatter_kernel<<<grid_blocks(n, 256, sms), 256, 0, ctx->stream>>>(ctx->d_packed.p, n, g, ctx->d_fill.p, ctx->d_pts.p);
+    scatter_kernel<<<grid_blocks(n, 256, sms), 256, 0, ctx->stream>>>(rec, rec_stride, n, g, ctx->d_fill.p, ctx->d_pts.p);
     const size_t ny_threads = ((size_t)g.nx + 1) * (size_t)g.nz, nz_threads = ((size_t)g.nx + 1) * ((size_t)g.ny + 1);
     sat_y_kernel<<<(unsigned)((ny_threads * 32 + 255) / 256), 256, 0, ctx->stream>>>(g, ctx->d_sat.p);
     sat_z_kernel<<<(unsigned)((nz_threads + 255) / 256), 256, 0, ctx->stream>>>(g, ctx->d_sat.p);
-    ctx->launches += 7;
+    ctx->launches += 6;
   }
   CK(cudaGetLastError());
   ctx->have_cloud = true;

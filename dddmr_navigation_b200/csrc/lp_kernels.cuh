@@ -111,11 +111,12 @@ __device__ __forceinline__ uint32_t cell_key(const GridDev& g, float3 v) {
 
 // histogram of points per cell (the key is three subtract-multiply-floors: cheaper to recompute in the scatter pass than
 // to store and re-read)
-__global__ void __launch_bounds__(256) hist_kernel(const float4* __restrict__ packed, size_t n, GridDev g,
+// Records [i0, i1) of `raw` at `stride` bytes: the 16-byte packed records of bounds_pack_kernel, or the 12-byte x,y,z rows
+// of a cloud that was packed on the host (launched per upload chunk then, so it overlaps the rest of the upload).
+__global__ void __launch_bounds__(256) hist_kernel(const char* __restrict__ raw, size_t stride, size_t i0, size_t i1, GridDev g,
                                                    uint32_t* __restrict__ counts) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const float4 p = __ldg(packed + i);
-    const float3 v = make_float3(p.x, p.y, p.z);
+  for (size_t i = i0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (size_t)gridDim.x * blockDim.x) {
+    const float3 v = load_xyz(raw, i, stride);
     if (finite3(v)) atomicAdd(counts + cell_key(g, v), 1u);
   }
 }
@@ -200,14 +201,13 @@ __global__ void __launch_bounds__(256) scan_add_kernel(uint32_t* __restrict__ da
 
 // counting-sort scatter. `fill` holds a copy of the exclusive offsets and is consumed by atomics, so the
 // order of points inside a cell is arbitrary; every consumer is an any-hit or a count.
-__global__ void __launch_bounds__(256) scatter_kernel(const float4* __restrict__ packed, size_t n, GridDev g,
+__global__ void __launch_bounds__(256) scatter_kernel(const char* __restrict__ raw, size_t stride, size_t n, GridDev g,
                                                       uint32_t* __restrict__ fill, float4* __restrict__ out) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const float4 p = __ldg(packed + i);
-    const float3 v = make_float3(p.x, p.y, p.z);
+    const float3 v = load_xyz(raw, i, stride);
     if (!finite3(v)) continue;
     const uint32_t slot = atomicAdd(fill + cell_key(g, v), 1u);
-    out[slot] = p;
+    out[slot] = make_float4(v.x, v.y, v.z, __uint_as_float((uint32_t)i));  // w = original index
   }
 }
 
