@@ -221,7 +221,7 @@ class PackPool {
 int pack_threads_wanted() {
   if (const char* e = std::getenv("B200LP_PACK_THREADS")) return std::max(0, std::min(64, atoi(e)));
   const unsigned hw = std::thread::hardware_concurrency();
-  return hw >= 4 ? (int)std::min(8u, hw / 2) : 0;  // 0: plain copies of the caller's buffer
+  return hw >= 4 ? (int)std::min(12u, hw * 3 / 4) : 0;  // 0: plain copies of the caller's buffer
 }
 
 }  // namespace
@@ -246,6 +246,9 @@ struct b200lp_ctx {
   DevBuf<uint32_t> d_cell_start, d_fill, d_block_sums, d_sat;
   DevBuf<float4> d_packed;  // the raw cloud as 16-byte records (x, y, z, original index)
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t prep_stream = nullptr;  // prep_kernel runs here while the grid of a cloud just handed over is still being built
+  cudaEvent_t ev_tail = nullptr;       // end of the previous cycle on the main stream
+  bool cycle_overlapped = false;
   PackPool* pack_pool = nullptr;     // host threads of the packing upload (created by the first large host cloud)
   PinBuf<float> h_stage;             // pinned staging buffer: x,y,z of every point, 12 bytes each
   int pack_threads_used = 0;         // threads that packed the last cloud (0: it was copied as is)
@@ -579,12 +582,13 @@ void resolve_cycle_timing(b200lp_ctx* ctx) {
   resolve_cloud_timing(ctx);
   if (!ctx->cycle_timing_pending) return;
   if (cudaEventSynchronize(ctx->ev[2]) == cudaSuccess) {
-    cudaEventElapsedTime(&ctx->ms_plan, ctx->ev[1], ctx->ev[2]);
     ctx->ms_readback = 0.f;
     if (!ctx->cycle_timing_direct) cudaEventElapsedTime(&ctx->ms_readback, ctx->ev[2], ctx->ev[3]);
     cudaEventElapsedTime(&ctx->ms_k_prep, ctx->ev[1], ctx->ev[4]);
-    cudaEventElapsedTime(&ctx->ms_k_plan, ctx->ev[4], ctx->ev[5]);
+    cudaEventElapsedTime(&ctx->ms_k_plan, ctx->ev[ctx->cycle_overlapped ? 6 : 4], ctx->ev[5]);
     cudaEventElapsedTime(&ctx->ms_k_argmin, ctx->ev[5], ctx->ev[2]);
+    if (ctx->cycle_overlapped) ctx->ms_plan = ctx->ms_k_prep + ctx->ms_k_plan + ctx->ms_k_argmin;  // prep ran under the grid build
+    else cudaEventElapsedTime(&ctx->ms_plan, ctx->ev[1], ctx->ev[2]);
   }
   ctx->cycle_timing_pending = false;
 }
@@ -626,20 +630,25 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   ctx->pose_stride = pose_stride;
   const int argmin_ctas = (int)std::max(1, std::min(kArgminMaxCtas, (cap_local + 2047) / 2048));
   CK(ctx->d_partial.reserve(std::max(n_robots * (size_t)kArgminMaxCtas, (size_t)16384)));  // >= the persistent plan grid (SMs x resident CTAs)
+  bool init_on_main = false;  // first use / growth: counters are zeroed on the main stream, prep_kernel must stay behind that
   if (ctx->d_tickets2.cap < n_robots) {
+    init_on_main = true;
     CK(ctx->d_tickets2.reserve(n_robots));
     CK(cudaMemsetAsync(ctx->d_tickets2.p, 0, ctx->d_tickets2.cap * sizeof(unsigned), ctx->stream));
   }
   if (ctx->d_tickets.cap < n_robots) {
+    init_on_main = true;
     CK(ctx->d_tickets.reserve(n_robots));
     CK(cudaMemsetAsync(ctx->d_tickets.p, 0, ctx->d_tickets.cap * sizeof(unsigned), ctx->stream));
   }
   if (ctx->d_aggs.cap < n_robots * (size_t)n_chunks) {
+    init_on_main = true;
     CK(ctx->d_aggs.reserve(n_robots * (size_t)n_chunks));
     CK(cudaMemsetAsync(ctx->d_aggs.p, 0, ctx->d_aggs.cap * sizeof(PrepAgg), ctx->stream));
     ctx->epoch = 0;
   }
   if (!ctx->d_work.p) {
+    init_on_main = true;
     CK(ctx->d_work.reserve(1));
     CK(cudaMemsetAsync(ctx->d_work.p, 0, sizeof(unsigned long long), ctx->stream));
   }
@@ -672,16 +681,32 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
       1ull, std::min<unsigned long long>((work + kWarpsPerCta - 1) / kWarpsPerCta,
                                          (unsigned long long)ctx->sm_count * ctx->plan_ctas_per_sm));
 
-  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-  CK(cudaMemcpyAsync(ctx->d_robots.p, ctx->h_robots.p, n_robots * sizeof(RobotIn), cudaMemcpyHostToDevice, ctx->stream));
+  // A cloud handed over just before this call may still be on its way (set_cloud returns when the caller's buffer has been
+  // read): the query upload and prep_kernel do not touch the grid, so they run on a second stream underneath the rest of the
+  // upload / grid build, and only plan_kernel waits for both. Everything the prep stream overwrites was last used by the
+  // previous cycle, whose end on the main stream is ev_tail.
+  bool overlap = false;
+  if (ctx->cloud_timing_pending) {
+    if (cudaEventQuery(ctx->cev[2]) == cudaErrorNotReady) overlap = !init_on_main;
+    else resolve_cloud_timing(ctx);  // the grid is ready: read its timeline now and stop asking
+  }
+  cudaStream_t ps = overlap ? ctx->prep_stream : ctx->stream;
+  if (overlap) CK(cudaStreamWaitEvent(ps, ctx->ev_tail, 0));
+  ctx->cycle_overlapped = overlap;
+  CK(cudaEventRecord(ctx->ev[0], ps));
+  CK(cudaMemcpyAsync(ctx->d_robots.p, ctx->h_robots.p, n_robots * sizeof(RobotIn), cudaMemcpyHostToDevice, ps));
   if (plan_total && !plan_resident)
-    CK(cudaMemcpyAsync(ctx->d_plan7.p, ctx->h_plan7.p, plan_total * 7 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-  prep_kernel<<<dim3((unsigned)n_chunks, (unsigned)n_robots), kPrepThreads, 0, ctx->stream>>>(
+    CK(cudaMemcpyAsync(ctx->d_plan7.p, ctx->h_plan7.p, plan_total * 7 * sizeof(double), cudaMemcpyHostToDevice, ps));
+  CK(cudaEventRecord(ctx->ev[1], ps));
+  prep_kernel<<<dim3((unsigned)n_chunks, (unsigned)n_robots), kPrepThreads, 0, ps>>>(
       ctx->C, ctx->d_robots.p, t_cap, rank, count, ctx->epoch, ctx->d_tickets.p, ctx->d_aggs.p, ctx->d_rec_vel.p,
       ctx->d_rec_steps.p, ctx->d_rec_dt.p, ctx->d_rec_sample.p, ctx->d_meta.p, ctx->d_plan7.p, ctx->d_plan_pts.p,
       ctx->d_rec_pose_off.p, ctx->d_poses.p, pose_stride, ctx->d_rec_pp.p, want_pp);
-  CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+  CK(cudaEventRecord(ctx->ev[4], ps));
+  if (overlap) {
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev[4], 0));
+    CK(cudaEventRecord(ctx->ev[6], ctx->stream));  // plan_kernel's start on the main stream (after the grid build)
+  }
   plan_kernel<<<plan_grid, kThreads, 0, ctx->stream>>>(
       ctx->C, ctx->grid, ctx->d_robots.p, ctx->d_meta.p, (int)n_robots, t_cap, cap_local, ctx->d_rec_vel.p,
       ctx->d_rec_steps.p, ctx->d_rec_pose_off.p, ctx->d_poses.p, ctx->d_rec_pp.p, ctx->d_plan_pts.p, ctx->d_cost.p,
@@ -696,6 +721,7 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   }
   ctx->launches += 2;
   CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  CK(cudaEventRecord(ctx->ev_tail, ctx->stream));
   if (direct) {
     // the kernel's last CTA writes the result block into pinned host memory and raises seq: no copies, no stream sync
     CK(cudaGetLastError());
@@ -795,6 +821,8 @@ int b200lp_create(b200lp_ctx** out, int device, const b200lp_limits* limits, con
   if ((e = cudaSetDevice(device)) != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
   if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+  if ((e = cudaStreamCreateWithFlags(&ctx->prep_stream, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_tail, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
   for (auto& ev : ctx->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
   for (auto& ev : ctx->chunk_ev)
@@ -842,6 +870,8 @@ void b200lp_destroy(b200lp_ctx* ctx) {
     if (ev) cudaEventDestroy(ev);
   for (auto& ev : ctx->cev)
     if (ev) cudaEventDestroy(ev);
+  if (ctx->prep_stream) { cudaStreamSynchronize(ctx->prep_stream); cudaStreamDestroy(ctx->prep_stream); }
+  if (ctx->ev_tail) cudaEventDestroy(ctx->ev_tail);
   delete ctx->pack_pool;
   ctx->h_stage.release();
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
