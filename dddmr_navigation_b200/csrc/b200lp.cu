@@ -247,8 +247,7 @@ struct b200lp_ctx {
   DevBuf<float4> d_packed;  // the raw cloud as 16-byte records (x, y, z, original index)
   cudaStream_t copy_stream = nullptr;
   cudaStream_t prep_stream = nullptr;  // prep_kernel runs here while the grid of a cloud just handed over is still being built
-  cudaEvent_t ev_tail = nullptr;       // end of the previous cycle on the main stream
-  bool cycle_overlapped = false;
+  bool cycle_overlapped = false, have_cycle_event = false;
   PackPool* pack_pool = nullptr;     // host threads of the packing upload (created by the first large host cloud)
   PinBuf<float> h_stage;             // pinned staging buffer: x,y,z of every point, 12 bytes each
   int pack_threads_used = 0;         // threads that packed the last cloud (0: it was copied as is)
@@ -684,14 +683,14 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   // A cloud handed over just before this call may still be on its way (set_cloud returns when the caller's buffer has been
   // read): the query upload and prep_kernel do not touch the grid, so they run on a second stream underneath the rest of the
   // upload / grid build, and only plan_kernel waits for both. Everything the prep stream overwrites was last used by the
-  // previous cycle, whose end on the main stream is ev_tail.
+  // previous cycle, whose end on the main stream is ev[2] (as recorded then; it is re-recorded further down).
   bool overlap = false;
   if (ctx->cloud_timing_pending) {
     if (cudaEventQuery(ctx->cev[2]) == cudaErrorNotReady) overlap = !init_on_main;
     else resolve_cloud_timing(ctx);  // the grid is ready: read its timeline now and stop asking
   }
   cudaStream_t ps = overlap ? ctx->prep_stream : ctx->stream;
-  if (overlap) CK(cudaStreamWaitEvent(ps, ctx->ev_tail, 0));
+  if (overlap && ctx->have_cycle_event) CK(cudaStreamWaitEvent(ps, ctx->ev[2], 0));
   ctx->cycle_overlapped = overlap;
   CK(cudaEventRecord(ctx->ev[0], ps));
   CK(cudaMemcpyAsync(ctx->d_robots.p, ctx->h_robots.p, n_robots * sizeof(RobotIn), cudaMemcpyHostToDevice, ps));
@@ -721,7 +720,7 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   }
   ctx->launches += 2;
   CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-  CK(cudaEventRecord(ctx->ev_tail, ctx->stream));
+  ctx->have_cycle_event = true;
   if (direct) {
     // the kernel's last CTA writes the result block into pinned host memory and raises seq: no copies, no stream sync
     CK(cudaGetLastError());
@@ -822,7 +821,6 @@ int b200lp_create(b200lp_ctx** out, int device, const b200lp_limits* limits, con
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
   if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
   if ((e = cudaStreamCreateWithFlags(&ctx->prep_stream, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
-  if ((e = cudaEventCreateWithFlags(&ctx->ev_tail, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
   for (auto& ev : ctx->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
   for (auto& ev : ctx->chunk_ev)
@@ -871,7 +869,6 @@ void b200lp_destroy(b200lp_ctx* ctx) {
   for (auto& ev : ctx->cev)
     if (ev) cudaEventDestroy(ev);
   if (ctx->prep_stream) { cudaStreamSynchronize(ctx->prep_stream); cudaStreamDestroy(ctx->prep_stream); }
-  if (ctx->ev_tail) cudaEventDestroy(ctx->ev_tail);
   delete ctx->pack_pool;
   ctx->h_stage.release();
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
