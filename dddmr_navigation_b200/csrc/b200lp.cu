@@ -145,10 +145,16 @@ inline void pack_xyz(const char* src, size_t stride, float* dst, size_t i0, size
 
 class PackPool {
  public:
-  explicit PackPool(int threads) : T_(threads) {
+  // Starts up to `threads` workers; fewer if the system refuses (threads() tells; 0 = unusable). Never throws.
+  explicit PackPool(int threads) noexcept {
     for (int c = 0; c < kPackChunks; ++c) done_[c].store(0);
-    bounds_.resize((size_t)T_);
-    for (int w = 0; w < T_; ++w) th_.emplace_back([this, w] { run(w); });
+    try {
+      bounds_.resize((size_t)threads);
+      th_.reserve((size_t)threads);
+      for (int w = 0; w < threads; ++w) th_.emplace_back([this, w] { run(w); });
+    } catch (...) {
+    }
+    T_ = (int)th_.size();  // the workers read T_ only after the first start(), which happens after construction
   }
   ~PackPool() {
     {
@@ -179,7 +185,8 @@ class PackPool {
   HostBounds bounds() const {
     HostBounds r;
     r.reset();
-    for (const HostBounds& b : bounds_) {
+    for (int w = 0; w < T_; ++w) {
+      const HostBounds& b = bounds_[(size_t)w];
       for (int a = 0; a < 3; ++a) { r.mn[a] = std::min(r.mn[a], b.mn[a]); r.mx[a] = std::max(r.mx[a], b.mx[a]); }
       r.n_finite += b.n_finite;
     }
@@ -205,7 +212,7 @@ class PackPool {
       }
     }
   }
-  const int T_;
+  int T_ = 0;
   std::vector<std::thread> th_;
   std::mutex mu_;
   std::condition_variable cv_;
@@ -444,6 +451,10 @@ int build_grid(b200lp_ctx* ctx, const void* src, size_t n, size_t stride, bool o
     if (!ctx->pack_pool) {
       const int t = pack_threads_wanted();
       if (t > 0) ctx->pack_pool = new (std::nothrow) PackPool(t);
+      if (ctx->pack_pool && ctx->pack_pool->threads() == 0) {  // no thread could be started: plain copies from now on
+        delete ctx->pack_pool;
+        ctx->pack_pool = nullptr;
+      }
     }
     // the staging buffer may still be feeding the copies of the previous cloud
     packing = ctx->pack_pool != nullptr && cudaStreamSynchronize(ctx->copy_stream) == cudaSuccess &&
