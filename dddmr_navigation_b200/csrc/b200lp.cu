@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <immintrin.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <atomic>
@@ -227,7 +228,9 @@ class PackPool {
 
 int pack_threads_wanted() {
   if (const char* e = std::getenv("B200LP_PACK_THREADS")) return std::max(0, std::min(64, atoi(e)));
-  const unsigned hw = std::thread::hardware_concurrency();
+  unsigned hw = std::thread::hardware_concurrency();
+  cpu_set_t set;  // the CPUs this process may run on (a rank bound to its GPU's NUMA node sees only those)
+  if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) hw = (unsigned)CPU_COUNT(&set);
   return hw >= 4 ? (int)std::min(12u, hw * 3 / 4) : 0;  // 0: plain copies of the caller's buffer
 }
 
