@@ -201,13 +201,31 @@ __global__ void __launch_bounds__(256) scan_add_kernel(uint32_t* __restrict__ da
 
 // counting-sort scatter. `fill` holds a copy of the exclusive offsets and is consumed by atomics, so the
 // order of points inside a cell is arbitrary; every consumer is an any-hit or a count.
+// Four points per thread and trip: the slot counter's round trip to L2 is the latency that bounds this pass, so four of
+// them are kept in flight per thread.
 __global__ void __launch_bounds__(256) scatter_kernel(const char* __restrict__ raw, size_t stride, size_t n, GridDev g,
                                                       uint32_t* __restrict__ fill, float4* __restrict__ out) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const float3 v = load_xyz(raw, i, stride);
-    if (!finite3(v)) continue;
-    const uint32_t slot = atomicAdd(fill + cell_key(g, v), 1u);
-    out[slot] = make_float4(v.x, v.y, v.z, __uint_as_float((uint32_t)i));  // w = original index
+  constexpr int kU = 4;
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += kU * step) {
+    float3 v[kU];
+    bool ok[kU];
+    uint32_t slot[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const size_t i = i0 + u * step;
+      ok[u] = i < n;
+      if (ok[u]) {
+        v[u] = load_xyz(raw, i, stride);
+        ok[u] = finite3(v[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u)
+      if (ok[u]) slot[u] = atomicAdd(fill + cell_key(g, v[u]), 1u);
+#pragma unroll
+    for (int u = 0; u < kU; ++u)
+      if (ok[u]) out[slot[u]] = make_float4(v[u].x, v[u].y, v[u].z, __uint_as_float((uint32_t)(i0 + u * step)));  // w = original index
   }
 }
 
