@@ -352,13 +352,19 @@ struct alignas(16) PrepAgg {  // 32 bytes: read back with two 16-byte volatile l
 static_assert(sizeof(PrepAgg) == 32, "PrepAgg layout");
 
 #ifndef B200LP_PREP_THREADS
-#define B200LP_PREP_THREADS 256
+#define B200LP_PREP_THREADS 128
 #endif
-constexpr int kPrepThreads = B200LP_PREP_THREADS;  // samples per chunk
+constexpr int kPrepThreads = B200LP_PREP_THREADS;  // samples per chunk: 16.5 k samples (C2) make 129 CTAs, one per SM — the
+                                                    // forward simulation is bound by the XU / FP64 pipes of the SMs it runs on
 constexpr int kPrepWarps = kPrepThreads / 32;
 // serial per-CTA jobs (three velocity axes, two pose matrices) are spread over different warps where possible
 __device__ __forceinline__ bool prep_job(int job, int tid) { return tid == (job % kPrepWarps) * 32 + job / kPrepWarps; }
 
+#ifdef B200LP_PREP_TRACE  // tools only: phase timestamps of thread 0 of the first / last chunk, printed by the kernel
+#define PREP_T(k) do { if (tid == 0) trace_t[k] = clock64(); } while (0)
+#else
+#define PREP_T(k) do { } while (0)
+#endif
 // grid = (n_chunks, robots). Chunk ids are handed out by a per-robot ticket, so a CTA only ever waits for
 // chunks that are already running; every CTA publishes its aggregate BEFORE it looks back.
 __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const RobotIn* __restrict__ robots, int t_cap,
@@ -386,6 +392,10 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
   const b200lp_limits& L = C.lim;
   const b200lp_params& P = C.par;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef B200LP_PREP_TRACE
+  long long trace_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+  PREP_T(0);
 
   if (tid == 0) {
     s_chunk = (int)atomicAdd(tickets + robot, 1u);
@@ -453,6 +463,7 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
     if (prep_job(2, tid)) s_n[2] = velocity_iterator_dev((double)mn2, (double)mx2, (int)P.angular_z_sample, s_th);
   }
   __syncthreads();
+  PREP_T(1);  // window + velocity axes done
 
   int n_raw;
   const int nys = s_n[1], nths = s_n[2];
@@ -519,6 +530,7 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
     totk += a; totv += b;
   }
   PrepAgg* my_aggs = aggs + (size_t)robot * n_chunks;
+  PREP_T(2);  // samples checked, CTA-level counts known
   if (tid == 0) {  // publish this chunk's aggregate
     PrepAgg* a = my_aggs + chunk;
     a->keep = totk; a->valid = totv;
@@ -562,6 +574,7 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
   }
   __syncthreads();
   const int base_keep = s_red[0], base_valid = s_red[1];
+  PREP_T(3);  // look-back done
 
   const unsigned lt = (1u << lane) - 1u;
   const long long pose_row = (long long)robot * pose_stride + (long long)(s_poses + offp + pscan - my_poses);
@@ -588,7 +601,10 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
     const double wdt = (double)v2 * dt;  // loop invariant of th' = (float)(th + w*dt)
     float4* out = pose_rows + pose_row;
     // Blocks of 4 steps: the heading chain th' = (float)(th + w*dt) is the only dependency the expensive
-    // sin/cos evaluations have, so it runs ahead and the four evaluations overlap in the FP64 pipe.
+    // sin/cos evaluations have, so it runs ahead and the four evaluations overlap in the FP64 pipe. (A three-stage
+    // software pipeline that also overlaps the position chain with the next block's headings was measured SLOWER,
+    // 39 vs 36 us at C2: the loop is bound by the conversion (XU) and FP64 pipes of the few SMs that hold the
+    // trajectories, not by the dependency chains — tools/prep_trace.py.)
     constexpr int kU = 4;
     for (int k0 = 0; k0 < steps; k0 += kU) {
       float tho[kU], thn[kU];
@@ -619,6 +635,7 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
         if (k0 + u < steps) out[k0 + u] = make_float4(x, y, thn[u], 0.f);
       }
     }
+    PREP_T(4);  // rollout done
     // the block loop may run past the last step: restore the state after step `steps - 1`
     {
       const float4 last = out[steps - 1];
@@ -631,6 +648,13 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
       rec_pp[rec] = make_double2(dist, yaw);
     }
   }
+  PREP_T(5);  // pure-pursuit terms done
+#ifdef B200LP_PREP_TRACE
+  if (tid == 0 && (chunk == 0 || chunk == n_chunks - 1) && robot == 0)
+    printf("prep trace chunk %d/%d steps %d: axes %lld, precheck %lld, look-back %lld, rollout %lld, pure pursuit %lld cycles (roll=%d)\n", chunk,
+           n_chunks, steps, trace_t[1] - trace_t[0], trace_t[2] - trace_t[1], trace_t[3] - trace_t[2],
+           trace_t[4] ? trace_t[4] - trace_t[3] : 0ll, trace_t[4] ? trace_t[5] - trace_t[4] : 0ll, (int)roll);
+#endif
   if (chunk == n_chunks - 1 && tid == 0) {  // the last ticket: every chunk of this robot has started
     const PrepAgg* a = my_aggs + chunk;
     RobotMeta m;
