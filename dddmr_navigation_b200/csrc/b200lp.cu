@@ -81,6 +81,10 @@ struct PinBuf {
 // points in 0.40 ms, the packed copy takes 0.44 ms, the raw copy 1.16 ms (5.3 ms from pageable memory).
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kPackChunks = 8;
+#ifndef B200LP_PACK_MIN_BYTES
+#define B200LP_PACK_MIN_BYTES (2u << 20)
+#endif
+constexpr size_t kPackMinBytes = B200LP_PACK_MIN_BYTES;  // smaller host clouds are copied as they are
 
 struct alignas(64) HostBounds {  // one per packing thread (own cache line)
   float mn[4], mx[4];
@@ -450,7 +454,7 @@ int build_grid(b200lp_ctx* ctx, const void* src, size_t n, size_t stride, bool o
   ctx->pack_threads_used = 0;
   // large host clouds with padding between the points: pack on the host, upload 12 bytes per point (see PackPool)
   bool packing = false;
-  if (src && !on_device && stride >= 16 && n * stride >= ((size_t)8 << 20)) {
+  if (src && !on_device && stride >= 16 && n * stride >= kPackMinBytes) {
     if (!ctx->pack_pool) {
       const int t = pack_threads_wanted();
       if (t > 0) ctx->pack_pool = new (std::nothrow) PackPool(t);

@@ -182,7 +182,7 @@ void b200lp_destroy(b200lp_ctx* ctx);
 
 /* Upload the aggregated observation cloud and (re)build the voxel grid. `pts` is host memory,
  * n points of `stride_bytes` each (32 = pcl::PointXYZI, 16 = pcl::PointXYZ), x,y,z = first three floats. */
-/* Host clouds of 8 MB or more whose points carry padding (stride >= 16) are packed to 12 bytes per point by a few host
+/* Host clouds of 2 MB or more whose points carry padding (stride >= 16) are packed to 12 bytes per point by a few host
  * threads of the ctx into a pinned staging buffer while the chunks already packed are copied: 24 MB instead of 64 MB
  * cross PCIe for 2 M PointXYZI points, and `pts` may be ordinary pageable memory. B200LP_PACK_THREADS in the
  * environment sets the thread count (default min(8, hardware threads / 2); 0 = copy the caller's buffer as is). */
