@@ -115,9 +115,16 @@ __device__ __forceinline__ uint32_t cell_key(const GridDev& g, float3 v) {
 // of a cloud that was packed on the host (launched per upload chunk then, so it overlaps the rest of the upload).
 __global__ void __launch_bounds__(256) hist_kernel(const char* __restrict__ raw, size_t stride, size_t i0, size_t i1, GridDev g,
                                                    uint32_t* __restrict__ counts) {
-  for (size_t i = i0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (size_t)gridDim.x * blockDim.x) {
-    const float3 v = load_xyz(raw, i, stride);
-    if (finite3(v)) atomicAdd(counts + cell_key(g, v), 1u);
+  const int lane = threadIdx.x & 31;
+  for (size_t w0 = i0 + (size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); w0 < i1; w0 += (size_t)gridDim.x * blockDim.x) {
+    const size_t i = w0 + lane;
+    uint32_t key = 0xffffffffu;
+    if (i < i1) {
+      const float3 v = load_xyz(raw, i, stride);
+      if (finite3(v)) key = cell_key(g, v);
+    }
+    const unsigned peers = __match_any_sync(kFull, key);  // one atomic per distinct cell of the warp (see scatter_kernel)
+    if (lane == __ffs(peers) - 1 && key != 0xffffffffu) atomicAdd(counts + key, (uint32_t)__popc(peers));
   }
 }
 
@@ -201,31 +208,41 @@ __global__ void __launch_bounds__(256) scan_add_kernel(uint32_t* __restrict__ da
 
 // counting-sort scatter. `fill` holds a copy of the exclusive offsets and is consumed by atomics, so the
 // order of points inside a cell is arbitrary; every consumer is an any-hit or a count.
-// Four points per thread and trip: the slot counter's round trip to L2 is the latency that bounds this pass, so four of
-// them are kept in flight per thread.
+// Neighbouring points of a cloud mostly fall into the same cell (obstacle surfaces sampled at centimetres, cells of
+// decimetres), and same-address atomics serialise in L2: the lanes of a warp that share a cell are found with
+// __match_any_sync, the lowest of them reserves slots for all of them with ONE atomic, and the others take their slot from
+// its answer. Four points per thread and trip keep four such round trips in flight.
 __global__ void __launch_bounds__(256) scatter_kernel(const char* __restrict__ raw, size_t stride, size_t n, GridDev g,
                                                       uint32_t* __restrict__ fill, float4* __restrict__ out) {
   constexpr int kU = 4;
   const size_t step = (size_t)gridDim.x * blockDim.x;
-  for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += kU * step) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  // warp-uniform trip count: every lane of a warp runs the same trips (the match needs all 32 lanes)
+  for (size_t w0 = (size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); w0 < n; w0 += kU * step) {
     float3 v[kU];
-    bool ok[kU];
-    uint32_t slot[kU];
+    uint32_t key[kU], slot[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
-      const size_t i = i0 + u * step;
-      ok[u] = i < n;
-      if (ok[u]) {
+      const size_t i = w0 + lane + u * step;
+      key[u] = 0xffffffffu;  // no point / not finite
+      if (i < n) {
         v[u] = load_xyz(raw, i, stride);
-        ok[u] = finite3(v[u]);
+        if (finite3(v[u])) key[u] = cell_key(g, v[u]);
       }
     }
 #pragma unroll
-    for (int u = 0; u < kU; ++u)
-      if (ok[u]) slot[u] = atomicAdd(fill + cell_key(g, v[u]), 1u);
+    for (int u = 0; u < kU; ++u) {
+      const unsigned peers = __match_any_sync(kFull, key[u]);
+      const int leader = __ffs(peers) - 1;
+      uint32_t base = 0u;
+      if (lane == leader && key[u] != 0xffffffffu) base = atomicAdd(fill + key[u], (uint32_t)__popc(peers));
+      slot[u] = __shfl_sync(kFull, base, leader) + (uint32_t)__popc(peers & lt);
+    }
 #pragma unroll
     for (int u = 0; u < kU; ++u)
-      if (ok[u]) out[slot[u]] = make_float4(v[u].x, v[u].y, v[u].z, __uint_as_float((uint32_t)(i0 + u * step)));  // w = original index
+      if (key[u] != 0xffffffffu)
+        out[slot[u]] = make_float4(v[u].x, v[u].y, v[u].z, __uint_as_float((uint32_t)(w0 + lane + u * step)));  // w = original index
   }
 }
 
