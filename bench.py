@@ -220,6 +220,15 @@ def bind_to_gpu_numa_node(gpu_index: int):
         return f"unavailable ({type(e).__name__})"
 
 
+def choose_pack_threads(numa, local_world: int) -> int:
+    """Host threads each rank's library may use to pack the cloud for upload (B200LP_PACK_THREADS): 3/4 of this rank's share
+    of the CPUs local to its GPU, at most 12, none below 4 (then the raw copy is as fast; with 8 ranks on a 32-CPU host the
+    host's memory bandwidth is the limit and packing only adds traffic)."""
+    cpus = len(numa) if isinstance(numa, list) and numa else (os.cpu_count() or 1)
+    t = min(12, (cpus // max(1, local_world)) * 3 // 4)
+    return t if t >= 4 else 0
+
+
 def pinned_copy(arr: np.ndarray):
     """Page-locked host copy of arr (torch allocates; numpy views it)."""
     import torch
@@ -325,8 +334,12 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     numa = bind_to_gpu_numa_node(local_rank)  # before any pinned allocation: the upload buffers should sit next to the GPU
+    if "B200LP_PACK_THREADS" not in os.environ:  # this process knows how many ranks share the host; the library does not
+        os.environ["B200LP_PACK_THREADS"] = str(choose_pack_threads(numa, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):  # NCCL's version banner would share stdout with the JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():

@@ -230,12 +230,20 @@ class PackPool {
   std::vector<HostBounds> bounds_;
 };
 
+// How many host threads pack a cloud. B200LP_PACK_THREADS decides when set (the embedding application knows how many
+// planner processes share the host). Otherwise: 3/4 of the CPUs this process may run on, divided by the GPUs it can see (one
+// planner process per GPU is the deployment this library is built for), at most 12 — and none when that leaves fewer than 4:
+// a thread packs ~18 GB/s, so three of them are no faster than the raw copy, and with every GPU of a box uploading at once
+// the host's memory bandwidth is the limit, which packing (read 32 B + write 12 B + DMA 12 B per point) only makes worse.
 int pack_threads_wanted() {
   if (const char* e = std::getenv("B200LP_PACK_THREADS")) return std::max(0, std::min(64, atoi(e)));
   unsigned hw = std::thread::hardware_concurrency();
   cpu_set_t set;  // the CPUs this process may run on (a rank bound to its GPU's NUMA node sees only those)
   if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) hw = (unsigned)CPU_COUNT(&set);
-  return hw >= 4 ? (int)std::min(12u, hw * 3 / 4) : 0;  // 0: plain copies of the caller's buffer
+  int gpus = 1;
+  if (cudaGetDeviceCount(&gpus) != cudaSuccess || gpus < 1) gpus = 1;
+  const unsigned t = std::min(12u, hw / (unsigned)gpus * 3 / 4);
+  return t >= 4 ? (int)t : 0;  // 0: plain copies of the caller's buffer
 }
 
 }  // namespace
