@@ -338,9 +338,19 @@ def main():
         os.environ["B200LP_PACK_THREADS"] = str(choose_pack_threads(numa, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):  # NCCL's version banner would share stdout with the JSON line
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL writes its version banner to stdout when the communicator comes up (NCCL_DEBUG=VERSION / WARN); stdout belongs to
+        # the one JSON line, so file descriptor 1 points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     def barrier():
         if world > 1:
