@@ -56,3 +56,22 @@ def test_pack_pool_survives_changing_cloud_sizes_and_small_clouds_bypass_it():
         assert_result_equal(lp.plan(q), ref.plan(q))
     lp.close()
     ref.close()
+
+
+@pytest.mark.gpu
+def test_pack_threads_environment_override(monkeypatch):
+    """B200LP_PACK_THREADS is read when a ctx starts its pool: 0 keeps the raw copy, n pins the thread count."""
+    sc = synth.c2_dense(n_points=300_000, samples=(12.0, 12.0))
+    q = make_query(sc.pose, sc.twist)
+    results = []
+    for env, want_threads, want_bytes in (("0", 0, 300_000 * 32), ("3", 3, 300_000 * 12)):
+        monkeypatch.setenv("B200LP_PACK_THREADS", env)
+        lp = LocalPlanner(sc.config, device=0)
+        lp.set_cloud(sc.cloud)
+        assert lp.last_upload() == {"h2d_bytes": want_bytes, "pack_threads": want_threads}
+        lp.set_plan(sc.plan)
+        results.append((lp.plan(q), lp.read_trajectories(), lp.grid_info()))
+        lp.close()
+    assert_result_equal(results[0][0], results[1][0])
+    assert_trajectories_equal(results[0][1], results[1][1])
+    assert results[0][2] == results[1][2]
