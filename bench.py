@@ -606,6 +606,19 @@ def main():
                 "ms_per_cycle": 1e3 * dt / n_cycles,
                 "best_id_matches_gpu": bool(ro.best_id == r.best_id), "best_cost_matches_gpu_1e-4": bool(abs(ro.best_cost - r.best_cost) <= 1e-4 * abs(ro.best_cost)),
             }
+            # courtesy upper bound: the oracle port with the trajectories split over every host core
+            # (the reference itself is single-threaded; the kd-tree build stays serial)
+            ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+            ora = O.OraclePlanner(sc.config, O.MATH_LIBM, O.INDEX_NANOFLANN if O.have_ref() else O.INDEX_GRID)
+            ora.set_plan(plan)
+            t0 = time.perf_counter()
+            ora.set_cloud(sc.cloud)
+            rm = ora.plan(q, ncores)
+            dtm = time.perf_counter() - t0
+            line["cpu_baseline"]["all_cores"] = {
+                "value": rm.n_poses / dtm, "unit": UNIT, "cores": ncores, "kind": "port", "ms_per_cycle": 1e3 * dtm,
+                "sample": "1 full cycle of the same workload through the oracle port, trajectories split over std::threads, index rebuilt (serial)",
+                "best_id_matches_gpu": bool(rm.best_id == r.best_id)}
         else:
             use_ref = O.have_ref()
             ora = O.OraclePlanner(sc.config, O.MATH_LIBM, O.INDEX_NANOFLANN if use_ref else O.INDEX_GRID)
