@@ -185,7 +185,8 @@ void b200lp_destroy(b200lp_ctx* ctx);
 /* Host clouds of 2 MB or more whose points carry padding (stride >= 16) are packed to 12 bytes per point by a few host
  * threads of the ctx into a pinned staging buffer while the chunks already packed are copied: 24 MB instead of 64 MB
  * cross PCIe for 2 M PointXYZI points, and `pts` may be ordinary pageable memory. B200LP_PACK_THREADS in the
- * environment sets the thread count (default min(8, hardware threads / 2); 0 = copy the caller's buffer as is). */
+ * environment sets the thread count (default: 3/4 of the CPUs the process may run on divided by the visible GPUs, at most 12,
+ * none below 4; 0 = copy the caller's buffer as is). */
 int b200lp_set_cloud(b200lp_ctx* ctx, const void* pts, size_t n, size_t stride_bytes);
 /* How the last b200lp_set_cloud moved the cloud: bytes copied host -> device and the host threads that packed them
  * (0 = the caller's buffer was copied as is). */
