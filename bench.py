@@ -551,13 +551,14 @@ def main():
         win, height = 10.0, 2.0
         for _ in range(10):
             oi = lp.sensor_observation(0, hscan, b2s, g2b, win, height)
-        wall, dev = [], []
+        wall, dev, upl = [], [], []
         for _ in range(args.observation_scans):
             flush_l2()
             t0 = time.perf_counter()
             oi = lp.sensor_observation(0, hscan, b2s, g2b, win, height)
             wall.append(1e3 * (time.perf_counter() - t0))
             dev.append(oi.ms_device)
+            upl.append(oi.ms_upload)
         passes = (oi.n_launches - 2) // 4
         n_s, n_w, n_o = int(oi.n_scan), int(oi.n_window), int(oi.n_points)
         obs_bytes = 32 * n_s + (16 * n_s + 16 * n_w) + (passes - 1) * 32 * n_w + 16 * n_w + 16 * n_o
@@ -571,7 +572,7 @@ def main():
             "what": ("MultiLayerSpinningLidar::cbSensor filter chain (transform, 3 pass-throughs, 0.1 m voxel centroids, transform) on one "
                      "262 144-point scan from pinned host memory; the observation stays on the device"),
             "scan_points": n_s, "window_points": n_w, "observation_points": n_o, "radix_passes": passes, "launches": int(oi.n_launches),
-            "ms_device_p50": d_ms, "ms_host_wall_p50": statistics.median(wall), "scan_points_per_sec_e2e": n_s / (statistics.median(wall) * 1e-3),
+            "ms_device_p50": d_ms, "ms_upload_p50": statistics.median(upl), "ms_host_wall_p50": statistics.median(wall), "scan_points_per_sec_e2e": n_s / (statistics.median(wall) * 1e-3),
             "roofline": {"bound": "hbm", "achieved": obs_bytes / (d_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": obs_bytes / (d_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": obs_bytes,
                          "note": "upload + ~10 dependent launches on 4 MB of records: launch/latency-bound, not HBM-bound"},

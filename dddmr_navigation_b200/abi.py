@@ -116,7 +116,7 @@ class SensorParams(C.Structure):
 
 class ObservationInfo(C.Structure):
     _fields_ = [("n_scan", C.c_int64), ("n_window", C.c_int64), ("n_points", C.c_int64), ("ms_device", C.c_float),
-                ("n_launches", C.c_int32)]
+                ("n_launches", C.c_int32), ("ms_upload", C.c_float), ("reserved_", C.c_int32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -302,7 +302,7 @@ struct b200lp_ctx {
   DevBuf<float4> d_obs_out[B200LP_MAX_SENSORS];  // Sensor::sensor_current_observation_ per sensor, pcl::PointXYZ layout
   size_t n_obs_out[B200LP_MAX_SENSORS] = {0, 0, 0, 0, 0, 0, 0, 0};
   bool have_obs[B200LP_MAX_SENSORS] = {false, false, false, false, false, false, false, false};
-  cudaEvent_t oev[2] = {nullptr, nullptr};
+  cudaEvent_t oev[3] = {nullptr, nullptr, nullptr};  // observation: start, end, scan uploaded
 
   // per-cycle state
   size_t n_robots = 0;
@@ -1248,6 +1248,7 @@ int b200lp_sensor_observation(b200lp_ctx* ctx, int sensor, const void* scan, siz
     cudaStream_t st = ctx->stream;
     CK(cudaEventRecord(ctx->oev[0], st));
     CK(cudaMemcpyAsync(ctx->d_scan.p, scan, n * stride, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(ctx->oev[2], st));
     obs_key_kernel<<<nb, kObsThreads, 0, st>>>(ctx->d_scan.p, n, stride, P, bits, ctx->d_obs_a.p, ctx->d_obs_hist.p);
     float4 *src = ctx->d_obs_a.p, *dst = ctx->d_obs_b.p;
     int launches = 1;
@@ -1275,6 +1276,7 @@ int b200lp_sensor_observation(b200lp_ctx* ctx, int sensor, const void* scan, siz
     I.n_window = ctx->h_obs_counts.p[0];
     I.n_points = ctx->h_obs_counts.p[1];
     cudaEventElapsedTime(&I.ms_device, ctx->oev[0], ctx->oev[1]);
+    cudaEventElapsedTime(&I.ms_upload, ctx->oev[0], ctx->oev[2]);
   }
   ctx->n_obs_out[sensor] = (size_t)I.n_points;
   ctx->have_obs[sensor] = true;

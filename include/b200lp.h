@@ -274,6 +274,8 @@ typedef struct b200lp_observation_info {
   int64_t n_points; /* voxels = points of the observation */
   float ms_device;  /* CUDA-event time of the device work of this call (upload included) */
   int32_t n_launches;
+  float ms_upload;  /* the part of ms_device the host -> device copy of the scan took */
+  int32_t reserved_;
 } b200lp_observation_info;
 /* MultiLayerSpinningLidar::cbSensor on one scan (after pcl::fromROSMsg / stitching): `scan` is host memory, n points of
  * stride_bytes each (16 = pcl::PointXYZ), x,y,z = first three floats, in the sensor frame. base_from_sensor =

@@ -1040,6 +1040,8 @@ int lporacle_sensor_observation(const void* scan, size_t n, size_t stride, const
   info->n_window = (int64_t)cloud.size();
   info->ms_device = 0.f;
   info->n_launches = 0;
+  info->ms_upload = 0.f;
+  info->reserved_ = 0;
   // pcl::VoxelGrid (:253-256)
   const float leaf = sp->leaf_size > 0.f ? sp->leaf_size : 0.1f;
   const float inv = 1.0f / leaf;  // inverse_leaf_size_ = Ones / leaf_size_

@@ -17,6 +17,14 @@ def run(tag):
         torch.cuda.synchronize()
         t0 = time.perf_counter(); oi = lp.sensor_observation(0, hscan, b2s, g2b, 10.0, 2.0); w.append(1e3*(time.perf_counter()-t0)); d.append(oi.ms_device)
     print(tag, "wall p50 %.3f device p50 %.3f" % (statistics.median(w), statistics.median(d)), flush=True)
+dscan = torch.empty_like(t, device="cuda")
+def h2d():
+    w = []
+    for _ in range(30):
+        if FLUSH: flush.zero_()
+        torch.cuda.synchronize(); t0 = time.perf_counter(); dscan.copy_(t, non_blocking=True); torch.cuda.synchronize(); w.append(1e3*(time.perf_counter()-t0))
+    print("plain 4 MB pinned H2D copy p50 %.3f ms" % statistics.median(w), flush=True)
+h2d()
 run("fresh ctx, no cloud yet      ")
 lp.set_cloud_ptr(cloud.ctypes.data, cloud.shape[0], 32); lp.last_timing()
 run("after one packed set_cloud   ")
