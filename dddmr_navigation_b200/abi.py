@@ -13,7 +13,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libb200lp.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # status codes
 OK, E_INVALID, E_CUDA, E_STATE, E_NOMEM = 0, -1, -2, -3, -4
@@ -42,6 +42,8 @@ MAX_CRITICS = 8
 MAX_STEPS = 512
 MAX_PLAN = 1024
 MAX_SENSORS = 8
+PEER_HANDLE_BYTES = 64
+MAX_PEERS = 16
 
 
 class Limits(C.Structure):
@@ -136,6 +138,9 @@ SYMBOLS = {
     "b200lp_set_plan": (C.c_int, [_P, C.POINTER(C.c_double), C.c_size_t]),
     "b200lp_plan": (C.c_int, [_P, C.POINTER(Query), C.POINTER(Result)]),
     "b200lp_plan_shard": (C.c_int, [_P, C.POINTER(Query), C.c_int, C.c_int, C.POINTER(Result)]),
+    "b200lp_peer_export": (C.c_int, [_P, C.POINTER(C.c_uint8)]),
+    "b200lp_peer_attach": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_uint8)]),
+    "b200lp_plan_shard_exchange": (C.c_int, [_P, C.POINTER(Query), C.POINTER(Result)]),
     "b200lp_plan_batch": (C.c_int, [_P, C.POINTER(Query), C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_int64),
                                     C.POINTER(Result)]),
     "b200lp_traj_count": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),

@@ -129,6 +129,13 @@ struct b200lp_ctx {
   bool have_obs[B200LP_MAX_SENSORS] = {false, false, false, false, false, false, false, false};
   cudaEvent_t oev[3] = {nullptr, nullptr, nullptr};  // observation: start, end, scan uploaded
 
+  // peer-memory argmin exchange of sample-sharded cycles
+  DevBuf<PeerSlot> d_peer_slots;          // 2 x kMaxPeers slots the peers write into
+  PeerTable peer_table{};                 // every rank's slot array, mapped into this process
+  void* peer_opened[kMaxPeers] = {nullptr};
+  int peer_rank = -1, peer_world = 0;
+  unsigned long long peer_seq = 0;
+
   // per-cycle state
   size_t n_robots = 0;
   int t_cap = 0;
@@ -443,7 +450,8 @@ void resolve_cycle_timing(b200lp_ctx* ctx) {
   ctx->cycle_timing_pending = false;
 }
 
-int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_result* outs, bool plan_resident = false) {
+int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_result* outs, bool plan_resident = false,
+              bool exchange = false) {
   // inputs are already staged in h_robots / h_plan7 (pinned); total plan poses in plan_total
   const int t_cap = traj_cap(ctx->C.par);
   const size_t T = n_robots * (size_t)t_cap;
@@ -561,12 +569,19 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
       ctx->C, ctx->grid, ctx->d_robots.p, ctx->d_meta.p, (int)n_robots, t_cap, cap_local, ctx->d_rec_vel.p,
       ctx->d_rec_steps.p, ctx->d_rec_pose_off.p, ctx->d_poses.p, ctx->d_rec_pp.p, ctx->d_plan_pts.p, ctx->d_cost.p,
       ctx->d_scores.p, ctx->d_first_hit.p, ctx->d_work.p, ctx->d_partial.p, ctx->d_tickets2.p, ctx->d_results.p,
-      direct ? ctx->h_direct.p : nullptr, ctx->direct_seq);
+      (direct && !exchange) ? ctx->h_direct.p : nullptr, ctx->direct_seq);
   CK(cudaEventRecord(ctx->ev[5], ctx->stream));
   if (n_robots > 1) {  // a single robot's argmin is folded into plan_kernel
     argmin_kernel<<<dim3((unsigned)argmin_ctas, (unsigned)n_robots), kArgminThreads, 0, ctx->stream>>>(
         ctx->C, ctx->d_meta.p, t_cap, ctx->d_rec_vel.p, ctx->d_cost.p, ctx->d_first_hit.p, ctx->d_partial.p,
         ctx->d_tickets2.p, ctx->d_results.p, ctx->d_work.p);
+    ++ctx->launches;
+  }
+  if (exchange) {  // the cross-GPU argmin through peer memory; its last lane hands the global result to the host
+    ++ctx->peer_seq;
+    exchange_kernel<<<1, 32, 0, ctx->stream>>>(ctx->peer_table, ctx->d_peer_slots.p, ctx->peer_rank, ctx->peer_world, ctx->peer_seq,
+                                               ctx->d_results.p, ctx->d_meta.p, ctx->h_direct.p, ctx->direct_seq,
+                                               (long long)4e9 /* ~2 s of SM clocks */);
     ++ctx->launches;
   }
   ctx->launches += 2;
@@ -597,6 +612,8 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
     CK(cudaGetLastError());
   }
   ctx->meta_host.assign(ctx->h_meta.p, ctx->h_meta.p + n_robots);
+  if (exchange && (ctx->meta_host[0].error & 8))
+    return ctx->fail(B200LP_E_STATE, "plan_shard_exchange: a peer did not deliver its result within the time limit");
   for (size_t i = 0; i < n_robots; ++i) {
     if (ctx->meta_host[i].error)
       return ctx->fail(B200LP_E_INVALID, "robot %zu: a trajectory exceeds B200LP_MAX_STEPS=%d poses or the trajectory / pose list overflowed",
@@ -696,6 +713,8 @@ int b200lp_create(b200lp_ctx** out, int device, const b200lp_limits* limits, con
   return B200LP_OK;
 }
 
+static void peer_detach(b200lp_ctx* ctx);
+
 void b200lp_destroy(b200lp_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
@@ -719,6 +738,8 @@ void b200lp_destroy(b200lp_ctx* ctx) {
     if (ev) cudaEventDestroy(ev);
   for (auto& ev : ctx->cev)
     if (ev) cudaEventDestroy(ev);
+  peer_detach(ctx);
+  ctx->d_peer_slots.release();
   if (ctx->prep_stream) { cudaStreamSynchronize(ctx->prep_stream); cudaStreamDestroy(ctx->prep_stream); }
   delete ctx->pack_pool;
   ctx->h_stage.release();
@@ -772,7 +793,7 @@ int b200lp_set_plan(b200lp_ctx* ctx, const double* p, size_t n) {
   return B200LP_OK;
 }
 
-int b200lp_plan_shard(b200lp_ctx* ctx, const b200lp_query* q, int rank, int count, b200lp_result* out) {
+static int plan_shard_common(b200lp_ctx* ctx, const b200lp_query* q, int rank, int count, b200lp_result* out, bool exchange) {
   if (!ctx) return B200LP_E_INVALID;
   if (!q || !out || count < 1 || rank < 0 || rank >= count) return ctx->fail(B200LP_E_INVALID, "plan: bad argument");
   CK(cudaSetDevice(ctx->device));
@@ -782,7 +803,77 @@ int b200lp_plan_shard(b200lp_ctx* ctx, const b200lp_query* q, int rank, int coun
   CK(ctx->h_plan7.reserve(std::max<size_t>(np * 7, 7)));
   fill_robot(ctx->h_robots.p, q, 0, (int32_t)np);
   if (np && !resident) memcpy(ctx->h_plan7.p, ctx->plan_host.data(), np * 7 * sizeof(double));
-  return run_cycle(ctx, 1, rank, count, out, resident);
+  return run_cycle(ctx, 1, rank, count, out, resident, exchange);
+}
+
+int b200lp_plan_shard(b200lp_ctx* ctx, const b200lp_query* q, int rank, int count, b200lp_result* out) {
+  return plan_shard_common(ctx, q, rank, count, out, false);
+}
+
+int b200lp_peer_export(b200lp_ctx* ctx, uint8_t handle[B200LP_PEER_HANDLE_BYTES]) {
+  if (!ctx) return B200LP_E_INVALID;
+  if (!handle) return ctx->fail(B200LP_E_INVALID, "peer_export: null handle");
+  static_assert(sizeof(cudaIpcMemHandle_t) == B200LP_PEER_HANDLE_BYTES, "CUDA IPC handle size");
+  static_assert(kMaxPeers == B200LP_MAX_PEERS, "peer table size");
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->d_peer_slots.p) {
+    CK(ctx->d_peer_slots.reserve(2 * kMaxPeers));
+    CK(cudaMemsetAsync(ctx->d_peer_slots.p, 0, 2 * kMaxPeers * sizeof(PeerSlot), ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, ctx->d_peer_slots.p));
+  memcpy(handle, &h, sizeof(h));
+  return B200LP_OK;
+}
+
+static void peer_detach(b200lp_ctx* ctx) {
+  for (int r = 0; r < kMaxPeers; ++r) {
+    if (ctx->peer_opened[r]) cudaIpcCloseMemHandle(ctx->peer_opened[r]);
+    ctx->peer_opened[r] = nullptr;
+    ctx->peer_table.slots[r] = nullptr;
+  }
+  ctx->peer_rank = -1;
+  ctx->peer_world = 0;
+}
+
+int b200lp_peer_attach(b200lp_ctx* ctx, int rank, int world, const uint8_t* handles) {
+  if (!ctx) return B200LP_E_INVALID;
+  if (!handles || world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
+    return ctx->fail(B200LP_E_INVALID, "peer_attach: bad rank / world (at most %d peers)", kMaxPeers);
+  if (!ctx->d_peer_slots.p) return ctx->fail(B200LP_E_STATE, "peer_attach: call b200lp_peer_export first");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  peer_detach(ctx);
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) {
+      ctx->peer_table.slots[r] = ctx->d_peer_slots.p;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)r * B200LP_PEER_HANDLE_BYTES, sizeof(h));
+    void* p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      peer_detach(ctx);
+      (void)cudaGetLastError();
+      return ctx->fail(B200LP_E_CUDA, "peer_attach: cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+    }
+    ctx->peer_opened[r] = p;
+    ctx->peer_table.slots[r] = (PeerSlot*)p;
+  }
+  ctx->peer_rank = rank;
+  ctx->peer_world = world;
+  ctx->peer_seq = 0;
+  CK(cudaMemsetAsync(ctx->d_peer_slots.p, 0, 2 * kMaxPeers * sizeof(PeerSlot), ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return B200LP_OK;
+}
+
+int b200lp_plan_shard_exchange(b200lp_ctx* ctx, const b200lp_query* q, b200lp_result* out) {
+  if (!ctx) return B200LP_E_INVALID;
+  if (ctx->peer_world < 1) return ctx->fail(B200LP_E_STATE, "plan_shard_exchange: call b200lp_peer_attach first");
+  return plan_shard_common(ctx, q, ctx->peer_rank, ctx->peer_world, out, true);
 }
 
 int b200lp_plan(b200lp_ctx* ctx, const b200lp_query* q, b200lp_result* out) { return b200lp_plan_shard(ctx, q, 0, 1, out); }

@@ -1045,6 +1045,88 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, const Robot
   }
 }
 
+// =============================================================================================
+// Sample-sharded cycles: the cross-GPU argmin through peer device memory.
+// Every rank owns 2 x kMaxPeers slots (double-buffered by the cycle's sequence number) that its peers can write over
+// NVLink (CUDA IPC mapping). After plan_kernel one warp stores this rank's local best into slot [rank] of EVERY peer
+// (payload, system-wide fence, then the sequence word), polls its own slots until all `world` of them carry this
+// cycle's sequence number, reduces them with the reference's rule (min cost, ties -> largest id: local_planner.cpp:460)
+// and hands the GLOBAL best to the spinning host thread like a single-robot cycle does. No host-launched collective,
+// no stream synchronisation: the exchange costs one NVLink store round plus the skew between the ranks.
+// Double buffering is enough: a peer can only be one cycle ahead (its cycle k+1 exchange needs our cycle k+1 store, which
+// is stream-ordered after our cycle k reads).
+// =============================================================================================
+constexpr int kMaxPeers = 16;
+struct alignas(16) PeerSlot {  // 64 bytes
+  unsigned long long cost_bits;  // ~0 = this rank has no feasible trajectory
+  int32_t id;                    // GLOBAL trajectory id
+  int32_t pad;
+  double xv, yv, thetav;         // the winner's velocities travel with it: only its owner has them
+  unsigned long long pad2;
+  unsigned long long seq;        // written last
+};
+static_assert(sizeof(PeerSlot) == 64, "PeerSlot layout");
+struct PeerTable {
+  PeerSlot* slots[kMaxPeers];  // base of every rank's slot array in THIS process's address space
+};
+
+__global__ void __launch_bounds__(32) exchange_kernel(PeerTable peers, PeerSlot* mine, int rank, int world, unsigned long long seq,
+                                                      b200lp_result* __restrict__ results, const RobotMeta* __restrict__ meta,
+                                                      DirectOut* direct, unsigned long long direct_seq, long long timeout_cycles) {
+  const int lane = threadIdx.x;
+  const int buf = (int)(seq & 1ull);
+  const b200lp_result r = results[0];
+  if (lane < world) {
+    PeerSlot* dst = peers.slots[lane] + buf * kMaxPeers + rank;
+    dst->cost_bits = (r.best_id < 0) ? ~0ull : lpm::d2u(r.best_cost);
+    dst->id = r.best_id;
+    dst->pad = 0;
+    dst->xv = r.xv; dst->yv = r.yv; dst->thetav = r.thetav;
+    dst->pad2 = 0ull;
+    __threadfence_system();
+    *(volatile unsigned long long*)&dst->seq = seq;
+  }
+  unsigned long long cb = ~0ull;
+  int id = -1;
+  double xv = 0.0, yv = 0.0, thetav = 0.0;
+  bool timed_out = false;
+  if (lane < world) {
+    const volatile PeerSlot* src = mine + buf * kMaxPeers + lane;
+    const long long t0 = clock64();
+    while (src->seq != seq) {
+      if (clock64() - t0 > timeout_cycles) { timed_out = true; break; }
+    }
+    __threadfence_system();
+    if (!timed_out) {
+      cb = src->cost_bits; id = src->id;
+      xv = src->xv; yv = src->yv; thetav = src->thetav;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long ocb = __shfl_xor_sync(kFull, cb, o);
+    const int oid = __shfl_xor_sync(kFull, id, o);
+    const double oxv = __shfl_xor_sync(kFull, xv, o), oyv = __shfl_xor_sync(kFull, yv, o), oth = __shfl_xor_sync(kFull, thetav, o);
+    if (better(ocb, oid, cb, id)) { cb = ocb; id = oid; xv = oxv; yv = oyv; thetav = oth; }
+  }
+  const unsigned any_timeout = __ballot_sync(kFull, timed_out);
+  if (lane == 0) {
+    b200lp_result g = r;  // n_samples / n_traj / n_collided / n_poses stay this shard's
+    g.best_id = (cb == ~0ull) ? -1 : id;
+    g.best_cost = (cb == ~0ull) ? -1.0 : lpm::u2d(cb);
+    g.xv = (cb == ~0ull) ? 0.0 : xv;
+    g.yv = (cb == ~0ull) ? 0.0 : yv;
+    g.thetav = (cb == ~0ull) ? 0.0 : thetav;
+    results[0] = g;
+    RobotMeta m = meta[0];
+    if (any_timeout) m.error |= 8;  // a peer did not deliver in time
+    direct->r = g;
+    direct->m = m;
+    __threadfence_system();
+    *(volatile unsigned long long*)&direct->seq = direct_seq;
+  }
+}
+
 // Local_Planner::getBestTrajectory (local_planner.cpp:447-480) over the costs plan_kernel wrote (fleet launches).
 // grid = (B, robots): B CTAs split a robot's trajectory range, the last one to finish (ticket) merges the B
 // partials and writes b200lp_result. The (cost bits, id) order is total, so any merge tree gives the reference's

@@ -61,3 +61,33 @@ def shard_range(n: int, rank: int, count: int):
     """[lo, hi) of n units for shard `rank` of `count` — the same split b200lp_plan_shard applies to the sample grid
     and the one fleet sharding applies to robots."""
     return n * rank // count, n * (rank + 1) // count
+
+
+def attach_peer_exchange(planner, device=None, group=None) -> bool:
+    """Set the peer-memory argmin exchange up for ``planner`` (a LocalPlanner) in the current process group: gather every
+    rank's 64-byte CUDA IPC handle with one all-gather and attach. Returns False (and leaves the planner on the
+    all-reduce path) when the box does not allow it; the decision is agreed on by all ranks."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    ok = 1
+    try:
+        mine = planner.peer_export()
+    except Exception:
+        mine, ok = bytes(64), 0
+    t = torch.tensor(list(mine) + [ok], dtype=torch.uint8, device=device)
+    gathered = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(gathered, t, group=group)
+    rows = [bytes(g.cpu().tolist()) for g in gathered]
+    if not all(r[64] for r in rows):
+        return False
+    try:
+        planner.peer_attach(rank, [r[:64] for r in rows])
+        ok = 1
+    except Exception:
+        ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    return bool(int(flag.cpu()[0]))

@@ -171,6 +171,26 @@ class LocalPlanner:
         self._results = [r]
         return r
 
+    # -- sample sharding with the argmin exchanged through peer device memory ---------
+    def peer_export(self) -> bytes:
+        h = (C.c_uint8 * abi.PEER_HANDLE_BYTES)()
+        self._ck(self.lib.b200lp_peer_export(self.h, h))
+        return bytes(h)
+
+    def peer_attach(self, rank: int, handles) -> None:
+        """handles: the peer_export() bytes of every rank, in rank order (this rank's own included)."""
+        blob = b"".join(handles)
+        arr = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        self._ck(self.lib.b200lp_peer_attach(self.h, int(rank), len(handles), arr))
+
+    def plan_shard_exchange(self, q: abi.Query) -> abi.Result:
+        """plan_shard(rank, world) of the attached group + the in-kernel exchange: the GLOBAL best on every rank."""
+        r = abi.Result()
+        self._ck(self.lib.b200lp_plan_shard_exchange(self.h, C.byref(q), C.byref(r)))
+        self.last, self._n_robots = r, 1
+        self._results = [r]
+        return r
+
     def plan_batch(self, queries, plans, plan_offsets):
         """queries: ctypes array of abi.Query; plans: (sum,7) float64; plan_offsets: (n+1,) int64."""
         n = len(queries)

@@ -17,6 +17,9 @@
  *   b200lp_plan              <- initializeTheories_wi_Shared_data() + the rollout loop + getBestTrajectory()
  *                               (local_planner.cpp:535-587; LP/trajectory_generators/src/stacked_generator.cpp:67-111;
  *                                LP/mpc_critics/src/stacked_scoring_model.cpp:75-93; local_planner.cpp:447-480).
+ *   b200lp_plan_shard / b200lp_plan_shard_exchange / b200lp_peer_* <- the same cycle with the velocity samples split over
+ *                               several GPUs (no reference analogue), argmin exchanged by the caller's collective or through
+ *                               peer device memory over NVLink.
  *   b200lp_plan_batch        <- the same cycle for many independent robots (fleet sharding; no reference analogue,
  *                               one reference process serves one robot).
  *   b200lp_traj_count /
@@ -51,7 +54,7 @@
 extern "C" {
 #endif
 
-#define B200LP_ABI_VERSION 4
+#define B200LP_ABI_VERSION 5
 
 /* status codes */
 #define B200LP_OK 0
@@ -205,6 +208,20 @@ int b200lp_plan(b200lp_ctx* ctx, const b200lp_query* q, b200lp_result* out);
  * best_id is the GLOBAL trajectory id, n_traj/n_poses/n_collided count the local shard. The caller
  * reduces (best_cost, best_id) across shards: min cost, ties -> largest id (local_planner.cpp:460). */
 int b200lp_plan_shard(b200lp_ctx* ctx, const b200lp_query* q, int rank, int count, b200lp_result* out);
+
+/* The same exchange through peer device memory instead of a host-launched collective (one process per GPU on one
+ * NVLink / NVSwitch box). Set-up, once: every rank calls b200lp_peer_export, the 64-byte handles are gathered by whatever
+ * transport the application has (torch.distributed, MPI, a socket), every rank calls b200lp_peer_attach with all of them.
+ * Per cycle: b200lp_plan_shard_exchange scores shard `rank` of `world`, stores its local best into every peer's slot over
+ * NVLink from a kernel, waits — in that kernel — for the peers' stores, applies the reference rule (min cost, ties ->
+ * largest id) and returns the GLOBAL best_id / best_cost / xv / yv / thetav on every rank (n_samples, n_traj, n_collided,
+ * n_poses stay the local shard's). All ranks must call it the same number of times; a peer that does not deliver within
+ * about two seconds fails the call with B200LP_E_STATE. */
+#define B200LP_PEER_HANDLE_BYTES 64
+#define B200LP_MAX_PEERS 16
+int b200lp_peer_export(b200lp_ctx* ctx, uint8_t handle[B200LP_PEER_HANDLE_BYTES]);
+int b200lp_peer_attach(b200lp_ctx* ctx, int rank, int world, const uint8_t* handles /* world * B200LP_PEER_HANDLE_BYTES */);
+int b200lp_plan_shard_exchange(b200lp_ctx* ctx, const b200lp_query* q, b200lp_result* out);
 
 /* Fleet cycle: n_robots independent queries on the shared cloud. Robot i's prune plan is
  * plans[plan_offsets[i] .. plan_offsets[i+1]) (7 doubles per pose). */

@@ -418,6 +418,93 @@ def test_sample_sharding_over_nccl_two_gpus():
     assert got[0][3] + got[1][3] == r_o.n_poses
 
 
+def _peer_exchange_worker(rank, world, device, q_in, q_out, n_cycles):
+    """One process of a sample-sharded group whose argmin travels through peer device memory (no torch.distributed)."""
+    sc = synth.c1_ramp()
+    gpu = LocalPlanner(sc.config, device=device)
+    gpu.set_cloud(sc.cloud)
+    gpu.set_plan(sc.plan)
+    q_out.put((rank, "handle", gpu.peer_export()))
+    handles = q_in.get(timeout=300)
+    gpu.peer_attach(rank, handles)
+    out = []
+    for c in range(n_cycles):
+        tw = [sc.twist[0] - 0.05 * c, 0.0, 0.04 * c - 0.1]
+        r = gpu.plan_shard_exchange(make_query(sc.pose, tw))
+        out.append((r.best_id, r.best_cost, r.xv, r.yv, r.thetav, r.n_poses, r.n_traj))
+    q_out.put((rank, "results", out))
+    gpu.close()
+
+
+def _run_peer_group(world, devices, n_cycles=6):
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q_out = ctx.Queue()
+    q_ins = [ctx.Queue() for _ in range(world)]
+    procs = [ctx.Process(target=_peer_exchange_worker, args=(r, world, devices[r], q_ins[r], q_out, n_cycles)) for r in range(world)]
+    for p in procs:
+        p.start()
+    handles = {}
+    while len(handles) < world:
+        rank, kind, payload = q_out.get(timeout=300)
+        assert kind == "handle"
+        handles[rank] = payload
+    for qi in q_ins:
+        qi.put([handles[r] for r in range(world)])
+    results = {}
+    while len(results) < world:
+        rank, kind, payload = q_out.get(timeout=300)
+        assert kind == "results"
+        results[rank] = payload
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    return results
+
+
+def _check_peer_group(results, world, n_cycles=6):
+    sc = synth.c1_ramp()
+    gpu, ora = _pair(sc.config)
+    for c in range(n_cycles):
+        tw = [sc.twist[0] - 0.05 * c, 0.0, 0.04 * c - 0.1]
+        r_g, r_o = run_pair(gpu, ora, sc.cloud, sc.plan, sc.pose, tw)
+        want = (r_o.best_id, r_o.best_cost, r_o.xv, r_o.yv, r_o.thetav)
+        for rank in range(world):
+            assert results[rank][c][:5] == want, (c, rank, results[rank][c], want)  # every rank holds the GLOBAL best
+        assert sum(results[rank][c][5] for rank in range(world)) == r_o.n_poses
+        assert sum(results[rank][c][6] for rank in range(world)) == r_o.n_traj
+
+
+def test_peer_memory_exchange_single_rank_equals_plan():
+    sc = synth.c1_ramp()
+    gpu, ora = _pair(sc.config)
+    gpu.set_cloud(sc.cloud)
+    gpu.set_plan(sc.plan)
+    with pytest.raises(Exception):
+        gpu.plan_shard_exchange(make_query(sc.pose, sc.twist))  # not attached yet
+    gpu.peer_attach(0, [gpu.peer_export()])
+    for c in range(4):
+        tw = [sc.twist[0] - 0.1 * c, 0.0, 0.05 * c]
+        q = make_query(sc.pose, tw)
+        r_x = gpu.plan_shard_exchange(q)
+        r_p = gpu.plan(q)
+        assert r_x.as_dict() == r_p.as_dict()
+
+
+def test_peer_memory_exchange_two_processes_on_one_gpu():
+    """Two ranks of a sample-sharded group share GPU 0 (their kernels are time-sliced, so the in-kernel wait really waits):
+    CUDA IPC mapping, sequence numbers and double buffering over six cycles; every rank ends up with the global best the
+    oracle picks for the whole sample set."""
+    _check_peer_group(_run_peer_group(2, [0, 0]), 2)
+
+
+def test_peer_memory_exchange_over_nvlink_two_gpus():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _check_peer_group(_run_peer_group(2, [0, 1]), 2)
+
+
 def test_first_cycle_of_a_fresh_process_is_already_right():
     """Regression: the very first launch in a process (lazy module load, cold caches, wide CTA start skew) once exposed
     a look-back poll the compiler had optimised away; later launches hid it."""
