@@ -315,6 +315,7 @@ def main():
     ap.add_argument("--cpu-baseline-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--latency-cycles", type=int, default=1000)
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="C4 at N > 1: how the argmin crosses GPUs")
     ap.add_argument("--observation-scans", type=int, default=50, help="timed lidar scans through the observation producer (0: skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -379,12 +380,22 @@ def main():
         f_plans = np.ascontiguousarray(f_plans, np.float64)
         f_offs = np.ascontiguousarray(f_offs, np.int64)
 
+    # sample sharding over several GPUs: exchange the argmin through peer memory when the box allows CUDA IPC between the
+    # ranks (--exchange nccl keeps the single NCCL all-reduce of 16*W bytes)
+    peer_exchange = False
+    if mode == "shard" and world > 1 and args.exchange == "peer":
+        from dddmr_navigation_b200.dist import attach_peer_exchange
+        peer_exchange = attach_peer_exchange(lp, device=torch.device("cuda", local_rank))
+
     def cycle():
         """One step of the hot path on resident inputs -> (poses scored on this rank, result summary)."""
         if mode == "fleet":
             res = lp.plan_batch(qs, f_plans, f_offs)
             return sum(int(r.n_poses) for r in res), res[0]
         if mode == "shard":
+            if peer_exchange:  # the argmin travels through peer device memory inside the cycle's last kernel
+                r = lp.plan_shard_exchange(q)
+                return int(r.n_poses), r
             r = lp.plan_shard(q, rank, world)
             if world > 1:
                 from dddmr_navigation_b200.dist import allreduce_best
@@ -500,7 +511,9 @@ def main():
                    "cloud_stride_bytes": stride, "timing": "CUDA events on the library stream; L2 flushed (256 MiB memset) between steps",
                    "parallelism": ({"single": "1 robot per GPU issuing the named query, map replicated (fleet sharding, no collective)",
                                     "fleet": f"{FLEET_ROBOTS_PER_GPU} robots per GPU, map replicated (fleet sharding, no collective)",
-                                    "shard": "sample grid split over the ranks, one 16*W-byte all-reduce per cycle (NCCL)"}[mode]
+                                    "shard": ("sample grid split over the ranks, argmin exchanged through peer device memory over NVLink inside "
+                                              "the cycle (exchange_kernel)" if peer_exchange else
+                                              "sample grid split over the ranks, one 16*W-byte all-reduce per cycle (NCCL)")}[mode]
                                    if world > 1 or mode != "single" else "single GPU"),
                    "grid": lp.grid_info()},
         "cpu_affinity": (f"{len(numa)} CPUs local to the GPU: {numa[0]}-{numa[-1]}" if isinstance(numa, list) and numa else str(numa)),
