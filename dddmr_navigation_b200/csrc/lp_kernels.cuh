@@ -487,8 +487,70 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
   if (!sampling_on) n_raw = 0;
   else if (P.theory == B200LP_THEORY_DD_ROTATE_INPLACE) n_raw = 2;
   else n_raw = s_n[0] * nys * nths;
-  const long long lo = (long long)n_raw * shard_rank / shard_count;
-  const long long hi = (long long)n_raw * (shard_rank + 1) / shard_count;
+  // ---- sample shard of this launch: a contiguous range [lo, hi) of the sample grid, balanced by estimated work ----
+  // The grid is ordered by rising linear speed and a trajectory's cost grows with its pose count
+  // ceil(max(|v| T / g, |w| T / g_a)), so equal sample counts leave the last rank with about twice the poses of the first
+  // (C4 on 8 GPUs: 0.23 vs 0.34 ms). Every CTA of every rank evaluates the same closed-form estimate per linear-speed row
+  // (|w| taken as uniform over the angular axis, plus a fixed per-trajectory term), prefix-sums it and cuts the rows at
+  // equal shares; identical arithmetic on identical inputs, so all ranks agree on the cuts without talking.
+  long long lo = (long long)n_raw * shard_rank / shard_count;
+  long long hi = (long long)n_raw * (shard_rank + 1) / shard_count;
+  if (shard_count > 1 && sampling_on && P.theory != B200LP_THEORY_DD_ROTATE_INPLACE && n_raw > 0) {
+    __shared__ float s_w[kMaxAxis];
+    __shared__ long long s_cut[2];
+    const int nx = s_n[0];
+    const long long row = (long long)nys * nths;
+    const float ta = (float)(P.sim_time / P.sim_granularity), tb = (float)(P.sim_time / P.angular_sim_granularity);
+    const float bw = fmaxf(fabsf(s_th[0]), fabsf(s_th[nths - 1])) * tb;  // largest angular step count of the axis
+    for (int ix = tid; ix < nx; ix += kPrepThreads) {
+      const float a = fabsf(s_x[ix]) * ta;
+      const float mean_steps = (a < bw) ? a + (bw - a) * (bw - a) / (2.0f * bw) : a;  // E[max(a, U(0, bw))]
+      s_w[ix] = mean_steps + 10.0f;  // + the fixed part of a trajectory (work fetch, critic epilogue, prep)
+    }
+    __syncthreads();
+    if (warp == 0) {  // inclusive prefix sum over the rows: lanes own contiguous runs
+      const int per = (nx + 31) / 32, i0 = lane * per, i1 = min(nx, i0 + per);
+      float run = 0.f;
+      for (int i = i0; i < i1; ++i) run += s_w[i];
+      float incl = run;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += t;
+      }
+      float acc = incl - run;
+      for (int i = i0; i < i1; ++i) {
+        acc += s_w[i];
+        s_w[i] = acc;
+      }
+    }
+    __syncthreads();
+    if (tid < 2) {
+      const int k = shard_rank + tid;  // cut number k of shard_count + 1
+      long long cut;
+      if (k <= 0) cut = 0;
+      else if (k >= shard_count) cut = n_raw;
+      else {
+        const float total = s_w[nx - 1];
+        const float target = total * (float)k / (float)shard_count;
+        int a = 0, b = nx - 1;  // smallest row whose inclusive prefix reaches the target
+        while (a < b) {
+          const int m = (a + b) >> 1;
+          if (s_w[m] >= target) b = m; else a = m + 1;
+        }
+        const float prev = a ? s_w[a - 1] : 0.f;
+        const float span = s_w[a] - prev;
+        float frac = span > 0.f ? (target - prev) / span : 0.f;
+        frac = fminf(fmaxf(frac, 0.f), 1.f);
+        cut = (long long)a * row + (long long)(frac * (float)row);
+        cut = max((long long)a * row, min(cut, (long long)(a + 1) * row));
+      }
+      s_cut[tid] = cut;
+    }
+    __syncthreads();
+    lo = s_cut[0];
+    hi = s_cut[1];
+  }
 
   // ---- this chunk's samples: one per thread ----
   const int s = chunk * kPrepThreads + tid;

@@ -203,9 +203,11 @@ int b200lp_set_plan(b200lp_ctx* ctx, const double* xyz_qxyzw, size_t n);
 /* One local-plan cycle for one robot. */
 int b200lp_plan(b200lp_ctx* ctx, const b200lp_query* q, b200lp_result* out);
 
-/* Sample-sharded cycle: this ctx scores only the contiguous sample range of shard `rank` of `count`
- * (samples [rank*S/count, (rank+1)*S/count)); ids and counters in `out` stay global / local resp.:
- * best_id is the GLOBAL trajectory id, n_traj/n_poses/n_collided count the local shard. The caller
+/* Sample-sharded cycle: this ctx scores only shard `rank` of `count` — a contiguous range of the velocity-sample grid.
+ * The cuts are placed at equal shares of the estimated pose count (the grid is ordered by rising linear speed, and fast
+ * trajectories have more poses), computed on the device from the query alone, so every rank derives the same cuts;
+ * b200lp_traj_count reports the trajectory-id range that was scored. ids and counters in `out` stay global / local
+ * resp.: best_id is the GLOBAL trajectory id, n_traj/n_poses/n_collided count the local shard. The caller
  * reduces (best_cost, best_id) across shards: min cost, ties -> largest id (local_planner.cpp:460). */
 int b200lp_plan_shard(b200lp_ctx* ctx, const b200lp_query* q, int rank, int count, b200lp_result* out);
 
