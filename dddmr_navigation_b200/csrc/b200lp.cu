@@ -1111,7 +1111,7 @@ int b200lp_sensor_observation(b200lp_ctx* ctx, int sensor, const void* scan, siz
   if (sensor < 0 || sensor >= B200LP_MAX_SENSORS) return ctx->fail(B200LP_E_INVALID, "sensor_observation: sensor index out of range");
   if (!sp || !base_from_sensor || !global_from_base || (n && !scan) || stride < 12 || (stride & 3))
     return ctx->fail(B200LP_E_INVALID, "sensor_observation: bad argument");
-  if (n > 0x7fffffffull) return ctx->fail(B200LP_E_INVALID, "sensor_observation: more than 2^31 points");
+  if (n > ((size_t)1 << 26)) return ctx->fail(B200LP_E_INVALID, "sensor_observation: more than 2^26 points in one scan");
   ObsDev P{};
   transform_to_rows(base_from_sensor, P.m1);
   transform_to_rows(global_from_base, P.m2);

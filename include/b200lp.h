@@ -302,7 +302,7 @@ typedef struct b200lp_observation_info {
  * The result is sensor `sensor`'s current observation (Sensor::sensor_current_observation_), kept on the device.
  * Voxels leave in ascending voxel-index order like pcl::VoxelGrid; inside a voxel the points are added in scan order
  * (PCL adds them in the order an unstable sort of the voxel indices leaves them).
- * B200LP_E_INVALID when the window holds more than 2^27 voxels of that leaf. */
+ * B200LP_E_INVALID when the window holds more than 2^27 voxels of that leaf or the scan more than 2^26 points. */
 int b200lp_sensor_observation(b200lp_ctx* ctx, int sensor, const void* scan, size_t n, size_t stride_bytes,
                               const double base_from_sensor[7], const double global_from_base[7],
                               const b200lp_sensor_params* params, b200lp_observation_info* info /* may be NULL */);
