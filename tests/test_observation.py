@@ -85,6 +85,18 @@ def test_empty_scan_and_empty_window_give_an_empty_observation():
     assert info.n_window == 0 and info.n_points == 0
 
 
+def test_voxel_grid_leaves_the_cloud_alone_when_its_indices_would_overflow():
+    """pcl::VoxelGrid::applyFilter: (dx*dy*dz) > INT32_MAX -> "Leaf size is too small for the input dataset", output = input.
+    (The device path refuses such windows up front with B200LP_E_INVALID; see test_gpu_empty_scan_empty_window_and_error_paths.)"""
+    scan = rows((-4000.0, -4000.0, 0.5), (4000.0, 4000.0, 90.0), (1.0, 1.0, 1.0), (1.0005, 1.0005, 1.0005))
+    info, obs = O.sensor_observation(scan, ID7, ID7, 5000.0, 100.0, leaf=0.01, is_local_planner=False)
+    assert info.n_window == 4 and info.n_points == 4
+    assert_same_array(obs[:, :3], scan[:, :3], "unfiltered output")
+    # the same four points with a leaf that fits: the two close ones merge
+    info, obs = O.sensor_observation(scan, ID7, ID7, 5000.0, 100.0, leaf=10.0, is_local_planner=False)  # 800 x 800 x 9 voxels
+    assert info.n_points == 3
+
+
 def test_summation_order_only_moves_centroids_by_rounding():
     scan, b2s, g2b = synth.lidar_scan(n_beams=64, n_azimuth=2048)
     i0, a = O.sensor_observation(scan, b2s, g2b, 10.0, 2.0, is_local_planner=False, order_mode=0)
