@@ -143,3 +143,21 @@ def test_config_from_reference_yaml_shape():
     assert arr[2].translation_weight == 1.0 and arr[2].orientation_weight == 0.01
     assert cfg.params().theory == abi.THEORY_DD_SIMPLE and cfg.limits().max_vel_x == 1.0
     assert np.allclose(cfg.cuboid()[0], [-0.35, 0.36, 0.0])  # blb first (dd_simple…cpp:211)
+
+
+def test_host_packing_pool_against_a_scalar_reference(tmp_path):
+    """The host side of the packing upload (csrc/lp_hostpack.h) needs no GPU: tests/cpp/pack_check.cpp runs the thread pool
+    over strides 16-48, sizes 0-300 001, 1-8 threads and clouds with NaN / inf points (and NaN padding) and compares the packed
+    rows, the chunk hand-over and the bounds with a scalar loop."""
+    import shutil
+    cxx = shutil.which(os.environ.get("CXX", "g++"))
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    if not cxx or not os.path.exists(os.path.join(cuda, "include", "cuda_runtime.h")):
+        pytest.skip("needs g++ and the CUDA headers")
+    exe = tmp_path / "pack_check"
+    subprocess.run([cxx, "-O2", "-std=c++17", "-pthread", "-I" + os.path.join(cuda, "include"), "-o", str(exe),
+                    os.path.join(ROOT, "tests", "cpp", "pack_check.cpp"), "-L" + os.path.join(cuda, "lib64"), "-lcudart",
+                    "-Wl,-rpath," + os.path.join(cuda, "lib64")], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:]
+    assert "0 failed" in out.stdout
