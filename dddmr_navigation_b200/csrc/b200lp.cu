@@ -1148,7 +1148,9 @@ int b200lp_sensor_observation(b200lp_ctx* ctx, int sensor, const void* scan, siz
   b200lp_observation_info I{};
   I.n_scan = (int64_t)n;
   if (n) {
-    const unsigned nb = (unsigned)((n + kObsTile - 1) / kObsTile);
+    const bool large = n >= kObsLargeScan;
+    const size_t tile = (size_t)kObsThreads * (large ? kObsItemsLarge : kObsItemsSmall);
+    const unsigned nb = (unsigned)((n + tile - 1) / tile);
     const size_t hist_n = ((size_t)1 << bits) * nb;
     const unsigned nbk = (unsigned)((hist_n + kScanItems - 1) / kScanItems);
     const unsigned nbh = (unsigned)((n + kObsHeadTile - 1) / kObsHeadTile);
@@ -1165,18 +1167,24 @@ int b200lp_sensor_observation(b200lp_ctx* ctx, int sensor, const void* scan, siz
     CK(cudaEventRecord(ctx->oev[0], st));
     CK(cudaMemcpyAsync(ctx->d_scan.p, scan, n * stride, cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(ctx->oev[2], st));
-    obs_key_kernel<<<nb, kObsThreads, 0, st>>>(ctx->d_scan.p, n, stride, P, bits, ctx->d_obs_a.p, ctx->d_obs_hist.p);
+    if (large) obs_key_kernel<kObsItemsLarge><<<nb, kObsThreads, 0, st>>>(ctx->d_scan.p, n, stride, P, bits, ctx->d_obs_a.p, ctx->d_obs_hist.p);
+    else obs_key_kernel<kObsItemsSmall><<<nb, kObsThreads, 0, st>>>(ctx->d_scan.p, n, stride, P, bits, ctx->d_obs_a.p, ctx->d_obs_hist.p);
     float4 *src = ctx->d_obs_a.p, *dst = ctx->d_obs_b.p;
     int launches = 1;
     for (int p = 0; p < passes; ++p) {
       if (p) {
-        obs_hist_kernel<<<nb, kObsThreads, 0, st>>>(src, ctx->d_obs_counts.p, p * bits, bits, ctx->d_obs_hist.p);
+        if (large) obs_hist_kernel<kObsItemsLarge><<<nb, kObsThreads, 0, st>>>(src, ctx->d_obs_counts.p, p * bits, bits, ctx->d_obs_hist.p);
+        else obs_hist_kernel<kObsItemsSmall><<<nb, kObsThreads, 0, st>>>(src, ctx->d_obs_counts.p, p * bits, bits, ctx->d_obs_hist.p);
         ++launches;
       }
       scan_block_kernel<<<nbk, 256, 0, st>>>(ctx->d_obs_hist.p, hist_n, ctx->d_obs_sums.p);
       scan_sums_kernel<<<1, 1024, 0, st>>>(ctx->d_obs_sums.p, (int)nbk, ctx->d_obs_counts.p);  // total = points in the window
-      obs_scatter_kernel<<<nb, kObsThreads, 0, st>>>(src, n, ctx->d_obs_counts.p, p == 0 ? 1 : 0, p * bits, bits, ctx->d_obs_hist.p,
-                                                     ctx->d_obs_sums.p, dst);
+      if (large)
+        obs_scatter_kernel<kObsItemsLarge><<<nb, kObsThreads, 0, st>>>(src, n, ctx->d_obs_counts.p, p == 0 ? 1 : 0, p * bits, bits,
+                                                                       ctx->d_obs_hist.p, ctx->d_obs_sums.p, dst);
+      else
+        obs_scatter_kernel<kObsItemsSmall><<<nb, kObsThreads, 0, st>>>(src, n, ctx->d_obs_counts.p, p == 0 ? 1 : 0, p * bits, bits,
+                                                                       ctx->d_obs_hist.p, ctx->d_obs_sums.p, dst);
       launches += 3;
       std::swap(src, dst);
     }

@@ -23,8 +23,10 @@
 namespace lp {
 
 constexpr int kObsThreads = 256;
-constexpr int kObsItems = 16;                         // records per thread in the sort passes
-constexpr int kObsTile = kObsThreads * kObsItems;     // 4096 records per CTA
+// records per thread in the sort passes (template parameter kItems): 16 (4096 records per CTA) for scans of millions of
+// points, 4 (1024 per CTA) below that so that a lidar revolution of a few hundred thousand points still covers every SM
+constexpr int kObsItemsLarge = 16, kObsItemsSmall = 4;
+constexpr size_t kObsLargeScan = (size_t)1 << 21;
 constexpr int kObsMaxBits = 10;                       // radix digit width (<= 10: 8 warps x 1024 counters = 32 KB smem)
 constexpr int kObsHeadTile = 1024;                    // records per CTA in the head / centroid passes
 constexpr uint32_t kObsInvalid = 0xffffffffu;         // key of a point the pass-through filters dropped
@@ -51,16 +53,17 @@ __device__ __forceinline__ float3 obs_transform(const double* m, float3 p) {
 
 // Pass 1: transform, pass-through, voxel key; per-CTA histogram of the first radix digit.
 // hist layout: [digit][cta] (digit-major), so that one exclusive scan yields every (digit, cta) output offset.
+template <int kItems>
 __global__ void __launch_bounds__(kObsThreads) obs_key_kernel(const char* __restrict__ raw, size_t n, size_t stride, ObsDev P,
                                                               int bits, float4* __restrict__ rec, uint32_t* __restrict__ hist) {
   __shared__ uint32_t s_h[1 << kObsMaxBits];
   const int nbins = 1 << bits;
   for (int b = threadIdx.x; b < nbins; b += kObsThreads) s_h[b] = 0u;
   __syncthreads();
-  const size_t base = (size_t)blockIdx.x * kObsTile;
+  const size_t base = (size_t)blockIdx.x * (kObsThreads * kItems);
   const uint32_t mask = (uint32_t)nbins - 1u;
 #pragma unroll 4
-  for (int k = 0; k < kObsItems; ++k) {
+  for (int k = 0; k < kItems; ++k) {
     const size_t i = base + (size_t)k * kObsThreads + threadIdx.x;
     if (i >= n) break;
     const float3 v = obs_transform(P.m1, load_xyz(raw, i, stride));
@@ -80,17 +83,18 @@ __global__ void __launch_bounds__(kObsThreads) obs_key_kernel(const char* __rest
 }
 
 // Per-CTA digit histogram of a later pass (records are compact by then: n_kept of them, count read from the device).
+template <int kItems>
 __global__ void __launch_bounds__(kObsThreads) obs_hist_kernel(const float4* __restrict__ rec, const uint32_t* __restrict__ n_ptr,
                                                                int shift, int bits, uint32_t* __restrict__ hist) {
   __shared__ uint32_t s_h[1 << kObsMaxBits];
   const int nbins = 1 << bits;
   for (int b = threadIdx.x; b < nbins; b += kObsThreads) s_h[b] = 0u;
   __syncthreads();
-  const size_t n = *n_ptr, base = (size_t)blockIdx.x * kObsTile;
+  const size_t n = *n_ptr, base = (size_t)blockIdx.x * (kObsThreads * kItems);
   const uint32_t mask = (uint32_t)nbins - 1u;
   if (base < n) {
 #pragma unroll 4
-    for (int k = 0; k < kObsItems; ++k) {
+    for (int k = 0; k < kItems; ++k) {
       const size_t i = base + (size_t)k * kObsThreads + threadIdx.x;
       if (i >= n) break;
       atomicAdd(&s_h[(__float_as_uint(__ldg(rec + i).w) >> shift) & mask], 1u);
@@ -103,11 +107,12 @@ __global__ void __launch_bounds__(kObsThreads) obs_hist_kernel(const float4* __r
 // Stable scatter of one radix pass. `hist` holds the block-local exclusive scan of the [digit][cta] counts and
 // `scan_sums` the scanned block totals of that scan (scan_block_kernel / scan_sums_kernel), so the first output slot of
 // (digit, cta) is hist[i] + scan_sums[i / kScanItems]. Warp w of a CTA owns the contiguous sub-tile
-// [w * 32 * kObsItems, (w+1) * 32 * kObsItems) of the CTA's tile and walks it 32 records at a time: a record's rank among
+// [w * 32 * kItems, (w+1) * 32 * kItems) of the CTA's tile and walks it 32 records at a time: a record's rank among
 // the records of its digit is (same digit in earlier warps) + (same digit earlier in this warp) + (same digit in lower
 // lanes of this row) — the three terms come from a cross-warp scan of per-warp counters, the counter value when the row
 // is processed, and __match_any_sync. Input order is preserved inside every digit: the sort is stable.
 // first_pass: n is the scan size and dropped records (key == kObsInvalid) are skipped; otherwise n comes from n_ptr.
+template <int kItems>
 __global__ void __launch_bounds__(kObsThreads) obs_scatter_kernel(const float4* __restrict__ in, size_t n_static,
                                                                   const uint32_t* __restrict__ n_ptr, int first_pass, int shift,
                                                                   int bits, const uint32_t* __restrict__ hist,
@@ -115,7 +120,7 @@ __global__ void __launch_bounds__(kObsThreads) obs_scatter_kernel(const float4* 
                                                                   float4* __restrict__ out) {
   __shared__ uint32_t s_wh[kObsThreads / 32][1 << kObsMaxBits];
   const size_t n = first_pass ? n_static : (size_t)*n_ptr;
-  const size_t tile = (size_t)blockIdx.x * kObsTile;
+  const size_t tile = (size_t)blockIdx.x * (kObsThreads * kItems);
   if (tile >= n) return;
   const int nbins = 1 << bits, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t mask = (uint32_t)nbins - 1u;
@@ -124,10 +129,10 @@ __global__ void __launch_bounds__(kObsThreads) obs_scatter_kernel(const float4* 
     for (int w = 0; w < kObsThreads / 32; ++w) s_wh[w][b] = 0u;
   }
   __syncthreads();
-  const size_t wbase = tile + (size_t)warp * 32 * kObsItems;
-  uint32_t packed[kObsItems];  // digit << 16 | rank inside the warp's sub-tile; ~0 = not a live record
+  const size_t wbase = tile + (size_t)warp * 32 * kItems;
+  uint32_t packed[kItems];  // digit << 16 | rank inside the warp's sub-tile; ~0 = not a live record
 #pragma unroll
-  for (int r = 0; r < kObsItems; ++r) {
+  for (int r = 0; r < kItems; ++r) {
     const size_t i = wbase + (size_t)r * 32 + lane;
     uint32_t key = kObsInvalid;
     if (i < n) key = __float_as_uint(__ldg(in + i).w);
@@ -158,7 +163,7 @@ __global__ void __launch_bounds__(kObsThreads) obs_scatter_kernel(const float4* 
   }
   __syncthreads();
 #pragma unroll
-  for (int r = 0; r < kObsItems; ++r) {
+  for (int r = 0; r < kItems; ++r) {
     if (packed[r] == 0xffffffffu) continue;
     const size_t i = wbase + (size_t)r * 32 + lane;
     out[s_wh[warp][packed[r] >> 16] + (packed[r] & 0xffffu)] = __ldg(in + i);

@@ -136,6 +136,14 @@ def test_gpu_observation_is_bit_identical_to_the_oracle_over_scan_sizes(gpu, n_b
 
 
 @pytest.mark.gpu
+def test_gpu_observation_of_a_stitched_scan_of_millions_of_points(gpu):
+    """>= 2^21 points switch the sort passes to 4096-record tiles (16 records per thread)."""
+    scan, b2s, g2b = synth.lidar_scan(n_beams=1100, n_azimuth=2048, seed=77)
+    assert scan.shape[0] >= (1 << 21)
+    check_against_oracle(gpu, scan, b2s, g2b, 10.0, 2.0)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("window,height,leaf,local", [(5.0, 1.5, 0.1, True), (10.0, 2.0, 0.1, False), (20.5, 2.5, 0.1, True),
                                                       (8.0, 2.0, 0.05, True), (8.0, 2.0, 0.25, False), (60.0, 3.0, 0.1, True),
                                                       (3.0, 0.4, 0.1, True)])
