@@ -43,8 +43,28 @@ def run_case(sc):
     return out
 
 
+OBSERVATION_CASES = {  # name -> (lidar_scan kwargs, window, marking_height, leaf, is_local_planner)
+    "observation_16x512": (dict(n_beams=16, n_azimuth=512, seed=synth.SEED0 + 60), 10.0, 2.0, 0.1, True),
+    "observation_24x700_base_frame": (dict(n_beams=24, n_azimuth=700, seed=synth.SEED0 + 61, room=(30.0, 20.0, 3.0), n_pillars=30),
+                                      6.0, 1.2, 0.25, False),
+}
+
+
+def run_observation(name):
+    """the restated cbSensor filter chain on a seeded synthetic scan (only the output is stored)."""
+    kw, window, height, leaf, local = OBSERVATION_CASES[name]
+    scan, b2s, g2b = synth.lidar_scan(**kw)
+    info, obs = O.sensor_observation(scan, b2s, g2b, window, height, leaf, local)
+    return {"n_scan": np.asarray(info.n_scan), "n_window": np.asarray(info.n_window), "n_points": np.asarray(info.n_points),
+            "observation": obs}
+
+
 if __name__ == "__main__":
     O.build()
+    for name in OBSERVATION_CASES:
+        out = run_observation(name)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print(name, int(out["n_scan"]), int(out["n_window"]), int(out["n_points"]))
     for name, sc in cases():
         out = run_case(sc)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)

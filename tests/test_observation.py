@@ -11,6 +11,7 @@ in its scan-order mode. Against PCL's own (unstable-sort) summation order a cent
 |delta| <= (k-1) * ulp(|sum|) / k per coordinate for a voxel of k points — measured in
 test_summation_order_only_moves_centroids_by_rounding."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -20,6 +21,7 @@ from oracle import lporacle as O
 from tests.helpers import assert_result_equal, assert_same_array, assert_trajectories_equal
 
 ID7 = (0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0)
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def rows(*pts):
@@ -107,6 +109,25 @@ def test_summation_order_only_moves_centroids_by_rounding():
     assert 0 < (a != b).any(axis=1).sum() < len(a) // 2  # the order does matter for some voxels: hence the canonical order
 
 
+def _golden_observation_cases():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLDEN, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    return mg.OBSERVATION_CASES
+
+
+@pytest.mark.parametrize("name", ["observation_16x512", "observation_24x700_base_frame"])
+def test_oracle_reproduces_the_committed_observation_fixtures(name):
+    """tests/golden/*.npz (made by tests/golden/make_golden.py) pin the restated filter chain against regressions."""
+    kw, window, height, leaf, local = _golden_observation_cases()[name]
+    want = np.load(os.path.join(GOLDEN, name + ".npz"))
+    scan, b2s, g2b = synth.lidar_scan(**kw)
+    info, obs = O.sensor_observation(scan, b2s, g2b, window, height, leaf, local)
+    assert (info.n_scan, info.n_window, info.n_points) == (int(want["n_scan"]), int(want["n_window"]), int(want["n_points"]))
+    assert_same_array(obs.view(np.uint32), want["observation"].view(np.uint32), "observation bits")
+
+
 # --------------------------------------------------------------------------------------------------------------------
 # GPU: the device pipeline against the oracle
 # --------------------------------------------------------------------------------------------------------------------
@@ -150,6 +171,17 @@ def test_gpu_observation_of_a_stitched_scan_of_millions_of_points(gpu):
 def test_gpu_observation_over_windows_leaves_and_pass_counts(gpu, window, height, leaf, local):
     scan, b2s, g2b = synth.lidar_scan(n_beams=48, n_azimuth=1500, room=(60.0, 40.0, 3.0), n_pillars=60)
     check_against_oracle(gpu, scan, b2s, g2b, window, height, leaf, local)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["observation_16x512", "observation_24x700_base_frame"])
+def test_gpu_observation_reproduces_the_committed_fixtures(gpu, name):
+    kw, window, height, leaf, local = _golden_observation_cases()[name]
+    want = np.load(os.path.join(GOLDEN, name + ".npz"))
+    scan, b2s, g2b = synth.lidar_scan(**kw)
+    info = gpu.sensor_observation(5, scan, b2s, g2b, window, height, leaf, local)
+    assert (info.n_scan, info.n_window, info.n_points) == (int(want["n_scan"]), int(want["n_window"]), int(want["n_points"]))
+    assert_same_array(gpu.read_observation(5, info.n_points).view(np.uint32), want["observation"].view(np.uint32), "observation bits")
 
 
 @pytest.mark.gpu
