@@ -8,6 +8,7 @@
 // §8(f) rows 1 and 2 — run on the device through the same session.
 #ifndef B200LP_LOCAL_PLANNER_H_
 #define B200LP_LOCAL_PLANNER_H_
+#include <deque>
 #include <memory>
 #include <string>
 #include <vector>
@@ -31,10 +32,11 @@ enum PerceptionOpinion { PASS = 0, PATH_BLOCKED_WAIT = 1, PATH_BLOCKED_REPLANNIN
 // there; getObservation() (Sensor::getObservation) reads it back for host-side consumers. SURVEY.md §8(f) row 4.
 class MultiLayerSpinningLidar {
  public:
+  // stitcher_num: the `stitcher_num` parameter (:118): the last stitcher_num scans are concatenated before filtering
   MultiLayerSpinningLidar(const std::string& name, const std::string& traj_gen_name, int slot, double perception_window_size,
-                          double marking_height, bool is_local_planner)
+                          double marking_height, bool is_local_planner, int stitcher_num = 0)
       : name_(name), traj_gen_name_(traj_gen_name), slot_(slot), perception_window_size_(perception_window_size),
-        marking_height_(marking_height), is_local_planner_(is_local_planner),
+        marking_height_(marking_height), is_local_planner_(is_local_planner), stitcher_num_(stitcher_num),
         sensor_current_observation_(new pcl::PointCloud<pcl::PointXYZI>) {}
   void cbSensor(const pcl::PointCloud<pcl::PointXYZ>& pcl_msg, const geometry_msgs::msg::TransformStamped& trans_b2s,
                 const geometry_msgs::msg::TransformStamped& trans_gbl2b);
@@ -49,6 +51,8 @@ class MultiLayerSpinningLidar {
   int slot_;
   double perception_window_size_, marking_height_;
   bool is_local_planner_, observation_stale_ = false;
+  int stitcher_num_ = 0;
+  std::deque<pcl::PointCloud<pcl::PointXYZ>> pcl_stitcher_;  // multilayer_spinning_lidar.cpp:186-199
   pcl::PointCloud<pcl::PointXYZI>::Ptr sensor_current_observation_;
   b200lp_observation_info last_info_{};
 };

@@ -688,7 +688,15 @@ void MultiLayerSpinningLidar::cbSensor(const pcl::PointCloud<pcl::PointXYZ>& pcl
   sp.marking_height = marking_height_;
   sp.leaf_size = 0.1f;  // sor.setLeafSize(0.1f, 0.1f, 0.1f) (:254)
   sp.is_local_planner = is_local_planner_ ? 1 : 0;
-  last_info_ = b200lp::Session::forGenerator(traj_gen_name_)->sensorObservation(slot_, pcl_msg, trans_b2s, trans_gbl2b, sp);
+  if (stitcher_num_ <= 0) {  // "if not stitch, save copy time" (:180-183)
+    last_info_ = b200lp::Session::forGenerator(traj_gen_name_)->sensorObservation(slot_, pcl_msg, trans_b2s, trans_gbl2b, sp);
+  } else {  // :184-199 — keep the last stitcher_num scans, filter their concatenation
+    if (pcl_stitcher_.size() >= (size_t)stitcher_num_) pcl_stitcher_.pop_front();
+    pcl_stitcher_.push_back(pcl_msg);
+    pcl::PointCloud<pcl::PointXYZ> stitched;
+    for (const auto& scan : pcl_stitcher_) stitched += scan;
+    last_info_ = b200lp::Session::forGenerator(traj_gen_name_)->sensorObservation(slot_, stitched, trans_b2s, trans_gbl2b, sp);
+  }
   observation_stale_ = true;
 }
 
