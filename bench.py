@@ -537,128 +537,137 @@ def main():
 
     # ---------------- p50 cycle latency on the reference's own CPU-runnable case (C1), rank 0 ----------------
     if rank == 0 and world == 1 and args.latency_cycles > 0:
-        w1 = make_workload("C1", 0)
-        sc1, pose1, twist1, plan1 = w1["sc"], w1["pose"], w1["twist"], w1["plan"]
-        lp1 = LocalPlanner(sc1.config, device=local_rank)
-        lp1.set_cloud(sc1.cloud)
-        lp1.set_plan(plan1)
-        rng = np.random.default_rng(0)
-        lat = []
-        for i in range(args.latency_cycles + 20):
-            tw = [float(np.clip(twist1[0] + rng.uniform(-0.2, 0.0), 0.0, 1.0)), 0.0, float(rng.uniform(-0.2, 0.2))]
-            q1 = make_query(pose1, tw)
-            t0 = time.perf_counter()
-            lp1.plan(q1)
-            if i >= 20:
-                lat.append(1e3 * (time.perf_counter() - t0))
-        line["p50_cycle_latency_ms"] = {"value": statistics.median(lat), "p99": float(np.percentile(lat, 99)),
-                                        "cycles": len(lat), "workload": "C1 (520 trajectories, 200k-point map resident), perturbed twists"}
-        lp1.close()
+        try:  # an extra that fails must not cost the run its JSON line
+            w1 = make_workload("C1", 0)
+            sc1, pose1, twist1, plan1 = w1["sc"], w1["pose"], w1["twist"], w1["plan"]
+            lp1 = LocalPlanner(sc1.config, device=local_rank)
+            lp1.set_cloud(sc1.cloud)
+            lp1.set_plan(plan1)
+            rng = np.random.default_rng(0)
+            lat = []
+            for i in range(args.latency_cycles + 20):
+                tw = [float(np.clip(twist1[0] + rng.uniform(-0.2, 0.0), 0.0, 1.0)), 0.0, float(rng.uniform(-0.2, 0.2))]
+                q1 = make_query(pose1, tw)
+                t0 = time.perf_counter()
+                lp1.plan(q1)
+                if i >= 20:
+                    lat.append(1e3 * (time.perf_counter() - t0))
+            line["p50_cycle_latency_ms"] = {"value": statistics.median(lat), "p99": float(np.percentile(lat, 99)),
+                                            "cycles": len(lat), "workload": "C1 (520 trajectories, 200k-point map resident), perturbed twists"}
+            lp1.close()
+        except Exception as exc:  # noqa: BLE001
+            line["p50_cycle_latency_ms"] = {"error": f"{type(exc).__name__}: {exc}"}
 
     # ---------------- the observation producer in front of the path, rank 0 ----------------
     if rank == 0 and world == 1 and args.observation_scans > 0:
-        from oracle import lporacle as O
-        from dddmr_navigation_b200 import synth
-        scan, b2s, g2b = synth.lidar_scan(n_beams=128, n_azimuth=2048)  # 262 144 points, one revolution
-        _keep_scan, hscan = pinned_copy(scan)  # (torch tensor owning the pinned pages, numpy view)
-        win, height = 10.0, 2.0
-        for _ in range(10):
-            oi = lp.sensor_observation(0, hscan, b2s, g2b, win, height)
-        wall, dev, upl = [], [], []
-        for _ in range(args.observation_scans):
-            flush_l2()
+        try:  # an extra that fails must not cost the run its JSON line
+            from oracle import lporacle as O
+            from dddmr_navigation_b200 import synth
+            scan, b2s, g2b = synth.lidar_scan(n_beams=128, n_azimuth=2048)  # 262 144 points, one revolution
+            _keep_scan, hscan = pinned_copy(scan)  # (torch tensor owning the pinned pages, numpy view)
+            win, height = 10.0, 2.0
+            for _ in range(10):
+                oi = lp.sensor_observation(0, hscan, b2s, g2b, win, height)
+            wall, dev, upl = [], [], []
+            for _ in range(args.observation_scans):
+                flush_l2()
+                t0 = time.perf_counter()
+                oi = lp.sensor_observation(0, hscan, b2s, g2b, win, height)
+                wall.append(1e3 * (time.perf_counter() - t0))
+                dev.append(oi.ms_device)
+                upl.append(oi.ms_upload)
+            passes = (oi.n_launches - 2) // 4
+            n_s, n_w, n_o = int(oi.n_scan), int(oi.n_window), int(oi.n_points)
+            obs_bytes = 32 * n_s + (16 * n_s + 16 * n_w) + (passes - 1) * 32 * n_w + 16 * n_w + 16 * n_o
             t0 = time.perf_counter()
-            oi = lp.sensor_observation(0, hscan, b2s, g2b, win, height)
-            wall.append(1e3 * (time.perf_counter() - t0))
-            dev.append(oi.ms_device)
-            upl.append(oi.ms_upload)
-        passes = (oi.n_launches - 2) // 4
-        n_s, n_w, n_o = int(oi.n_scan), int(oi.n_window), int(oi.n_points)
-        obs_bytes = 32 * n_s + (16 * n_s + 16 * n_w) + (passes - 1) * 32 * n_w + 16 * n_w + 16 * n_o
-        t0 = time.perf_counter()
-        for _ in range(3):
-            o_info, o_obs = O.sensor_observation(scan, b2s, g2b, win, height)
-        cpu_ms = 1e3 * (time.perf_counter() - t0) / 3
-        g_obs = lp.read_observation(0, n_o)
-        d_ms = statistics.median(dev)
-        line["observation"] = {
-            "what": ("MultiLayerSpinningLidar::cbSensor filter chain (transform, 3 pass-throughs, 0.1 m voxel centroids, transform) on one "
-                     "262 144-point scan from pinned host memory; the observation stays on the device"),
-            "scan_points": n_s, "window_points": n_w, "observation_points": n_o, "radix_passes": passes, "launches": int(oi.n_launches),
-            "ms_device_p50": d_ms, "ms_upload_p50": statistics.median(upl), "ms_host_wall_p50": statistics.median(wall), "scan_points_per_sec_e2e": n_s / (statistics.median(wall) * 1e-3),
-            "roofline": {"bound": "hbm", "achieved": obs_bytes / (d_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": obs_bytes / (d_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": obs_bytes,
-                         "note": "upload + ~10 dependent launches on 4 MB of records: launch/latency-bound, not HBM-bound"},
-            "cpu_baseline": {"ms": cpu_ms, "kind": "port", "cores": 1,
-                             "sample": "3 runs of the oracle restatement of the PCL filter chain on the same scan"},
-            "matches_oracle_bits": bool(np.array_equal(g_obs.view(np.uint32), o_obs.view(np.uint32))),
-        }
-        del _keep_scan
+            for _ in range(3):
+                o_info, o_obs = O.sensor_observation(scan, b2s, g2b, win, height)
+            cpu_ms = 1e3 * (time.perf_counter() - t0) / 3
+            g_obs = lp.read_observation(0, n_o)
+            d_ms = statistics.median(dev)
+            line["observation"] = {
+                "what": ("MultiLayerSpinningLidar::cbSensor filter chain (transform, 3 pass-throughs, 0.1 m voxel centroids, transform) on one "
+                         "262 144-point scan from pinned host memory; the observation stays on the device"),
+                "scan_points": n_s, "window_points": n_w, "observation_points": n_o, "radix_passes": passes, "launches": int(oi.n_launches),
+                "ms_device_p50": d_ms, "ms_upload_p50": statistics.median(upl), "ms_host_wall_p50": statistics.median(wall), "scan_points_per_sec_e2e": n_s / (statistics.median(wall) * 1e-3),
+                "roofline": {"bound": "hbm", "achieved": obs_bytes / (d_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": obs_bytes / (d_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": obs_bytes,
+                             "note": "upload + ~10 dependent launches on 4 MB of records: launch/latency-bound, not HBM-bound"},
+                "cpu_baseline": {"ms": cpu_ms, "kind": "port", "cores": 1,
+                                 "sample": "3 runs of the oracle restatement of the PCL filter chain on the same scan"},
+                "matches_oracle_bits": bool(np.array_equal(g_obs.view(np.uint32), o_obs.view(np.uint32))),
+            }
+            del _keep_scan
+        except Exception as exc:  # noqa: BLE001
+            line["observation"] = {"error": f"{type(exc).__name__}: {exc}"}
 
     # ---------------- CPU baseline on this box's host cores (rank 0, N=1) ----------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline and mode == "single":
-        from oracle import lporacle as O
-        if O.have_reference_sources() and max(1, args.ref_stride) == 1:
-            # the reference's own sources, the FULL workload, one thread (as upstream); ~10 s per cycle at C2
-            ref = O.ReferencePlanner(sc.config)
-            ref.set_plan(plan)
-            n_cycles = max(1, min(args.cpu_baseline_steps, 2))
-            t0 = time.perf_counter()
-            cp = 0
-            for _ in range(n_cycles):
-                ref.set_cloud(sc.cloud)
-                ro = ref.plan(q)
-                cp += ro.n_poses
-            dt = time.perf_counter() - t0
-            assert ro.best_id == r.best_id, (ro.best_id, r.best_id)  # the GPU picks the trajectory the reference's own code picks
-            line["cpu_baseline"] = {
-                "value": cp / dt, "unit": UNIT, "cores": 1, "kind": "reference",
-                "sample": (f"{n_cycles} full cycle(s) of the same workload ({ro.n_poses} poses each) through the reference's own C++ "
-                           "(oracle/_ref/liblpref.so: its theory / critic / stacked-model sources compiled from /root/reference against "
-                           "stand-ins for Eigen/PCL/tf2/rclcpp, its vendored nanoflann as kd-tree), kd-tree rebuilt every cycle, "
-                           f"1 thread (the reference path is single-threaded); host has {os.cpu_count()} cores"),
-                "ms_per_cycle": 1e3 * dt / n_cycles,
-                "best_id_matches_gpu": bool(ro.best_id == r.best_id), "best_cost_matches_gpu_1e-4": bool(abs(ro.best_cost - r.best_cost) <= 1e-4 * abs(ro.best_cost)),
-            }
-            # courtesy upper bound: the oracle port with the trajectories split over every host core
-            # (the reference itself is single-threaded; the kd-tree build stays serial)
-            ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-            ora = O.OraclePlanner(sc.config, O.MATH_LIBM, O.INDEX_NANOFLANN if O.have_ref() else O.INDEX_GRID)
-            ora.set_plan(plan)
-            t0 = time.perf_counter()
-            ora.set_cloud(sc.cloud)
-            rm = ora.plan(q, ncores)
-            dtm = time.perf_counter() - t0
-            line["cpu_baseline"]["all_cores"] = {
-                "value": rm.n_poses / dtm, "unit": UNIT, "cores": ncores, "kind": "port", "ms_per_cycle": 1e3 * dtm,
-                "sample": "1 full cycle of the same workload through the oracle port, trajectories split over std::threads, index rebuilt (serial)",
-                "best_id_matches_gpu": bool(rm.best_id == r.best_id)}
-        else:
-            use_ref = O.have_ref()
-            ora = O.OraclePlanner(sc.config, O.MATH_LIBM, O.INDEX_NANOFLANN if use_ref else O.INDEX_GRID)
-            ora.set_cloud(sc.cloud)
-            ora.set_plan(plan)
-            stride_s = max(1, args.ref_stride)
-            ora.set_sample_stride(stride_s)
-            t0 = time.perf_counter()
-            cp = 0
-            for _ in range(args.cpu_baseline_steps):
-                ro = ora.plan(q, 1)
-                cp += ro.n_poses
-            dt = time.perf_counter() - t0
-            if stride_s == 1:
-                assert ro.best_id == r.best_id, (ro.best_id, r.best_id)
-            line["cpu_baseline"] = {
-                "value": cp / dt, "unit": UNIT, "cores": 1, "kind": "port",
-                "sample": (f"{args.cpu_baseline_steps} full cycles of the same workload"
-                           + ("" if stride_s == 1 else f" restricted to every {stride_s}-th velocity sample")
-                           + f" ({ro.n_poses} poses each) through the oracle port, kd-tree rebuilt every cycle; "
-                           f"index={'reference-vendored nanoflann 1.5.1 (oracle/_ref)' if use_ref else 'oracle bucket grid'}, glibc libm, "
-                           f"1 thread; host has {os.cpu_count()} cores"),
-                "ms_per_cycle": 1e3 * dt / args.cpu_baseline_steps,
-                "stages_s_last_cycle": {"index_build": ora.timing[0], "rollout": ora.timing[1], "score": ora.timing[2]},
-                "best_id_matches_gpu": bool(stride_s != 1 or ro.best_id == r.best_id),
-            }
+        try:  # an extra that fails must not cost the run its JSON line
+            from oracle import lporacle as O
+            if O.have_reference_sources() and max(1, args.ref_stride) == 1:
+                # the reference's own sources, the FULL workload, one thread (as upstream); ~10 s per cycle at C2
+                ref = O.ReferencePlanner(sc.config)
+                ref.set_plan(plan)
+                n_cycles = max(1, min(args.cpu_baseline_steps, 2))
+                t0 = time.perf_counter()
+                cp = 0
+                for _ in range(n_cycles):
+                    ref.set_cloud(sc.cloud)
+                    ro = ref.plan(q)
+                    cp += ro.n_poses
+                dt = time.perf_counter() - t0
+                assert ro.best_id == r.best_id, (ro.best_id, r.best_id)  # the GPU picks the trajectory the reference's own code picks
+                line["cpu_baseline"] = {
+                    "value": cp / dt, "unit": UNIT, "cores": 1, "kind": "reference",
+                    "sample": (f"{n_cycles} full cycle(s) of the same workload ({ro.n_poses} poses each) through the reference's own C++ "
+                               "(oracle/_ref/liblpref.so: its theory / critic / stacked-model sources compiled from /root/reference against "
+                               "stand-ins for Eigen/PCL/tf2/rclcpp, its vendored nanoflann as kd-tree), kd-tree rebuilt every cycle, "
+                               f"1 thread (the reference path is single-threaded); host has {os.cpu_count()} cores"),
+                    "ms_per_cycle": 1e3 * dt / n_cycles,
+                    "best_id_matches_gpu": bool(ro.best_id == r.best_id), "best_cost_matches_gpu_1e-4": bool(abs(ro.best_cost - r.best_cost) <= 1e-4 * abs(ro.best_cost)),
+                }
+                # courtesy upper bound: the oracle port with the trajectories split over every host core
+                # (the reference itself is single-threaded; the kd-tree build stays serial)
+                ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+                ora = O.OraclePlanner(sc.config, O.MATH_LIBM, O.INDEX_NANOFLANN if O.have_ref() else O.INDEX_GRID)
+                ora.set_plan(plan)
+                t0 = time.perf_counter()
+                ora.set_cloud(sc.cloud)
+                rm = ora.plan(q, ncores)
+                dtm = time.perf_counter() - t0
+                line["cpu_baseline"]["all_cores"] = {
+                    "value": rm.n_poses / dtm, "unit": UNIT, "cores": ncores, "kind": "port", "ms_per_cycle": 1e3 * dtm,
+                    "sample": "1 full cycle of the same workload through the oracle port, trajectories split over std::threads, index rebuilt (serial)",
+                    "best_id_matches_gpu": bool(rm.best_id == r.best_id)}
+            else:
+                use_ref = O.have_ref()
+                ora = O.OraclePlanner(sc.config, O.MATH_LIBM, O.INDEX_NANOFLANN if use_ref else O.INDEX_GRID)
+                ora.set_cloud(sc.cloud)
+                ora.set_plan(plan)
+                stride_s = max(1, args.ref_stride)
+                ora.set_sample_stride(stride_s)
+                t0 = time.perf_counter()
+                cp = 0
+                for _ in range(args.cpu_baseline_steps):
+                    ro = ora.plan(q, 1)
+                    cp += ro.n_poses
+                dt = time.perf_counter() - t0
+                if stride_s == 1:
+                    assert ro.best_id == r.best_id, (ro.best_id, r.best_id)
+                line["cpu_baseline"] = {
+                    "value": cp / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                    "sample": (f"{args.cpu_baseline_steps} full cycles of the same workload"
+                               + ("" if stride_s == 1 else f" restricted to every {stride_s}-th velocity sample")
+                               + f" ({ro.n_poses} poses each) through the oracle port, kd-tree rebuilt every cycle; "
+                               f"index={'reference-vendored nanoflann 1.5.1 (oracle/_ref)' if use_ref else 'oracle bucket grid'}, glibc libm, "
+                               f"1 thread; host has {os.cpu_count()} cores"),
+                    "ms_per_cycle": 1e3 * dt / args.cpu_baseline_steps,
+                    "stages_s_last_cycle": {"index_build": ora.timing[0], "rollout": ora.timing[1], "score": ora.timing[2]},
+                    "best_id_matches_gpu": bool(stride_s != 1 or ro.best_id == r.best_id),
+                }
+        except Exception as exc:  # noqa: BLE001
+            line["cpu_baseline"] = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank == 0:
         print(json.dumps(line), flush=True)
