@@ -1,7 +1,7 @@
 // b200lp::Session — the C++ owner of one b200lp_ctx, shared by a generator plugin and the critic plugins bound to it.
 //
 // The reference runs a cycle as: generator initialise() -> nextTrajectory() x S -> critics' shared data update ->
-// scoreTrajectory() x S x critics (local_planner.cpp:528-587). The device runs the whole cycle in ONE b200lp_plan call (three kernels back to back), so
+// scoreTrajectory() x S x critics (local_planner.cpp:528-587). The device runs the whole cycle in ONE b200lp_plan call (two kernels back to back), so
 // the plugins are adapters around a session: the generator opens the cycle, the first consumer of results triggers
 // the launch, everyone else reads cached read-backs. A session is looked up by GENERATOR NAME, which is the key the
 // reference binds critics to generators with (`<critic>.trajectory_generator`, mpc_critics_ros.cpp:71-79), so neither
