@@ -459,8 +459,10 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   for (size_t i = 0; i < n_robots; ++i) plan_total = std::max<size_t>(plan_total, ctx->h_robots.p[i].plan_off + ctx->h_robots.p[i].plan_n);
   const int nc = std::max(1, ctx->C.n_critics);
   const int n_chunks = (t_cap + kPrepThreads - 1) / kPrepThreads;
-  // upper bound on the trajectories of one robot inside one sample shard
-  const int cap_local = (int)std::min<long long>(t_cap, ((long long)t_cap + count - 1) / count + 1);
+  // Upper bound on the trajectories one launch scores per robot. A sample shard's cuts sit at equal shares of the estimated
+  // pose count, not of the sample count (prep_kernel), so a shard of slow trajectories can hold far more than t_cap / count
+  // of them: the only bound that always holds is t_cap. plan_kernel takes the real count from prep_kernel's meta.
+  const int cap_local = t_cap;
   CK(ctx->d_robots.reserve(n_robots));
   CK(ctx->d_meta.reserve(n_robots));
   if (!plan_resident) CK(ctx->d_plan7.reserve(std::max<size_t>(plan_total * 7, 7)));  // (a resident plan must not move)
@@ -615,6 +617,10 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   if (exchange && (ctx->meta_host[0].error & 8))
     return ctx->fail(B200LP_E_STATE, "plan_shard_exchange: a peer did not deliver its result within the time limit");
   for (size_t i = 0; i < n_robots; ++i) {
+    if (ctx->meta_host[i].error & 16)
+      return ctx->fail(B200LP_E_STATE, "robot %zu: plan_kernel scored %d trajectories / %lld poses where prep_kernel listed %d / %lld",
+                       i, ctx->h_results.p[i].n_traj, (long long)ctx->h_results.p[i].n_poses,
+                       ctx->meta_host[i].t_end - ctx->meta_host[i].t_begin, (long long)ctx->meta_host[i].n_poses);
     if (ctx->meta_host[i].error)
       return ctx->fail(B200LP_E_INVALID, "robot %zu: a trajectory exceeds B200LP_MAX_STEPS=%d poses or the trajectory / pose list overflowed",
                        i, B200LP_MAX_STEPS);

@@ -96,11 +96,15 @@ struct DirectOut {
   unsigned long long seq;
 };
 
-struct BlockBest {
+struct alignas(16) BlockBest {    // 32 bytes: read back with two 16-byte loads
   unsigned long long cost_bits;  // ~0 = none
   int32_t id;
   int32_t n_collided;
+  int32_t n_scored;              // trajectories this CTA actually scored (checked against prep_kernel's count)
+  int32_t pad;
+  long long poses_scored;        // sum of their num_steps
 };
+static_assert(sizeof(BlockBest) == 32, "BlockBest layout");
 
 // ---------------------------------------------------------------------------------------------
 // double-precision pose algebra (mirrors oracle: quat_to_matrix, affine_mul, affine_inverse, matrix_to_quat)

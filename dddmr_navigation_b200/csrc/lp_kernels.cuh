@@ -767,8 +767,18 @@ struct WarpCtx {
 struct Best {
   unsigned long long cb;  // cost bits, ~0 = none
   int bi, ncoll;
+  int nscored = 0;         // trajectories scored / their poses: what the launch really did, checked against prep_kernel's list
+  long long nposes = 0;
   __device__ __forceinline__ void take(unsigned long long ocb, int obi) {
     if (ocb != ~0ull && (cb == ~0ull || better(ocb, obi, cb, bi))) { cb = ocb; bi = obi; }
+  }
+  __device__ __forceinline__ void reset() { cb = ~0ull; bi = -1; ncoll = 0; nscored = 0; nposes = 0; }
+  __device__ __forceinline__ void store(BlockBest* d) const {
+    d->cost_bits = cb; d->id = bi; d->n_collided = ncoll; d->n_scored = nscored; d->pad = 0; d->poses_scored = nposes;
+  }
+  __device__ __forceinline__ void merge(const BlockBest& o) {
+    ncoll += o.n_collided; nscored += o.n_scored; nposes += o.poses_scored;
+    take(o.cost_bits, o.id);
   }
   __device__ __forceinline__ void warp_reduce() {
 #pragma unroll
@@ -776,6 +786,8 @@ struct Best {
       const unsigned long long ocb = __shfl_xor_sync(kFull, cb, o);
       const int obi = __shfl_xor_sync(kFull, bi, o);
       ncoll += __shfl_xor_sync(kFull, ncoll, o);
+      nscored += __shfl_xor_sync(kFull, nscored, o);
+      nposes += __shfl_xor_sync(kFull, nposes, o);
       take(ocb, obi);
     }
   }
@@ -793,7 +805,7 @@ struct CtaShared {
 #define B200LP_PLAN_MIN_CTAS 5
 #endif
 __global__ void __launch_bounds__(kThreads, B200LP_PLAN_MIN_CTAS)
-plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, const RobotMeta* __restrict__ meta, int n_robots,
+plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotMeta* meta, int n_robots,
             int t_cap, int cap_local, const float4* __restrict__ rec_vel, const int* __restrict__ rec_steps,
             const long long* __restrict__ rec_pose_off, const float4* __restrict__ poses,
             const double2* __restrict__ rec_pp, const float4* __restrict__ plan_pts, double* __restrict__ out_cost,
@@ -805,7 +817,11 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, const Robot
   float* stash = S.stash[warp];
   float4* pre = S.pre[warp];
   WarpCtx& W = S.wc[warp];
-  const unsigned long long total = (unsigned long long)n_robots * (unsigned long long)cap_local;
+  // Work space: (robot, local trajectory index). A single-robot launch takes its trajectory count from prep_kernel's meta
+  // (a sample shard's size is only known on the device: the cuts are balanced by poses, not by samples); fleets pad
+  // every robot to cap_local = t_cap.
+  const unsigned long long total = n_robots == 1 ? (unsigned long long)max(0, min(meta[0].t_end, t_cap) - meta[0].t_begin)
+                                                 : (unsigned long long)n_robots * (unsigned long long)cap_local;
   const int nc = C.n_critics;
 
   // single-robot launches stage the prune plan in shared memory once per CTA
@@ -1030,6 +1046,8 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, const Robot
     }
     if (fused_argmin) {
       wb.ncoll += first_hit >= 0 ? 1 : 0;
+      wb.nscored += 1;
+      wb.nposes += n;
       if (cost >= 0.0 && cost <= 9999999.0) wb.take(lpm::d2u(cost), id);  // local_planner.cpp:450,460
     }
     __syncwarp();
@@ -1039,20 +1057,14 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, const Robot
   // ---- getBestTrajectory for the single robot of this launch --------------------------------------------------
   __shared__ BlockBest s_best[kWarpsPerCta];
   __shared__ int s_last;
-  if (lane == 0) {
-    s_best[warp].cost_bits = wb.cb;
-    s_best[warp].id = wb.bi;
-    s_best[warp].n_collided = wb.ncoll;
-  }
+  if (lane == 0) wb.store(&s_best[warp]);
   __syncthreads();
   Best b = {~0ull, -1, 0};
   if (warp == 0) {
-    if (lane < kWarpsPerCta) { b.cb = s_best[lane].cost_bits; b.bi = s_best[lane].id; b.ncoll = s_best[lane].n_collided; }
+    if (lane < kWarpsPerCta) b.merge(s_best[lane]);
     b.warp_reduce();
     if (lane == 0) {
-      BlockBest pb;
-      pb.cost_bits = b.cb; pb.id = b.bi; pb.n_collided = b.ncoll;
-      partial[blockIdx.x] = pb;
+      b.store(partial + blockIdx.x);
       __threadfence();
       s_last = atomicAdd(tickets, 1u) == gridDim.x - 1 ? 1 : 0;
     }
@@ -1061,32 +1073,32 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, const Robot
   if (!s_last) return;
   // the last CTA: every other CTA has stored its partial and left the work loop; all its threads merge the partials
   __threadfence();
-  b.cb = ~0ull; b.bi = -1; b.ncoll = 0;
+  b.reset();
   for (int i = threadIdx.x; i < (int)gridDim.x; i += kThreads) {
-    const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(partial + i));  // cost bits (lo, hi), id, n_collided
-    b.ncoll += (int)raw.w;
-    b.take(((unsigned long long)raw.y << 32) | (unsigned long long)raw.x, (int)raw.z);
+    const uint4 r0 = __ldcg(reinterpret_cast<const uint4*>(partial + i));      // cost bits (lo, hi), id, n_collided
+    const uint4 r1 = __ldcg(reinterpret_cast<const uint4*>(partial + i) + 1);  // n_scored, pad, poses (lo, hi)
+    BlockBest pb;
+    pb.cost_bits = ((unsigned long long)r0.y << 32) | (unsigned long long)r0.x;
+    pb.id = (int)r0.z; pb.n_collided = (int)r0.w; pb.n_scored = (int)r1.x; pb.pad = 0;
+    pb.poses_scored = (long long)(((unsigned long long)r1.w << 32) | (unsigned long long)r1.z);
+    b.merge(pb);
   }
   b.warp_reduce();
-  if (lane == 0) {
-    s_best[warp].cost_bits = b.cb;
-    s_best[warp].id = b.bi;
-    s_best[warp].n_collided = b.ncoll;
-  }
+  if (lane == 0) b.store(&s_best[warp]);
   __syncthreads();
   if (threadIdx.x == 0) {
-    b.cb = ~0ull; b.bi = -1; b.ncoll = 0;
-    for (int w = 0; w < kWarpsPerCta; ++w) {
-      b.ncoll += s_best[w].n_collided;
-      b.take(s_best[w].cost_bits, s_best[w].id);
-    }
-    const RobotMeta m = meta[0];
+    b.reset();
+    for (int w = 0; w < kWarpsPerCta; ++w) b.merge(s_best[w]);
+    RobotMeta m = meta[0];
+    // what this launch really scored must be what prep_kernel listed for it: anything else means trajectories were
+    // skipped (work space too small, pose rows overflowed) and the argmin cannot be trusted
+    if (b.nscored != m.t_end - m.t_begin || b.nposes != m.n_poses) m.error |= 16;
     b200lp_result r;
     r.best_id = (b.cb == ~0ull) ? -1 : b.bi;
     r.n_samples = m.n_samples;
-    r.n_traj = m.t_end - m.t_begin;
+    r.n_traj = b.nscored;
     r.n_collided = b.ncoll;
-    r.n_poses = m.n_poses;
+    r.n_poses = b.nposes;
     r.best_cost = (b.cb == ~0ull) ? -1.0 : lpm::u2d(b.cb);
     r.xv = r.yv = r.thetav = 0.0;
     if (b.cb != ~0ull) {
@@ -1104,6 +1116,7 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, const Robot
       __threadfence_system();
       *(volatile unsigned long long*)&direct->seq = direct_seq;
     }
+    meta[0] = m;  // (the exchange kernel reads the error bits from device memory)
   }
 }
 
@@ -1228,22 +1241,16 @@ argmin_kernel(Consts C, const RobotMeta* __restrict__ meta, int t_cap, const flo
     }
   }
   b.warp_reduce();
-  if (lane == 0) {
-    s_best[warp].cost_bits = b.cb;
-    s_best[warp].id = b.bi;
-    s_best[warp].n_collided = b.ncoll;
-  }
+  if (lane == 0) b.store(&s_best[warp]);
   __syncthreads();
   if (warp == 0) {
-    b.cb = ~0ull; b.bi = -1; b.ncoll = 0;
-    if (lane < kArgminThreads / 32) { b.cb = s_best[lane].cost_bits; b.bi = s_best[lane].id; b.ncoll = s_best[lane].n_collided; }
+    b.reset();
+    if (lane < kArgminThreads / 32) b.merge(s_best[lane]);
     b.warp_reduce();
     if (lane == 0) {
       s_last = 1;
       if (B > 1) {
-        BlockBest pb;
-        pb.cost_bits = b.cb; pb.id = b.bi; pb.n_collided = b.ncoll;
-        partial[(size_t)robot * B + blockIdx.x] = pb;
+        b.store(&partial[(size_t)robot * B + blockIdx.x]);
         __threadfence();
         s_last = atomicAdd(tickets + robot, 1u) == (unsigned)(B - 1) ? 1 : 0;
       }
@@ -1253,7 +1260,7 @@ argmin_kernel(Consts C, const RobotMeta* __restrict__ meta, int t_cap, const flo
   if (!s_last || warp != 0) return;
   if (B > 1) {  // merge the CTA partials
     __threadfence();
-    b.cb = ~0ull; b.bi = -1; b.ncoll = 0;
+    b.reset();
     for (int i = lane; i < B; i += 32) {
       const volatile BlockBest* pb = &partial[(size_t)robot * B + i];
       b.ncoll += pb->n_collided;

@@ -206,24 +206,42 @@ def test_sample_shard_union_equals_whole():
     gpu, ora = _pair(sc.config)
     r_g, r_o = run_pair(gpu, ora, sc.cloud, sc.plan, sc.pose, sc.twist)
     whole = gpu.read_trajectories()
+    other = make_query(sc.pose, [0.35, 0.0, 0.25])  # a different window: whatever it leaves in the output arrays is wrong for `sc`
     for count in (2, 3, 8):
         best = (None, -1)
         cost = np.full(r_o.n_traj, np.nan)
-        n_poses = n_traj = 0
+        first_hit = np.full(r_o.n_traj, -7, np.int32)
+        n_poses = n_traj = n_collided = 0
+        ranges = []
         for rank in range(count):
+            # the output arrays are not cleared between cycles: overwrite them with another query's values first, so that a
+            # trajectory the shard launch skips cannot pass with what the unsharded run left there
+            gpu.plan(other)
             r = gpu.plan_shard(make_query(sc.pose, sc.twist), rank, count)
             n_g, b, e = gpu.traj_count()
             assert n_g == r_o.n_traj
+            ranges.append((b, e))
             t = gpu.read_trajectories()
             cost[b:e] = t["cost"][b:e]
+            first_hit[b:e] = t["first_hit_pose"][b:e]
             assert np.all(np.isnan(t["cost"][:b])) and np.all(np.isnan(t["cost"][e:]))
+            # the counters come from what plan_kernel scored, not from prep_kernel's list
+            assert r.n_traj == e - b and r.n_poses == int(whole["num_steps"][b:e].sum())
+            assert r.n_collided == int((whole["first_hit_pose"][b:e] >= 0).sum())
             n_poses += r.n_poses
             n_traj += r.n_traj
+            n_collided += r.n_collided
             if r.best_id >= 0 and (best[0] is None or r.best_cost < best[0] or (r.best_cost == best[0] and r.best_id > best[1])):
                 best = (r.best_cost, r.best_id)
-        assert n_poses == r_o.n_poses and n_traj == r_o.n_traj
+        assert ranges[0][0] == 0 and ranges[-1][1] == r_o.n_traj and all(ranges[i][1] == ranges[i + 1][0] for i in range(count - 1))
+        assert n_poses == r_o.n_poses and n_traj == r_o.n_traj and n_collided == r_o.n_collided
         assert_same_array(cost, whole["cost"], f"shard x{count} cost")
+        assert_same_array(first_hit, whole["first_hit_pose"], f"shard x{count} first hit")
         assert best[1] == r_o.best_id and best[0] == r_o.best_cost
+        # the cuts are balanced by estimated poses: no shard may hold a gross multiple of its share
+        if count > 1:
+            shares = [int(whole["num_steps"][b:e].sum()) for b, e in ranges]
+            assert max(shares) <= 2.5 * r_o.n_poses / count + 64, shares
 
 
 def test_fleet_batch_equals_individual_plans():
