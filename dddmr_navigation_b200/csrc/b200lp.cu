@@ -140,6 +140,7 @@ struct b200lp_ctx {
   size_t n_robots = 0;
   int t_cap = 0;
   int shard_rank = 0, shard_count = 1;
+  ShardCuts cuts{};                       // where sample-sharded launches cut the estimated-work axis (n == 0: equal shares)
   DevBuf<RobotIn> d_robots;
   DevBuf<RobotMeta> d_meta;
   DevBuf<double> d_plan7;
@@ -458,7 +459,7 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   size_t plan_total = 0;
   for (size_t i = 0; i < n_robots; ++i) plan_total = std::max<size_t>(plan_total, ctx->h_robots.p[i].plan_off + ctx->h_robots.p[i].plan_n);
   const int nc = std::max(1, ctx->C.n_critics);
-  const int n_chunks = (t_cap + kPrepThreads - 1) / kPrepThreads;
+  const int n_chunks = (t_cap + kPrepSamples - 1) / kPrepSamples;
   // Upper bound on the trajectories one launch scores per robot. A sample shard's cuts sit at equal shares of the estimated
   // pose count, not of the sample count (prep_kernel), so a shard of slow trajectories can hold far more than t_cap / count
   // of them: the only bound that always holds is t_cap. plan_kernel takes the real count from prep_kernel's meta.
@@ -514,6 +515,7 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   }
   if (!ctx->plan_ctas_per_sm) {
     ctx->sm_count = sm_count_of(ctx->device);
+    CK(cudaFuncSetAttribute(prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrepSmemBytes));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->plan_ctas_per_sm, plan_kernel, kThreads, 0));
     if (ctx->plan_ctas_per_sm < 1) return ctx->fail(B200LP_E_CUDA, "plan_kernel does not fit on an SM");
   }
@@ -558,8 +560,8 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   if (plan_total && !plan_resident)
     CK(cudaMemcpyAsync(ctx->d_plan7.p, ctx->h_plan7.p, plan_total * 7 * sizeof(double), cudaMemcpyHostToDevice, ps));
   CK(cudaEventRecord(ctx->ev[1], ps));
-  prep_kernel<<<dim3((unsigned)n_chunks, (unsigned)n_robots), kPrepThreads, 0, ps>>>(
-      ctx->C, ctx->d_robots.p, t_cap, rank, count, ctx->epoch, ctx->d_tickets.p, ctx->d_aggs.p, ctx->d_rec_vel.p,
+  prep_kernel<<<dim3((unsigned)n_chunks, (unsigned)n_robots), kPrepThreads, kPrepSmemBytes, ps>>>(
+      ctx->C, ctx->d_robots.p, t_cap, rank, count, ctx->cuts, ctx->epoch, ctx->d_tickets.p, ctx->d_aggs.p, ctx->d_rec_vel.p,
       ctx->d_rec_steps.p, ctx->d_rec_dt.p, ctx->d_rec_sample.p, ctx->d_meta.p, ctx->d_plan7.p, ctx->d_plan_pts.p,
       ctx->d_rec_pose_off.p, ctx->d_poses.p, pose_stride, ctx->d_rec_pp.p, want_pp);
   CK(cudaEventRecord(ctx->ev[4], ps));
@@ -676,6 +678,9 @@ int b200lp_create(b200lp_ctx** out, int device, const b200lp_limits* limits, con
           (params->theory == B200LP_THEORY_OMNI_SIMPLE ? axis_count(params->linear_y_sample) : 1) > (1ll << 24))
     return bad("more than 2^24 velocity samples");
 
+  for (int k = 0; k < 24; ++k)
+    if (!std::isfinite(cuboid_xyz[k])) return bad("cuboid vertices must be finite");
+
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) {
@@ -713,6 +718,22 @@ int b200lp_create(b200lp_ctx** out, int device, const b200lp_limits* limits, con
     ctx->C.critics[k].weight = critics[k].weight;
     ctx->C.critics[k].tw = critics[k].translation_weight;
     ctx->C.critics[k].ow = critics[k].orientation_weight;
+  }
+  {  // robot-frame bounding box of the cuboid: what plan_kernel's float pre-cull rotates instead of the 8 vertices
+    float ext = 0.f;
+    for (int a = 0; a < 3; ++a) {
+      float mn = ctx->C.cuboid[0][a], mx = mn;
+      for (int k = 1; k < 8; ++k) {
+        mn = std::min(mn, ctx->C.cuboid[k][a]);
+        mx = std::max(mx, ctx->C.cuboid[k][a]);
+      }
+      ctx->C.box_c[a] = 0.5f * (mn + mx);
+      ctx->C.box_h[a] = std::nextafter(0.5f * (mx - mn), INFINITY) + 1e-6f * std::max(std::fabs(mn), std::fabs(mx));
+      ext += std::max(std::fabs(mn), std::fabs(mx));
+    }
+    // float rounding of loose_box: ~1.5e-6 relative error of the rotation entries times the cuboid's reach, plus a floor
+    ctx->C.box_slack = 2e-5f * (1.0f + ext);
+    ctx->C.pad2 = 0.f;
   }
   if (grid) ctx->gcfg = *grid;
   *out = ctx;

@@ -67,6 +67,10 @@ struct Consts {
   int n_critics;
   int pad;
   CriticDev critics[B200LP_MAX_CRITICS];
+  // axis-aligned bounding box of the 8 cuboid vertices in the robot frame (centre, half extents) and the slack that
+  // covers the float arithmetic of loose_box(): filled by b200lp_create
+  float box_c[3], box_h[3];
+  float box_slack, pad2;
 };
 
 struct RobotIn {
@@ -294,6 +298,63 @@ __device__ __forceinline__ void pose_affine(const double* R0, const double* t0, 
   }
 }
 
+// Cell range of the box [lo, hi] clamped to the grid, and whether any cloud point lies in those cells (inclusion-exclusion
+// on the summed-volume table, exact in modular u32 arithmetic): most poses drive through free space and are culled right
+// here. *cb is the range when the answer is yes, the empty box (x0 > x1) otherwise.
+__device__ __forceinline__ bool cells_with_points(const GridDev& g, const float* lo, const float* hi, CellBox* cb) {
+  const float fx0 = cell_f(lo[0], g.org[0], g.inv_xy), fx1 = cell_f(hi[0], g.org[0], g.inv_xy);
+  const float fy0 = cell_f(lo[1], g.org[1], g.inv_xy), fy1 = cell_f(hi[1], g.org[1], g.inv_xy);
+  const float fz0 = cell_f(lo[2], g.org[2], g.inv_z), fz1 = cell_f(hi[2], g.org[2], g.inv_z);
+  const bool empty = !(lo[0] <= hi[0] && lo[1] <= hi[1] && lo[2] <= hi[2]) || fx1 < 0.f || fy1 < 0.f || fz1 < 0.f ||
+                     fx0 > (float)(g.nx - 1) || fy0 > (float)(g.ny - 1) || fz0 > (float)(g.nz - 1) || g.n_kept == 0;
+  cb->x0 = cb->y0 = cb->z0 = 0x7fffffff;
+  cb->x1 = cb->y1 = cb->z1 = -1;
+  if (empty) return false;
+  const int x0 = (int)fmaxf(fx0, 0.f), x1 = (int)fminf(fx1, (float)(g.nx - 1));
+  const int y0 = (int)fmaxf(fy0, 0.f), y1 = (int)fminf(fy1, (float)(g.ny - 1));
+  const int z0 = (int)fmaxf(fz0, 0.f), z1 = (int)fminf(fz1, (float)(g.nz - 1));
+  const size_t sx = (size_t)(g.nx + 1), sy = (size_t)(g.ny + 1) * sx;
+  const uint32_t* s0 = g.sat + (size_t)z0 * sy;
+  const uint32_t* s1 = g.sat + (size_t)(z1 + 1) * sy;
+  const size_t a0 = (size_t)y0 * sx, a1 = (size_t)(y1 + 1) * sx;
+  const uint32_t up = (__ldg(s1 + a1 + x1 + 1) - __ldg(s1 + a1 + x0)) - (__ldg(s1 + a0 + x1 + 1) - __ldg(s1 + a0 + x0));
+  const uint32_t dn = (__ldg(s0 + a1 + x1 + 1) - __ldg(s0 + a1 + x0)) - (__ldg(s0 + a0 + x1 + 1) - __ldg(s0 + a0 + x0));
+  if (up - dn == 0u) return false;
+  cb->x0 = x0; cb->x1 = x1;
+  cb->y0 = y0; cb->y1 = y1;
+  cb->z0 = z0; cb->z1 = z1;
+  return true;
+}
+
+// Cheap, conservative stand-in for pose_geometry's candidate box, in float: a box that CONTAINS the exact candidate box
+// of the pose (x, y, th), so a pose whose loose box holds no cloud point cannot collide and never needs the
+// double-precision cuboid. R0f / t0f are the robot's world transform rounded to float. The cuboid is replaced by its
+// robot-frame bounding box (C.box_c +- C.box_h), whose world extent along axis a is sum_j |L[a][j]| h[j]; sin/cos come
+// from the fast intrinsics after a two-constant range reduction. Every rounding on the way — the intrinsics (< 5e-7 on
+// [-pi, pi]), the float transform, the float-rounded vertices of the exact path — is far below C.box_slack +
+// 2e-6 * cmax, which widens the box on every side.
+__device__ __forceinline__ void loose_box(const Consts& C, const GridDev& g, const float* R0f, const float* t0f, float x,
+                                          float y, float th, float* lo, float* hi) {
+  const float k = rintf(th * 0.15915494309189535f);
+  float r = __fmaf_rn(-k, 6.2831855f, th);
+  r = __fmaf_rn(-k, -1.7484555e-07f, r);  // 2 pi = 6.2831855 - 1.7484555e-07
+  float sn, cs;
+  __sincosf(r, &sn, &cs);
+  const float m = box_margin(g);
+  const float slack = C.box_slack + 2e-6f * g.cmax + m;
+  const float rad = 1.0f + slack;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float ra = R0f[a * 3], rb = R0f[a * 3 + 1], rc = R0f[a * 3 + 2];
+    const float l0 = __fmaf_rn(ra, cs, rb * sn), l1 = __fmaf_rn(rb, cs, -(ra * sn));
+    const float t = __fmaf_rn(ra, x, __fmaf_rn(rb, y, t0f[a]));
+    const float c = __fmaf_rn(l0, C.box_c[0], __fmaf_rn(l1, C.box_c[1], __fmaf_rn(rc, C.box_c[2], t)));
+    const float e = __fmaf_rn(fabsf(l0), C.box_h[0], __fmaf_rn(fabsf(l1), C.box_h[1], fabsf(rc) * C.box_h[2])) + slack;
+    lo[a] = fmaxf(c - e, t - rad);
+    hi[a] = fminf(c + e, t + rad);
+  }
+}
+
 // Everything CollisionModel derives per pose from the transformed cuboid, written to the warp stash:
 //  * stash (SoA [field][lane]): the reference's own quantities, read by the exact tests and the path critics;
 //  * pre (AoS, kPreStride float4 per lane, may be nullptr): coefficients of the conservative pre-test of
@@ -381,31 +442,7 @@ __device__ __forceinline__ void pose_geometry(const Consts& C, const GridDev& g,
       lo[a] = fmaxf(mn[a] - m, p[a] - r);
       hi[a] = fminf(mx[a] + m, p[a] + r);
     }
-    const float fx0 = cell_f(lo[0], g.org[0], g.inv_xy), fx1 = cell_f(hi[0], g.org[0], g.inv_xy);
-    const float fy0 = cell_f(lo[1], g.org[1], g.inv_xy), fy1 = cell_f(hi[1], g.org[1], g.inv_xy);
-    const float fz0 = cell_f(lo[2], g.org[2], g.inv_z), fz1 = cell_f(hi[2], g.org[2], g.inv_z);
-    const bool empty = !(lo[0] <= hi[0] && lo[1] <= hi[1] && lo[2] <= hi[2]) || fx1 < 0.f || fy1 < 0.f || fz1 < 0.f ||
-                       fx0 > (float)(g.nx - 1) || fy0 > (float)(g.ny - 1) || fz0 > (float)(g.nz - 1) || g.n_kept == 0;
-    cb->x0 = cb->y0 = cb->z0 = 0x7fffffff;
-    cb->x1 = cb->y1 = cb->z1 = -1;
-    if (!empty) {
-      const int x0 = (int)fmaxf(fx0, 0.f), x1 = (int)fminf(fx1, (float)(g.nx - 1));
-      const int y0 = (int)fmaxf(fy0, 0.f), y1 = (int)fminf(fy1, (float)(g.ny - 1));
-      const int z0 = (int)fmaxf(fz0, 0.f), z1 = (int)fminf(fz1, (float)(g.nz - 1));
-      // number of cloud points in those cells (inclusion-exclusion on the summed-volume table, exact in
-      // modular u32 arithmetic): most poses drive through free space and are culled right here
-      const size_t sx = (size_t)(g.nx + 1), sy = (size_t)(g.ny + 1) * sx;
-      const uint32_t* s0 = g.sat + (size_t)z0 * sy;
-      const uint32_t* s1 = g.sat + (size_t)(z1 + 1) * sy;
-      const size_t a0 = (size_t)y0 * sx, a1 = (size_t)(y1 + 1) * sx;
-      const uint32_t hi = (__ldg(s1 + a1 + x1 + 1) - __ldg(s1 + a1 + x0)) - (__ldg(s1 + a0 + x1 + 1) - __ldg(s1 + a0 + x0));
-      const uint32_t lo = (__ldg(s0 + a1 + x1 + 1) - __ldg(s0 + a1 + x0)) - (__ldg(s0 + a0 + x1 + 1) - __ldg(s0 + a0 + x0));
-      if (hi - lo != 0u) {
-        cb->x0 = x0; cb->x1 = x1;
-        cb->y0 = y0; cb->y1 = y1;
-        cb->z0 = z0; cb->z1 = z1;
-      }
-    }
+    cells_with_points(g, lo, hi, cb);
   }
 }
 
@@ -516,13 +553,14 @@ __device__ __forceinline__ unsigned sweep_points(const GridDev& g, const float* 
           for (int q = 0; q < kGroup; ++q) {
             bool in;
             if (kMinMax) {
-              in = p.x >= ca[q].x && p.x <= cb[q].x && p.y >= ca[q].y && p.y <= cb[q].y && p.z >= ca[q].z && p.z <= cb[q].z;
+              in = (p.x >= ca[q].x) & (p.x <= cb[q].x) & (p.y >= ca[q].y) & (p.y <= cb[q].y) & (p.z >= ca[q].z) & (p.z <= cb[q].z);
             } else {
-              // conservative superset of the exact test: |v' - v| <= delta
+              // conservative superset of the exact test: |v' - v| <= delta; no short-circuit, so the three
+              // compares chain through one predicate instead of branching
               const float vx = __fmaf_rn(p.x, ca[q].x, __fmaf_rn(p.y, ca[q].y, __fmaf_rn(p.z, ca[q].z, ca[q].w)));
               const float vy = __fmaf_rn(p.x, cb[q].x, __fmaf_rn(p.y, cb[q].y, __fmaf_rn(p.z, cb[q].z, cb[q].w)));
               const float vz = __fmaf_rn(p.x, cc[q].x, __fmaf_rn(p.y, cc[q].y, __fmaf_rn(p.z, cc[q].z, cc[q].w)));
-              in = fabsf(vx) <= ch[q].x && fabsf(vy) <= ch[q].y && fabsf(vz) <= ch[q].z;
+              in = (fabsf(vx) <= ch[q].x) & (fabsf(vy) <= ch[q].y) & (fabsf(vz) <= ch[q].z);
             }
             pm |= in ? (1u << q) : 0u;
           }

@@ -358,6 +358,13 @@ __device__ __forceinline__ bool traj_precheck(const Consts& C, const RobotIn& q,
   return true;
 }
 
+// Where a sample-sharded launch cuts the estimated-work axis: frac[k] = share of the work below cut k (frac[0] = 0,
+// frac[n] = 1). n == 0: equal shares. Kernel argument, identical on every rank of a cycle.
+struct ShardCuts {
+  int n;
+  float frac[B200LP_MAX_PEERS + 1];
+};
+
 // Per-(robot, chunk) aggregate of the decoupled look-back that orders the trajectory list across CTAs.
 struct alignas(16) PrepAgg {  // 32 bytes: read back with two 16-byte volatile loads
   int keep, valid;     // samples kept by the motor constraint / trajectories that passed the prologue
@@ -368,13 +375,24 @@ struct alignas(16) PrepAgg {  // 32 bytes: read back with two 16-byte volatile l
 };
 static_assert(sizeof(PrepAgg) == 32, "PrepAgg layout");
 
-#ifndef B200LP_PREP_THREADS
-#define B200LP_PREP_THREADS 128
-#endif
-constexpr int kPrepThreads = B200LP_PREP_THREADS;  // samples per chunk: 16.5 k samples (C2) make 129 CTAs, one per SM — the
-                                                    // forward simulation is bound by the XU / FP64 pipes of the SMs it runs on
+// prep_kernel geometry: a CTA of kPrepThreads threads owns one chunk of kPrepSamples velocity samples. The sample checks,
+// the ordering of the trajectory list and the three float recurrences of a rollout (heading, x, y) are one-thread-per-
+// trajectory work; everything between the recurrences (sinf/cosf of every heading, the per-step increments, the pose
+// rows) is one-item-per-pose work that the whole CTA shares.
+constexpr int kPrepSamples = 128;
+constexpr int kPrepThreads = 512;
 constexpr int kPrepWarps = kPrepThreads / 32;
-// serial per-CTA jobs (three velocity axes, two pose matrices) are spread over different warps where possible
+constexpr int kPrepBlock = 32;               // steps per pass of the rollout phases
+constexpr int kPrepPitch = kPrepSamples + 1; // row pitch of the [step][trajectory] arrays: conflict-free both ways
+constexpr long long kSpinLimit = 4000000000ll;  // ~2 s of SM clocks: a look-back that waits this long reports an error
+// dynamic shared memory: the three velocity axes while the samples are checked, the rollout buffers afterwards
+struct PrepRoll {
+  float th[kPrepSamples][kPrepBlock + 1];  // heading before step j of the pass (entry kPrepBlock: after the last one)
+  double e[2][kPrepBlock][kPrepPitch];     // per-step increments (x, y); overwritten in place by the positions (float)
+};
+constexpr size_t kPrepAxesBytes = 3 * (size_t)kMaxAxis * sizeof(float);
+constexpr size_t kPrepSmemBytes = sizeof(PrepRoll) > kPrepAxesBytes ? sizeof(PrepRoll) : kPrepAxesBytes;
+// serial per-CTA jobs (three velocity axes, two pose matrices) are spread over different warps
 __device__ __forceinline__ bool prep_job(int job, int tid) { return tid == (job % kPrepWarps) * 32 + job / kPrepWarps; }
 
 #ifdef B200LP_PREP_TRACE  // tools only: phase timestamps of thread 0 of the first / last chunk, printed by the kernel
@@ -385,7 +403,7 @@ __device__ __forceinline__ bool prep_job(int job, int tid) { return tid == (job 
 // grid = (n_chunks, robots). Chunk ids are handed out by a per-robot ticket, so a CTA only ever waits for
 // chunks that are already running; every CTA publishes its aggregate BEFORE it looks back.
 __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const RobotIn* __restrict__ robots, int t_cap,
-                                                             int shard_rank, int shard_count, unsigned epoch,
+                                                             int shard_rank, int shard_count, ShardCuts cuts, unsigned epoch,
                                                              unsigned* __restrict__ tickets, PrepAgg* aggs,
                                                              float4* __restrict__ rec_vel, int* __restrict__ rec_steps,
                                                              double* __restrict__ rec_dt, int* __restrict__ rec_sample,
@@ -395,14 +413,25 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
                                                              long long* __restrict__ rec_pose_off,
                                                              float4* __restrict__ pose_rows, long long pose_stride,
                                                              double2* __restrict__ rec_pp, int want_pp) {
-  __shared__ float s_x[kMaxAxis], s_y[kMaxAxis], s_th[kMaxAxis];
+  extern __shared__ __align__(16) unsigned char prep_smem[];
+  float* s_x = reinterpret_cast<float*>(prep_smem);  // [kMaxAxis] each, dead once the samples are checked
+  float* s_y = s_x + kMaxAxis;
+  float* s_th = s_y + kMaxAxis;
+  PrepRoll& RB = *reinterpret_cast<PrepRoll*>(prep_smem);
   __shared__ double s_R0[9], s_t0[3], s_gL[9], s_gt[3];
-  __shared__ unsigned long long s_wposes[kPrepThreads / 32];
+  __shared__ unsigned long long s_wposes[kPrepWarps];
   __shared__ int s_n[3];
-  __shared__ int s_wkeep[kPrepThreads / 32], s_wvalid[kPrepThreads / 32];
+  __shared__ int s_wkeep[kPrepWarps], s_wvalid[kPrepWarps];
   __shared__ int s_chunk;
   __shared__ int s_red[6];
   __shared__ unsigned long long s_poses;
+  // per-trajectory parameters of the rollout phases
+  __shared__ float s_v0[kPrepSamples], s_v1[kPrepSamples];
+  __shared__ double s_wdt[kPrepSamples], s_dt[kPrepSamples];
+  __shared__ int s_steps[kPrepSamples];  // 0: nothing to roll out
+  __shared__ long long s_row[kPrepSamples];
+  __shared__ float s_last[3][kPrepSamples];  // x, y, th after the last step (pure pursuit)
+  __shared__ int s_maxsteps;
   const int robot = blockIdx.y;
   const int n_chunks = gridDim.x;
   const RobotIn q = robots[robot];
@@ -419,6 +448,7 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
     s_n[0] = s_n[1] = s_n[2] = 0;
     s_red[0] = s_red[1] = s_red[2] = s_red[3] = s_red[4] = s_red[5] = 0;
     s_poses = 0ull;
+    s_maxsteps = 0;
   }
   __syncthreads();
   const int chunk = s_chunk;
@@ -492,7 +522,9 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
   // ceil(max(|v| T / g, |w| T / g_a)), so equal sample counts leave the last rank with about twice the poses of the first
   // (C4 on 8 GPUs: 0.23 vs 0.34 ms). Every CTA of every rank evaluates the same closed-form estimate per linear-speed row
   // (|w| taken as uniform over the angular axis, plus a fixed per-trajectory term), prefix-sums it and cuts the rows at
-  // equal shares; identical arithmetic on identical inputs, so all ranks agree on the cuts without talking.
+  // the shares `cuts` names (k / count by default; the host may move them with the kernel times of earlier cycles, which
+  // every rank sees through the exchange slots); identical arithmetic on identical inputs, so all ranks agree on the cuts
+  // without talking.
   long long lo = (long long)n_raw * shard_rank / shard_count;
   long long hi = (long long)n_raw * (shard_rank + 1) / shard_count;
   if (shard_count > 1 && sampling_on && P.theory != B200LP_THEORY_DD_ROTATE_INPLACE && n_raw > 0) {
@@ -532,7 +564,8 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
       else if (k >= shard_count) cut = n_raw;
       else {
         const float total = s_w[nx - 1];
-        const float target = total * (float)k / (float)shard_count;
+        const float share = cuts.n == shard_count ? cuts.frac[k] : (float)k / (float)shard_count;
+        const float target = total * share;
         int a = 0, b = nx - 1;  // smallest row whose inclusive prefix reaches the target
         while (a < b) {
           const int m = (a + b) >> 1;
@@ -552,8 +585,8 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
     hi = s_cut[1];
   }
 
-  // ---- this chunk's samples: one per thread ----
-  const int s = chunk * kPrepThreads + tid;
+  // ---- this chunk's samples: one per thread of the first kPrepSamples ----
+  const int s = tid < kPrepSamples ? chunk * kPrepSamples + tid : 0x7fffffff;
   bool keep = false, valid = false;
   float v0 = 0.f, v1 = 0.f, v2 = 0.f;
   int steps = 0, err = 0;
@@ -599,11 +632,11 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
     atomicOr(&s_red[2], err);
     atomicAdd(&s_poses, poses);
   }
-  __syncthreads();
+  __syncthreads();  // (also the last read of the velocity axes: the rollout buffers may overwrite them from here on)
   int offk = 0, offv = 0, totk = 0, totv = 0;
   unsigned long long offp = 0ull;
 #pragma unroll
-  for (int w = 0; w < kPrepThreads / 32; ++w) {
+  for (int w = 0; w < kPrepWarps; ++w) {
     const int a = s_wkeep[w], b = s_wvalid[w];
     if (w < warp) { offk += a; offv += b; offp += s_wposes[w]; }
     totk += a; totv += b;
@@ -625,8 +658,14 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
   for (int c = tid; c < chunk; c += kPrepThreads) {
     const PrepAgg* a = my_aggs + c;
     // the poll must be a volatile access: an empty loop around a plain intrinsic load has no side effect the compiler
-    // is obliged to keep
-    while (*(volatile const unsigned*)&a->flag != epoch) {}
+    // is obliged to keep. Every chunk polled here holds a ticket, i.e. its CTA is running; the time limit only guards
+    // against a device fault in that CTA, and turns a hang into an error the host reports.
+    if (*(volatile const unsigned*)&a->flag != epoch) {
+      const long long t_start = clock64();
+      while (*(volatile const unsigned*)&a->flag != epoch) {
+        if (clock64() - t_start > kSpinLimit) { perr |= 32; break; }
+      }
+    }
     __threadfence();
     const uint4 w0 = __ldcv(reinterpret_cast<const uint4*>(a));      // keep, valid, cnt_lo, cnt_hi
     const uint4 w1 = __ldcv(reinterpret_cast<const uint4*>(a) + 1);  // poses (lo, hi), err, flag
@@ -645,7 +684,7 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
   __syncthreads();  // s_red / s_poses were consumed by thread 0 above; reuse them for the prefix
   if (tid == 0) { s_red[0] = s_red[1] = s_red[3] = s_red[4] = 0; s_poses = 0ull; }
   __syncthreads();
-  if (lane == 0 && chunk > 0) {
+  if (lane == 0 && (chunk > 0 || perr)) {
     atomicAdd(&s_red[0], pk); atomicAdd(&s_red[1], pv);
     atomicAdd(&s_red[3], plo); atomicAdd(&s_red[4], phi);
     atomicOr(&s_red[5], perr);
@@ -672,67 +711,101 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
       roll = in_shard && (long long)(s_poses + offp + pscan) <= pose_stride;
     }
   }
-  // ---- forward simulation of this thread's trajectory (computeNewPositions, dd_simple…cpp:457-464,
-  // omni_simple…cpp:498-505): x,y,th in the robot frame after every step, then the pure-pursuit terms
-  // of the last pose ----
-  if (roll) {
-    float x = 0.f, y = 0.f, th = 0.f;
-    const double wdt = (double)v2 * dt;  // loop invariant of th' = (float)(th + w*dt)
-    float4* out = pose_rows + pose_row;
-    // Blocks of 4 steps: the heading chain th' = (float)(th + w*dt) is the only dependency the expensive
-    // sin/cos evaluations have, so it runs ahead and the four evaluations overlap in the FP64 pipe. (A three-stage
-    // software pipeline that also overlaps the position chain with the next block's headings was measured SLOWER,
-    // 39 vs 36 us at C2: the loop is bound by the conversion (XU) and FP64 pipes of the few SMs that hold the
-    // trajectories, not by the dependency chains — tools/prep_trace.py.)
-    constexpr int kU = 4;
-    for (int k0 = 0; k0 < steps; k0 += kU) {
-      float tho[kU], thn[kU];
-      double ex[kU], ey[kU];
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        tho[u] = th;
+  // ---- forward simulation (computeNewPositions, dd_simple…cpp:457-464, omni_simple…cpp:498-505): x, y, th in the
+  // robot frame after every step, in passes of kPrepBlock steps. Per pass:
+  //   1. heading recurrence th' = (float)(th + w dt), one thread per trajectory;
+  //   2. sinf / cosf of every heading and the double increments, one item per (trajectory, step) over the whole CTA;
+  //   3. position recurrences x' = (float)(x + ex), y' = (float)(y + ey), one thread per trajectory and coordinate;
+  //   4. the pose rows, one item per pose, 512-byte coalesced stores.
+  // Exactly the reference's operations in the reference's order; only the independent ones run side by side. (The
+  // version of round 1 ran a whole trajectory in one thread: 60 sinf/cosf evaluations deep, 34 us at C2.) ----
+  if (tid < kPrepSamples) {
+    s_v0[tid] = v0; s_v1[tid] = v1;
+    s_wdt[tid] = (double)v2 * dt;  // loop invariant of the heading recurrence
+    s_dt[tid] = dt;
+    s_steps[tid] = roll ? steps : 0;
+    s_row[tid] = pose_row;
+    if (roll) atomicMax(&s_maxsteps, steps);
+  }
+  __syncthreads();
+  const int max_steps = s_maxsteps;
+  const int my_steps = tid < 2 * kPrepSamples ? s_steps[tid & (kPrepSamples - 1)] : 0;
+  float th = 0.f;  // heading of trajectory `tid` (threads < kPrepSamples)
+  float pos = 0.f; // x of trajectory `tid` (threads < kPrepSamples), y of trajectory `tid - kPrepSamples` (the next kPrepSamples)
+  const bool omni = P.theory == B200LP_THEORY_OMNI_SIMPLE;
+  for (int k0 = 0; k0 < max_steps; k0 += kPrepBlock) {
+    if (tid < kPrepSamples && my_steps > k0) {
+      const double wdt = s_wdt[tid];
+      float* row = RB.th[tid];
+#pragma unroll 8
+      for (int j = 0; j < kPrepBlock; ++j) {
+        row[j] = th;
         th = (float)((double)th + wdt);
-        thn[u] = th;
+        if (k0 + j == my_steps - 1) s_last[2][tid] = th;
       }
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
+      row[kPrepBlock] = th;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int it = tid; it < kPrepSamples * kPrepBlock; it += kPrepThreads) {
+      const int j = it & (kPrepBlock - 1), t = it / kPrepBlock;
+      if (k0 + j < s_steps[t]) {
+        const float tho = RB.th[t][j];
+        const float a0 = s_v0[t];
+        const double tdt = s_dt[t];
         float sn, cs;
-        lpm::sincosf(tho[u], &sn, &cs);
-        if (P.theory == B200LP_THEORY_OMNI_SIMPLE) {
-          const double a = 1.57079632679489661923 + (double)tho[u];  // M_PI_2 + pos[2]
-          ex[u] = ((double)(v0 * cs) + (double)v1 * lpm::cos(a)) * dt;
-          ey[u] = ((double)(v0 * sn) + (double)v1 * lpm::sin(a)) * dt;
+        lpm::sincosf(tho, &sn, &cs);
+        double ex, ey;
+        if (omni) {
+          const double a = 1.57079632679489661923 + (double)tho;  // M_PI_2 + pos[2]
+          const double a1 = (double)s_v1[t];
+          ex = ((double)(a0 * cs) + a1 * lpm::cos(a)) * tdt;
+          ey = ((double)(a0 * sn) + a1 * lpm::sin(a)) * tdt;
         } else {
-          ex[u] = (double)(v0 * cs) * dt;
-          ey[u] = (double)(v0 * sn) * dt;
+          ex = (double)(a0 * cs) * tdt;
+          ey = (double)(a0 * sn) * tdt;
         }
-      }
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        x = (float)((double)x + ex[u]);
-        y = (float)((double)y + ey[u]);
-        if (k0 + u < steps) out[k0 + u] = make_float4(x, y, thn[u], 0.f);
+        RB.e[0][j][t] = ex;
+        RB.e[1][j][t] = ey;
       }
     }
-    PREP_T(4);  // rollout done
-    // the block loop may run past the last step: restore the state after step `steps - 1`
-    {
-      const float4 last = out[steps - 1];
-      x = last.x; y = last.y; th = last.z;
+    __syncthreads();
+    if (tid < 2 * kPrepSamples && my_steps > k0) {
+      const int c = tid / kPrepSamples, t = tid & (kPrepSamples - 1);
+      const int n_here = min(kPrepBlock, my_steps - k0);
+#pragma unroll 4
+      for (int j = 0; j < n_here; ++j) {
+        double* slot = &RB.e[c][j][t];
+        pos = (float)((double)pos + *slot);
+        *reinterpret_cast<float*>(slot) = pos;  // the position replaces the increment it consumed
+      }
+      if (k0 + n_here == my_steps) s_last[c][t] = pos;
     }
-    if (want_pp && q.plan_n > 0 && steps >= 2) {
-      double Lm[9], tv[3], dist, yaw;
-      pose_affine(s_R0, s_t0, x, y, th, Lm, tv);
-      pure_pursuit_terms(Lm, tv, s_gL, s_gt, &dist, &yaw);
-      rec_pp[rec] = make_double2(dist, yaw);
+    __syncthreads();
+#pragma unroll 2
+    for (int it = tid; it < kPrepSamples * kPrepBlock; it += kPrepThreads) {
+      const int j = it & (kPrepBlock - 1), t = it / kPrepBlock;
+      if (k0 + j < s_steps[t])
+        pose_rows[s_row[t] + k0 + j] = make_float4(*reinterpret_cast<const float*>(&RB.e[0][j][t]),
+                                                   *reinterpret_cast<const float*>(&RB.e[1][j][t]), RB.th[t][j + 1], 0.f);
     }
+    __syncthreads();
+  }
+  PREP_T(4);  // rollout done
+  // the pure-pursuit terms of the last pose (quaternion round trip, 3x3 inverse, asin / atan2 / fmod): kept out of the
+  // hot kernel
+  if (roll && want_pp && q.plan_n > 0 && steps >= 2) {
+    double Lm[9], tv[3], dist, yaw;
+    pose_affine(s_R0, s_t0, s_last[0][tid], s_last[1][tid], s_last[2][tid], Lm, tv);
+    pure_pursuit_terms(Lm, tv, s_gL, s_gt, &dist, &yaw);
+    rec_pp[rec] = make_double2(dist, yaw);
   }
   PREP_T(5);  // pure-pursuit terms done
 #ifdef B200LP_PREP_TRACE
   if (tid == 0 && (chunk == 0 || chunk == n_chunks - 1) && robot == 0)
     printf("prep trace chunk %d/%d steps %d: axes %lld, precheck %lld, look-back %lld, rollout %lld, pure pursuit %lld cycles (roll=%d)\n", chunk,
            n_chunks, steps, trace_t[1] - trace_t[0], trace_t[2] - trace_t[1], trace_t[3] - trace_t[2],
-           trace_t[4] ? trace_t[4] - trace_t[3] : 0ll, trace_t[4] ? trace_t[5] - trace_t[4] : 0ll, (int)roll);
+           trace_t[4] - trace_t[3], trace_t[5] - trace_t[4], (int)roll);
 #endif
   if (chunk == n_chunks - 1 && tid == 0) {  // the last ticket: every chunk of this robot has started
     const PrepAgg* a = my_aggs + chunk;
@@ -762,6 +835,7 @@ __device__ __forceinline__ bool better(unsigned long long ca, int ia, unsigned l
 
 struct WarpCtx {
   double R0[9], t0[3];
+  float R0f[9], t0f[3];  // the same transform rounded to float: operands of the conservative pre-cull (loose_box)
 };
 
 struct Best {
@@ -799,10 +873,21 @@ struct CtaShared {
   float4 pre[kWarpsPerCta][32 * kPreStride];
   WarpCtx wc[kWarpsPerCta];
   float4 plan[kPlanSmem];
+  unsigned short list[kWarpsPerCta][64];  // poses that survived the pre-cull and wait for the exact geometry, ascending
 };
+
+// lanes that head a group of kGroup consecutive stash columns
+__host__ __device__ constexpr unsigned group_heads() {
+  unsigned m = 0u;
+  for (int i = 0; i < 32; i += kGroup) m |= 1u << i;
+  return m;
+}
 
 #ifndef B200LP_PLAN_MIN_CTAS
 #define B200LP_PLAN_MIN_CTAS 5
+#endif
+#ifndef B200LP_PRECULL
+#define B200LP_PRECULL 1  // 0: every pose goes through the double-precision geometry (A/B builds, tools/time_variants.py)
 #endif
 __global__ void __launch_bounds__(kThreads, B200LP_PLAN_MIN_CTAS)
 plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotMeta* meta, int n_robots,
@@ -861,6 +946,10 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotMeta* 
         // tf2::transformToEigen(robot_pose_) (dd_simple…cpp:355)
         quat_to_matrix(q.pose[3], q.pose[4], q.pose[5], q.pose[6], W.R0);
         W.t0[0] = q.pose[0]; W.t0[1] = q.pose[1]; W.t0[2] = q.pose[2];
+#pragma unroll
+        for (int a = 0; a < 9; ++a) W.R0f[a] = (float)W.R0[a];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) W.t0f[a] = (float)W.t0[a];
       }
       __syncwarp();
     }
@@ -929,28 +1018,64 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotMeta* 
         }
       }
     }
-    // ---- pass 1: cuboids + obstacle query, 32 poses at a time ----------------------------------------
+    // ---- pass 1: obstacle query ------------------------------------------------------------------------
+    // Stage A (cheap, float): every pose gets a conservative box around its candidate box (loose_box) and one look at the
+    // summed-volume table; poses whose box holds no cloud point cannot collide and drop out (about 6 of 10 at C2). The
+    // survivors are queued in ascending pose order. Stage B (exact, double): as soon as 32 survivors wait — or the
+    // trajectory is exhausted — their cuboids are built with the reference's arithmetic, and groups of kGroup consecutive
+    // survivors are swept against their united candidate stream, lowest pose first, so the first colliding pose found is
+    // the reference's. The double-precision geometry therefore runs for compacted survivors only.
     int hit_box = -1, hit_mm = -1;  // first colliding pose per collision-critic kind
     bool rejected = false;           // the stack's first collision critic hit and ends the evaluation
     if (need_box || need_mm) {
-      for (int base = 0; base < n; base += 32) {
-        const int k = base + lane;
-        const bool live = k < n;
-        const float4 pz = live ? __ldg(traj_poses + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+      unsigned short* list = S.list[warp];
+      const unsigned lt = (1u << lane) - 1u;
+      int cnt = 0, base = 0;  // survivors waiting / next pose to pre-cull (warp-uniform)
+      for (;;) {
+#if B200LP_PRECULL
+        while (cnt < 32 && base < n) {
+          const int k = base + lane;
+          bool keep = false;
+          if (k < n) {
+            const float4 pz = __ldg(traj_poses + k);
+            float lo[3], hi[3];
+            loose_box(C, g, W.R0f, W.t0f, pz.x, pz.y, pz.z, lo, hi);
+            CellBox unused;
+            keep = cells_with_points(g, lo, hi, &unused);
+          }
+          const unsigned mk = __ballot_sync(kFull, keep);
+          if (keep) list[cnt + __popc(mk & lt)] = (unsigned short)k;
+          cnt += __popc(mk);
+          base += 32;
+        }
+#else
+        if (base < n) {  // no pre-cull: every pose goes through the exact geometry
+          if (base + lane < n) list[lane] = (unsigned short)(base + lane);
+          cnt = min(32, n - base);
+          base += 32;
+        }
+#endif
+        if (cnt == 0) break;
+        __syncwarp();
+        const int m_here = min(cnt, 32);
+        const bool live = lane < m_here;
+        const float4 pz = live ? __ldg(traj_poses + list[lane]) : make_float4(0.f, 0.f, 0.f, 0.f);
         double L[9], t[3];
         pose_affine(W.R0, W.t0, pz.x, pz.y, pz.z, L, t);
         CellBox cbx;
         pose_geometry(C, g, L, t, stash, pre, &cbx, lane, live, nullptr);
         group_union(cbx);
         __syncwarp();
-
-        // groups of kGroup consecutive poses, once per collision-critic kind still undecided
-        const int n_here = min(32, n - base);
+        // groups of kGroup consecutive survivors whose united box holds points, once per collision-critic kind still undecided
+        const unsigned heads = __ballot_sync(kFull, cbx.x0 <= cbx.x1) & group_heads();
 #pragma unroll 1
         for (int kind = 0; kind < 2; ++kind) {
           if (kind == 0 ? !(need_box && hit_box < 0) : !(need_mm && hit_mm < 0)) continue;
+          unsigned todo = heads;
 #pragma unroll 1
-          for (int col0 = 0; col0 < n_here; col0 += kGroup) {
+          while (todo) {
+            const int col0 = __ffs(todo) - 1;
+            todo &= todo - 1u;
             CellBox ub;
             ub.x0 = __shfl_sync(kFull, cbx.x0, col0); ub.x1 = __shfl_sync(kFull, cbx.x1, col0);
             ub.y0 = __shfl_sync(kFull, cbx.y0, col0); ub.y1 = __shfl_sync(kFull, cbx.y1, col0);
@@ -958,13 +1083,12 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotMeta* 
             const unsigned h = kind ? sweep_points<true>(g, stash, pre, col0, lane, ub)
                                     : sweep_points<false>(g, stash, pre, col0, lane, ub);
             if (h) {
-              const int hp = base + col0 + (__ffs(h) - 1);
+              const int hp = (int)list[col0 + (__ffs(h) - 1)];
               if (kind) hit_mm = hp; else hit_box = hp;
               break;
             }
           }
         }
-        __syncwarp();
         // A hit of the FIRST collision critic of the stack ends the trajectory (the reference returns -1
         // there) when nothing that precedes it in the stack depends on the rollout. A later collision
         // critic hitting first only retires that critic: the earlier one must still run to the end.
@@ -973,7 +1097,16 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotMeta* 
           break;
         }
         if (!(need_box && hit_box < 0) && !(need_mm && hit_mm < 0)) break;  // every collision critic is decided
+        // drop the chunk from the queue
+        const int rest = cnt - m_here;  // < 32
+        const unsigned short carry = lane < rest ? list[m_here + lane] : (unsigned short)0;
+        __syncwarp();
+        if (lane < rest) list[lane] = carry;
+        cnt = rest;
+        if (cnt == 0 && base >= n) break;
+        __syncwarp();
       }
+      __syncwarp();
     }
 
     // ---- pass 2: path critics, only for trajectories the collision critic did not already reject ----
