@@ -11,9 +11,10 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+COUNT_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libb200lp_count.so")
 LIB_PATH = os.path.join(HERE, "csrc", "libb200lp.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # status codes
 OK, E_INVALID, E_CUDA, E_STATE, E_NOMEM = 0, -1, -2, -3, -4
@@ -141,6 +142,13 @@ SYMBOLS = {
     "b200lp_peer_export": (C.c_int, [_P, C.POINTER(C.c_uint8)]),
     "b200lp_peer_attach": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_uint8)]),
     "b200lp_plan_shard_exchange": (C.c_int, [_P, C.POINTER(Query), C.POINTER(Result)]),
+    "b200lp_peer_resync": (C.c_int, [_P]),
+    "b200lp_peer_reserve_cloud": (C.c_int, [_P, C.c_size_t]),
+    "b200lp_set_cloud_shared": (C.c_int, [_P, C.c_int, _P, C.c_size_t, C.c_size_t]),
+    "b200lp_set_shard_cuts": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int]),
+    "b200lp_get_shard_cuts": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "b200lp_set_adaptive_cuts": (C.c_int, [_P, C.c_int]),
+    "b200lp_last_cycle_ns": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "b200lp_plan_batch": (C.c_int, [_P, C.POINTER(Query), C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_int64),
                                     C.POINTER(Result)]),
     "b200lp_traj_count": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
@@ -157,6 +165,7 @@ SYMBOLS = {
     "b200lp_read_observation": (C.c_int, [_P, C.c_int, _P, C.c_size_t, C.c_size_t, C.POINTER(C.c_size_t)]),
     "b200lp_aggregate_observations": (C.c_int, [_P, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_size_t)]),
     "b200lp_count_radius": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "b200lp_work_counters": (C.c_int, [_P, C.POINTER(C.c_uint64), C.c_int]),
     "b200lp_last_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
                                      C.POINTER(C.c_float)]),
     "b200lp_last_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
@@ -186,11 +195,15 @@ def load_library(path: str | None = None):
             f"{p} not found: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()'). "
             "dddmr_navigation_b200 has no CPU fallback.")
     lib = C.CDLL(p)
+    lib.b200lp_abi_version.restype = C.c_int
+    older = path is not None and lib.b200lp_abi_version() < ABI_VERSION  # an A/B build of an earlier round (tools/time_variants.py)
     for name, (res, args) in SYMBOLS.items():
+        if path is not None and not hasattr(lib, name):  # explicitly named A/B builds may predate an entry point
+            continue
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.b200lp_abi_version() != ABI_VERSION:
+    if lib.b200lp_abi_version() != ABI_VERSION and not older:
         raise ImportError(f"{p}: ABI version {lib.b200lp_abi_version()} != {ABI_VERSION}")
     if path is None:
         _lib = lib

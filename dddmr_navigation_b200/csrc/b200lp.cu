@@ -130,8 +130,21 @@ struct b200lp_ctx {
   cudaEvent_t oev[3] = {nullptr, nullptr, nullptr};  // observation: start, end, scan uploaded
 
   // peer-memory argmin exchange of sample-sharded cycles
-  DevBuf<PeerSlot> d_peer_slots;          // 2 x kMaxPeers slots the peers write into
+  DevBuf<char> d_peer_block;              // [2 x kMaxPeers slots the peers write into | CloudHeader | shared-cloud rows]
+  size_t peer_cloud_cap = 0;              // points the shared-cloud row buffer holds (b200lp_peer_reserve_cloud)
   PeerTable peer_table{};                 // every rank's slot array, mapped into this process
+  PeerBlocks peer_blocks{};               // ... and the base of every rank's block
+  unsigned long long cloud_seq = 0;       // shared-cloud cycles so far
+  cudaStream_t push_stream = nullptr;     // root: pushes of the upload pieces to the peers
+  cudaEvent_t push_done = nullptr;        // ... as of the last piece (the next upload may overwrite d_raw after it)
+  bool push_pending = false;
+  DevBuf<unsigned> d_push_ticket;
+  DevBuf<int> d_share_err;
+  PinBuf<CloudHeader> h_share_hdr;        // peer: the root's header, written by share_wait_header_kernel
+  PinBuf<int> h_share_err;
+  PeerSlot* peer_slots() const { return reinterpret_cast<PeerSlot*>(d_peer_block.p); }
+  CloudHeader* my_header() const { return reinterpret_cast<CloudHeader*>(d_peer_block.p + kPeerHeaderOff); }
+  char* my_rows() const { return d_peer_block.p + kPeerRowsOff; }
   void* peer_opened[kMaxPeers] = {nullptr};
   int peer_rank = -1, peer_world = 0;
   unsigned long long peer_seq = 0;
@@ -157,6 +170,12 @@ struct b200lp_ctx {
   DevBuf<unsigned> d_tickets;            // prep_kernel chunk tickets, one per robot (self-resetting)
   DevBuf<PrepAgg> d_aggs;                // prep_kernel look-back aggregates
   DevBuf<unsigned long long> d_work;     // plan_kernel work counter (reset by argmin_kernel)
+  DevBuf<unsigned long long> d_tstart;   // globaltimer at the start of the cycle (prep_kernel's first CTA)
+  bool plan_uploaded = false;            // d_plan7 already holds the host plan (b200lp_set_plan uploads it)
+  cudaEvent_t plan_ev = nullptr;         // ... as of this event on the main stream
+  bool plan_ev_pending = false;          // a prep kernel on the second stream has not yet been ordered behind it
+  bool adaptive_cuts = true;             // sample-sharded exchange cycles move their cuts with the ranks' device times
+  uint32_t last_cycle_ns = 0, last_peer_ns[kMaxPeers] = {0};
   unsigned epoch = 0;                    // launch number, the "published" flag value of d_aggs
   int plan_ctas_per_sm = 0, sm_count = 0;
   DevBuf<b200lp_result> d_results;
@@ -272,6 +291,60 @@ size_t size_grid(b200lp_ctx* ctx, const float mn[3], const float mx[3], size_t n
   return n_cells;
 }
 
+// Everything of the grid build behind the bounds: tables, histogram (per upload piece when `piece_bound` names the pieces,
+// each one behind its copy event — or, for a rank that RECEIVES the cloud from a peer, behind a kernel that waits for the
+// piece's flag in `wait_hdr`), scan, scatter, summed-volume table.
+int grid_tail(b200lp_ctx* ctx, const char* rec, size_t rec_stride, size_t n, size_t n_cells, const size_t* piece_bound,
+              const CloudHeader* wait_hdr, unsigned long long wait_seq) {
+  const int sms = sm_count_of(ctx->device);
+  GridDev& g = ctx->grid;
+  const int nb = (int)((n_cells + kScanItems - 1) / kScanItems);
+  CK(ctx->d_cell_start.reserve(n_cells + 1));
+  CK(ctx->d_fill.reserve(n_cells + 1));
+  CK(ctx->d_block_sums.reserve(nb));
+  CK(ctx->d_pts.reserve(std::max<size_t>(g.n_kept, 1)));
+  const size_t n_sat = ((size_t)g.nx + 1) * ((size_t)g.ny + 1) * ((size_t)g.nz + 1);
+  CK(ctx->d_sat.reserve(n_sat));
+  CK(cudaMemsetAsync(ctx->d_cell_start.p, 0, (n_cells + 1) * sizeof(uint32_t), ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_sat.p, 0, n_sat * sizeof(uint32_t), ctx->stream));
+  g.pts = ctx->d_pts.p;
+  g.cell_start = ctx->d_cell_start.p;
+  g.sat = ctx->d_sat.p;
+  if (piece_bound) {  // every piece is counted as soon as it has landed; only the last one is not hidden by the upload
+    for (int c = 0; c < kPackChunks; ++c) {
+      const size_t i0 = piece_bound[c], i1 = piece_bound[c + 1];
+      if (wait_hdr) {
+        share_wait_piece_kernel<<<1, 32, 0, ctx->stream>>>(wait_hdr, wait_seq, c, (long long)4e9, ctx->d_share_err.p);
+        ++ctx->launches;
+      } else if (i1 > i0) {
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[c], 0));
+      }
+      if (c == kPackChunks - 1) CK(cudaEventRecord(ctx->cev[1], ctx->stream));  // everything has arrived
+      if (i1 > i0 && g.n_kept) {
+        hist_kernel<<<grid_blocks(i1 - i0, 256, sms), 256, 0, ctx->stream>>>(rec, rec_stride, i0, i1, g, ctx->d_cell_start.p);
+        ++ctx->launches;
+      }
+    }
+  } else if (g.n_kept) {
+    hist_kernel<<<grid_blocks(n, 256, sms), 256, 0, ctx->stream>>>(rec, rec_stride, 0, n, g, ctx->d_cell_start.p);
+    ++ctx->launches;
+  }
+  if (g.n_kept) {
+    scan_block_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_cell_start.p, n_cells, ctx->d_block_sums.p);
+    scan_sums_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_block_sums.p, nb, ctx->d_total.p);
+    scan_add_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_cell_start.p, n_cells, ctx->d_block_sums.p, ctx->d_total.p,
+                                                 ctx->d_fill.p);
+    scatter_kernel<<<grid_blocks(n, 256, sms), 256, 0, ctx->stream>>>(rec, rec_stride, n, g, ctx->d_fill.p, ctx->d_pts.p);
+    const size_t ny_threads = ((size_t)g.nx + 1) * (size_t)g.nz, nz_threads = ((size_t)g.nx + 1) * ((size_t)g.ny + 1);
+    sat_y_kernel<<<(unsigned)((ny_threads * 32 + 255) / 256), 256, 0, ctx->stream>>>(g, ctx->d_sat.p);
+    sat_z_kernel<<<(unsigned)((nz_threads + 255) / 256), 256, 0, ctx->stream>>>(g, ctx->d_sat.p);
+    ctx->launches += 6;
+  }
+  CK(cudaGetLastError());
+  ctx->have_cloud = true;
+  return B200LP_OK;
+}
+
 // Brings the cloud to the device and builds the voxel grid + summed-volume table.
 //   src == nullptr : the raw cloud is already in d_raw (or n == 0)
 //   otherwise      : `src` (host, or device when on_device) is copied in pieces on the copy stream, overlapped with the
@@ -281,7 +354,7 @@ size_t size_grid(b200lp_ctx* ctx, const float mn[3], const float mx[3], size_t n
 //       and the call returns when the caller's buffer has been read — nothing waits for the device;
 //     plain upload: bounds_pack_kernel per piece (bounds + 16-byte records on the device), one host round trip for the
 //       bounds, then the histogram over the whole cloud.
-int build_grid(b200lp_ctx* ctx, const void* src, size_t n, size_t stride, bool on_device) {
+int build_grid(b200lp_ctx* ctx, const void* src, size_t n, size_t stride, bool on_device, int share_root = -1) {
   const int sms = sm_count_of(ctx->device);
   GridDev& g = ctx->grid;
   g.n_raw = (uint32_t)n;
@@ -295,9 +368,10 @@ int build_grid(b200lp_ctx* ctx, const void* src, size_t n, size_t stride, bool o
   ctx->pack_threads_used = 0;
   // large host clouds with padding between the points: pack on the host, upload 12 bytes per point (see PackPool)
   bool packing = false;
-  if (src && !on_device && stride >= 16 && n * stride >= kPackMinBytes) {
+  const bool share = share_root >= 0;  // this rank is the root of a shared cloud: always the packing upload (12-byte rows)
+  if (src && !on_device && ((stride >= 16 && n * stride >= kPackMinBytes) || share)) {
     if (!ctx->pack_pool) {
-      const int t = pack_threads_wanted();
+      const int t = share ? std::max(1, pack_threads_wanted()) : pack_threads_wanted();
       if (t > 0) ctx->pack_pool = new (std::nothrow) PackPool(t);
       if (ctx->pack_pool && ctx->pack_pool->threads() == 0) {  // no thread could be started: plain copies from now on
         delete ctx->pack_pool;
@@ -308,6 +382,7 @@ int build_grid(b200lp_ctx* ctx, const void* src, size_t n, size_t stride, bool o
     packing = ctx->pack_pool != nullptr && cudaStreamSynchronize(ctx->copy_stream) == cudaSuccess &&
               ctx->h_stage.reserve(n * 3) == cudaSuccess;
   }
+  if (share && n && !packing) return ctx->fail(B200LP_E_NOMEM, "set_cloud_shared: the packing upload is not available (threads / pinned memory)");
   const char* rec = nullptr;  // what the histogram / scatter passes read, and its stride
   size_t rec_stride = 0;
   size_t n_cells = 1;
@@ -319,6 +394,15 @@ int build_grid(b200lp_ctx* ctx, const void* src, size_t n, size_t stride, bool o
     ctx->pack_threads_used = pool.threads();
     ctx->raw_stride = 12;  // what d_raw holds from here on
     cudaError_t pe = cudaStreamWaitEvent(ctx->copy_stream, ctx->cev[0], 0);  // the copies may not overtake earlier work on d_raw
+    if (pe == cudaSuccess && ctx->push_pending) {  // ... nor the pushes of the previous shared cloud, which read d_raw
+      pe = cudaStreamWaitEvent(ctx->copy_stream, ctx->push_done, 0);
+      ctx->push_pending = false;
+    }
+    if (share && pe == cudaSuccess) {  // the peers must be through with the rows of the previous cycle
+      share_wait_acks_kernel<<<1, 32, 0, ctx->push_stream>>>(ctx->my_header(), ctx->peer_world, ctx->peer_rank, ctx->cloud_seq - 1,
+                                                             (long long)4e9, ctx->d_share_err.p);
+      ++ctx->launches;
+    }
     for (int c = 0; c < kPackChunks; ++c) {
       const size_t i0 = pool.bound(c), i1 = pool.bound(c + 1);
       chunk_bound[c] = i0;
@@ -327,10 +411,37 @@ int build_grid(b200lp_ctx* ctx, const void* src, size_t n, size_t stride, bool o
       if (pe != cudaSuccess || i1 == i0) continue;
       pe = cudaMemcpyAsync(ctx->d_raw.p + i0 * 12, ctx->h_stage.p + i0 * 3, (i1 - i0) * 12, cudaMemcpyHostToDevice, ctx->copy_stream);
       if (pe == cudaSuccess) pe = cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream);
+      if (share && pe == cudaSuccess) {  // piece c goes on to every peer as soon as it has landed here
+        pe = cudaStreamWaitEvent(ctx->push_stream, ctx->chunk_ev[c], 0);
+        const size_t b0 = i0 * 12, b1 = i1 * 12;  // (piece bounds are multiples of 4 points: b0 is 16-byte aligned)
+        share_push_kernel<<<grid_blocks((b1 - b0) / 16 + 1, 256, sm_count_of(ctx->device)), 256, 0, ctx->push_stream>>>(
+            ctx->d_raw.p, b0, b1, ctx->peer_blocks, ctx->peer_world, ctx->peer_rank, c, ctx->cloud_seq, ctx->d_push_ticket.p);
+        ++ctx->launches;
+      }
+    }
+    if (share && pe == cudaSuccess) {
+      for (int c = 0; c < kPackChunks; ++c)  // empty pieces still raise their flag
+        if (pool.bound(c + 1) == pool.bound(c)) {
+          share_push_kernel<<<1, 256, 0, ctx->push_stream>>>(ctx->d_raw.p, 0, 0, ctx->peer_blocks, ctx->peer_world, ctx->peer_rank, c,
+                                                             ctx->cloud_seq, ctx->d_push_ticket.p);
+          ++ctx->launches;
+        }
+      pe = cudaEventRecord(ctx->push_done, ctx->push_stream);
+      ctx->push_pending = true;
     }
     if (pe != cudaSuccess) return ctx->fail(B200LP_E_CUDA, "set_cloud (packing upload): %s", cudaGetErrorString(pe));
     // the caller's buffer is free from here on, and the bounds are already on the host
     const HostBounds hb = pool.bounds();
+    if (share) {  // size, bounds and piece boundaries for the peers: a one-warp kernel on the idle prep stream
+      CloudHeader H{};
+      H.n = n;
+      H.n_finite = hb.n_finite;
+      for (int a = 0; a < 3; ++a) { H.mn[a] = hb.mn[a]; H.mx[a] = hb.mx[a]; }
+      for (int c = 0; c <= kPackChunks; ++c) H.bound[c] = pool.bound(c);
+      H.seq = ctx->cloud_seq;
+      share_header_kernel<<<1, 32, 0, ctx->prep_stream>>>(H, ctx->peer_blocks, ctx->peer_world, ctx->peer_rank);
+      ++ctx->launches;
+    }
     n_cells = size_grid(ctx, hb.mn, hb.mx, hb.n_finite);
     rec = ctx->d_raw.p;
     rec_stride = 12;
@@ -384,46 +495,7 @@ int build_grid(b200lp_ctx* ctx, const void* src, size_t n, size_t stride, bool o
     rec = (const char*)ctx->d_packed.p;
     rec_stride = 16;
   }
-  const int nb = (int)((n_cells + kScanItems - 1) / kScanItems);
-  CK(ctx->d_cell_start.reserve(n_cells + 1));
-  CK(ctx->d_fill.reserve(n_cells + 1));
-  CK(ctx->d_block_sums.reserve(nb));
-  CK(ctx->d_pts.reserve(std::max<size_t>(g.n_kept, 1)));
-  const size_t n_sat = ((size_t)g.nx + 1) * ((size_t)g.ny + 1) * ((size_t)g.nz + 1);
-  CK(ctx->d_sat.reserve(n_sat));
-  CK(cudaMemsetAsync(ctx->d_cell_start.p, 0, (n_cells + 1) * sizeof(uint32_t), ctx->stream));
-  CK(cudaMemsetAsync(ctx->d_sat.p, 0, n_sat * sizeof(uint32_t), ctx->stream));
-  g.pts = ctx->d_pts.p;
-  g.cell_start = ctx->d_cell_start.p;
-  g.sat = ctx->d_sat.p;
-  if (hist_per_chunk) {  // every piece is counted as soon as it has landed; only the last one is not hidden by the upload
-    for (int c = 0; c < kPackChunks; ++c) {
-      const size_t i0 = chunk_bound[c], i1 = chunk_bound[c + 1];
-      if (i1 > i0) CK(cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[c], 0));
-      if (c == kPackChunks - 1) CK(cudaEventRecord(ctx->cev[1], ctx->stream));  // everything has arrived
-      if (i1 > i0 && g.n_kept) {
-        hist_kernel<<<grid_blocks(i1 - i0, 256, sms), 256, 0, ctx->stream>>>(rec, rec_stride, i0, i1, g, ctx->d_cell_start.p);
-        ++ctx->launches;
-      }
-    }
-  } else if (g.n_kept) {
-    hist_kernel<<<grid_blocks(n, 256, sms), 256, 0, ctx->stream>>>(rec, rec_stride, 0, n, g, ctx->d_cell_start.p);
-    ++ctx->launches;
-  }
-  if (g.n_kept) {
-    scan_block_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_cell_start.p, n_cells, ctx->d_block_sums.p);
-    scan_sums_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_block_sums.p, nb, ctx->d_total.p);
-    scan_add_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_cell_start.p, n_cells, ctx->d_block_sums.p, ctx->d_total.p,
-                                                 ctx->d_fill.p);
-    scatter_kernel<<<grid_blocks(n, 256, sms), 256, 0, ctx->stream>>>(rec, rec_stride, n, g, ctx->d_fill.p, ctx->d_pts.p);
-    const size_t ny_threads = ((size_t)g.nx + 1) * (size_t)g.nz, nz_threads = ((size_t)g.nx + 1) * ((size_t)g.ny + 1);
-    sat_y_kernel<<<(unsigned)((ny_threads * 32 + 255) / 256), 256, 0, ctx->stream>>>(g, ctx->d_sat.p);
-    sat_z_kernel<<<(unsigned)((nz_threads + 255) / 256), 256, 0, ctx->stream>>>(g, ctx->d_sat.p);
-    ctx->launches += 6;
-  }
-  CK(cudaGetLastError());
-  ctx->have_cloud = true;
-  return B200LP_OK;
+  return grid_tail(ctx, rec, rec_stride, n, n_cells, hist_per_chunk ? chunk_bound : nullptr, nullptr, 0ull);
 }
 
 // set_cloud returns as soon as the host buffer has been consumed; its device timeline is read back lazily
@@ -449,6 +521,58 @@ void resolve_cycle_timing(b200lp_ctx* ctx) {
     else cudaEventElapsedTime(&ctx->ms_plan, ctx->ev[1], ctx->ev[2]);
   }
   ctx->cycle_timing_pending = false;
+}
+
+unsigned long long cuts_hash(const ShardCuts& c) {  // FNV-1a over the cut shares a launch used
+  unsigned long long h = 1469598103934665603ull;
+  auto mix = [&](uint32_t v) {
+    for (int b = 0; b < 4; ++b) {
+      h ^= (v >> (8 * b)) & 0xffu;
+      h *= 1099511628211ull;
+    }
+  };
+  mix((uint32_t)c.n);
+  for (int k = 0; k <= c.n && k <= B200LP_MAX_PEERS; ++k) {
+    uint32_t u;
+    memcpy(&u, &c.frac[k], 4);
+    mix(u);
+  }
+  return h;
+}
+
+// Moves the shard cuts of the NEXT sample-sharded cycle with the device times the ranks needed for this one. Every rank
+// ends an exchange cycle with the same W durations (they travel in the exchange slots) and the same current cuts, and
+// runs the same arithmetic: all ranks arrive at the same new cuts without another exchange. Model: the time of rank r is
+// spread evenly over its share [f_r, f_r+1) of the estimated-work axis; the new cuts sit at equal shares of the summed
+// time, approached half way per cycle.
+void adapt_cuts(b200lp_ctx* ctx, const uint32_t* ns, int W) {
+  if (W < 2 || W > B200LP_MAX_PEERS) return;
+  double T[B200LP_MAX_PEERS], total = 0.0, mx = 0.0;
+  for (int r = 0; r < W; ++r) {
+    if (ns[r] == 0u) return;
+    T[r] = (double)ns[r];
+    total += T[r];
+    mx = std::max(mx, T[r]);
+  }
+  if (mx <= 1.03 * total / W) return;  // balanced to 3 %: leave the cuts alone
+  double f[B200LP_MAX_PEERS + 1];
+  for (int k = 0; k <= W; ++k) f[k] = ctx->cuts.n == W ? (double)ctx->cuts.frac[k] : (double)k / W;
+  double nf[B200LP_MAX_PEERS + 1];
+  nf[0] = 0.0;
+  nf[W] = 1.0;
+  double cum = 0.0;
+  int r = 0;
+  for (int k = 1; k < W; ++k) {
+    const double target = total * k / W;
+    while (r < W - 1 && cum + T[r] < target) cum += T[r++];
+    const double want = f[r] + (target - cum) / T[r] * (f[r + 1] - f[r]);
+    nf[k] = f[k] + 0.5 * (want - f[k]);
+  }
+  for (int k = 1; k <= W; ++k) nf[k] = std::max(nf[k], nf[k - 1]);
+  ctx->cuts.n = W;
+  for (int k = 0; k <= W; ++k) ctx->cuts.frac[k] = (float)std::min(1.0, std::max(0.0, nf[k]));
+  ctx->cuts.frac[0] = 0.f;
+  ctx->cuts.frac[W] = 1.f;
 }
 
 int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_result* outs, bool plan_resident = false,
@@ -512,10 +636,11 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
     init_on_main = true;
     CK(ctx->d_work.reserve(1));
     CK(cudaMemsetAsync(ctx->d_work.p, 0, sizeof(unsigned long long), ctx->stream));
+    CK(ctx->d_tstart.reserve(1));
+    CK(cudaMemsetAsync(ctx->d_tstart.p, 0, sizeof(unsigned long long), ctx->stream));
   }
   if (!ctx->plan_ctas_per_sm) {
     ctx->sm_count = sm_count_of(ctx->device);
-    CK(cudaFuncSetAttribute(prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrepSmemBytes));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->plan_ctas_per_sm, plan_kernel, kThreads, 0));
     if (ctx->plan_ctas_per_sm < 1) return ctx->fail(B200LP_E_CUDA, "plan_kernel does not fit on an SM");
   }
@@ -554,26 +679,43 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   }
   cudaStream_t ps = overlap ? ctx->prep_stream : ctx->stream;
   if (overlap && ctx->have_cycle_event) CK(cudaStreamWaitEvent(ps, ctx->ev[2], 0));
+  if (overlap && ctx->plan_ev_pending) CK(cudaStreamWaitEvent(ps, ctx->plan_ev, 0));
+  ctx->plan_ev_pending = false;  // (on the main stream the upload is ordered before the kernels anyway)
   ctx->cycle_overlapped = overlap;
   CK(cudaEventRecord(ctx->ev[0], ps));
-  CK(cudaMemcpyAsync(ctx->d_robots.p, ctx->h_robots.p, n_robots * sizeof(RobotIn), cudaMemcpyHostToDevice, ps));
-  if (plan_total && !plan_resident)
+  if (n_robots > 1) CK(cudaMemcpyAsync(ctx->d_robots.p, ctx->h_robots.p, n_robots * sizeof(RobotIn), cudaMemcpyHostToDevice, ps));
+  if (plan_total && !plan_resident && !ctx->plan_uploaded)
     CK(cudaMemcpyAsync(ctx->d_plan7.p, ctx->h_plan7.p, plan_total * 7 * sizeof(double), cudaMemcpyHostToDevice, ps));
   CK(cudaEventRecord(ctx->ev[1], ps));
+  // single-robot cycles hand their query to the kernels as an argument; the device copy (read by the read-back kernels
+  // only) follows the launches
+  const int by_value = n_robots == 1 ? 1 : 0;
+  const RobotIn q0 = ctx->h_robots.p[0];
   prep_kernel<<<dim3((unsigned)n_chunks, (unsigned)n_robots), kPrepThreads, kPrepSmemBytes, ps>>>(
-      ctx->C, ctx->d_robots.p, t_cap, rank, count, ctx->cuts, ctx->epoch, ctx->d_tickets.p, ctx->d_aggs.p, ctx->d_rec_vel.p,
-      ctx->d_rec_steps.p, ctx->d_rec_dt.p, ctx->d_rec_sample.p, ctx->d_meta.p, ctx->d_plan7.p, ctx->d_plan_pts.p,
-      ctx->d_rec_pose_off.p, ctx->d_poses.p, pose_stride, ctx->d_rec_pp.p, want_pp);
+      ctx->C, ctx->d_robots.p, q0, by_value, ctx->d_tstart.p, t_cap, rank, count, ctx->cuts, ctx->epoch, ctx->d_tickets.p,
+      ctx->d_aggs.p, ctx->d_rec_vel.p, ctx->d_rec_steps.p, ctx->d_rec_dt.p, ctx->d_rec_sample.p, ctx->d_meta.p, ctx->d_plan7.p,
+      ctx->d_plan_pts.p, ctx->d_rec_pose_off.p, ctx->d_poses.p, pose_stride, ctx->d_rec_pp.p, want_pp);
   CK(cudaEventRecord(ctx->ev[4], ps));
   if (overlap) {
     CK(cudaStreamWaitEvent(ctx->stream, ctx->ev[4], 0));
     CK(cudaEventRecord(ctx->ev[6], ctx->stream));  // plan_kernel's start on the main stream (after the grid build)
   }
+  PeerExchange px{};
+  px.t_start = ctx->d_tstart.p;
+  if (exchange) {  // the cross-GPU argmin through peer memory, by the last CTA of plan_kernel
+    px.world = ctx->peer_world;
+    px.rank = ctx->peer_rank;
+    px.seq = ctx->peer_seq;  // (advanced by the caller before anything could fail)
+    px.mine = ctx->peer_slots();
+    px.timeout_cycles = (long long)4e9;  // ~2 s of SM clocks
+    px.cuts_hash = cuts_hash(ctx->cuts);
+    px.peers = ctx->peer_table;
+  }
   plan_kernel<<<plan_grid, kThreads, 0, ctx->stream>>>(
-      ctx->C, ctx->grid, ctx->d_robots.p, ctx->d_meta.p, (int)n_robots, t_cap, cap_local, ctx->d_rec_vel.p,
+      ctx->C, ctx->grid, ctx->d_robots.p, q0, by_value, ctx->d_meta.p, (int)n_robots, t_cap, cap_local, ctx->d_rec_vel.p,
       ctx->d_rec_steps.p, ctx->d_rec_pose_off.p, ctx->d_poses.p, ctx->d_rec_pp.p, ctx->d_plan_pts.p, ctx->d_cost.p,
       ctx->d_scores.p, ctx->d_first_hit.p, ctx->d_work.p, ctx->d_partial.p, ctx->d_tickets2.p, ctx->d_results.p,
-      (direct && !exchange) ? ctx->h_direct.p : nullptr, ctx->direct_seq);
+      direct ? ctx->h_direct.p : nullptr, ctx->direct_seq, px);
   CK(cudaEventRecord(ctx->ev[5], ctx->stream));
   if (n_robots > 1) {  // a single robot's argmin is folded into plan_kernel
     argmin_kernel<<<dim3((unsigned)argmin_ctas, (unsigned)n_robots), kArgminThreads, 0, ctx->stream>>>(
@@ -581,16 +723,11 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
         ctx->d_tickets2.p, ctx->d_results.p, ctx->d_work.p);
     ++ctx->launches;
   }
-  if (exchange) {  // the cross-GPU argmin through peer memory; its last lane hands the global result to the host
-    ++ctx->peer_seq;
-    exchange_kernel<<<1, 32, 0, ctx->stream>>>(ctx->peer_table, ctx->d_peer_slots.p, ctx->peer_rank, ctx->peer_world, ctx->peer_seq,
-                                               ctx->d_results.p, ctx->d_meta.p, ctx->h_direct.p, ctx->direct_seq,
-                                               (long long)4e9 /* ~2 s of SM clocks */);
-    ++ctx->launches;
-  }
   ctx->launches += 2;
   CK(cudaEventRecord(ctx->ev[2], ctx->stream));
   ctx->have_cycle_event = true;
+  if (n_robots == 1)  // for the read-back kernels (poses_kernel, count_radius_kernel); off the cycle's critical path
+    CK(cudaMemcpyAsync(ctx->d_robots.p, ctx->h_robots.p, sizeof(RobotIn), cudaMemcpyHostToDevice, ctx->stream));
   if (direct) {
     // the kernel's last CTA writes the result block into pinned host memory and raises seq: no copies, no stream sync
     CK(cudaGetLastError());
@@ -608,6 +745,8 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
     __atomic_thread_fence(__ATOMIC_ACQUIRE);
     ctx->h_results.p[0] = ctx->h_direct.p->r;
     ctx->h_meta.p[0] = ctx->h_direct.p->m;
+    ctx->last_cycle_ns = ctx->h_direct.p->cycle_ns;
+    if (exchange) memcpy(ctx->last_peer_ns, ctx->h_direct.p->peer_ns, sizeof(ctx->last_peer_ns));
   } else {
     CK(cudaMemcpyAsync(ctx->h_results.p, ctx->d_results.p, n_robots * sizeof(b200lp_result), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_meta.p, ctx->d_meta.p, n_robots * sizeof(RobotMeta), cudaMemcpyDeviceToHost, ctx->stream));
@@ -617,7 +756,12 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   }
   ctx->meta_host.assign(ctx->h_meta.p, ctx->h_meta.p + n_robots);
   if (exchange && (ctx->meta_host[0].error & 8))
-    return ctx->fail(B200LP_E_STATE, "plan_shard_exchange: a peer did not deliver its result within the time limit");
+    return ctx->fail(B200LP_E_STATE, "plan_shard_exchange: a peer did not deliver its result within the time limit "
+                                     "(call b200lp_peer_resync on every rank before the next cycle)");
+  if (exchange && (ctx->meta_host[0].error & 64))
+    return ctx->fail(B200LP_E_STATE, "plan_shard_exchange: the ranks cut the sample grid differently "
+                                     "(call b200lp_peer_resync on every rank before the next cycle)");
+  if (exchange && ctx->adaptive_cuts && !ctx->meta_host[0].error) adapt_cuts(ctx, ctx->last_peer_ns, ctx->peer_world);
   for (size_t i = 0; i < n_robots; ++i) {
     if (ctx->meta_host[i].error & 16)
       return ctx->fail(B200LP_E_STATE, "robot %zu: plan_kernel scored %d trajectories / %lld poses where prep_kernel listed %d / %lld",
@@ -751,7 +895,7 @@ void b200lp_destroy(b200lp_ctx* ctx) {
   ctx->h_bounds.release(); ctx->d_robots.release(); ctx->d_meta.release(); ctx->d_plan7.release();
   ctx->d_plan_pts.release(); ctx->d_rec_vel.release(); ctx->d_rec_steps.release(); ctx->d_rec_sample.release();
   ctx->d_first_hit.release(); ctx->d_rec_dt.release(); ctx->d_cost.release(); ctx->d_scores.release();
-  ctx->d_rec_pose_off.release(); ctx->d_poses.release(); ctx->d_rec_pp.release(); ctx->d_gplan7.release(); ctx->d_prune_pcl.release(); ctx->d_prune_meta.release(); ctx->h_prune_meta.release(); ctx->d_blocked.release(); ctx->h_blocked.release(); ctx->d_partial.release(); ctx->d_tickets2.release(); ctx->d_tickets.release(); ctx->d_aggs.release(); ctx->d_work.release(); ctx->d_results.release(); ctx->d_count.release(); ctx->d_scratch.release();
+  ctx->d_rec_pose_off.release(); ctx->d_poses.release(); ctx->d_rec_pp.release(); ctx->d_gplan7.release(); ctx->d_prune_pcl.release(); ctx->d_prune_meta.release(); ctx->h_prune_meta.release(); ctx->d_blocked.release(); ctx->h_blocked.release(); ctx->d_partial.release(); ctx->d_tickets2.release(); ctx->d_tickets.release(); ctx->d_aggs.release(); ctx->d_work.release(); ctx->d_tstart.release(); ctx->d_results.release(); ctx->d_count.release(); ctx->d_scratch.release();
   ctx->h_robots.release(); ctx->h_plan7.release(); ctx->h_results.release(); ctx->h_meta.release();
   ctx->h_count.release(); ctx->h_direct.release();
   ctx->d_scan.release(); ctx->d_obs_a.release(); ctx->d_obs_b.release(); ctx->d_obs_hist.release(); ctx->d_obs_sums.release();
@@ -765,8 +909,12 @@ void b200lp_destroy(b200lp_ctx* ctx) {
     if (ev) cudaEventDestroy(ev);
   for (auto& ev : ctx->cev)
     if (ev) cudaEventDestroy(ev);
+  if (ctx->plan_ev) cudaEventDestroy(ctx->plan_ev);
   peer_detach(ctx);
-  ctx->d_peer_slots.release();
+  ctx->d_peer_block.release();
+  ctx->d_push_ticket.release(); ctx->d_share_err.release(); ctx->h_share_hdr.release(); ctx->h_share_err.release();
+  if (ctx->push_done) cudaEventDestroy(ctx->push_done);
+  if (ctx->push_stream) { cudaStreamSynchronize(ctx->push_stream); cudaStreamDestroy(ctx->push_stream); }
   if (ctx->prep_stream) { cudaStreamSynchronize(ctx->prep_stream); cudaStreamDestroy(ctx->prep_stream); }
   delete ctx->pack_pool;
   ctx->h_stage.release();
@@ -804,6 +952,104 @@ int b200lp_set_cloud_device(b200lp_ctx* ctx, const void* dev_pts, size_t n, size
   return set_cloud_common(ctx, dev_pts, n, stride_bytes, true);
 }
 
+int b200lp_peer_reserve_cloud(b200lp_ctx* ctx, size_t max_points) {
+  if (!ctx) return B200LP_E_INVALID;
+  if (ctx->d_peer_block.p) return ctx->fail(B200LP_E_STATE, "peer_reserve_cloud: call it before b200lp_peer_export");
+  if (max_points > 0xfffffff0ull) return ctx->fail(B200LP_E_INVALID, "peer_reserve_cloud: more than 2^32 points");
+  ctx->peer_cloud_cap = max_points;
+  return B200LP_OK;
+}
+
+int b200lp_set_cloud_shared(b200lp_ctx* ctx, int root, const void* pts, size_t n, size_t stride) {
+  if (!ctx) return B200LP_E_INVALID;
+  if (ctx->peer_world < 1) return ctx->fail(B200LP_E_STATE, "set_cloud_shared: call b200lp_peer_attach first");
+  if (root < 0 || root >= ctx->peer_world) return ctx->fail(B200LP_E_INVALID, "set_cloud_shared: bad root");
+  const bool is_root = root == ctx->peer_rank;
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->push_stream) {
+    CK(cudaStreamCreateWithFlags(&ctx->push_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->push_done, cudaEventDisableTiming));
+    CK(ctx->d_push_ticket.reserve(1));
+    CK(ctx->d_share_err.reserve(1));
+    CK(ctx->h_share_hdr.reserve(1));
+    CK(ctx->h_share_err.reserve(1));
+    memset(ctx->h_share_hdr.p, 0, sizeof(CloudHeader));
+    CK(cudaMemsetAsync(ctx->d_push_ticket.p, 0, sizeof(unsigned), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_share_err.p, 0, sizeof(int), ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  ++ctx->cloud_seq;  // before anything can fail: the ranks stay in step
+  ctx->cloud_timing_pending = false;
+  if (is_root) {
+    if ((n && !pts) || stride < 12 || (stride & 3)) return ctx->fail(B200LP_E_INVALID, "set_cloud_shared: bad pointer or stride");
+    if (n > ctx->peer_cloud_cap)
+      return ctx->fail(B200LP_E_INVALID, "set_cloud_shared: %zu points exceed the %zu reserved with b200lp_peer_reserve_cloud", n, ctx->peer_cloud_cap);
+    if (ctx->peer_world == 1) return set_cloud_common(ctx, pts, n, stride, false);  // nobody to share with
+    CK(ctx->d_raw.reserve(std::max<size_t>(n * 12, 16)));
+    ctx->raw_stride = 12;
+    if (n == 0) {  // an empty cloud: header and piece flags only
+      CloudHeader H{};
+      H.seq = ctx->cloud_seq;
+      share_wait_acks_kernel<<<1, 32, 0, ctx->push_stream>>>(ctx->my_header(), ctx->peer_world, ctx->peer_rank, ctx->cloud_seq - 1,
+                                                             (long long)4e9, ctx->d_share_err.p);
+      share_header_kernel<<<1, 32, 0, ctx->push_stream>>>(H, ctx->peer_blocks, ctx->peer_world, ctx->peer_rank);
+      for (int c = 0; c < kPackChunks; ++c)
+        share_push_kernel<<<1, 256, 0, ctx->push_stream>>>(ctx->d_raw.p, 0, 0, ctx->peer_blocks, ctx->peer_world, ctx->peer_rank, c,
+                                                           ctx->cloud_seq, ctx->d_push_ticket.p);
+      ctx->launches += 2 + kPackChunks;
+    }
+    int rc = build_grid(ctx, n ? pts : nullptr, n, stride, false, n ? root : -1);
+    if (rc) return rc;
+    ctx->last_h2d_bytes = n * 12;
+  } else {
+    // receive: the root's header first (the host sizes the grid with it), then the pieces, each behind its flag
+    share_wait_header_kernel<<<1, 32, 0, ctx->stream>>>(ctx->my_header(), ctx->cloud_seq, ctx->h_share_hdr.p, (long long)4e9);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+    volatile unsigned long long* flag = &ctx->h_share_hdr.p->seq;
+    unsigned spins = 0;
+    while (*flag != ctx->cloud_seq) {
+      __builtin_ia32_pause();
+      if ((++spins & 0xfffu) == 0u) {
+        const cudaError_t qe = cudaStreamQuery(ctx->stream);
+        if (qe == cudaErrorNotReady) continue;
+        if (qe != cudaSuccess) return ctx->fail(B200LP_E_CUDA, "set_cloud_shared: %s", cudaGetErrorString(qe));
+        if (*flag != ctx->cloud_seq) return ctx->fail(B200LP_E_CUDA, "set_cloud_shared: the header kernel finished without publishing");
+      }
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    const CloudHeader H = *ctx->h_share_hdr.p;
+    if (H.n == ~0ull)
+      return ctx->fail(B200LP_E_STATE, "set_cloud_shared: the root did not deliver the cloud within the time limit "
+                                       "(call b200lp_peer_resync on every rank before the next cycle)");
+    if (H.n > ctx->peer_cloud_cap)
+      return ctx->fail(B200LP_E_INVALID, "set_cloud_shared: the root's %llu points exceed the %zu reserved here", H.n, ctx->peer_cloud_cap);
+    GridDev& g = ctx->grid;
+    g.n_raw = (uint32_t)H.n;
+    g.n_kept = 0;
+    g.nx = g.ny = g.nz = 1;
+    g.org[0] = g.org[1] = g.org[2] = 0.f;
+    g.inv_xy = g.inv_z = 1.f;
+    g.cmax = 1.f;
+    CK(ctx->d_total.reserve(1));
+    CK(cudaEventRecord(ctx->cev[0], ctx->stream));
+    ctx->pack_threads_used = 0;
+    const size_t n_cells = size_grid(ctx, H.mn, H.mx, (size_t)H.n_finite);
+    size_t bound[kPackChunks + 1];
+    for (int c = 0; c <= kPackChunks; ++c) bound[c] = (size_t)H.bound[c];
+    int rc = grid_tail(ctx, ctx->my_rows(), 12, (size_t)H.n, n_cells, bound, ctx->my_header(), ctx->cloud_seq);
+    if (rc) return rc;
+    share_ack_kernel<<<1, 32, 0, ctx->stream>>>(ctx->peer_blocks.base[root], ctx->peer_rank, ctx->cloud_seq);
+    ++ctx->launches;
+    ctx->last_h2d_bytes = 0;
+    ctx->raw_stride = 12;
+  }
+  CK(cudaEventRecord(ctx->cev[2], ctx->stream));
+  ctx->cloud_timing_pending = true;
+  ctx->have_cycle = false;
+  return B200LP_OK;
+}
+
 int b200lp_last_upload(const b200lp_ctx* ctx, size_t* h2d_bytes, int32_t* pack_threads) {
   if (!ctx || !ctx->have_cloud) return B200LP_E_STATE;
   if (h2d_bytes) *h2d_bytes = ctx->last_h2d_bytes;
@@ -817,6 +1063,21 @@ int b200lp_set_plan(b200lp_ctx* ctx, const double* p, size_t n) {
   if (n > B200LP_MAX_PLAN) return ctx->fail(B200LP_E_INVALID, "set_plan: more than B200LP_MAX_PLAN poses");
   ctx->plan_host.assign(p, p + n * 7);
   ctx->plan_on_device = false;
+  // upload now, so that the cycle itself starts with its first kernel: the copy is ordered on the main stream, a prep
+  // kernel on the second stream waits for plan_ev
+  ctx->plan_uploaded = false;
+  if (n) {
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->plan_ev) CK(cudaEventSynchronize(ctx->plan_ev));  // the staging buffer may still feed the previous upload
+    CK(ctx->h_plan7.reserve(n * 7));
+    CK(ctx->d_plan7.reserve(std::max<size_t>(n * 7, (size_t)B200LP_MAX_PLAN * 7)));
+    memcpy(ctx->h_plan7.p, p, n * 7 * sizeof(double));
+    CK(cudaMemcpyAsync(ctx->d_plan7.p, ctx->h_plan7.p, n * 7 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (!ctx->plan_ev) CK(cudaEventCreateWithFlags(&ctx->plan_ev, cudaEventDisableTiming));
+    CK(cudaEventRecord(ctx->plan_ev, ctx->stream));
+    ctx->plan_uploaded = true;
+    ctx->plan_ev_pending = true;
+  }
   return B200LP_OK;
 }
 
@@ -829,7 +1090,7 @@ static int plan_shard_common(b200lp_ctx* ctx, const b200lp_query* q, int rank, i
   CK(ctx->h_robots.reserve(1));
   CK(ctx->h_plan7.reserve(std::max<size_t>(np * 7, 7)));
   fill_robot(ctx->h_robots.p, q, 0, (int32_t)np);
-  if (np && !resident) memcpy(ctx->h_plan7.p, ctx->plan_host.data(), np * 7 * sizeof(double));
+  if (np && !resident && !ctx->plan_uploaded) memcpy(ctx->h_plan7.p, ctx->plan_host.data(), np * 7 * sizeof(double));
   return run_cycle(ctx, 1, rank, count, out, resident, exchange);
 }
 
@@ -843,13 +1104,14 @@ int b200lp_peer_export(b200lp_ctx* ctx, uint8_t handle[B200LP_PEER_HANDLE_BYTES]
   static_assert(sizeof(cudaIpcMemHandle_t) == B200LP_PEER_HANDLE_BYTES, "CUDA IPC handle size");
   static_assert(kMaxPeers == B200LP_MAX_PEERS, "peer table size");
   CK(cudaSetDevice(ctx->device));
-  if (!ctx->d_peer_slots.p) {
-    CK(ctx->d_peer_slots.reserve(2 * kMaxPeers));
-    CK(cudaMemsetAsync(ctx->d_peer_slots.p, 0, 2 * kMaxPeers * sizeof(PeerSlot), ctx->stream));
+  if (!ctx->d_peer_block.p) {
+    const size_t bytes = kPeerRowsOff + ((ctx->peer_cloud_cap * 12 + 255) & ~(size_t)255);
+    CK(ctx->d_peer_block.reserve(bytes));
+    CK(cudaMemsetAsync(ctx->d_peer_block.p, 0, kPeerRowsOff, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
   }
   cudaIpcMemHandle_t h;
-  CK(cudaIpcGetMemHandle(&h, ctx->d_peer_slots.p));
+  CK(cudaIpcGetMemHandle(&h, ctx->d_peer_block.p));
   memcpy(handle, &h, sizeof(h));
   return B200LP_OK;
 }
@@ -859,6 +1121,7 @@ static void peer_detach(b200lp_ctx* ctx) {
     if (ctx->peer_opened[r]) cudaIpcCloseMemHandle(ctx->peer_opened[r]);
     ctx->peer_opened[r] = nullptr;
     ctx->peer_table.slots[r] = nullptr;
+    ctx->peer_blocks.base[r] = nullptr;
   }
   ctx->peer_rank = -1;
   ctx->peer_world = 0;
@@ -868,13 +1131,14 @@ int b200lp_peer_attach(b200lp_ctx* ctx, int rank, int world, const uint8_t* hand
   if (!ctx) return B200LP_E_INVALID;
   if (!handles || world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
     return ctx->fail(B200LP_E_INVALID, "peer_attach: bad rank / world (at most %d peers)", kMaxPeers);
-  if (!ctx->d_peer_slots.p) return ctx->fail(B200LP_E_STATE, "peer_attach: call b200lp_peer_export first");
+  if (!ctx->d_peer_block.p) return ctx->fail(B200LP_E_STATE, "peer_attach: call b200lp_peer_export first");
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
   peer_detach(ctx);
   for (int r = 0; r < world; ++r) {
     if (r == rank) {
-      ctx->peer_table.slots[r] = ctx->d_peer_slots.p;
+      ctx->peer_table.slots[r] = ctx->peer_slots();
+      ctx->peer_blocks.base[r] = ctx->d_peer_block.p;
       continue;
     }
     cudaIpcMemHandle_t h;
@@ -888,19 +1152,78 @@ int b200lp_peer_attach(b200lp_ctx* ctx, int rank, int world, const uint8_t* hand
     }
     ctx->peer_opened[r] = p;
     ctx->peer_table.slots[r] = (PeerSlot*)p;
+    ctx->peer_blocks.base[r] = (char*)p;
   }
   ctx->peer_rank = rank;
   ctx->peer_world = world;
-  ctx->peer_seq = 0;
-  CK(cudaMemsetAsync(ctx->d_peer_slots.p, 0, 2 * kMaxPeers * sizeof(PeerSlot), ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->cuts = ShardCuts{};
+  // The slots and the cloud header were zeroed when the block was allocated (b200lp_peer_export), i.e. before any peer
+  // could know its handle: a FIRST attach must not clear them again — a faster peer may already have stored its first
+  // result. Only a ctx that has exchanged before starts over (then the application needs a barrier between this call
+  // and the first exchange, as for b200lp_peer_resync).
+  if (ctx->peer_seq != 0 || ctx->cloud_seq != 0) {
+    ctx->peer_seq = 0;
+    ctx->cloud_seq = 0;
+    CK(cudaMemsetAsync(ctx->d_peer_block.p, 0, kPeerRowsOff, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
   return B200LP_OK;
 }
 
 int b200lp_plan_shard_exchange(b200lp_ctx* ctx, const b200lp_query* q, b200lp_result* out) {
   if (!ctx) return B200LP_E_INVALID;
   if (ctx->peer_world < 1) return ctx->fail(B200LP_E_STATE, "plan_shard_exchange: call b200lp_peer_attach first");
+  ++ctx->peer_seq;  // before anything can fail: a rank whose cycle errors out early stays in step with its peers
   return plan_shard_common(ctx, q, ctx->peer_rank, ctx->peer_world, out, true);
+}
+
+int b200lp_peer_resync(b200lp_ctx* ctx) {
+  if (!ctx) return B200LP_E_INVALID;
+  if (ctx->peer_world < 1) return ctx->fail(B200LP_E_STATE, "peer_resync: call b200lp_peer_attach first");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->peer_seq = 0;
+  ctx->cuts = ShardCuts{};
+  ctx->cloud_seq = 0;
+  if (ctx->push_stream) CK(cudaStreamSynchronize(ctx->push_stream));
+  CK(cudaMemsetAsync(ctx->d_peer_block.p, 0, kPeerRowsOff, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return B200LP_OK;
+}
+
+int b200lp_set_shard_cuts(b200lp_ctx* ctx, const float* shares, int count) {
+  if (!ctx) return B200LP_E_INVALID;
+  if (count < 0 || count > B200LP_MAX_PEERS || (count && !shares)) return ctx->fail(B200LP_E_INVALID, "set_shard_cuts: bad count");
+  ShardCuts c{};
+  c.n = count;
+  for (int k = 0; k <= count && count; ++k) {
+    if (!(shares[k] >= 0.f && shares[k] <= 1.f) || (k && shares[k] < shares[k - 1]))
+      return ctx->fail(B200LP_E_INVALID, "set_shard_cuts: shares must rise from 0 to 1");
+    c.frac[k] = shares[k];
+  }
+  if (count && (c.frac[0] != 0.f || c.frac[count] != 1.f)) return ctx->fail(B200LP_E_INVALID, "set_shard_cuts: shares must rise from 0 to 1");
+  ctx->cuts = c;
+  return B200LP_OK;
+}
+
+int b200lp_get_shard_cuts(const b200lp_ctx* ctx, float* shares, int* count) {
+  if (!ctx || !shares || !count) return B200LP_E_INVALID;
+  *count = ctx->cuts.n;
+  for (int k = 0; k <= ctx->cuts.n; ++k) shares[k] = ctx->cuts.frac[k];
+  return B200LP_OK;
+}
+
+int b200lp_set_adaptive_cuts(b200lp_ctx* ctx, int on) {
+  if (!ctx) return B200LP_E_INVALID;
+  ctx->adaptive_cuts = on != 0;
+  return B200LP_OK;
+}
+
+int b200lp_last_cycle_ns(const b200lp_ctx* ctx, uint32_t* cycle_ns, uint32_t* peer_ns) {
+  if (!ctx || !ctx->have_cycle) return B200LP_E_STATE;
+  if (cycle_ns) *cycle_ns = ctx->last_cycle_ns;
+  if (peer_ns) memcpy(peer_ns, ctx->last_peer_ns, sizeof(ctx->last_peer_ns));
+  return B200LP_OK;
 }
 
 int b200lp_plan(b200lp_ctx* ctx, const b200lp_query* q, b200lp_result* out) { return b200lp_plan_shard(ctx, q, 0, 1, out); }
@@ -922,6 +1245,7 @@ int b200lp_plan_batch(b200lp_ctx* ctx, const b200lp_query* qs, size_t n_robots, 
   }
   if (total) memcpy(ctx->h_plan7.p, plans, (size_t)total * 7 * sizeof(double));
   ctx->plan_on_device = false;  // the fleet call brings its own plans; a device-side prune plan does not survive it
+  ctx->plan_uploaded = false;   // ... and neither does the uploaded copy of the single-robot plan (plan_host does)
   return run_cycle(ctx, n_robots, 0, 1, outs);
 }
 
@@ -1328,6 +1652,28 @@ int b200lp_last_kernel_ms(const b200lp_ctx* ctx, float* ms_prep_kernel, float* m
   if (ms_plan_kernel) *ms_plan_kernel = ctx->ms_k_plan;
   if (ms_argmin_kernel) *ms_argmin_kernel = ctx->ms_k_argmin;
   return B200LP_OK;
+}
+
+int b200lp_work_counters(b200lp_ctx* ctx, uint64_t out[4], int reset) {
+  if (!ctx) return B200LP_E_INVALID;
+#if B200LP_COUNT
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  unsigned long long v[4] = {0ull, 0ull, 0ull, 0ull};
+  if (out) {
+    CK(cudaMemcpyFromSymbol(v, g_counters, sizeof(v)));
+    for (int k = 0; k < 4; ++k) out[k] = v[k];
+  }
+  if (reset) {
+    const unsigned long long z[4] = {0ull, 0ull, 0ull, 0ull};
+    CK(cudaMemcpyToSymbol(g_counters, z, sizeof(z)));
+  }
+  return B200LP_OK;
+#else
+  (void)out;
+  (void)reset;
+  return ctx->fail(B200LP_E_STATE, "work_counters: this is not the counting build (libb200lp_count.so, -DB200LP_COUNT=1)");
+#endif
 }
 
 int64_t b200lp_launch_count(const b200lp_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -13,10 +13,16 @@
 
 namespace lp {
 
-constexpr int kWarpsPerCta = 4;
+#ifndef B200LP_WARPS
+#define B200LP_WARPS 4
+#endif
+constexpr int kWarpsPerCta = B200LP_WARPS;
 constexpr int kThreads = kWarpsPerCta * 32;
 #ifndef B200LP_GROUP
 #define B200LP_GROUP 4
+#endif
+#ifndef B200LP_SC_COMPARE
+#define B200LP_SC_COMPARE 0  // 1: short-circuit && in the sweep's pre-test compare (A/B builds)
 #endif
 constexpr int kGroup = B200LP_GROUP;  // consecutive poses swept against one candidate stream (power of two)
 constexpr int kPreStride = 5;   // float4 per pose in the pre-test stash (4 used + 1 pad: conflict-free 80-byte stride)
@@ -97,6 +103,9 @@ struct RobotMeta {
 struct DirectOut {
   b200lp_result r;
   RobotMeta m;
+  uint32_t cycle_ns;     // device time of the cycle: first CTA of prep_kernel -> last CTA of plan_kernel (globaltimer)
+  uint32_t pad;
+  uint32_t peer_ns[16];  // sample-sharded cycles: the same figure of every rank (what the shard cuts are moved with)
   unsigned long long seq;
 };
 
@@ -497,33 +506,92 @@ __device__ __forceinline__ bool exact_in_radius(const float* stash, int col, flo
 // (iy, iz); cell-sorted storage makes it ONE contiguous range of float4, which the warp streams with coalesced
 // 512-byte loads.
 // ---------------------------------------------------------------------------------------------
+#ifndef B200LP_COUNT
+#define B200LP_COUNT 0  // 1: the counting build (libb200lp_count.so): work counters for the roofline accounting, never timed
+#endif
+#if B200LP_COUNT
+__device__ unsigned long long g_counters[4];  // candidates pre-tested, 32-candidate rounds, exact re-tests, groups swept
+#endif
+
+// What the sweep needs of the grid, by value: the function is NOT inlined (its inner loop wants the whole predicate file and
+// a register allocation of its own; inlined into plan_kernel's nested loops its twelve compares per candidate serialised
+// through the few predicates left over, +18 % on the kernel), and a reference to a kernel parameter would cost a local copy.
+struct SweepGrid {
+  const float4* pts;
+  const uint32_t* cell_start;
+  int nx, ny;
+  float cmax;
+};
+#ifndef B200LP_SWEEP_INLINE
+#define B200LP_SWEEP_INLINE 1
+#endif
+#if B200LP_SWEEP_INLINE
+#define B200LP_SWEEP_ATTR __forceinline__
+#else
+#define B200LP_SWEEP_ATTR __noinline__
+#endif
 template <bool kMinMax>
-__device__ __forceinline__ unsigned sweep_points(const GridDev& g, const float* stash, const float4* pre, int col0,
-                                                 int lane, const CellBox& ub) {
+__device__ B200LP_SWEEP_ATTR unsigned sweep_points(const SweepGrid g, const float* stash, const float4* pre, int col0,
+                                                   int lane, const CellBox ub) {
   if (ub.x0 > ub.x1) return 0u;
   const int nyr = ub.y1 - ub.y0 + 1;
   const int nrows = nyr * (ub.z1 - ub.z0 + 1);
   const float inv_nyr = 1.0f / (float)nyr;
 
-  // pre-test coefficients of the 4 poses, in registers
-  float4 ca[kGroup], cb[kGroup], cc[kGroup], ch[kGroup];
+  // Pre-test coefficients of the kGroup poses, in registers. CollisionModel: per pose the x and y axes of the box with
+  // -k = -fl(centre . axis) folded in (8 floats); the half extents of x and y shared by the group (their maximum: the
+  // poses carry the same cuboid, the extents differ by roundings only); and ONE slab for the z axis of all poses: the box's
+  // z axis is the robot's, which the rollout never tilts, so the poses' slabs a_q . p - k_q in [-h_q, h_q] are intervals
+  // of (nearly) the same linear form. With A the axis of the group's first pose, a_q . p = A . p - (A - a_q) . p and
+  // |(A - a_q) . p| <= |A - a_q|_1 cmax for every cloud point, so A . p in [k_q - h_q - D_q, k_q + h_q + D_q]; the slab
+  // tested is the hull of those intervals, widened by the rounding of both FMA chains and of this arithmetic
+  // (<= 2e-6 cmax in all). A superset of the per-pose test, like everything in the pre-test: survivors are re-decided
+  // exactly. 39 registers instead of 60, and 27 FMAs + 9 compares per candidate instead of 36 + 12.
+  // CollisionMinMaxModel: the poses' AABBs (exact compares need no slack).
+  float4 ca[kGroup], cb[kGroup];
+  float hx = -1.0f, hy = -1.0f, zc = 0.f, zr = -1.0f;
+  float ax_z = 0.f, ay_z = 0.f, az_z = 0.f;
+  unsigned alive = 0u;  // poses still worth testing: live ones below the lowest pose known to collide (warp-uniform)
+  {
+    float lo = 3.402823466e+38f, hi = -3.402823466e+38f;
 #pragma unroll
-  for (int q = 0; q < kGroup; ++q) {
-    const int col = col0 + q;
-    if (kMinMax) {  // exact compares need no slack
-      ca[q] = make_float4(stash[F_MNX * 32 + col], stash[F_MNY * 32 + col], stash[F_MNZ * 32 + col], 0.f);
-      cb[q] = make_float4(stash[F_MXX * 32 + col], stash[F_MXY * 32 + col], stash[F_MXZ * 32 + col], 0.f);
-      cc[q] = ch[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    } else {
-      ca[q] = pre[col * kPreStride + 0];
-      cb[q] = pre[col * kPreStride + 1];
-      cc[q] = pre[col * kPreStride + 2];
-      ch[q] = pre[col * kPreStride + 3];
+    for (int q = 0; q < kGroup; ++q) {
+      const int col = col0 + q;
+      if (kMinMax) {
+        ca[q] = make_float4(stash[F_MNX * 32 + col], stash[F_MNY * 32 + col], stash[F_MNZ * 32 + col], 0.f);
+        cb[q] = make_float4(stash[F_MXX * 32 + col], stash[F_MXY * 32 + col], stash[F_MXZ * 32 + col], 0.f);
+        alive |= 1u << q;  // (lanes past the end carry an inverted box: never inside)
+      } else {
+        ca[q] = pre[col * kPreStride + 0];
+        cb[q] = pre[col * kPreStride + 1];
+        const float4 cz = pre[col * kPreStride + 2];
+        const float4 h = pre[col * kPreStride + 3];
+        if (q == 0) { ax_z = cz.x; ay_z = cz.y; az_z = cz.z; }
+        if (h.x >= 0.f) {  // a live pose (lanes past the end carry half extents of -1)
+          alive |= 1u << q;
+          hx = fmaxf(hx, h.x);
+          hy = fmaxf(hy, h.y);
+          const float d = ((fabsf(ax_z - cz.x) + fabsf(ay_z - cz.y)) + fabsf(az_z - cz.z)) * g.cmax;
+          const float s_q = h.z + d;
+          lo = fminf(lo, -cz.w - s_q);
+          hi = fmaxf(hi, -cz.w + s_q);
+        }
+      }
+    }
+    if (!kMinMax && alive) {
+      zc = 0.5f * (lo + hi);
+      zr = 0.5f * (hi - lo) + (4e-6f + 4e-6f * g.cmax);
     }
   }
 
   unsigned hit = 0u;     // per-lane, exact hits
-  unsigned alive = (1u << kGroup) - 1u; // poses still worth testing: those below the lowest pose known to collide (warp-uniform)
+#if B200LP_COUNT
+  unsigned long long c_cand = 0ull, c_rounds = 0ull, c_exact = 0ull;
+#define B200LP_COUNT_FLUSH() do { if (lane == 0) { atomicAdd(&g_counters[0], c_cand); atomicAdd(&g_counters[1], c_rounds); \
+    atomicAdd(&g_counters[2], c_exact); atomicAdd(&g_counters[3], 1ull); } } while (0)
+#else
+#define B200LP_COUNT_FLUSH() do { } while (0)
+#endif
   for (int r0 = 0; r0 < nrows; r0 += 32) {
     const int r = r0 + lane;
     uint32_t beg = 0, end = 0;
@@ -547,22 +615,30 @@ __device__ __forceinline__ unsigned sweep_points(const GridDev& g, const float* 
         const uint32_t j = j0 + lane;
         unsigned pm = 0u;
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+#if B200LP_COUNT
+        c_cand += (unsigned long long)min(32u, e - j0) * (unsigned long long)__popc(alive);  // (candidate, pose) pre-tests
+        c_rounds += 1ull;
+#endif
         if (j < e) {
           p = __ldg(g.pts + j);
+          if (kMinMax) {
 #pragma unroll
-          for (int q = 0; q < kGroup; ++q) {
-            bool in;
-            if (kMinMax) {
-              in = (p.x >= ca[q].x) & (p.x <= cb[q].x) & (p.y >= ca[q].y) & (p.y <= cb[q].y) & (p.z >= ca[q].z) & (p.z <= cb[q].z);
-            } else {
-              // conservative superset of the exact test: |v' - v| <= delta; no short-circuit, so the three
-              // compares chain through one predicate instead of branching
+            for (int q = 0; q < kGroup; ++q) {
+              const bool in = (p.x >= ca[q].x) & (p.x <= cb[q].x) & (p.y >= ca[q].y) & (p.y <= cb[q].y) & (p.z >= ca[q].z) & (p.z <= cb[q].z);
+              pm |= in ? (1u << q) : 0u;
+            }
+          } else {
+            // conservative superset of the exact test: |v' - v| <= delta; no short-circuit, so the
+            // compares chain through predicates instead of branching
+            const float tz = __fmaf_rn(p.x, ax_z, __fmaf_rn(p.y, ay_z, __fmaf_rn(p.z, az_z, -zc)));
+            const bool inz = fabsf(tz) <= zr;
+#pragma unroll
+            for (int q = 0; q < kGroup; ++q) {
               const float vx = __fmaf_rn(p.x, ca[q].x, __fmaf_rn(p.y, ca[q].y, __fmaf_rn(p.z, ca[q].z, ca[q].w)));
               const float vy = __fmaf_rn(p.x, cb[q].x, __fmaf_rn(p.y, cb[q].y, __fmaf_rn(p.z, cb[q].z, cb[q].w)));
-              const float vz = __fmaf_rn(p.x, cc[q].x, __fmaf_rn(p.y, cc[q].y, __fmaf_rn(p.z, cc[q].z, cc[q].w)));
-              in = (fabsf(vx) <= ch[q].x) & (fabsf(vy) <= ch[q].y) & (fabsf(vz) <= ch[q].z);
+              const bool in = inz & (fabsf(vx) <= hx) & (fabsf(vy) <= hy);
+              pm |= in ? (1u << q) : 0u;
             }
-            pm |= in ? (1u << q) : 0u;
           }
           pm &= alive;
         }
@@ -575,13 +651,17 @@ __device__ __forceinline__ unsigned sweep_points(const GridDev& g, const float* 
               if (in && exact_in_radius(stash, col, p.x, p.y, p.z)) hit |= 1u << q;
             }
           }
+#if B200LP_COUNT
+          c_exact += (unsigned long long)__popc(__ballot_sync(kFull, pm != 0u));
+#endif
           const unsigned wh = __reduce_or_sync(kFull, hit);
-          if (wh & 1u) return wh;  // the lowest pose of the group collides: nothing can precede it
-          if (wh) alive = (wh & (0u - wh)) - 1u;
+          if (wh & 1u) { B200LP_COUNT_FLUSH(); return wh; }  // the lowest pose of the group collides: nothing can precede it
+          if (wh) alive &= (wh & (0u - wh)) - 1u;
         }
       }
     }
   }
+  B200LP_COUNT_FLUSH();
   return __reduce_or_sync(kFull, hit);
 }
 

@@ -10,6 +10,17 @@
 
 namespace lp {
 
+__device__ __forceinline__ bool better(unsigned long long ca, int ia, unsigned long long cb, int ib) {
+  // getBestTrajectory: `cost <= minimum_cost` while scanning in id order => min cost, ties -> largest id
+  return ca < cb || (ca == cb && ia > ib);
+}
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // =============================================================================================
 // grid build
 // =============================================================================================
@@ -375,24 +386,16 @@ struct alignas(16) PrepAgg {  // 32 bytes: read back with two 16-byte volatile l
 };
 static_assert(sizeof(PrepAgg) == 32, "PrepAgg layout");
 
-// prep_kernel geometry: a CTA of kPrepThreads threads owns one chunk of kPrepSamples velocity samples. The sample checks,
-// the ordering of the trajectory list and the three float recurrences of a rollout (heading, x, y) are one-thread-per-
-// trajectory work; everything between the recurrences (sinf/cosf of every heading, the per-step increments, the pose
-// rows) is one-item-per-pose work that the whole CTA shares.
-constexpr int kPrepSamples = 128;
-constexpr int kPrepThreads = 512;
+#ifndef B200LP_PREP_THREADS
+#define B200LP_PREP_THREADS 128
+#endif
+constexpr int kPrepThreads = B200LP_PREP_THREADS;  // samples per chunk: 16.5 k samples (C2) make 129 CTAs, one per SM — the
+                                                    // forward simulation is bound by the XU / FP64 pipes of the SMs it runs on
 constexpr int kPrepWarps = kPrepThreads / 32;
-constexpr int kPrepBlock = 32;               // steps per pass of the rollout phases
-constexpr int kPrepPitch = kPrepSamples + 1; // row pitch of the [step][trajectory] arrays: conflict-free both ways
+constexpr int kPrepSamples = kPrepThreads;      // one velocity sample per thread
+constexpr size_t kPrepSmemBytes = 0;            // (no dynamic shared memory)
 constexpr long long kSpinLimit = 4000000000ll;  // ~2 s of SM clocks: a look-back that waits this long reports an error
-// dynamic shared memory: the three velocity axes while the samples are checked, the rollout buffers afterwards
-struct PrepRoll {
-  float th[kPrepSamples][kPrepBlock + 1];  // heading before step j of the pass (entry kPrepBlock: after the last one)
-  double e[2][kPrepBlock][kPrepPitch];     // per-step increments (x, y); overwritten in place by the positions (float)
-};
-constexpr size_t kPrepAxesBytes = 3 * (size_t)kMaxAxis * sizeof(float);
-constexpr size_t kPrepSmemBytes = sizeof(PrepRoll) > kPrepAxesBytes ? sizeof(PrepRoll) : kPrepAxesBytes;
-// serial per-CTA jobs (three velocity axes, two pose matrices) are spread over different warps
+// serial per-CTA jobs (three velocity axes, two pose matrices) are spread over different warps where possible
 __device__ __forceinline__ bool prep_job(int job, int tid) { return tid == (job % kPrepWarps) * 32 + job / kPrepWarps; }
 
 #ifdef B200LP_PREP_TRACE  // tools only: phase timestamps of thread 0 of the first / last chunk, printed by the kernel
@@ -402,7 +405,8 @@ __device__ __forceinline__ bool prep_job(int job, int tid) { return tid == (job 
 #endif
 // grid = (n_chunks, robots). Chunk ids are handed out by a per-robot ticket, so a CTA only ever waits for
 // chunks that are already running; every CTA publishes its aggregate BEFORE it looks back.
-__global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const RobotIn* __restrict__ robots, int t_cap,
+__global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const RobotIn* __restrict__ robots, RobotIn q0,
+                                                             int by_value, unsigned long long* __restrict__ t_start, int t_cap,
                                                              int shard_rank, int shard_count, ShardCuts cuts, unsigned epoch,
                                                              unsigned* __restrict__ tickets, PrepAgg* aggs,
                                                              float4* __restrict__ rec_vel, int* __restrict__ rec_steps,
@@ -413,28 +417,18 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
                                                              long long* __restrict__ rec_pose_off,
                                                              float4* __restrict__ pose_rows, long long pose_stride,
                                                              double2* __restrict__ rec_pp, int want_pp) {
-  extern __shared__ __align__(16) unsigned char prep_smem[];
-  float* s_x = reinterpret_cast<float*>(prep_smem);  // [kMaxAxis] each, dead once the samples are checked
-  float* s_y = s_x + kMaxAxis;
-  float* s_th = s_y + kMaxAxis;
-  PrepRoll& RB = *reinterpret_cast<PrepRoll*>(prep_smem);
+  __shared__ float s_x[kMaxAxis], s_y[kMaxAxis], s_th[kMaxAxis];
   __shared__ double s_R0[9], s_t0[3], s_gL[9], s_gt[3];
-  __shared__ unsigned long long s_wposes[kPrepWarps];
+  __shared__ unsigned long long s_wposes[kPrepThreads / 32];
   __shared__ int s_n[3];
-  __shared__ int s_wkeep[kPrepWarps], s_wvalid[kPrepWarps];
+  __shared__ int s_wkeep[kPrepThreads / 32], s_wvalid[kPrepThreads / 32];
   __shared__ int s_chunk;
   __shared__ int s_red[6];
   __shared__ unsigned long long s_poses;
-  // per-trajectory parameters of the rollout phases
-  __shared__ float s_v0[kPrepSamples], s_v1[kPrepSamples];
-  __shared__ double s_wdt[kPrepSamples], s_dt[kPrepSamples];
-  __shared__ int s_steps[kPrepSamples];  // 0: nothing to roll out
-  __shared__ long long s_row[kPrepSamples];
-  __shared__ float s_last[3][kPrepSamples];  // x, y, th after the last step (pure pursuit)
-  __shared__ int s_maxsteps;
   const int robot = blockIdx.y;
   const int n_chunks = gridDim.x;
-  const RobotIn q = robots[robot];
+  // single-robot launches carry their query as a kernel argument: no host -> device copy in front of the cycle
+  const RobotIn q = by_value ? q0 : robots[robot];
   const b200lp_limits& L = C.lim;
   const b200lp_params& P = C.par;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -448,10 +442,10 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
     s_n[0] = s_n[1] = s_n[2] = 0;
     s_red[0] = s_red[1] = s_red[2] = s_red[3] = s_red[4] = s_red[5] = 0;
     s_poses = 0ull;
-    s_maxsteps = 0;
   }
   __syncthreads();
   const int chunk = s_chunk;
+  if (chunk == 0 && robot == 0 && tid == 0) *t_start = globaltimer_ns();  // the cycle's first CTA: start of its device timeline
 
   if (prep_job(3, tid)) {
     // tf2::transformToEigen(robot_pose_) (dd_simple…cpp:355)
@@ -522,7 +516,7 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
   // ceil(max(|v| T / g, |w| T / g_a)), so equal sample counts leave the last rank with about twice the poses of the first
   // (C4 on 8 GPUs: 0.23 vs 0.34 ms). Every CTA of every rank evaluates the same closed-form estimate per linear-speed row
   // (|w| taken as uniform over the angular axis, plus a fixed per-trajectory term), prefix-sums it and cuts the rows at
-  // the shares `cuts` names (k / count by default; the host may move them with the kernel times of earlier cycles, which
+  // the shares `cuts` names (k / count by default; the host may move them with the device times of earlier cycles, which
   // every rank sees through the exchange slots); identical arithmetic on identical inputs, so all ranks agree on the cuts
   // without talking.
   long long lo = (long long)n_raw * shard_rank / shard_count;
@@ -585,8 +579,8 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
     hi = s_cut[1];
   }
 
-  // ---- this chunk's samples: one per thread of the first kPrepSamples ----
-  const int s = tid < kPrepSamples ? chunk * kPrepSamples + tid : 0x7fffffff;
+  // ---- this chunk's samples: one per thread ----
+  const int s = chunk * kPrepThreads + tid;
   bool keep = false, valid = false;
   float v0 = 0.f, v1 = 0.f, v2 = 0.f;
   int steps = 0, err = 0;
@@ -632,11 +626,11 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
     atomicOr(&s_red[2], err);
     atomicAdd(&s_poses, poses);
   }
-  __syncthreads();  // (also the last read of the velocity axes: the rollout buffers may overwrite them from here on)
+  __syncthreads();
   int offk = 0, offv = 0, totk = 0, totv = 0;
   unsigned long long offp = 0ull;
 #pragma unroll
-  for (int w = 0; w < kPrepWarps; ++w) {
+  for (int w = 0; w < kPrepThreads / 32; ++w) {
     const int a = s_wkeep[w], b = s_wvalid[w];
     if (w < warp) { offk += a; offv += b; offp += s_wposes[w]; }
     totk += a; totv += b;
@@ -659,11 +653,11 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
     const PrepAgg* a = my_aggs + c;
     // the poll must be a volatile access: an empty loop around a plain intrinsic load has no side effect the compiler
     // is obliged to keep. Every chunk polled here holds a ticket, i.e. its CTA is running; the time limit only guards
-    // against a device fault in that CTA, and turns a hang into an error the host reports.
+    // against a device fault in that CTA, and turns a hang into an error bit the host reports.
     if (*(volatile const unsigned*)&a->flag != epoch) {
-      const long long t_start = clock64();
+      const long long t_start_poll = clock64();
       while (*(volatile const unsigned*)&a->flag != epoch) {
-        if (clock64() - t_start > kSpinLimit) { perr |= 32; break; }
+        if (clock64() - t_start_poll > kSpinLimit) { perr |= 32; break; }
       }
     }
     __threadfence();
@@ -711,101 +705,67 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
       roll = in_shard && (long long)(s_poses + offp + pscan) <= pose_stride;
     }
   }
-  // ---- forward simulation (computeNewPositions, dd_simple…cpp:457-464, omni_simple…cpp:498-505): x, y, th in the
-  // robot frame after every step, in passes of kPrepBlock steps. Per pass:
-  //   1. heading recurrence th' = (float)(th + w dt), one thread per trajectory;
-  //   2. sinf / cosf of every heading and the double increments, one item per (trajectory, step) over the whole CTA;
-  //   3. position recurrences x' = (float)(x + ex), y' = (float)(y + ey), one thread per trajectory and coordinate;
-  //   4. the pose rows, one item per pose, 512-byte coalesced stores.
-  // Exactly the reference's operations in the reference's order; only the independent ones run side by side. (The
-  // version of round 1 ran a whole trajectory in one thread: 60 sinf/cosf evaluations deep, 34 us at C2.) ----
-  if (tid < kPrepSamples) {
-    s_v0[tid] = v0; s_v1[tid] = v1;
-    s_wdt[tid] = (double)v2 * dt;  // loop invariant of the heading recurrence
-    s_dt[tid] = dt;
-    s_steps[tid] = roll ? steps : 0;
-    s_row[tid] = pose_row;
-    if (roll) atomicMax(&s_maxsteps, steps);
-  }
-  __syncthreads();
-  const int max_steps = s_maxsteps;
-  const int my_steps = tid < 2 * kPrepSamples ? s_steps[tid & (kPrepSamples - 1)] : 0;
-  float th = 0.f;  // heading of trajectory `tid` (threads < kPrepSamples)
-  float pos = 0.f; // x of trajectory `tid` (threads < kPrepSamples), y of trajectory `tid - kPrepSamples` (the next kPrepSamples)
-  const bool omni = P.theory == B200LP_THEORY_OMNI_SIMPLE;
-  for (int k0 = 0; k0 < max_steps; k0 += kPrepBlock) {
-    if (tid < kPrepSamples && my_steps > k0) {
-      const double wdt = s_wdt[tid];
-      float* row = RB.th[tid];
-#pragma unroll 8
-      for (int j = 0; j < kPrepBlock; ++j) {
-        row[j] = th;
+  // ---- forward simulation of this thread's trajectory (computeNewPositions, dd_simple…cpp:457-464,
+  // omni_simple…cpp:498-505): x,y,th in the robot frame after every step, then the pure-pursuit terms
+  // of the last pose ----
+  if (roll) {
+    float x = 0.f, y = 0.f, th = 0.f;
+    const double wdt = (double)v2 * dt;  // loop invariant of th' = (float)(th + w*dt)
+    float4* out = pose_rows + pose_row;
+    // Blocks of 4 steps: the heading chain th' = (float)(th + w*dt) is the only dependency the expensive
+    // sin/cos evaluations have, so it runs ahead and the four evaluations overlap in the FP64 pipe. (A three-stage
+    // software pipeline that also overlaps the position chain with the next block's headings was measured SLOWER,
+    // 39 vs 36 us at C2: the loop is bound by the conversion (XU) and FP64 pipes of the few SMs that hold the
+    // trajectories, not by the dependency chains — tools/prep_trace.py.)
+    constexpr int kU = 4;
+    for (int k0 = 0; k0 < steps; k0 += kU) {
+      float tho[kU], thn[kU];
+      double ex[kU], ey[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        tho[u] = th;
         th = (float)((double)th + wdt);
-        if (k0 + j == my_steps - 1) s_last[2][tid] = th;
+        thn[u] = th;
       }
-      row[kPrepBlock] = th;
-    }
-    __syncthreads();
-#pragma unroll 2
-    for (int it = tid; it < kPrepSamples * kPrepBlock; it += kPrepThreads) {
-      const int j = it & (kPrepBlock - 1), t = it / kPrepBlock;
-      if (k0 + j < s_steps[t]) {
-        const float tho = RB.th[t][j];
-        const float a0 = s_v0[t];
-        const double tdt = s_dt[t];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
         float sn, cs;
-        lpm::sincosf(tho, &sn, &cs);
-        double ex, ey;
-        if (omni) {
-          const double a = 1.57079632679489661923 + (double)tho;  // M_PI_2 + pos[2]
-          const double a1 = (double)s_v1[t];
-          ex = ((double)(a0 * cs) + a1 * lpm::cos(a)) * tdt;
-          ey = ((double)(a0 * sn) + a1 * lpm::sin(a)) * tdt;
+        lpm::sincosf(tho[u], &sn, &cs);
+        if (P.theory == B200LP_THEORY_OMNI_SIMPLE) {
+          const double a = 1.57079632679489661923 + (double)tho[u];  // M_PI_2 + pos[2]
+          ex[u] = ((double)(v0 * cs) + (double)v1 * lpm::cos(a)) * dt;
+          ey[u] = ((double)(v0 * sn) + (double)v1 * lpm::sin(a)) * dt;
         } else {
-          ex = (double)(a0 * cs) * tdt;
-          ey = (double)(a0 * sn) * tdt;
+          ex[u] = (double)(v0 * cs) * dt;
+          ey[u] = (double)(v0 * sn) * dt;
         }
-        RB.e[0][j][t] = ex;
-        RB.e[1][j][t] = ey;
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        x = (float)((double)x + ex[u]);
+        y = (float)((double)y + ey[u]);
+        if (k0 + u < steps) out[k0 + u] = make_float4(x, y, thn[u], 0.f);
       }
     }
-    __syncthreads();
-    if (tid < 2 * kPrepSamples && my_steps > k0) {
-      const int c = tid / kPrepSamples, t = tid & (kPrepSamples - 1);
-      const int n_here = min(kPrepBlock, my_steps - k0);
-#pragma unroll 4
-      for (int j = 0; j < n_here; ++j) {
-        double* slot = &RB.e[c][j][t];
-        pos = (float)((double)pos + *slot);
-        *reinterpret_cast<float*>(slot) = pos;  // the position replaces the increment it consumed
-      }
-      if (k0 + n_here == my_steps) s_last[c][t] = pos;
+    PREP_T(4);  // rollout done
+    // the block loop may run past the last step: restore the state after step `steps - 1`
+    {
+      const float4 last = out[steps - 1];
+      x = last.x; y = last.y; th = last.z;
     }
-    __syncthreads();
-#pragma unroll 2
-    for (int it = tid; it < kPrepSamples * kPrepBlock; it += kPrepThreads) {
-      const int j = it & (kPrepBlock - 1), t = it / kPrepBlock;
-      if (k0 + j < s_steps[t])
-        pose_rows[s_row[t] + k0 + j] = make_float4(*reinterpret_cast<const float*>(&RB.e[0][j][t]),
-                                                   *reinterpret_cast<const float*>(&RB.e[1][j][t]), RB.th[t][j + 1], 0.f);
+    if (want_pp && q.plan_n > 0 && steps >= 2) {
+      double Lm[9], tv[3], dist, yaw;
+      pose_affine(s_R0, s_t0, x, y, th, Lm, tv);
+      pure_pursuit_terms(Lm, tv, s_gL, s_gt, &dist, &yaw);
+      rec_pp[rec] = make_double2(dist, yaw);
     }
-    __syncthreads();
-  }
-  PREP_T(4);  // rollout done
-  // the pure-pursuit terms of the last pose (quaternion round trip, 3x3 inverse, asin / atan2 / fmod): kept out of the
-  // hot kernel
-  if (roll && want_pp && q.plan_n > 0 && steps >= 2) {
-    double Lm[9], tv[3], dist, yaw;
-    pose_affine(s_R0, s_t0, s_last[0][tid], s_last[1][tid], s_last[2][tid], Lm, tv);
-    pure_pursuit_terms(Lm, tv, s_gL, s_gt, &dist, &yaw);
-    rec_pp[rec] = make_double2(dist, yaw);
   }
   PREP_T(5);  // pure-pursuit terms done
 #ifdef B200LP_PREP_TRACE
   if (tid == 0 && (chunk == 0 || chunk == n_chunks - 1) && robot == 0)
     printf("prep trace chunk %d/%d steps %d: axes %lld, precheck %lld, look-back %lld, rollout %lld, pure pursuit %lld cycles (roll=%d)\n", chunk,
            n_chunks, steps, trace_t[1] - trace_t[0], trace_t[2] - trace_t[1], trace_t[3] - trace_t[2],
-           trace_t[4] - trace_t[3], trace_t[5] - trace_t[4], (int)roll);
+           trace_t[4] ? trace_t[4] - trace_t[3] : 0ll, trace_t[4] ? trace_t[5] - trace_t[4] : 0ll, (int)roll);
 #endif
   if (chunk == n_chunks - 1 && tid == 0) {  // the last ticket: every chunk of this robot has started
     const PrepAgg* a = my_aggs + chunk;
@@ -823,19 +783,239 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
 }
 
 // =============================================================================================
+// Sample-sharded cycles (SURVEY.md §8e): the cross-GPU argmin through peer device memory.
+// Every rank owns 2 x kMaxPeers slots (double-buffered by the cycle's sequence number) that its peers can write over
+// NVLink (CUDA IPC mapping). The last CTA of plan_kernel — every other CTA has left — stores this rank's local best into
+// slot [rank] of EVERY peer (payload, system-wide fence, then the sequence word), polls its own slots until all `world` of
+// them carry this cycle's sequence number, reduces them with the reference's rule (min cost, ties -> largest id:
+// local_planner.cpp:460) and hands the GLOBAL best to the spinning host thread like a single-robot cycle does. No
+// host-launched collective, no extra launch, no stream synchronisation: the exchange costs one NVLink store round plus the
+// skew between the ranks. Double buffering is enough: a peer can only be one cycle ahead (its cycle k+1 exchange needs our
+// cycle k+1 store, which is stream-ordered after our cycle k reads).
+// Every slot also carries the device time its rank needed for the cycle (prep_kernel's first CTA -> here), so all ranks
+// end a cycle with the same W durations: the host moves the shard cuts of the next cycle with them (b200lp.cu).
+// =============================================================================================
+constexpr int kMaxPeers = 16;
+struct alignas(16) PeerSlot {  // 64 bytes
+  unsigned long long cost_bits;  // ~0 = this rank has no feasible trajectory
+  int32_t id;                    // GLOBAL trajectory id
+  uint32_t cycle_ns;             // device time of this rank's cycle up to the exchange
+  double xv, yv, thetav;         // the winner's velocities travel with it: only its owner has them
+  unsigned long long cuts_hash;  // which shard cuts this rank scored with: all ranks of a cycle must agree
+  unsigned long long seq;        // written last
+};
+static_assert(sizeof(PeerSlot) == 64, "PeerSlot layout");
+struct PeerTable {
+  PeerSlot* slots[kMaxPeers];  // base of every rank's slot array in THIS process's address space
+};
+struct PeerExchange {
+  int world, rank;             // world == 0: no exchange in this launch
+  unsigned long long seq;
+  PeerSlot* mine;
+  long long timeout_cycles;
+  unsigned long long* t_start; // prep_kernel's start-of-cycle timestamp (device word; valid in every launch)
+  unsigned long long cuts_hash;
+  PeerTable peers;
+};
+
+__device__ __forceinline__ void peer_exchange(const PeerExchange& px, int lane, const b200lp_result& r, const RobotMeta& meta0,
+                                              DirectOut* direct, unsigned long long direct_seq) {
+  const int buf = (int)(px.seq & 1ull);
+  const unsigned my_ns = (unsigned)min(globaltimer_ns() - *px.t_start, 0xffffffffull);
+  if (lane < px.world) {
+    PeerSlot* dst = px.peers.slots[lane] + buf * kMaxPeers + px.rank;
+    dst->cost_bits = (r.best_id < 0) ? ~0ull : lpm::d2u(r.best_cost);
+    dst->id = r.best_id;
+    dst->cycle_ns = my_ns;
+    dst->xv = r.xv; dst->yv = r.yv; dst->thetav = r.thetav;
+    dst->cuts_hash = px.cuts_hash;
+    __threadfence_system();
+    *(volatile unsigned long long*)&dst->seq = px.seq;
+  }
+  unsigned long long cb = ~0ull;
+  int id = -1;
+  unsigned ns = 0u;
+  double xv = 0.0, yv = 0.0, thetav = 0.0;
+  bool timed_out = false, cuts_differ = false;
+  if (lane < px.world) {
+    const volatile PeerSlot* src = px.mine + buf * kMaxPeers + lane;
+    const long long t0 = clock64();
+    while (src->seq != px.seq) {
+      if (clock64() - t0 > px.timeout_cycles) { timed_out = true; break; }
+    }
+    __threadfence_system();
+    if (!timed_out) {
+      cb = src->cost_bits; id = src->id; ns = src->cycle_ns;
+      xv = src->xv; yv = src->yv; thetav = src->thetav;
+      cuts_differ = src->cuts_hash != px.cuts_hash;
+    }
+  }
+  if (lane < kMaxPeers) direct->peer_ns[lane] = lane < px.world ? ns : 0u;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long ocb = __shfl_xor_sync(kFull, cb, o);
+    const int oid = __shfl_xor_sync(kFull, id, o);
+    const double oxv = __shfl_xor_sync(kFull, xv, o), oyv = __shfl_xor_sync(kFull, yv, o), oth = __shfl_xor_sync(kFull, thetav, o);
+    if (better(ocb, oid, cb, id)) { cb = ocb; id = oid; xv = oxv; yv = oyv; thetav = oth; }
+  }
+  const unsigned any_timeout = __ballot_sync(kFull, timed_out), any_differ = __ballot_sync(kFull, cuts_differ);
+  __syncwarp();
+  if (lane == 0) {
+    b200lp_result g = r;  // n_samples / n_traj / n_collided / n_poses stay this shard's
+    g.best_id = (cb == ~0ull) ? -1 : id;
+    g.best_cost = (cb == ~0ull) ? -1.0 : lpm::u2d(cb);
+    g.xv = (cb == ~0ull) ? 0.0 : xv;
+    g.yv = (cb == ~0ull) ? 0.0 : yv;
+    g.thetav = (cb == ~0ull) ? 0.0 : thetav;
+    RobotMeta m = meta0;
+    if (any_timeout) m.error |= 8;  // a peer did not deliver in time
+    if (any_differ) m.error |= 64;  // a peer cut the sample grid differently: the shards do not tile it
+    direct->r = g;
+    direct->m = m;
+    direct->cycle_ns = my_ns;
+    __threadfence_system();
+    *(volatile unsigned long long*)&direct->seq = direct_seq;
+  }
+}
+
+// =============================================================================================
+// One map for every rank of a peer group (replicated-map configurations: fleets, sample shards): ONE rank — the root —
+// brings the cloud from its host, packed to 12-byte rows, and pushes every upload piece into the row buffer of every
+// peer over NVLink as soon as the piece has landed in its own memory; the peers count the piece into their histogram
+// as soon as its flag is up and build their grid locally. The host link is crossed once instead of once per rank.
+// Block layout of every rank's peer allocation: [2 x kMaxPeers PeerSlot | CloudHeader | rows].
+// =============================================================================================
+constexpr int kSharePieces = 8;  // == kPackChunks of the packing upload (lp_hostpack.h)
+struct alignas(16) CloudHeader {
+  unsigned long long n;                         // points of the cloud (rows in the buffer)
+  unsigned long long n_finite;
+  float mn[4], mx[4];                           // bounds of the finite points (root's packing threads)
+  unsigned long long bound[kSharePieces + 1];   // piece c holds points [bound[c], bound[c + 1])
+  unsigned long long seq;                       // == cycle number once the fields above are visible
+  unsigned long long piece_seq[kSharePieces];   // == cycle number once piece c has landed in the rows
+  unsigned long long ack[kMaxPeers];            // (root's copy) rank r has finished reading the rows of cycle ack[r]
+};
+constexpr size_t kPeerHeaderOff = 2 * kMaxPeers * sizeof(PeerSlot);
+constexpr size_t kPeerRowsOff = 4096;
+static_assert(kPeerHeaderOff + sizeof(CloudHeader) <= kPeerRowsOff, "peer block layout");
+struct PeerBlocks {
+  char* base[kMaxPeers];  // every rank's peer allocation in THIS process's address space
+};
+__device__ __forceinline__ CloudHeader* peer_header(char* base) { return reinterpret_cast<CloudHeader*>(base + kPeerHeaderOff); }
+
+// root, before the first piece of a cycle: every peer must have finished reading the rows of the previous cycle
+__global__ void __launch_bounds__(32) share_wait_acks_kernel(const CloudHeader* mine, int world, int root, unsigned long long prev_seq,
+                                                             long long timeout_cycles, int* __restrict__ err) {
+  const int r = threadIdx.x;
+  if (r >= world || r == root || prev_seq == 0ull) return;
+  const volatile unsigned long long* a = &mine->ack[r];
+  const long long t0 = clock64();
+  while (*a < prev_seq)
+    if (clock64() - t0 > timeout_cycles) { atomicOr(err, 1); break; }
+}
+
+// root: copy bytes [b0, b1) of the rows (16-byte aligned start) into the same place of every peer's row buffer; the last
+// CTA to finish raises the piece's flag on every peer
+__global__ void __launch_bounds__(256) share_push_kernel(const char* __restrict__ rows, size_t b0, size_t b1, PeerBlocks peers, int world,
+                                                         int root, int piece, unsigned long long seq, unsigned* __restrict__ ticket) {
+  const size_t n16 = (b1 - b0) / 16;
+  const uint4* src = reinterpret_cast<const uint4*>(rows + b0);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+    const uint4 v = __ldg(src + i);
+    for (int r = 0; r < world; ++r)
+      if (r != root) reinterpret_cast<uint4*>(peers.base[r] + kPeerRowsOff + b0)[i] = v;
+  }
+  if (blockIdx.x == 0) {  // the (at most 12) bytes behind the last 16-byte word
+    const size_t t0 = b0 + n16 * 16;
+    for (size_t b = t0 + (size_t)threadIdx.x * 4; b < b1; b += 4 * blockDim.x) {
+      const uint32_t v = *reinterpret_cast<const uint32_t*>(rows + b);
+      for (int r = 0; r < world; ++r)
+        if (r != root) *reinterpret_cast<uint32_t*>(peers.base[r] + kPeerRowsOff + b) = v;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ int s_last;
+  if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence_system();
+  if ((int)threadIdx.x < world && (int)threadIdx.x != root)
+    *(volatile unsigned long long*)&peer_header(peers.base[threadIdx.x])->piece_seq[piece] = seq;
+  if (threadIdx.x == 0) *ticket = 0u;
+}
+
+// root: the cloud's size, bounds and piece boundaries for every peer (known once the packing threads are through)
+__global__ void __launch_bounds__(32) share_header_kernel(CloudHeader h, PeerBlocks peers, int world, int root) {
+  const int r = threadIdx.x;
+  if (r >= world || r == root) return;
+  CloudHeader* d = peer_header(peers.base[r]);
+  d->n = h.n;
+  d->n_finite = h.n_finite;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) { d->mn[a] = h.mn[a]; d->mx[a] = h.mx[a]; }
+#pragma unroll
+  for (int c = 0; c <= kSharePieces; ++c) d->bound[c] = h.bound[c];
+  __threadfence_system();
+  *(volatile unsigned long long*)&d->seq = h.seq;
+}
+
+// peer: wait for the root's header and hand it to the host (mapped pinned memory; the host spins on host_out->seq)
+__global__ void __launch_bounds__(32) share_wait_header_kernel(const CloudHeader* mine, unsigned long long seq, CloudHeader* host_out,
+                                                               long long timeout_cycles) {
+  if (threadIdx.x != 0) return;
+  const volatile unsigned long long* s = &mine->seq;
+  const long long t0 = clock64();
+  bool ok = true;
+  while (*s != seq)
+    if (clock64() - t0 > timeout_cycles) { ok = false; break; }
+  __threadfence_system();
+  const volatile CloudHeader* m = mine;
+  host_out->n = ok ? m->n : ~0ull;  // ~0: timed out
+  host_out->n_finite = m->n_finite;
+  for (int a = 0; a < 4; ++a) { host_out->mn[a] = m->mn[a]; host_out->mx[a] = m->mx[a]; }
+  for (int c = 0; c <= kSharePieces; ++c) host_out->bound[c] = m->bound[c];
+  __threadfence_system();
+  *(volatile unsigned long long*)&host_out->seq = seq;
+}
+
+// peer: hold the stream until piece `piece` of cycle `seq` has landed
+__global__ void __launch_bounds__(32) share_wait_piece_kernel(const CloudHeader* mine, unsigned long long seq, int piece,
+                                                              long long timeout_cycles, int* __restrict__ err) {
+  if (threadIdx.x != 0) return;
+  const volatile unsigned long long* s = &mine->piece_seq[piece];
+  const long long t0 = clock64();
+  while (*s != seq)
+    if (clock64() - t0 > timeout_cycles) { atomicOr(err, 2); break; }
+  __threadfence_system();
+}
+
+// peer, after its grid is built: the rows may be overwritten by the next cycle
+__global__ void __launch_bounds__(32) share_ack_kernel(char* root_base, int rank, unsigned long long seq) {
+  if (threadIdx.x != 0) return;
+  __threadfence_system();
+  *(volatile unsigned long long*)&peer_header(root_base)->ack[rank] = seq;
+}
+
+// =============================================================================================
 // plan: persistent warps, one trajectory per work item (robot, local trajectory index), handed out by a
 // global counter; grid = min(work, SMs x resident CTAs). Each warp rolls the trajectory out 32 poses at a
 // time, queries the grid, evaluates the critic stack and writes cost / per-critic scores / first-hit pose.
 // argmin_kernel then picks the best trajectory per robot.
 // =============================================================================================
-__device__ __forceinline__ bool better(unsigned long long ca, int ia, unsigned long long cb, int ib) {
-  // getBestTrajectory: `cost <= minimum_cost` while scanning in id order => min cost, ties -> largest id
-  return ca < cb || (ca == cb && ia > ib);
-}
 
+// Per-warp state that lives in shared memory, not in registers: the work loop of plan_kernel is register-bound (96 per
+// thread for 5 CTAs per SM), and everything here is read a few times per trajectory at most.
 struct WarpCtx {
   double R0[9], t0[3];
   float R0f[9], t0f[3];  // the same transform rounded to float: operands of the conservative pre-cull (loose_box)
+  double heading_deviation;
+  const float4* plan;    // the robot's prune plan (shared-memory copy for single-robot launches)
+  int t_begin, n_local, plan_n;
+  // running best of the trajectories this warp scored (single-robot launches): (cost bits, id), collisions
+  unsigned long long best_cb;
+  int best_id, n_coll;
+  int gbox[32 / kGroup][6];  // united cell box of each group of kGroup consecutive stash columns
 };
 
 struct Best {
@@ -874,6 +1054,8 @@ struct CtaShared {
   WarpCtx wc[kWarpsPerCta];
   float4 plan[kPlanSmem];
   unsigned short list[kWarpsPerCta][64];  // poses that survived the pre-cull and wait for the exact geometry, ascending
+  int scored[kWarpsPerCta];               // trajectories / poses each warp scored (single-robot launches)
+  long long poses_scored[kWarpsPerCta];
 };
 
 // lanes that head a group of kGroup consecutive stash columns
@@ -890,13 +1072,13 @@ __host__ __device__ constexpr unsigned group_heads() {
 #define B200LP_PRECULL 1  // 0: every pose goes through the double-precision geometry (A/B builds, tools/time_variants.py)
 #endif
 __global__ void __launch_bounds__(kThreads, B200LP_PLAN_MIN_CTAS)
-plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotMeta* meta, int n_robots,
+plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0, int by_value, RobotMeta* meta, int n_robots,
             int t_cap, int cap_local, const float4* __restrict__ rec_vel, const int* __restrict__ rec_steps,
             const long long* __restrict__ rec_pose_off, const float4* __restrict__ poses,
             const double2* __restrict__ rec_pp, const float4* __restrict__ plan_pts, double* __restrict__ out_cost,
             double* __restrict__ out_scores, int* __restrict__ out_first_hit,
             unsigned long long* __restrict__ work_counter, BlockBest* partial, unsigned* __restrict__ tickets,
-            b200lp_result* __restrict__ results, DirectOut* direct, unsigned long long direct_seq) {
+            b200lp_result* __restrict__ results, DirectOut* direct, unsigned long long direct_seq, PeerExchange px) {
   __shared__ CtaShared S;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* stash = S.stash[warp];
@@ -910,20 +1092,22 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotMeta* 
   const int nc = C.n_critics;
 
   // single-robot launches stage the prune plan in shared memory once per CTA
-  const bool plan_staged = n_robots == 1 && robots[0].plan_n <= kPlanSmem;
+  const RobotIn& first = by_value ? q0 : robots[0];
+  const int plan_staged = (n_robots == 1 && first.plan_n <= kPlanSmem) ? 1 : 0;  // (int, like fused_argmin below: see `fl`)
   if (plan_staged) {
-    const float4* gp = plan_pts + robots[0].plan_off;
-    for (int i = threadIdx.x; i < robots[0].plan_n; i += kThreads) S.plan[i] = gp[i];
+    const float4* gp = plan_pts + first.plan_off;
+    for (int i = threadIdx.x; i < first.plan_n; i += kThreads) S.plan[i] = gp[i];
   }
   __syncthreads();
 
   // Single-robot launches fold Local_Planner::getBestTrajectory into this kernel (warp -> CTA -> last CTA by ticket);
   // fleets run argmin_kernel afterwards. The (cost bits, id) order is total, so the merge tree does not matter.
-  const bool fused_argmin = n_robots == 1;
-  Best wb = {~0ull, -1, 0};
-  int cur_robot = -1, t_begin = 0, n_local = 0, plan_n = 0;
-  double heading_deviation = 0.0;
-  const float4* plan = nullptr;
+  const int fused_argmin = n_robots == 1 ? 1 : 0;
+  if (lane == 0) {
+    S.scored[warp] = 0; S.poses_scored[warp] = 0;
+    W.best_cb = ~0ull; W.best_id = -1; W.n_coll = 0;
+  }
+  int cur_robot = -1;
   // work items are fetched one ahead, so the atomic's round trip overlaps the previous trajectory
   unsigned long long pending = 0ull;
   if (lane == 0) pending = atomicAdd(work_counter, 1ull);
@@ -935,14 +1119,14 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotMeta* 
     const int local = (int)(w - (unsigned long long)robot * (unsigned long long)cap_local);
     if (robot != cur_robot) {
       cur_robot = robot;
-      const RobotIn& q = robots[robot];
-      t_begin = meta[robot].t_begin;
-      n_local = meta[robot].t_end - t_begin;
-      plan_n = q.plan_n;
-      heading_deviation = q.heading_deviation;
-      plan = plan_staged ? S.plan : plan_pts + q.plan_off;
+      const RobotIn& q = by_value ? q0 : robots[robot];
       __syncwarp();
       if (lane == 0) {
+        W.t_begin = meta[robot].t_begin;
+        W.n_local = meta[robot].t_end - W.t_begin;
+        W.plan_n = q.plan_n;
+        W.heading_deviation = q.heading_deviation;
+        W.plan = plan_staged ? S.plan : plan_pts + q.plan_off;
         // tf2::transformToEigen(robot_pose_) (dd_simple…cpp:355)
         quat_to_matrix(q.pose[3], q.pose[4], q.pose[5], q.pose[6], W.R0);
         W.t0[0] = q.pose[0]; W.t0[1] = q.pose[1]; W.t0[2] = q.pose[2];
@@ -953,20 +1137,19 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotMeta* 
       }
       __syncwarp();
     }
-    if (local >= n_local) continue;  // padding of the (robot, local) work space
+    if (local >= W.n_local) continue;  // padding of the (robot, local) work space
     // hand trajectories out from the END of the list: the sample grid is ordered by rising linear speed, so the
     // longest rollouts start first and the kernel's tail is made of short ones
-    const int id = t_begin + (n_local - 1 - local);
+    const int id = W.t_begin + (W.n_local - 1 - local);
     const size_t rec = (size_t)robot * t_cap + id;
-    const float4 vel = rec_vel[rec];
     const int n = rec_steps[rec];
     const float4* traj_poses = poses + rec_pose_off[rec];  // prep_kernel's forward simulation
 
     // ---- critic stack analysis (warp-uniform) ------------------------------------------------
     // A critic's value may be known before the rollout (collision_model.cpp:53-55, stick_path_model.cpp:53-55,
     // pure_pursuit_model.cpp:62-84, shortest_angle_model.cpp:51-69, twirling_model.cpp:51-55).
-    const double thetav = (double)vel.z;
     auto upfront = [&](const CriticDev& cr, double& v) -> bool {
+      const int plan_n = W.plan_n;
       switch (cr.kind) {
         case B200LP_CRITIC_COLLISION:
         case B200LP_CRITIC_COLLISION_MIN_MAX:
@@ -979,18 +1162,22 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotMeta* 
         case B200LP_CRITIC_PURE_PURSUIT:
           if (plan_n == 0 || n < 2) { v = -4.0; return true; }
           return false;
-        case B200LP_CRITIC_SHORTEST_ANGLE:
-          if (heading_deviation >= 0) v = (thetav >= 0) ? cr.weight : cr.weight * 2;
+        case B200LP_CRITIC_SHORTEST_ANGLE: {
+          const double thetav = (double)rec_vel[rec].z;
+          if (W.heading_deviation >= 0) v = (thetav >= 0) ? cr.weight : cr.weight * 2;
           else v = (thetav >= 0) ? cr.weight * 2 : cr.weight;
           return true;
+        }
         case B200LP_CRITIC_TWIRLING:
-          v = lpm::dabs(thetav) * cr.weight;
+          v = lpm::dabs((double)rec_vel[rec].z) * cr.weight;
           return true;
       }
       return false;
     };
-    bool need_box = false, need_mm = false, need_stick = false, need_last_nn = false, need_pp = false;
-    bool early_ok = true;      // may a collision hit end the rollout?
+    // (kept as bits of ONE general register, not as bools: long-lived predicates starve the sweep's inner loop, whose
+    // twelve compares then serialise through the one predicate that is left — measured +18 % on the whole kernel)
+    enum : unsigned { kNeedBox = 1u, kNeedMM = 2u, kNeedStick = 4u, kNeedLastNN = 8u, kNeedPP = 16u, kEarlyOk = 32u, kRejected = 64u };
+    unsigned fl = kEarlyOk;    // kEarlyOk: may a collision hit end the rollout?
     int first_coll_kind = -1;  // kind of the stack's first live collision critic: 0 box, 1 min-max
     {
       bool rollout_dep_seen = false;
@@ -1006,14 +1193,14 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotMeta* 
           case B200LP_CRITIC_COLLISION:
           case B200LP_CRITIC_COLLISION_MIN_MAX: {
             const bool mm = cr.kind == B200LP_CRITIC_COLLISION_MIN_MAX;
-            if (rollout_dep_seen) early_ok = false;
-            if (mm) need_mm = true; else need_box = true;
+            if (rollout_dep_seen) fl &= ~kEarlyOk;
+            fl |= mm ? kNeedMM : kNeedBox;
             if (first_coll_kind < 0) first_coll_kind = mm ? 1 : 0;
             break;
           }
-          case B200LP_CRITIC_STICK_PATH: need_stick = true; rollout_dep_seen = true; break;
-          case B200LP_CRITIC_TOWARD_GLOBAL_PLAN: need_last_nn = true; rollout_dep_seen = true; break;
-          case B200LP_CRITIC_PURE_PURSUIT: need_pp = true; rollout_dep_seen = true; break;
+          case B200LP_CRITIC_STICK_PATH: fl |= kNeedStick; rollout_dep_seen = true; break;
+          case B200LP_CRITIC_TOWARD_GLOBAL_PLAN: fl |= kNeedLastNN; rollout_dep_seen = true; break;
+          case B200LP_CRITIC_PURE_PURSUIT: fl |= kNeedPP; rollout_dep_seen = true; break;
           default: break;
         }
       }
@@ -1026,8 +1213,8 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotMeta* 
     // survivors are swept against their united candidate stream, lowest pose first, so the first colliding pose found is
     // the reference's. The double-precision geometry therefore runs for compacted survivors only.
     int hit_box = -1, hit_mm = -1;  // first colliding pose per collision-critic kind
-    bool rejected = false;           // the stack's first collision critic hit and ends the evaluation
-    if (need_box || need_mm) {
+    // kRejected: the stack's first collision critic hit and ends the evaluation
+    if (fl & (kNeedBox | kNeedMM)) {
       unsigned short* list = S.list[warp];
       const unsigned lt = (1u << lane) - 1u;
       int cnt = 0, base = 0;  // survivors waiting / next pose to pre-cull (warp-uniform)
@@ -1065,23 +1252,26 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotMeta* 
         CellBox cbx;
         pose_geometry(C, g, L, t, stash, pre, &cbx, lane, live, nullptr);
         group_union(cbx);
-        __syncwarp();
+        if ((lane & (kGroup - 1)) == 0) {  // the group's box goes to shared memory: six registers less across the sweeps
+          int* gb = W.gbox[lane / kGroup];
+          gb[0] = cbx.x0; gb[1] = cbx.x1; gb[2] = cbx.y0; gb[3] = cbx.y1; gb[4] = cbx.z0; gb[5] = cbx.z1;
+        }
         // groups of kGroup consecutive survivors whose united box holds points, once per collision-critic kind still undecided
         const unsigned heads = __ballot_sync(kFull, cbx.x0 <= cbx.x1) & group_heads();
+        __syncwarp();
 #pragma unroll 1
         for (int kind = 0; kind < 2; ++kind) {
-          if (kind == 0 ? !(need_box && hit_box < 0) : !(need_mm && hit_mm < 0)) continue;
+          if (kind == 0 ? !((fl & kNeedBox) && hit_box < 0) : !((fl & kNeedMM) && hit_mm < 0)) continue;
           unsigned todo = heads;
 #pragma unroll 1
           while (todo) {
             const int col0 = __ffs(todo) - 1;
             todo &= todo - 1u;
-            CellBox ub;
-            ub.x0 = __shfl_sync(kFull, cbx.x0, col0); ub.x1 = __shfl_sync(kFull, cbx.x1, col0);
-            ub.y0 = __shfl_sync(kFull, cbx.y0, col0); ub.y1 = __shfl_sync(kFull, cbx.y1, col0);
-            ub.z0 = __shfl_sync(kFull, cbx.z0, col0); ub.z1 = __shfl_sync(kFull, cbx.z1, col0);
-            const unsigned h = kind ? sweep_points<true>(g, stash, pre, col0, lane, ub)
-                                    : sweep_points<false>(g, stash, pre, col0, lane, ub);
+            const int* gb = W.gbox[col0 / kGroup];
+            const CellBox ub = {gb[0], gb[1], gb[2], gb[3], gb[4], gb[5]};
+            const SweepGrid sg = {g.pts, g.cell_start, g.nx, g.ny, g.cmax};
+            const unsigned h = kind ? sweep_points<true>(sg, stash, pre, col0, lane, ub)
+                                    : sweep_points<false>(sg, stash, pre, col0, lane, ub);
             if (h) {
               const int hp = (int)list[col0 + (__ffs(h) - 1)];
               if (kind) hit_mm = hp; else hit_box = hp;
@@ -1092,11 +1282,11 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotMeta* 
         // A hit of the FIRST collision critic of the stack ends the trajectory (the reference returns -1
         // there) when nothing that precedes it in the stack depends on the rollout. A later collision
         // critic hitting first only retires that critic: the earlier one must still run to the end.
-        if (early_ok && first_coll_kind >= 0 && (first_coll_kind ? hit_mm : hit_box) >= 0) {
-          rejected = true;
+        if ((fl & kEarlyOk) && first_coll_kind >= 0 && (first_coll_kind ? hit_mm : hit_box) >= 0) {
+          fl |= kRejected;
           break;
         }
-        if (!(need_box && hit_box < 0) && !(need_mm && hit_mm < 0)) break;  // every collision critic is decided
+        if (!((fl & kNeedBox) && hit_box < 0) && !((fl & kNeedMM) && hit_mm < 0)) break;  // every collision critic is decided
         // drop the chunk from the queue
         const int rest = cnt - m_here;  // < 32
         const unsigned short carry = lane < rest ? list[m_here + lane] : (unsigned short)0;
@@ -1112,7 +1302,7 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotMeta* 
     // ---- pass 2: path critics, only for trajectories the collision critic did not already reject ----
     double stick_sum = 0.0;
     float last_nn = 0.f;
-    if (!rejected && (need_stick || need_last_nn)) {
+    if (!(fl & kRejected) && (fl & (kNeedStick | kNeedLastNN))) {
       for (int base = 0; base < n; base += 32) {
         const int k = base + lane;
         const int n_here = min(32, n - base);
@@ -1123,10 +1313,10 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotMeta* 
           float pw[3];
 #pragma unroll
           for (int a = 0; a < 3; ++a) pw[a] = (float)((W.R0[a * 3] * (double)pz.x + W.R0[a * 3 + 1] * (double)pz.y) + W.t0[a]);
-          d2 = plan_nn_d2(plan, plan_n, pw[0], pw[1], pw[2]);
+          d2 = plan_nn_d2(W.plan, W.plan_n, pw[0], pw[1], pw[2]);
         }
         const float sq = lpm::fsqrt(d2);
-        if (need_stick) {
+        if (fl & kNeedStick) {
           // normalized_distance += sqrt(d2), in pose order, in double (stick_path_model.cpp:68)
           for (int j = 0; j < n_here; ++j) stick_sum += (double)__shfl_sync(kFull, sq, j);
         }
@@ -1134,7 +1324,7 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotMeta* 
       }
     }
     double pp_dist = 0.0, pp_yaw = 0.0;
-    if (need_pp) {
+    if (fl & kNeedPP) {
       const double2 pp = rec_pp[rec];
       pp_dist = pp.x;
       pp_yaw = pp.y;
@@ -1158,7 +1348,7 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotMeta* 
               if (hp >= 0 && first_hit < 0) first_hit = hp;
               break;
             }
-            case B200LP_CRITIC_STICK_PATH: v = stick_sum / (double)plan_n; break;
+            case B200LP_CRITIC_STICK_PATH: v = stick_sum / (double)W.plan_n; break;
             case B200LP_CRITIC_TOWARD_GLOBAL_PLAN: v = (double)last_nn * cr.weight; break;
             case B200LP_CRITIC_PURE_PURSUIT: v = cr.tw * pp_dist + cr.ow * pp_yaw; break;
             default: break;
@@ -1177,11 +1367,14 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotMeta* 
       out_cost[rec] = cost;
       out_first_hit[rec] = first_hit;
     }
-    if (fused_argmin) {
-      wb.ncoll += first_hit >= 0 ? 1 : 0;
-      wb.nscored += 1;
-      wb.nposes += n;
-      if (cost >= 0.0 && cost <= 9999999.0) wb.take(lpm::d2u(cost), id);  // local_planner.cpp:450,460
+    if (fused_argmin && lane == 0) {  // running best and counters of this warp (kept out of the registers of the work loop)
+      S.scored[warp] += 1;
+      S.poses_scored[warp] += n;
+      W.n_coll += first_hit >= 0 ? 1 : 0;
+      if (cost >= 0.0 && cost <= 9999999.0) {  // local_planner.cpp:450,460
+        const unsigned long long cbits = lpm::d2u(cost);
+        if (W.best_cb == ~0ull || better(cbits, id, W.best_cb, W.best_id)) { W.best_cb = cbits; W.best_id = id; }
+      }
     }
     __syncwarp();
   }
@@ -1190,7 +1383,14 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotMeta* 
   // ---- getBestTrajectory for the single robot of this launch --------------------------------------------------
   __shared__ BlockBest s_best[kWarpsPerCta];
   __shared__ int s_last;
-  if (lane == 0) wb.store(&s_best[warp]);
+  __shared__ b200lp_result s_result;
+  __shared__ RobotMeta s_meta;
+  if (lane == 0) {
+    Best wb = {W.best_cb, W.best_id, W.n_coll};
+    wb.nscored = S.scored[warp];
+    wb.nposes = S.poses_scored[warp];
+    wb.store(&s_best[warp]);
+  }
   __syncthreads();
   Best b = {~0ull, -1, 0};
   if (warp == 0) {
@@ -1243,93 +1443,20 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotMeta* 
     results[0] = r;
     *tickets = 0u;          // ready for the next launch
     *work_counter = 0ull;
-    if (direct) {  // hand the result to the spinning host thread
-      direct->r = r;
-      direct->m = m;
-      __threadfence_system();
-      *(volatile unsigned long long*)&direct->seq = direct_seq;
-    }
-    meta[0] = m;  // (the exchange kernel reads the error bits from device memory)
+    meta[0] = m;
+    s_result = r;
+    s_meta = m;
   }
-}
-
-// =============================================================================================
-// Sample-sharded cycles (SURVEY.md §8e): the cross-GPU argmin through peer device memory.
-// Every rank owns 2 x kMaxPeers slots (double-buffered by the cycle's sequence number) that its peers can write over
-// NVLink (CUDA IPC mapping). After plan_kernel one warp stores this rank's local best into slot [rank] of EVERY peer
-// (payload, system-wide fence, then the sequence word), polls its own slots until all `world` of them carry this
-// cycle's sequence number, reduces them with the reference's rule (min cost, ties -> largest id: local_planner.cpp:460)
-// and hands the GLOBAL best to the spinning host thread like a single-robot cycle does. No host-launched collective,
-// no stream synchronisation: the exchange costs one NVLink store round plus the skew between the ranks.
-// Double buffering is enough: a peer can only be one cycle ahead (its cycle k+1 exchange needs our cycle k+1 store, which
-// is stream-ordered after our cycle k reads).
-// =============================================================================================
-constexpr int kMaxPeers = 16;
-struct alignas(16) PeerSlot {  // 64 bytes
-  unsigned long long cost_bits;  // ~0 = this rank has no feasible trajectory
-  int32_t id;                    // GLOBAL trajectory id
-  int32_t pad;
-  double xv, yv, thetav;         // the winner's velocities travel with it: only its owner has them
-  unsigned long long pad2;
-  unsigned long long seq;        // written last
-};
-static_assert(sizeof(PeerSlot) == 64, "PeerSlot layout");
-struct PeerTable {
-  PeerSlot* slots[kMaxPeers];  // base of every rank's slot array in THIS process's address space
-};
-
-__global__ void __launch_bounds__(32) exchange_kernel(PeerTable peers, PeerSlot* mine, int rank, int world, unsigned long long seq,
-                                                      b200lp_result* __restrict__ results, const RobotMeta* __restrict__ meta,
-                                                      DirectOut* direct, unsigned long long direct_seq, long long timeout_cycles) {
-  const int lane = threadIdx.x;
-  const int buf = (int)(seq & 1ull);
-  const b200lp_result r = results[0];
-  if (lane < world) {
-    PeerSlot* dst = peers.slots[lane] + buf * kMaxPeers + rank;
-    dst->cost_bits = (r.best_id < 0) ? ~0ull : lpm::d2u(r.best_cost);
-    dst->id = r.best_id;
-    dst->pad = 0;
-    dst->xv = r.xv; dst->yv = r.yv; dst->thetav = r.thetav;
-    dst->pad2 = 0ull;
-    __threadfence_system();
-    *(volatile unsigned long long*)&dst->seq = seq;
+  if (px.world > 0) {
+    // sample-sharded cycle: the cross-GPU argmin through peer memory, by the first warp of this last CTA (see below)
+    __syncthreads();
+    if (warp == 0) peer_exchange(px, lane, s_result, s_meta, direct, direct_seq);
+    return;
   }
-  unsigned long long cb = ~0ull;
-  int id = -1;
-  double xv = 0.0, yv = 0.0, thetav = 0.0;
-  bool timed_out = false;
-  if (lane < world) {
-    const volatile PeerSlot* src = mine + buf * kMaxPeers + lane;
-    const long long t0 = clock64();
-    while (src->seq != seq) {
-      if (clock64() - t0 > timeout_cycles) { timed_out = true; break; }
-    }
-    __threadfence_system();
-    if (!timed_out) {
-      cb = src->cost_bits; id = src->id;
-      xv = src->xv; yv = src->yv; thetav = src->thetav;
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const unsigned long long ocb = __shfl_xor_sync(kFull, cb, o);
-    const int oid = __shfl_xor_sync(kFull, id, o);
-    const double oxv = __shfl_xor_sync(kFull, xv, o), oyv = __shfl_xor_sync(kFull, yv, o), oth = __shfl_xor_sync(kFull, thetav, o);
-    if (better(ocb, oid, cb, id)) { cb = ocb; id = oid; xv = oxv; yv = oyv; thetav = oth; }
-  }
-  const unsigned any_timeout = __ballot_sync(kFull, timed_out);
-  if (lane == 0) {
-    b200lp_result g = r;  // n_samples / n_traj / n_collided / n_poses stay this shard's
-    g.best_id = (cb == ~0ull) ? -1 : id;
-    g.best_cost = (cb == ~0ull) ? -1.0 : lpm::u2d(cb);
-    g.xv = (cb == ~0ull) ? 0.0 : xv;
-    g.yv = (cb == ~0ull) ? 0.0 : yv;
-    g.thetav = (cb == ~0ull) ? 0.0 : thetav;
-    results[0] = g;
-    RobotMeta m = meta[0];
-    if (any_timeout) m.error |= 8;  // a peer did not deliver in time
-    direct->r = g;
-    direct->m = m;
+  if (threadIdx.x == 0 && direct) {  // hand the result to the spinning host thread
+    direct->r = s_result;
+    direct->m = s_meta;
+    direct->cycle_ns = (unsigned)min(globaltimer_ns() - *px.t_start, 0xffffffffull);
     __threadfence_system();
     *(volatile unsigned long long*)&direct->seq = direct_seq;
   }

@@ -58,15 +58,19 @@ def allreduce_best(local_cost: float, local_id: int, device=None, group=None):
 
 
 def shard_range(n: int, rank: int, count: int):
-    """[lo, hi) of n units for shard `rank` of `count` — the same split b200lp_plan_shard applies to the sample grid
-    and the one fleet sharding applies to robots."""
+    """[lo, hi) of n units for shard `rank` of `count`: the equal-count split fleet sharding applies to robots. NOT the split
+    of a sample-sharded cycle: b200lp_plan_shard cuts the sample grid at equal shares of the estimated pose count (and the
+    exchange path moves the cuts with measured times); ask ``LocalPlanner.traj_count()`` for the trajectory-id range a
+    shard really scored."""
     return n * rank // count, n * (rank + 1) // count
 
 
-def attach_peer_exchange(planner, device=None, group=None) -> bool:
-    """Set the peer-memory argmin exchange up for ``planner`` (a LocalPlanner) in the current process group: gather every
-    rank's 64-byte CUDA IPC handle with one all-gather and attach. Returns False (and leaves the planner on the
-    all-reduce path) when the box does not allow it; the decision is agreed on by all ranks."""
+def attach_peer_exchange(planner, device=None, group=None, cloud_capacity: int = 0) -> bool:
+    """Set the peer-memory exchanges up for ``planner`` (a LocalPlanner) in the current process group: gather every
+    rank's 64-byte CUDA IPC handle with one all-gather and attach. ``cloud_capacity`` > 0 also reserves the row buffer of
+    ``set_cloud_shared`` (points). Returns False (and leaves the planner on the all-reduce / per-rank upload path) when the
+    box does not allow it; the decision is agreed on by all ranks. The attach ends with a collective, i.e. a barrier: no
+    rank starts its first exchange before every rank is attached."""
     import torch
     import torch.distributed as dist
 
@@ -74,6 +78,8 @@ def attach_peer_exchange(planner, device=None, group=None) -> bool:
     rank = dist.get_rank(group)
     ok = 1
     try:
+        if cloud_capacity:
+            planner.peer_reserve_cloud(int(cloud_capacity))
         mine = planner.peer_export()
     except Exception:
         mine, ok = bytes(64), 0
@@ -91,3 +97,13 @@ def attach_peer_exchange(planner, device=None, group=None) -> bool:
     flag = torch.tensor([ok], dtype=torch.int32, device=device)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
     return bool(int(flag.cpu()[0]))
+
+
+def resync_peer_exchange(planner, group=None) -> None:
+    """After a failed plan_shard_exchange / set_cloud_shared on ANY rank: every rank calls this; sequence numbers, slots and
+    shard cuts start over, fenced by two barriers."""
+    import torch.distributed as dist
+
+    dist.barrier(group)
+    planner.peer_resync()
+    dist.barrier(group)

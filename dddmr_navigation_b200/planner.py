@@ -191,6 +191,44 @@ class LocalPlanner:
         self._results = [r]
         return r
 
+    def peer_reserve_cloud(self, max_points: int) -> None:
+        """Size the row buffer of set_cloud_shared; before peer_export."""
+        self._ck(self.lib.b200lp_peer_reserve_cloud(self.h, int(max_points)))
+
+    def set_cloud_shared(self, root: int, cloud=None, host_ptr=None, n=0, stride=0) -> None:
+        """Collective over the attached peer group: the root passes the cloud (array, or host_ptr/n/stride), the others nothing."""
+        if cloud is not None:
+            cloud = np.ascontiguousarray(cloud, dtype=np.float32)
+            self._keep_cloud = cloud
+            host_ptr, n, stride = cloud.ctypes.data, cloud.shape[0], cloud.shape[1] * 4
+        self._ck(self.lib.b200lp_set_cloud_shared(self.h, int(root), _P(host_ptr) if host_ptr else None, int(n), int(stride)))
+
+    def peer_resync(self) -> None:
+        """After a failed plan_shard_exchange: every rank calls this between two barriers; the exchange starts over."""
+        self._ck(self.lib.b200lp_peer_resync(self.h))
+
+    def set_shard_cuts(self, shares=None) -> None:
+        """shares: rising floats from 0.0 to 1.0, one more than there are shards; None = equal shares."""
+        if shares is None:
+            self._ck(self.lib.b200lp_set_shard_cuts(self.h, None, 0))
+            return
+        arr = (C.c_float * len(shares))(*[float(v) for v in shares])
+        self._ck(self.lib.b200lp_set_shard_cuts(self.h, arr, len(shares) - 1))
+
+    def shard_cuts(self):
+        arr, n = (C.c_float * (abi.MAX_PEERS + 1))(), C.c_int()
+        self._ck(self.lib.b200lp_get_shard_cuts(self.h, arr, C.byref(n)))
+        return [arr[k] for k in range(n.value + 1)] if n.value else None
+
+    def set_adaptive_cuts(self, on: bool) -> None:
+        self._ck(self.lib.b200lp_set_adaptive_cuts(self.h, 1 if on else 0))
+
+    def last_cycle_ns(self) -> dict:
+        """Device time of the last single-robot cycle (GPU global timer) and, after plan_shard_exchange, of every rank."""
+        a, peers = C.c_uint32(), (C.c_uint32 * abi.MAX_PEERS)()
+        self._ck(self.lib.b200lp_last_cycle_ns(self.h, C.byref(a), peers))
+        return {"cycle_ns": a.value, "peer_ns": list(peers)}
+
     def plan_batch(self, queries, plans, plan_offsets):
         """queries: ctypes array of abi.Query; plans: (sum,7) float64; plan_offsets: (n+1,) int64."""
         n = len(queries)
@@ -270,6 +308,12 @@ class LocalPlanner:
         a, b, c, d = C.c_float(), C.c_float(), C.c_float(), C.c_float()
         self.lib.b200lp_last_timing(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
         return {"ms_upload": a.value, "ms_grid_build": b.value, "ms_plan_kernels": c.value, "ms_readback": d.value}
+
+    def work_counters(self, reset: bool = False) -> dict:
+        """Counting build only (LocalPlanner(..., lib_path=abi.COUNT_LIB_PATH))."""
+        v = (C.c_uint64 * 4)()
+        self._ck(self.lib.b200lp_work_counters(self.h, v, 1 if reset else 0))
+        return {"pretests": v[0], "rounds": v[1], "exact_tests": v[2], "groups": v[3]}
 
     def last_kernel_ms(self) -> dict:
         a, b, c = C.c_float(), C.c_float(), C.c_float()

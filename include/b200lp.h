@@ -54,7 +54,7 @@
 extern "C" {
 #endif
 
-#define B200LP_ABI_VERSION 5
+#define B200LP_ABI_VERSION 6
 
 /* status codes */
 #define B200LP_OK 0
@@ -222,8 +222,34 @@ int b200lp_plan_shard(b200lp_ctx* ctx, const b200lp_query* q, int rank, int coun
 #define B200LP_PEER_HANDLE_BYTES 64
 #define B200LP_MAX_PEERS 16
 int b200lp_peer_export(b200lp_ctx* ctx, uint8_t handle[B200LP_PEER_HANDLE_BYTES]);
+/* (A ctx attached for the first time may start exchanging at once. Attaching a ctx AGAIN — a new group, or the same one
+ * after a failure — clears its slots: the application then puts a barrier between the attach and the first exchange.) */
 int b200lp_peer_attach(b200lp_ctx* ctx, int rank, int world, const uint8_t* handles /* world * B200LP_PEER_HANDLE_BYTES */);
 int b200lp_plan_shard_exchange(b200lp_ctx* ctx, const b200lp_query* q, b200lp_result* out);
+/* One map for all ranks of a peer group (the replicated-map configurations: fleets and sample shards share ONE cloud,
+ * model_shared_data.h:74-81 gives every planner the same pcl_perception_). Collective: every rank of the group calls it
+ * once per new cloud. The root passes the host cloud (what b200lp_set_cloud takes); it is packed to 12-byte rows, uploaded
+ * once, and every upload piece is pushed into every peer's row buffer over NVLink by a kernel as soon as it has landed. The
+ * other ranks pass pts = NULL: they wait for the root's header (size, bounds), count the pieces into their histogram as the
+ * pieces' flags come up and build their own grid. The host link is crossed once per cloud, not once per rank.
+ * b200lp_peer_reserve_cloud(max_points) must be called on every rank BEFORE b200lp_peer_export: it sizes the row buffer
+ * that travels with the exported handle. A root that does not deliver within about two seconds fails the peers' call with
+ * B200LP_E_STATE (then: b200lp_peer_resync). */
+int b200lp_peer_reserve_cloud(b200lp_ctx* ctx, size_t max_points);
+int b200lp_set_cloud_shared(b200lp_ctx* ctx, int root, const void* pts /* root only */, size_t n, size_t stride_bytes);
+/* After a failed b200lp_plan_shard_exchange (a peer timed out, or the ranks disagreed on the cuts) EVERY rank calls this —
+ * with a barrier of the application before and after — and the exchange starts over: sequence numbers, slots and shard
+ * cuts return to their initial state. */
+int b200lp_peer_resync(b200lp_ctx* ctx);
+/* Where sample-sharded cycles cut the sample grid. The estimated work of the grid (expected pose count per linear-speed
+ * row plus a fixed term per trajectory) is cut at the shares shares[0] = 0 <= shares[1] <= ... <= shares[count] = 1; rank r
+ * scores the samples between cuts r and r + 1. Default (count = 0): equal shares. Every rank of a cycle must use the same
+ * cuts: b200lp_plan_shard_exchange checks that and, unless b200lp_set_adaptive_cuts(ctx, 0) was called, moves the cuts
+ * of the next cycle with the device times all ranks needed for this one (they travel with the exchanged results, so every
+ * rank derives the same new cuts). With b200lp_plan_shard the cuts are the caller's business. */
+int b200lp_set_shard_cuts(b200lp_ctx* ctx, const float* shares /* count + 1 */, int count /* 0: equal shares */);
+int b200lp_get_shard_cuts(const b200lp_ctx* ctx, float* shares /* B200LP_MAX_PEERS + 1 */, int* count);
+int b200lp_set_adaptive_cuts(b200lp_ctx* ctx, int on);
 
 /* Fleet cycle: n_robots independent queries on the shared cloud. Robot i's prune plan is
  * plans[plan_offsets[i] .. plan_offsets[i+1]) (7 doubles per pose). */
@@ -319,6 +345,12 @@ int b200lp_aggregate_observations(b200lp_ctx* ctx, const int32_t* sensors, int n
  * |{cloud points with float d^2 < 1.0 to the pose}| (the reference's radiusSearch candidate set). */
 int b200lp_count_radius(b200lp_ctx* ctx, int64_t* sum_n_r1, int64_t* n_poses);
 
+/* Work counters of the sweep (roofline accounting): out[0] = (candidate point, pose) pre-tests, out[1] = 32-candidate
+ * rounds, out[2] = candidates that went on to the exact test, out[3] = pose groups swept, summed over every plan call since
+ * the last reset. Only the counting build (libb200lp_count.so, compiled with -DB200LP_COUNT=1, never timed) keeps them;
+ * the product library answers B200LP_E_STATE. */
+int b200lp_work_counters(b200lp_ctx* ctx, uint64_t out[4], int reset);
+
 /* Device-timeline instrumentation, CUDA events on ctx's stream: ms_upload / ms_grid_build of the last
  * b200lp_set_cloud* (which returns once the caller's buffer is consumed, with the grid kernels still in
  * flight — asking here waits for them), ms_plan_kernels / ms_readback of the last plan call. Any pointer may be NULL. */
@@ -328,6 +360,10 @@ int b200lp_last_timing(const b200lp_ctx* ctx, float* ms_upload, float* ms_grid_b
  * forward simulation), plan_kernel (pose geometry + obstacle query + critics; the one the roofline is reported
  * for) and argmin_kernel (best trajectory per robot). */
 int b200lp_last_kernel_ms(const b200lp_ctx* ctx, float* ms_prep_kernel, float* ms_plan_kernel, float* ms_argmin_kernel);
+/* Device time of the last single-robot cycle, nanoseconds of the GPU's global timer from the first CTA of prep_kernel to
+ * the last CTA of plan_kernel (the one that writes the result into host memory); after b200lp_plan_shard_exchange
+ * peer_ns[r] (B200LP_MAX_PEERS entries, may be NULL) holds the same figure of every rank r < world. */
+int b200lp_last_cycle_ns(const b200lp_ctx* ctx, uint32_t* cycle_ns, uint32_t* peer_ns);
 /* Number of kernels this library launched on ctx's stream since creation. */
 int64_t b200lp_launch_count(const b200lp_ctx* ctx);
 /* Grid geometry of the current cloud (for tests / docs). dims = nx,ny,nz; origin xyz; cell xy,z. */

@@ -523,6 +523,90 @@ def test_peer_memory_exchange_over_nvlink_two_gpus():
     _check_peer_group(_run_peer_group(2, [0, 1]), 2)
 
 
+def _shared_cloud_clouds():
+    """The clouds of the shared-cloud cycles: different sizes (also below the packing threshold and empty), so that piece
+    boundaries, row-buffer reuse and the acknowledgements between cycles are all exercised."""
+    sc = synth.c1_ramp()
+    return sc, [sc.cloud, sc.cloud[:30_000], sc.cloud[:0], sc.cloud[50_000:180_001], sc.cloud]
+
+
+def _shared_cloud_worker(rank, world, device, q_in, q_out):
+    """One process of a peer group whose map is uploaded ONCE (by rank 0) and pushed to the others over peer memory."""
+    sc, clouds = _shared_cloud_clouds()
+    gpu = LocalPlanner(sc.config, device=device)
+    gpu.set_plan(sc.plan)
+    gpu.peer_reserve_cloud(max(len(c) for c in clouds))
+    q_out.put((rank, "handle", gpu.peer_export()))
+    gpu.peer_attach(rank, q_in.get(timeout=300))
+    out = []
+    q = make_query(sc.pose, sc.twist)
+    for c, cloud in enumerate(clouds):
+        gpu.set_cloud_shared(0, cloud if rank == 0 else None)
+        r = gpu.plan(q)  # every rank scores the whole sample set on ITS copy of the map
+        t = gpu.read_trajectories()
+        out.append((r.as_dict(), t["cost"].tobytes(), t["first_hit_pose"].tobytes(), gpu.grid_info()["n_points_kept"],
+                    gpu.last_upload()["h2d_bytes"]))
+        # sample-sharded cycle on the shared map as well: both exchanges live in the same peer block
+        x = gpu.plan_shard_exchange(q)
+        out[-1] += ((x.best_id, x.best_cost),)
+    q_out.put((rank, "results", out))
+    gpu.close()
+
+
+def _run_shared_cloud_group(world, devices):
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q_out = ctx.Queue()
+    q_ins = [ctx.Queue() for _ in range(world)]
+    procs = [ctx.Process(target=_shared_cloud_worker, args=(r, world, devices[r], q_ins[r], q_out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    handles, results = {}, {}
+    while len(handles) < world:
+        rank, kind, payload = q_out.get(timeout=300)
+        assert kind == "handle"
+        handles[rank] = payload
+    for qi in q_ins:
+        qi.put([handles[r] for r in range(world)])
+    while len(results) < world:
+        rank, kind, payload = q_out.get(timeout=600)
+        assert kind == "results"
+        results[rank] = payload
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    return results
+
+
+def _check_shared_cloud_group(results, world):
+    sc, clouds = _shared_cloud_clouds()
+    gpu, ora = _pair(sc.config)
+    for c, cloud in enumerate(clouds):
+        r_g, r_o = run_pair(gpu, ora, cloud, sc.plan, sc.pose, sc.twist)
+        t = gpu.read_trajectories()
+        for rank in range(world):
+            got = results[rank][c]
+            assert got[0] == r_o.as_dict(), (c, rank)
+            assert got[1] == t["cost"].tobytes() and got[2] == t["first_hit_pose"].tobytes(), (c, rank)
+            assert got[3] == len(cloud), (c, rank)
+            assert got[4] == (12 * len(cloud) if rank == 0 else 0), (c, rank)  # only the root crosses the host link
+            assert got[5] == (r_o.best_id, r_o.best_cost), (c, rank)
+
+
+def test_shared_cloud_two_processes_on_one_gpu():
+    """The map of a peer group is uploaded by ONE rank and pushed to the other through peer memory (here both ranks share
+    GPU 0: the same CUDA IPC mapping, flags and acknowledgements as over NVLink); every rank then plans on its own copy and
+    must get what a plain set_cloud of the same cloud gives, bit for bit."""
+    _check_shared_cloud_group(_run_shared_cloud_group(2, [0, 0]), 2)
+
+
+def test_shared_cloud_over_nvlink_two_gpus():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _check_shared_cloud_group(_run_shared_cloud_group(2, [0, 1]), 2)
+
+
 def test_first_cycle_of_a_fresh_process_is_already_right():
     """Regression: the very first launch in a process (lazy module load, cold caches, wide CTA start skew) once exposed
     a look-back poll the compiler had optimised away; later launches hid it."""

@@ -4,9 +4,9 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from dddmr_navigation_b200 import LocalPlanner, make_query, synth
-for mk in (synth.c1_ramp, synth.c2_dense):
+for mk in (synth.c2_dense,):
     sc = mk()
-    lp = LocalPlanner(sc.config, device=0, lib_path=os.path.join(ROOT, "tools", "variants", "lib_trace.so"))
+    lp = LocalPlanner(sc.config, device=0, lib_path=os.path.join(ROOT, "tools", "variants_trace", "lib_trace.so"))
     lp.set_cloud(sc.cloud); lp.set_plan(sc.plan)
     q = make_query(sc.pose, sc.twist)
     for i in range(3):
