@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""bench.py — trajectory-poses scored per second on the BASELINE.json workload.
+"""bench.py — trajectory-poses scored per second on the BASELINE.json workloads.
 
     python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--workload C2|C1|C3|C4|C5]
 
@@ -8,23 +8,31 @@ for one robot on the named synthetic workload (default C2: 128 x 129 = 16.5 k tr
 1.2 x 0.8 x 1.0 m footprint, 2 M-point single-floor lethal cloud). Metric: poses scored per second, where
 poses = sum of num_steps over the generated trajectories (exactly what the oracle counts).
 
-  value            device time of the cycle's kernels (CUDA events on the library's launching stream), cloud,
-                   grid, plan and query resident in HBM; L2 flushed between steps.
+  value            SURVEY.md §8d interval: one b200lp_plan call from "query handed in" to "result on the host" (host clock
+                   around the call: the query travels as a kernel argument, the result is written into pinned host memory by
+                   the cycle's last CTA), cloud, grid and plan resident in HBM; L2 flushed between steps. The CUDA-event time
+                   of the kernels alone is kernel_ms.cycle_events.
   e2e              the same metric through the C ABI with HOST buffers: every step uploads the PointXYZI cloud
                    from pinned host memory, rebuilds the voxel grid (the reference rebuilds its kd-tree every
-                   cycle, model_shared_data.h:78-81), uploads plan + query and reads the result back.
-  roofline         fused plan kernel: algorithmic bytes (16 B x n_r1(pose) + 64 B per pose) / its
-                   CUDA-event duration, against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
+                   cycle, model_shared_data.h:78-81), uploads plan + query and reads the result back. N > 1: the ranks
+                   share ONE map (b200lp_set_cloud_shared): rank 0 uploads it once, the peers receive the packed rows over
+                   NVLink and build their own grid.
+  roofline         fused plan kernel. `effective`/achieved = SURVEY.md §8d algorithmic bytes (16 B x n_r1(pose) + 64 B per
+                   pose) / its CUDA-event duration against the measured HBM copy bandwidth; `physical` = what the kernel
+                   really does: candidate pre-tests counted by the counting build of the same sources (one untimed cycle)
+                   x 24 FLOP / kernel time against the FP32 pipe, and ncu's dram bytes / kernel time against HBM.
   cpu_baseline     the reference's OWN theory/critic sources (oracle/_ref/liblpref.so, built from /root/reference against
-                   stand-ins for its third-party headers), single thread as upstream, one or two full cycles of the
+                   stand-ins for its third-party headers), single thread as upstream, full cycles of the
                    same workload on this box's host cores (N=1, rank 0 only); the oracle port when that .so is absent.
+  c4 / c5          the two multi-GPU configurations of BASELINE.json in the same line: C4 = 131 k trajectories of ONE robot
+                   sample-sharded over the ranks (strong scaling; argmin exchanged through peer memory inside plan_kernel,
+                   and with one NCCL all-reduce), C5 = 512 robots per GPU on the shared 8 M-point map (weak scaling, no
+                   collective). Both carry an in-run parity assert against unsharded / single-robot cycles.
 
-N > 1 (torchrun, one rank per GPU): fleet sharding, weak scaling — every rank plans for its own robot on its
-own replica of the map; no collective on the data path. value = poses of all ranks / max-over-ranks time.
---workload C5 is the batched-fleet configuration (512 robots per GPU on the 8 M-point map, weak scaling, no
-collective); --workload C4 is the sample-sharded one (131 k trajectories split over the ranks, strong scaling,
-one NCCL all-reduce of 16*W bytes per cycle, step time = host-observed kernels + exchange).
---impl reference times the reference's own sources (same .so) on a thinned velocity sampling of the workload (rank 0 only).
+N > 1 (torchrun, one rank per GPU): the headline stays C2 — every rank plans for its own robot on the shared map; no
+collective on the data path. value = poses of all ranks / max-over-ranks time.
+--workload C5 / C4 make that configuration the headline of the line instead (tools/evidence_*.sh).
+--impl reference times the reference's own sources (same .so) on the SAME workload (rank 0 only).
 """
 from __future__ import annotations
 
@@ -56,14 +64,20 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def load_traffic(workload):
-    """dram bytes per launch of plan_kernel from the committed ncu capture, if one exists for this workload."""
+def load_traffic_entry(workload):
+    """The committed ncu figures of plan_kernel for this workload (profiles/traffic.json: dram bytes per launch, issue-slot
+    utilisation, the commit they were captured at), if a capture exists."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        return d.get(workload, {}).get("plan_kernel_dram_bytes_per_launch")
+        return d.get(workload) or None
     return None
+
+
+def load_traffic(workload):
+    e = load_traffic_entry(workload)
+    return e.get("plan_kernel_dram_bytes_per_launch") if e else None
 
 
 FLEET_ROBOTS_PER_GPU = 512  # C5: 4096 robots over 8 GPUs
@@ -236,17 +250,13 @@ def pinned_copy(arr: np.ndarray):
     return t, t.numpy()
 
 
-REF_SAMPLES = (64.0, 64.0)  # --impl reference: velocity samples per axis of the bounded sample (C2 itself is 128 x 128)
-
-
 def run_reference(args, rank, world):
     """CPU arm. With oracle/_ref/liblpref.so present (built from the reference's OWN theory / critic sources, see
-    oracle/Makefile) it times that code — single-threaded, as the reference is — on the named map and parameters with the
-    velocity sampling thinned to REF_SAMPLES so that K steps end within minutes. Otherwise it times the oracle port on all
-    host threads."""
+    oracle/Makefile) it times that code — single-threaded, as the reference is — on the SAME workload as the GPU arm (same
+    map, same parameters, the full velocity sampling; ~4.4 s per C2 cycle), kd-tree rebuilt every step like upstream.
+    Otherwise it times the oracle port on all host threads."""
     if rank != 0:
         return 0
-    import dataclasses
     from dddmr_navigation_b200 import make_query
     from oracle import lporacle as O
     name = args.workload if args.workload in ("C1", "C2", "C3") else "C3"
@@ -254,23 +264,16 @@ def run_reference(args, rank, world):
     sc, pose, twist, plan, desc = wl["sc"], wl["pose"], wl["twist"], wl["plan"], wl["desc"]
     q = make_query(pose, twist)
     if O.have_reference_sources():
-        gen = dict(sc.config.generator)
-        thinned = name != "C1"
-        if thinned:
-            gen.update(linear_x_sample=REF_SAMPLES[0], angular_z_sample=REF_SAMPLES[1])
-        cfg = dataclasses.replace(sc.config, generator=gen)
-        ref = O.ReferencePlanner(cfg)
+        ref = O.ReferencePlanner(sc.config)
         ref.set_plan(plan)
         threads, kind = 1, "reference"
 
         def step():
             ref.set_cloud(sc.cloud)  # the cloud object is new every cycle upstream; the kd-tree is rebuilt in updateData()
             return ref.plan(q)
-        sample = ((f"the reference's own C++ (oracle/_ref/liblpref.so: theories, critics, stacked models compiled from /root/reference "
-                   f"against stand-ins for Eigen/PCL/tf2/rclcpp, vendored nanoflann kd-tree), 1 thread as upstream; "
-                   + (f"velocity sampling thinned from the workload's to {int(REF_SAMPLES[0])} x {int(REF_SAMPLES[1])} samples, "
-                      if thinned else "the full workload, ")
-                   + "kd-tree over the full cloud rebuilt every step"))
+        sample = ("the reference's own C++ (oracle/_ref/liblpref.so: theories, critics, stacked models compiled from /root/reference "
+                  "against stand-ins for Eigen/PCL/tf2/rclcpp, vendored nanoflann kd-tree), 1 thread as upstream; "
+                  "the full workload, kd-tree over the full cloud rebuilt every step")
     else:
         use_ref = O.have_ref()
         ora = O.OraclePlanner(sc.config, O.MATH_LIBM, O.INDEX_NANOFLANN if use_ref else O.INDEX_GRID)
@@ -297,11 +300,290 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-            "config": {"workload": desc, "threads": threads},
+            "config": {"workload": desc, "trajectories": int(r.n_traj), "poses_per_step": int(r.n_poses), "threads": threads},
+            "result": {"best_id": int(r.best_id), "best_cost": float(r.best_cost)},
             "cpu_baseline": base,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
     return 0
+
+
+class Env:
+    """What every section of the run shares: ranks, the device, barrier and L2 flush."""
+
+    def __init__(self, args, torch, dist, rank, local_rank, world):
+        self.args, self.torch, self.dist = args, torch, dist
+        self.rank, self.local_rank, self.world = rank, local_rank, world
+        self.device = torch.device("cuda", local_rank)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def flush_l2(self, sync_ranks=False):
+        self.flush.zero_()
+        self.torch.cuda.synchronize()
+        if sync_ranks and self.world > 1:  # steps that end in a cross-GPU exchange start together
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, *vals):
+        if self.world == 1:
+            return [float(v) for v in vals]
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(v) for v in t.cpu()]
+
+    def sum_over_ranks(self, *vals):
+        if self.world == 1:
+            return [int(v) for v in vals]
+        t = self.torch.tensor(list(vals), dtype=self.torch.int64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [int(v) for v in t.cpu()]
+
+    def gather(self, val):
+        """-> list of one float per rank (on every rank)."""
+        if self.world == 1:
+            return [float(val)]
+        t = self.torch.zeros(self.world, dtype=self.torch.float64, device="cuda")
+        t[self.rank] = float(val)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [float(v) for v in t.cpu()]
+
+
+def attach_group(env, lp, n_points):
+    """Peer-memory group of all ranks (argmin exchange, shared cloud) -> True when every rank is attached."""
+    if env.world == 1:
+        return False
+    from dddmr_navigation_b200.dist import attach_peer_exchange
+    return attach_peer_exchange(lp, device=env.device, cloud_capacity=n_points)
+
+
+def share_or_upload(env, lp, shared, cloud):
+    """One map for all ranks: rank 0 uploads, the peers receive over NVLink (or every rank uploads its own copy)."""
+    n_pts, stride = cloud.shape[0], cloud.shape[1] * 4
+    if shared:
+        if env.rank == 0:
+            lp.set_cloud_shared(0, host_ptr=cloud.ctypes.data, n=n_pts, stride=stride)
+        else:
+            lp.set_cloud_shared(0)
+    else:
+        lp.set_cloud_ptr(cloud.ctypes.data, n_pts, stride)
+
+
+def run_c4(env, steps, warmup):
+    """BASELINE config C4: ONE robot, 131 k trajectories on the 8 M-point 3-floor map, the sample grid split over the ranks
+    (strong scaling). N = 1: the unsharded cycle. N > 1: (a) the argmin exchanged through peer device memory inside
+    plan_kernel's last CTA with the shard cuts following the ranks' device times, (b) one NCCL all-reduce of 16*W bytes per
+    cycle. In-run parity: the global (best_id, best_cost) of every rank and every variant equals the unsharded cycle that
+    rank 0 runs on the same inputs, and the shards' trajectory / pose / collision counts add up to its counts."""
+    from dddmr_navigation_b200 import LocalPlanner, make_query
+    from dddmr_navigation_b200.dist import allreduce_best
+    torch, dist, rank, world = env.torch, env.dist, env.rank, env.world
+    wl = make_workload("C4", rank, world)
+    sc = wl["sc"]
+    pin_t, cloud = pinned_copy(sc.cloud)
+    q = make_query(wl["pose"], wl["twist"])
+    lp = LocalPlanner(sc.config, device=env.local_rank)
+    shared = attach_group(env, lp, cloud.shape[0])
+    share_or_upload(env, lp, shared, cloud)
+    lp.set_plan(np.ascontiguousarray(wl["plan"], np.float64))
+    out = {"workload": wl["desc"], "scaling": "strong", "steps": steps, "warmup": warmup, "unit": UNIT,
+           "map": "shared: rank 0 uploaded, peers received over NVLink" if shared else "uploaded by every rank",
+           "timing": "host clock around the call on every rank (the cycle ends with the cross-GPU exchange), ranks released by a "
+                     "barrier after the L2 flush, max over ranks of the summed step times"}
+
+    def timed(fn, adapt_warmup=0):
+        for _ in range(warmup + adapt_warmup):
+            env.flush_l2(True)
+            r = fn()
+        wall, dev = [], []
+        env.barrier()
+        for _ in range(steps):
+            env.flush_l2(True)
+            t0 = time.perf_counter()
+            r = fn()
+            wall.append(1e3 * (time.perf_counter() - t0))
+            dev.append(lp.last_timing()["ms_plan_kernels"])
+        env.barrier()
+        (t,) = env.max_over_ranks(sum(wall) / 1e3)
+        return r, t, wall, dev
+
+    # the unsharded cycle: the N = 1 figure, and the parity anchor of the sharded variants (rank 0's is the one compared)
+    ru, t_u, wall_u, dev_u = timed(lambda: lp.plan(q))
+    whole = {"best_id": int(ru.best_id), "best_cost": float(ru.best_cost), "n_traj": int(ru.n_traj), "n_poses": int(ru.n_poses),
+             "n_collided": int(ru.n_collided)}
+    out["unsharded"] = {"ms_per_step": statistics.mean(wall_u), "kernel_ms": statistics.mean(dev_u), **whole,
+                        "value": whole["n_poses"] / (statistics.mean(wall_u) * 1e-3)}
+    if world == 1:
+        out.update(value=whole["n_poses"] * steps / t_u, ms_per_step=1e3 * t_u / steps, n_gpus=1, poses_per_step=whole["n_poses"],
+                   trajectories=whole["n_traj"], parity={"checked": "nothing to compare at N = 1 (the unsharded cycle IS the run)"})
+        lp.close()
+        return out
+    ref = torch.tensor([whole["best_id"], whole["n_traj"], whole["n_poses"], whole["n_collided"]], dtype=torch.int64, device="cuda")
+    refc = torch.tensor([whole["best_cost"]], dtype=torch.float64, device="cuda")
+    dist.broadcast(ref, 0)
+    dist.broadcast(refc, 0)
+    ref_id, ref_traj, ref_poses, ref_coll = (int(v) for v in ref.cpu())
+    ref_cost = float(refc.cpu()[0])
+
+    def check(r, what):
+        n_traj, n_poses, n_coll = env.sum_over_ranks(r.n_traj, r.n_poses, r.n_collided)
+        ok = (int(r.best_id) == ref_id and float(r.best_cost) == ref_cost and n_traj == ref_traj and n_poses == ref_poses
+              and n_coll == ref_coll)
+        (bad,) = env.sum_over_ranks(0 if ok else 1)
+        assert bad == 0, (f"C4 {what}: rank {rank} got best ({r.best_id}, {r.best_cost!r}), shards sum to {n_traj} trajectories / "
+                          f"{n_poses} poses / {n_coll} collided; unsharded on rank 0: ({ref_id}, {ref_cost!r}), {ref_traj} / {ref_poses} / {ref_coll}")
+        return {"best_id_equals_unsharded_on_every_rank": True, "best_cost_bits_equal": True,
+                "shard_counts_sum_to_unsharded": True, "ranks_checked": world}
+
+    variants = {}
+    if shared:
+        lp.set_adaptive_cuts(True)
+        r, t, wall, dev = timed(lambda: lp.plan_shard_exchange(q), adapt_warmup=12)  # the cuts settle within a dozen cycles
+        ns = lp.last_cycle_ns()["peer_ns"][:world]
+        variants["peer_memory"] = {
+            "what": "argmin exchanged through peer device memory over NVLink by plan_kernel's last CTA; shard cuts follow the "
+                    "ranks' device times of the previous cycle",
+            "value": ref_poses * steps / t, "ms_per_step": 1e3 * t / steps, "p50_ms_rank0": statistics.median(wall),
+            "kernel_ms_this_rank": statistics.mean(dev),
+            "rank_device_ms_last_cycle": [v / 1e6 for v in ns], "rank_skew_ms": (max(ns) - min(ns)) / 1e6,
+            "shard_cuts": lp.shard_cuts(), "parity": check(r, "peer exchange")}
+    # (b) NCCL: the cuts are the ones the peer variant settled on (identical on every rank), or equal pose shares
+
+    def nccl_cycle():
+        r = lp.plan_shard(q, rank, world)
+        cost, bid = allreduce_best(r.best_cost, r.best_id, device=env.device)
+        r.best_cost, r.best_id = cost, bid
+        return r
+    r, t, wall, dev = timed(nccl_cycle)
+    kms = env.gather(statistics.mean(dev))
+    variants["nccl_allreduce"] = {
+        "what": "b200lp_plan_shard + ONE all-reduce(SUM) of a zero-initialised 2*W int64 vector (an exact 16 B/rank all-gather), "
+                "reference rule applied locally; cuts as left by the peer variant" if shared else
+                "b200lp_plan_shard + ONE all-reduce(SUM) of a zero-initialised 2*W int64 vector; equal estimated-pose shares",
+        "value": ref_poses * steps / t, "ms_per_step": 1e3 * t / steps, "p50_ms_rank0": statistics.median(wall),
+        "rank_kernel_ms": kms, "rank_skew_ms": max(kms) - min(kms), "parity": check(r, "NCCL all-reduce")}
+    best = min(variants.values(), key=lambda v: v["ms_per_step"])
+    out.update(value=best["value"], ms_per_step=best["ms_per_step"], n_gpus=world, poses_per_step=ref_poses, trajectories=ref_traj,
+               variants=variants, speedup_vs_unsharded_same_run=out["unsharded"]["ms_per_step"] / best["ms_per_step"])
+    lp.close()
+    return out
+
+
+def run_c5(env, steps, warmup):
+    """BASELINE config C5: 512 robots per GPU (4096 on 8) on the shared 8 M-point map, one plan_batch per step, no collective
+    (weak scaling). In-run parity: a sample of robots of every rank replanned one by one with b200lp_plan must give the same
+    b200lp_result, field for field."""
+    from dddmr_navigation_b200 import LocalPlanner, abi, make_query
+    rank, world = env.rank, env.world
+    wl = make_workload("C5", rank, world)
+    sc = wl["sc"]
+    pin_t, cloud = pinned_copy(sc.cloud)
+    f_poses, f_twists, f_plans, f_offs = wl["fleet"]
+    qs = (abi.Query * len(f_poses))()
+    for i in range(len(f_poses)):
+        qs[i] = make_query(f_poses[i], f_twists[i])
+    f_plans = np.ascontiguousarray(f_plans, np.float64)
+    f_offs = np.ascontiguousarray(f_offs, np.int64)
+    lp = LocalPlanner(sc.config, device=env.local_rank)
+    shared = attach_group(env, lp, cloud.shape[0])
+    share_or_upload(env, lp, shared, cloud)
+    for _ in range(warmup):
+        env.flush_l2()
+        res = lp.plan_batch(qs, f_plans, f_offs)
+    wall, dev = [], []
+    env.barrier()
+    for _ in range(steps):
+        env.flush_l2()
+        t0 = time.perf_counter()
+        res = lp.plan_batch(qs, f_plans, f_offs)
+        wall.append(1e3 * (time.perf_counter() - t0))
+        dev.append(lp.last_timing()["ms_plan_kernels"])
+    env.barrier()
+    poses = sum(int(r.n_poses) for r in res)
+    batch = [res[i].as_dict() for i in range(len(qs))]
+    # e2e: the shared map re-sent every step as well (rank 0 uploads 8 M PointXYZI points, peers receive over NVLink)
+    e2e_steps = max(2, min(5, steps))
+    for _ in range(2):
+        share_or_upload(env, lp, shared, cloud)
+        lp.plan_batch(qs, f_plans, f_offs)
+    e2e = []
+    env.barrier()
+    for _ in range(e2e_steps):
+        env.flush_l2()
+        t0 = time.perf_counter()
+        share_or_upload(env, lp, shared, cloud)
+        lp.plan_batch(qs, f_plans, f_offs)
+        e2e.append(1e3 * (time.perf_counter() - t0))
+    env.barrier()
+    h2d_cloud = lp.last_upload()["h2d_bytes"]
+    # parity: robots replanned one by one
+    sample = sorted({0, len(qs) // 3, (2 * len(qs)) // 3, len(qs) - 1})
+    bad = 0
+    for i in sample:
+        lp.set_plan(f_plans[f_offs[i]:f_offs[i + 1]])
+        one = lp.plan(qs[i]).as_dict()
+        bad += 0 if one == batch[i] else 1
+        assert one == batch[i], f"C5: robot {i} of rank {rank}: plan_batch {batch[i]} != single-robot plan {one}"
+    (bad_total,) = env.sum_over_ranks(bad)
+    t_dev, t_e2e = env.max_over_ranks(sum(wall) / 1e3, sum(e2e) / 1e3)
+    (poses_total,) = env.sum_over_ranks(poses)
+    kms = env.gather(statistics.mean(dev))
+    out = {"workload": wl["desc"], "scaling": "weak", "n_gpus": world, "steps": steps, "warmup": warmup, "unit": UNIT,
+           "value": poses_total * steps / t_dev, "ms_per_step": 1e3 * t_dev / steps, "poses_per_step": poses_total,
+           "robots": len(qs) * world, "robots_per_gpu": len(qs), "rank_kernel_ms": kms, "rank_skew_ms": max(kms) - min(kms),
+           "timing": "host clock around b200lp_plan_batch (queries + plans host -> device, kernels, results device -> host), map "
+                     "resident, L2 flushed between steps; max over ranks",
+           "map": "shared: rank 0 uploaded, peers received over NVLink" if shared else "uploaded by every rank",
+           "e2e": {"value": poses_total * e2e_steps / t_e2e, "unit": UNIT, "ms_per_step": 1e3 * t_e2e / e2e_steps, "steps": e2e_steps,
+                   "h2d_bytes_per_step": int(h2d_cloud + f_plans.nbytes + len(qs) * ctypes.sizeof(abi.Query)),
+                   "d2h_bytes_per_step": len(qs) * (56 + 32) + 32,
+                   "what": "map upload (+ NVLink share at N > 1) + grid build + plan_batch every step; h2d bytes are this rank's (rank 0: "
+                           "the packed cloud; peers at N > 1 receive it over NVLink)"},
+           "parity": {"robots_replanned_singly_per_rank": len(sample), "results_equal_field_for_field": bad_total == 0,
+                      "ranks_checked": world}}
+    lp.close()
+    return out
+
+
+def physical_roofline(sc, plan, q, local_rank, k_ms, n_p, peak, workload):
+    """What plan_kernel really does per launch, against the ceilings it could hit: FP32 work from the counting build of the
+    same sources (one untimed cycle), DRAM bytes from the committed ncu capture, issue-slot utilisation from the same capture."""
+    from dddmr_navigation_b200 import LocalPlanner, abi
+    phys = {}
+    lpc = LocalPlanner(sc.config, device=local_rank, lib_path=abi.COUNT_LIB_PATH)
+    try:
+        lpc.set_cloud(sc.cloud)
+        lpc.set_plan(plan)
+        lpc.work_counters(reset=True)
+        rc = lpc.plan(q)
+        wc = lpc.work_counters()
+    finally:
+        lpc.close()
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12  # SURVEY.md §8d: 74.4 TFLOP/s at 1965 MHz
+    flops = 24.0 * wc["pretests"]
+    phys["fp32"] = {"candidate_pose_pretests_per_launch": int(wc["pretests"]), "rounds_of_32_candidates": int(wc["rounds"]),
+                    "exact_retests": int(wc["exact_tests"]), "pose_groups_swept": int(wc["groups"]),
+                    "pretests_per_pose": wc["pretests"] / max(1, n_p), "flop_per_pretest": 24,
+                    "achieved_tflops": flops / (k_ms * 1e-3) / 1e12, "peak_tflops": fp32_peak,
+                    "frac": flops / (k_ms * 1e-3) / 1e12 / fp32_peak,
+                    "counting_cycle_matches": bool(int(rc.n_poses) == int(n_p)),
+                    "source": "libb200lp_count.so (same sources, -DB200LP_COUNT=1), one untimed cycle of this workload in this run"}
+    tr = load_traffic_entry(workload)
+    if tr:
+        dram = tr.get("plan_kernel_dram_bytes_per_launch")
+        phys["hbm"] = {"dram_bytes_per_launch": dram, "achieved_gbs": dram / (k_ms * 1e-3) / 1e9, "peak_gbs": peak,
+                       "frac": dram / (k_ms * 1e-3) / 1e9 / peak, "source": tr.get("source"), "commit": tr.get("commit")}
+        if "issue_active_pct" in tr:
+            phys["issue"] = {"issue_active_pct": tr["issue_active_pct"], "warps_eligible_per_cycle": tr.get("warps_eligible_per_cycle"),
+                             "frac": tr["issue_active_pct"] / 100.0, "source": tr.get("source"), "commit": tr.get("commit")}
+    fr = {k: v["frac"] for k, v in phys.items() if "frac" in v}
+    phys["bound"] = max(fr, key=fr.get) if fr else None
+    phys["frac"] = fr.get(phys["bound"]) if fr else None
+    return phys
 
 
 def main():
@@ -315,8 +597,11 @@ def main():
     ap.add_argument("--cpu-baseline-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--latency-cycles", type=int, default=1000)
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="C4 at N > 1: how the argmin crosses GPUs")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="--workload C4 at N > 1: how the argmin crosses GPUs")
     ap.add_argument("--observation-scans", type=int, default=50, help="timed lidar scans through the observation producer (0: skip)")
+    ap.add_argument("--no-multi", action="store_true", help="skip the c4 / c5 sections of the line")
+    ap.add_argument("--no-physical", action="store_true", help="skip roofline.physical (the counting-build cycle)")
+    ap.add_argument("--per-rank-upload", action="store_true", help="N > 1: every rank uploads its own copy of the map (no shared cloud)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -336,7 +621,9 @@ def main():
     torch.cuda.set_device(local_rank)
     numa = bind_to_gpu_numa_node(local_rank)  # before any pinned allocation: the upload buffers should sit next to the GPU
     if "B200LP_PACK_THREADS" not in os.environ:  # this process knows how many ranks share the host; the library does not
-        os.environ["B200LP_PACK_THREADS"] = str(choose_pack_threads(numa, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
+        # with the shared map only rank 0 packs and uploads: it may use the threads the other ranks leave idle
+        sharing = world > 1 and not args.per_rank_upload
+        os.environ["B200LP_PACK_THREADS"] = str(choose_pack_threads(numa, 1 if sharing else int(os.environ.get("LOCAL_WORLD_SIZE", world))))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL writes its version banner to stdout when the communicator comes up (NCCL_DEBUG=VERSION / WARN); stdout belongs to
@@ -353,10 +640,8 @@ def main():
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    env = Env(args, torch, dist, rank, local_rank, world)
+    barrier, flush_l2 = env.barrier, env.flush_l2
 
     wl = make_workload(args.workload, rank, world)
     sc, pose, twist, plan, desc, mode = wl["sc"], wl["pose"], wl["twist"], wl["plan"], wl["desc"], wl["mode"]
@@ -365,11 +650,6 @@ def main():
     plan = np.ascontiguousarray(plan, np.float64)
     q = make_query(pose, twist)
     lp = LocalPlanner(sc.config, device=local_rank)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-
-    def flush_l2():
-        flush.zero_()
-        torch.cuda.synchronize()
 
     if mode == "fleet":
         from dddmr_navigation_b200 import abi
@@ -380,12 +660,11 @@ def main():
         f_plans = np.ascontiguousarray(f_plans, np.float64)
         f_offs = np.ascontiguousarray(f_offs, np.int64)
 
-    # sample sharding over several GPUs: exchange the argmin through peer memory when the box allows CUDA IPC between the
-    # ranks (--exchange nccl keeps the single NCCL all-reduce of 16*W bytes)
-    peer_exchange = False
-    if mode == "shard" and world > 1 and args.exchange == "peer":
-        from dddmr_navigation_b200.dist import attach_peer_exchange
-        peer_exchange = attach_peer_exchange(lp, device=torch.device("cuda", local_rank))
+    # N > 1: one peer-memory group of all ranks — the shared map (rank 0 uploads, peers receive over NVLink) and, for sample
+    # shards, the argmin exchange inside plan_kernel (--exchange nccl keeps the single NCCL all-reduce of 16*W bytes)
+    attached = world > 1 and attach_group(env, lp, n_pts)
+    shared_map = bool(attached and not args.per_rank_upload)
+    peer_exchange = bool(attached and mode == "shard" and args.exchange == "peer")
 
     def cycle():
         """One step of the hot path on resident inputs -> (poses scored on this rank, result summary)."""
@@ -407,15 +686,16 @@ def main():
 
     def upload():
         # returns as soon as the host buffer is consumed; the grid kernels run under the host work of the plan call
-        lp.set_cloud_ptr(cloud.ctypes.data, n_pts, stride)
+        share_or_upload(env, lp, shared_map, cloud)
         if mode != "fleet":
             lp.set_plan(plan)
 
-    # ---------------- device-resident arm: kernels only ----------------
+    # ---------------- map-resident arm: one plan call, query in -> result on the host ----------------
     upload()
     grid_ms = lp.last_timing()["ms_grid_build"]  # (asking waits for the grid)
-    for _ in range(args.warmup):
-        flush_l2()
+    sync_steps = mode == "shard" and world > 1
+    for _ in range(args.warmup + (12 if peer_exchange else 0)):
+        flush_l2(sync_steps)
         poses_per_step, r = cycle()
     launches0 = lp.launch_count()
     sampler = ClockSampler(local_rank)
@@ -423,7 +703,7 @@ def main():
     barrier()
     dev_ms, plan_k_ms, prep_k_ms, argmin_k_ms, wall_ms = [], [], [], [], []
     for _ in range(args.steps):
-        flush_l2()
+        flush_l2(sync_steps)
         t0 = time.perf_counter()
         poses_per_step, r = cycle()
         wall_ms.append(1e3 * (time.perf_counter() - t0))
@@ -434,8 +714,8 @@ def main():
         argmin_k_ms.append(km["argmin_kernel"])
     barrier()
     launches = lp.launch_count() - launches0
-    # the sample-sharded cycle ends with a collective: its step time is the host-observed one (kernels + exchange)
-    t_dev = (sum(wall_ms) if mode == "shard" and world > 1 else sum(dev_ms)) / 1e3
+    t_dev = sum(wall_ms) / 1e3
+    t_events = sum(dev_ms) / 1e3
 
     # ---------------- e2e arm: host buffers through the C ABI, every step ----------------
     # warm-up of the host->device path: the first dozen pinned uploads of a process run at a fraction of the link rate
@@ -446,7 +726,7 @@ def main():
     barrier()
     e2e_ms, e2e_stage = [], {"ms_upload": 0.0, "ms_grid_build": 0.0, "ms_plan": 0.0}
     for _ in range(args.steps):
-        flush_l2()
+        flush_l2(sync_steps)
         t0 = time.perf_counter()
         upload()
         _, r2 = cycle()
@@ -468,13 +748,15 @@ def main():
 
     # ---------------- reductions over ranks (max time, summed poses) ----------------
     poses_total = poses_per_step * args.steps
-    if world > 1:
-        t = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_dev, t_e2e = float(t[0]), float(t[1])
-        p = torch.tensor([poses_total], dtype=torch.int64, device="cuda")
-        dist.all_reduce(p, op=dist.ReduceOp.SUM)
-        poses_total = int(p[0])
+    t_dev, t_e2e, t_events = env.max_over_ranks(t_dev, t_e2e, t_events)
+    (poses_total,) = env.sum_over_ranks(poses_total)
+    h2d_per_rank = [int(v) for v in env.gather(h2d)]
+    if world > 1 and mode == "single":  # every rank planned the same query on the same map: identical results, bit for bit
+        same = torch.tensor([r.best_id, r.n_traj, r.n_poses, r.n_collided], dtype=torch.int64, device="cuda")
+        lo, hi = same.clone(), same.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert bool((lo == hi).all()), "ranks disagree on the result of the same query on the shared map"
     value = poses_total / t_dev
     e2e_value = poses_total / t_e2e
 
@@ -484,13 +766,23 @@ def main():
     peak, peak_src = load_peaks()
     k_ms = sum(plan_k_ms) / len(plan_k_ms)
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    effective = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                 "algorithmic_bytes_per_launch": alg_bytes, "sum_n_r1": sum_nr1, "poses": n_p,
+                 "note": ("effective-bandwidth figure (SURVEY.md §8d): bytes the reference's radiusSearch(1.0) candidate "
+                          "sets would stream; the voxel-grid prune touches far fewer and re-reads them from L1/L2 — not a "
+                          "ceiling, see physical")}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": load_traffic(args.workload), "kernel": "plan_kernel", "kernel_ms": k_ms,
-                "kernel_share_of_step": k_ms / (sum(dev_ms) / len(dev_ms)),
-                "algorithmic_bytes_per_launch": alg_bytes, "sum_n_r1": sum_nr1, "poses": n_p, "peak_source": peak_src,
-                "note": ("effective-bandwidth figure (SURVEY.md §8d): bytes the reference's radiusSearch(1.0) candidate "
-                         "sets would stream; the voxel-grid prune touches far fewer and re-reads them from L1/L2, so the "
-                         "kernel is issue/latency-bound, not DRAM-bound — see profiles/ for dram bytes and pipe utilisation")}
+                "kernel_share_of_step": k_ms / (sum(dev_ms) / len(dev_ms)), "peak_source": peak_src,
+                "effective": effective,
+                "note": ("achieved/frac are SURVEY.md §8d's EFFECTIVE bandwidth (logical candidate bytes / kernel time) and can "
+                         "exceed 1; the kernel's binding resource is in `physical` (in-run FP32 work counters, ncu dram bytes "
+                         "and issue-slot utilisation of the commit named there)")}
+    if rank == 0 and not args.no_physical and mode == "single":
+        try:
+            roofline["physical"] = physical_roofline(sc, plan, q, local_rank, k_ms, n_p, peak, args.workload)
+        except Exception as exc:  # noqa: BLE001
+            roofline["physical"] = {"error": f"{type(exc).__name__}: {exc}"}
 
     gi = lp.grid_info()
     n_cells = gi["dims"][0] * gi["dims"][1] * gi["dims"][2]
@@ -498,9 +790,8 @@ def main():
     grid_ms_e2e = e2e_stage["ms_grid_build"] / args.steps
     roofline_grid = {"bound": "hbm", "achieved": grid_bytes / (grid_ms_e2e * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": grid_bytes / (grid_ms_e2e * 1e-3) / 1e9 / peak, "algorithmic_bytes": grid_bytes, "ms": grid_ms_e2e,
-                     "note": ("whole grid build of one set_cloud (bounds, histogram, 3-kernel scan, scatter, two summed-volume passes, "
-                              "two memsets and one host round trip for the grid dimensions); at this size it is launch/latency-bound, "
-                              "and it sits behind a PCIe upload ~8x longer")}
+                     "note": ("what the grid build adds after the last byte of the cloud has landed (scan, scatter, summed-volume "
+                              "passes; the per-piece histograms run under the upload); launch/latency-bound at this size")}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -508,32 +799,63 @@ def main():
         "vs_baseline": None,
         "dtype": "f32+f64", "data": "synthetic",
         "config": {"workload": desc, "trajectories": int(r.n_traj), "poses_per_step": poses_per_step, "cloud_points": n_pts,
-                   "cloud_stride_bytes": stride, "timing": "CUDA events on the library stream; L2 flushed (256 MiB memset) between steps",
-                   "parallelism": ({"single": "1 robot per GPU issuing the named query, map replicated (fleet sharding, no collective)",
-                                    "fleet": f"{FLEET_ROBOTS_PER_GPU} robots per GPU, map replicated (fleet sharding, no collective)",
+                   "cloud_stride_bytes": stride,
+                   "timing": ("SURVEY.md §8d interval: host clock around one b200lp_plan call (query in as a kernel argument -> "
+                              "kernels -> result written into pinned host memory), map resident; it brackets the CUDA-event time "
+                              "of the kernels (kernel_ms.cycle_events); L2 flushed (256 MiB memset) between steps; max over ranks"),
+                   "parallelism": ({"single": "1 robot per GPU issuing the named query on ONE shared map (fleet sharding, no collective on the data path)",
+                                    "fleet": f"{FLEET_ROBOTS_PER_GPU} robots per GPU on one shared map (fleet sharding, no collective)",
                                     "shard": ("sample grid split over the ranks, argmin exchanged through peer device memory over NVLink inside "
-                                              "the cycle (exchange_kernel)" if peer_exchange else
+                                              "plan_kernel" if peer_exchange else
                                               "sample grid split over the ranks, one 16*W-byte all-reduce per cycle (NCCL)")}[mode]
                                    if world > 1 or mode != "single" else "single GPU"),
+                   "map_distribution": ("rank 0 packs + uploads once, peers receive the 12 B/point rows over NVLink (b200lp_set_cloud_shared) "
+                                        "and build their own grid" if shared_map else
+                                        ("every rank uploads its own copy" if world > 1 else "single GPU")),
                    "grid": lp.grid_info()},
         "cpu_affinity": (f"{len(numa)} CPUs local to the GPU: {numa[0]}-{numa[-1]}" if isinstance(numa, list) and numa else str(numa)),
-        "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
+                   "samples": clocks.get("samples")},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": max(h2d_per_rank), "d2h_bytes_per_step": d2h,
+                "h2d_bytes_per_step_per_rank": h2d_per_rank,
                 "ms_per_step": 1e3 * t_e2e / args.steps,
                 "stages_ms_per_step": {k: v / args.steps for k, v in e2e_stage.items()},
                 "host_cloud_bytes_per_step": n_pts * stride, "host_pack_threads": lp.last_upload()["pack_threads"],
                 "what": ("set_cloud (PointXYZI cloud in pinned host memory -> packed to 12 B/point by host_pack_threads host threads -> "
-                         "upload + grid build) + set_plan + plan, host wall clock, every step")},
-        "e2e_map_resident": {"value": poses_per_step * args.steps / (sum(wall_ms) / 1e3), "unit": UNIT,
-                             "ms_per_step": sum(wall_ms) / len(wall_ms), "p50_ms": statistics.median(wall_ms),
-                             "what": "b200lp_plan only (query+plan upload, kernels, result read-back), host wall clock, rank 0"},
+                         "upload + grid build) + set_plan + plan, host wall clock, every step"
+                         + ("; N > 1: ONE upload by rank 0, the rows reach the peers over NVLink" if shared_map else ""))},
         "gpu_launches": int(launches),
         "kernel_ms": {"prep_kernel": sum(prep_k_ms) / len(prep_k_ms), "plan_kernel": k_ms,
-                      "argmin_kernel": sum(argmin_k_ms) / len(argmin_k_ms), "grid_build_total": grid_ms},
+                      "argmin_kernel": sum(argmin_k_ms) / len(argmin_k_ms), "cycle_events": 1e3 * t_events / args.steps,
+                      "grid_build_total": grid_ms,
+                      "what": "CUDA events on the library's stream; cycle_events = first kernel start -> last kernel end, max over ranks"},
+        "kernel_only": {"value": poses_total / t_events, "unit": UNIT, "ms_per_step": 1e3 * t_events / args.steps},
+        "p50_plan_call_ms": statistics.median(wall_ms),
         "roofline": roofline,
         "roofline_grid_build": roofline_grid,
         "result": {"best_id": int(r.best_id), "best_cost": float(r.best_cost), "n_collided": int(r.n_collided)},
     }
+    lp.close()
+    del lp, pin_t, cloud
+
+    # ---------------- the multi-GPU configurations of BASELINE.json, in the same line ----------------
+    if not args.no_multi and args.workload == "C2":
+        multi_steps = max(5, min(args.steps, 20))
+        for key, fn in (("c4", run_c4), ("c5", run_c5)):
+            try:
+                line[key] = fn(env, multi_steps, args.warmup)
+            except AssertionError:
+                raise  # a parity failure must fail the run
+            except Exception as exc:  # noqa: BLE001
+                if world > 1:
+                    raise  # ranks must not drift apart silently
+                line[key] = {"error": f"{type(exc).__name__}: {exc}"}
+        line["scaling_c4"] = {"kind": "strong", "n_gpus": world, "value": line["c4"].get("value"), "ms_per_step": line["c4"].get("ms_per_step"),
+                              "how": "efficiency = value(N) / (N * value(1)) across the driver's per-N lines; "
+                                     "speedup_vs_unsharded_same_run compares with the unsharded cycle of THIS run",
+                              "speedup_vs_unsharded_same_run": line["c4"].get("speedup_vs_unsharded_same_run")}
+        line["scaling_c5"] = {"kind": "weak", "n_gpus": world, "value": line["c5"].get("value"), "ms_per_step": line["c5"].get("ms_per_step"),
+                              "how": "efficiency = value(N) / (N * value(1)) across the driver's per-N lines"}
 
     # ---------------- p50 cycle latency on the reference's own CPU-runnable case (C1), rank 0 ----------------
     if rank == 0 and world == 1 and args.latency_cycles > 0:
@@ -561,120 +883,133 @@ def main():
     # ---------------- the observation producer in front of the path, rank 0 ----------------
     if rank == 0 and world == 1 and args.observation_scans > 0:
         try:  # an extra that fails must not cost the run its JSON line
-            from oracle import lporacle as O
-            from dddmr_navigation_b200 import synth
-            scan, b2s, g2b = synth.lidar_scan(n_beams=128, n_azimuth=2048)  # 262 144 points, one revolution
-            _keep_scan, hscan = pinned_copy(scan)  # (torch tensor owning the pinned pages, numpy view)
-            win, height = 10.0, 2.0
-            for _ in range(10):
-                oi = lp.sensor_observation(0, hscan, b2s, g2b, win, height)
-            wall, dev, upl = [], [], []
-            for _ in range(args.observation_scans):
-                flush_l2()
-                t0 = time.perf_counter()
-                oi = lp.sensor_observation(0, hscan, b2s, g2b, win, height)
-                wall.append(1e3 * (time.perf_counter() - t0))
-                dev.append(oi.ms_device)
-                upl.append(oi.ms_upload)
-            passes = (oi.n_launches - 2) // 4
-            n_s, n_w, n_o = int(oi.n_scan), int(oi.n_window), int(oi.n_points)
-            obs_bytes = 32 * n_s + (16 * n_s + 16 * n_w) + (passes - 1) * 32 * n_w + 16 * n_w + 16 * n_o
-            t0 = time.perf_counter()
-            for _ in range(3):
-                o_info, o_obs = O.sensor_observation(scan, b2s, g2b, win, height)
-            cpu_ms = 1e3 * (time.perf_counter() - t0) / 3
-            g_obs = lp.read_observation(0, n_o)
-            d_ms = statistics.median(dev)
-            line["observation"] = {
-                "what": ("MultiLayerSpinningLidar::cbSensor filter chain (transform, 3 pass-throughs, 0.1 m voxel centroids, transform) on one "
-                         "262 144-point scan from pinned host memory; the observation stays on the device"),
-                "scan_points": n_s, "window_points": n_w, "observation_points": n_o, "radix_passes": passes, "launches": int(oi.n_launches),
-                "ms_device_p50": d_ms, "ms_upload_p50": statistics.median(upl), "ms_host_wall_p50": statistics.median(wall), "scan_points_per_sec_e2e": n_s / (statistics.median(wall) * 1e-3),
-                "roofline": {"bound": "hbm", "achieved": obs_bytes / (d_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                             "frac": obs_bytes / (d_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": obs_bytes,
-                             "note": "upload + ~10 dependent launches on 4 MB of records: launch/latency-bound, not HBM-bound"},
-                "cpu_baseline": {"ms": cpu_ms, "kind": "port", "cores": 1,
-                                 "sample": "3 runs of the oracle restatement of the PCL filter chain on the same scan"},
-                "matches_oracle_bits": bool(np.array_equal(g_obs.view(np.uint32), o_obs.view(np.uint32))),
-            }
-            del _keep_scan
+            line["observation"] = run_observation(env, args, peak)
         except Exception as exc:  # noqa: BLE001
             line["observation"] = {"error": f"{type(exc).__name__}: {exc}"}
 
     # ---------------- CPU baseline on this box's host cores (rank 0, N=1) ----------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline and mode == "single":
         try:  # an extra that fails must not cost the run its JSON line
-            from oracle import lporacle as O
-            if O.have_reference_sources() and max(1, args.ref_stride) == 1:
-                # the reference's own sources, the FULL workload, one thread (as upstream); ~10 s per cycle at C2
-                ref = O.ReferencePlanner(sc.config)
-                ref.set_plan(plan)
-                n_cycles = max(1, min(args.cpu_baseline_steps, 2))
-                t0 = time.perf_counter()
-                cp = 0
-                for _ in range(n_cycles):
-                    ref.set_cloud(sc.cloud)
-                    ro = ref.plan(q)
-                    cp += ro.n_poses
-                dt = time.perf_counter() - t0
-                assert ro.best_id == r.best_id, (ro.best_id, r.best_id)  # the GPU picks the trajectory the reference's own code picks
-                line["cpu_baseline"] = {
-                    "value": cp / dt, "unit": UNIT, "cores": 1, "kind": "reference",
-                    "sample": (f"{n_cycles} full cycle(s) of the same workload ({ro.n_poses} poses each) through the reference's own C++ "
-                               "(oracle/_ref/liblpref.so: its theory / critic / stacked-model sources compiled from /root/reference against "
-                               "stand-ins for Eigen/PCL/tf2/rclcpp, its vendored nanoflann as kd-tree), kd-tree rebuilt every cycle, "
-                               f"1 thread (the reference path is single-threaded); host has {os.cpu_count()} cores"),
-                    "ms_per_cycle": 1e3 * dt / n_cycles,
-                    "best_id_matches_gpu": bool(ro.best_id == r.best_id), "best_cost_matches_gpu_1e-4": bool(abs(ro.best_cost - r.best_cost) <= 1e-4 * abs(ro.best_cost)),
-                }
-                # courtesy upper bound: the oracle port with the trajectories split over every host core
-                # (the reference itself is single-threaded; the kd-tree build stays serial)
-                ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-                ora = O.OraclePlanner(sc.config, O.MATH_LIBM, O.INDEX_NANOFLANN if O.have_ref() else O.INDEX_GRID)
-                ora.set_plan(plan)
-                t0 = time.perf_counter()
-                ora.set_cloud(sc.cloud)
-                rm = ora.plan(q, ncores)
-                dtm = time.perf_counter() - t0
-                line["cpu_baseline"]["all_cores"] = {
-                    "value": rm.n_poses / dtm, "unit": UNIT, "cores": ncores, "kind": "port", "ms_per_cycle": 1e3 * dtm,
-                    "sample": "1 full cycle of the same workload through the oracle port, trajectories split over std::threads, index rebuilt (serial)",
-                    "best_id_matches_gpu": bool(rm.best_id == r.best_id)}
-            else:
-                use_ref = O.have_ref()
-                ora = O.OraclePlanner(sc.config, O.MATH_LIBM, O.INDEX_NANOFLANN if use_ref else O.INDEX_GRID)
-                ora.set_cloud(sc.cloud)
-                ora.set_plan(plan)
-                stride_s = max(1, args.ref_stride)
-                ora.set_sample_stride(stride_s)
-                t0 = time.perf_counter()
-                cp = 0
-                for _ in range(args.cpu_baseline_steps):
-                    ro = ora.plan(q, 1)
-                    cp += ro.n_poses
-                dt = time.perf_counter() - t0
-                if stride_s == 1:
-                    assert ro.best_id == r.best_id, (ro.best_id, r.best_id)
-                line["cpu_baseline"] = {
-                    "value": cp / dt, "unit": UNIT, "cores": 1, "kind": "port",
-                    "sample": (f"{args.cpu_baseline_steps} full cycles of the same workload"
-                               + ("" if stride_s == 1 else f" restricted to every {stride_s}-th velocity sample")
-                               + f" ({ro.n_poses} poses each) through the oracle port, kd-tree rebuilt every cycle; "
-                               f"index={'reference-vendored nanoflann 1.5.1 (oracle/_ref)' if use_ref else 'oracle bucket grid'}, glibc libm, "
-                               f"1 thread; host has {os.cpu_count()} cores"),
-                    "ms_per_cycle": 1e3 * dt / args.cpu_baseline_steps,
-                    "stages_s_last_cycle": {"index_build": ora.timing[0], "rollout": ora.timing[1], "score": ora.timing[2]},
-                    "best_id_matches_gpu": bool(stride_s != 1 or ro.best_id == r.best_id),
-                }
+            line["cpu_baseline"] = run_cpu_baseline(args, sc, plan, q, r)
+        except AssertionError:
+            raise
         except Exception as exc:  # noqa: BLE001
             line["cpu_baseline"] = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank == 0:
         print(json.dumps(line), flush=True)
-    lp.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def run_observation(env, args, peak):
+    from oracle import lporacle as O
+    from dddmr_navigation_b200 import LocalPlanner, synth
+    lp = LocalPlanner(synth.c1_ramp(n_points=1000).config, device=env.local_rank)
+    scan, b2s, g2b = synth.lidar_scan(n_beams=128, n_azimuth=2048)  # 262 144 points, one revolution
+    _keep_scan, hscan = pinned_copy(scan)  # (torch tensor owning the pinned pages, numpy view)
+    win, height = 10.0, 2.0
+    for _ in range(10):
+        oi = lp.sensor_observation(0, hscan, b2s, g2b, win, height)
+    wall, dev, upl = [], [], []
+    for _ in range(args.observation_scans):
+        env.flush_l2()
+        t0 = time.perf_counter()
+        oi = lp.sensor_observation(0, hscan, b2s, g2b, win, height)
+        wall.append(1e3 * (time.perf_counter() - t0))
+        dev.append(oi.ms_device)
+        upl.append(oi.ms_upload)
+    passes = (oi.n_launches - 2) // 4
+    n_s, n_w, n_o = int(oi.n_scan), int(oi.n_window), int(oi.n_points)
+    obs_bytes = 32 * n_s + (16 * n_s + 16 * n_w) + (passes - 1) * 32 * n_w + 16 * n_w + 16 * n_o
+    t0 = time.perf_counter()
+    for _ in range(3):
+        o_info, o_obs = O.sensor_observation(scan, b2s, g2b, win, height)
+    cpu_ms = 1e3 * (time.perf_counter() - t0) / 3
+    g_obs = lp.read_observation(0, n_o)
+    d_ms = statistics.median(dev)
+    out = {
+        "what": ("MultiLayerSpinningLidar::cbSensor filter chain (transform, 3 pass-throughs, 0.1 m voxel centroids, transform) on one "
+                 "262 144-point scan from pinned host memory; the observation stays on the device"),
+        "scan_points": n_s, "window_points": n_w, "observation_points": n_o, "radix_passes": passes, "launches": int(oi.n_launches),
+        "ms_device_p50": d_ms, "ms_upload_p50": statistics.median(upl), "ms_host_wall_p50": statistics.median(wall),
+        "scan_points_per_sec_e2e": n_s / (statistics.median(wall) * 1e-3),
+        "roofline": {"bound": "hbm", "achieved": obs_bytes / (d_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": obs_bytes / (d_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": obs_bytes,
+                     "note": "upload + dependent launches on 4 MB of records: launch/latency-bound, not HBM-bound"},
+        "cpu_baseline": {"ms": cpu_ms, "kind": "port", "cores": 1,
+                         "sample": "3 runs of the oracle restatement of the PCL filter chain on the same scan"},
+        "matches_oracle_bits": bool(np.array_equal(g_obs.view(np.uint32), o_obs.view(np.uint32))),
+    }
+    lp.close()
+    return out
+
+
+def run_cpu_baseline(args, sc, plan, q, r):
+    from oracle import lporacle as O
+    if O.have_reference_sources() and max(1, args.ref_stride) == 1:
+        # the reference's own sources, the FULL workload, one thread (as upstream); ~4.4 s per cycle at C2
+        ref = O.ReferencePlanner(sc.config)
+        ref.set_plan(plan)
+        n_cycles = max(1, min(args.cpu_baseline_steps, 4))
+        t0 = time.perf_counter()
+        cp = 0
+        for _ in range(n_cycles):
+            ref.set_cloud(sc.cloud)
+            ro = ref.plan(q)
+            cp += ro.n_poses
+        dt = time.perf_counter() - t0
+        assert ro.best_id == r.best_id, (ro.best_id, r.best_id)  # the GPU picks the trajectory the reference's own code picks
+        out = {
+            "value": cp / dt, "unit": UNIT, "cores": 1, "kind": "reference",
+            "sample": (f"{n_cycles} full cycle(s) of the same workload ({ro.n_poses} poses each) through the reference's own C++ "
+                       "(oracle/_ref/liblpref.so: its theory / critic / stacked-model sources compiled from /root/reference against "
+                       "stand-ins for Eigen/PCL/tf2/rclcpp, its vendored nanoflann as kd-tree), kd-tree rebuilt every cycle, "
+                       f"1 thread (the reference path is single-threaded); host has {os.cpu_count()} cores"),
+            "ms_per_cycle": 1e3 * dt / n_cycles,
+            "best_id_matches_gpu": bool(ro.best_id == r.best_id),
+            "best_cost_matches_gpu_1e-4": bool(abs(ro.best_cost - r.best_cost) <= 1e-4 * abs(ro.best_cost)),
+        }
+        # courtesy upper bound: the oracle port with the trajectories split over every host core
+        # (the reference itself is single-threaded; the kd-tree build stays serial)
+        ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        ora = O.OraclePlanner(sc.config, O.MATH_LIBM, O.INDEX_NANOFLANN if O.have_ref() else O.INDEX_GRID)
+        ora.set_plan(plan)
+        t0 = time.perf_counter()
+        ora.set_cloud(sc.cloud)
+        rm = ora.plan(q, ncores)
+        dtm = time.perf_counter() - t0
+        out["all_cores"] = {
+            "value": rm.n_poses / dtm, "unit": UNIT, "cores": ncores, "kind": "port", "ms_per_cycle": 1e3 * dtm,
+            "sample": "1 full cycle of the same workload through the oracle port, trajectories split over std::threads, index rebuilt (serial)",
+            "best_id_matches_gpu": bool(rm.best_id == r.best_id)}
+        return out
+    use_ref = O.have_ref()
+    ora = O.OraclePlanner(sc.config, O.MATH_LIBM, O.INDEX_NANOFLANN if use_ref else O.INDEX_GRID)
+    ora.set_cloud(sc.cloud)
+    ora.set_plan(plan)
+    stride_s = max(1, args.ref_stride)
+    ora.set_sample_stride(stride_s)
+    t0 = time.perf_counter()
+    cp = 0
+    for _ in range(args.cpu_baseline_steps):
+        ro = ora.plan(q, 1)
+        cp += ro.n_poses
+    dt = time.perf_counter() - t0
+    if stride_s == 1:
+        assert ro.best_id == r.best_id, (ro.best_id, r.best_id)
+    return {
+        "value": cp / dt, "unit": UNIT, "cores": 1, "kind": "port",
+        "sample": (f"{args.cpu_baseline_steps} full cycles of the same workload"
+                   + ("" if stride_s == 1 else f" restricted to every {stride_s}-th velocity sample")
+                   + f" ({ro.n_poses} poses each) through the oracle port, kd-tree rebuilt every cycle; "
+                   f"index={'reference-vendored nanoflann 1.5.1 (oracle/_ref)' if use_ref else 'oracle bucket grid'}, glibc libm, "
+                   f"1 thread; host has {os.cpu_count()} cores"),
+        "ms_per_cycle": 1e3 * dt / args.cpu_baseline_steps,
+        "stages_s_last_cycle": {"index_build": ora.timing[0], "rollout": ora.timing[1], "score": ora.timing[2]},
+        "best_id_matches_gpu": bool(stride_s != 1 or ro.best_id == r.best_id),
+    }
 
 
 if __name__ == "__main__":
