@@ -169,6 +169,7 @@ SYMBOLS = {
     "b200lp_last_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
                                      C.POINTER(C.c_float)]),
     "b200lp_last_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "b200lp_last_kernel_times": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int]),
     "b200lp_launch_count": (C.c_int64, [_P]),
     "b200lp_grid_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_float),
                                    C.POINTER(C.c_int64)]),

@@ -76,7 +76,7 @@ struct PinBuf {
 struct b200lp_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t cev[3] = {nullptr, nullptr, nullptr};  // set_cloud: start, cloud arrived, grid built
   bool cloud_timing_pending = false;
   std::string err;
@@ -170,6 +170,9 @@ struct b200lp_ctx {
   DevBuf<unsigned> d_tickets;            // prep_kernel chunk tickets, one per robot (self-resetting)
   DevBuf<PrepAgg> d_aggs;                // prep_kernel look-back aggregates
   DevBuf<unsigned long long> d_work;     // plan_kernel work counter (reset by argmin_kernel)
+  DevBuf<uint32_t> d_surv;               // cull_kernel: one bit per row of d_poses — does the pose survive the float pre-cull?
+  DevBuf<int> d_order;                   // classify_kernel: the work lists of the cycle, one per cost class (kCostClasses x T entries)
+  DevBuf<unsigned> d_class_counts;       // entries per list (zeroed by prep_kernel)
   DevBuf<unsigned long long> d_tstart;   // globaltimer at the start of the cycle (prep_kernel's first CTA)
   bool plan_uploaded = false;            // d_plan7 already holds the host plan (b200lp_set_plan uploads it)
   cudaEvent_t plan_ev = nullptr;         // ... as of this event on the main stream
@@ -194,7 +197,7 @@ struct b200lp_ctx {
 
   // timing of the last call
   float ms_upload = 0.f, ms_grid = 0.f, ms_plan = 0.f, ms_readback = 0.f;
-  float ms_k_prep = 0.f, ms_k_plan = 0.f, ms_k_argmin = 0.f;
+  float ms_k_prep = 0.f, ms_k_cull = 0.f, ms_k_plan = 0.f, ms_k_argmin = 0.f;
 
   int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -515,9 +518,10 @@ void resolve_cycle_timing(b200lp_ctx* ctx) {
     ctx->ms_readback = 0.f;
     if (!ctx->cycle_timing_direct) cudaEventElapsedTime(&ctx->ms_readback, ctx->ev[2], ctx->ev[3]);
     cudaEventElapsedTime(&ctx->ms_k_prep, ctx->ev[1], ctx->ev[4]);
-    cudaEventElapsedTime(&ctx->ms_k_plan, ctx->ev[ctx->cycle_overlapped ? 6 : 4], ctx->ev[5]);
+    cudaEventElapsedTime(&ctx->ms_k_cull, ctx->ev[ctx->cycle_overlapped ? 6 : 4], ctx->ev[7]);
+    cudaEventElapsedTime(&ctx->ms_k_plan, ctx->ev[7], ctx->ev[5]);
     cudaEventElapsedTime(&ctx->ms_k_argmin, ctx->ev[5], ctx->ev[2]);
-    if (ctx->cycle_overlapped) ctx->ms_plan = ctx->ms_k_prep + ctx->ms_k_plan + ctx->ms_k_argmin;  // prep ran under the grid build
+    if (ctx->cycle_overlapped) ctx->ms_plan = ctx->ms_k_prep + ctx->ms_k_cull + ctx->ms_k_plan + ctx->ms_k_argmin;  // prep ran under the grid build
     else cudaEventElapsedTime(&ctx->ms_plan, ctx->ev[1], ctx->ev[2]);
   }
   ctx->cycle_timing_pending = false;
@@ -603,12 +607,16 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   CK(ctx->h_results.reserve(n_robots));
   CK(ctx->h_meta.reserve(n_robots));
   // the forward simulation of every scored trajectory is materialised once per cycle (16 B per pose)
-  const long long pose_stride = (long long)cap_local * (long long)max_steps_bound(ctx->C.lim, ctx->C.par);
+  // (a multiple of 256: cull_kernel's CTAs and the words of its survivor bits never straddle two robots)
+  const long long pose_stride = ((long long)cap_local * (long long)max_steps_bound(ctx->C.lim, ctx->C.par) + 255) / 256 * 256;
   if ((double)pose_stride * (double)n_robots * 16.0 > 64e9)
     return ctx->fail(B200LP_E_NOMEM, "plan: %zu robots x %d trajectories x %d poses need more than 64 GB of pose storage",
                      n_robots, cap_local, (int)max_steps_bound(ctx->C.lim, ctx->C.par));
   CK(ctx->d_poses.reserve((size_t)pose_stride * n_robots));
   CK(ctx->d_rec_pose_off.reserve(T));
+  if (T > 0x7fffffffull) return ctx->fail(B200LP_E_INVALID, "plan: %zu robots x %d trajectories exceed the work-list index range", n_robots, t_cap);
+  CK(ctx->d_surv.reserve((size_t)pose_stride * n_robots / 32 + 2));
+  CK(ctx->d_order.reserve(T * (size_t)kCostClasses));
   int want_pp = 0;
   for (int k = 0; k < ctx->C.n_critics; ++k) want_pp |= ctx->C.critics[k].kind == B200LP_CRITIC_PURE_PURSUIT;
   CK(ctx->d_rec_pp.reserve(want_pp ? T : 1));
@@ -638,6 +646,8 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
     CK(cudaMemsetAsync(ctx->d_work.p, 0, sizeof(unsigned long long), ctx->stream));
     CK(ctx->d_tstart.reserve(1));
     CK(cudaMemsetAsync(ctx->d_tstart.p, 0, sizeof(unsigned long long), ctx->stream));
+    CK(ctx->d_class_counts.reserve(kCostClasses));
+    CK(cudaMemsetAsync(ctx->d_class_counts.p, 0, kCostClasses * sizeof(unsigned), ctx->stream));
   }
   if (!ctx->plan_ctas_per_sm) {
     ctx->sm_count = sm_count_of(ctx->device);
@@ -694,12 +704,18 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   prep_kernel<<<dim3((unsigned)n_chunks, (unsigned)n_robots), kPrepThreads, kPrepSmemBytes, ps>>>(
       ctx->C, ctx->d_robots.p, q0, by_value, ctx->d_tstart.p, t_cap, rank, count, ctx->cuts, ctx->epoch, ctx->d_tickets.p,
       ctx->d_aggs.p, ctx->d_rec_vel.p, ctx->d_rec_steps.p, ctx->d_rec_dt.p, ctx->d_rec_sample.p, ctx->d_meta.p, ctx->d_plan7.p,
-      ctx->d_plan_pts.p, ctx->d_rec_pose_off.p, ctx->d_poses.p, pose_stride, ctx->d_rec_pp.p, want_pp);
+      ctx->d_plan_pts.p, ctx->d_rec_pose_off.p, ctx->d_poses.p, pose_stride, ctx->d_rec_pp.p, want_pp, ctx->d_class_counts.p);
   CK(cudaEventRecord(ctx->ev[4], ps));
   if (overlap) {
     CK(cudaStreamWaitEvent(ctx->stream, ctx->ev[4], 0));
-    CK(cudaEventRecord(ctx->ev[6], ctx->stream));  // plan_kernel's start on the main stream (after the grid build)
+    CK(cudaEventRecord(ctx->ev[6], ctx->stream));  // cull_kernel's start on the main stream (after the grid build)
   }
+  // the float pre-cull of every pose (needs the grid) and the work lists plan_kernel drains
+  cull_kernel<<<dim3((unsigned)(pose_stride / kCullThreads), (unsigned)n_robots), kCullThreads, 0, ctx->stream>>>(
+      ctx->C, ctx->grid, ctx->d_robots.p, q0, by_value, ctx->d_meta.p, ctx->d_poses.p, pose_stride, ctx->d_surv.p);
+  classify_kernel<<<dim3((unsigned)((t_cap + kCullThreads - 1) / kCullThreads), (unsigned)n_robots), kCullThreads, 0, ctx->stream>>>(
+      ctx->d_meta.p, t_cap, ctx->d_rec_steps.p, ctx->d_rec_pose_off.p, ctx->d_surv.p, ctx->d_order.p, T, ctx->d_class_counts.p);
+  CK(cudaEventRecord(ctx->ev[7], ctx->stream));
   PeerExchange px{};
   px.t_start = ctx->d_tstart.p;
   if (exchange) {  // the cross-GPU argmin through peer memory, by the last CTA of plan_kernel
@@ -712,10 +728,10 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
     px.peers = ctx->peer_table;
   }
   plan_kernel<<<plan_grid, kThreads, 0, ctx->stream>>>(
-      ctx->C, ctx->grid, ctx->d_robots.p, q0, by_value, ctx->d_meta.p, (int)n_robots, t_cap, cap_local, ctx->d_rec_vel.p,
+      ctx->C, ctx->grid, ctx->d_robots.p, q0, by_value, ctx->d_meta.p, (int)n_robots, t_cap, ctx->d_rec_vel.p,
       ctx->d_rec_steps.p, ctx->d_rec_pose_off.p, ctx->d_poses.p, ctx->d_rec_pp.p, ctx->d_plan_pts.p, ctx->d_cost.p,
       ctx->d_scores.p, ctx->d_first_hit.p, ctx->d_work.p, ctx->d_partial.p, ctx->d_tickets2.p, ctx->d_results.p,
-      direct ? ctx->h_direct.p : nullptr, ctx->direct_seq, px);
+      direct ? ctx->h_direct.p : nullptr, ctx->direct_seq, px, ctx->d_surv.p, ctx->d_order.p, T, ctx->d_class_counts.p);
   CK(cudaEventRecord(ctx->ev[5], ctx->stream));
   if (n_robots > 1) {  // a single robot's argmin is folded into plan_kernel
     argmin_kernel<<<dim3((unsigned)argmin_ctas, (unsigned)n_robots), kArgminThreads, 0, ctx->stream>>>(
@@ -723,7 +739,7 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
         ctx->d_tickets2.p, ctx->d_results.p, ctx->d_work.p);
     ++ctx->launches;
   }
-  ctx->launches += 2;
+  ctx->launches += 4;
   CK(cudaEventRecord(ctx->ev[2], ctx->stream));
   ctx->have_cycle_event = true;
   if (n_robots == 1)  // for the read-back kernels (poses_kernel, count_radius_kernel); off the cycle's critical path
@@ -1651,6 +1667,14 @@ int b200lp_last_kernel_ms(const b200lp_ctx* ctx, float* ms_prep_kernel, float* m
   if (ms_prep_kernel) *ms_prep_kernel = ctx->ms_k_prep;
   if (ms_plan_kernel) *ms_plan_kernel = ctx->ms_k_plan;
   if (ms_argmin_kernel) *ms_argmin_kernel = ctx->ms_k_argmin;
+  return B200LP_OK;
+}
+
+int b200lp_last_kernel_times(const b200lp_ctx* ctx, float* ms, int n) {
+  if (!ctx || !ctx->have_cycle || !ms || n < 1) return B200LP_E_STATE;
+  resolve_cycle_timing(const_cast<b200lp_ctx*>(ctx));
+  const float v[4] = {ctx->ms_k_prep, ctx->ms_k_cull, ctx->ms_k_plan, ctx->ms_k_argmin};
+  for (int k = 0; k < n && k < 4; ++k) ms[k] = v[k];
   return B200LP_OK;
 }
 

@@ -369,6 +369,18 @@ __device__ __forceinline__ bool traj_precheck(const Consts& C, const RobotIn& q,
   return true;
 }
 
+// Work lists of a cycle: cull_kernel sorts the trajectories into kCostClasses lists by how many of their poses survive the
+// pre-cull (an upper bound on the obstacle-query work), plan_kernel drains the lists from the most expensive class down,
+// so the tail of the persistent kernel is made of the cheap trajectories (those in free space only pay the path critics).
+constexpr int kCostClasses = 8;
+__host__ __device__ constexpr int cost_class(int survivors) {
+#ifdef B200LP_ONE_CLASS  // A/B builds: one list in (roughly) reverse id order
+  return 0;
+#endif
+  return survivors == 0 ? 7 : survivors <= 4 ? 6 : survivors <= 8 ? 5 : survivors <= 16 ? 4 : survivors <= 24 ? 3
+         : survivors <= 32 ? 2 : survivors <= 48 ? 1 : 0;
+}
+
 // Where a sample-sharded launch cuts the estimated-work axis: frac[k] = share of the work below cut k (frac[0] = 0,
 // frac[n] = 1). n == 0: equal shares. Kernel argument, identical on every rank of a cycle.
 struct ShardCuts {
@@ -416,7 +428,8 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
                                                              float4* __restrict__ plan_pts,
                                                              long long* __restrict__ rec_pose_off,
                                                              float4* __restrict__ pose_rows, long long pose_stride,
-                                                             double2* __restrict__ rec_pp, int want_pp) {
+                                                             double2* __restrict__ rec_pp, int want_pp,
+                                                             unsigned* __restrict__ class_counts) {
   __shared__ float s_x[kMaxAxis], s_y[kMaxAxis], s_th[kMaxAxis];
   __shared__ double s_R0[9], s_t0[3], s_gL[9], s_gt[3];
   __shared__ unsigned long long s_wposes[kPrepThreads / 32];
@@ -446,6 +459,9 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
   __syncthreads();
   const int chunk = s_chunk;
   if (chunk == 0 && robot == 0 && tid == 0) *t_start = globaltimer_ns();  // the cycle's first CTA: start of its device timeline
+  // the work lists of this cycle (cull_kernel fills them, plan_kernel drains them) start empty; the previous cycle's
+  // plan_kernel is behind us in stream order
+  if (chunk == 0 && robot == 0 && tid < kCostClasses) class_counts[tid] = 0u;
 
   if (prep_job(3, tid)) {
     // tf2::transformToEigen(robot_pose_) (dd_simple…cpp:355)
@@ -998,6 +1014,121 @@ __global__ void __launch_bounds__(32) share_ack_kernel(char* root_base, int rank
 }
 
 // =============================================================================================
+// cull + classify: the float pre-cull of every pose, pose-parallel, in front of plan_kernel.
+// cull_kernel — one thread per pose ROW of the cycle's pose array (rows of a robot are dense: trajectories back to back):
+// a conservative box around the pose's candidate box (loose_box) and one look at the summed-volume table; poses whose box
+// holds no cloud point cannot collide (about 6 of 10 at C2) and never reach the double-precision geometry. One bit per
+// row: bit (row & 31) of word (row >> 5) of `surv`, rows numbered like d_poses (robot * pose_stride + row, pose_stride a
+// multiple of 256).
+// classify_kernel — one thread per trajectory: counts the surviving poses of its rows and appends the trajectory to the
+// work list of its cost class. Trajectories are visited from the END of the list (longest rollouts first), so every
+// class list starts with its longest members.
+// =============================================================================================
+constexpr int kCullThreads = 256;
+#ifndef B200LP_PRECULL
+#define B200LP_PRECULL 1  // 0: every pose goes through the double-precision geometry (A/B builds, tools/time_variants.py)
+#endif
+// cells_with_points() without the cell range: 32-bit index arithmetic (the table has < 2^29 entries: b200lp_grid_config
+// caps the cells at 2^26)
+__device__ __forceinline__ bool box_has_points(const GridDev& g, const float* lo, const float* hi) {
+  const float fx0 = cell_f(lo[0], g.org[0], g.inv_xy), fx1 = cell_f(hi[0], g.org[0], g.inv_xy);
+  const float fy0 = cell_f(lo[1], g.org[1], g.inv_xy), fy1 = cell_f(hi[1], g.org[1], g.inv_xy);
+  const float fz0 = cell_f(lo[2], g.org[2], g.inv_z), fz1 = cell_f(hi[2], g.org[2], g.inv_z);
+  const float nxm = (float)(g.nx - 1), nym = (float)(g.ny - 1), nzm = (float)(g.nz - 1);
+  const bool empty = !(lo[0] <= hi[0] && lo[1] <= hi[1] && lo[2] <= hi[2]) || fx1 < 0.f || fy1 < 0.f || fz1 < 0.f ||
+                     fx0 > nxm || fy0 > nym || fz0 > nzm || g.n_kept == 0;
+  if (empty) return false;
+  const unsigned x0 = (unsigned)fmaxf(fx0, 0.f), x1 = (unsigned)fminf(fx1, nxm) + 1u;
+  const unsigned y0 = (unsigned)fmaxf(fy0, 0.f), y1 = (unsigned)fminf(fy1, nym) + 1u;
+  const unsigned z0 = (unsigned)fmaxf(fz0, 0.f), z1 = (unsigned)fminf(fz1, nzm) + 1u;
+  const unsigned sx = (unsigned)(g.nx + 1), sy = (unsigned)(g.ny + 1) * sx;
+  const uint32_t* s00 = g.sat + (z0 * sy + y0 * sx);
+  const uint32_t* s01 = g.sat + (z0 * sy + y1 * sx);
+  const uint32_t* s10 = g.sat + (z1 * sy + y0 * sx);
+  const uint32_t* s11 = g.sat + (z1 * sy + y1 * sx);
+  const uint32_t up = (__ldg(s11 + x1) - __ldg(s11 + x0)) - (__ldg(s10 + x1) - __ldg(s10 + x0));
+  const uint32_t dn = (__ldg(s01 + x1) - __ldg(s01 + x0)) - (__ldg(s00 + x1) - __ldg(s00 + x0));
+  return up != dn;
+}
+
+__global__ void __launch_bounds__(kCullThreads)
+cull_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0, int by_value, const RobotMeta* __restrict__ meta,
+            const float4* __restrict__ poses, long long pose_stride, uint32_t* __restrict__ surv) {
+  __shared__ float s_R0f[9], s_t0f[3];
+  const int robot = blockIdx.y;
+  const long long n_rows = min(meta[robot].n_poses, pose_stride);
+  const long long row0 = (long long)blockIdx.x * kCullThreads;
+  if (row0 >= n_rows) return;  // (whole CTA)
+  if (threadIdx.x == 0) {
+    const RobotIn& q = by_value ? q0 : robots[robot];
+    double R0[9];
+    quat_to_matrix(q.pose[3], q.pose[4], q.pose[5], q.pose[6], R0);
+#pragma unroll
+    for (int a = 0; a < 9; ++a) s_R0f[a] = (float)R0[a];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) s_t0f[a] = (float)q.pose[a];
+  }
+  __syncthreads();
+  const long long row = row0 + threadIdx.x;
+  const long long grow = (long long)robot * pose_stride + row;
+  bool keep = false;
+  if (row < n_rows) {
+#if B200LP_PRECULL
+    const float4 pz = __ldg(poses + grow);
+    float lo[3], hi[3];
+    loose_box(C, g, s_R0f, s_t0f, pz.x, pz.y, pz.z, lo, hi);
+    keep = box_has_points(g, lo, hi);
+#else
+    keep = true;
+#endif
+  }
+  const unsigned mk = __ballot_sync(kFull, keep);
+  if ((threadIdx.x & 31) == 0) surv[grow >> 5] = mk;
+}
+
+// the surviving poses among rows [off, off + n)
+__device__ __forceinline__ int count_survivors(const uint32_t* __restrict__ surv, long long off, int n) {
+  int total = 0;
+  long long b = off;
+  const long long end = off + n;
+  while (b < end) {
+    const int lo = (int)(b & 31);
+    const int take = (int)min((long long)(32 - lo), end - b);
+    const unsigned mask = (take == 32 ? 0xffffffffu : ((1u << take) - 1u)) << lo;
+    total += __popc(__ldg(surv + (b >> 5)) & mask);
+    b += take;
+  }
+  return total;
+}
+
+__global__ void __launch_bounds__(kCullThreads)
+classify_kernel(const RobotMeta* __restrict__ meta, int t_cap, const int* __restrict__ rec_steps,
+                const long long* __restrict__ rec_pose_off, const uint32_t* __restrict__ surv, int* __restrict__ order,
+                size_t order_stride, unsigned* __restrict__ class_counts) {
+  __shared__ unsigned s_cnt[kCostClasses], s_base[kCostClasses];
+  const int robot = blockIdx.y;
+  const RobotMeta m = meta[robot];
+  const int n_local = min(m.t_end, t_cap) - m.t_begin;
+  if ((int)blockIdx.x * kCullThreads >= n_local) return;  // (whole CTA)
+  if (threadIdx.x < kCostClasses) s_cnt[threadIdx.x] = 0u;
+  __syncthreads();
+  const int idx = (int)blockIdx.x * kCullThreads + threadIdx.x;
+  int cls = -1, rec_i = 0;
+  unsigned pos = 0u;
+  if (idx < n_local) {
+    const int id = m.t_begin + (n_local - 1 - idx);
+    const size_t rec = (size_t)robot * t_cap + id;
+    cls = cost_class(count_survivors(surv, rec_pose_off[rec], rec_steps[rec]));
+    rec_i = (int)rec;
+    pos = atomicAdd(&s_cnt[cls], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < kCostClasses && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(class_counts + threadIdx.x, s_cnt[threadIdx.x]);
+  __syncthreads();
+  if (cls >= 0) order[(size_t)cls * order_stride + s_base[cls] + pos] = rec_i;
+}
+
+// =============================================================================================
 // plan: persistent warps, one trajectory per work item (robot, local trajectory index), handed out by a
 // global counter; grid = min(work, SMs x resident CTAs). Each warp rolls the trajectory out 32 poses at a
 // time, queries the grid, evaluates the critic stack and writes cost / per-critic scores / first-hit pose.
@@ -1011,7 +1142,7 @@ struct WarpCtx {
   float R0f[9], t0f[3];  // the same transform rounded to float: operands of the conservative pre-cull (loose_box)
   double heading_deviation;
   const float4* plan;    // the robot's prune plan (shared-memory copy for single-robot launches)
-  int t_begin, n_local, plan_n;
+  int plan_n;
   // running best of the trajectories this warp scored (single-robot launches): (cost bits, id), collisions
   unsigned long long best_cb;
   int best_id, n_coll;
@@ -1056,6 +1187,7 @@ struct CtaShared {
   unsigned short list[kWarpsPerCta][64];  // poses that survived the pre-cull and wait for the exact geometry, ascending
   int scored[kWarpsPerCta];               // trajectories / poses each warp scored (single-robot launches)
   long long poses_scored[kWarpsPerCta];
+  unsigned cls_first[kCostClasses + 1];   // first work index of every cost class; [kCostClasses] = number of work items
 };
 
 // lanes that head a group of kGroup consecutive stash columns
@@ -1068,27 +1200,32 @@ __host__ __device__ constexpr unsigned group_heads() {
 #ifndef B200LP_PLAN_MIN_CTAS
 #define B200LP_PLAN_MIN_CTAS 5
 #endif
-#ifndef B200LP_PRECULL
-#define B200LP_PRECULL 1  // 0: every pose goes through the double-precision geometry (A/B builds, tools/time_variants.py)
-#endif
 __global__ void __launch_bounds__(kThreads, B200LP_PLAN_MIN_CTAS)
 plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0, int by_value, RobotMeta* meta, int n_robots,
-            int t_cap, int cap_local, const float4* __restrict__ rec_vel, const int* __restrict__ rec_steps,
+            int t_cap, const float4* __restrict__ rec_vel, const int* __restrict__ rec_steps,
             const long long* __restrict__ rec_pose_off, const float4* __restrict__ poses,
             const double2* __restrict__ rec_pp, const float4* __restrict__ plan_pts, double* __restrict__ out_cost,
             double* __restrict__ out_scores, int* __restrict__ out_first_hit,
             unsigned long long* __restrict__ work_counter, BlockBest* partial, unsigned* __restrict__ tickets,
-            b200lp_result* __restrict__ results, DirectOut* direct, unsigned long long direct_seq, PeerExchange px) {
+            b200lp_result* __restrict__ results, DirectOut* direct, unsigned long long direct_seq, PeerExchange px,
+            const uint32_t* __restrict__ surv, const int* __restrict__ order, size_t order_stride,
+            const unsigned* __restrict__ class_counts) {
   __shared__ CtaShared S;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* stash = S.stash[warp];
   float4* pre = S.pre[warp];
   WarpCtx& W = S.wc[warp];
-  // Work space: (robot, local trajectory index). A single-robot launch takes its trajectory count from prep_kernel's meta
-  // (a sample shard's size is only known on the device: the cuts are balanced by poses, not by samples); fleets pad
-  // every robot to cap_local = t_cap.
-  const unsigned long long total = n_robots == 1 ? (unsigned long long)max(0, min(meta[0].t_end, t_cap) - meta[0].t_begin)
-                                                 : (unsigned long long)n_robots * (unsigned long long)cap_local;
+  // Work space: the class lists cull_kernel filled, most expensive class first; position w of the concatenation is entry
+  // w - cls_first[k] of list k.
+  if (threadIdx.x == 0) {
+    unsigned acc = 0u;
+#pragma unroll
+    for (int k = 0; k < kCostClasses; ++k) {
+      S.cls_first[k] = acc;
+      acc += class_counts[k];
+    }
+    S.cls_first[kCostClasses] = acc;
+  }
   const int nc = C.n_critics;
 
   // single-robot launches stage the prune plan in shared memory once per CTA
@@ -1108,22 +1245,36 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0,
     W.best_cb = ~0ull; W.best_id = -1; W.n_coll = 0;
   }
   int cur_robot = -1;
-  // work items are fetched one ahead, so the atomic's round trip overlaps the previous trajectory
-  unsigned long long pending = 0ull;
-  if (lane == 0) pending = atomicAdd(work_counter, 1ull);
+  const unsigned total = S.cls_first[kCostClasses];  // (written before the __syncthreads above)
+  // Work items: position w of the concatenated class lists, claimed with an atomic on the global counter. A claimed item
+  // is a trajectory nobody else can take, and trajectories differ a lot in cost (C2: mean 17 us, p99 55 us, max 90 us), so a
+  // warp claims its next item LATE — when the obstacle query of the current one is over and only the path critics and the
+  // scoring are left — and fetches the list entry when those are done: both round trips overlap work, and no item waits
+  // behind a long one while other warps leave (claiming one or two items ahead at the top of the loop left the last 25 %
+  // of the launch with < 2 % of the warps busy).
+  auto list_entry = [&](unsigned w) -> int {  // (robot * t_cap + id) of work item w, -1 past the end
+    if (w >= total) return -1;
+    int k = 0;
+#pragma unroll
+    for (int c = 1; c < kCostClasses; ++c) k += w >= S.cls_first[c] ? 1 : 0;
+    return __ldg(order + (size_t)k * order_stride + (w - S.cls_first[k]));
+  };
+  unsigned ticket = 0u;  // lane 0
+  int next_rec = -1;     // lane 0: list entry of the next item (-1: past the end)
+  if (lane == 0) {
+    ticket = (unsigned)atomicAdd(work_counter, 1ull);
+    next_rec = list_entry(ticket);
+  }
   for (;;) {
-    const unsigned long long w = __shfl_sync(kFull, pending, 0);
-    if (w >= total) break;
-    if (lane == 0) pending = atomicAdd(work_counter, 1ull);
-    const int robot = (int)(w / (unsigned long long)cap_local);
-    const int local = (int)(w - (unsigned long long)robot * (unsigned long long)cap_local);
+    const int rec_i = __shfl_sync(kFull, next_rec, 0);
+    if (rec_i < 0) break;
+    const int robot = rec_i / t_cap;
+    const int id = rec_i - robot * t_cap;
     if (robot != cur_robot) {
       cur_robot = robot;
       const RobotIn& q = by_value ? q0 : robots[robot];
       __syncwarp();
       if (lane == 0) {
-        W.t_begin = meta[robot].t_begin;
-        W.n_local = meta[robot].t_end - W.t_begin;
         W.plan_n = q.plan_n;
         W.heading_deviation = q.heading_deviation;
         W.plan = plan_staged ? S.plan : plan_pts + q.plan_off;
@@ -1137,13 +1288,13 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0,
       }
       __syncwarp();
     }
-    if (local >= W.n_local) continue;  // padding of the (robot, local) work space
-    // hand trajectories out from the END of the list: the sample grid is ordered by rising linear speed, so the
-    // longest rollouts start first and the kernel's tail is made of short ones
-    const int id = W.t_begin + (W.n_local - 1 - local);
-    const size_t rec = (size_t)robot * t_cap + id;
+    const size_t rec = (size_t)rec_i;
+#ifdef B200LP_TRAJ_TRACE  // tools only (tools/traj_trace.py): when every trajectory started and how long it took
+    const unsigned long long trace_t0 = globaltimer_ns();
+#endif
     const int n = rec_steps[rec];
-    const float4* traj_poses = poses + rec_pose_off[rec];  // prep_kernel's forward simulation
+    const long long pose_row = rec_pose_off[rec];
+    const float4* traj_poses = poses + pose_row;  // prep_kernel's forward simulation
 
     // ---- critic stack analysis (warp-uniform) ------------------------------------------------
     // A critic's value may be known before the rollout (collision_model.cpp:53-55, stick_path_model.cpp:53-55,
@@ -1206,42 +1357,28 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0,
       }
     }
     // ---- pass 1: obstacle query ------------------------------------------------------------------------
-    // Stage A (cheap, float): every pose gets a conservative box around its candidate box (loose_box) and one look at the
-    // summed-volume table; poses whose box holds no cloud point cannot collide and drop out (about 6 of 10 at C2). The
-    // survivors are queued in ascending pose order. Stage B (exact, double): as soon as 32 survivors wait — or the
-    // trajectory is exhausted — their cuboids are built with the reference's arithmetic, and groups of kGroup consecutive
-    // survivors are swept against their united candidate stream, lowest pose first, so the first colliding pose found is
-    // the reference's. The double-precision geometry therefore runs for compacted survivors only.
+    // cull_kernel has already looked at every pose in float: `surv` holds, per pose row, whether the pose's
+    // conservative candidate box contains cloud points at all (about 4 of 10 at C2); the others cannot collide. The
+    // survivors are queued in ascending pose order; as soon as 32 wait — or the trajectory is exhausted — their cuboids are
+    // built with the reference's arithmetic (double precision), and groups of kGroup consecutive survivors are swept
+    // against their united candidate stream, lowest pose first, so the first colliding pose found is the reference's.
     int hit_box = -1, hit_mm = -1;  // first colliding pose per collision-critic kind
     // kRejected: the stack's first collision critic hit and ends the evaluation
     if (fl & (kNeedBox | kNeedMM)) {
       unsigned short* list = S.list[warp];
       const unsigned lt = (1u << lane) - 1u;
-      int cnt = 0, base = 0;  // survivors waiting / next pose to pre-cull (warp-uniform)
+      int cnt = 0, base = 0;  // survivors waiting / next pose to look at (warp-uniform)
       for (;;) {
-#if B200LP_PRECULL
         while (cnt < 32 && base < n) {
-          const int k = base + lane;
-          bool keep = false;
-          if (k < n) {
-            const float4 pz = __ldg(traj_poses + k);
-            float lo[3], hi[3];
-            loose_box(C, g, W.R0f, W.t0f, pz.x, pz.y, pz.z, lo, hi);
-            CellBox unused;
-            keep = cells_with_points(g, lo, hi, &unused);
-          }
-          const unsigned mk = __ballot_sync(kFull, keep);
-          if (keep) list[cnt + __popc(mk & lt)] = (unsigned short)k;
+          // bits of rows pose_row + base .. + 31 (warp-uniform addresses; the array is padded by two words)
+          const long long b0 = pose_row + base;
+          const uint32_t* wp = surv + (b0 >> 5);
+          unsigned mk = __funnelshift_r(__ldg(wp), __ldg(wp + 1), (unsigned)(b0 & 31));
+          if (n - base < 32) mk &= (1u << (n - base)) - 1u;  // (the rows behind belong to the next trajectory)
+          if ((mk >> lane) & 1u) list[cnt + __popc(mk & lt)] = (unsigned short)(base + lane);
           cnt += __popc(mk);
           base += 32;
         }
-#else
-        if (base < n) {  // no pre-cull: every pose goes through the exact geometry
-          if (base + lane < n) list[lane] = (unsigned short)(base + lane);
-          cnt = min(32, n - base);
-          base += 32;
-        }
-#endif
         if (cnt == 0) break;
         __syncwarp();
         const int m_here = min(cnt, 32);
@@ -1299,6 +1436,7 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0,
       __syncwarp();
     }
 
+    if (lane == 0) ticket = (unsigned)atomicAdd(work_counter, 1ull);  // the next item, claimed late (see the top of the loop)
     // ---- pass 2: path critics, only for trajectories the collision critic did not already reject ----
     double stick_sum = 0.0;
     float last_nn = 0.f;
@@ -1330,6 +1468,7 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0,
       pp_yaw = pp.y;
     }
 
+    if (lane == 0) next_rec = list_entry(ticket);
     // ---- StackedScoringModel::scoreTrajectory (stacked_scoring_model.cpp:75-93) -----------------
     double cost = 0.0;
     int first_hit = -1;
@@ -1366,6 +1505,11 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0,
     if (lane == 0) {
       out_cost[rec] = cost;
       out_first_hit[rec] = first_hit;
+#ifdef B200LP_TRAJ_TRACE
+      out_cost[rec] = (double)(trace_t0 - *px.t_start);             // start, ns after the cycle's first CTA
+      out_first_hit[rec] = (int)(globaltimer_ns() - trace_t0);      // duration, ns
+      out_scores[rec * nc] = (double)(first_hit >= 0 ? first_hit : -1);
+#endif
     }
     if (fused_argmin && lane == 0) {  // running best and counters of this warp (kept out of the registers of the work loop)
       S.scored[warp] += 1;

@@ -316,9 +316,13 @@ class LocalPlanner:
         return {"pretests": v[0], "rounds": v[1], "exact_tests": v[2], "groups": v[3]}
 
     def last_kernel_ms(self) -> dict:
-        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        if hasattr(self.lib, "b200lp_last_kernel_times"):
+            v = (C.c_float * 4)()
+            self.lib.b200lp_last_kernel_times(self.h, v, 4)
+            return {"prep_kernel": v[0], "cull_kernel": v[1], "plan_kernel": v[2], "argmin_kernel": v[3]}
+        a, b, c = C.c_float(), C.c_float(), C.c_float()  # (A/B builds of earlier rounds)
         self.lib.b200lp_last_kernel_ms(self.h, C.byref(a), C.byref(b), C.byref(c))
-        return {"prep_kernel": a.value, "plan_kernel": b.value, "argmin_kernel": c.value}
+        return {"prep_kernel": a.value, "cull_kernel": 0.0, "plan_kernel": b.value, "argmin_kernel": c.value}
 
     def set_cloud_ptr(self, host_ptr: int, n: int, stride: int):
         """set_cloud from a raw host address (e.g. a pinned buffer)."""

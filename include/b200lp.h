@@ -360,6 +360,9 @@ int b200lp_last_timing(const b200lp_ctx* ctx, float* ms_upload, float* ms_grid_b
  * forward simulation), plan_kernel (pose geometry + obstacle query + critics; the one the roofline is reported
  * for) and argmin_kernel (best trajectory per robot). */
 int b200lp_last_kernel_ms(const b200lp_ctx* ctx, float* ms_prep_kernel, float* ms_plan_kernel, float* ms_argmin_kernel);
+/* The same with every kernel of the cycle: ms[0] = prep_kernel, ms[1] = cull_kernel (float pre-cull of every pose + the work
+ * lists plan_kernel drains), ms[2] = plan_kernel, ms[3] = argmin_kernel (fleets). Writes min(n, 4) values. */
+int b200lp_last_kernel_times(const b200lp_ctx* ctx, float* ms, int n);
 /* Device time of the last single-robot cycle, nanoseconds of the GPU's global timer from the first CTA of prep_kernel to
  * the last CTA of plan_kernel (the one that writes the result into host memory); after b200lp_plan_shard_exchange
  * peer_ns[r] (B200LP_MAX_PEERS entries, may be NULL) holds the same figure of every rank r < world. */
