@@ -701,7 +701,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
-    dev_ms, plan_k_ms, prep_k_ms, argmin_k_ms, wall_ms = [], [], [], [], []
+    dev_ms, plan_k_ms, prep_k_ms, argmin_k_ms, cull_k_ms, wall_ms = [], [], [], [], [], []
     for _ in range(args.steps):
         flush_l2(sync_steps)
         t0 = time.perf_counter()
@@ -712,6 +712,7 @@ def main():
         plan_k_ms.append(km["plan_kernel"])
         prep_k_ms.append(km["prep_kernel"])
         argmin_k_ms.append(km["argmin_kernel"])
+        cull_k_ms.append(km["cull_kernel"])
     barrier()
     launches = lp.launch_count() - launches0
     t_dev = sum(wall_ms) / 1e3
@@ -825,7 +826,8 @@ def main():
                          "upload + grid build) + set_plan + plan, host wall clock, every step"
                          + ("; N > 1: ONE upload by rank 0, the rows reach the peers over NVLink" if shared_map else ""))},
         "gpu_launches": int(launches),
-        "kernel_ms": {"prep_kernel": sum(prep_k_ms) / len(prep_k_ms), "plan_kernel": k_ms,
+        "kernel_ms": {"prep_kernel": sum(prep_k_ms) / len(prep_k_ms), "cull_and_classify_kernels": sum(cull_k_ms) / len(cull_k_ms),
+                      "plan_kernel": k_ms,
                       "argmin_kernel": sum(argmin_k_ms) / len(argmin_k_ms), "cycle_events": 1e3 * t_events / args.steps,
                       "grid_build_total": grid_ms,
                       "what": "CUDA events on the library's stream; cycle_events = first kernel start -> last kernel end, max over ranks"},

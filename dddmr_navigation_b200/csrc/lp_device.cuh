@@ -27,7 +27,7 @@ constexpr int kThreads = kWarpsPerCta * 32;
 constexpr int kGroup = B200LP_GROUP;  // consecutive poses swept against one candidate stream (power of two)
 constexpr int kPreStride = 5;   // float4 per pose in the pre-test stash (4 used + 1 pad: conflict-free 80-byte stride)
 constexpr int kMaxAxis = 2048;  // cap on samples per velocity axis (incl. the inserted zero)
-constexpr int kPlanSmem = 256;  // prune-plan points staged in shared memory
+constexpr int kPlanWarp = 96;   // prune-plan points every warp stages in shared memory (longer plans are scanned in global memory)
 constexpr unsigned kFull = 0xffffffffu;
 
 // per-warp pose stash (structure of arrays: [field][lane])
@@ -367,7 +367,8 @@ __device__ __forceinline__ void loose_box(const Consts& C, const GridDev& g, con
 // Everything CollisionModel derives per pose from the transformed cuboid, written to the warp stash:
 //  * stash (SoA [field][lane]): the reference's own quantities, read by the exact tests and the path critics;
 //  * pre (AoS, kPreStride float4 per lane, may be nullptr): coefficients of the conservative pre-test of
-//    sweep_points — (axis, -k) per box axis with k = fl(centre . axis), and the half extents rounded up by delta;
+//    sweep_points — the box axes with -k, k = fl(centre . axis) (x and y axis interleaved component by component, then the
+//    z axis), and the half extents rounded up by delta;
 //  * *cb (may be nullptr): the cell range of the pose's candidate box.
 __device__ __forceinline__ void pose_geometry(const Consts& C, const GridDev& g, const double* L, const double* t,
                                               float* stash /* [F_COUNT][32] */, float4* pre, CellBox* cb, int lane,
@@ -433,13 +434,16 @@ __device__ __forceinline__ void pose_geometry(const Consts& C, const GridDev& g,
   stash[F_MXX * 32 + lane] = mx[0]; stash[F_MXY * 32 + lane] = mx[1]; stash[F_MXZ * 32 + lane] = mx[2];
   if (pre) {
     const float delta = pretest_delta(g);
-    float hb[3];
+    float hb[3], k[3];
 #pragma unroll
     for (int e = 0; e < 3; ++e) {
-      const float k = (float)(((double)c[0] * ax[e][0] + (double)c[1] * ax[e][1]) + (double)c[2] * ax[e][2]);
-      pre[lane * kPreStride + e] = make_float4(ax[e][0], ax[e][1], ax[e][2], -k);
+      k[e] = (float)(((double)c[0] * ax[e][0] + (double)c[1] * ax[e][1]) + (double)c[2] * ax[e][2]);
       hb[e] = (half[e] < 0.f) ? -1.0f : __fadd_ru(half[e], delta);
     }
+    // the x and y axes interleaved: the sweep evaluates both dot products of a pose with packed (2 x fp32) FMAs
+    pre[lane * kPreStride + 0] = make_float4(ax[0][0], ax[1][0], ax[0][1], ax[1][1]);
+    pre[lane * kPreStride + 1] = make_float4(ax[0][2], ax[1][2], -k[0], -k[1]);
+    pre[lane * kPreStride + 2] = make_float4(ax[2][0], ax[2][1], ax[2][2], -k[2]);
     pre[lane * kPreStride + 3] = make_float4(hb[0], hb[1], hb[2], 0.f);
   }
   if (cb) {
@@ -530,6 +534,20 @@ struct SweepGrid {
 #else
 #define B200LP_SWEEP_ATTR __noinline__
 #endif
+// packed 2 x fp32 arithmetic (FFMA2): only ever used by the conservative pre-test, whose rounding does not matter
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
 template <bool kMinMax>
 __device__ B200LP_SWEEP_ATTR unsigned sweep_points(const SweepGrid g, const float* stash, const float4* pre, int col0,
                                                    int lane, const CellBox ub) {
@@ -539,19 +557,23 @@ __device__ B200LP_SWEEP_ATTR unsigned sweep_points(const SweepGrid g, const floa
   const float inv_nyr = 1.0f / (float)nyr;
 
   // Pre-test coefficients of the kGroup poses, in registers. CollisionModel: per pose the x and y axes of the box with
-  // -k = -fl(centre . axis) folded in (8 floats); the half extents of x and y shared by the group (their maximum: the
-  // poses carry the same cuboid, the extents differ by roundings only); and ONE slab for the z axis of all poses: the box's
-  // z axis is the robot's, which the rollout never tilts, so the poses' slabs a_q . p - k_q in [-h_q, h_q] are intervals
-  // of (nearly) the same linear form. With A the axis of the group's first pose, a_q . p = A . p - (A - a_q) . p and
-  // |(A - a_q) . p| <= |A - a_q|_1 cmax for every cloud point, so A . p in [k_q - h_q - D_q, k_q + h_q + D_q]; the slab
-  // tested is the hull of those intervals, widened by the rounding of both FMA chains and of this arithmetic
-  // (<= 2e-6 cmax in all). A superset of the per-pose test, like everything in the pre-test: survivors are re-decided
-  // exactly. 39 registers instead of 60, and 27 FMAs + 9 compares per candidate instead of 36 + 12.
+  // -k = -fl(centre . axis) folded in, interleaved so that both dot products of a pose are three packed FMAs (8 floats);
+  // the half extents of x and y shared by the group (their maximum: the poses carry the same cuboid, the extents differ by
+  // roundings only); and ONE slab for the z axis of all poses: the box's z axis is the robot's, which the rollout never
+  // tilts, so the poses' slabs a_q . p - k_q in [-h_q, h_q] are intervals of (nearly) the same linear form. With A the
+  // axis of the group's first pose, a_q . p = A . p - (A - a_q) . p and |(A - a_q) . p| <= |A - a_q|_1 cmax for every cloud
+  // point, so A . p in [k_q - h_q - D_q, k_q + h_q + D_q]; the slab tested is the hull of those intervals, widened by the
+  // rounding of both FMA chains and of this arithmetic (<= 2e-6 cmax in all). A superset of the per-pose test, like
+  // everything in the pre-test: survivors are re-decided exactly. Per candidate: 12 packed + 3 scalar FMAs and 9 compares
+  // chained through predicates; which pose a survivor belongs to is only worked out when a lane has one.
+  // A pose that is no longer worth testing (past the end, or above the lowest pose known to collide) gets -k = +inf.
   // CollisionMinMaxModel: the poses' AABBs (exact compares need no slack).
-  float4 ca[kGroup], cb[kGroup];
+  f32x2 c0[kGroup], c1[kGroup], c2[kGroup], c3[kGroup];  // (ax.x, ay.x), (ax.y, ay.y), (ax.z, ay.z), (-kx, -ky)
+  float4 ca[kGroup], cb[kGroup];                         // min-max: AABB corners
   float hx = -1.0f, hy = -1.0f, zc = 0.f, zr = -1.0f;
   float ax_z = 0.f, ay_z = 0.f, az_z = 0.f;
   unsigned alive = 0u;  // poses still worth testing: live ones below the lowest pose known to collide (warp-uniform)
+  const f32x2 never = pack2(__int_as_float(0x7f800000), __int_as_float(0x7f800000));
   {
     float lo = 3.402823466e+38f, hi = -3.402823466e+38f;
 #pragma unroll
@@ -562,10 +584,14 @@ __device__ B200LP_SWEEP_ATTR unsigned sweep_points(const SweepGrid g, const floa
         cb[q] = make_float4(stash[F_MXX * 32 + col], stash[F_MXY * 32 + col], stash[F_MXZ * 32 + col], 0.f);
         alive |= 1u << q;  // (lanes past the end carry an inverted box: never inside)
       } else {
-        ca[q] = pre[col * kPreStride + 0];
-        cb[q] = pre[col * kPreStride + 1];
+        const float4 p0 = pre[col * kPreStride + 0];
+        const float4 p1 = pre[col * kPreStride + 1];
         const float4 cz = pre[col * kPreStride + 2];
         const float4 h = pre[col * kPreStride + 3];
+        c0[q] = pack2(p0.x, p0.y);
+        c1[q] = pack2(p0.z, p0.w);
+        c2[q] = pack2(p1.x, p1.y);
+        c3[q] = pack2(p1.z, p1.w);
         if (q == 0) { ax_z = cz.x; ay_z = cz.y; az_z = cz.z; }
         if (h.x >= 0.f) {  // a live pose (lanes past the end carry half extents of -1)
           alive |= 1u << q;
@@ -575,6 +601,8 @@ __device__ B200LP_SWEEP_ATTR unsigned sweep_points(const SweepGrid g, const floa
           const float s_q = h.z + d;
           lo = fminf(lo, -cz.w - s_q);
           hi = fmaxf(hi, -cz.w + s_q);
+        } else {
+          c3[q] = never;
         }
       }
     }
@@ -612,51 +640,64 @@ __device__ B200LP_SWEEP_ATTR unsigned sweep_points(const SweepGrid g, const floa
       rows &= rows - 1;
       const uint32_t b = __shfl_sync(kFull, beg, src), e = __shfl_sync(kFull, end, src);
       for (uint32_t j0 = b; j0 < e; j0 += 32) {  // warp-uniform trip count
-        const uint32_t j = j0 + lane;
-        unsigned pm = 0u;
-        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        // lanes past the end of the row look at its last point again: no divergence, and a duplicate cannot change an any-hit
+        const float4 p = __ldg(g.pts + min(j0 + lane, e - 1u));
 #if B200LP_COUNT
         c_cand += (unsigned long long)min(32u, e - j0) * (unsigned long long)__popc(alive);  // (candidate, pose) pre-tests
         c_rounds += 1ull;
 #endif
-        if (j < e) {
-          p = __ldg(g.pts + j);
-          if (kMinMax) {
+        bool any = false;
+        if (kMinMax) {
 #pragma unroll
-            for (int q = 0; q < kGroup; ++q) {
-              const bool in = (p.x >= ca[q].x) & (p.x <= cb[q].x) & (p.y >= ca[q].y) & (p.y <= cb[q].y) & (p.z >= ca[q].z) & (p.z <= cb[q].z);
-              pm |= in ? (1u << q) : 0u;
-            }
-          } else {
-            // conservative superset of the exact test: |v' - v| <= delta; no short-circuit, so the
-            // compares chain through predicates instead of branching
-            const float tz = __fmaf_rn(p.x, ax_z, __fmaf_rn(p.y, ay_z, __fmaf_rn(p.z, az_z, -zc)));
-            const bool inz = fabsf(tz) <= zr;
+          for (int q = 0; q < kGroup; ++q)
+            any |= (p.x >= ca[q].x) & (p.x <= cb[q].x) & (p.y >= ca[q].y) & (p.y <= cb[q].y) & (p.z >= ca[q].z) & (p.z <= cb[q].z);
+        } else {
+          // conservative superset of the exact test: |v' - v| <= delta
+          const float tz = __fmaf_rn(p.x, ax_z, __fmaf_rn(p.y, ay_z, __fmaf_rn(p.z, az_z, -zc)));
+          const f32x2 px = pack2(p.x, p.x), py = pack2(p.y, p.y), pz = pack2(p.z, p.z);
 #pragma unroll
-            for (int q = 0; q < kGroup; ++q) {
-              const float vx = __fmaf_rn(p.x, ca[q].x, __fmaf_rn(p.y, ca[q].y, __fmaf_rn(p.z, ca[q].z, ca[q].w)));
-              const float vy = __fmaf_rn(p.x, cb[q].x, __fmaf_rn(p.y, cb[q].y, __fmaf_rn(p.z, cb[q].z, cb[q].w)));
-              const bool in = inz & (fabsf(vx) <= hx) & (fabsf(vy) <= hy);
-              pm |= in ? (1u << q) : 0u;
-            }
+          for (int q = 0; q < kGroup; ++q) {
+            float vx, vy;
+            unpack2(fma2(px, c0[q], fma2(py, c1[q], fma2(pz, c2[q], c3[q]))), vx, vy);
+            any |= (fabsf(vx) <= hx) & (fabsf(vy) <= hy);
           }
-          pm &= alive;
+          any &= fabsf(tz) <= zr;
         }
-        if (__any_sync(kFull, pm != 0u)) {  // rare: decide with the reference's own arithmetic
+        if (__any_sync(kFull, any)) {  // rare: find the poses concerned and decide with the reference's own arithmetic
 #pragma unroll 1
           for (int q = 0; q < kGroup; ++q) {
-            if (pm & (1u << q)) {
-              const int col = col0 + q;
-              const bool in = kMinMax ? exact_in_aabb(stash, col, p.x, p.y, p.z) : exact_in_box(stash, col, p.x, p.y, p.z);
-              if (in && exact_in_radius(stash, col, p.x, p.y, p.z)) hit |= 1u << q;
+            if (!((alive >> q) & 1u)) continue;  // (warp-uniform)
+            const int col = col0 + q;
+            bool in;
+            if (kMinMax) {
+              in = exact_in_aabb(stash, col, p.x, p.y, p.z);
+            } else {
+              const float4 p0 = pre[col * kPreStride + 0];
+              const float4 p1 = pre[col * kPreStride + 1];
+              const float vx = __fmaf_rn(p.x, p0.x, __fmaf_rn(p.y, p0.z, __fmaf_rn(p.z, p1.x, p1.z)));
+              const float vy = __fmaf_rn(p.x, p0.y, __fmaf_rn(p.y, p0.w, __fmaf_rn(p.z, p1.y, p1.w)));
+              in = any & (fabsf(vx) <= hx) & (fabsf(vy) <= hy);
+              if (__any_sync(kFull, in)) in = in && exact_in_box(stash, col, p.x, p.y, p.z);
             }
+            if (in && exact_in_radius(stash, col, p.x, p.y, p.z)) hit |= 1u << q;
           }
 #if B200LP_COUNT
-          c_exact += (unsigned long long)__popc(__ballot_sync(kFull, pm != 0u));
+          c_exact += (unsigned long long)__popc(__ballot_sync(kFull, any));
 #endif
           const unsigned wh = __reduce_or_sync(kFull, hit);
           if (wh & 1u) { B200LP_COUNT_FLUSH(); return wh; }  // the lowest pose of the group collides: nothing can precede it
-          if (wh) alive &= (wh & (0u - wh)) - 1u;
+          if (wh) {
+            alive &= (wh & (0u - wh)) - 1u;
+            if (!kMinMax) {
+#pragma unroll
+              for (int q = 1; q < kGroup; ++q)
+                if (!((alive >> q) & 1u)) c3[q] = never;
+            } else {
+#pragma unroll
+              for (int q = 1; q < kGroup; ++q)
+                if (!((alive >> q) & 1u)) ca[q].x = 3.402823466e+38f;
+            }
+          }
         }
       }
     }
@@ -674,6 +715,42 @@ __device__ __forceinline__ float plan_nn_d2(const float4* plan, int n, float qx,
     const float4 p = plan[i];
     const float d = l2_simple(qx, qy, qz, p.x, p.y, p.z);
     best = fminf(best, d);
+  }
+  return best;
+}
+
+// The same scan over the warp's shared-memory copy of the plan, two points per trip: pair k holds points 2k and 2k + 1 as
+// xy[k] = (ax, ay, bx, by), z[k] = (az, bz) (an odd last point is doubled: a duplicate cannot change a minimum). Per point
+// the arithmetic is l2_simple's, operation for operation — dx = qx - px, r = dx * dx, dy = qy - py, r = r + dy * dy, ... —
+// each an individually rounded IEEE operation; only the INDEPENDENT subtractions and squares of a pair share an
+// instruction (FADD2 / FMUL2: two fp32 lanes, each rounded like the scalar operation). The additions stay scalar:
+// ptxas contracts a packed multiply feeding a packed add into FFMA2 even under --fmad=false (checked on CUDA 12.9), which
+// would change the rounding; it does not split a packed multiply to feed a scalar add (SASS checked: no FFMA in this loop).
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float plan_nn_d2_pairs(const float4* xy, const float2* z, int n_pairs, float qx, float qy, float qz) {
+  float best = 3.402823466e+38f;
+  const f32x2 qxy = pack2(qx, qy), qzz = pack2(qz, qz);
+#pragma unroll 2
+  for (int k = 0; k < n_pairs; ++k) {
+    const float4 p = xy[k];
+    const float2 pz = z[k];
+    const f32x2 da = sub2(qxy, pack2(p.x, p.y)), db = sub2(qxy, pack2(p.z, p.w)), dz = sub2(qzz, pack2(pz.x, pz.y));
+    float ax2, ay2, bx2, by2, az2, bz2;
+    unpack2(mul2(da, da), ax2, ay2);
+    unpack2(mul2(db, db), bx2, by2);
+    unpack2(mul2(dz, dz), az2, bz2);
+    const float ra = __fadd_rn(__fadd_rn(ax2, ay2), az2);
+    const float rb = __fadd_rn(__fadd_rn(bx2, by2), bz2);
+    best = fminf(best, fminf(ra, rb));
   }
   return best;
 }

@@ -1139,7 +1139,6 @@ classify_kernel(const RobotMeta* __restrict__ meta, int t_cap, const int* __rest
 // thread for 5 CTAs per SM), and everything here is read a few times per trajectory at most.
 struct WarpCtx {
   double R0[9], t0[3];
-  float R0f[9], t0f[3];  // the same transform rounded to float: operands of the conservative pre-cull (loose_box)
   double heading_deviation;
   const float4* plan;    // the robot's prune plan (shared-memory copy for single-robot launches)
   int plan_n;
@@ -1183,7 +1182,8 @@ struct CtaShared {
   float stash[kWarpsPerCta][F_COUNT * 32];
   float4 pre[kWarpsPerCta][32 * kPreStride];
   WarpCtx wc[kWarpsPerCta];
-  float4 plan[kPlanSmem];
+  float4 plan_xy[kWarpsPerCta][kPlanWarp / 2];  // every warp's copy of its robot's prune plan, two points per entry
+  float2 plan_z[kWarpsPerCta][kPlanWarp / 2];
   unsigned short list[kWarpsPerCta][64];  // poses that survived the pre-cull and wait for the exact geometry, ascending
   int scored[kWarpsPerCta];               // trajectories / poses each warp scored (single-robot launches)
   long long poses_scored[kWarpsPerCta];
@@ -1228,14 +1228,7 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0,
   }
   const int nc = C.n_critics;
 
-  // single-robot launches stage the prune plan in shared memory once per CTA
-  const RobotIn& first = by_value ? q0 : robots[0];
-  const int plan_staged = (n_robots == 1 && first.plan_n <= kPlanSmem) ? 1 : 0;  // (int, like fused_argmin below: see `fl`)
-  if (plan_staged) {
-    const float4* gp = plan_pts + first.plan_off;
-    for (int i = threadIdx.x; i < first.plan_n; i += kThreads) S.plan[i] = gp[i];
-  }
-  __syncthreads();
+  __syncthreads();  // (cls_first)
 
   // Single-robot launches fold Local_Planner::getBestTrajectory into this kernel (warp -> CTA -> last CTA by ticket);
   // fleets run argmin_kernel afterwards. The (cost bits, id) order is total, so the merge tree does not matter.
@@ -1277,14 +1270,19 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0,
       if (lane == 0) {
         W.plan_n = q.plan_n;
         W.heading_deviation = q.heading_deviation;
-        W.plan = plan_staged ? S.plan : plan_pts + q.plan_off;
+        W.plan = plan_pts + q.plan_off;
         // tf2::transformToEigen(robot_pose_) (dd_simple…cpp:355)
         quat_to_matrix(q.pose[3], q.pose[4], q.pose[5], q.pose[6], W.R0);
         W.t0[0] = q.pose[0]; W.t0[1] = q.pose[1]; W.t0[2] = q.pose[2];
-#pragma unroll
-        for (int a = 0; a < 9; ++a) W.R0f[a] = (float)W.R0[a];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) W.t0f[a] = (float)W.t0[a];
+      }
+      // the warp's copy of the robot's prune plan (pcl_prune_plan_), two points per entry, for the path critics' scans
+      if (q.plan_n <= kPlanWarp) {
+        const float4* gp = plan_pts + q.plan_off;
+        for (int k = lane; 2 * k < q.plan_n; k += 32) {
+          const float4 a = gp[2 * k], b = gp[min(2 * k + 1, q.plan_n - 1)];
+          S.plan_xy[warp][k] = make_float4(a.x, a.y, b.x, b.y);
+          S.plan_z[warp][k] = make_float2(a.z, b.z);
+        }
       }
       __syncwarp();
     }
@@ -1451,7 +1449,8 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0,
           float pw[3];
 #pragma unroll
           for (int a = 0; a < 3; ++a) pw[a] = (float)((W.R0[a * 3] * (double)pz.x + W.R0[a * 3 + 1] * (double)pz.y) + W.t0[a]);
-          d2 = plan_nn_d2(W.plan, W.plan_n, pw[0], pw[1], pw[2]);
+          d2 = W.plan_n <= kPlanWarp ? plan_nn_d2_pairs(S.plan_xy[warp], S.plan_z[warp], (W.plan_n + 1) >> 1, pw[0], pw[1], pw[2])
+                                     : plan_nn_d2(W.plan, W.plan_n, pw[0], pw[1], pw[2]);
         }
         const float sq = lpm::fsqrt(d2);
         if (fl & kNeedStick) {
