@@ -190,7 +190,8 @@ def load_library(path: str | None = None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    # B200LP_LIB: run everything against another build of the SAME sources (A/B builds of tools/variants); still CUDA only
+    p = path or os.environ.get("B200LP_LIB") or LIB_PATH
     if not os.path.exists(p):
         raise ImportError(
             f"{p} not found: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()'). "

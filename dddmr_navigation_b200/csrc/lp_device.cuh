@@ -534,6 +534,51 @@ struct SweepGrid {
 #else
 #define B200LP_SWEEP_ATTR __noinline__
 #endif
+// How the sweep gets its candidate points (A/B builds; DESIGN.md §4.1 holds the measurements):
+//   0  every lane loads its point of the current 32-candidate round with __ldg, then tests it;
+//   1  the same, software-pipelined: the loads of the NEXT round are issued before the current one is tested;
+//   2  bulk-asynchronous staging: one lane issues cp.async.bulk (the TMA unit's 1-D copy: a candidate run is ONE contiguous
+//      range of float4) of the next <= 64 candidates into a two-deep per-warp ring in shared memory, completion signalled
+//      through an mbarrier (complete_tx); the warp tests the current chunk out of shared memory meanwhile.
+#ifndef B200LP_STREAM
+#define B200LP_STREAM 0
+#endif
+constexpr int kRingPoints = 64;  // candidates per bulk copy (1 KB)
+struct alignas(16) SweepRing {   // per warp
+  float4 buf[2][kRingPoints];
+  unsigned long long bar[2];
+};
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ring_init(SweepRing* r, int lane) {
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&r->bar[0])) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&r->bar[1])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+}
+// one lane: announce `bytes` to the slot's barrier and start the bulk copy global -> shared
+__device__ __forceinline__ void ring_issue(SweepRing* r, int slot, const float4* src, uint32_t n_points) {
+  const uint32_t bytes = n_points * 16u, bar = smem_addr(&r->bar[slot]);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(&r->buf[slot][0])),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void ring_wait(SweepRing* r, int slot, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "RING_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra RING_DONE;\n"
+      "bra RING_WAIT;\n"
+      "RING_DONE:\n"
+      "}\n" ::"r"(smem_addr(&r->bar[slot])),
+      "r"(parity)
+      : "memory");
+}
+
 // packed 2 x fp32 arithmetic (FFMA2): only ever used by the conservative pre-test, whose rounding does not matter
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pack2(float lo, float hi) {
@@ -550,7 +595,7 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
 
 template <bool kMinMax>
 __device__ B200LP_SWEEP_ATTR unsigned sweep_points(const SweepGrid g, const float* stash, const float4* pre, int col0,
-                                                   int lane, const CellBox ub) {
+                                                   int lane, const CellBox ub, SweepRing* ring, unsigned& ring_state) {
   if (ub.x0 > ub.x1) return 0u;
   const int nyr = ub.y1 - ub.y0 + 1;
   const int nrows = nyr * (ub.z1 - ub.z0 + 1);
@@ -620,6 +665,77 @@ __device__ B200LP_SWEEP_ATTR unsigned sweep_points(const SweepGrid g, const floa
 #else
 #define B200LP_COUNT_FLUSH() do { } while (0)
 #endif
+  // One 32-candidate round: pre-test, and — rarely — the exact decision. Returns true when the group's lowest pose
+  // collides (nothing can precede it: the sweep is over).
+  auto test_round = [&](const float4 p, uint32_t n_valid) -> bool {
+#if B200LP_COUNT
+    c_cand += (unsigned long long)n_valid * (unsigned long long)__popc(alive);  // (candidate, pose) pre-tests
+    c_rounds += 1ull;
+#else
+    (void)n_valid;
+#endif
+    bool any = false;
+    if (kMinMax) {
+#pragma unroll
+      for (int q = 0; q < kGroup; ++q)
+        any |= (p.x >= ca[q].x) & (p.x <= cb[q].x) & (p.y >= ca[q].y) & (p.y <= cb[q].y) & (p.z >= ca[q].z) & (p.z <= cb[q].z);
+    } else {
+      // conservative superset of the exact test: |v' - v| <= delta
+      const float tz = __fmaf_rn(p.x, ax_z, __fmaf_rn(p.y, ay_z, __fmaf_rn(p.z, az_z, -zc)));
+      const f32x2 px = pack2(p.x, p.x), py = pack2(p.y, p.y), pz = pack2(p.z, p.z);
+#pragma unroll
+      for (int q = 0; q < kGroup; ++q) {
+        float vx, vy;
+        unpack2(fma2(px, c0[q], fma2(py, c1[q], fma2(pz, c2[q], c3[q]))), vx, vy);
+        any |= (fabsf(vx) <= hx) & (fabsf(vy) <= hy);
+      }
+      any &= fabsf(tz) <= zr;
+    }
+    if (!__any_sync(kFull, any)) return false;
+    // rare: find the poses concerned and decide with the reference's own arithmetic
+#pragma unroll 1
+    for (int q = 0; q < kGroup; ++q) {
+      if (!((alive >> q) & 1u)) continue;  // (warp-uniform)
+      const int col = col0 + q;
+      bool in;
+      if (kMinMax) {
+        in = exact_in_aabb(stash, col, p.x, p.y, p.z);
+      } else {
+        const float4 p0 = pre[col * kPreStride + 0];
+        const float4 p1 = pre[col * kPreStride + 1];
+        const float vx = __fmaf_rn(p.x, p0.x, __fmaf_rn(p.y, p0.z, __fmaf_rn(p.z, p1.x, p1.z)));
+        const float vy = __fmaf_rn(p.x, p0.y, __fmaf_rn(p.y, p0.w, __fmaf_rn(p.z, p1.y, p1.w)));
+        in = any & (fabsf(vx) <= hx) & (fabsf(vy) <= hy);
+        if (__any_sync(kFull, in)) in = in && exact_in_box(stash, col, p.x, p.y, p.z);
+      }
+      if (in && exact_in_radius(stash, col, p.x, p.y, p.z)) hit |= 1u << q;
+    }
+#if B200LP_COUNT
+    c_exact += (unsigned long long)__popc(__ballot_sync(kFull, any));
+#endif
+    const unsigned wh = __reduce_or_sync(kFull, hit);
+    if (wh & 1u) return true;
+    if (wh) {
+      alive &= (wh & (0u - wh)) - 1u;
+      if (!kMinMax) {
+#pragma unroll
+        for (int q = 1; q < kGroup; ++q)
+          if (!((alive >> q) & 1u)) c3[q] = never;
+      } else {
+#pragma unroll
+        for (int q = 1; q < kGroup; ++q)
+          if (!((alive >> q) & 1u)) ca[q].x = 3.402823466e+38f;
+      }
+    }
+    return false;
+  };
+
+  constexpr uint32_t kChunk = B200LP_STREAM == 2 ? (uint32_t)kRingPoints : 32u;  // candidates fetched at a time
+#if B200LP_STREAM == 2
+  int slot = (int)(ring_state >> 2) & 1;  // ring_state: bit 0 / 1 = phase parity of barrier 0 / 1, bit 2 = slot to fill next
+#else
+  (void)ring; (void)ring_state;
+#endif
   for (int r0 = 0; r0 < nrows; r0 += 32) {
     const int r = r0 + lane;
     uint32_t beg = 0, end = 0;
@@ -635,73 +751,59 @@ __device__ B200LP_SWEEP_ATTR unsigned sweep_points(const SweepGrid g, const floa
       end = __ldg(g.cell_start + base + ub.x1 + 1);
     }
     unsigned rows = __ballot_sync(kFull, beg < end);
-    while (rows) {
+    // cursor over the chunks of these rows, one chunk ahead of the tests (all warp-uniform)
+    uint32_t nj = 0u, ne = 0u;
+    auto advance = [&]() -> bool {
+      if (nj + kChunk < ne) { nj += kChunk; return true; }
+      if (!rows) return false;
       const int src = __ffs(rows) - 1;
       rows &= rows - 1;
-      const uint32_t b = __shfl_sync(kFull, beg, src), e = __shfl_sync(kFull, end, src);
-      for (uint32_t j0 = b; j0 < e; j0 += 32) {  // warp-uniform trip count
-        // lanes past the end of the row look at its last point again: no divergence, and a duplicate cannot change an any-hit
-        const float4 p = __ldg(g.pts + min(j0 + lane, e - 1u));
-#if B200LP_COUNT
-        c_cand += (unsigned long long)min(32u, e - j0) * (unsigned long long)__popc(alive);  // (candidate, pose) pre-tests
-        c_rounds += 1ull;
+      nj = __shfl_sync(kFull, beg, src);
+      ne = __shfl_sync(kFull, end, src);
+      return true;
+    };
+    bool more = advance();
+#if B200LP_STREAM == 1
+    float4 pn = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (more) pn = __ldg(g.pts + min(nj + lane, ne - 1u));
+#elif B200LP_STREAM == 2
+    if (more && lane == 0) ring_issue(ring, slot, g.pts + nj, min(kChunk, ne - nj));
 #endif
-        bool any = false;
-        if (kMinMax) {
-#pragma unroll
-          for (int q = 0; q < kGroup; ++q)
-            any |= (p.x >= ca[q].x) & (p.x <= cb[q].x) & (p.y >= ca[q].y) & (p.y <= cb[q].y) & (p.z >= ca[q].z) & (p.z <= cb[q].z);
-        } else {
-          // conservative superset of the exact test: |v' - v| <= delta
-          const float tz = __fmaf_rn(p.x, ax_z, __fmaf_rn(p.y, ay_z, __fmaf_rn(p.z, az_z, -zc)));
-          const f32x2 px = pack2(p.x, p.x), py = pack2(p.y, p.y), pz = pack2(p.z, p.z);
-#pragma unroll
-          for (int q = 0; q < kGroup; ++q) {
-            float vx, vy;
-            unpack2(fma2(px, c0[q], fma2(py, c1[q], fma2(pz, c2[q], c3[q]))), vx, vy);
-            any |= (fabsf(vx) <= hx) & (fabsf(vy) <= hy);
-          }
-          any &= fabsf(tz) <= zr;
+    while (more) {
+      const uint32_t j0 = nj, e = ne;
+      const uint32_t cnt = min(kChunk, e - j0);
+      more = advance();
+#if B200LP_STREAM == 0
+      // lanes past the end of the row look at its last point again: no divergence, and a duplicate cannot change an any-hit
+      if (test_round(__ldg(g.pts + min(j0 + lane, e - 1u)), cnt)) { B200LP_COUNT_FLUSH(); return __reduce_or_sync(kFull, hit); }
+#elif B200LP_STREAM == 1
+      const float4 p = pn;
+      if (more) pn = __ldg(g.pts + min(nj + lane, ne - 1u));  // in flight while this round is tested
+      if (test_round(p, cnt)) { B200LP_COUNT_FLUSH(); return __reduce_or_sync(kFull, hit); }
+#else
+      if (more && lane == 0) ring_issue(ring, slot ^ 1, g.pts + nj, min(kChunk, ne - nj));  // in flight while this chunk is tested
+      ring_wait(ring, slot, (ring_state >> slot) & 1u);
+      ring_state ^= 1u << slot;
+      bool over = false;
+      for (uint32_t o = 0; o < cnt && !over; o += 32) over = test_round(ring->buf[slot][min(o + lane, cnt - 1u)], min(32u, cnt - o));
+      __syncwarp();  // every lane has read the slot before it is filled again
+      slot ^= 1;
+      if (over) {
+        if (more) {  // the copy already under way must land before the ring is used again
+          ring_wait(ring, slot, (ring_state >> slot) & 1u);
+          ring_state ^= 1u << slot;
+          slot ^= 1;
         }
-        if (__any_sync(kFull, any)) {  // rare: find the poses concerned and decide with the reference's own arithmetic
-#pragma unroll 1
-          for (int q = 0; q < kGroup; ++q) {
-            if (!((alive >> q) & 1u)) continue;  // (warp-uniform)
-            const int col = col0 + q;
-            bool in;
-            if (kMinMax) {
-              in = exact_in_aabb(stash, col, p.x, p.y, p.z);
-            } else {
-              const float4 p0 = pre[col * kPreStride + 0];
-              const float4 p1 = pre[col * kPreStride + 1];
-              const float vx = __fmaf_rn(p.x, p0.x, __fmaf_rn(p.y, p0.z, __fmaf_rn(p.z, p1.x, p1.z)));
-              const float vy = __fmaf_rn(p.x, p0.y, __fmaf_rn(p.y, p0.w, __fmaf_rn(p.z, p1.y, p1.w)));
-              in = any & (fabsf(vx) <= hx) & (fabsf(vy) <= hy);
-              if (__any_sync(kFull, in)) in = in && exact_in_box(stash, col, p.x, p.y, p.z);
-            }
-            if (in && exact_in_radius(stash, col, p.x, p.y, p.z)) hit |= 1u << q;
-          }
-#if B200LP_COUNT
-          c_exact += (unsigned long long)__popc(__ballot_sync(kFull, any));
-#endif
-          const unsigned wh = __reduce_or_sync(kFull, hit);
-          if (wh & 1u) { B200LP_COUNT_FLUSH(); return wh; }  // the lowest pose of the group collides: nothing can precede it
-          if (wh) {
-            alive &= (wh & (0u - wh)) - 1u;
-            if (!kMinMax) {
-#pragma unroll
-              for (int q = 1; q < kGroup; ++q)
-                if (!((alive >> q) & 1u)) c3[q] = never;
-            } else {
-#pragma unroll
-              for (int q = 1; q < kGroup; ++q)
-                if (!((alive >> q) & 1u)) ca[q].x = 3.402823466e+38f;
-            }
-          }
-        }
+        ring_state = (ring_state & 3u) | ((unsigned)slot << 2);
+        B200LP_COUNT_FLUSH();
+        return __reduce_or_sync(kFull, hit);
       }
+#endif
     }
   }
+#if B200LP_STREAM == 2
+  ring_state = (ring_state & 3u) | ((unsigned)slot << 2);
+#endif
   B200LP_COUNT_FLUSH();
   return __reduce_or_sync(kFull, hit);
 }

@@ -1188,6 +1188,9 @@ struct CtaShared {
   int scored[kWarpsPerCta];               // trajectories / poses each warp scored (single-robot launches)
   long long poses_scored[kWarpsPerCta];
   unsigned cls_first[kCostClasses + 1];   // first work index of every cost class; [kCostClasses] = number of work items
+#if B200LP_STREAM == 2
+  SweepRing ring[kWarpsPerCta];           // bulk-copy staging of the candidate stream (lp_device.cuh)
+#endif
 };
 
 // lanes that head a group of kGroup consecutive stash columns
@@ -1215,6 +1218,13 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0,
   float* stash = S.stash[warp];
   float4* pre = S.pre[warp];
   WarpCtx& W = S.wc[warp];
+  unsigned ring_state = 0u;
+#if B200LP_STREAM == 2
+  SweepRing* ring = &S.ring[warp];
+  ring_init(ring, lane);
+#else
+  SweepRing* ring = nullptr;
+#endif
   // Work space: the class lists cull_kernel filled, most expensive class first; position w of the concatenation is entry
   // w - cls_first[k] of list k.
   if (threadIdx.x == 0) {
@@ -1405,8 +1415,8 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0,
             const int* gb = W.gbox[col0 / kGroup];
             const CellBox ub = {gb[0], gb[1], gb[2], gb[3], gb[4], gb[5]};
             const SweepGrid sg = {g.pts, g.cell_start, g.nx, g.ny, g.cmax};
-            const unsigned h = kind ? sweep_points<true>(sg, stash, pre, col0, lane, ub)
-                                    : sweep_points<false>(sg, stash, pre, col0, lane, ub);
+            const unsigned h = kind ? sweep_points<true>(sg, stash, pre, col0, lane, ub, ring, ring_state)
+                                    : sweep_points<false>(sg, stash, pre, col0, lane, ub, ring, ring_state);
             if (h) {
               const int hp = (int)list[col0 + (__ffs(h) - 1)];
               if (kind) hit_mm = hp; else hit_box = hp;
