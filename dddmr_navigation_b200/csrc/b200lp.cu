@@ -170,8 +170,8 @@ struct b200lp_ctx {
   DevBuf<unsigned> d_tickets;            // prep_kernel chunk tickets, one per robot (self-resetting)
   DevBuf<PrepAgg> d_aggs;                // prep_kernel look-back aggregates
   DevBuf<unsigned long long> d_work;     // plan_kernel work counter (reset by argmin_kernel)
-  DevBuf<uint32_t> d_surv;               // cull_kernel: one bit per row of d_poses — does the pose survive the float pre-cull?
-  DevBuf<int> d_order;                   // classify_kernel: the work lists of the cycle, one per cost class (kCostClasses x T entries)
+  DevBuf<uint32_t> d_surv;               // cull_kernel: per trajectory, the mask of the poses that survive the float pre-cull
+  DevBuf<int> d_order;                   // ... and the work lists of the cycle, one per cost class (kCostClasses x T entries)
   DevBuf<unsigned> d_class_counts;       // entries per list (zeroed by prep_kernel)
   DevBuf<unsigned long long> d_tstart;   // globaltimer at the start of the cycle (prep_kernel's first CTA)
   bool plan_uploaded = false;            // d_plan7 already holds the host plan (b200lp_set_plan uploads it)
@@ -615,7 +615,7 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   CK(ctx->d_poses.reserve((size_t)pose_stride * n_robots));
   CK(ctx->d_rec_pose_off.reserve(T));
   if (T > 0x7fffffffull) return ctx->fail(B200LP_E_INVALID, "plan: %zu robots x %d trajectories exceed the work-list index range", n_robots, t_cap);
-  CK(ctx->d_surv.reserve((size_t)pose_stride * n_robots / 32 + 2));
+  CK(ctx->d_surv.reserve(T * (size_t)(((int)max_steps_bound(ctx->C.lim, ctx->C.par) + 31) / 32)));
   CK(ctx->d_order.reserve(T * (size_t)kCostClasses));
   int want_pp = 0;
   for (int k = 0; k < ctx->C.n_critics; ++k) want_pp |= ctx->C.critics[k].kind == B200LP_CRITIC_PURE_PURSUIT;
@@ -711,10 +711,10 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
     CK(cudaEventRecord(ctx->ev[6], ctx->stream));  // cull_kernel's start on the main stream (after the grid build)
   }
   // the float pre-cull of every pose (needs the grid) and the work lists plan_kernel drains
-  cull_kernel<<<dim3((unsigned)(pose_stride / kCullThreads), (unsigned)n_robots), kCullThreads, 0, ctx->stream>>>(
-      ctx->C, ctx->grid, ctx->d_robots.p, q0, by_value, ctx->d_meta.p, ctx->d_poses.p, pose_stride, ctx->d_surv.p);
-  classify_kernel<<<dim3((unsigned)((t_cap + kCullThreads - 1) / kCullThreads), (unsigned)n_robots), kCullThreads, 0, ctx->stream>>>(
-      ctx->d_meta.p, t_cap, ctx->d_rec_steps.p, ctx->d_rec_pose_off.p, ctx->d_surv.p, ctx->d_order.p, T, ctx->d_class_counts.p);
+  const int mask_stride = ((int)max_steps_bound(ctx->C.lim, ctx->C.par) + 31) / 32;
+  cull_kernel<<<dim3((unsigned)((t_cap + kCullTraj - 1) / kCullTraj), (unsigned)n_robots), kCullThreads, 0, ctx->stream>>>(
+      ctx->C, ctx->grid, ctx->d_robots.p, q0, by_value, ctx->d_meta.p, t_cap, ctx->d_rec_steps.p, ctx->d_rec_pose_off.p,
+      ctx->d_poses.p, ctx->d_surv.p, mask_stride, ctx->d_order.p, T, ctx->d_class_counts.p);
   CK(cudaEventRecord(ctx->ev[7], ctx->stream));
   PeerExchange px{};
   px.t_start = ctx->d_tstart.p;
@@ -731,7 +731,8 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
       ctx->C, ctx->grid, ctx->d_robots.p, q0, by_value, ctx->d_meta.p, (int)n_robots, t_cap, ctx->d_rec_vel.p,
       ctx->d_rec_steps.p, ctx->d_rec_pose_off.p, ctx->d_poses.p, ctx->d_rec_pp.p, ctx->d_plan_pts.p, ctx->d_cost.p,
       ctx->d_scores.p, ctx->d_first_hit.p, ctx->d_work.p, ctx->d_partial.p, ctx->d_tickets2.p, ctx->d_results.p,
-      direct ? ctx->h_direct.p : nullptr, ctx->direct_seq, px, ctx->d_surv.p, ctx->d_order.p, T, ctx->d_class_counts.p);
+      direct ? ctx->h_direct.p : nullptr, ctx->direct_seq, px, ctx->d_surv.p, mask_stride, ctx->d_order.p, T,
+      ctx->d_class_counts.p);
   CK(cudaEventRecord(ctx->ev[5], ctx->stream));
   if (n_robots > 1) {  // a single robot's argmin is folded into plan_kernel
     argmin_kernel<<<dim3((unsigned)argmin_ctas, (unsigned)n_robots), kArgminThreads, 0, ctx->stream>>>(
@@ -739,7 +740,7 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
         ctx->d_tickets2.p, ctx->d_results.p, ctx->d_work.p);
     ++ctx->launches;
   }
-  ctx->launches += 4;
+  ctx->launches += 3;
   CK(cudaEventRecord(ctx->ev[2], ctx->stream));
   ctx->have_cycle_event = true;
   if (n_robots == 1)  // for the read-back kernels (poses_kernel, count_radius_kernel); off the cycle's critical path

@@ -1014,17 +1014,17 @@ __global__ void __launch_bounds__(32) share_ack_kernel(char* root_base, int rank
 }
 
 // =============================================================================================
-// cull + classify: the float pre-cull of every pose, pose-parallel, in front of plan_kernel.
-// cull_kernel — one thread per pose ROW of the cycle's pose array (rows of a robot are dense: trajectories back to back):
-// a conservative box around the pose's candidate box (loose_box) and one look at the summed-volume table; poses whose box
-// holds no cloud point cannot collide (about 6 of 10 at C2) and never reach the double-precision geometry. One bit per
-// row: bit (row & 31) of word (row >> 5) of `surv`, rows numbered like d_poses (robot * pose_stride + row, pose_stride a
-// multiple of 256).
-// classify_kernel — one thread per trajectory: counts the surviving poses of its rows and appends the trajectory to the
-// work list of its cost class. Trajectories are visited from the END of the list (longest rollouts first), so every
-// class list starts with its longest members.
+// cull: the float pre-cull of every pose and the work lists of the cycle, in front of plan_kernel.
+// A CTA takes kCullTraj consecutive trajectories of one robot — their pose rows are one contiguous range of the cycle's pose
+// array — and gives every row a thread: a conservative box around the pose's candidate box (loose_box) and one look at the
+// summed-volume table; poses whose box holds no cloud point cannot collide (about 6 of 10 at C2) and never reach the
+// double-precision geometry. The survivor bits of the range are collected in shared memory; one thread per trajectory then
+// cuts its bits out (`surv`: mask_stride words per trajectory, bit k = pose k survives), counts them and appends the
+// trajectory to the work list of its cost class. Trajectories are visited from the END of the list (longest rollouts first),
+// so every class list starts with its longest members.
 // =============================================================================================
 constexpr int kCullThreads = 256;
+constexpr int kCullTraj = 32;
 #ifndef B200LP_PRECULL
 #define B200LP_PRECULL 1  // 0: every pose goes through the double-precision geometry (A/B builds, tools/time_variants.py)
 #endif
@@ -1053,13 +1053,29 @@ __device__ __forceinline__ bool box_has_points(const GridDev& g, const float* lo
 
 __global__ void __launch_bounds__(kCullThreads)
 cull_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0, int by_value, const RobotMeta* __restrict__ meta,
-            const float4* __restrict__ poses, long long pose_stride, uint32_t* __restrict__ surv) {
+            int t_cap, const int* __restrict__ rec_steps, const long long* __restrict__ rec_pose_off,
+            const float4* __restrict__ poses, uint32_t* __restrict__ surv, int mask_stride, int* __restrict__ order,
+            size_t order_stride, unsigned* __restrict__ class_counts) {
+  constexpr int kBitWords = kCullTraj * (B200LP_MAX_STEPS / 32) + 1;
   __shared__ float s_R0f[9], s_t0f[3];
+  __shared__ long long s_off[kCullTraj];
+  __shared__ int s_n[kCullTraj];
+  __shared__ uint32_t s_bits[kBitWords];
+  __shared__ unsigned s_cnt[kCostClasses], s_base[kCostClasses];
   const int robot = blockIdx.y;
-  const long long n_rows = min(meta[robot].n_poses, pose_stride);
-  const long long row0 = (long long)blockIdx.x * kCullThreads;
-  if (row0 >= n_rows) return;  // (whole CTA)
-  if (threadIdx.x == 0) {
+  const RobotMeta m = meta[robot];
+  const int n_local = min(m.t_end, t_cap) - m.t_begin;
+  const int first = (int)blockIdx.x * kCullTraj;
+  if (first >= n_local) return;  // (whole CTA)
+  const int cnt = min(kCullTraj, n_local - first);
+  const int id_lo = m.t_begin + (n_local - first - cnt);  // the CTA's trajectories, ascending ids id_lo .. id_lo + cnt - 1
+  const int tid = threadIdx.x;
+  if (tid < cnt) {
+    const size_t rec = (size_t)robot * t_cap + id_lo + tid;
+    s_off[tid] = rec_pose_off[rec];
+    s_n[tid] = rec_steps[rec];
+  }
+  if (tid == 32) {  // (another warp than the one that loads the offsets)
     const RobotIn& q = by_value ? q0 : robots[robot];
     double R0[9];
     quat_to_matrix(q.pose[3], q.pose[4], q.pose[5], q.pose[6], R0);
@@ -1068,62 +1084,48 @@ cull_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0,
 #pragma unroll
     for (int a = 0; a < 3; ++a) s_t0f[a] = (float)q.pose[a];
   }
+  if (tid < kCostClasses) s_cnt[tid] = 0u;
   __syncthreads();
-  const long long row = row0 + threadIdx.x;
-  const long long grow = (long long)robot * pose_stride + row;
-  bool keep = false;
-  if (row < n_rows) {
+  // the rows of the cycle's pose array these trajectories occupy (prep_kernel lays trajectories out back to back)
+  const long long row0 = s_off[0];
+  const int n_rows = (int)min((long long)(kBitWords - 1) * 32, s_off[cnt - 1] + s_n[cnt - 1] - row0);
+  for (int r = tid; r < ((n_rows + 31) & ~31); r += kCullThreads) {
+    bool keep = false;
+    if (r < n_rows) {
 #if B200LP_PRECULL
-    const float4 pz = __ldg(poses + grow);
-    float lo[3], hi[3];
-    loose_box(C, g, s_R0f, s_t0f, pz.x, pz.y, pz.z, lo, hi);
-    keep = box_has_points(g, lo, hi);
+      const float4 pz = __ldg(poses + row0 + r);
+      float lo[3], hi[3];
+      loose_box(C, g, s_R0f, s_t0f, pz.x, pz.y, pz.z, lo, hi);
+      keep = box_has_points(g, lo, hi);
 #else
-    keep = true;
+      keep = true;
 #endif
+    }
+    const unsigned mk = __ballot_sync(kFull, keep);
+    if ((tid & 31) == 0) s_bits[r >> 5] = mk;
   }
-  const unsigned mk = __ballot_sync(kFull, keep);
-  if ((threadIdx.x & 31) == 0) surv[grow >> 5] = mk;
-}
-
-// the surviving poses among rows [off, off + n)
-__device__ __forceinline__ int count_survivors(const uint32_t* __restrict__ surv, long long off, int n) {
-  int total = 0;
-  long long b = off;
-  const long long end = off + n;
-  while (b < end) {
-    const int lo = (int)(b & 31);
-    const int take = (int)min((long long)(32 - lo), end - b);
-    const unsigned mask = (take == 32 ? 0xffffffffu : ((1u << take) - 1u)) << lo;
-    total += __popc(__ldg(surv + (b >> 5)) & mask);
-    b += take;
-  }
-  return total;
-}
-
-__global__ void __launch_bounds__(kCullThreads)
-classify_kernel(const RobotMeta* __restrict__ meta, int t_cap, const int* __restrict__ rec_steps,
-                const long long* __restrict__ rec_pose_off, const uint32_t* __restrict__ surv, int* __restrict__ order,
-                size_t order_stride, unsigned* __restrict__ class_counts) {
-  __shared__ unsigned s_cnt[kCostClasses], s_base[kCostClasses];
-  const int robot = blockIdx.y;
-  const RobotMeta m = meta[robot];
-  const int n_local = min(m.t_end, t_cap) - m.t_begin;
-  if ((int)blockIdx.x * kCullThreads >= n_local) return;  // (whole CTA)
-  if (threadIdx.x < kCostClasses) s_cnt[threadIdx.x] = 0u;
+  if (tid == 0) s_bits[(n_rows + 31) >> 5] = 0u;  // (the word behind the last one is read by the funnel shifts below)
   __syncthreads();
-  const int idx = (int)blockIdx.x * kCullThreads + threadIdx.x;
   int cls = -1, rec_i = 0;
   unsigned pos = 0u;
-  if (idx < n_local) {
-    const int id = m.t_begin + (n_local - 1 - idx);
-    const size_t rec = (size_t)robot * t_cap + id;
-    cls = cost_class(count_survivors(surv, rec_pose_off[rec], rec_steps[rec]));
+  if (tid < cnt) {
+    const size_t rec = (size_t)robot * t_cap + id_lo + tid;
+    const int b0 = (int)(s_off[tid] - row0), n = s_n[tid];
+    int total = 0;
+    for (int w = 0; w * 32 < n; ++w) {
+      const int b = b0 + w * 32;
+      unsigned mk = 0u;
+      if (b < n_rows) mk = __funnelshift_r(s_bits[b >> 5], s_bits[(b >> 5) + 1], (unsigned)(b & 31));
+      if (n - w * 32 < 32) mk &= (1u << (n - w * 32)) - 1u;  // (the rows behind belong to the next trajectory)
+      surv[rec * (size_t)mask_stride + w] = mk;
+      total += __popc(mk);
+    }
+    cls = cost_class(total);
     rec_i = (int)rec;
     pos = atomicAdd(&s_cnt[cls], 1u);
   }
   __syncthreads();
-  if (threadIdx.x < kCostClasses && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(class_counts + threadIdx.x, s_cnt[threadIdx.x]);
+  if (tid < kCostClasses && s_cnt[tid]) s_base[tid] = atomicAdd(class_counts + tid, s_cnt[tid]);
   __syncthreads();
   if (cls >= 0) order[(size_t)cls * order_stride + s_base[cls] + pos] = rec_i;
 }
@@ -1211,7 +1213,7 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0,
             double* __restrict__ out_scores, int* __restrict__ out_first_hit,
             unsigned long long* __restrict__ work_counter, BlockBest* partial, unsigned* __restrict__ tickets,
             b200lp_result* __restrict__ results, DirectOut* direct, unsigned long long direct_seq, PeerExchange px,
-            const uint32_t* __restrict__ surv, const int* __restrict__ order, size_t order_stride,
+            const uint32_t* __restrict__ surv, int mask_stride, const int* __restrict__ order, size_t order_stride,
             const unsigned* __restrict__ class_counts) {
   __shared__ CtaShared S;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1365,7 +1367,7 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0,
       }
     }
     // ---- pass 1: obstacle query ------------------------------------------------------------------------
-    // cull_kernel has already looked at every pose in float: `surv` holds, per pose row, whether the pose's
+    // cull_kernel has already looked at every pose in float: `surv` holds, per trajectory, the mask of the poses whose
     // conservative candidate box contains cloud points at all (about 4 of 10 at C2); the others cannot collide. The
     // survivors are queued in ascending pose order; as soon as 32 wait — or the trajectory is exhausted — their cuboids are
     // built with the reference's arithmetic (double precision), and groups of kGroup consecutive survivors are swept
@@ -1378,11 +1380,7 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0,
       int cnt = 0, base = 0;  // survivors waiting / next pose to look at (warp-uniform)
       for (;;) {
         while (cnt < 32 && base < n) {
-          // bits of rows pose_row + base .. + 31 (warp-uniform addresses; the array is padded by two words)
-          const long long b0 = pose_row + base;
-          const uint32_t* wp = surv + (b0 >> 5);
-          unsigned mk = __funnelshift_r(__ldg(wp), __ldg(wp + 1), (unsigned)(b0 & 31));
-          if (n - base < 32) mk &= (1u << (n - base)) - 1u;  // (the rows behind belong to the next trajectory)
+          const unsigned mk = __ldg(surv + rec * (size_t)mask_stride + (base >> 5));  // (warp-uniform address)
           if ((mk >> lane) & 1u) list[cnt + __popc(mk & lt)] = (unsigned short)(base + lane);
           cnt += __popc(mk);
           base += 32;
