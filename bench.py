@@ -922,7 +922,7 @@ def run_observation(env, args, peak):
         wall.append(1e3 * (time.perf_counter() - t0))
         dev.append(oi.ms_device)
         upl.append(oi.ms_upload)
-    passes = (oi.n_launches - 2) // 4
+    passes = (oi.n_launches - 2) // 3
     n_s, n_w, n_o = int(oi.n_scan), int(oi.n_window), int(oi.n_points)
     obs_bytes = 32 * n_s + (16 * n_s + 16 * n_w) + (passes - 1) * 32 * n_w + 16 * n_w + 16 * n_o
     t0 = time.perf_counter()

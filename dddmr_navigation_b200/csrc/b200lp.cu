@@ -90,7 +90,10 @@ struct b200lp_ctx {
   size_t last_h2d_bytes = 0;         // what the last set_cloud* copied host -> device
   DevBuf<char> d_raw;
   DevBuf<float4> d_pts;
-  DevBuf<uint32_t> d_cell_start, d_fill, d_block_sums, d_sat;
+  DevBuf<uint32_t> d_cell_start, d_rank, d_sat;  // d_rank: every point's rank inside its cell (hist_kernel -> scatter_kernel)
+  DevBuf<unsigned long long> d_scan_status;      // scan_kernel: per block {epoch, status, value}
+  DevBuf<unsigned> d_scan_ticket;
+  unsigned scan_epoch = 0;
   DevBuf<float4> d_packed;  // the raw cloud as 16-byte records (x, y, z, original index)
   cudaStream_t copy_stream = nullptr;
   cudaStream_t prep_stream = nullptr;  // prep_kernel runs here while the grid of a cloud just handed over is still being built
@@ -303,8 +306,16 @@ int grid_tail(b200lp_ctx* ctx, const char* rec, size_t rec_stride, size_t n, siz
   GridDev& g = ctx->grid;
   const int nb = (int)((n_cells + kScanItems - 1) / kScanItems);
   CK(ctx->d_cell_start.reserve(n_cells + 1));
-  CK(ctx->d_fill.reserve(n_cells + 1));
-  CK(ctx->d_block_sums.reserve(nb));
+  CK(ctx->d_rank.reserve(std::max<size_t>(n, 1)));
+  if (ctx->d_scan_status.cap < (size_t)nb) {  // (new words carry epoch 0: never the current one)
+    CK(ctx->d_scan_status.reserve(nb));
+    CK(cudaMemsetAsync(ctx->d_scan_status.p, 0, ctx->d_scan_status.cap * sizeof(unsigned long long), ctx->stream));
+  }
+  if (!ctx->d_scan_ticket.p) {
+    CK(ctx->d_scan_ticket.reserve(1));
+    CK(cudaMemsetAsync(ctx->d_scan_ticket.p, 0, sizeof(unsigned), ctx->stream));
+  }
+  if (++ctx->scan_epoch >= (1u << 30)) ctx->scan_epoch = 1u;
   CK(ctx->d_pts.reserve(std::max<size_t>(g.n_kept, 1)));
   const size_t n_sat = ((size_t)g.nx + 1) * ((size_t)g.ny + 1) * ((size_t)g.nz + 1);
   CK(ctx->d_sat.reserve(n_sat));
@@ -324,24 +335,23 @@ int grid_tail(b200lp_ctx* ctx, const char* rec, size_t rec_stride, size_t n, siz
       }
       if (c == kPackChunks - 1) CK(cudaEventRecord(ctx->cev[1], ctx->stream));  // everything has arrived
       if (i1 > i0 && g.n_kept) {
-        hist_kernel<<<grid_blocks(i1 - i0, 256, sms), 256, 0, ctx->stream>>>(rec, rec_stride, i0, i1, g, ctx->d_cell_start.p);
+        hist_kernel<<<grid_blocks(i1 - i0, 256, sms), 256, 0, ctx->stream>>>(rec, rec_stride, i0, i1, g, ctx->d_cell_start.p,
+                                                                              ctx->d_rank.p);
         ++ctx->launches;
       }
     }
   } else if (g.n_kept) {
-    hist_kernel<<<grid_blocks(n, 256, sms), 256, 0, ctx->stream>>>(rec, rec_stride, 0, n, g, ctx->d_cell_start.p);
+    hist_kernel<<<grid_blocks(n, 256, sms), 256, 0, ctx->stream>>>(rec, rec_stride, 0, n, g, ctx->d_cell_start.p, ctx->d_rank.p);
     ++ctx->launches;
   }
   if (g.n_kept) {
-    scan_block_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_cell_start.p, n_cells, ctx->d_block_sums.p);
-    scan_sums_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_block_sums.p, nb, ctx->d_total.p);
-    scan_add_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_cell_start.p, n_cells, ctx->d_block_sums.p, ctx->d_total.p,
-                                                 ctx->d_fill.p);
-    scatter_kernel<<<grid_blocks(n, 256, sms), 256, 0, ctx->stream>>>(rec, rec_stride, n, g, ctx->d_fill.p, ctx->d_pts.p);
+    scan_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_cell_start.p, n_cells, ctx->d_scan_status.p, ctx->d_scan_ticket.p,
+                                             ctx->scan_epoch, ctx->d_total.p);
+    scatter_kernel<<<grid_blocks(n, 256, sms), 256, 0, ctx->stream>>>(rec, rec_stride, n, g, ctx->d_rank.p, ctx->d_pts.p);
     const size_t ny_threads = ((size_t)g.nx + 1) * (size_t)g.nz, nz_threads = ((size_t)g.nx + 1) * ((size_t)g.ny + 1);
     sat_y_kernel<<<(unsigned)((ny_threads * 32 + 255) / 256), 256, 0, ctx->stream>>>(g, ctx->d_sat.p);
     sat_z_kernel<<<(unsigned)((nz_threads + 255) / 256), 256, 0, ctx->stream>>>(g, ctx->d_sat.p);
-    ctx->launches += 6;
+    ctx->launches += 4;
   }
   CK(cudaGetLastError());
   ctx->have_cloud = true;
@@ -907,8 +917,8 @@ void b200lp_destroy(b200lp_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  ctx->d_raw.release(); ctx->d_pts.release(); ctx->d_cell_start.release(); ctx->d_fill.release();
-  ctx->d_packed.release(); ctx->d_block_sums.release(); ctx->d_sat.release(); ctx->d_bounds.release(); ctx->d_total.release();
+  ctx->d_raw.release(); ctx->d_pts.release(); ctx->d_cell_start.release(); ctx->d_rank.release(); ctx->d_scan_status.release(); ctx->d_scan_ticket.release();
+  ctx->d_packed.release(); ctx->d_sat.release(); ctx->d_bounds.release(); ctx->d_total.release();
   ctx->h_bounds.release(); ctx->d_robots.release(); ctx->d_meta.release(); ctx->d_plan7.release();
   ctx->d_plan_pts.release(); ctx->d_rec_vel.release(); ctx->d_rec_steps.release(); ctx->d_rec_sample.release();
   ctx->d_first_hit.release(); ctx->d_rec_dt.release(); ctx->d_cost.release(); ctx->d_scores.release();
@@ -1525,8 +1535,15 @@ int b200lp_sensor_observation(b200lp_ctx* ctx, int sensor, const void* scan, siz
     CK(ctx->d_scan.reserve(n * stride));
     CK(ctx->d_obs_a.reserve(n));
     CK(ctx->d_obs_b.reserve(n));
-    CK(ctx->d_obs_hist.reserve(hist_n));
-    CK(ctx->d_obs_sums.reserve(nbk));
+    CK(ctx->d_obs_hist.reserve(hist_n + 1));
+    if (ctx->d_scan_status.cap < (size_t)nbk) {  // (new words carry epoch 0: never the current one)
+      CK(ctx->d_scan_status.reserve(nbk));
+      CK(cudaMemsetAsync(ctx->d_scan_status.p, 0, ctx->d_scan_status.cap * sizeof(unsigned long long), ctx->stream));
+    }
+    if (!ctx->d_scan_ticket.p) {
+      CK(ctx->d_scan_ticket.reserve(1));
+      CK(cudaMemsetAsync(ctx->d_scan_ticket.p, 0, sizeof(unsigned), ctx->stream));
+    }
     CK(ctx->d_obs_heads.reserve(nbh));
     CK(ctx->d_obs_counts.reserve(2));
     CK(ctx->h_obs_counts.reserve(2));
@@ -1545,15 +1562,16 @@ int b200lp_sensor_observation(b200lp_ctx* ctx, int sensor, const void* scan, siz
         else obs_hist_kernel<kObsItemsSmall><<<nb, kObsThreads, 0, st>>>(src, ctx->d_obs_counts.p, p * bits, bits, ctx->d_obs_hist.p);
         ++launches;
       }
-      scan_block_kernel<<<nbk, 256, 0, st>>>(ctx->d_obs_hist.p, hist_n, ctx->d_obs_sums.p);
-      scan_sums_kernel<<<1, 1024, 0, st>>>(ctx->d_obs_sums.p, (int)nbk, ctx->d_obs_counts.p);  // total = points in the window
+      if (++ctx->scan_epoch >= (1u << 30)) ctx->scan_epoch = 1u;
+      scan_kernel<<<nbk, 256, 0, st>>>(ctx->d_obs_hist.p, hist_n, ctx->d_scan_status.p, ctx->d_scan_ticket.p, ctx->scan_epoch,
+                                       ctx->d_obs_counts.p);  // total = points in the window
       if (large)
         obs_scatter_kernel<kObsItemsLarge><<<nb, kObsThreads, 0, st>>>(src, n, ctx->d_obs_counts.p, p == 0 ? 1 : 0, p * bits, bits,
-                                                                       ctx->d_obs_hist.p, ctx->d_obs_sums.p, dst);
+                                                                       ctx->d_obs_hist.p, dst);
       else
         obs_scatter_kernel<kObsItemsSmall><<<nb, kObsThreads, 0, st>>>(src, n, ctx->d_obs_counts.p, p == 0 ? 1 : 0, p * bits, bits,
-                                                                       ctx->d_obs_hist.p, ctx->d_obs_sums.p, dst);
-      launches += 3;
+                                                                       ctx->d_obs_hist.p, dst);
+      launches += 2;
       std::swap(src, dst);
     }
     obs_heads_kernel<<<nbh, kObsThreads, 0, st>>>(src, ctx->d_obs_counts.p, ctx->d_obs_heads.p);

@@ -125,8 +125,9 @@ __device__ __forceinline__ uint32_t cell_key(const GridDev& g, float3 v) {
 // Records [i0, i1) of `raw` at `stride` bytes: the 16-byte packed records of bounds_pack_kernel, or the 12-byte x,y,z rows
 // of a cloud that was packed on the host (launched per upload chunk then, so it overlaps the rest of the upload).
 __global__ void __launch_bounds__(256) hist_kernel(const char* __restrict__ raw, size_t stride, size_t i0, size_t i1, GridDev g,
-                                                   uint32_t* __restrict__ counts) {
+                                                   uint32_t* __restrict__ counts, uint32_t* __restrict__ rank) {
   const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
   for (size_t w0 = i0 + (size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); w0 < i1; w0 += (size_t)gridDim.x * blockDim.x) {
     const size_t i = w0 + lane;
     uint32_t key = 0xffffffffu;
@@ -134,24 +135,47 @@ __global__ void __launch_bounds__(256) hist_kernel(const char* __restrict__ raw,
       const float3 v = load_xyz(raw, i, stride);
       if (finite3(v)) key = cell_key(g, v);
     }
-    const unsigned peers = __match_any_sync(kFull, key);  // one atomic per distinct cell of the warp (see scatter_kernel)
-    if (lane == __ffs(peers) - 1 && key != 0xffffffffu) atomicAdd(counts + key, (uint32_t)__popc(peers));
+    // Neighbouring points of a cloud mostly fall into the same cell (obstacle surfaces sampled at centimetres, cells of
+    // decimetres), and same-address atomics serialise in L2: the lanes of a warp that share a cell are found with
+    // __match_any_sync and the lowest of them counts all of them with ONE atomic. Its answer — how many points the cell
+    // held before — makes every point's RANK inside its cell; the scatter pass then needs no atomics at all
+    // (slot = cell_start[cell] + rank), and this pass runs per upload piece underneath the rest of the upload.
+    const unsigned peers = __match_any_sync(kFull, key);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0u;
+    if (lane == leader && key != 0xffffffffu) base = atomicAdd(counts + key, (uint32_t)__popc(peers));
+    base = __shfl_sync(kFull, base, leader);
+    if (i < i1) rank[i] = base + (uint32_t)__popc(peers & lt);
   }
 }
 
-// exclusive scan of counts[0..n) in place, three kernels, 2048 items per block
+// exclusive scan of counts[0..n) in place, ONE pass (decoupled look-back, Merrill & Garland): blocks of 2048 items take
+// their place in the order by ticket (so a block only ever waits for blocks that are running), publish their aggregate,
+// walk back over their predecessors' published words 32 at a time until one carries an inclusive prefix, and publish
+// their own. A word is {build epoch : 30, status : 2, value : 32}; the epoch makes last build's words invisible, so
+// nothing is cleared between builds.
 constexpr int kScanItems = 2048;
-__global__ void __launch_bounds__(256) scan_block_kernel(uint32_t* __restrict__ data, size_t n,
-                                                         uint32_t* __restrict__ block_sums) {
+constexpr unsigned long long kScanAggregate = 1ull, kScanPrefix = 2ull;
+__global__ void __launch_bounds__(256) scan_kernel(uint32_t* __restrict__ data, size_t n, unsigned long long* status,
+                                                   unsigned* __restrict__ ticket, unsigned epoch, uint32_t* __restrict__ total_out) {
   __shared__ uint32_t s_warp[8];
-  const size_t base = (size_t)blockIdx.x * kScanItems + (size_t)threadIdx.x * 8;
+  __shared__ unsigned s_block;
+  __shared__ uint32_t s_prefix;
+  if (threadIdx.x == 0) s_block = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const unsigned block = s_block;
+  const size_t base = (size_t)block * kScanItems + (size_t)threadIdx.x * 8;
   uint32_t v[8];
   uint32_t sum = 0;
+  if (base + 8 <= n) {
+    const uint4 a = *reinterpret_cast<const uint4*>(data + base), b = *reinterpret_cast<const uint4*>(data + base + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    v[k] = (base + k < n) ? data[base + k] : 0u;
-    sum += v[k];
+    for (int k = 0; k < 8; ++k) v[k] = (base + k < n) ? data[base + k] : 0u;
   }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sum += v[k];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t incl = sum;
 #pragma unroll
@@ -161,99 +185,90 @@ __global__ void __launch_bounds__(256) scan_block_kernel(uint32_t* __restrict__ 
   }
   if (lane == 31) s_warp[warp] = incl;
   __syncthreads();
-  uint32_t woff = 0;
-  for (int w = 0; w < warp; ++w) woff += s_warp[w];
-  uint32_t run = woff + incl - sum;
+  uint32_t woff = 0, block_sum = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    if (w < warp) woff += s_warp[w];
+    block_sum += s_warp[w];
+  }
+  const unsigned long long tag = (unsigned long long)epoch << 34;
+  if (warp == 0) {
+    volatile unsigned long long* st = status;
+    if (lane == 0) st[block] = tag | ((block == 0 ? kScanPrefix : kScanAggregate) << 32) | block_sum;
+    uint32_t prefix = 0;
+    int hi = (int)block - 1;  // predecessors still to be added
+    while (hi >= 0) {
+      const int j = hi - lane;
+      unsigned long long w = 0ull;
+      if (j >= 0) {
+        do { w = st[j]; } while ((w >> 34) != (unsigned long long)epoch);  // (its block holds a ticket: it is running)
+      }
+      const unsigned is_prefix = __ballot_sync(kFull, j >= 0 && ((w >> 32) & 3ull) == kScanPrefix);
+      const int stop = is_prefix ? __ffs(is_prefix) - 1 : 32;  // nearest predecessor with an inclusive prefix
+      uint32_t part = (j >= 0 && lane <= stop) ? (uint32_t)w : 0u;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(kFull, part, o);
+      prefix += part;
+      if (is_prefix) break;
+      hi -= 32;
+    }
+    if (lane == 0) {
+      if (block != 0) {
+        __threadfence();
+        st[block] = tag | (kScanPrefix << 32) | (unsigned long long)(prefix + block_sum);
+      }
+      s_prefix = prefix;
+      if ((size_t)(block + 1) * kScanItems >= n) {  // the last block: cell_start[n_cells], and the ticket for the next build
+        *total_out = prefix + block_sum;
+        data[n] = prefix + block_sum;
+        *ticket = 0u;
+      }
+    }
+  }
+  __syncthreads();
+  uint32_t run = s_prefix + woff + incl - sum;
+  uint32_t o8[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    if (base + k < n) data[base + k] = run;
+    o8[k] = run;
     run += v[k];
   }
-  if (threadIdx.x == 255) block_sums[blockIdx.x] = woff + incl;
-}
-
-__global__ void __launch_bounds__(1024) scan_sums_kernel(uint32_t* __restrict__ block_sums, int nb,
-                                                         uint32_t* __restrict__ total_out) {
-  __shared__ uint32_t s_warp[32];
-  __shared__ uint32_t s_carry;
-  if (threadIdx.x == 0) s_carry = 0;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int base = 0; base < nb; base += 1024) {
-    const int i = base + threadIdx.x;
-    const uint32_t v = (i < nb) ? block_sums[i] : 0u;
-    uint32_t incl = v;
+  if (base + 8 <= n) {
+    *reinterpret_cast<uint4*>(data + base) = make_uint4(o8[0], o8[1], o8[2], o8[3]);
+    *reinterpret_cast<uint4*>(data + base + 4) = make_uint4(o8[4], o8[5], o8[6], o8[7]);
+  } else {
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(kFull, incl, o);
-      if (lane >= o) incl += t;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    uint32_t woff = 0;
-    for (int w = 0; w < warp; ++w) woff += s_warp[w];
-    const uint32_t carry = s_carry;
-    if (i < nb) block_sums[i] = carry + woff + incl - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) s_carry = carry + woff + incl;
-    __syncthreads();
+    for (int k = 0; k < 8; ++k)
+      if (base + k < n) data[base + k] = o8[k];
   }
-  if (threadIdx.x == 0) *total_out = s_carry;
 }
 
-// adds the block offsets and leaves a second copy of the offsets in `fill` (the scatter pass's slot counters)
-__global__ void __launch_bounds__(256) scan_add_kernel(uint32_t* __restrict__ data, size_t n,
-                                                       const uint32_t* __restrict__ block_sums,
-                                                       const uint32_t* __restrict__ total, uint32_t* __restrict__ fill) {
-  const uint32_t off = block_sums[blockIdx.x];
-  const size_t base = (size_t)blockIdx.x * kScanItems + (size_t)threadIdx.x * 8;
-#pragma unroll
-  for (int k = 0; k < 8; ++k)
-    if (base + k < n) {
-      const uint32_t v = data[base + k] + off;
-      data[base + k] = v;
-      fill[base + k] = v;
-    }
-  if (blockIdx.x == 0 && threadIdx.x == 0) data[n] = *total;  // cell_start[n_cells]
-}
-
-// counting-sort scatter. `fill` holds a copy of the exclusive offsets and is consumed by atomics, so the
-// order of points inside a cell is arbitrary; every consumer is an any-hit or a count.
-// Neighbouring points of a cloud mostly fall into the same cell (obstacle surfaces sampled at centimetres, cells of
-// decimetres), and same-address atomics serialise in L2: the lanes of a warp that share a cell are found with
-// __match_any_sync, the lowest of them reserves slots for all of them with ONE atomic, and the others take their slot from
-// its answer. Four points per thread and trip keep four such round trips in flight.
+// counting-sort scatter: slot = cell_start[cell] + the point's rank inside its cell (hist_kernel). The order of points
+// inside a cell is whatever order the histogram's atomics were served in; every consumer is an any-hit or a count.
 __global__ void __launch_bounds__(256) scatter_kernel(const char* __restrict__ raw, size_t stride, size_t n, GridDev g,
-                                                      uint32_t* __restrict__ fill, float4* __restrict__ out) {
+                                                      const uint32_t* __restrict__ rank, float4* __restrict__ out) {
   constexpr int kU = 4;
   const size_t step = (size_t)gridDim.x * blockDim.x;
-  const int lane = threadIdx.x & 31;
-  const unsigned lt = (1u << lane) - 1u;
-  // warp-uniform trip count: every lane of a warp runs the same trips (the match needs all 32 lanes)
-  for (size_t w0 = (size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); w0 < n; w0 += kU * step) {
+  for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += kU * step) {
     float3 v[kU];
-    uint32_t key[kU], slot[kU];
+    uint32_t slot[kU];
+    bool ok[kU];
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const size_t i = w0 + lane + u * step;
-      key[u] = 0xffffffffu;  // no point / not finite
+    for (int u = 0; u < kU; ++u) {  // independent loads first
+      const size_t i = i0 + u * step;
+      ok[u] = false;
       if (i < n) {
         v[u] = load_xyz(raw, i, stride);
-        if (finite3(v[u])) key[u] = cell_key(g, v[u]);
+        slot[u] = __ldg(rank + i);
+        ok[u] = finite3(v[u]);
       }
     }
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const unsigned peers = __match_any_sync(kFull, key[u]);
-      const int leader = __ffs(peers) - 1;
-      uint32_t base = 0u;
-      if (lane == leader && key[u] != 0xffffffffu) base = atomicAdd(fill + key[u], (uint32_t)__popc(peers));
-      slot[u] = __shfl_sync(kFull, base, leader) + (uint32_t)__popc(peers & lt);
-    }
+    for (int u = 0; u < kU; ++u)
+      if (ok[u]) slot[u] += __ldg(g.cell_start + cell_key(g, v[u]));
 #pragma unroll
     for (int u = 0; u < kU; ++u)
-      if (key[u] != 0xffffffffu)
-        out[slot[u]] = make_float4(v[u].x, v[u].y, v[u].z, __uint_as_float((uint32_t)(w0 + lane + u * step)));  // w = original index
+      if (ok[u]) out[slot[u]] = make_float4(v[u].x, v[u].y, v[u].z, __uint_as_float((uint32_t)(i0 + u * step)));  // w = original index
   }
 }
 

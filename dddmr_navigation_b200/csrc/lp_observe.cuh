@@ -105,8 +105,7 @@ __global__ void __launch_bounds__(kObsThreads) obs_hist_kernel(const float4* __r
 }
 
 // Stable scatter of one radix pass. `hist` holds the block-local exclusive scan of the [digit][cta] counts and
-// `scan_sums` the scanned block totals of that scan (scan_block_kernel / scan_sums_kernel), so the first output slot of
-// (digit, cta) is hist[i] + scan_sums[i / kScanItems]. Warp w of a CTA owns the contiguous sub-tile
+// exclusively scanned in place by scan_kernel, so the first output slot of (digit, cta) is hist[i]. Warp w of a CTA owns the contiguous sub-tile
 // [w * 32 * kItems, (w+1) * 32 * kItems) of the CTA's tile and walks it 32 records at a time: a record's rank among
 // the records of its digit is (same digit in earlier warps) + (same digit earlier in this warp) + (same digit in lower
 // lanes of this row) — the three terms come from a cross-warp scan of per-warp counters, the counter value when the row
@@ -116,7 +115,6 @@ template <int kItems>
 __global__ void __launch_bounds__(kObsThreads) obs_scatter_kernel(const float4* __restrict__ in, size_t n_static,
                                                                   const uint32_t* __restrict__ n_ptr, int first_pass, int shift,
                                                                   int bits, const uint32_t* __restrict__ hist,
-                                                                  const uint32_t* __restrict__ scan_sums,
                                                                   float4* __restrict__ out) {
   __shared__ uint32_t s_wh[kObsThreads / 32][1 << kObsMaxBits];
   const size_t n = first_pass ? n_static : (size_t)*n_ptr;
@@ -153,7 +151,7 @@ __global__ void __launch_bounds__(kObsThreads) obs_scatter_kernel(const float4* 
   // cross-warp exclusive scan per digit, seeded with the (digit, cta) global offset
   for (int b = threadIdx.x; b < nbins; b += kObsThreads) {
     const size_t hi = (size_t)b * gridDim.x + blockIdx.x;
-    uint32_t run = hist[hi] + scan_sums[hi / kScanItems];
+    uint32_t run = hist[hi];
 #pragma unroll
     for (int w = 0; w < kObsThreads / 32; ++w) {
       const uint32_t c = s_wh[w][b];
