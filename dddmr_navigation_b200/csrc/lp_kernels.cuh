@@ -160,7 +160,6 @@ __global__ void __launch_bounds__(256) scan_kernel(uint32_t* __restrict__ data, 
                                                    unsigned* __restrict__ ticket, unsigned epoch, uint32_t* __restrict__ total_out) {
   __shared__ uint32_t s_warp[8];
   __shared__ unsigned s_block;
-  __shared__ uint32_t s_prefix;
   if (threadIdx.x == 0) s_block = atomicAdd(ticket, 1u);
   __syncthreads();
   const unsigned block = s_block;
@@ -192,41 +191,47 @@ __global__ void __launch_bounds__(256) scan_kernel(uint32_t* __restrict__ data, 
     block_sum += s_warp[w];
   }
   const unsigned long long tag = (unsigned long long)epoch << 34;
-  if (warp == 0) {
-    volatile unsigned long long* st = status;
-    if (lane == 0) st[block] = tag | ((block == 0 ? kScanPrefix : kScanAggregate) << 32) | block_sum;
-    uint32_t prefix = 0;
-    int hi = (int)block - 1;  // predecessors still to be added
-    while (hi >= 0) {
-      const int j = hi - lane;
-      unsigned long long w = 0ull;
-      if (j >= 0) {
-        do { w = st[j]; } while ((w >> 34) != (unsigned long long)epoch);  // (its block holds a ticket: it is running)
-      }
-      const unsigned is_prefix = __ballot_sync(kFull, j >= 0 && ((w >> 32) & 3ull) == kScanPrefix);
-      const int stop = is_prefix ? __ffs(is_prefix) - 1 : 32;  // nearest predecessor with an inclusive prefix
-      uint32_t part = (j >= 0 && lane <= stop) ? (uint32_t)w : 0u;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(kFull, part, o);
-      prefix += part;
-      if (is_prefix) break;
-      hi -= 32;
+  volatile unsigned long long* st = status;
+  if (threadIdx.x == 0) st[block] = tag | ((block == 0 ? kScanPrefix : kScanAggregate) << 32) | block_sum;
+  // look back with the whole block: thread t takes predecessor block - 1 - t (256 per trip; up to 256 blocks, i.e. half a
+  // million cells, need ONE trip), every warp sums its lanes down to the nearest inclusive prefix, thread 0 joins the warps
+  __shared__ uint32_t s_part[8];
+  __shared__ int s_found[8];
+  uint32_t prefix = 0;
+  for (int hi = (int)block - 1; hi >= 0; hi -= 256) {
+    const int j = hi - (int)threadIdx.x;
+    unsigned long long w = 0ull;
+    if (j >= 0) {
+      do { w = st[j]; } while ((w >> 34) != (unsigned long long)epoch);  // (its block holds a ticket: it is running)
     }
-    if (lane == 0) {
-      if (block != 0) {
-        __threadfence();
-        st[block] = tag | (kScanPrefix << 32) | (unsigned long long)(prefix + block_sum);
-      }
-      s_prefix = prefix;
-      if ((size_t)(block + 1) * kScanItems >= n) {  // the last block: cell_start[n_cells], and the ticket for the next build
-        *total_out = prefix + block_sum;
-        data[n] = prefix + block_sum;
-        *ticket = 0u;
-      }
+    const unsigned is_prefix = __ballot_sync(kFull, j >= 0 && ((w >> 32) & 3ull) == kScanPrefix);
+    const int stop = is_prefix ? __ffs(is_prefix) - 1 : 32;  // nearest predecessor of this warp with an inclusive prefix
+    uint32_t part = (j >= 0 && lane <= stop) ? (uint32_t)w : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(kFull, part, o);
+    __syncthreads();  // (s_part / s_found of the previous trip have been read)
+    if (lane == 0) { s_part[warp] = part; s_found[warp] = is_prefix ? 1 : 0; }
+    __syncthreads();
+    bool found = false;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {  // (every thread: the same answer, no broadcast needed)
+      if (!found) prefix += s_part[k];
+      found = found || s_found[k];
+    }
+    if (found) break;
+  }
+  if (threadIdx.x == 0) {
+    if (block != 0) {
+      __threadfence();
+      st[block] = tag | (kScanPrefix << 32) | (unsigned long long)(prefix + block_sum);
+    }
+    if ((size_t)(block + 1) * kScanItems >= n) {  // the last block: cell_start[n_cells], and the ticket for the next build
+      *total_out = prefix + block_sum;
+      data[n] = prefix + block_sum;
+      *ticket = 0u;
     }
   }
-  __syncthreads();
-  uint32_t run = s_prefix + woff + incl - sum;
+  uint32_t run = prefix + woff + incl - sum;
   uint32_t o8[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -245,6 +250,9 @@ __global__ void __launch_bounds__(256) scan_kernel(uint32_t* __restrict__ data, 
 
 // counting-sort scatter: slot = cell_start[cell] + the point's rank inside its cell (hist_kernel). The order of points
 // inside a cell is whatever order the histogram's atomics were served in; every consumer is an any-hit or a count.
+// (A cloud arrives in no particular order, so every 16-byte record lands in a sector of its own: the pass is bound by the
+// latency of dependent random accesses, 2 M points take ~33 us. Eight points per thread in block-contiguous tiles were
+// slower, 39 us.)
 __global__ void __launch_bounds__(256) scatter_kernel(const char* __restrict__ raw, size_t stride, size_t n, GridDev g,
                                                       const uint32_t* __restrict__ rank, float4* __restrict__ out) {
   constexpr int kU = 4;
