@@ -12,5 +12,13 @@ enum PlannerState {
   PATH_BLOCKED_WAIT,
   PATH_BLOCKED_REPLANNING
 };
+// the return codes of a recovery behaviour (dddmr_enum_states.h:56-62), same enumerators in the same order
+enum RecoveryState {
+  RECOVERY_BEHAVIOR_NOT_FOUND,
+  INTERRUPT_BY_CANCEL,
+  INTERRUPT_BY_NEW_GOAL,
+  RECOVERY_DONE,
+  RECOVERY_FAIL
+};
 }
 #endif

@@ -11,6 +11,7 @@
 #include "b200lp/plugin_factory.hpp"
 #include "b200lp/session.hpp"
 #include "local_planner/local_planner.h"
+#include "recovery_behaviors/rotate_inplace_behavior.h"
 #include "mpc_critics/b200_models.h"
 #include "trajectory_generators/b200_theories.h"
 
@@ -820,3 +821,120 @@ dddmr_sys_core::PlannerState Local_Planner::computeVelocityCommand(std::string t
 }
 
 }  // namespace local_planner
+
+// =============================================================================================
+// recovery_behaviors::RotateInPlaceBehavior (rotate_inplace_behavior.cpp:137-305)
+// =============================================================================================
+namespace recovery_behaviors {
+
+double yaw_of(double x, double y, double z, double w) {  // tf2::impl::getYaw (tf2/impl/utils.h)
+  const double sqx = x * x, sqy = y * y, sqz = z * z, sqw = w * w;
+  const double sarg = -2 * (x * z - w * y) / (sqx + sqy + sqz + sqw);  // normalization added from urdfom_headers
+  if (sarg <= -0.99999) return -2 * std::atan2(y, x);
+  if (sarg >= 0.99999) return 2 * std::atan2(y, x);
+  return std::atan2(2 * (x * y + w * z), sqw + sqx - sqy - sqz);
+}
+
+double shortest_angular_distance(double from, double to) {  // angles/angles.h: normalize_angle(to - from)
+  const double result = std::fmod((to - from) + M_PI, 2.0 * M_PI);
+  if (result <= 0.0) return result + M_PI;
+  return result - M_PI;
+}
+
+void RotateInPlaceBehavior::initial(const std::shared_ptr<perception_3d::SharedData>& perception_3d,
+                                    const std::shared_ptr<mpc_critics::MPC_Critics_ROS>& mpc_critics,
+                                    const std::shared_ptr<trajectory_generators::Trajectory_Generators_ROS>& trajectory_generators,
+                                    const std::string& trajectory_generator_name, double tolerance, double frequency) {
+  perception_3d_ = perception_3d;
+  mpc_critics_ros_ = mpc_critics;
+  trajectory_generators_ros_ = trajectory_generators;
+  trajectory_generator_name_ = trajectory_generator_name;
+  tolerance_ = tolerance;
+  frequency_ = frequency;
+}
+
+void RotateInPlaceBehavior::getBestTrajectory(const std::string& traj_gen_name, base_trajectory::Trajectory& best_traj) {
+  best_traj.cost_ = -1;  // :82
+  double minimum_cost = 9999999;
+  for (auto& traj : *trajectories_) {
+    mpc_critics_ros_->scoreTrajectory(traj_gen_name, traj);
+    if (traj.cost_ >= 0 && traj.cost_ <= minimum_cost) {  // :92
+      best_traj = traj;
+      minimum_cost = traj.cost_;
+    }
+  }
+}
+
+void RotateInPlaceBehavior::begin(const geometry_msgs::msg::TransformStamped& t, double now_s) {
+  current_angle_ = yaw_of(t.transform.rotation.x, t.transform.rotation.y, t.transform.rotation.z, t.transform.rotation.w);
+  start_angle_ = current_angle_;
+  got_180_ = false;
+  last_valid_control_ = now_s;
+}
+
+RotateInPlaceBehavior::Step RotateInPlaceBehavior::step(const geometry_msgs::msg::TransformStamped& trans_gbl2b,
+                                                        const nav_msgs::msg::Odometry& robot_state, double now_s) {
+  Step s;
+  // :140-142 — the loop condition
+  if (!(!got_180_ || std::fabs(shortest_angular_distance(current_angle_, start_angle_)) > tolerance_)) {
+    s.finished = true;
+    s.got_180 = got_180_;
+    return s;
+  }
+  // :186-193 — aggregateObservations() has run (the embedding code's perception loop); the pose is read
+  current_angle_ = yaw_of(trans_gbl2b.transform.rotation.x, trans_gbl2b.transform.rotation.y, trans_gbl2b.transform.rotation.z,
+                          trans_gbl2b.transform.rotation.w);
+  // :203-219 — the distance left to rotate
+  if (!got_180_) {
+    const double distance_to_180 = std::fabs(shortest_angular_distance(current_angle_, start_angle_ + M_PI));
+    s.dist_left = M_PI + distance_to_180;
+    if (distance_to_180 < tolerance_) got_180_ = true;
+  } else {
+    s.dist_left = std::fabs(shortest_angular_distance(current_angle_, start_angle_));
+  }
+  // :223-239 — open the cycle, queue every trajectory
+  auto tg = trajectory_generators_ros_->getSharedDataPtr();
+  tg->robot_pose_ = trans_gbl2b;
+  tg->robot_state_ = robot_state;
+  trajectory_generators_ros_->initializeTheories_wi_Shared_data();
+  trajectories_ = std::make_shared<std::vector<base_trajectory::Trajectory>>();
+  while (trajectory_generators_ros_->hasMoreTrajectories(trajectory_generator_name_)) {
+    base_trajectory::Trajectory a_traj;
+    if (trajectory_generators_ros_->nextTrajectory(trajectory_generator_name_, a_traj)) trajectories_->push_back(a_traj);
+  }
+  // :246-256 — the critics' shared data, the scores, and the RESET of the critics' cloud (it is a shared_ptr copied from
+  // the perception stack: the behaviour must not keep it alive, and the next pass brings a new one)
+  base_trajectory::Trajectory best_traj;
+  {
+    std::unique_lock<mpc_critics::StackedScoringModel::model_mutex_t> critics_lock(*(mpc_critics_ros_->getStackedScoringModelPtr()->getMutex()));
+    auto mc = mpc_critics_ros_->getSharedDataPtr();
+    mc->robot_pose_ = trans_gbl2b;
+    mc->robot_state_ = robot_state;
+    mc->pcl_perception_ = perception_3d_->aggregate_observation_;
+    mpc_critics_ros_->updateSharedData();
+    getBestTrajectory(trajectory_generator_name_, best_traj);
+    mc->pcl_perception_.reset(new pcl::PointCloud<pcl::PointXYZI>);
+  }
+  s.best_id = best_traj.cost_ < 0 ? -1 : best_traj.id_;
+  s.best_cost = best_traj.cost_;
+  s.got_180 = got_180_;
+  if (got_180_) {  // :258-268 — half a circle behind us and back within tolerance of 180: stop, succeed
+    s.finished = true;
+    s.result = dddmr_sys_core::RECOVERY_DONE;
+    return s;
+  }
+  if (best_traj.cost_ < 0) {  // :270-289 — every trajectory rejected: stand still, give up after 5 s
+    if (now_s - last_valid_control_ > 5.0) {
+      s.finished = true;
+      s.result = dddmr_sys_core::RECOVERY_FAIL;
+    }
+    return s;
+  }
+  s.cmd_linear_x = best_traj.xv_;      // :291-296
+  s.cmd_angular_z = best_traj.thetav_;
+  last_valid_control_ = now_s;
+  return s;
+}
+
+}  // namespace recovery_behaviors
+

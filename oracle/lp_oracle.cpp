@@ -100,13 +100,23 @@ Affine pose_to_affine(const double p[7]) {
   return a;
 }
 
+// How a 3-term inner product inside Eigen's fixed-size products is associated. The oracle (and the device) evaluate
+// (a0*b0 + a1*b1) + a2*b2, which is what Eigen 3.4's scalar reducer of a coefficient-based 3x3 product does as far as its
+// source can be read from memory (not re-readable here, Eigen is not vendored). The ALTERNATIVE
+// a0*b0 + (a1*b1 + a2*b2) exists only to measure how much of the result depends on that reading
+// (tests/test_oracle.py::test_eigen_association_changes_nothing_discrete): test infrastructure, process-wide.
+int g_assoc_right = 0;
+inline double dot3(double a0, double b0, double a1, double b1, double a2, double b2) {
+  return g_assoc_right ? a0 * b0 + (a1 * b1 + a2 * b2) : (a0 * b0 + a1 * b1) + a2 * b2;
+}
+
 // Affine3d * Affine3d (A4): L = L1*L2 with each entry a0*b0 + a1*b1 + a2*b2 left to right,
 // t = L1*t2 + t1.
 Affine affine_mul(const Affine& a, const Affine& b) {
   Affine r;
   for (int i = 0; i < 3; ++i) {
-    for (int j = 0; j < 3; ++j) r.L[i][j] = (a.L[i][0] * b.L[0][j] + a.L[i][1] * b.L[1][j]) + a.L[i][2] * b.L[2][j];
-    r.t[i] = ((a.L[i][0] * b.t[0] + a.L[i][1] * b.t[1]) + a.L[i][2] * b.t[2]) + a.t[i];
+    for (int j = 0; j < 3; ++j) r.L[i][j] = dot3(a.L[i][0], b.L[0][j], a.L[i][1], b.L[1][j], a.L[i][2], b.L[2][j]);
+    r.t[i] = dot3(a.L[i][0], b.t[0], a.L[i][1], b.t[1], a.L[i][2], b.t[2]) + a.t[i];
   }
   return r;
 }
@@ -120,7 +130,7 @@ double cofactor3(const double m[3][3], int i, int j) {
 Affine affine_inverse(const Affine& a) {
   Affine r;
   const double c00 = cofactor3(a.L, 0, 0), c10 = cofactor3(a.L, 1, 0), c20 = cofactor3(a.L, 2, 0);
-  const double det = (c00 * a.L[0][0] + c10 * a.L[1][0]) + c20 * a.L[2][0];
+  const double det = dot3(c00, a.L[0][0], c10, a.L[1][0], c20, a.L[2][0]);
   const double invdet = 1.0 / det;
   r.L[0][0] = c00 * invdet;
   r.L[0][1] = c10 * invdet;
@@ -131,7 +141,7 @@ Affine affine_inverse(const Affine& a) {
   r.L[2][0] = cofactor3(a.L, 0, 2) * invdet;
   r.L[2][1] = cofactor3(a.L, 1, 2) * invdet;
   r.L[2][2] = cofactor3(a.L, 2, 2) * invdet;
-  for (int i = 0; i < 3; ++i) r.t[i] = -((r.L[i][0] * a.t[0] + r.L[i][1] * a.t[1]) + r.L[i][2] * a.t[2]);
+  for (int i = 0; i < 3; ++i) r.t[i] = -dot3(r.L[i][0], a.t[0], r.L[i][1], a.t[1], r.L[i][2], a.t[2]);
   return r;
 }
 
@@ -295,6 +305,7 @@ struct lporacle_ctx {
   std::unique_ptr<NfTree> nf_tree;
 #endif
   bool index_valid = false;
+  bool keep_index = false;  // tests only: do not rebuild an index that is still valid (same cloud, same contents)
 
   // cycle state
   b200lp_query q{};
@@ -700,6 +711,7 @@ void build_index(lporacle_ctx& c) {
   // ModelSharedData::updateData rebuilds the kd-tree every cycle when the cloud has >= 5 points
   // (MC/include/mpc_critics/model_shared_data.h:78-81)
   if (c.cloud.size() < 5) return;
+  if (c.keep_index && c.index_valid) return;
   if (c.index_mode == LPORACLE_INDEX_GRID) c.grid.build(c.cloud);
 #ifdef LPORACLE_WITH_NANOFLANN
   if (c.index_mode == LPORACLE_INDEX_NANOFLANN) {
@@ -759,6 +771,17 @@ int lporacle_set_plan(lporacle_ctx* c, const double* p, size_t n) {
   c->plan.assign(p, p + n * 7);
   c->pcl_plan.resize(n);  // model_shared_data.h:83-91
   for (size_t i = 0; i < n; ++i) c->pcl_plan[i] = Pt{(float)p[i * 7], (float)p[i * 7 + 1], (float)p[i * 7 + 2]};
+  return B200LP_OK;
+}
+
+int lporacle_set_eigen_association(int right) {
+  g_assoc_right = right != 0;
+  return B200LP_OK;
+}
+
+int lporacle_set_keep_index(lporacle_ctx* c, int keep) {
+  if (!c) return B200LP_E_INVALID;
+  c->keep_index = keep != 0;
   return B200LP_OK;
 }
 

@@ -46,6 +46,13 @@ int lporacle_set_cloud(lporacle_ctx* ctx, const void* pts, size_t n, size_t stri
 int lporacle_set_plan(lporacle_ctx* ctx, const double* xyz_qxyzw, size_t n);
 /* Score only samples whose index % stride == phase (bounded-sample CPU baseline). Default 1, 0. */
 int lporacle_set_sample_stride(lporacle_ctx* ctx, int stride, int phase);
+/* The reference rebuilds its kd-tree every cycle (model_shared_data.h:78-81) and so does lporacle_plan; keep != 0 reuses an
+ * index that is still valid for the current cloud (same contents, same answers) — for tests that plan many robots on one map. */
+int lporacle_set_keep_index(lporacle_ctx* ctx, int keep);
+/* Process-wide: right != 0 evaluates every 3-term inner product of the restated Eigen products (Affine3d * Affine3d,
+ * Affine3d::inverse) as a0*b0 + (a1*b1 + a2*b2) instead of (a0*b0 + a1*b1) + a2*b2. Exists to MEASURE how much of the
+ * result depends on an association that cannot be pinned offline (Eigen is not vendored under /root/reference). */
+int lporacle_set_eigen_association(int right);
 /* One cycle: (re)build the spatial index like ModelSharedData::updateData, roll out, score, argmin.
  * n_threads > 1 splits the trajectories over std::threads (a courtesy upper bound; the reference
  * is single-threaded). seconds_index / seconds_rollout / seconds_score may be NULL. */

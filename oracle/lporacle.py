@@ -32,6 +32,8 @@ _SYMS = {
     "lporacle_set_cloud": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t]),
     "lporacle_set_plan": (C.c_int, [_P, C.POINTER(C.c_double), C.c_size_t]),
     "lporacle_set_sample_stride": (C.c_int, [_P, C.c_int, C.c_int]),
+    "lporacle_set_keep_index": (C.c_int, [_P, C.c_int]),
+    "lporacle_set_eigen_association": (C.c_int, [C.c_int]),
     "lporacle_plan": (C.c_int, [_P, C.POINTER(abi.Query), C.c_int, C.POINTER(abi.Result), C.POINTER(C.c_double),
                                 C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "lporacle_read_trajectories": (C.c_int, [_P, C.POINTER(abi.TrajView)]),
@@ -132,6 +134,10 @@ class OraclePlanner:
     def set_sample_stride(self, stride: int, phase: int = 0):
         assert self.lib.lporacle_set_sample_stride(self.h, stride, phase) == 0
 
+    def set_keep_index(self, keep: bool = True):
+        """Do not rebuild the radius-search index on every plan() while the cloud stays the same (results are unaffected)."""
+        assert self.lib.lporacle_set_keep_index(self.h, 1 if keep else 0) == 0
+
     def plan(self, q: abi.Query, n_threads: int = 1) -> abi.Result:
         r = abi.Result()
         t = [C.c_double(), C.c_double(), C.c_double()]
@@ -185,6 +191,13 @@ class OraclePlanner:
         assert self.lib.lporacle_path_blocked(self.h, pcl.ctypes.data_as(C.POINTER(C.c_float)), pcl.shape[0],
                                               float(check_radius), C.byref(b)) == 0
         return b
+
+
+def set_eigen_association(right: bool) -> None:
+    """Process-wide switch of the restated Eigen products' 3-term association (see lp_oracle.h); default left."""
+    assert load().lporacle_set_eigen_association(1 if right else 0) == 0
+    if have_ref():
+        assert load(ref=True).lporacle_set_eigen_association(1 if right else 0) == 0
 
 
 def prune_plan(global_plan, robot_xyz, forward_distance, backward_distance, capacity=abi.MAX_PLAN):

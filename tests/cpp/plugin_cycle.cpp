@@ -9,10 +9,15 @@
 // host copy of the aggregate.
 // With `prune`, the scenario's plan is the GLOBAL plan: Local_Planner::setPlan + prunePlan run on the device and a
 // PathBlockedStrategy gives its opinion after scoring; .prune.f64 / .prunepcl.f32 are dumped too.
+// With `rotate <max_passes> <tolerance>`, the OTHER caller of the path runs instead: recovery_behaviors::RotateInPlaceBehavior's
+// control loop (rotate_inplace_behavior.cpp:137-305) with a robot that turns by cmd.angular.z / frequency per pass;
+// .rotate.f64 holds one row per pass: yaw, cmd.angular.z, cmd.linear.x, finished, result, best_id, best_cost, got_180,
+// dist_left, size of the critics' cloud after the pass (the behaviour resets it, :254-256).
 // scenario.bin: int64 n_points, int64 n_plan, float32 points[n][8] (PointXYZI), float64 plan[m][7], float64 pose[7],
 //               float64 twist[3], float64 max_speed, float64 heading_deviation
 // outputs:      <out_prefix>.summary.txt (key=value), .traj.f64 (n x 6: cost,xv,yv,thetav,time_delta,n_points),
 //               .pose.f64 (P x 7), .pcl.f32 (P x 3), .cuboid.f32 (P x 24), .aabb.f32 (P x 6)
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -22,6 +27,7 @@
 
 #include "b200lp/session.hpp"
 #include "local_planner/local_planner.h"
+#include "recovery_behaviors/rotate_inplace_behavior.h"
 
 static std::string slurp(const char* path) {
   std::ifstream f(path, std::ios::binary);
@@ -122,6 +128,31 @@ int main(int argc, char** argv) {
         stacked.addPluginToVector(lidars.back());
       }
       observe();
+    }
+    if (argc >= 9 && std::string(argv[6]) == "rotate") {
+      recovery_behaviors::RotateInPlaceBehavior beh("rotate_inplace");
+      beh.initial(perception, mc, tg, gen, std::atof(argv[8]), 10.0);
+      const double yaw0 = recovery_behaviors::yaw_of(tail[3], tail[4], tail[5], tail[6]);
+      double yaw = yaw0, now = 0.0;
+      beh.begin(pose, now);
+      std::vector<double> rows;
+      for (int it = 0; it < std::atoi(argv[7]); ++it) {
+        geometry_msgs::msg::TransformStamped t = pose;  // the robot turns on the spot, about z
+        t.transform.rotation.x = 0.0; t.transform.rotation.y = 0.0;
+        t.transform.rotation.z = std::sin(yaw / 2); t.transform.rotation.w = std::cos(yaw / 2);
+        // aggregateObservations() builds a fresh cloud object every pass (stacked_perception.cpp:128-140)
+        perception->aggregate_observation_.reset(new pcl::PointCloud<pcl::PointXYZI>(*perception->aggregate_observation_));
+        const auto st = beh.step(t, odom, now);
+        rows.insert(rows.end(), {yaw, st.cmd_angular_z, st.cmd_linear_x, st.finished ? 1.0 : 0.0, (double)st.result, (double)st.best_id,
+                                 st.best_cost, st.got_180 ? 1.0 : 0.0, st.dist_left,
+                                 (double)mc->getSharedDataPtr()->pcl_perception_->points.size()});
+        if (st.finished) break;
+        yaw += st.cmd_angular_z / beh.frequency();
+        now += 1.0 / beh.frequency();
+      }
+      dump(out + ".rotate.f64", rows);
+      b200lp::Session::resetAll();
+      return 0;
     }
     const bool prune = argc >= 10 && std::string(argv[6]) == "prune";
     std::shared_ptr<perception_3d::PathBlockedStrategy> blocked;

@@ -7,6 +7,7 @@ and getBestTrajectory keeps the last minimum. The GPU tests compare everything t
 """
 from __future__ import annotations
 
+import math
 import os
 import struct
 import subprocess
@@ -223,3 +224,91 @@ def test_plugin_cycle_fed_by_the_device_side_observation_producer(driver, tmp_pa
     assert np.array_equal(traj[:, 0], ora.read_trajectories()["cost"])
     assert int(s["best_id"]) == r.best_id == int(s["best_id2"]) and 0 < r.n_collided < r.n_traj
     assert int(s["launches_first"]) == 1 and int(s["launches_second"]) == 1
+
+
+def _yaw_of(x, y, z, w):
+    """tf2::impl::getYaw, as recovery_behaviors::yaw_of restates it."""
+    sqx, sqy, sqz, sqw = x * x, y * y, z * z, w * w
+    sarg = -2 * (x * z - w * y) / (sqx + sqy + sqz + sqw)
+    if sarg <= -0.99999:
+        return -2 * math.atan2(y, x)
+    if sarg >= 0.99999:
+        return 2 * math.atan2(y, x)
+    return math.atan2(2 * (x * y + w * z), sqw + sqx - sqy - sqz)
+
+
+def _shortest_angular_distance(a, b):
+    r = math.fmod((b - a) + math.pi, 2.0 * math.pi)
+    return r + math.pi if r <= 0.0 else r - math.pi
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("blocked", [False, True])
+def test_rotate_inplace_behavior_loop_matches_the_restated_loop(driver, tmp_path, blocked):
+    """SURVEY.md §8f row 3, the caller: RotateInPlaceBehavior's control loop (rotate_inplace_behavior.cpp:137-305) through
+    the C++ mirror — the rotate-in-place theory and its critic stack on the device once per pass, a robot that turns by
+    cmd.angular.z / frequency — against the same loop restated here around the oracle: per pass the selected trajectory,
+    its cost (bit for bit), the published command, got_180, dist_left, the end of the loop and its RecoveryState; and the
+    critics' cloud must be empty after every pass (:254-256). `blocked`: a wall next to the robot rejects every
+    trajectory, the robot stands still and the behaviour gives up after 5 s (RECOVERY_FAIL)."""
+    from oracle import lporacle as O
+    sc, gen, hdev = CASES["rotate_shortest"]()
+    cloud = sc.cloud
+    if blocked:
+        wall = synth.voxel_block(-0.3, 0.3, -0.3, 0.3, 0.2, 0.6)
+        cloud = synth.to_xyzi(wall[:, :3])
+    pose = [0.2, -0.1, 0.0, *synth.quat_from_rpy(0.0, 0.0, 0.4)]
+    twist = [0.0, 0.0, 0.0]
+    tol, freq, max_passes = 0.3, 10.0, 400
+    yaml, scb = _write_case(str(tmp_path), sc.config, gen, cloud, sc.plan, pose, twist, -1.0, hdev)
+    prefix = str(tmp_path / "out")
+    p = subprocess.run([driver, yaml, scb, prefix, gen, "early", "rotate", str(max_passes), str(tol)], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr
+    rows = np.fromfile(prefix + ".rotate.f64", np.float64).reshape(-1, 10)
+
+    ora = O.OraclePlanner(sc.config, O.MATH_SHARED, O.INDEX_GRID)
+    ora.set_cloud(cloud)
+    ora.set_plan(sc.plan)
+    yaw = start = current = _yaw_of(*pose[3:])
+    got_180, now, last_valid = False, 0.0, 0.0
+    expect = []
+    for _ in range(max_passes):
+        if not (not got_180 or abs(_shortest_angular_distance(current, start)) > tol):
+            expect.append([yaw, 0.0, 0.0, 1.0, 3.0, -1.0, -1.0, float(got_180), 0.0, None])
+            break
+        q = [0.0, 0.0, math.sin(yaw / 2), math.cos(yaw / 2)]
+        current = _yaw_of(*q)
+        if not got_180:
+            d180 = abs(_shortest_angular_distance(current, start + math.pi))
+            dist_left = math.pi + d180
+            got_180 = got_180 or d180 < tol
+        else:
+            dist_left = abs(_shortest_angular_distance(current, start))
+        r = ora.plan(make_query(pose[:3] + q, twist, -1.0, hdev))
+        row = [yaw, 0.0, 0.0, 0.0, 3.0, float(r.best_id), float(r.best_cost), float(got_180), dist_left, 0.0]
+        if got_180:
+            row[3] = 1.0
+            expect.append(row)
+            break
+        if r.best_id < 0:
+            if now - last_valid > 5.0:
+                row[3], row[4] = 1.0, 4.0  # RECOVERY_FAIL
+                expect.append(row)
+                break
+        else:
+            row[1], row[2] = r.thetav, r.xv
+            last_valid = now
+        expect.append(row)
+        yaw += row[1] / freq
+        now += 1.0 / freq
+    assert len(rows) == len(expect)
+    for k, (got, want) in enumerate(zip(rows, expect)):
+        for c in range(10):
+            if want[c] is not None:
+                assert got[c] == want[c], (k, c, got, want)
+    last = rows[-1]
+    if blocked:
+        assert last[3] == 1.0 and last[4] == 4.0 and np.all(rows[:, 5] == -1) and 50 <= len(rows) <= 53
+    else:
+        assert last[3] == 1.0 and last[4] == 3.0 and last[7] == 1.0 and len(rows) > 50  # RECOVERY_DONE after the half turn
+        assert np.all(rows[:-1, 1] != 0.0)

@@ -282,3 +282,52 @@ def test_playground_counts_match_the_survey():
     sc = synth.playground()
     o, r = run(sc.config, sc.cloud, sc.plan, pose=sc.pose, twist=sc.twist)
     assert (r.n_samples, r.n_traj, r.n_poses) == (55, 55, 2363)  # SURVEY.md §2.1F, derived from the shipped YAML
+
+
+def test_eigen_association_changes_nothing_discrete():
+    """The one arithmetic choice inside Eigen the restatement cannot pin offline: a 3-term inner product of a
+    fixed-size product is (a0*b0 + a1*b1) + a2*b2 here; Eigen's reducer might associate a0*b0 + (a1*b1 + a2*b2). This test
+    turns the risk into numbers: both associations on the C1 ramp (pitched poses, 520 trajectories), a C2 slice and 24
+    random scenes with tilted start poses and the big cuboid. Every integer output — num_steps, the sample -> trajectory
+    map, first-hit poses, collision counts, the selected trajectory — must be IDENTICAL, and the critic doubles may move by
+    rounding only (measured: <= 6e-15 relative on pitched poses, exactly 0 on flat ones, where the products hit exact
+    zeros; full C2 and all three C3 stations were measured with zero discrete changes as well)."""
+    rng = np.random.default_rng(7)
+    cases = []
+    sc = synth.c1_ramp(n_points=50_000)
+    cases.append((sc.config, sc.cloud, sc.plan, sc.pose, sc.twist, 1))
+    sc = synth.c2_dense(n_points=200_000)
+    cases.append((sc.config, sc.cloud, sc.plan, sc.pose, sc.twist, 8))
+    for seed in range(24):
+        c = cfg({"linear_x_sample": 6.0, "angular_z_sample": 7.0, **({"cuboid": synth.big_cuboid()} if seed % 2 else {})})
+        pose = [0.1, -0.2, 0.0, *synth.quat_from_rpy(float(rng.uniform(-0.2, 0.2)), float(rng.uniform(-0.2, 0.2)), float(rng.uniform(-3, 3)))]
+        cases.append((c, synth.small_scene(100 + seed, n_points=4000), plan_line(), pose, (0.7, 0, float(rng.uniform(-0.3, 0.3))), 1))
+    n_traj = n_diff_bits = 0
+    max_rel = 0.0
+    try:
+        for c, cloud, plan, pose, twist, stride in cases:
+            outs = []
+            for right in (False, True):
+                O.set_eigen_association(right)
+                o = O.OraclePlanner(c, O.MATH_SHARED, O.INDEX_GRID)
+                o.set_cloud(cloud)
+                o.set_plan(plan)
+                o.set_sample_stride(stride)
+                r = o.plan(make_query(pose, twist), n_threads=4)
+                outs.append((r.as_dict(), o.read_trajectories()))
+            (ra, ta), (rb, tb) = outs
+            for k in ("best_id", "n_samples", "n_traj", "n_collided", "n_poses"):
+                assert ra[k] == rb[k], k
+            for k in ("sample_index", "num_steps", "first_hit_pose", "vel", "time_delta"):
+                assert_same_array(ta[k], tb[k], k)
+            a, b = ta["critic_scores"], tb["critic_scores"]
+            assert np.array_equal(np.isnan(a), np.isnan(b))
+            m = ~np.isnan(a)
+            if m.any():
+                max_rel = max(max_rel, float(np.max(np.abs(a[m] - b[m]) / np.maximum(np.abs(a[m]), 1e-300))))
+            n_traj += ra["n_traj"]
+            n_diff_bits += int((ta["cost"] != tb["cost"]).sum())
+    finally:
+        O.set_eigen_association(False)
+    print(f"eigen association: {n_traj} trajectories, {n_diff_bits} costs differ in their last bits, max relative difference {max_rel:.3g}")
+    assert max_rel < 1e-12

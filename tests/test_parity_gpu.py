@@ -336,6 +336,63 @@ def test_c3_multilevel_full_size_all_stations():
     assert seen_hit and seen_free
 
 
+def test_c3_full_size_every_sample_against_the_oracle():
+    """BASELINE config C3 at full size, NOT strided: the ramp-entry station (pitched start pose, trajectories crossing the
+    floor transition) on the 8 M-point map, all 16.5 k trajectories — result, every per-trajectory array and every critic
+    double — against the oracle on all host threads."""
+    sc = synth.c3_multilevel()
+    pose, twist, plan = sc.extra_poses[0]
+    q = make_query(pose, twist)
+    gpu = LocalPlanner(sc.config)
+    gpu.set_cloud(sc.cloud)
+    gpu.set_plan(plan)
+    r = gpu.plan(q)
+    ora = O.OraclePlanner(sc.config)
+    ora.set_cloud(sc.cloud)
+    ora.set_plan(plan)
+    r_o = ora.plan(q, n_threads=os.cpu_count() or 8)
+    assert r.n_traj > 16_000 and r.n_collided > 0
+    assert r.as_dict() == r_o.as_dict()
+    assert_trajectories_equal(gpu.read_trajectories(), ora.read_trajectories())
+
+
+def test_c5_fleet_512_robots_against_single_cycles_and_the_oracle():
+    """BASELINE config C5 at the per-GPU size the bench runs (512 robots, C1 sampling, the 8 M-point three-floor map): EVERY
+    robot of the batch against its own single-robot cycle, field for field and array for array, and every 4th robot (128 of
+    them, all of their samples) against the oracle on all host threads. (The oracle materialises every radius-1 candidate
+    set: robots next to walls take it about a second each, which is what bounds the count here.)"""
+    base = synth.c3_multilevel()
+    cfg = synth.c1_ramp(n_points=1000).config
+    n = 512
+    poses, twists, plans, offs = synth.fleet_queries(n, region=(-28.0, 28.0, -20.0, 20.0), levels=(0.0, 3.0, 6.0), cloud=base.cloud)
+    gpu = LocalPlanner(cfg)
+    gpu.set_cloud(base.cloud)
+    qs = (abi.Query * n)()
+    for i in range(n):
+        qs[i] = make_query(poses[i], twists[i])
+    res = gpu.plan_batch(qs, plans, offs)
+    batch = [(res[i].as_dict(), gpu.read_trajectories(i)) for i in range(n)]
+    single = LocalPlanner(cfg)
+    single.set_cloud(base.cloud)
+    ora = O.OraclePlanner(cfg)
+    ora.set_cloud(base.cloud)
+    ora.set_keep_index(True)  # one map for all robots: the index is built once (the answers do not depend on it)
+    threads = os.cpu_count() or 8
+    found = 0
+    for i in range(n):
+        single.set_plan(plans[offs[i]:offs[i + 1]])
+        r1 = single.plan(qs[i])
+        assert r1.as_dict() == batch[i][0], f"robot {i}"
+        assert_trajectories_equal(single.read_trajectories(), batch[i][1])
+        found += r1.best_id >= 0
+        if i % 4 == 0:
+            ora.set_plan(plans[offs[i]:offs[i + 1]])
+            r_o = ora.plan(qs[i], n_threads=threads)
+            assert batch[i][0] == r_o.as_dict(), f"robot {i} vs oracle"
+            assert_trajectories_equal(batch[i][1], ora.read_trajectories())
+    assert found > n // 2
+
+
 def test_c4_sample_shards_at_full_size():
     """BASELINE config C4 sampling (361 x 362 = 131 k samples) on the C3 map: the union of 8 contiguous sample shards
     reproduces the unsharded cycle bit for bit, and the reference argmin rule over the shard winners picks the same id."""
