@@ -110,7 +110,21 @@ class Session {
   std::vector<b200lp_critic> critics_;
   b200lp_grid_config grid_{};
 
-  pcl::PointCloud<pcl::PointXYZI>::ConstPtr cloud_;  // kept alive: pointer identity is the freshness token
+  // Is the device's grid still the caller's cloud? Pointer identity alone misses a caller that refills the SAME cloud object
+  // in place: the token also carries the header stamp / seq, the size, the address of the point storage and the bits of
+  // three points (first, middle, last).
+  struct CloudToken {
+    const void* object = nullptr;
+    const void* storage = nullptr;
+    std::size_t size = 0;
+    std::uint64_t stamp = 0;
+    std::uint32_t seq = 0;
+    float probe[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    bool operator==(const CloudToken& o) const;
+  };
+  static CloudToken tokenOf(const pcl::PointCloud<pcl::PointXYZI>::ConstPtr& cloud);
+  pcl::PointCloud<pcl::PointXYZI>::ConstPtr cloud_;  // kept alive
+  CloudToken cloud_token_;
   bool cloud_uploaded_ = false;
   bool cloud_from_device_ = false;  // cloud_ is the host copy of a device-side aggregate: the device already holds it
   b200lp_query query_{};

@@ -256,8 +256,32 @@ void Session::ensureContext() {
   plan_resident_ = false;
 }
 
+bool Session::CloudToken::operator==(const CloudToken& o) const {
+  return object == o.object && storage == o.storage && size == o.size && stamp == o.stamp && seq == o.seq &&
+         std::memcmp(probe, o.probe, sizeof(probe)) == 0;
+}
+
+Session::CloudToken Session::tokenOf(const pcl::PointCloud<pcl::PointXYZI>::ConstPtr& cloud) {
+  CloudToken t;
+  if (!cloud) return t;
+  t.object = cloud.get();
+  t.size = cloud->points.size();
+  t.storage = t.size ? (const void*)cloud->points.data() : nullptr;
+  t.stamp = cloud->header.stamp;
+  t.seq = cloud->header.seq;
+  if (t.size) {
+    const std::size_t pick[3] = {0, t.size / 2, t.size - 1};
+    for (int k = 0; k < 3; ++k) {
+      const auto& p = cloud->points[pick[k]];
+      t.probe[3 * k] = p.x; t.probe[3 * k + 1] = p.y; t.probe[3 * k + 2] = p.z;
+    }
+  }
+  return t;
+}
+
 void Session::uploadCloud(const pcl::PointCloud<pcl::PointXYZI>::ConstPtr& cloud) {
   cloud_ = cloud;
+  cloud_token_ = tokenOf(cloud);
   const size_t n = cloud ? cloud->points.size() : 0;
   const int rc = b200lp_set_cloud(ctx_, n ? (const void*)cloud->points.data() : nullptr, n, sizeof(pcl::PointXYZI));
   if (rc != B200LP_OK) raise(rc, "b200lp_set_cloud");
@@ -269,7 +293,7 @@ void Session::setObservation(const pcl::PointCloud<pcl::PointXYZI>::ConstPtr& cl
   std::lock_guard<std::mutex> lk(mu_);
   ensureContext();
   // the host copy of a device-side aggregate (aggregateObservations) is already where the kernels read it
-  if (!(cloud_from_device_ && cloud_uploaded_ && cloud && cloud.get() == cloud_.get())) uploadCloud(cloud);
+  if (!(cloud_from_device_ && cloud_uploaded_ && cloud && tokenOf(cloud) == cloud_token_)) uploadCloud(cloud);
   launched_ = false;
 }
 
@@ -326,6 +350,7 @@ void Session::aggregateObservations(const std::vector<int>& sensors, const pcl::
   if (rc != B200LP_OK) raise(rc, "b200lp_aggregate_observations");
   if (total != aggregate->points.size()) throw Error(B200LP_E_STATE, "b200lp::Session::aggregateObservations: host copy and device aggregate differ in size");
   cloud_ = aggregate;
+  cloud_token_ = tokenOf(aggregate);
   cloud_uploaded_ = true;
   cloud_from_device_ = true;
   launched_ = false;
@@ -482,7 +507,7 @@ double Session::criticScore(int critic_index, const base_trajectory::Trajectory&
   std::lock_guard<std::mutex> lk(mu_);
   if (!in_cycle_) throw Error(B200LP_E_STATE, "b200lp critic: scoreTrajectory before the generator's initialise()");
   // the critics' view of the world is authoritative: (re)launch if the cycle ran against something else
-  if (pcl_perception && pcl_perception.get() != cloud_.get()) {
+  if (pcl_perception && !(tokenOf(pcl_perception) == cloud_token_)) {
     ensureContext();
     uploadCloud(pcl_perception);
     launched_ = false;
