@@ -15,6 +15,11 @@ __device__ __forceinline__ bool better(unsigned long long ca, int ia, unsigned l
   return ca < cb || (ca == cb && ia > ib);
 }
 
+__device__ __forceinline__ unsigned __smid() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -470,6 +475,7 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #ifdef B200LP_PREP_TRACE
   long long trace_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const unsigned long long trace_g0 = globaltimer_ns();
 #endif
   PREP_T(0);
 
@@ -801,10 +807,10 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
   }
   PREP_T(5);  // pure-pursuit terms done
 #ifdef B200LP_PREP_TRACE
-  if (tid == 0 && (chunk == 0 || chunk == n_chunks - 1) && robot == 0)
-    printf("prep trace chunk %d/%d steps %d: axes %lld, precheck %lld, look-back %lld, rollout %lld, pure pursuit %lld cycles (roll=%d)\n", chunk,
-           n_chunks, steps, trace_t[1] - trace_t[0], trace_t[2] - trace_t[1], trace_t[3] - trace_t[2],
-           trace_t[4] ? trace_t[4] - trace_t[3] : 0ll, trace_t[4] ? trace_t[5] - trace_t[4] : 0ll, (int)roll);
+  if (tid == 0 && (chunk % 100 == 0 || chunk == n_chunks - 1) && robot == 0)
+    printf("prep trace chunk %d/%d on sm %u: started %lld ns after the first CTA, steps %d: axes %lld, precheck %lld, look-back %lld, rollout %lld, pure pursuit %lld cycles (roll=%d), ends at %lld ns\n", chunk,
+           n_chunks, (unsigned)__smid(), (long long)(trace_g0 - *t_start), steps, trace_t[1] - trace_t[0], trace_t[2] - trace_t[1], trace_t[3] - trace_t[2],
+           trace_t[4] ? trace_t[4] - trace_t[3] : 0ll, trace_t[4] ? trace_t[5] - trace_t[4] : 0ll, (int)roll, (long long)(globaltimer_ns() - *t_start));
 #endif
   if (chunk == n_chunks - 1 && tid == 0) {  // the last ticket: every chunk of this robot has started
     const PrepAgg* a = my_aggs + chunk;
