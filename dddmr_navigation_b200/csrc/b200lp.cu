@@ -156,6 +156,8 @@ struct b200lp_ctx {
   size_t n_robots = 0;
   int t_cap = 0;
   int shard_rank = 0, shard_count = 1;
+  PrepPlan prep_plan{};                   // host-planned sample layout of the single-robot launch being issued (plan_samples)
+  unsigned long long sample_cuts_hash = 0; // hash of the sample cuts that layout used: all ranks of an exchange cycle must agree
   ShardCuts cuts{};                       // where sample-sharded launches cut the estimated-work axis (n == 0: equal shares)
   DevBuf<RobotIn> d_robots;
   DevBuf<RobotMeta> d_meta;
@@ -174,6 +176,7 @@ struct b200lp_ctx {
   DevBuf<PrepAgg> d_aggs;                // prep_kernel look-back aggregates
   DevBuf<unsigned long long> d_work;     // plan_kernel work counter (reset by argmin_kernel)
   DevBuf<uint32_t> d_surv;               // cull_kernel: per trajectory, the mask of the poses that survive the float pre-cull
+  DevBuf<unsigned> d_hist;               // SM clocks every velocity sample's trajectory took in the previous cycle (0: unknown)
   DevBuf<int> d_order;                   // ... and the work lists of the cycle, one per cost class (kCostClasses x T entries)
   DevBuf<unsigned> d_class_counts;       // entries per list (zeroed by prep_kernel)
   DevBuf<unsigned long long> d_tstart;   // globaltimer at the start of the cycle (prep_kernel's first CTA)
@@ -537,21 +540,121 @@ void resolve_cycle_timing(b200lp_ctx* ctx) {
   ctx->cycle_timing_pending = false;
 }
 
-unsigned long long cuts_hash(const ShardCuts& c) {  // FNV-1a over the cut shares a launch used
-  unsigned long long h = 1469598103934665603ull;
-  auto mix = [&](uint32_t v) {
-    for (int b = 0; b < 4; ++b) {
-      h ^= (v >> (8 * b)) & 0xffu;
+// The sample layout of a single-robot launch, planned on the host (PrepPlan, lp_kernels.cuh): velocity window and the three
+// VelocityIterator axes (the code every CTA would run, IEEE double on both sides), the shard [lo, hi) of a sample-sharded
+// launch and the chunk layout that makes prep_kernel one wave. Returns the number of chunks to launch.
+//
+// Where a shard is cut: the sample grid is ordered by rising linear speed and a trajectory's cost grows with its pose count
+// ceil(max(|v| T / g, |w| T / g_a)), so equal sample counts leave the last rank with about twice the poses of the first
+// (C4 on 8 GPUs: 0.23 vs 0.34 ms). Per linear-speed row the expected pose count has a closed form (|w| taken as uniform
+// over the angular axis, plus a fixed per-trajectory term); the rows' prefix sum is cut at the shares ctx->cuts names
+// (k / count by default; adapt_cuts moves them with the device times of earlier cycles, which every rank sees through the
+// exchange slots). Every rank runs this code on the same query and the same shares, so all ranks cut alike; the hash of
+// the cuts travels in the exchange slots and a mismatch is reported (error bit 64).
+int plan_samples(b200lp_ctx* ctx, const RobotIn& q, int rank, int count) {
+  const b200lp_limits& L = ctx->C.lim;
+  const b200lp_params& P = ctx->C.par;
+  PrepPlan& pp = ctx->prep_plan;
+  static thread_local float ax[3][kMaxAxis];
+  int n[3] = {0, 0, 0};
+  const bool sampling_on = P.linear_x_sample * P.angular_z_sample > 0;
+  const bool axes = sampling_on && P.theory != B200LP_THEORY_DD_ROTATE_INPLACE;
+  long long n_raw = 0;
+  if (axes) {
+    float mn[3], mx[3];
+    velocity_window(L, P, q, mn, mx);
+    n[0] = velocity_iterator_dev((double)mn[0], (double)mx[0], (int)P.linear_x_sample, ax[0]);
+    if (P.theory == B200LP_THEORY_OMNI_SIMPLE) n[1] = velocity_iterator_dev((double)mn[1], (double)mx[1], (int)P.linear_y_sample, ax[1]);
+    else { ax[1][0] = 0.f; n[1] = 1; }
+    n[2] = velocity_iterator_dev((double)mn[2], (double)mx[2], (int)P.angular_z_sample, ax[2]);
+    n_raw = (long long)n[0] * n[1] * n[2];
+  } else if (sampling_on) {
+    n_raw = 2;
+  }
+  pp.planned = 1;
+  pp.host_axes = axes ? 1 : 0;
+  pp.n_exc = 0;
+  if (axes) {
+    float mn[3], mx[3];
+    velocity_window(L, P, q, mn, mx);
+    const int want[3] = {(int)P.linear_x_sample, (int)P.linear_y_sample, (int)P.angular_z_sample};
+    for (int a = 0; a < 3 && pp.host_axes; ++a) {
+      AxisPlan& A = pp.ax[a];
+      A.mn = (double)mn[a];
+      A.step = 0.0;
+      A.n_out = n[a];
+      A.zero_at = -1;
+      A.pad = 0;
+      A.last = ax[a][n[a] - 1];
+      if (a == 1 && P.theory != B200LP_THEORY_OMNI_SIMPLE) continue;  // the single 0.0f of a differential drive
+      if (mn[a] != mx[a]) A.step = ((double)mx[a] - (double)mn[a]) / (double)(std::max(2, want[a]) - 1);  // as velocity_iterator_dev
+      if (n[a] == std::max(2, want[a]) + 1)  // one entry more than asked for: the inserted zero
+        for (int i = 1; i < n[a] - 1; ++i)
+          if (ax[a][i] == 0.0f && ax[a][i - 1] < 0.0f) { A.zero_at = i; break; }
+      for (int i = 0; i < n[a]; ++i) {
+        const float v = axis_value(A, i);
+        if (memcmp(&v, &ax[a][i], sizeof(float)) == 0) continue;
+        if (pp.n_exc == kAxisExceptions) { pp.host_axes = 0; break; }  // the kernel runs the chains itself
+        pp.exc_at[pp.n_exc] = (a << 24) | i;
+        pp.exc_val[pp.n_exc++] = ax[a][i];
+      }
+    }
+  }
+  pp.n_raw = n_raw;
+  // ---- the W + 1 sample cuts ----
+  long long cut[B200LP_MAX_PEERS + 1];
+  const int W = std::max(1, std::min(count, (int)B200LP_MAX_PEERS));
+  for (int k = 0; k <= W; ++k) cut[k] = n_raw * k / W;
+  if (W > 1 && axes && n_raw > 0) {
+    static thread_local float w[kMaxAxis];
+    const int nx = n[0], nths = n[2];
+    const long long row = (long long)n[1] * nths;
+    const float ta = (float)(P.sim_time / P.sim_granularity), tb = (float)(P.sim_time / P.angular_sim_granularity);
+    const float bw = fmaxf(fabsf(ax[2][0]), fabsf(ax[2][nths - 1])) * tb;  // largest angular step count of the axis
+    float acc = 0.f;
+    for (int ix = 0; ix < nx; ++ix) {
+      const float a = fabsf(ax[0][ix]) * ta;
+      const float mean_steps = (a < bw) ? a + (bw - a) * (bw - a) / (2.0f * bw) : a;  // E[max(a, U(0, bw))]
+      acc += mean_steps + 10.0f;  // + the fixed part of a trajectory (work fetch, critic epilogue, prep)
+      w[ix] = acc;                // inclusive prefix over the rows
+    }
+    const float total = w[nx - 1];
+    for (int k = 1; k < W; ++k) {
+      const float share = ctx->cuts.n == W ? ctx->cuts.frac[k] : (float)k / (float)W;
+      const float target = total * share;
+      int a = 0, b = nx - 1;  // smallest row whose inclusive prefix reaches the target
+      while (a < b) {
+        const int m = (a + b) >> 1;
+        if (w[m] >= target) b = m; else a = m + 1;
+      }
+      const float prev = a ? w[a - 1] : 0.f;
+      const float span = w[a] - prev;
+      float frac = span > 0.f ? (target - prev) / span : 0.f;
+      frac = fminf(fmaxf(frac, 0.f), 1.f);
+      long long c = (long long)a * row + (long long)(frac * (float)row);
+      c = std::max((long long)a * row, std::min(c, (long long)(a + 1) * row));
+      cut[k] = std::max(c, cut[k - 1]);
+    }
+  }
+  const int r = std::max(0, std::min(rank, W - 1));
+  pp.lo = cut[r];
+  pp.hi = cut[r + 1];
+  unsigned long long h = 1469598103934665603ull;  // FNV-1a over the cuts
+  for (int k = 0; k <= W; ++k)
+    for (int b = 0; b < 8; ++b) {
+      h ^= ((unsigned long long)cut[k] >> (8 * b)) & 0xffull;
       h *= 1099511628211ull;
     }
-  };
-  mix((uint32_t)c.n);
-  for (int k = 0; k <= c.n && k <= B200LP_MAX_PEERS; ++k) {
-    uint32_t u;
-    memcpy(&u, &c.frac[k], 4);
-    mix(u);
-  }
-  return h;
+  ctx->sample_cuts_hash = h;
+  // ---- chunk layout: the shard in kPrepThreads-sample chunks, everything else in about two count chunks per SM ----
+  const long long outside = n_raw - (pp.hi - pp.lo);
+  const long long target = 2ll * std::max(1, ctx->sm_count);
+  const long long per = std::max(1ll, (outside + target * kPrepThreads - 1) / (target * kPrepThreads));
+  pp.count_span = (int)std::min<long long>(per, 1 << 20) * kPrepThreads;
+  pp.nb = (int)((pp.lo + pp.count_span - 1) / pp.count_span);
+  pp.ns = (int)std::max<long long>(1, (pp.hi - pp.lo + kPrepThreads - 1) / kPrepThreads);
+  const int na = (int)((n_raw - pp.hi + pp.count_span - 1) / pp.count_span);
+  return pp.nb + pp.ns + na;
 }
 
 // Moves the shard cuts of the NEXT sample-sharded cycle with the device times the ranks needed for this one. Every rank
@@ -597,7 +700,7 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   size_t plan_total = 0;
   for (size_t i = 0; i < n_robots; ++i) plan_total = std::max<size_t>(plan_total, ctx->h_robots.p[i].plan_off + ctx->h_robots.p[i].plan_n);
   const int nc = std::max(1, ctx->C.n_critics);
-  const int n_chunks = (t_cap + kPrepSamples - 1) / kPrepSamples;
+  const int n_chunks_cap = (t_cap + kPrepSamples - 1) / kPrepSamples + 4;  // (a planned layout never needs more: three regions, each rounded up once)
   // Upper bound on the trajectories one launch scores per robot. A sample shard's cuts sit at equal shares of the estimated
   // pose count, not of the sample count (prep_kernel), so a shard of slow trajectories can hold far more than t_cap / count
   // of them: the only bound that always holds is t_cap. plan_kernel takes the real count from prep_kernel's meta.
@@ -627,6 +730,10 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   if (T > 0x7fffffffull) return ctx->fail(B200LP_E_INVALID, "plan: %zu robots x %d trajectories exceed the work-list index range", n_robots, t_cap);
   CK(ctx->d_surv.reserve(T * (size_t)(((int)max_steps_bound(ctx->C.lim, ctx->C.par) + 31) / 32)));
   CK(ctx->d_order.reserve(T * (size_t)kCostClasses));
+  if (ctx->d_hist.cap < T) {
+    CK(ctx->d_hist.reserve(T));
+    CK(cudaMemsetAsync(ctx->d_hist.p, 0, ctx->d_hist.cap * sizeof(unsigned), ctx->stream));  // (cull_kernel runs on this stream)
+  }
   int want_pp = 0;
   for (int k = 0; k < ctx->C.n_critics; ++k) want_pp |= ctx->C.critics[k].kind == B200LP_CRITIC_PURE_PURSUIT;
   CK(ctx->d_rec_pp.reserve(want_pp ? T : 1));
@@ -644,9 +751,9 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
     CK(ctx->d_tickets.reserve(n_robots));
     CK(cudaMemsetAsync(ctx->d_tickets.p, 0, ctx->d_tickets.cap * sizeof(unsigned), ctx->stream));
   }
-  if (ctx->d_aggs.cap < n_robots * (size_t)n_chunks) {
+  if (ctx->d_aggs.cap < n_robots * (size_t)n_chunks_cap) {
     init_on_main = true;
-    CK(ctx->d_aggs.reserve(n_robots * (size_t)n_chunks));
+    CK(ctx->d_aggs.reserve(n_robots * (size_t)n_chunks_cap));
     CK(cudaMemsetAsync(ctx->d_aggs.p, 0, ctx->d_aggs.cap * sizeof(PrepAgg), ctx->stream));
     ctx->epoch = 0;
   }
@@ -711,8 +818,12 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   // only) follows the launches
   const int by_value = n_robots == 1 ? 1 : 0;
   const RobotIn q0 = ctx->h_robots.p[0];
+  int n_chunks = n_chunks_cap - 4;
+  if (by_value) n_chunks = plan_samples(ctx, q0, rank, count);
+  else ctx->prep_plan.planned = 0;
+  if (n_chunks > n_chunks_cap) return ctx->fail(B200LP_E_STATE, "plan: %d sample chunks planned, %d provided for", n_chunks, n_chunks_cap);
   prep_kernel<<<dim3((unsigned)n_chunks, (unsigned)n_robots), kPrepThreads, kPrepSmemBytes, ps>>>(
-      ctx->C, ctx->d_robots.p, q0, by_value, ctx->d_tstart.p, t_cap, rank, count, ctx->cuts, ctx->epoch, ctx->d_tickets.p,
+      ctx->C, ctx->d_robots.p, q0, by_value, ctx->d_tstart.p, t_cap, ctx->prep_plan, ctx->epoch, ctx->d_tickets.p,
       ctx->d_aggs.p, ctx->d_rec_vel.p, ctx->d_rec_steps.p, ctx->d_rec_dt.p, ctx->d_rec_sample.p, ctx->d_meta.p, ctx->d_plan7.p,
       ctx->d_plan_pts.p, ctx->d_rec_pose_off.p, ctx->d_poses.p, pose_stride, ctx->d_rec_pp.p, want_pp, ctx->d_class_counts.p);
   CK(cudaEventRecord(ctx->ev[4], ps));
@@ -722,9 +833,11 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   }
   // the float pre-cull of every pose (needs the grid) and the work lists plan_kernel drains
   const int mask_stride = ((int)max_steps_bound(ctx->C.lim, ctx->C.par) + 31) / 32;
-  cull_kernel<<<dim3((unsigned)((t_cap + kCullTraj - 1) / kCullTraj), (unsigned)n_robots), kCullThreads, 0, ctx->stream>>>(
+  // (a planned launch lists at most ns x kPrepThreads trajectories: a sample shard does not pay for the whole grid's CTAs)
+  const int cull_traj = by_value ? std::min<long long>(t_cap, (long long)ctx->prep_plan.ns * kPrepThreads) : t_cap;
+  cull_kernel<<<dim3((unsigned)((cull_traj + kCullTraj - 1) / kCullTraj), (unsigned)n_robots), kCullThreads, 0, ctx->stream>>>(
       ctx->C, ctx->grid, ctx->d_robots.p, q0, by_value, ctx->d_meta.p, t_cap, ctx->d_rec_steps.p, ctx->d_rec_pose_off.p,
-      ctx->d_poses.p, ctx->d_surv.p, mask_stride, ctx->d_order.p, T, ctx->d_class_counts.p);
+      ctx->d_poses.p, ctx->d_surv.p, mask_stride, ctx->d_order.p, T, ctx->d_class_counts.p, ctx->d_hist.p);
   CK(cudaEventRecord(ctx->ev[7], ctx->stream));
   PeerExchange px{};
   px.t_start = ctx->d_tstart.p;
@@ -734,7 +847,7 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
     px.seq = ctx->peer_seq;  // (advanced by the caller before anything could fail)
     px.mine = ctx->peer_slots();
     px.timeout_cycles = (long long)4e9;  // ~2 s of SM clocks
-    px.cuts_hash = cuts_hash(ctx->cuts);
+    px.cuts_hash = ctx->sample_cuts_hash;
     px.peers = ctx->peer_table;
   }
   plan_kernel<<<plan_grid, kThreads, 0, ctx->stream>>>(
@@ -742,7 +855,7 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
       ctx->d_rec_steps.p, ctx->d_rec_pose_off.p, ctx->d_poses.p, ctx->d_rec_pp.p, ctx->d_plan_pts.p, ctx->d_cost.p,
       ctx->d_scores.p, ctx->d_first_hit.p, ctx->d_work.p, ctx->d_partial.p, ctx->d_tickets2.p, ctx->d_results.p,
       direct ? ctx->h_direct.p : nullptr, ctx->direct_seq, px, ctx->d_surv.p, mask_stride, ctx->d_order.p, T,
-      ctx->d_class_counts.p);
+      ctx->d_class_counts.p, ctx->d_hist.p);
   CK(cudaEventRecord(ctx->ev[5], ctx->stream));
   if (n_robots > 1) {  // a single robot's argmin is folded into plan_kernel
     argmin_kernel<<<dim3((unsigned)argmin_ctas, (unsigned)n_robots), kArgminThreads, 0, ctx->stream>>>(
@@ -925,6 +1038,7 @@ void b200lp_destroy(b200lp_ctx* ctx) {
   ctx->d_rec_pose_off.release(); ctx->d_poses.release(); ctx->d_rec_pp.release(); ctx->d_gplan7.release(); ctx->d_prune_pcl.release(); ctx->d_prune_meta.release(); ctx->h_prune_meta.release(); ctx->d_blocked.release(); ctx->h_blocked.release(); ctx->d_partial.release(); ctx->d_tickets2.release(); ctx->d_tickets.release(); ctx->d_aggs.release(); ctx->d_work.release(); ctx->d_tstart.release(); ctx->d_results.release(); ctx->d_count.release(); ctx->d_scratch.release();
   ctx->h_robots.release(); ctx->h_plan7.release(); ctx->h_results.release(); ctx->h_meta.release();
   ctx->h_count.release(); ctx->h_direct.release();
+  ctx->d_surv.release(); ctx->d_order.release(); ctx->d_hist.release(); ctx->d_class_counts.release();
   ctx->d_scan.release(); ctx->d_obs_a.release(); ctx->d_obs_b.release(); ctx->d_obs_hist.release(); ctx->d_obs_sums.release();
   ctx->d_obs_heads.release(); ctx->d_obs_counts.release(); ctx->h_obs_counts.release();
   for (auto& b : ctx->d_obs_out) b.release();

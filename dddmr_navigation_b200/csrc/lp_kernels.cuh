@@ -329,15 +329,16 @@ __global__ void __launch_bounds__(256) sat_z_kernel(GridDev g, uint32_t* __restr
 // =============================================================================================
 // trajectory_generators::VelocityIterator (velocity_iterator.h:44-69); values are rounded to float where
 // the reference stores them into an Eigen::Vector3f (dd_simple…cpp:282-286).
-// One lane runs it; the only serial dependency is the `next += step` chain (b200lp_create bounds n so that
-// every index below stays inside out[kMaxAxis]).
-__device__ int velocity_iterator_dev(double mn, double mx, int n, float* out) {
+// One lane runs it — or the host, for single-robot launches (plan_samples in b200lp.cu): the only serial dependency is
+// the `next += step` chain (b200lp_create bounds n so that every index below stays inside out[kMaxAxis]). Plain IEEE
+// double adds and compares: host and device produce the same bits.
+__host__ __device__ inline int velocity_iterator_dev(double mn, double mx, int n, float* out) {
   if (mn == mx) {
     out[0] = (float)mn;
     return 1;
   }
-  n = max(2, n);
-  const double step = (mx - mn) / (double)max(1, n - 1);
+  n = n < 2 ? 2 : n;
+  const double step = (mx - mn) / (double)(n - 1);
   double next = mn;
   int cnt = 0;
   for (int j = 0; j < n - 1; ++j) {
@@ -348,7 +349,44 @@ __device__ int velocity_iterator_dev(double mn, double mx, int n, float* out) {
     cnt += (cur < 0 && next > 0) ? 2 : 1;
   }
   out[cnt] = (float)mx;
-  return min(cnt + 1, kMaxAxis);
+  return cnt + 1 < kMaxAxis ? cnt + 1 : kMaxAxis;
+}
+
+// The velocity window of a cycle (dd_simple…cpp:255-277; omni…cpp:277-303); Vector3f stores round to float.
+// mn / mx: linear x, linear y, angular z. IEEE double arithmetic only, so the host evaluates it bit for bit like a CTA.
+__host__ __device__ inline void velocity_window(const b200lp_limits& L, const b200lp_params& P, const RobotIn& q, float* mn,
+                                                float* mx) {
+  const double max_vel_th = L.max_vel_theta, min_vel_th = -1.0 * max_vel_th;
+  const float acc0 = (float)L.acc_lim_x, acc1 = (float)L.acc_lim_y, acc2 = (float)L.acc_lim_theta;
+  const double sim_period = 1.0 / P.controller_frequency;
+  const double tx = q.twist[0], ty = q.twist[1], tw = q.twist[2];
+  double min_vel_x = L.min_vel_x, max_vel_x = L.max_vel_x;
+  float mx0, mn0, mx1 = 0.f, mn1 = 0.f, mx2, mn2;
+  if (P.theory == B200LP_THEORY_DD_SIMPLE) {
+    if (q.max_speed_override > 0.0) max_vel_x = fmin(max_vel_x, q.max_speed_override);
+    mx0 = (float)fmin(max_vel_x, tx + (double)acc0 * sim_period);
+    mx2 = (float)fmin(max_vel_th, tw + (double)acc2 * sim_period);
+    mn0 = (float)fmax(min_vel_x, tx / L.deceleration_ratio);
+    mn2 = (float)fmax(min_vel_th, tw - (double)acc2 * sim_period);
+    if (mx0 < mn0) {
+      mn0 = (float)(tx / L.deceleration_ratio);
+      mx0 = (float)(tx / L.deceleration_ratio);
+    }
+  } else {
+    const double min_vel_y = L.min_vel_y, max_vel_y = L.max_vel_y;
+    mx0 = (float)fmin(max_vel_x, tx + (double)acc0 * sim_period);
+    mx1 = (float)fmin(max_vel_y, ty + (double)acc1 * sim_period);
+    mx2 = (float)fmin(max_vel_th, tw + (double)acc2 * sim_period);
+    mn0 = (float)fmax(min_vel_x, tx - (double)acc0 * sim_period);
+    mn1 = (float)fmax(min_vel_y, ty - (double)acc1 * sim_period);
+    mn2 = (float)fmax(min_vel_th, tw - (double)acc2 * sim_period);
+    if (tx >= max_vel_x / L.deceleration_ratio) mn0 = (float)fmax(min_vel_x, tx / L.deceleration_ratio);
+    else if (tx <= min_vel_x / L.deceleration_ratio) mx0 = (float)fmin(max_vel_x, tx / L.deceleration_ratio);
+    if (ty >= max_vel_y / L.deceleration_ratio) mn1 = (float)fmax(min_vel_y, ty / L.deceleration_ratio);
+    else if (ty <= min_vel_y / L.deceleration_ratio) mx1 = (float)fmin(max_vel_y, ty / L.deceleration_ratio);
+  }
+  mn[0] = mn0; mn[1] = mn1; mn[2] = mn2;
+  mx[0] = mx0; mx[1] = mx1; mx[2] = mx2;
 }
 
 __device__ __forceinline__ bool motor_ok(const b200lp_limits& L, float v0, float v2) {
@@ -397,16 +435,34 @@ __device__ __forceinline__ bool traj_precheck(const Consts& C, const RobotIn& q,
   return true;
 }
 
-// Work lists of a cycle: cull_kernel sorts the trajectories into kCostClasses lists by how many of their poses survive the
-// pre-cull (an upper bound on the obstacle-query work), plan_kernel drains the lists from the most expensive class down,
-// so the tail of the persistent kernel is made of the cheap trajectories (those in free space only pay the path critics).
-constexpr int kCostClasses = 8;
-__host__ __device__ constexpr int cost_class(int survivors) {
+// Work lists of a cycle: cull_kernel sorts the trajectories into kCostClasses lists and plan_kernel drains them in order,
+// so that the tail of the persistent kernel is made of cheap trajectories (those in free space only pay the path critics).
+//  * Classes 0 and 1: the trajectories that took longest in the PREVIOUS cycle (plan_kernel leaves every trajectory's
+//    SM-clock duration in `hist`, keyed by trajectory id (a dependent load of the sample index at the end of every
+//    work item cost 5 % of the kernel); consecutive cycles see nearly the same map from nearly
+//    the same pose). Nothing else predicts the expensive case — a trajectory that brushes along an obstacle for all of
+//    its poses without ever hitting it takes 40-50 us on C4, the average collider (it stops at its first hit) 18 us —
+//    and one of those starting half way through the launch is what the last tenth of a C4 shard's kernel waited for
+//    (26 of 2960 warps busy).
+//  * Classes 2..9: by the number of poses that survive the pre-cull (an upper bound on the obstacle-query work), most
+//    first. This is also where a sample without history goes (first cycle, samples new to a shard).
+// Only the top decile is ordered by history: draining ALL trajectories longest-first was measured and lost — the SMs then
+// run nothing but long obstacle sweeps for the first half of the launch and every trajectory takes 6 % longer (C4 shard:
+// 94.2 instead of 88.9 us of work per resident warp, as much as the shorter tail won). The number of cloud points inside
+// the poses' candidate boxes, which the summed-volume table would hand the pre-cull for free, ranks the colliders first
+// and did not help either. The order only decides who is scored when; results do not depend on it.
+constexpr int kCostClasses = 10;
+constexpr unsigned kHistVeryLong = 76000u, kHistLong = 53000u;  // SM clocks: ~40 us and ~28 us
+__host__ __device__ constexpr int cost_class(unsigned hist_clocks, int survivors) {
 #ifdef B200LP_ONE_CLASS  // A/B builds: one list in (roughly) reverse id order
   return 0;
 #endif
-  return survivors == 0 ? 7 : survivors <= 4 ? 6 : survivors <= 8 ? 5 : survivors <= 16 ? 4 : survivors <= 24 ? 3
-         : survivors <= 32 ? 2 : survivors <= 48 ? 1 : 0;
+#ifndef B200LP_NO_HISTORY  // A/B builds
+  if (hist_clocks >= kHistVeryLong) return 0;
+  if (hist_clocks >= kHistLong) return 1;
+#endif
+  return survivors == 0 ? 9 : survivors <= 4 ? 8 : survivors <= 8 ? 7 : survivors <= 16 ? 6 : survivors <= 24 ? 5
+         : survivors <= 32 ? 4 : survivors <= 48 ? 3 : 2;
 }
 
 // Where a sample-sharded launch cuts the estimated-work axis: frac[k] = share of the work below cut k (frac[0] = 0,
@@ -416,15 +472,63 @@ struct ShardCuts {
   float frac[B200LP_MAX_PEERS + 1];
 };
 
-// Per-(robot, chunk) aggregate of the decoupled look-back that orders the trajectory list across CTAs.
-struct alignas(16) PrepAgg {  // 32 bytes: read back with two 16-byte volatile loads
-  int keep, valid;     // samples kept by the motor constraint / trajectories that passed the prologue
-  int cnt_lo, cnt_hi;  // valid samples below the shard's first / end sample
-  long long poses;     // sum of num_steps inside the shard
-  int err;
-  unsigned flag;       // == launch epoch once the fields above are visible
+// Host-planned sample layout of a SINGLE-ROBOT launch (plan_samples in b200lp.cu). The host owns the query, so it runs the
+// three serial VelocityIterator chains once (every CTA used to repeat them: 17 k cycles per CTA at C4's 361-sample axes)
+// and, for sample shards, cuts the sample grid itself and lays the chunks out so that the launch is ONE wave:
+//   chunks [0, nb)            count the valid samples below the shard, `count_span` samples per CTA, nothing written;
+//   chunks [nb, nb + ns)      the shard [lo, hi): one sample per thread, records + forward simulation as ever;
+//   chunks [nb + ns, n_chunks) count the samples above the shard (n_samples / n_traj stay global).
+// Fleet launches (planned == 0) keep one chunk per kPrepThreads samples and build the axes in the kernel: their windows
+// differ per robot and live on the device.
+// The axes travel as a closed form, not as arrays (a 12 KB kernel parameter block cost ~10 us of launch latency): entry j
+// of a VelocityIterator chain is (float)(mn + j * step) unless the chain's accumulated rounding moved it across a float
+// rounding boundary. The host runs the real chain, compares it entry by entry with the closed form (the same
+// axis_value() the kernel evaluates, DMUL + DADD on both sides) and lists the entries that differ as exceptions; with
+// more than kAxisExceptions of them the kernel falls back to running the chains itself.
+constexpr int kAxisExceptions = 8;
+struct AxisPlan {
+  double mn, step;  // the chain: next += step from mn
+  float last;       // the axis' final entry, (float)max
+  int n_out;        // entries of the axis (with the inserted zero)
+  int zero_at;      // index of the 0.0f inserted where the chain crosses zero, or -1
+  int pad;
 };
-static_assert(sizeof(PrepAgg) == 32, "PrepAgg layout");
+__host__ __device__ inline float axis_value(const AxisPlan& a, int i) {
+  if (i == a.n_out - 1) return a.last;
+  if (i == a.zero_at) return 0.0f;
+  const int j = (a.zero_at >= 0 && i > a.zero_at) ? i - 1 : i;
+  return (float)(a.mn + (double)j * a.step);
+}
+struct PrepPlan {
+  int planned;    // 0: fleet layout, nothing below is read
+  int host_axes;  // 1: ax / exceptions are valid
+  AxisPlan ax[3];
+  int n_exc;
+  int exc_at[kAxisExceptions];  // axis << 24 | entry
+  float exc_val[kAxisExceptions];
+  int nb, ns, count_span;
+  long long n_raw, lo, hi;
+};
+
+// Per-(robot, chunk) aggregate of the decoupled look-back that orders the trajectory list across CTAs: ONE 16-byte word
+// {kept samples, valid trajectories, pose count | error bits << 24, launch epoch}, written with a single 16-byte store
+// and polled with a single 16-byte volatile load — payload and flag travel together, so neither side needs a fence (the
+// fenced two-word version spent 7-18 us per CTA in MEMBAR.GPU when several hundred CTAs looked back at once). Which of
+// a chunk's valid samples lie below the shard's first / end sample follows from the chunk's position in the layout.
+struct alignas(16) PrepAgg {
+  unsigned keep, valid;  // samples kept by the motor constraint / trajectories that passed the prologue
+  unsigned poses_err;    // sum of num_steps of the chunk's shard trajectories (< 2^24) | error bits << 24
+  unsigned epoch;        // == launch epoch once the chunk has published
+};
+static_assert(sizeof(PrepAgg) == 16, "PrepAgg layout");
+__device__ __forceinline__ void agg_store(PrepAgg* p, unsigned keep, unsigned valid, unsigned poses_err, unsigned epoch) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(keep), "r"(valid), "r"(poses_err), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ uint4 agg_load(const PrepAgg* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
 
 #ifndef B200LP_PREP_THREADS
 #define B200LP_PREP_THREADS 128
@@ -447,7 +551,7 @@ __device__ __forceinline__ bool prep_job(int job, int tid) { return tid == (job 
 // chunks that are already running; every CTA publishes its aggregate BEFORE it looks back.
 __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const RobotIn* __restrict__ robots, RobotIn q0,
                                                              int by_value, unsigned long long* __restrict__ t_start, int t_cap,
-                                                             int shard_rank, int shard_count, ShardCuts cuts, unsigned epoch,
+                                                             const __grid_constant__ PrepPlan PP, unsigned epoch,
                                                              unsigned* __restrict__ tickets, PrepAgg* aggs,
                                                              float4* __restrict__ rec_vel, int* __restrict__ rec_steps,
                                                              double* __restrict__ rec_dt, int* __restrict__ rec_sample,
@@ -510,43 +614,26 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
     }
 
   const bool sampling_on = P.linear_x_sample * P.angular_z_sample > 0;
-  if (sampling_on && P.theory != B200LP_THEORY_DD_ROTATE_INPLACE && (prep_job(0, tid) || prep_job(1, tid) || prep_job(2, tid))) {
-    // window (dd_simple…cpp:255-277; omni…cpp:277-303); Vector3f stores round to float
-    const double max_vel_th = L.max_vel_theta, min_vel_th = -1.0 * max_vel_th;
-    const float acc0 = (float)L.acc_lim_x, acc1 = (float)L.acc_lim_y, acc2 = (float)L.acc_lim_theta;
-    const double sim_period = 1.0 / P.controller_frequency;
-    const double tx = q.twist[0], ty = q.twist[1], tw = q.twist[2];
-    double min_vel_x = L.min_vel_x, max_vel_x = L.max_vel_x;
-    float mx0, mn0, mx1 = 0.f, mn1 = 0.f, mx2, mn2;
-    if (P.theory == B200LP_THEORY_DD_SIMPLE) {
-      if (q.max_speed_override > 0.0) max_vel_x = fmin(max_vel_x, q.max_speed_override);
-      mx0 = (float)fmin(max_vel_x, tx + (double)acc0 * sim_period);
-      mx2 = (float)fmin(max_vel_th, tw + (double)acc2 * sim_period);
-      mn0 = (float)fmax(min_vel_x, tx / L.deceleration_ratio);
-      mn2 = (float)fmax(min_vel_th, tw - (double)acc2 * sim_period);
-      if (mx0 < mn0) {
-        mn0 = (float)(tx / L.deceleration_ratio);
-        mx0 = (float)(tx / L.deceleration_ratio);
-      }
-    } else {
-      const double min_vel_y = L.min_vel_y, max_vel_y = L.max_vel_y;
-      mx0 = (float)fmin(max_vel_x, tx + (double)acc0 * sim_period);
-      mx1 = (float)fmin(max_vel_y, ty + (double)acc1 * sim_period);
-      mx2 = (float)fmin(max_vel_th, tw + (double)acc2 * sim_period);
-      mn0 = (float)fmax(min_vel_x, tx - (double)acc0 * sim_period);
-      mn1 = (float)fmax(min_vel_y, ty - (double)acc1 * sim_period);
-      mn2 = (float)fmax(min_vel_th, tw - (double)acc2 * sim_period);
-      if (tx >= max_vel_x / L.deceleration_ratio) mn0 = (float)fmax(min_vel_x, tx / L.deceleration_ratio);
-      else if (tx <= min_vel_x / L.deceleration_ratio) mx0 = (float)fmin(max_vel_x, tx / L.deceleration_ratio);
-      if (ty >= max_vel_y / L.deceleration_ratio) mn1 = (float)fmax(min_vel_y, ty / L.deceleration_ratio);
-      else if (ty <= min_vel_y / L.deceleration_ratio) mx1 = (float)fmin(max_vel_y, ty / L.deceleration_ratio);
+  if (PP.planned && PP.host_axes) {
+    // the host ran the VelocityIterator chains and checked this closed form against them, entry by entry
+    for (int i = tid; i < PP.ax[0].n_out; i += kPrepThreads) s_x[i] = axis_value(PP.ax[0], i);
+    for (int i = tid; i < PP.ax[1].n_out; i += kPrepThreads) s_y[i] = axis_value(PP.ax[1], i);
+    for (int i = tid; i < PP.ax[2].n_out; i += kPrepThreads) s_th[i] = axis_value(PP.ax[2], i);
+    if (tid < 3) s_n[tid] = PP.ax[tid].n_out;
+    __syncthreads();
+    if (tid < PP.n_exc) {
+      float* dst = (PP.exc_at[tid] >> 24) == 0 ? s_x : (PP.exc_at[tid] >> 24) == 1 ? s_y : s_th;
+      dst[PP.exc_at[tid] & 0xffffff] = PP.exc_val[tid];
     }
-    if (prep_job(0, tid)) s_n[0] = velocity_iterator_dev((double)mn0, (double)mx0, (int)P.linear_x_sample, s_x);
+  } else if (sampling_on && P.theory != B200LP_THEORY_DD_ROTATE_INPLACE && (prep_job(0, tid) || prep_job(1, tid) || prep_job(2, tid))) {
+    float mn[3], mx[3];
+    velocity_window(L, P, q, mn, mx);
+    if (prep_job(0, tid)) s_n[0] = velocity_iterator_dev((double)mn[0], (double)mx[0], (int)P.linear_x_sample, s_x);
     if (prep_job(1, tid)) {
-      if (P.theory == B200LP_THEORY_OMNI_SIMPLE) s_n[1] = velocity_iterator_dev((double)mn1, (double)mx1, (int)P.linear_y_sample, s_y);
+      if (P.theory == B200LP_THEORY_OMNI_SIMPLE) s_n[1] = velocity_iterator_dev((double)mn[1], (double)mx[1], (int)P.linear_y_sample, s_y);
       else { s_y[0] = 0.f; s_n[1] = 1; }
     }
-    if (prep_job(2, tid)) s_n[2] = velocity_iterator_dev((double)mn2, (double)mx2, (int)P.angular_z_sample, s_th);
+    if (prep_job(2, tid)) s_n[2] = velocity_iterator_dev((double)mn[2], (double)mx[2], (int)P.angular_z_sample, s_th);
   }
   __syncthreads();
   PREP_T(1);  // window + velocity axes done
@@ -556,97 +643,67 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
   if (!sampling_on) n_raw = 0;
   else if (P.theory == B200LP_THEORY_DD_ROTATE_INPLACE) n_raw = 2;
   else n_raw = s_n[0] * nys * nths;
-  // ---- sample shard of this launch: a contiguous range [lo, hi) of the sample grid, balanced by estimated work ----
-  // The grid is ordered by rising linear speed and a trajectory's cost grows with its pose count
-  // ceil(max(|v| T / g, |w| T / g_a)), so equal sample counts leave the last rank with about twice the poses of the first
-  // (C4 on 8 GPUs: 0.23 vs 0.34 ms). Every CTA of every rank evaluates the same closed-form estimate per linear-speed row
-  // (|w| taken as uniform over the angular axis, plus a fixed per-trajectory term), prefix-sums it and cuts the rows at
-  // the shares `cuts` names (k / count by default; the host may move them with the device times of earlier cycles, which
-  // every rank sees through the exchange slots); identical arithmetic on identical inputs, so all ranks agree on the cuts
-  // without talking.
-  long long lo = (long long)n_raw * shard_rank / shard_count;
-  long long hi = (long long)n_raw * (shard_rank + 1) / shard_count;
-  if (shard_count > 1 && sampling_on && P.theory != B200LP_THEORY_DD_ROTATE_INPLACE && n_raw > 0) {
-    __shared__ float s_w[kMaxAxis];
-    __shared__ long long s_cut[2];
-    const int nx = s_n[0];
-    const long long row = (long long)nys * nths;
-    const float ta = (float)(P.sim_time / P.sim_granularity), tb = (float)(P.sim_time / P.angular_sim_granularity);
-    const float bw = fmaxf(fabsf(s_th[0]), fabsf(s_th[nths - 1])) * tb;  // largest angular step count of the axis
-    for (int ix = tid; ix < nx; ix += kPrepThreads) {
-      const float a = fabsf(s_x[ix]) * ta;
-      const float mean_steps = (a < bw) ? a + (bw - a) * (bw - a) / (2.0f * bw) : a;  // E[max(a, U(0, bw))]
-      s_w[ix] = mean_steps + 10.0f;  // + the fixed part of a trajectory (work fetch, critic epilogue, prep)
+  // ---- the samples of this chunk (PrepPlan) ----
+  long long lo = 0, hi = n_raw;         // the launch's sample shard
+  long long s0 = (long long)chunk * kPrepThreads, s1 = s0 + kPrepThreads;
+  bool count_chunk = false;             // only counts its samples (they belong to another rank's shard)
+  if (PP.planned) {
+    lo = PP.lo; hi = PP.hi;
+    if (chunk < PP.nb) {
+      count_chunk = true;
+      s0 = (long long)chunk * PP.count_span;
+      s1 = s0 + PP.count_span < lo ? s0 + PP.count_span : lo;
+    } else if (chunk < PP.nb + PP.ns) {
+      s0 = lo + (long long)(chunk - PP.nb) * kPrepThreads;
+      s1 = s0 + kPrepThreads < hi ? s0 + kPrepThreads : hi;
+    } else {
+      count_chunk = true;
+      s0 = hi + (long long)(chunk - PP.nb - PP.ns) * PP.count_span;
+      s1 = s0 + PP.count_span;
     }
-    __syncthreads();
-    if (warp == 0) {  // inclusive prefix sum over the rows: lanes own contiguous runs
-      const int per = (nx + 31) / 32, i0 = lane * per, i1 = min(nx, i0 + per);
-      float run = 0.f;
-      for (int i = i0; i < i1; ++i) run += s_w[i];
-      float incl = run;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const float t = __shfl_up_sync(kFull, incl, o);
-        if (lane >= o) incl += t;
-      }
-      float acc = incl - run;
-      for (int i = i0; i < i1; ++i) {
-        acc += s_w[i];
-        s_w[i] = acc;
-      }
-    }
-    __syncthreads();
-    if (tid < 2) {
-      const int k = shard_rank + tid;  // cut number k of shard_count + 1
-      long long cut;
-      if (k <= 0) cut = 0;
-      else if (k >= shard_count) cut = n_raw;
-      else {
-        const float total = s_w[nx - 1];
-        const float share = cuts.n == shard_count ? cuts.frac[k] : (float)k / (float)shard_count;
-        const float target = total * share;
-        int a = 0, b = nx - 1;  // smallest row whose inclusive prefix reaches the target
-        while (a < b) {
-          const int m = (a + b) >> 1;
-          if (s_w[m] >= target) b = m; else a = m + 1;
-        }
-        const float prev = a ? s_w[a - 1] : 0.f;
-        const float span = s_w[a] - prev;
-        float frac = span > 0.f ? (target - prev) / span : 0.f;
-        frac = fminf(fmaxf(frac, 0.f), 1.f);
-        cut = (long long)a * row + (long long)(frac * (float)row);
-        cut = max((long long)a * row, min(cut, (long long)(a + 1) * row));
-      }
-      s_cut[tid] = cut;
-    }
-    __syncthreads();
-    lo = s_cut[0];
-    hi = s_cut[1];
   }
+  if (s1 > n_raw) s1 = n_raw;
 
-  // ---- this chunk's samples: one per thread ----
-  const int s = chunk * kPrepThreads + tid;
+  // ---- this chunk's samples: one per thread (count chunks: a strided run per thread, counted only) ----
+  auto sample = [&](int si, float& a0, float& a1, float& a2, int& st, double& d, int& e, bool& k, bool& v) {
+    a0 = a1 = a2 = 0.f;
+    if (P.theory == B200LP_THEORY_DD_ROTATE_INPLACE) {
+      a2 = (si == 0) ? (float)L.rotation_speed : (float)(-1.0 * L.rotation_speed);
+      k = motor_ok(L, a0, a2);
+    } else {
+      const int ith = si % nths, iy = (si / nths) % nys, ix = si / (nths * nys);
+      a0 = s_x[ix]; a1 = s_y[iy]; a2 = s_th[ith];
+      k = (P.theory == B200LP_THEORY_OMNI_SIMPLE) || !L.use_motor_constraint || motor_ok(L, a0, a2);
+    }
+    v = k && traj_precheck(C, q, a0, a1, a2, &st, &d, &e);
+  };
+  const long long s = s0 + tid;
   bool keep = false, valid = false;
   float v0 = 0.f, v1 = 0.f, v2 = 0.f;
   int steps = 0, err = 0;
   double dt = 0.0;
-  if (s < n_raw) {
-    if (P.theory == B200LP_THEORY_DD_ROTATE_INPLACE) {
-      v2 = (s == 0) ? (float)L.rotation_speed : (float)(-1.0 * L.rotation_speed);
-      keep = motor_ok(L, v0, v2);
-    } else {
-      const int ith = s % nths, iy = (s / nths) % nys, ix = s / (nths * nys);
-      v0 = s_x[ix]; v1 = s_y[iy]; v2 = s_th[ith];
-      keep = (P.theory == B200LP_THEORY_OMNI_SIMPLE) || !L.use_motor_constraint || motor_ok(L, v0, v2);
+  int ck = 0, cv = 0;
+  if (count_chunk) {
+    for (long long ss = s; ss < s1; ss += kPrepThreads) {
+      bool k, v;
+      int st = 0;
+      double d;
+      sample((int)ss, v0, v1, v2, st, d, err, k, v);
+      ck += k ? 1 : 0;
+      cv += v ? 1 : 0;
     }
-    if (keep) valid = traj_precheck(C, q, v0, v1, v2, &steps, &dt, &err);
+  } else if (s < s1) {
+    sample((int)s, v0, v1, v2, steps, dt, err, keep, valid);
+    ck = keep ? 1 : 0;
+    cv = valid ? 1 : 0;
   }
   const unsigned mk = __ballot_sync(kFull, keep), mv = __ballot_sync(kFull, valid);
+  ck = __reduce_add_sync(kFull, ck);
+  cv = __reduce_add_sync(kFull, cv);
   if (lane == 0) {
-    s_wkeep[warp] = __popc(mk);
-    s_wvalid[warp] = __popc(mv);
+    s_wkeep[warp] = ck;
+    s_wvalid[warp] = cv;
   }
-  int cnt_lo = (valid && s < lo) ? 1 : 0, cnt_hi = (valid && s < hi) ? 1 : 0;
   const bool in_shard = valid && s >= lo && s < hi;
   const unsigned long long my_poses = in_shard ? (unsigned long long)steps : 0ull;
   unsigned long long poses = my_poses;
@@ -660,18 +717,16 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
   if (lane == 31) s_wposes[warp] = pscan;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    cnt_lo += __shfl_xor_sync(kFull, cnt_lo, o);
-    cnt_hi += __shfl_xor_sync(kFull, cnt_hi, o);
     err |= __shfl_xor_sync(kFull, err, o);
     poses += __shfl_xor_sync(kFull, poses, o);
   }
   if (lane == 0) {
-    atomicAdd(&s_red[0], cnt_lo);
-    atomicAdd(&s_red[1], cnt_hi);
     atomicOr(&s_red[2], err);
     atomicAdd(&s_poses, poses);
   }
   __syncthreads();
+  const int own_err = s_red[2];
+  const long long own_poses = (long long)s_poses;
   int offk = 0, offv = 0, totk = 0, totv = 0;
   unsigned long long offp = 0ull;
 #pragma unroll
@@ -682,36 +737,31 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
   }
   PrepAgg* my_aggs = aggs + (size_t)robot * n_chunks;
   PREP_T(2);  // samples checked, CTA-level counts known
-  if (tid == 0) {  // publish this chunk's aggregate
-    PrepAgg* a = my_aggs + chunk;
-    a->keep = totk; a->valid = totv;
-    a->cnt_lo = s_red[0]; a->cnt_hi = s_red[1];
-    a->poses = (long long)s_poses;
-    a->err = s_red[2];
-    __threadfence();
-    *(volatile unsigned*)&a->flag = epoch;
-  }
+  // (pose counts: a shard chunk holds at most kPrepThreads x B200LP_MAX_STEPS < 2^24 poses, count chunks none)
+  if (tid == 0) agg_store(my_aggs + chunk, (unsigned)totk, (unsigned)totv, (unsigned)own_poses | ((unsigned)own_err << 24), epoch);
   // ---- look back over every earlier chunk ----
+  // In a planned layout the chunks below the shard lie entirely below `lo`, the shard's chunks between `lo` and `hi`;
+  // fleet launches have lo = 0 and hi = n_raw.
+  const int c_lo = PP.planned ? PP.nb : 0, c_hi = PP.planned ? PP.nb + PP.ns : n_chunks;
   int pk = 0, pv = 0, plo = 0, phi = 0, perr = 0;
   long long pposes = 0;
   for (int c = tid; c < chunk; c += kPrepThreads) {
     const PrepAgg* a = my_aggs + c;
-    // the poll must be a volatile access: an empty loop around a plain intrinsic load has no side effect the compiler
-    // is obliged to keep. Every chunk polled here holds a ticket, i.e. its CTA is running; the time limit only guards
-    // against a device fault in that CTA, and turns a hang into an error bit the host reports.
-    if (*(volatile const unsigned*)&a->flag != epoch) {
+    // Every chunk polled here holds a ticket, i.e. its CTA is running; the time limit only guards against a device fault
+    // in that CTA, and turns a hang into an error bit the host reports.
+    uint4 w = agg_load(a);
+    if (w.w != epoch) {
       const long long t_start_poll = clock64();
-      while (*(volatile const unsigned*)&a->flag != epoch) {
-        if (clock64() - t_start_poll > kSpinLimit) { perr |= 32; break; }
-      }
+      do {
+        w = agg_load(a);
+        if (clock64() - t_start_poll > kSpinLimit) { perr |= 32; w = make_uint4(0u, 0u, 0u, epoch); }
+      } while (w.w != epoch);
     }
-    __threadfence();
-    const uint4 w0 = __ldcv(reinterpret_cast<const uint4*>(a));      // keep, valid, cnt_lo, cnt_hi
-    const uint4 w1 = __ldcv(reinterpret_cast<const uint4*>(a) + 1);  // poses (lo, hi), err, flag
-    pk += (int)w0.x; pv += (int)w0.y;
-    plo += (int)w0.z; phi += (int)w0.w;
-    pposes += (long long)(((unsigned long long)w1.y << 32) | (unsigned long long)w1.x);
-    perr |= (int)w1.z;
+    pk += (int)w.x; pv += (int)w.y;
+    if (c < c_lo) plo += (int)w.y;
+    if (c < c_hi) phi += (int)w.y;
+    pposes += (long long)(w.z & 0xffffffu);
+    perr |= (int)(w.z >> 24);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -813,15 +863,14 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
            trace_t[4] ? trace_t[4] - trace_t[3] : 0ll, trace_t[4] ? trace_t[5] - trace_t[4] : 0ll, (int)roll, (long long)(globaltimer_ns() - *t_start));
 #endif
   if (chunk == n_chunks - 1 && tid == 0) {  // the last ticket: every chunk of this robot has started
-    const PrepAgg* a = my_aggs + chunk;
     RobotMeta m;
     m.n_samples = base_keep + totk;
     m.n_traj = base_valid + totv;
-    m.t_begin = s_red[3] + a->cnt_lo;
-    m.t_end = s_red[4] + a->cnt_hi;
-    m.error = (s_red[5] | a->err) | (m.n_traj > t_cap ? 2 : 0) | ((long long)s_poses + a->poses > pose_stride ? 4 : 0);
+    m.t_begin = s_red[3] + (chunk < c_lo ? totv : 0);
+    m.t_end = s_red[4] + (chunk < c_hi ? totv : 0);
+    m.error = (s_red[5] | own_err) | (m.n_traj > t_cap ? 2 : 0) | ((long long)s_poses + own_poses > pose_stride ? 4 : 0);
     m.pad = 0;
-    m.n_poses = (long long)s_poses + a->poses;
+    m.n_poses = (long long)s_poses + own_poses;
     meta[robot] = m;
     tickets[robot] = 0u;  // ready for the next launch
   }
@@ -1059,14 +1108,14 @@ constexpr int kCullTraj = 32;
 #endif
 // cells_with_points() without the cell range: 32-bit index arithmetic (the table has < 2^29 entries: b200lp_grid_config
 // caps the cells at 2^26)
-__device__ __forceinline__ bool box_has_points(const GridDev& g, const float* lo, const float* hi) {
+__device__ __forceinline__ uint32_t box_point_count(const GridDev& g, const float* lo, const float* hi) {
   const float fx0 = cell_f(lo[0], g.org[0], g.inv_xy), fx1 = cell_f(hi[0], g.org[0], g.inv_xy);
   const float fy0 = cell_f(lo[1], g.org[1], g.inv_xy), fy1 = cell_f(hi[1], g.org[1], g.inv_xy);
   const float fz0 = cell_f(lo[2], g.org[2], g.inv_z), fz1 = cell_f(hi[2], g.org[2], g.inv_z);
   const float nxm = (float)(g.nx - 1), nym = (float)(g.ny - 1), nzm = (float)(g.nz - 1);
   const bool empty = !(lo[0] <= hi[0] && lo[1] <= hi[1] && lo[2] <= hi[2]) || fx1 < 0.f || fy1 < 0.f || fz1 < 0.f ||
                      fx0 > nxm || fy0 > nym || fz0 > nzm || g.n_kept == 0;
-  if (empty) return false;
+  if (empty) return 0u;
   const unsigned x0 = (unsigned)fmaxf(fx0, 0.f), x1 = (unsigned)fminf(fx1, nxm) + 1u;
   const unsigned y0 = (unsigned)fmaxf(fy0, 0.f), y1 = (unsigned)fminf(fy1, nym) + 1u;
   const unsigned z0 = (unsigned)fmaxf(fz0, 0.f), z1 = (unsigned)fminf(fz1, nzm) + 1u;
@@ -1077,14 +1126,14 @@ __device__ __forceinline__ bool box_has_points(const GridDev& g, const float* lo
   const uint32_t* s11 = g.sat + (z1 * sy + y1 * sx);
   const uint32_t up = (__ldg(s11 + x1) - __ldg(s11 + x0)) - (__ldg(s10 + x1) - __ldg(s10 + x0));
   const uint32_t dn = (__ldg(s01 + x1) - __ldg(s01 + x0)) - (__ldg(s00 + x1) - __ldg(s00 + x0));
-  return up != dn;
+  return up - dn;  // (modular: the differences of a summed-volume table)
 }
 
 __global__ void __launch_bounds__(kCullThreads)
 cull_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0, int by_value, const RobotMeta* __restrict__ meta,
             int t_cap, const int* __restrict__ rec_steps, const long long* __restrict__ rec_pose_off,
             const float4* __restrict__ poses, uint32_t* __restrict__ surv, int mask_stride, int* __restrict__ order,
-            size_t order_stride, unsigned* __restrict__ class_counts) {
+            size_t order_stride, unsigned* __restrict__ class_counts, const unsigned* __restrict__ hist) {
   constexpr int kBitWords = kCullTraj * (B200LP_MAX_STEPS / 32) + 1;
   __shared__ float s_R0f[9], s_t0f[3];
   __shared__ long long s_off[kCullTraj];
@@ -1125,7 +1174,7 @@ cull_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0,
       const float4 pz = __ldg(poses + row0 + r);
       float lo[3], hi[3];
       loose_box(C, g, s_R0f, s_t0f, pz.x, pz.y, pz.z, lo, hi);
-      keep = box_has_points(g, lo, hi);
+      keep = box_point_count(g, lo, hi) != 0u;
 #else
       keep = true;
 #endif
@@ -1149,7 +1198,7 @@ cull_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0,
       surv[rec * (size_t)mask_stride + w] = mk;
       total += __popc(mk);
     }
-    cls = cost_class(total);
+    cls = cost_class(__ldg(hist + rec), total);
     rec_i = (int)rec;
     pos = atomicAdd(&s_cnt[cls], 1u);
   }
@@ -1176,6 +1225,7 @@ struct WarpCtx {
   // running best of the trajectories this warp scored (single-robot launches): (cost bits, id), collisions
   unsigned long long best_cb;
   int best_id, n_coll;
+  unsigned t_item;       // SM clock at the start of the current work item
   int gbox[32 / kGroup][6];  // united cell box of each group of kGroup consecutive stash columns
 };
 
@@ -1243,7 +1293,7 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0,
             unsigned long long* __restrict__ work_counter, BlockBest* partial, unsigned* __restrict__ tickets,
             b200lp_result* __restrict__ results, DirectOut* direct, unsigned long long direct_seq, PeerExchange px,
             const uint32_t* __restrict__ surv, int mask_stride, const int* __restrict__ order, size_t order_stride,
-            const unsigned* __restrict__ class_counts) {
+            const unsigned* __restrict__ class_counts, unsigned* __restrict__ hist) {
   __shared__ CtaShared S;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* stash = S.stash[warp];
@@ -1330,6 +1380,9 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0,
     const size_t rec = (size_t)rec_i;
 #ifdef B200LP_TRAJ_TRACE  // tools only (tools/traj_trace.py): when every trajectory started and how long it took
     const unsigned long long trace_t0 = globaltimer_ns();
+#endif
+#ifndef B200LP_NO_HIST_RECORD
+    if (lane == 0) W.t_item = (unsigned)clock64();  // (its duration becomes the trajectory's cost estimate of the next cycle)
 #endif
     const int n = rec_steps[rec];
     const long long pose_row = rec_pose_off[rec];
@@ -1541,6 +1594,9 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0,
     if (lane == 0) {
       out_cost[rec] = cost;
       out_first_hit[rec] = first_hit;
+#ifndef B200LP_NO_HIST_RECORD
+      hist[rec] = max(1u, (unsigned)clock64() - W.t_item);
+#endif
 #ifdef B200LP_TRAJ_TRACE
       out_cost[rec] = (double)(trace_t0 - *px.t_start);             // start, ns after the cycle's first CTA
       out_first_hit[rec] = (int)(globaltimer_ns() - trace_t0);      // duration, ns

@@ -1,23 +1,27 @@
 #!/usr/bin/env python
 """Schedule of plan_kernel at trajectory granularity (needs a -DB200LP_TRAJ_TRACE build, which overwrites cost / first_hit with
-start / duration in ns):  python tools/traj_trace.py tools/variants_trace/lib_trace.so [C2]"""
+start / duration in ns):  python tools/traj_trace.py tools/variants_trace/lib_trace.so [C2|C4 [shard_rank shard_count]]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 from dddmr_navigation_b200 import LocalPlanner, make_query, synth
-mk = {"C1": synth.c1_ramp, "C2": synth.c2_dense, "C3": synth.c3_multilevel}[sys.argv[2] if len(sys.argv) > 2 else "C2"]
-sc = mk()
+name = sys.argv[2] if len(sys.argv) > 2 else "C2"
+sc = synth.c3_multilevel(samples=(361.0, 361.0)) if name == "C4" else {"C1": synth.c1_ramp, "C2": synth.c2_dense, "C3": synth.c3_multilevel}[name]()
+shard = (int(sys.argv[3]), int(sys.argv[4])) if len(sys.argv) > 4 else None
 lp = LocalPlanner(sc.config, device=0, lib_path=os.path.abspath(sys.argv[1]))
 lp.set_cloud(sc.cloud); lp.set_plan(sc.plan)
 q = make_query(sc.pose, sc.twist)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for i in range(6):
     flush.zero_(); torch.cuda.synchronize()
-    r = lp.plan(q)
+    r = lp.plan_shard(q, *shard) if shard else lp.plan(q)
 km = lp.last_kernel_ms()
 t = lp.read_trajectories()
+if shard:
+    _, b, e = lp.traj_count()
+    t = {k: v[b:e] for k, v in t.items()}
 start, dur, steps = t["cost"] / 1e3, t["first_hit_pose"].astype(np.float64) / 1e3, t["num_steps"]
 hit = t["critic_scores"][:, 0]
 end = start + dur
