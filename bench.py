@@ -316,6 +316,34 @@ class Env:
         self.rank, self.local_rank, self.world = rank, local_rank, world
         self.device = torch.device("cuda", local_rank)
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+        # Steps that end in a cross-GPU exchange must START together: every rank's step time contains the wait for the rank
+        # that was called last. An NCCL barrier followed by a stream synchronise releases the host threads of 8 ranks
+        # tens of microseconds apart (measured: 47 us between the ranks' device time and the host-observed step), which
+        # is the harness, not the exchange. The ranks of one node therefore line up on a page of shared memory: one
+        # 64-byte slot per rank, written by its owner only, polled by everybody (a few microseconds of skew).
+        self.gate, self.gate_n = None, 0
+        if world > 1:
+            path = "/dev/shm/b200lp_bench_gate_%s" % os.environ.get("MASTER_PORT", "0")
+            if rank == 0:
+                with open(path, "wb") as f:
+                    f.write(bytes(64 * world))
+            dist.barrier()
+            self.gate = np.memmap(path, dtype=np.int64, mode="r+", shape=(world * 8,))
+            dist.barrier()
+            if rank == 0:
+                os.unlink(path)  # (the mappings keep the page alive)
+
+    def release_together(self):
+        """Returns on all ranks of the node within microseconds of each other (host-side spin on shared memory)."""
+        if self.gate is None:
+            return
+        self.gate_n += 1
+        self.gate[self.rank * 8] = self.gate_n
+        slots = self.gate[::8]
+        t0 = time.perf_counter()
+        while int(slots.min()) < self.gate_n:
+            if time.perf_counter() - t0 > 30.0:
+                raise RuntimeError("bench: a rank did not reach the start gate within 30 s")
 
     def barrier(self):
         if self.world > 1:
@@ -328,6 +356,7 @@ class Env:
         if sync_ranks and self.world > 1:  # steps that end in a cross-GPU exchange start together
             self.dist.barrier()
             self.torch.cuda.synchronize()
+            self.release_together()
 
     def max_over_ranks(self, *vals):
         if self.world == 1:
@@ -392,14 +421,18 @@ def run_c4(env, steps, warmup):
     lp.set_plan(np.ascontiguousarray(wl["plan"], np.float64))
     out = {"workload": wl["desc"], "scaling": "strong", "steps": steps, "warmup": warmup, "unit": UNIT,
            "map": "shared: rank 0 uploaded, peers received over NVLink" if shared else "uploaded by every rank",
-           "timing": "host clock around the call on every rank (the cycle ends with the cross-GPU exchange), ranks released by a "
-                     "barrier after the L2 flush, max over ranks of the summed step times"}
+           "timing": "host clock around the call on every rank (the cycle ends with the cross-GPU exchange); after the L2 flush the "
+                     "ranks pass an NCCL barrier and then a shared-memory gate that releases their host threads within "
+                     "microseconds of each other; max over ranks of the summed step times"}
+
+    cyc = []  # device time of every timed cycle of the last timed() call: first CTA of prep_kernel -> result (exchange included)
 
     def timed(fn, adapt_warmup=0):
         for _ in range(warmup + adapt_warmup):
             env.flush_l2(True)
             r = fn()
         wall, dev = [], []
+        cyc.clear()
         env.barrier()
         for _ in range(steps):
             env.flush_l2(True)
@@ -407,6 +440,7 @@ def run_c4(env, steps, warmup):
             r = fn()
             wall.append(1e3 * (time.perf_counter() - t0))
             dev.append(lp.last_timing()["ms_plan_kernels"])
+            cyc.append(lp.last_cycle_ns()["cycle_ns"] / 1e6)
         env.barrier()
         (t,) = env.max_over_ranks(sum(wall) / 1e3)
         return r, t, wall, dev
@@ -415,7 +449,8 @@ def run_c4(env, steps, warmup):
     ru, t_u, wall_u, dev_u = timed(lambda: lp.plan(q))
     whole = {"best_id": int(ru.best_id), "best_cost": float(ru.best_cost), "n_traj": int(ru.n_traj), "n_poses": int(ru.n_poses),
              "n_collided": int(ru.n_collided)}
-    out["unsharded"] = {"ms_per_step": statistics.mean(wall_u), "kernel_ms": statistics.mean(dev_u), **whole,
+    out["unsharded"] = {"ms_per_step": statistics.mean(wall_u), "kernel_ms": statistics.mean(dev_u),
+                        "device_ms_per_step": statistics.mean(cyc), **whole,
                         "value": whole["n_poses"] / (statistics.mean(wall_u) * 1e-3)}
     if world == 1:
         out.update(value=whole["n_poses"] * steps / t_u, ms_per_step=1e3 * t_u / steps, n_gpus=1, poses_per_step=whole["n_poses"],
@@ -449,6 +484,10 @@ def run_c4(env, steps, warmup):
                     "ranks' device times of the previous cycle",
             "value": ref_poses * steps / t, "ms_per_step": 1e3 * t / steps, "p50_ms_rank0": statistics.median(wall),
             "kernel_ms_this_rank": statistics.mean(dev),
+            "device_ms_per_step": env.max_over_ranks(statistics.mean(cyc))[0],
+            "device_ms_what": "globaltimer, first CTA of prep_kernel -> the global result written by plan_kernel's last CTA (the wait "
+                              "for the peers' slots included), mean over the timed steps, max over ranks; ms_per_step minus this "
+                              "is launch latency, the ranks' start skew and the host's poll",
             "rank_device_ms_last_cycle": [v / 1e6 for v in ns], "rank_skew_ms": (max(ns) - min(ns)) / 1e6,
             "shard_cuts": lp.shard_cuts(), "parity": check(r, "peer exchange")}
     # (b) NCCL: the cuts are the ones the peer variant settled on (identical on every rank), or equal pose shares

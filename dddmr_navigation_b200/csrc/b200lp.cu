@@ -14,6 +14,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <ctime>
 #include <new>
 #include <string>
 #include <vector>
@@ -156,6 +158,10 @@ struct b200lp_ctx {
   size_t n_robots = 0;
   int t_cap = 0;
   int shard_rank = 0, shard_count = 1;
+  float axes_host[3][kMaxAxis];           // plan_samples: the VelocityIterator chains of the window below
+  float axes_window[6] = {0, 0, 0, 0, 0, 0};
+  int axes_n[3] = {0, 0, 0};
+  bool axes_valid = false;
   PrepPlan prep_plan{};                   // host-planned sample layout of the single-robot launch being issued (plan_samples)
   unsigned long long sample_cuts_hash = 0; // hash of the sample cuts that layout used: all ranks of an exchange cycle must agree
   ShardCuts cuts{};                       // where sample-sharded launches cut the estimated-work axis (n == 0: equal shares)
@@ -555,50 +561,62 @@ int plan_samples(b200lp_ctx* ctx, const RobotIn& q, int rank, int count) {
   const b200lp_limits& L = ctx->C.lim;
   const b200lp_params& P = ctx->C.par;
   PrepPlan& pp = ctx->prep_plan;
-  static thread_local float ax[3][kMaxAxis];
+  float (*ax)[kMaxAxis] = ctx->axes_host;  // the chains of the last window (kept: a robot at steady speed keeps its window)
   int n[3] = {0, 0, 0};
   const bool sampling_on = P.linear_x_sample * P.angular_z_sample > 0;
   const bool axes = sampling_on && P.theory != B200LP_THEORY_DD_ROTATE_INPLACE;
   long long n_raw = 0;
-  if (axes) {
-    float mn[3], mx[3];
-    velocity_window(L, P, q, mn, mx);
-    n[0] = velocity_iterator_dev((double)mn[0], (double)mx[0], (int)P.linear_x_sample, ax[0]);
-    if (P.theory == B200LP_THEORY_OMNI_SIMPLE) n[1] = velocity_iterator_dev((double)mn[1], (double)mx[1], (int)P.linear_y_sample, ax[1]);
-    else { ax[1][0] = 0.f; n[1] = 1; }
-    n[2] = velocity_iterator_dev((double)mn[2], (double)mx[2], (int)P.angular_z_sample, ax[2]);
-    n_raw = (long long)n[0] * n[1] * n[2];
-  } else if (sampling_on) {
-    n_raw = 2;
-  }
   pp.planned = 1;
-  pp.host_axes = axes ? 1 : 0;
-  pp.n_exc = 0;
   if (axes) {
-    float mn[3], mx[3];
-    velocity_window(L, P, q, mn, mx);
-    const int want[3] = {(int)P.linear_x_sample, (int)P.linear_y_sample, (int)P.angular_z_sample};
-    for (int a = 0; a < 3 && pp.host_axes; ++a) {
-      AxisPlan& A = pp.ax[a];
-      A.mn = (double)mn[a];
-      A.step = 0.0;
-      A.n_out = n[a];
-      A.zero_at = -1;
-      A.pad = 0;
-      A.last = ax[a][n[a] - 1];
-      if (a == 1 && P.theory != B200LP_THEORY_OMNI_SIMPLE) continue;  // the single 0.0f of a differential drive
-      if (mn[a] != mx[a]) A.step = ((double)mx[a] - (double)mn[a]) / (double)(std::max(2, want[a]) - 1);  // as velocity_iterator_dev
-      if (n[a] == std::max(2, want[a]) + 1)  // one entry more than asked for: the inserted zero
-        for (int i = 1; i < n[a] - 1; ++i)
-          if (ax[a][i] == 0.0f && ax[a][i - 1] < 0.0f) { A.zero_at = i; break; }
-      for (int i = 0; i < n[a]; ++i) {
-        const float v = axis_value(A, i);
-        if (memcmp(&v, &ax[a][i], sizeof(float)) == 0) continue;
-        if (pp.n_exc == kAxisExceptions) { pp.host_axes = 0; break; }  // the kernel runs the chains itself
-        pp.exc_at[pp.n_exc] = (a << 24) | i;
-        pp.exc_val[pp.n_exc++] = ax[a][i];
+    float win[6];
+    velocity_window(L, P, q, win, win + 3);
+    const float* mn = win;
+    const float* mx = win + 3;
+    if (ctx->axes_valid && memcmp(win, ctx->axes_window, sizeof(win)) == 0) {
+      for (int a = 0; a < 3; ++a) n[a] = ctx->axes_n[a];  // same window, same chains, same closed form: nothing to redo
+    } else {
+      const int want[3] = {(int)P.linear_x_sample, (int)P.linear_y_sample, (int)P.angular_z_sample};
+      n[0] = velocity_iterator_dev((double)mn[0], (double)mx[0], want[0], ax[0]);
+      if (P.theory == B200LP_THEORY_OMNI_SIMPLE) n[1] = velocity_iterator_dev((double)mn[1], (double)mx[1], want[1], ax[1]);
+      else { ax[1][0] = 0.f; n[1] = 1; }
+      n[2] = velocity_iterator_dev((double)mn[2], (double)mx[2], want[2], ax[2]);
+      // B200LP_AXIS_DEBUG (tests only): "0" leaves the chains to the kernel, "skew" hands it a closed form that is slightly
+      // off, so that entries really differ and travel as exceptions (or, beyond kAxisExceptions, force the fallback)
+      const char* dbg = getenv("B200LP_AXIS_DEBUG");
+      pp.host_axes = (dbg && !strcmp(dbg, "0")) ? 0 : 1;
+      pp.n_exc = 0;
+      for (int a = 0; a < 3 && pp.host_axes; ++a) {
+        AxisPlan& A = pp.ax[a];
+        A.mn = (double)mn[a];
+        A.step = 0.0;
+        A.n_out = n[a];
+        A.zero_at = -1;
+        A.pad = 0;
+        A.last = ax[a][n[a] - 1];
+        if (a == 1 && P.theory != B200LP_THEORY_OMNI_SIMPLE) continue;  // the single 0.0f of a differential drive
+        if (mn[a] != mx[a]) A.step = ((double)mx[a] - (double)mn[a]) / (double)(std::max(2, want[a]) - 1);  // as velocity_iterator_dev
+        if (dbg && !strcmp(dbg, "skew")) A.step = nextafter(A.step * (1.0 + 1e-9), 1e300);  // (tests: a closed form that is off)
+        if (n[a] == std::max(2, want[a]) + 1)  // one entry more than asked for: the inserted zero
+          for (int i = 1; i < n[a] - 1; ++i)
+            if (ax[a][i] == 0.0f && ax[a][i - 1] < 0.0f) { A.zero_at = i; break; }
+        for (int i = 0; i < n[a]; ++i) {
+          const float v = axis_value(A, i);
+          if (memcmp(&v, &ax[a][i], sizeof(float)) == 0) continue;
+          if (pp.n_exc == kAxisExceptions) { pp.host_axes = 0; break; }  // the kernel runs the chains itself
+          pp.exc_at[pp.n_exc] = (a << 24) | i;
+          pp.exc_val[pp.n_exc++] = ax[a][i];
+        }
       }
+      memcpy(ctx->axes_window, win, sizeof(win));
+      for (int a = 0; a < 3; ++a) ctx->axes_n[a] = n[a];
+      ctx->axes_valid = true;
     }
+    n_raw = (long long)n[0] * n[1] * n[2];
+  } else {
+    pp.host_axes = 0;
+    pp.n_exc = 0;
+    ctx->axes_valid = false;
+    if (sampling_on) n_raw = 2;
   }
   pp.n_raw = n_raw;
   // ---- the W + 1 sample cuts ----
@@ -692,8 +710,18 @@ void adapt_cuts(b200lp_ctx* ctx, const uint32_t* ns, int W) {
   ctx->cuts.frac[W] = 1.f;
 }
 
+// B200LP_HOST_TRACE=1 (tools only): host clock at the stations of a single-robot cycle, printed to stderr
+inline long long host_ns() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (long long)ts.tv_sec * 1000000000ll + ts.tv_nsec;
+}
+
 int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_result* outs, bool plan_resident = false,
               bool exchange = false) {
+  static const bool host_trace = getenv("B200LP_HOST_TRACE") != nullptr;
+  long long ht[5] = {0, 0, 0, 0, 0};
+  if (host_trace) ht[0] = host_ns();
   // inputs are already staged in h_robots / h_plan7 (pinned); total plan poses in plan_total
   const int t_cap = traj_cap(ctx->C.par);
   const size_t T = n_robots * (size_t)t_cap;
@@ -819,6 +847,7 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   const int by_value = n_robots == 1 ? 1 : 0;
   const RobotIn q0 = ctx->h_robots.p[0];
   int n_chunks = n_chunks_cap - 4;
+  if (host_trace) ht[1] = host_ns();
   if (by_value) n_chunks = plan_samples(ctx, q0, rank, count);
   else ctx->prep_plan.planned = 0;
   if (n_chunks > n_chunks_cap) return ctx->fail(B200LP_E_STATE, "plan: %d sample chunks planned, %d provided for", n_chunks, n_chunks_cap);
@@ -826,6 +855,7 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
       ctx->C, ctx->d_robots.p, q0, by_value, ctx->d_tstart.p, t_cap, ctx->prep_plan, ctx->epoch, ctx->d_tickets.p,
       ctx->d_aggs.p, ctx->d_rec_vel.p, ctx->d_rec_steps.p, ctx->d_rec_dt.p, ctx->d_rec_sample.p, ctx->d_meta.p, ctx->d_plan7.p,
       ctx->d_plan_pts.p, ctx->d_rec_pose_off.p, ctx->d_poses.p, pose_stride, ctx->d_rec_pp.p, want_pp, ctx->d_class_counts.p);
+  if (host_trace) ht[2] = host_ns();
   CK(cudaEventRecord(ctx->ev[4], ps));
   if (overlap) {
     CK(cudaStreamWaitEvent(ctx->stream, ctx->ev[4], 0));
@@ -868,6 +898,7 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   ctx->have_cycle_event = true;
   if (n_robots == 1)  // for the read-back kernels (poses_kernel, count_radius_kernel); off the cycle's critical path
     CK(cudaMemcpyAsync(ctx->d_robots.p, ctx->h_robots.p, sizeof(RobotIn), cudaMemcpyHostToDevice, ctx->stream));
+  if (host_trace) ht[3] = host_ns();
   if (direct) {
     // the kernel's last CTA writes the result block into pinned host memory and raises seq: no copies, no stream sync
     CK(cudaGetLastError());
@@ -886,6 +917,12 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
     ctx->h_results.p[0] = ctx->h_direct.p->r;
     ctx->h_meta.p[0] = ctx->h_direct.p->m;
     ctx->last_cycle_ns = ctx->h_direct.p->cycle_ns;
+    if (host_trace) {
+      ht[4] = host_ns();
+      fprintf(stderr, "host trace: entry -> launches %.1f us (reserves, events), plan_samples + prep launch %.1f us, cull + plan launches %.1f us, "
+                      "wait %.1f us; call %.1f us, device cycle %.1f us\n", (ht[1] - ht[0]) / 1e3, (ht[2] - ht[1]) / 1e3, (ht[3] - ht[2]) / 1e3,
+              (ht[4] - ht[3]) / 1e3, (ht[4] - ht[0]) / 1e3, ctx->last_cycle_ns / 1e3);
+    }
     if (exchange) memcpy(ctx->last_peer_ns, ctx->h_direct.p->peer_ns, sizeof(ctx->last_peer_ns));
   } else {
     CK(cudaMemcpyAsync(ctx->h_results.p, ctx->d_results.p, n_robots * sizeof(b200lp_result), cudaMemcpyDeviceToHost, ctx->stream));

@@ -158,6 +158,27 @@ def test_speed_override_motor_constraint_and_degenerate_window():
         _full_compare(gpu, ora, r_g, r_o, n_pose_trajs=4)
 
 
+@pytest.mark.parametrize("mode", ["0", "skew"])
+def test_velocity_axes_kernel_chains_and_exception_lists_equal_the_host_closed_form(mode, monkeypatch):
+    """Single-robot launches get their VelocityIterator axes as a closed form the host checked against the chains
+    (PrepPlan, lp_kernels.cuh). B200LP_AXIS_DEBUG=0 makes the kernel run the chains itself; =skew hands it a closed
+    form that is slightly off, so entries travel as exceptions or (more than 8 of them) force the kernel's own chains.
+    Every path must give the oracle's samples bit for bit — dd with a zero crossing, omni with three axes."""
+    monkeypatch.setenv("B200LP_AXIS_DEBUG", mode)
+    sc = synth.c1_ramp(n_points=20_000)
+    gpu, ora = _pair(sc.config)
+    for twist in (sc.twist, [0.05, 0.0, -0.3], [0.6, 0.0, 0.0]):  # (a new window each time: the axis plan is rebuilt)
+        r_g, r_o = run_pair(gpu, ora, sc.cloud, sc.plan, sc.pose, twist)
+        _full_compare(gpu, ora, r_g, r_o, n_pose_trajs=3)
+    gpu.close()
+    cfg = PlannerConfig(generator=copy.deepcopy(OMNI_SIMPLE_DEFAULT), critics=copy.deepcopy(OMNI_SIMPLE_CRITICS))
+    gpu, ora = _pair(cfg)
+    cloud = synth.small_scene(9, n_points=4000)
+    r_g, r_o = run_pair(gpu, ora, cloud, _straight_plan(), [0.1, -0.1, 0, *synth.quat_from_rpy(0, 0, 0.4)], [0.3, 0.1, 0.1])
+    _full_compare(gpu, ora, r_g, r_o, n_pose_trajs=4)
+    gpu.close()
+
+
 def test_omni_theory():
     cfg = PlannerConfig(generator=copy.deepcopy(OMNI_SIMPLE_DEFAULT), critics=copy.deepcopy(OMNI_SIMPLE_CRITICS))
     gpu, ora = _pair(cfg)
