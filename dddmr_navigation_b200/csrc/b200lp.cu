@@ -4,6 +4,7 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
 // -fmad=false is part of the numeric contract (lp_device.cuh). There is no CPU path in this file.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX 3: ranges cost a null-pointer test unless a profiler injects its library
 
 #include <algorithm>
 #include <atomic>
@@ -30,6 +31,15 @@ using namespace lp;
 namespace {
 
 thread_local std::string g_create_error;
+
+// One NVTX range per C-ABI call that reaches the device (SURVEY.md §5 "Tracing"): nsys / ncu --nvtx show the upload, the grid
+// build, the plan cycle and the observation producer as named spans on the calling thread.
+struct TraceRange {
+  explicit TraceRange(const char* name) { nvtxRangePushA(name); }
+  ~TraceRange() { nvtxRangePop(); }
+  TraceRange(const TraceRange&) = delete;
+  TraceRange& operator=(const TraceRange&) = delete;
+};
 
 template <class T>
 struct DevBuf {
@@ -377,6 +387,7 @@ int grid_tail(b200lp_ctx* ctx, const char* rec, size_t rec_stride, size_t n, siz
 //     plain upload: bounds_pack_kernel per piece (bounds + 16-byte records on the device), one host round trip for the
 //       bounds, then the histogram over the whole cloud.
 int build_grid(b200lp_ctx* ctx, const void* src, size_t n, size_t stride, bool on_device, int share_root = -1) {
+  TraceRange trace_range("b200lp cloud upload + grid build");
   const int sms = sm_count_of(ctx->device);
   GridDev& g = ctx->grid;
   g.n_raw = (uint32_t)n;
@@ -719,6 +730,7 @@ inline long long host_ns() {
 
 int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_result* outs, bool plan_resident = false,
               bool exchange = false) {
+  TraceRange trace_range("b200lp plan cycle");
   static const bool host_trace = getenv("B200LP_HOST_TRACE") != nullptr;
   long long ht[5] = {0, 0, 0, 0, 0};
   if (host_trace) ht[0] = host_ns();
@@ -1547,6 +1559,7 @@ int b200lp_set_global_plan(b200lp_ctx* ctx, const double* p, size_t n) {
 
 int b200lp_prune_plan(b200lp_ctx* ctx, const double robot_xyz[3], double forward_distance, double backward_distance,
                       b200lp_prune_info* out) {
+  TraceRange trace_range("b200lp prune plan");
   if (!ctx) return B200LP_E_INVALID;
   if (!robot_xyz || !out) return ctx->fail(B200LP_E_INVALID, "prune_plan: null argument");
   if (ctx->n_gplan < 3) {  // prunePlan's first early return (:376-377): nothing changes
@@ -1591,6 +1604,7 @@ int b200lp_read_prune_plan(b200lp_ctx* ctx, double* poses7, float* pcl_xyzi, siz
 }
 
 int b200lp_path_blocked(b200lp_ctx* ctx, double check_radius, b200lp_blocked* out) {
+  TraceRange trace_range("b200lp path blocked");
   if (!ctx) return B200LP_E_INVALID;
   if (!out) return ctx->fail(B200LP_E_INVALID, "path_blocked: null argument");
   if (!ctx->have_prune || !ctx->plan_on_device) return ctx->fail(B200LP_E_STATE, "path_blocked: no device-side prune plan");
@@ -1636,6 +1650,7 @@ static void transform_to_rows(const double p[7], double m[12]) {
 int b200lp_sensor_observation(b200lp_ctx* ctx, int sensor, const void* scan, size_t n, size_t stride,
                               const double base_from_sensor[7], const double global_from_base[7],
                               const b200lp_sensor_params* sp, b200lp_observation_info* info) {
+  TraceRange trace_range("b200lp sensor observation");
   if (!ctx) return B200LP_E_INVALID;
   if (sensor < 0 || sensor >= B200LP_MAX_SENSORS) return ctx->fail(B200LP_E_INVALID, "sensor_observation: sensor index out of range");
   if (!sp || !base_from_sensor || !global_from_base || (n && !scan) || stride < 12 || (stride & 3))
@@ -1770,6 +1785,7 @@ int b200lp_read_observation(b200lp_ctx* ctx, int sensor, void* out, size_t capac
 }
 
 int b200lp_aggregate_observations(b200lp_ctx* ctx, const int32_t* sensors, int n_sensors, size_t* n_total) {
+  TraceRange trace_range("b200lp aggregate observations");
   if (!ctx) return B200LP_E_INVALID;
   if (n_sensors < 0 || n_sensors > B200LP_MAX_SENSORS || (n_sensors && !sensors))
     return ctx->fail(B200LP_E_INVALID, "aggregate_observations: bad sensor list");
