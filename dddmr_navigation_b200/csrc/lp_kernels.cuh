@@ -1101,7 +1101,10 @@ __global__ void __launch_bounds__(32) share_ack_kernel(char* root_base, int rank
 // trajectory to the work list of its cost class. Trajectories are visited from the END of the list (longest rollouts first),
 // so every class list starts with its longest members.
 // =============================================================================================
-constexpr int kCullThreads = 256;
+#ifndef B200LP_CULL_THREADS
+#define B200LP_CULL_THREADS 256
+#endif
+constexpr int kCullThreads = B200LP_CULL_THREADS;
 constexpr int kCullTraj = 32;
 #ifndef B200LP_PRECULL
 #define B200LP_PRECULL 1  // 0: every pose goes through the double-precision geometry (A/B builds, tools/time_variants.py)

@@ -15,13 +15,13 @@ for name in names:
     for lib in sorted(glob.glob(os.path.join(ROOT, "tools", "variants", "*.so"))):
         lp = LocalPlanner(sc.config, device=0, lib_path=lib)
         lp.set_cloud(sc.cloud); lp.set_plan(sc.plan)
-        pk, pp = [], []
+        pk, pp, cu = [], [], []
         for i in range(23):
             flush.zero_(); torch.cuda.synchronize()
             r = lp.plan(q)
             if i >= 3:
-                km = lp.last_kernel_ms(); pk.append(km["plan_kernel"]); pp.append(km["prep_kernel"])
-        print(f"{name} {os.path.basename(lib):20s} plan_kernel={statistics.median(pk):.4f} ms (min {min(pk):.4f}) prep={statistics.median(pp):.4f} ms best={r.best_id} cost={r.best_cost:.9f} coll={r.n_collided}", flush=True)
+                km = lp.last_kernel_ms(); pk.append(km["plan_kernel"]); pp.append(km["prep_kernel"]); cu.append(km["cull_kernel"])
+        print(f"{name} {os.path.basename(lib):20s} plan_kernel={statistics.median(pk):.4f} ms (min {min(pk):.4f}) prep={statistics.median(pp):.4f} cull={statistics.median(cu):.4f} ms best={r.best_id} cost={r.best_cost:.9f} coll={r.n_collided}", flush=True)
         for k in ((0, 4, 7) if name == "C4" else ()):
             pk, cy = [], []
             for i in range(23):
