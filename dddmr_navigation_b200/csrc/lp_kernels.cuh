@@ -533,6 +533,12 @@ __device__ __forceinline__ uint4 agg_load(const PrepAgg* p) {
 #ifndef B200LP_PREP_THREADS
 #define B200LP_PREP_THREADS 128
 #endif
+#ifndef B200LP_ROLL_BLOCK
+#define B200LP_ROLL_BLOCK 4  // rollout steps per block (A/B builds)
+#endif
+#ifndef B200LP_ROLL_PIPE
+#define B200LP_ROLL_PIPE 0  // 1: three-stage software pipeline of the rollout loop (A/B builds; measured slower, see the loop)
+#endif
 constexpr int kPrepThreads = B200LP_PREP_THREADS;  // samples per chunk: 16.5 k samples (C2) make 129 CTAs, one per SM — the
                                                     // forward simulation is bound by the XU / FP64 pipes of the SMs it runs on
 constexpr int kPrepWarps = kPrepThreads / 32;
@@ -807,12 +813,64 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
     float x = 0.f, y = 0.f, th = 0.f;
     const double wdt = (double)v2 * dt;  // loop invariant of th' = (float)(th + w*dt)
     float4* out = pose_rows + pose_row;
-    // Blocks of 4 steps: the heading chain th' = (float)(th + w*dt) is the only dependency the expensive
-    // sin/cos evaluations have, so it runs ahead and the four evaluations overlap in the FP64 pipe. (A three-stage
-    // software pipeline that also overlaps the position chain with the next block's headings was measured SLOWER,
-    // 39 vs 36 us at C2: the loop is bound by the conversion (XU) and FP64 pipes of the few SMs that hold the
-    // trajectories, not by the dependency chains — tools/prep_trace.py.)
-    constexpr int kU = 4;
+    // Blocks of 4 steps: the heading chain th' = (float)(th + w*dt) is the only dependency the expensive sin/cos
+    // evaluations have, so it runs ahead and the four evaluations overlap in the FP64 pipe.
+    // B200LP_ROLL_PIPE=1 is the same arithmetic as a three-stage software pipeline (heading chain of block i + 1, sin/cos
+    // of block i, position chains of block i - 1 in one loop body, independent of each other). Measured twice and slower
+    // both times — round 1 with 256-trajectory CTAs (39 vs 36 us at C2) and again with one warp per SM sub-partition
+    // (28.6 vs 26.8 us at C2, 29.5 vs 27.0 at C1, +4 us on a C4 shard; same box, gpurun r4s): the loop is bound by the
+    // conversion (XU) and FP64 pipes of the sub-partition that holds the warp, not by the dependency chains.
+    constexpr int kU = B200LP_ROLL_BLOCK;
+#if B200LP_ROLL_PIPE
+    float tho_c[kU], thn_c[kU], thn_p[kU];
+    double ex_p[kU], ey_p[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {  // stage A of block 0
+      tho_c[u] = th;
+      th = (float)((double)th + wdt);
+      thn_c[u] = th;
+      thn_p[u] = 0.f; ex_p[u] = 0.0; ey_p[u] = 0.0;
+    }
+    const int n_blocks = (steps + kU - 1) / kU;
+    for (int i = 0; i <= n_blocks; ++i) {
+      float tho_n[kU], thn_n[kU];
+      double ex_n[kU], ey_n[kU];
+      // stage C of block i - 1 (nothing to store for i == 0: the guard is on the step index)
+      const int kc = (i - 1) * kU;
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        x = (float)((double)x + ex_p[u]);
+        y = (float)((double)y + ey_p[u]);
+        if (i > 0 && kc + u < steps) out[kc + u] = make_float4(x, y, thn_p[u], 0.f);
+      }
+      // stage B of block i (one block past the end is evaluated and dropped)
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        float sn, cs;
+        lpm::sincosf(tho_c[u], &sn, &cs);
+        if (P.theory == B200LP_THEORY_OMNI_SIMPLE) {
+          const double a = 1.57079632679489661923 + (double)tho_c[u];  // M_PI_2 + pos[2]
+          ex_n[u] = ((double)(v0 * cs) + (double)v1 * lpm::cos(a)) * dt;
+          ey_n[u] = ((double)(v0 * sn) + (double)v1 * lpm::sin(a)) * dt;
+        } else {
+          ex_n[u] = (double)(v0 * cs) * dt;
+          ey_n[u] = (double)(v0 * sn) * dt;
+        }
+      }
+      // stage A of block i + 1
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        tho_n[u] = th;
+        th = (float)((double)th + wdt);
+        thn_n[u] = th;
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        ex_p[u] = ex_n[u]; ey_p[u] = ey_n[u]; thn_p[u] = thn_c[u];
+        tho_c[u] = tho_n[u]; thn_c[u] = thn_n[u];
+      }
+    }
+#else
     for (int k0 = 0; k0 < steps; k0 += kU) {
       float tho[kU], thn[kU];
       double ex[kU], ey[kU];
@@ -842,6 +900,7 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
         if (k0 + u < steps) out[k0 + u] = make_float4(x, y, thn[u], 0.f);
       }
     }
+#endif
     PREP_T(4);  // rollout done
     // the block loop may run past the last step: restore the state after step `steps - 1`
     {
