@@ -308,6 +308,33 @@ def run_reference(args, rank, world):
     return 0
 
 
+class StartGate:
+    """Steps that end in a cross-GPU exchange must START together: every rank's step time contains the wait for the rank that
+    was called last. An NCCL barrier followed by a stream synchronise releases the host threads of 8 ranks tens of
+    microseconds apart (measured: 47 us between the ranks' device time and the host-observed step), which is the harness,
+    not the exchange. The ranks of one node therefore line up on a page of shared memory: one 64-byte slot per rank, written
+    by its owner only, polled by everybody (a few microseconds of skew)."""
+
+    def __init__(self, path: str, rank: int, world: int):
+        self.rank, self.world, self.n = rank, world, 0
+        self.slots = np.memmap(path, dtype=np.int64, mode="r+", shape=(world * 8,))
+
+    @staticmethod
+    def create(path: str, world: int):
+        with open(path, "wb") as f:
+            f.write(bytes(64 * world))
+
+    def wait(self, timeout_s: float = 30.0):
+        """Returns on all ranks within microseconds of each other (host-side spin on shared memory)."""
+        self.n += 1
+        self.slots[self.rank * 8] = self.n
+        mine = self.slots[::8]
+        t0 = time.perf_counter()
+        while int(mine.min()) < self.n:
+            if time.perf_counter() - t0 > timeout_s:
+                raise RuntimeError("bench: a rank did not reach the start gate within %.0f s" % timeout_s)
+
+
 class Env:
     """What every section of the run shares: ranks, the device, barrier and L2 flush."""
 
@@ -316,34 +343,20 @@ class Env:
         self.rank, self.local_rank, self.world = rank, local_rank, world
         self.device = torch.device("cuda", local_rank)
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-        # Steps that end in a cross-GPU exchange must START together: every rank's step time contains the wait for the rank
-        # that was called last. An NCCL barrier followed by a stream synchronise releases the host threads of 8 ranks
-        # tens of microseconds apart (measured: 47 us between the ranks' device time and the host-observed step), which
-        # is the harness, not the exchange. The ranks of one node therefore line up on a page of shared memory: one
-        # 64-byte slot per rank, written by its owner only, polled by everybody (a few microseconds of skew).
-        self.gate, self.gate_n = None, 0
+        self.gate = None
         if world > 1:
             path = "/dev/shm/b200lp_bench_gate_%s" % os.environ.get("MASTER_PORT", "0")
             if rank == 0:
-                with open(path, "wb") as f:
-                    f.write(bytes(64 * world))
+                StartGate.create(path, world)
             dist.barrier()
-            self.gate = np.memmap(path, dtype=np.int64, mode="r+", shape=(world * 8,))
+            self.gate = StartGate(path, rank, world)
             dist.barrier()
             if rank == 0:
                 os.unlink(path)  # (the mappings keep the page alive)
 
     def release_together(self):
-        """Returns on all ranks of the node within microseconds of each other (host-side spin on shared memory)."""
-        if self.gate is None:
-            return
-        self.gate_n += 1
-        self.gate[self.rank * 8] = self.gate_n
-        slots = self.gate[::8]
-        t0 = time.perf_counter()
-        while int(slots.min()) < self.gate_n:
-            if time.perf_counter() - t0 > 30.0:
-                raise RuntimeError("bench: a rank did not reach the start gate within 30 s")
+        if self.gate is not None:
+            self.gate.wait()
 
     def barrier(self):
         if self.world > 1:
@@ -740,7 +753,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
-    dev_ms, plan_k_ms, prep_k_ms, argmin_k_ms, cull_k_ms, wall_ms = [], [], [], [], [], []
+    dev_ms, plan_k_ms, prep_k_ms, argmin_k_ms, cull_k_ms, wall_ms, cyc_ms = [], [], [], [], [], [], []
     for _ in range(args.steps):
         flush_l2(sync_steps)
         t0 = time.perf_counter()
@@ -752,6 +765,8 @@ def main():
         prep_k_ms.append(km["prep_kernel"])
         argmin_k_ms.append(km["argmin_kernel"])
         cull_k_ms.append(km["cull_kernel"])
+        if mode != "fleet":  # (single-robot cycles carry the device's own clock: first CTA of prep_kernel -> result published)
+            cyc_ms.append(lp.last_cycle_ns()["cycle_ns"] / 1e6)
     barrier()
     launches = lp.launch_count() - launches0
     t_dev = sum(wall_ms) / 1e3
@@ -869,7 +884,10 @@ def main():
                       "plan_kernel": k_ms,
                       "argmin_kernel": sum(argmin_k_ms) / len(argmin_k_ms), "cycle_events": 1e3 * t_events / args.steps,
                       "grid_build_total": grid_ms,
-                      "what": "CUDA events on the library's stream; cycle_events = first kernel start -> last kernel end, max over ranks"},
+                      "device_cycle": (sum(cyc_ms) / len(cyc_ms)) if cyc_ms else None,
+                      "what": "CUDA events on the library's stream; cycle_events = first kernel start -> last kernel end, max over ranks; "
+                              "device_cycle = the GPU's global timer from prep_kernel's first CTA to the result published by "
+                              "plan_kernel's last CTA (this rank) - what is left of ms_per_step is launch latency and the host's poll"},
         "kernel_only": {"value": poses_total / t_events, "unit": UNIT, "ms_per_step": 1e3 * t_events / args.steps},
         "p50_plan_call_ms": statistics.median(wall_ms),
         "roofline": roofline,

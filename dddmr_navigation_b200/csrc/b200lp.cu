@@ -113,7 +113,7 @@ struct b200lp_ctx {
   PackPool* pack_pool = nullptr;     // host threads of the packing upload (created by the first large host cloud)
   PinBuf<float> h_stage;             // pinned staging buffer: x,y,z of every point, 12 bytes each
   int pack_threads_used = 0;         // threads that packed the last cloud (0: it was copied as is)
-  cudaEvent_t chunk_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t chunk_ev[16] = {};
   DevBuf<BoundsDev> d_bounds;
   DevBuf<uint32_t> d_total;
   PinBuf<BoundsDev> h_bounds;

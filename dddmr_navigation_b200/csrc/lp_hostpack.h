@@ -24,7 +24,10 @@ namespace lp {
 // cudaMemcpy from pageable memory runs at ~12 GB/s). Measured on the bench box (tools/pack_bw.cpp): 8 threads pack 2 M
 // points in 0.40 ms, the packed copy takes 0.44 ms, the raw copy 1.16 ms (5.3 ms from pageable memory).
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kPackChunks = 8;
+#ifndef B200LP_PACK_CHUNKS
+#define B200LP_PACK_CHUNKS 8
+#endif
+constexpr int kPackChunks = B200LP_PACK_CHUNKS;  // <= 16 (chunk_ev, CloudHeader)
 #ifndef B200LP_PACK_MIN_BYTES
 #define B200LP_PACK_MIN_BYTES (2u << 20)
 #endif

@@ -1038,7 +1038,7 @@ __device__ __forceinline__ void peer_exchange(const PeerExchange& px, int lane, 
 // as soon as its flag is up and build their grid locally. The host link is crossed once instead of once per rank.
 // Block layout of every rank's peer allocation: [2 x kMaxPeers PeerSlot | CloudHeader | rows].
 // =============================================================================================
-constexpr int kSharePieces = 8;  // == kPackChunks of the packing upload (lp_hostpack.h)
+constexpr int kSharePieces = kPackChunks;  // the pieces of the packing upload (lp_hostpack.h)
 struct alignas(16) CloudHeader {
   unsigned long long n;                         // points of the cloud (rows in the buffer)
   unsigned long long n_finite;
