@@ -343,6 +343,14 @@ int grid_tail(b200lp_ctx* ctx, const char* rec, size_t rec_stride, size_t n, siz
   g.pts = ctx->d_pts.p;
   g.cell_start = ctx->d_cell_start.p;
   g.sat = ctx->d_sat.p;
+  // scatter_kernel writes 16-byte records to random places: half a 32-byte sector each, i.e. a fetch of the other half
+  // from DRAM when the sector is not in L2. Clearing the output first — while the cloud is still on its way, for the
+  // uploads that come in pieces — leaves its sectors resident and dirty in the 126 MB L2, so the records land there:
+  // grid tail at 2 M points 0.070 -> 0.052 ms, upload unchanged (B200LP_PREZERO_PTS=0 switches it off; gpurun r4v / r4w).
+  // Not for outputs that do not fit L2 beside the rows they are sorted from (8 M points: 128 MB).
+  static const bool prezero = [] { const char* e = getenv("B200LP_PREZERO_PTS"); return !e || atoi(e) != 0; }();
+  if (prezero && g.n_kept && (size_t)g.n_kept * sizeof(float4) <= (size_t)64 << 20)
+    CK(cudaMemsetAsync(ctx->d_pts.p, 0, (size_t)g.n_kept * sizeof(float4), ctx->stream));
   if (piece_bound) {  // every piece is counted as soon as it has landed; only the last one is not hidden by the upload
     for (int c = 0; c < kPackChunks; ++c) {
       const size_t i0 = piece_bound[c], i1 = piece_bound[c + 1];
@@ -366,6 +374,8 @@ int grid_tail(b200lp_ctx* ctx, const char* rec, size_t rec_stride, size_t n, siz
   if (g.n_kept) {
     scan_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_cell_start.p, n_cells, ctx->d_scan_status.p, ctx->d_scan_ticket.p,
                                              ctx->scan_epoch, ctx->d_total.p);
+    // (the summed-volume passes need the scan only, like the scatter; running them beside it on a second stream was
+    // measured twice and changes nothing at 2 M points: 0.055-0.057 against 0.052 ms for the tail, gpurun r4w)
     scatter_kernel<<<grid_blocks(n, 256, sms), 256, 0, ctx->stream>>>(rec, rec_stride, n, g, ctx->d_rank.p, ctx->d_pts.p);
     const size_t ny_threads = ((size_t)g.nx + 1) * (size_t)g.nz, nz_threads = ((size_t)g.nx + 1) * ((size_t)g.ny + 1);
     sat_y_kernel<<<(unsigned)((ny_threads * 32 + 255) / 256), 256, 0, ctx->stream>>>(g, ctx->d_sat.p);
@@ -1033,6 +1043,7 @@ int b200lp_create(b200lp_ctx** out, int device, const b200lp_limits* limits, con
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
   if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
   if ((e = cudaStreamCreateWithFlags(&ctx->prep_stream, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+
   for (auto& ev : ctx->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
   for (auto& ev : ctx->chunk_ev)
@@ -1106,6 +1117,7 @@ void b200lp_destroy(b200lp_ctx* ctx) {
   if (ctx->push_done) cudaEventDestroy(ctx->push_done);
   if (ctx->push_stream) { cudaStreamSynchronize(ctx->push_stream); cudaStreamDestroy(ctx->push_stream); }
   if (ctx->prep_stream) { cudaStreamSynchronize(ctx->prep_stream); cudaStreamDestroy(ctx->prep_stream); }
+
   delete ctx->pack_pool;
   ctx->h_stage.release();
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
