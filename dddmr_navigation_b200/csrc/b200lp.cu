@@ -372,14 +372,36 @@ int grid_tail(b200lp_ctx* ctx, const char* rec, size_t rec_stride, size_t n, siz
     ++ctx->launches;
   }
   if (g.n_kept) {
+    // B200LP_TAIL_TRACE=1 (tools only): CUDA events between the kernels of the tail, printed after a synchronise
+    static const bool tail_trace = getenv("B200LP_TAIL_TRACE") != nullptr;
+    cudaEvent_t te[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    auto mark = [&](int k) {
+      if (!tail_trace) return;
+      cudaEventCreate(&te[k]);
+      cudaEventRecord(te[k], ctx->stream);
+    };
+    mark(0);
     scan_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_cell_start.p, n_cells, ctx->d_scan_status.p, ctx->d_scan_ticket.p,
                                              ctx->scan_epoch, ctx->d_total.p);
+    mark(1);
     // (the summed-volume passes need the scan only, like the scatter; running them beside it on a second stream was
     // measured twice and changes nothing at 2 M points: 0.055-0.057 against 0.052 ms for the tail, gpurun r4w)
     scatter_kernel<<<grid_blocks(n, 256, sms), 256, 0, ctx->stream>>>(rec, rec_stride, n, g, ctx->d_rank.p, ctx->d_pts.p);
+    mark(2);
     const size_t ny_threads = ((size_t)g.nx + 1) * (size_t)g.nz, nz_threads = ((size_t)g.nx + 1) * ((size_t)g.ny + 1);
     sat_y_kernel<<<(unsigned)((ny_threads * 32 + 255) / 256), 256, 0, ctx->stream>>>(g, ctx->d_sat.p);
+    mark(3);
     sat_z_kernel<<<(unsigned)((nz_threads + 255) / 256), 256, 0, ctx->stream>>>(g, ctx->d_sat.p);
+    mark(4);
+    if (tail_trace) {
+      cudaStreamSynchronize(ctx->stream);
+      float ms[4] = {0, 0, 0, 0}, since_arrival = 0.f;
+      for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&ms[k], te[k], te[k + 1]);
+      cudaEventElapsedTime(&since_arrival, ctx->cev[1], te[0]);
+      fprintf(stderr, "grid tail: last piece arrived -> scan starts %.1f us, scan %.1f, scatter %.1f, sat_y %.1f, sat_z %.1f us\n",
+              since_arrival * 1e3f, ms[0] * 1e3f, ms[1] * 1e3f, ms[2] * 1e3f, ms[3] * 1e3f);
+      for (auto& e : te) cudaEventDestroy(e);
+    }
     ctx->launches += 4;
   }
   CK(cudaGetLastError());
