@@ -28,6 +28,9 @@ namespace lp {
 #define B200LP_PACK_CHUNKS 8
 #endif
 constexpr int kPackChunks = B200LP_PACK_CHUNKS;  // <= 16 (chunk_ev, CloudHeader)
+#ifndef B200LP_PACK_GEOMETRIC
+#define B200LP_PACK_GEOMETRIC 1  // 0: eight equal pieces (A/B builds)
+#endif
 #ifndef B200LP_PACK_MIN_BYTES
 #define B200LP_PACK_MIN_BYTES (2u << 20)
 #endif
@@ -120,7 +123,18 @@ class PackPool {
   int threads() const { return T_; }
   // chunk c covers points [bound(c), bound(c+1)); every bound is a multiple of 4 points so that the 16-byte streaming
   // stores of neighbouring slices never share a destination line fragment
-  size_t bound(int c) const { return c >= kPackChunks ? n_ : ((n_ * (size_t)c / kPackChunks) & ~(size_t)3); }
+  // The pieces are not equal: the copy engine cannot start before the first piece is packed and the grid build cannot
+  // finish before the last piece's histogram, so the first and the last piece are small (1/32 and 2/32 of the cloud) and
+  // the middle ones carry the rest — packing is faster than the copy, so the link stays busy in between.
+  size_t bound(int c) const {
+    if (c >= kPackChunks) return n_;
+#if B200LP_PACK_CHUNKS == 8 && B200LP_PACK_GEOMETRIC
+    constexpr size_t cum[9] = {0, 1, 3, 7, 13, 19, 25, 30, 32};
+    return (n_ * cum[c] / 32) & ~(size_t)3;
+#else
+    return (n_ * (size_t)c / kPackChunks) & ~(size_t)3;
+#endif
+  }
   void start(const char* src, size_t stride, float* dst, size_t n) {
     {
       std::lock_guard<std::mutex> lk(mu_);
