@@ -240,6 +240,13 @@ struct b200lp_ctx {
 
 namespace {
 
+// B200LP_HOST_TRACE=1 (tools only): host clock at the stations of a single-robot cycle, printed to stderr
+inline long long host_ns() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (long long)ts.tv_sec * 1000000000ll + ts.tv_nsec;
+}
+
 int grid_blocks(size_t n, int threads, int sm_count) {
   const size_t want = (n + threads - 1) / threads;
   return (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)sm_count * 16));
@@ -455,6 +462,9 @@ int build_grid(b200lp_ctx* ctx, const void* src, size_t n, size_t stride, bool o
   size_t chunk_bound[kPackChunks + 1] = {0};
   if (packing) {
     PackPool& pool = *ctx->pack_pool;
+    static const bool up_trace = getenv("B200LP_HOST_TRACE") != nullptr;
+    const long long up_t0 = up_trace ? host_ns() : 0;
+    long long up_t1 = 0;
     pool.start((const char*)src, stride, ctx->h_stage.p, n);
     ctx->pack_threads_used = pool.threads();
     ctx->raw_stride = 12;  // what d_raw holds from here on
@@ -473,6 +483,10 @@ int build_grid(b200lp_ctx* ctx, const void* src, size_t n, size_t stride, bool o
       chunk_bound[c] = i0;
       chunk_bound[c + 1] = i1;
       pool.wait_chunk(c);  // also on the error path: the workers read the caller's buffer until the last chunk is packed
+      if (up_trace && c == 0) up_t1 = host_ns();
+      if (up_trace && c == kPackChunks - 1)
+        fprintf(stderr, "upload trace: %d threads, first piece (%zu points) packed %.1f us after start(), all %zu points %.1f us\n",
+                pool.threads(), pool.bound(1), (up_t1 - up_t0) / 1e3, n, (host_ns() - up_t0) / 1e3);
       if (pe != cudaSuccess || i1 == i0) continue;
       pe = cudaMemcpyAsync(ctx->d_raw.p + i0 * 12, ctx->h_stage.p + i0 * 3, (i1 - i0) * 12, cudaMemcpyHostToDevice, ctx->copy_stream);
       if (pe == cudaSuccess) pe = cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream);
@@ -751,13 +765,6 @@ void adapt_cuts(b200lp_ctx* ctx, const uint32_t* ns, int W) {
   for (int k = 0; k <= W; ++k) ctx->cuts.frac[k] = (float)std::min(1.0, std::max(0.0, nf[k]));
   ctx->cuts.frac[0] = 0.f;
   ctx->cuts.frac[W] = 1.f;
-}
-
-// B200LP_HOST_TRACE=1 (tools only): host clock at the stations of a single-robot cycle, printed to stderr
-inline long long host_ns() {
-  timespec ts;
-  clock_gettime(CLOCK_MONOTONIC, &ts);
-  return (long long)ts.tv_sec * 1000000000ll + ts.tv_nsec;
 }
 
 int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_result* outs, bool plan_resident = false,

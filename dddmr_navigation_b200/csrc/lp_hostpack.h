@@ -11,6 +11,7 @@
 #include <condition_variable>
 #include <cstdint>
 #include <cstdlib>
+#include <ctime>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -116,6 +117,7 @@ class PackPool {
       std::lock_guard<std::mutex> lk(mu_);
       stop_ = true;
       ++gen_;
+      gen_live_.store(gen_, std::memory_order_release);
     }
     cv_.notify_all();
     for (auto& t : th_) t.join();
@@ -141,6 +143,7 @@ class PackPool {
       src_ = src; stride_ = stride; dst_ = dst; n_ = n;
       for (int c = 0; c < kPackChunks; ++c) done_[c].store(0, std::memory_order_relaxed);
       ++gen_;
+      gen_live_.store(gen_, std::memory_order_release);
     }
     cv_.notify_all();
   }
@@ -163,6 +166,15 @@ class PackPool {
   void run(int w) {
     unsigned long long seen = 0;
     for (;;) {
+      // Spin-then-park: a worker that has just packed a cloud polls for the next one for spin_ns_ before it sleeps on the
+      // condition variable. Waking a parked thread costs 100-200 us on the bench hosts (B200LP_HOST_TRACE: the first
+      // 2 MB piece was packed 107-197 us after start() with parked workers, ~15 us with polling ones) — a fifth of a
+      // 2 M-point upload. B200LP_PACK_SPIN_US sets the window (default 2000 us: back-to-back uploads stay hot, a planner
+      // that uploads every 50 ms parks its workers in between; 0 parks at once).
+      if (spin_ns_ > 0) {
+        const long long t0 = now_ns();
+        while (gen_live_.load(std::memory_order_acquire) == seen && now_ns() - t0 < spin_ns_) __builtin_ia32_pause();
+      }
       {
         std::unique_lock<std::mutex> lk(mu_);
         cv_.wait(lk, [&] { return gen_ != seen; });
@@ -178,6 +190,18 @@ class PackPool {
       }
     }
   }
+  static long long now_ns() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (long long)ts.tv_sec * 1000000000ll + ts.tv_nsec;
+  }
+  static long long spin_window_ns() {
+    const char* e = std::getenv("B200LP_PACK_SPIN_US");
+    const long long us = e ? atoll(e) : 2000;
+    return us < 0 ? 0 : (us > 1000000 ? 1000000 : us) * 1000;
+  }
+  const long long spin_ns_ = spin_window_ns();
+  std::atomic<unsigned long long> gen_live_{0};  // copy of gen_ the spinning workers poll without the mutex
   int T_ = 0;
   std::vector<std::thread> th_;
   std::mutex mu_;
