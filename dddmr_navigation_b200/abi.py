@@ -12,6 +12,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 COUNT_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libb200lp_count.so")
+CHECKS_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libb200lp_checks.so")
 LIB_PATH = os.path.join(HERE, "csrc", "libb200lp.so")
 
 ABI_VERSION = 6

@@ -676,6 +676,9 @@ int plan_samples(b200lp_ctx* ctx, const RobotIn& q, int rank, int count) {
     if (sampling_on) n_raw = 2;
   }
   pp.n_raw = n_raw;
+#if B200LP_CHECKS  // (checking build only) B200LP_CHECK_SELFTEST: hand the kernel a wrong sample count, so that a test can see a check fire
+  if (getenv("B200LP_CHECK_SELFTEST")) pp.n_raw = n_raw + 1;
+#endif
   // ---- the W + 1 sample cuts ----
   long long cut[B200LP_MAX_PEERS + 1];
   const int W = std::max(1, std::min(count, (int)B200LP_MAX_PEERS));

@@ -510,6 +510,23 @@ __device__ __forceinline__ bool exact_in_radius(const float* stash, int col, flo
 // (iy, iz); cell-sorted storage makes it ONE contiguous range of float4, which the warp streams with coalesced
 // 512-byte loads.
 // ---------------------------------------------------------------------------------------------
+#ifndef B200LP_CHECKS
+#define B200LP_CHECKS 0  // 1: the checking build (libb200lp_checks.so): device-side bounds assertions at every indexed store and
+                         // list access of the cycle and the grid build; a failed one prints its source line and traps, which
+                         // the host sees as a CUDA error (compute-sanitizer is not available on the GPU pool). Never timed.
+#endif
+#if B200LP_CHECKS
+#define LP_CHECK(cond)                                                                      \
+  do {                                                                                      \
+    if (!(cond)) {                                                                          \
+      printf("b200lp check failed: %s (%s:%d)\n", #cond, __FILE__, __LINE__);               \
+      __trap();                                                                             \
+    }                                                                                       \
+  } while (0)
+#else
+#define LP_CHECK(cond) do { } while (0)
+#endif
+
 #ifndef B200LP_COUNT
 #define B200LP_COUNT 0  // 1: the counting build (libb200lp_count.so): work counters for the roofline accounting, never timed
 #endif
@@ -775,6 +792,7 @@ __device__ B200LP_SWEEP_ATTR unsigned sweep_points(const SweepGrid g, const floa
       more = advance();
 #if B200LP_STREAM == 0
       // lanes past the end of the row look at its last point again: no divergence, and a duplicate cannot change an any-hit
+      LP_CHECK(e >= 1u && j0 < e);
       if (test_round(__ldg(g.pts + min(j0 + lane, e - 1u)), cnt)) { B200LP_COUNT_FLUSH(); return __reduce_or_sync(kFull, hit); }
 #elif B200LP_STREAM == 1
       const float4 p = pn;

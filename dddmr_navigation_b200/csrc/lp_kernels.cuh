@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(256) hist_kernel(const char* __restrict__ raw,
     const unsigned peers = __match_any_sync(kFull, key);
     const int leader = __ffs(peers) - 1;
     uint32_t base = 0u;
+    LP_CHECK(key == 0xffffffffu || key < (uint32_t)g.nx * (uint32_t)g.ny * (uint32_t)g.nz);
     if (lane == leader && key != 0xffffffffu) base = atomicAdd(counts + key, (uint32_t)__popc(peers));
     base = __shfl_sync(kFull, base, leader);
     if (i < i1) rank[i] = base + (uint32_t)__popc(peers & lt);
@@ -279,6 +280,8 @@ __global__ void __launch_bounds__(256) scatter_kernel(const char* __restrict__ r
 #pragma unroll
     for (int u = 0; u < kU; ++u)
       if (ok[u]) slot[u] += __ldg(g.cell_start + cell_key(g, v[u]));
+#pragma unroll
+    for (int u = 0; u < kU; ++u) LP_CHECK(!ok[u] || slot[u] < g.n_kept);
 #pragma unroll
     for (int u = 0; u < kU; ++u)
       if (ok[u]) out[slot[u]] = make_float4(v[u].x, v[u].y, v[u].z, __uint_as_float((uint32_t)(i0 + u * step)));  // w = original index
@@ -671,6 +674,8 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
     }
   }
   if (s1 > n_raw) s1 = n_raw;
+  LP_CHECK(!PP.planned || (PP.lo <= PP.hi && PP.hi <= n_raw && PP.n_raw == n_raw));  // the host planned the samples the kernel sees
+  LP_CHECK(chunk < n_chunks);
 
   // ---- this chunk's samples: one per thread (count chunks: a strided run per thread, counted only) ----
   auto sample = [&](int si, float& a0, float& a1, float& a2, int& st, double& d, int& e, bool& k, bool& v) {
@@ -815,6 +820,8 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
     float x = 0.f, y = 0.f, th = 0.f;
     const double wdt = (double)v2 * dt;  // loop invariant of th' = (float)(th + w*dt)
     float4* out = pose_rows + pose_row;
+    LP_CHECK(steps >= 1 && steps <= B200LP_MAX_STEPS);
+    LP_CHECK(pose_row >= (long long)robot * pose_stride && pose_row + steps <= (long long)(robot + 1) * pose_stride);
     // Blocks of 4 steps: the heading chain th' = (float)(th + w*dt) is the only dependency the expensive sin/cos
     // evaluations have, so it runs ahead and the four evaluations overlap in the FP64 pipe.
     // B200LP_ROLL_PIPE=1 is the same arithmetic as a three-stage software pipeline (heading chain of block i + 1, sin/cos
@@ -1210,6 +1217,7 @@ cull_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0,
   const int first = (int)blockIdx.x * kCullTraj;
   if (first >= n_local) return;  // (whole CTA)
   const int cnt = min(kCullTraj, n_local - first);
+  LP_CHECK(cnt >= 1 && m.t_begin >= 0 && m.t_end <= m.n_traj);
   const int id_lo = m.t_begin + (n_local - first - cnt);  // the CTA's trajectories, ascending ids id_lo .. id_lo + cnt - 1
   const int tid = threadIdx.x;
   if (tid < cnt) {
@@ -1257,7 +1265,9 @@ cull_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0,
     for (int w = 0; w * 32 < n; ++w) {
       const int b = b0 + w * 32;
       unsigned mk = 0u;
+      LP_CHECK(b >= 0 && (b >= n_rows || (b >> 5) + 1 < kBitWords));
       if (b < n_rows) mk = __funnelshift_r(s_bits[b >> 5], s_bits[(b >> 5) + 1], (unsigned)(b & 31));
+      LP_CHECK(w < mask_stride);
       if (n - w * 32 < 32) mk &= (1u << (n - w * 32)) - 1u;  // (the rows behind belong to the next trajectory)
       surv[rec * (size_t)mask_stride + w] = mk;
       total += __popc(mk);
@@ -1269,6 +1279,7 @@ cull_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0,
   __syncthreads();
   if (tid < kCostClasses && s_cnt[tid]) s_base[tid] = atomicAdd(class_counts + tid, s_cnt[tid]);
   __syncthreads();
+  LP_CHECK(cls < 0 || (size_t)s_base[cls] + pos < order_stride);
   if (cls >= 0) order[(size_t)cls * order_stride + s_base[cls] + pos] = rec_i;
 }
 
@@ -1418,6 +1429,7 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0,
     if (rec_i < 0) break;
     const int robot = rec_i / t_cap;
     const int id = rec_i - robot * t_cap;
+    LP_CHECK(robot >= 0 && robot < n_robots && id >= meta[robot].t_begin && id < meta[robot].t_end);
     if (robot != cur_robot) {
       cur_robot = robot;
       const RobotIn& q = by_value ? q0 : robots[robot];
@@ -1527,6 +1539,7 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0,
       for (;;) {
         while (cnt < 32 && base < n) {
           const unsigned mk = __ldg(surv + rec * (size_t)mask_stride + (base >> 5));  // (warp-uniform address)
+          LP_CHECK(cnt + __popc(mk) <= 64 && (base >> 5) < mask_stride);
           if ((mk >> lane) & 1u) list[cnt + __popc(mk & lt)] = (unsigned short)(base + lane);
           cnt += __popc(mk);
           base += 32;
@@ -1535,6 +1548,7 @@ plan_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0,
         __syncwarp();
         const int m_here = min(cnt, 32);
         const bool live = lane < m_here;
+        LP_CHECK(!live || list[lane] < n);
         const float4 pz = live ? __ldg(traj_poses + list[lane]) : make_float4(0.f, 0.f, 0.f, 0.f);
         double L[9], t[3];
         pose_affine(W.R0, W.t0, pz.x, pz.y, pz.z, L, t);
