@@ -344,15 +344,26 @@ class Env:
         self.device = torch.device("cuda", local_rank)
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
         self.gate = None
-        if world > 1:
+        if world > 1:  # (all ranks of this bench share one node; without /dev/shm the NCCL barrier alone releases the steps)
             path = "/dev/shm/b200lp_bench_gate_%s" % os.environ.get("MASTER_PORT", "0")
-            if rank == 0:
-                StartGate.create(path, world)
+            ok = 1
+            try:
+                if rank == 0:
+                    StartGate.create(path, world)
+            except OSError:
+                ok = 0
             dist.barrier()
-            self.gate = StartGate(path, rank, world)
-            dist.barrier()
+            try:
+                gate = StartGate(path, rank, world) if ok else None
+            except (OSError, ValueError):
+                gate, ok = None, 0
+            (n_ok,) = self.sum_over_ranks(ok)
+            self.gate = gate if n_ok == world else None  # all ranks or none
             if rank == 0:
-                os.unlink(path)  # (the mappings keep the page alive)
+                try:
+                    os.unlink(path)  # (the mappings keep the page alive)
+                except OSError:
+                    pass
 
     def release_together(self):
         if self.gate is not None:

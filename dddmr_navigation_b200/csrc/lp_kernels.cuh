@@ -293,7 +293,9 @@ __global__ void __launch_bounds__(256) scatter_kernel(const char* __restrict__ r
 // cell_start; sat_y_kernel accumulates along y, sat_z_kernel along z. Consecutive threads walk consecutive X.
 // one warp per (X, z): the lanes scan 32 consecutive y at a time. (Both passes are bound by L2 transactions, not by latency:
 // the lanes of a warp read one 32-byte sector each — issuing all loads of a warp before the first scan changed nothing,
-// 0.0520 vs 0.0522 ms for the whole tail at C2. B200LP_TAIL_TRACE=1 times the kernels of the tail one by one.)
+// 0.0520 vs 0.0522 ms for the whole tail at C2, and neither did a tiled version with the lanes along x and coalesced
+// 128-byte reads (0.0541 vs 0.0542 ms): at this size the tail is five dependent launches of ~10 us each whatever they do.
+// B200LP_TAIL_TRACE=1 times the kernels of the tail one by one.)
 __global__ void __launch_bounds__(256) sat_y_kernel(GridDev g, uint32_t* __restrict__ sat) {
   const size_t nxp = (size_t)g.nx + 1;
   const size_t wid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
