@@ -560,7 +560,7 @@ def run_c5(env, steps, warmup):
     qs = (abi.Query * len(f_poses))()
     for i in range(len(f_poses)):
         qs[i] = make_query(f_poses[i], f_twists[i])
-    f_plans = np.ascontiguousarray(f_plans, np.float64)
+    _keep_plans, f_plans = pinned_copy(np.ascontiguousarray(f_plans, np.float64))  # (the plan table: pinned like the cloud)
     f_offs = np.ascontiguousarray(f_offs, np.int64)
     lp = LocalPlanner(sc.config, device=env.local_rank)
     shared = attach_group(env, lp, cloud.shape[0])
@@ -731,7 +731,7 @@ def main():
         qs = (abi.Query * len(f_poses))()
         for i in range(len(f_poses)):
             qs[i] = make_query(f_poses[i], f_twists[i])
-        f_plans = np.ascontiguousarray(f_plans, np.float64)
+        _keep_plans, f_plans = pinned_copy(np.ascontiguousarray(f_plans, np.float64))  # (the plan table: pinned like the cloud)
         f_offs = np.ascontiguousarray(f_offs, np.int64)
 
     # N > 1: one peer-memory group of all ranks — the shared map (rank 0 uploads, peers receive over NVLink) and, for sample

@@ -284,6 +284,13 @@ def test_fleet_batch_equals_individual_plans():
         r_o = ora.plan(qs[i])
         assert batch[i][0] == r_o.as_dict(), f"robot {i}"
         assert_trajectories_equal(batch[i][1], ora.read_trajectories())
+    # a plan table in page-locked memory is uploaded from where it is (no staging copy): same results, and the staging
+    # path still works afterwards
+    import torch
+    keep = torch.from_numpy(np.ascontiguousarray(plans, np.float64)).pin_memory()
+    for table in (keep.numpy(), plans):
+        res2 = gpu.plan_batch(qs, table, offs)
+        assert [res2[i].as_dict() for i in range(n)] == [b[0] for b in batch]
 
 
 def test_c2_full_size_properties_and_sampled_oracle():
