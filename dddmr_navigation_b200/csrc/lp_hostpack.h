@@ -142,6 +142,9 @@ class PackPool {
       std::lock_guard<std::mutex> lk(mu_);
       src_ = src; stride_ = stride; dst_ = dst; n_ = n;
       for (int c = 0; c < kPackChunks; ++c) done_[c].store(0, std::memory_order_relaxed);
+      const long long now = now_ns();
+      hot_.store(last_start_ns_ != 0 && now - last_start_ns_ < 2 * spin_ns_, std::memory_order_relaxed);
+      last_start_ns_ = now;
       ++gen_;
       gen_live_.store(gen_, std::memory_order_release);
     }
@@ -168,10 +171,11 @@ class PackPool {
     for (;;) {
       // Spin-then-park: a worker that has just packed a cloud polls for the next one for spin_ns_ before it sleeps on the
       // condition variable. Waking a parked thread costs 100-200 us on the bench hosts (B200LP_HOST_TRACE: the first
-      // 2 MB piece was packed 107-197 us after start() with parked workers, ~15 us with polling ones) — a fifth of a
-      // 2 M-point upload. B200LP_PACK_SPIN_US sets the window (default 2000 us: back-to-back uploads stay hot, a planner
-      // that uploads every 50 ms parks its workers in between; 0 parks at once).
-      if (spin_ns_ > 0) {
+      // 2 MB piece was packed 107-197 us after start() with parked workers, ~20 us with polling ones) — a fifth of a
+      // 2 M-point upload. Only while clouds really arrive back to back: the workers poll when the last two clouds came
+      // within twice the window of each other, so a planner that uploads every 50 ms never burns a core waiting.
+      // B200LP_PACK_SPIN_US sets the window (default 2000 us; 0 parks at once).
+      if (spin_ns_ > 0 && hot_.load(std::memory_order_relaxed)) {
         const long long t0 = now_ns();
         while (gen_live_.load(std::memory_order_acquire) == seen && now_ns() - t0 < spin_ns_) __builtin_ia32_pause();
       }
@@ -202,6 +206,8 @@ class PackPool {
   }
   const long long spin_ns_ = spin_window_ns();
   std::atomic<unsigned long long> gen_live_{0};  // copy of gen_ the spinning workers poll without the mutex
+  std::atomic<bool> hot_{false};                 // the last two clouds arrived within 2 x spin_ns_ of each other
+  long long last_start_ns_ = 0;
   int T_ = 0;
   std::vector<std::thread> th_;
   std::mutex mu_;
