@@ -892,7 +892,6 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   if (overlap && ctx->plan_ev_pending) CK(cudaStreamWaitEvent(ps, ctx->plan_ev, 0));
   ctx->plan_ev_pending = false;  // (on the main stream the upload is ordered before the kernels anyway)
   ctx->cycle_overlapped = overlap;
-  CK(cudaEventRecord(ctx->ev[0], ps));
   if (n_robots > 1) CK(cudaMemcpyAsync(ctx->d_robots.p, ctx->h_robots.p, n_robots * sizeof(RobotIn), cudaMemcpyHostToDevice, ps));
   if (plan_total && !plan_resident && !ctx->plan_uploaded)
     CK(cudaMemcpyAsync(ctx->d_plan7.p, ctx->plan_src ? ctx->plan_src : ctx->h_plan7.p, plan_total * 7 * sizeof(double),
