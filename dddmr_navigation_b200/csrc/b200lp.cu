@@ -906,10 +906,14 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   if (by_value) n_chunks = plan_samples(ctx, q0, rank, count);
   else ctx->prep_plan.planned = 0;
   if (n_chunks > n_chunks_cap) return ctx->fail(B200LP_E_STATE, "plan: %d sample chunks planned, %d provided for", n_chunks, n_chunks_cap);
-  prep_kernel<<<dim3((unsigned)n_chunks, (unsigned)n_robots), kPrepThreads, kPrepSmemBytes, ps>>>(
+  // the longest axis the parameter set can produce (VelocityIterator: max(2, samples) entries + the inserted zero) + the slot
+  // the iterator writes ahead of its count; b200lp_create keeps this below kMaxAxis
+  const int axis_cap = std::max(axis_count(ctx->C.par.linear_x_sample),
+                                std::max(axis_count(ctx->C.par.linear_y_sample), axis_count(ctx->C.par.angular_z_sample))) + 1;
+  prep_kernel<<<dim3((unsigned)n_chunks, (unsigned)n_robots), kPrepThreads, 3 * (size_t)axis_cap * sizeof(float), ps>>>(
       ctx->C, ctx->d_robots.p, q0, by_value, ctx->d_tstart.p, t_cap, ctx->prep_plan, ctx->epoch, ctx->d_tickets.p,
       ctx->d_aggs.p, ctx->d_rec_vel.p, ctx->d_rec_steps.p, ctx->d_rec_dt.p, ctx->d_rec_sample.p, ctx->d_meta.p, ctx->d_plan7.p,
-      ctx->d_plan_pts.p, ctx->d_rec_pose_off.p, ctx->d_poses.p, pose_stride, ctx->d_rec_pp.p, want_pp, ctx->d_class_counts.p);
+      ctx->d_plan_pts.p, ctx->d_rec_pose_off.p, ctx->d_poses.p, pose_stride, ctx->d_rec_pp.p, want_pp, ctx->d_class_counts.p, axis_cap);
   if (host_trace) ht[2] = host_ns();
   CK(cudaEventRecord(ctx->ev[4], ps));
   if (overlap) {

@@ -550,7 +550,6 @@ constexpr int kPrepThreads = B200LP_PREP_THREADS;  // samples per chunk: 16.5 k 
                                                     // forward simulation is bound by the XU / FP64 pipes of the SMs it runs on
 constexpr int kPrepWarps = kPrepThreads / 32;
 constexpr int kPrepSamples = kPrepThreads;      // one velocity sample per thread
-constexpr size_t kPrepSmemBytes = 0;            // (no dynamic shared memory)
 constexpr long long kSpinLimit = 4000000000ll;  // ~2 s of SM clocks: a look-back that waits this long reports an error
 // serial per-CTA jobs (three velocity axes, two pose matrices) are spread over different warps where possible
 __device__ __forceinline__ bool prep_job(int job, int tid) { return tid == (job % kPrepWarps) * 32 + job / kPrepWarps; }
@@ -574,8 +573,13 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
                                                              long long* __restrict__ rec_pose_off,
                                                              float4* __restrict__ pose_rows, long long pose_stride,
                                                              double2* __restrict__ rec_pp, int want_pp,
-                                                             unsigned* __restrict__ class_counts) {
-  __shared__ float s_x[kMaxAxis], s_y[kMaxAxis], s_th[kMaxAxis];
+                                                             unsigned* __restrict__ class_counts, int axis_cap) {
+  // the three velocity axes: dynamic shared memory, `axis_cap` floats each (what the parameter set can produce plus the slot
+  // the iterator writes ahead; 24 KB of static arrays for kMaxAxis entries cost a resident CTA per SM)
+  extern __shared__ float s_axes[];
+  float* const s_x = s_axes;
+  float* const s_y = s_axes + axis_cap;
+  float* const s_th = s_axes + 2 * axis_cap;
   __shared__ double s_R0[9], s_t0[3], s_gL[9], s_gt[3];
   __shared__ unsigned long long s_wposes[kPrepThreads / 32];
   __shared__ int s_n[3];
