@@ -252,7 +252,8 @@ int b200lp_get_shard_cuts(const b200lp_ctx* ctx, float* shares /* B200LP_MAX_PEE
 int b200lp_set_adaptive_cuts(b200lp_ctx* ctx, int on);
 
 /* Fleet cycle: n_robots independent queries on the shared cloud. Robot i's prune plan is
- * plans[plan_offsets[i] .. plan_offsets[i+1]) (7 doubles per pose). */
+ * plans[plan_offsets[i] .. plan_offsets[i+1]) (7 doubles per pose). A plan table in page-locked host memory
+ * (cudaHostAlloc / cudaHostRegister) is uploaded from where it is; any other buffer is staged first (one extra host copy). */
 int b200lp_plan_batch(b200lp_ctx* ctx, const b200lp_query* qs, size_t n_robots, const double* plans,
                       const int64_t* plan_offsets /* n_robots+1 */, b200lp_result* outs);
 
