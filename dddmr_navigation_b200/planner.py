@@ -241,7 +241,10 @@ class LocalPlanner:
             o = np.ascontiguousarray(plan_offsets, dtype=np.int64)
             assert o.shape == (n + 1,)
             c = (plans, plan_offsets, n, p, o, p.ctypes.data_as(C.POINTER(C.c_double)), o.ctypes.data_as(C.POINTER(C.c_int64)))
-            self._batch_cache = c
+            # (kept only when the views ARE the caller's buffers: a converted copy would go stale when the caller refills its array)
+            direct = all(isinstance(a, np.ndarray) and a.flags.c_contiguous and a.dtype == d
+                         for a, d in ((plans, np.float64), (plan_offsets, np.int64)))
+            self._batch_cache = c if direct else None
         res = (abi.Result * n)()
         self._ck(self.lib.b200lp_plan_batch(self.h, queries, n, c[5], c[6], res))
         self._n_robots = n
