@@ -172,6 +172,8 @@ struct b200lp_ctx {
   float axes_window[6] = {0, 0, 0, 0, 0, 0};
   int axes_n[3] = {0, 0, 0};
   bool axes_valid = false;
+  float row_work[kMaxAxis];               // plan_samples: inclusive prefix of the estimated work per linear-speed row (shard cuts)
+  bool row_work_valid = false;
   const double* plan_src = nullptr;       // fleet calls whose plan table already sits in pinned host memory: uploaded from there
   PrepPlan prep_plan{};                   // host-planned sample layout of the single-robot launch being issued (plan_samples)
   unsigned long long sample_cuts_hash = 0; // hash of the sample cuts that layout used: all ranks of an exchange cycle must agree
@@ -668,12 +670,14 @@ int plan_samples(b200lp_ctx* ctx, const RobotIn& q, int rank, int count) {
       memcpy(ctx->axes_window, win, sizeof(win));
       for (int a = 0; a < 3; ++a) ctx->axes_n[a] = n[a];
       ctx->axes_valid = true;
+      ctx->row_work_valid = false;
     }
     n_raw = (long long)n[0] * n[1] * n[2];
   } else {
     pp.host_axes = 0;
     pp.n_exc = 0;
     ctx->axes_valid = false;
+    ctx->row_work_valid = false;
     if (sampling_on) n_raw = 2;
   }
   pp.n_raw = n_raw;
@@ -685,17 +689,20 @@ int plan_samples(b200lp_ctx* ctx, const RobotIn& q, int rank, int count) {
   const int W = std::max(1, std::min(count, (int)B200LP_MAX_PEERS));
   for (int k = 0; k <= W; ++k) cut[k] = n_raw * k / W;
   if (W > 1 && axes && n_raw > 0) {
-    static thread_local float w[kMaxAxis];
+    float* w = ctx->row_work;  // inclusive prefix of the rows' estimated work: a function of the window, kept with the axes
     const int nx = n[0], nths = n[2];
     const long long row = (long long)n[1] * nths;
-    const float ta = (float)(P.sim_time / P.sim_granularity), tb = (float)(P.sim_time / P.angular_sim_granularity);
-    const float bw = fmaxf(fabsf(ax[2][0]), fabsf(ax[2][nths - 1])) * tb;  // largest angular step count of the axis
-    float acc = 0.f;
-    for (int ix = 0; ix < nx; ++ix) {
-      const float a = fabsf(ax[0][ix]) * ta;
-      const float mean_steps = (a < bw) ? a + (bw - a) * (bw - a) / (2.0f * bw) : a;  // E[max(a, U(0, bw))]
-      acc += mean_steps + 10.0f;  // + the fixed part of a trajectory (work fetch, critic epilogue, prep)
-      w[ix] = acc;                // inclusive prefix over the rows
+    if (!ctx->row_work_valid) {
+      const float ta = (float)(P.sim_time / P.sim_granularity), tb = (float)(P.sim_time / P.angular_sim_granularity);
+      const float bw = fmaxf(fabsf(ax[2][0]), fabsf(ax[2][nths - 1])) * tb;  // largest angular step count of the axis
+      float acc = 0.f;
+      for (int ix = 0; ix < nx; ++ix) {
+        const float a = fabsf(ax[0][ix]) * ta;
+        const float mean_steps = (a < bw) ? a + (bw - a) * (bw - a) / (2.0f * bw) : a;  // E[max(a, U(0, bw))]
+        acc += mean_steps + 10.0f;  // + the fixed part of a trajectory (work fetch, critic epilogue, prep)
+        w[ix] = acc;
+      }
+      ctx->row_work_valid = true;
     }
     const float total = w[nx - 1];
     for (int k = 1; k < W; ++k) {
