@@ -998,9 +998,8 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
     CK(cudaGetLastError());
     if (host_trace) {
       ht[4] = host_ns();
-      float ms_up = 0.f, ms_all = 0.f;
+      float ms_all = 0.f;
       cudaEventElapsedTime(&ms_all, ctx->ev[1], ctx->ev[3]);
-      (void)ms_up;
       fprintf(stderr, "host trace (fleet of %zu): entry -> launches %.1f us, prep launch %.1f us, other launches %.1f us, wait %.1f us; call %.1f us, "
                       "first kernel -> results on the host %.1f us by CUDA events\n", n_robots, (ht[1] - ht[0]) / 1e3, (ht[2] - ht[1]) / 1e3,
               (ht[3] - ht[2]) / 1e3, (ht[4] - ht[3]) / 1e3, (ht[4] - ht[0]) / 1e3, ms_all * 1e3f);
