@@ -200,6 +200,7 @@ struct b200lp_ctx {
   DevBuf<unsigned> d_class_counts;       // entries per list (zeroed by prep_kernel)
   DevBuf<unsigned long long> d_tstart;   // globaltimer at the start of the cycle (prep_kernel's first CTA)
   bool plan_uploaded = false;            // d_plan7 already holds the host plan (b200lp_set_plan uploads it)
+  cudaEvent_t fleet_fork_ev = nullptr, fleet_plan_ev = nullptr;  // fleet calls: the plan table's upload beside prep_kernel
   cudaEvent_t plan_ev = nullptr;         // ... as of this event on the main stream
   bool plan_ev_pending = false;          // a prep kernel on the second stream has not yet been ordered behind it
   bool adaptive_cuts = true;             // sample-sharded exchange cycles move their cuts with the ranks' device times
@@ -899,10 +900,26 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   if (overlap && ctx->plan_ev_pending) CK(cudaStreamWaitEvent(ps, ctx->plan_ev, 0));
   ctx->plan_ev_pending = false;  // (on the main stream the upload is ordered before the kernels anyway)
   ctx->cycle_overlapped = overlap;
+  // A fleet's plan table (1.7 MB for 512 robots) goes up on the copy stream BESIDE prep_kernel: the robots' records carry the
+  // one pose of each plan prep_kernel needs (the goal), and the float copy of the plan positions is made by cull_kernel,
+  // which waits for the table like plan_kernel behind it. Ordered behind everything the main stream was given so far
+  // (the previous cycle's readers of d_plan7 / d_plan_pts).
+  int defer_pts = 0;
   if (n_robots > 1) CK(cudaMemcpyAsync(ctx->d_robots.p, ctx->h_robots.p, n_robots * sizeof(RobotIn), cudaMemcpyHostToDevice, ps));
-  if (plan_total && !plan_resident && !ctx->plan_uploaded)
-    CK(cudaMemcpyAsync(ctx->d_plan7.p, ctx->plan_src ? ctx->plan_src : ctx->h_plan7.p, plan_total * 7 * sizeof(double),
-                       cudaMemcpyHostToDevice, ps));
+  if (plan_total && !plan_resident && !ctx->plan_uploaded) {
+    const double* src = ctx->plan_src ? ctx->plan_src : ctx->h_plan7.p;
+    if (n_robots > 1 && !overlap) {
+      if (!ctx->fleet_fork_ev) CK(cudaEventCreateWithFlags(&ctx->fleet_fork_ev, cudaEventDisableTiming));
+      if (!ctx->fleet_plan_ev) CK(cudaEventCreateWithFlags(&ctx->fleet_plan_ev, cudaEventDisableTiming));
+      CK(cudaEventRecord(ctx->fleet_fork_ev, ctx->stream));
+      CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->fleet_fork_ev, 0));
+      CK(cudaMemcpyAsync(ctx->d_plan7.p, src, plan_total * 7 * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_stream));
+      CK(cudaEventRecord(ctx->fleet_plan_ev, ctx->copy_stream));
+      defer_pts = 1;
+    } else {
+      CK(cudaMemcpyAsync(ctx->d_plan7.p, src, plan_total * 7 * sizeof(double), cudaMemcpyHostToDevice, ps));
+    }
+  }
   CK(cudaEventRecord(ctx->ev[1], ps));
   // single-robot cycles hand their query to the kernels as an argument; the device copy (read by the read-back kernels
   // only) follows the launches
@@ -920,7 +937,8 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   prep_kernel<<<dim3((unsigned)n_chunks, (unsigned)n_robots), kPrepThreads, 3 * (size_t)axis_cap * sizeof(float), ps>>>(
       ctx->C, ctx->d_robots.p, q0, by_value, ctx->d_tstart.p, t_cap, ctx->prep_plan, ctx->epoch, ctx->d_tickets.p,
       ctx->d_aggs.p, ctx->d_rec_vel.p, ctx->d_rec_steps.p, ctx->d_rec_dt.p, ctx->d_rec_sample.p, ctx->d_meta.p, ctx->d_plan7.p,
-      ctx->d_plan_pts.p, ctx->d_rec_pose_off.p, ctx->d_poses.p, pose_stride, ctx->d_rec_pp.p, want_pp, ctx->d_class_counts.p, axis_cap);
+      ctx->d_plan_pts.p, ctx->d_rec_pose_off.p, ctx->d_poses.p, pose_stride, ctx->d_rec_pp.p, want_pp, ctx->d_class_counts.p, axis_cap,
+      defer_pts);
   if (host_trace) ht[2] = host_ns();
   CK(cudaEventRecord(ctx->ev[4], ps));
   if (overlap) {
@@ -929,11 +947,13 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   }
   // the float pre-cull of every pose (needs the grid) and the work lists plan_kernel drains
   const int mask_stride = ((int)max_steps_bound(ctx->C.lim, ctx->C.par) + 31) / 32;
+  if (defer_pts) CK(cudaStreamWaitEvent(ctx->stream, ctx->fleet_plan_ev, 0));  // cull_kernel converts the plan positions
   // (a planned launch lists at most ns x kPrepThreads trajectories: a sample shard does not pay for the whole grid's CTAs)
   const int cull_traj = by_value ? std::min<long long>(t_cap, (long long)ctx->prep_plan.ns * kPrepThreads) : t_cap;
   cull_kernel<<<dim3((unsigned)((cull_traj + kCullTraj - 1) / kCullTraj), (unsigned)n_robots), kCullThreads, 0, ctx->stream>>>(
       ctx->C, ctx->grid, ctx->d_robots.p, q0, by_value, ctx->d_meta.p, t_cap, ctx->d_rec_steps.p, ctx->d_rec_pose_off.p,
-      ctx->d_poses.p, ctx->d_surv.p, mask_stride, ctx->d_order.p, T, ctx->d_class_counts.p, ctx->d_hist.p);
+      ctx->d_poses.p, ctx->d_surv.p, mask_stride, ctx->d_order.p, T, ctx->d_class_counts.p, ctx->d_hist.p, ctx->d_plan7.p,
+      ctx->d_plan_pts.p, defer_pts);
   CK(cudaEventRecord(ctx->ev[7], ctx->stream));
   PeerExchange px{};
   px.t_start = ctx->d_tstart.p;
@@ -1029,14 +1049,16 @@ int run_cycle(b200lp_ctx* ctx, size_t n_robots, int rank, int count, b200lp_resu
   return B200LP_OK;
 }
 
-void fill_robot(RobotIn* r, const b200lp_query* q, int64_t plan_off, int32_t plan_n) {
+void fill_robot(RobotIn* r, const b200lp_query* q, int64_t plan_off, int32_t plan_n, const double* goal7 /* may be null */) {
   memcpy(r->pose, q->pose, sizeof(r->pose));
   memcpy(r->twist, q->twist, sizeof(r->twist));
   r->max_speed_override = q->max_speed_override;
   r->heading_deviation = q->heading_deviation;
   r->plan_off = plan_off;
   r->plan_n = plan_n;
-  r->pad = 0;
+  r->goal_valid = (goal7 && plan_n > 0) ? 1 : 0;
+  if (r->goal_valid) memcpy(r->goal, goal7, sizeof(r->goal));
+  else memset(r->goal, 0, sizeof(r->goal));
 }
 
 }  // namespace
@@ -1163,6 +1185,8 @@ void b200lp_destroy(b200lp_ctx* ctx) {
   for (auto& ev : ctx->cev)
     if (ev) cudaEventDestroy(ev);
   if (ctx->plan_ev) cudaEventDestroy(ctx->plan_ev);
+  if (ctx->fleet_fork_ev) cudaEventDestroy(ctx->fleet_fork_ev);
+  if (ctx->fleet_plan_ev) cudaEventDestroy(ctx->fleet_plan_ev);
   peer_detach(ctx);
   ctx->d_peer_block.release();
   ctx->d_push_ticket.release(); ctx->d_share_err.release(); ctx->h_share_hdr.release(); ctx->h_share_err.release();
@@ -1343,7 +1367,7 @@ static int plan_shard_common(b200lp_ctx* ctx, const b200lp_query* q, int rank, i
   const size_t np = resident ? (size_t)ctx->plan_n_device : ctx->plan_host.size() / 7;
   CK(ctx->h_robots.reserve(1));
   CK(ctx->h_plan7.reserve(std::max<size_t>(np * 7, 7)));
-  fill_robot(ctx->h_robots.p, q, 0, (int32_t)np);
+  fill_robot(ctx->h_robots.p, q, 0, (int32_t)np, (np && !resident) ? ctx->plan_host.data() + (np - 1) * 7 : nullptr);
   if (np && !resident && !ctx->plan_uploaded) memcpy(ctx->h_plan7.p, ctx->plan_host.data(), np * 7 * sizeof(double));
   return run_cycle(ctx, 1, rank, count, out, resident, exchange);
 }
@@ -1495,7 +1519,7 @@ int b200lp_plan_batch(b200lp_ctx* ctx, const b200lp_query* qs, size_t n_robots, 
   for (size_t i = 0; i < n_robots; ++i) {
     const int64_t a = plan_offsets[i], b = plan_offsets[i + 1];
     if (a < 0 || b < a || b > total || b - a > B200LP_MAX_PLAN) return ctx->fail(B200LP_E_INVALID, "plan_batch: bad plan offsets for robot %zu", i);
-    fill_robot(ctx->h_robots.p + i, qs + i, a, (int32_t)(b - a));
+    fill_robot(ctx->h_robots.p + i, qs + i, a, (int32_t)(b - a), b > a ? plans + (size_t)(b - 1) * 7 : nullptr);
   }
   // A plan table that already sits in page-locked memory is uploaded from where it is (the call returns after the cycle, so
   // the caller's buffer outlives the copy); anything else goes through the pinned staging buffer first — for 512 robots x 60

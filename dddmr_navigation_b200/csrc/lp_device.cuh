@@ -86,7 +86,9 @@ struct RobotIn {
   double heading_deviation;
   int64_t plan_off;
   int32_t plan_n;
-  int32_t pad;
+  int32_t goal_valid;  // goal[] holds the last pose of the robot's prune plan (the host had the plan when it filled this record)
+  double goal[7];      // prune_plan_.poses.back(): what the pure-pursuit critic aims at; lets prep_kernel start before the plan
+                       // table itself has reached the device (fleet calls upload it beside prep_kernel)
 };
 
 struct RobotMeta {

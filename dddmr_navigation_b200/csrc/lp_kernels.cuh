@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
                                                              long long* __restrict__ rec_pose_off,
                                                              float4* __restrict__ pose_rows, long long pose_stride,
                                                              double2* __restrict__ rec_pp, int want_pp,
-                                                             unsigned* __restrict__ class_counts, int axis_cap) {
+                                                             unsigned* __restrict__ class_counts, int axis_cap, int defer_pts) {
   // the three velocity axes: dynamic shared memory, `axis_cap` floats each (what the parameter set can produce plus the slot
   // the iterator writes ahead; 24 KB of static arrays for kMaxAxis entries cost a resident CTA per SM)
   extern __shared__ float s_axes[];
@@ -619,12 +619,13 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(Consts C, const Robo
     s_t0[0] = q.pose[0]; s_t0[1] = q.pose[1]; s_t0[2] = q.pose[2];
   }
   if (prep_job(4, tid) && q.plan_n > 0) {
-    const double* e = plan7 + (q.plan_off + q.plan_n - 1) * 7;  // prune_plan_.poses.back()
+    const double* e = q.goal_valid ? q.goal : plan7 + (q.plan_off + q.plan_n - 1) * 7;  // prune_plan_.poses.back()
     quat_to_matrix(e[3], e[4], e[5], e[6], s_gL);
     s_gt[0] = e[0]; s_gt[1] = e[1]; s_gt[2] = e[2];
   }
-  // pcl_prune_plan_: float-cast plan positions (model_shared_data.h:83-91)
-  if (chunk == 0)
+  // pcl_prune_plan_: float-cast plan positions (model_shared_data.h:83-91); left to cull_kernel when the plan table is
+  // still on its way (defer_pts: fleet calls)
+  if (chunk == 0 && !defer_pts)
     for (int i = tid; i < q.plan_n; i += blockDim.x) {
       const double* p = plan7 + (q.plan_off + i) * 7;
       plan_pts[q.plan_off + i] = make_float4((float)p[0], (float)p[1], (float)p[2], 0.f);
@@ -1210,7 +1211,8 @@ __global__ void __launch_bounds__(kCullThreads)
 cull_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0, int by_value, const RobotMeta* __restrict__ meta,
             int t_cap, const int* __restrict__ rec_steps, const long long* __restrict__ rec_pose_off,
             const float4* __restrict__ poses, uint32_t* __restrict__ surv, int mask_stride, int* __restrict__ order,
-            size_t order_stride, unsigned* __restrict__ class_counts, const unsigned* __restrict__ hist) {
+            size_t order_stride, unsigned* __restrict__ class_counts, const unsigned* __restrict__ hist,
+            const double* __restrict__ plan7, float4* __restrict__ plan_pts, int defer_pts) {
   constexpr int kBitWords = kCullTraj * (B200LP_MAX_STEPS / 32) + 1;
   __shared__ float s_R0f[9], s_t0f[3];
   __shared__ long long s_off[kCullTraj];
@@ -1218,6 +1220,14 @@ cull_kernel(Consts C, GridDev g, const RobotIn* __restrict__ robots, RobotIn q0,
   __shared__ uint32_t s_bits[kBitWords];
   __shared__ unsigned s_cnt[kCostClasses], s_base[kCostClasses];
   const int robot = blockIdx.y;
+  if (defer_pts && blockIdx.x == 0) {  // pcl_prune_plan_ (model_shared_data.h:83-91) of this robot: see prep_kernel
+    const long long off = by_value ? q0.plan_off : robots[robot].plan_off;
+    const int pn = by_value ? q0.plan_n : robots[robot].plan_n;
+    for (int i = threadIdx.x; i < pn; i += kCullThreads) {
+      const double* p = plan7 + (off + i) * 7;
+      plan_pts[off + i] = make_float4((float)p[0], (float)p[1], (float)p[2], 0.f);
+    }
+  }
   const RobotMeta m = meta[robot];
   const int n_local = min(m.t_end, t_cap) - m.t_begin;
   const int first = (int)blockIdx.x * kCullTraj;
