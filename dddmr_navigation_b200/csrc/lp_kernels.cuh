@@ -1803,7 +1803,8 @@ __global__ void __launch_bounds__(kArgminThreads)
 argmin_kernel(Consts C, const RobotMeta* __restrict__ meta, int t_cap, const float4* __restrict__ rec_vel,
               const double* __restrict__ cost, const int* __restrict__ first_hit, BlockBest* partial,
               unsigned* __restrict__ tickets, b200lp_result* __restrict__ results,
-              unsigned long long* __restrict__ work_counter) {
+              unsigned long long* __restrict__ work_counter, b200lp_result* host_results, RobotMeta* host_meta,
+              unsigned* __restrict__ robots_done, unsigned long long* host_seq, unsigned long long seq) {
   __shared__ BlockBest s_best[kArgminThreads / 32];
   __shared__ int s_last;
   const int robot = blockIdx.y, B = gridDim.x;
@@ -1875,6 +1876,18 @@ argmin_kernel(Consts C, const RobotMeta* __restrict__ meta, int t_cap, const flo
     }
     results[robot] = r;
     if (B > 1) tickets[robot] = 0u;  // ready for the next launch
+    // Fleet results go straight into mapped pinned host memory, like a single robot's (DirectOut): the robot that
+    // finishes last raises the sequence word the host thread spins on — no read-back copies, no stream synchronisation.
+    if (host_results) {
+      host_results[robot] = r;
+      host_meta[robot] = m;
+      __threadfence_system();  // this robot's block is visible to the host before it counts as done
+      if (atomicAdd(robots_done, 1u) == gridDim.y - 1u) {
+        *robots_done = 0u;  // ready for the next launch
+        __threadfence_system();
+        *(volatile unsigned long long*)host_seq = seq;
+      }
+    }
   }
 }
 
