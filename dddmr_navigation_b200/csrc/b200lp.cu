@@ -1,8 +1,10 @@
 // b200lp.cu — C ABI (include/b200lp.h) over the sm_100a kernels in lp_kernels.cuh.
 //
 // Build (see __graft_entry__.build):
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
-// -fmad=false is part of the numeric contract (lp_device.cuh). There is no CPU path in this file.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC,-pthread,-ffp-contract=off
+// -fmad=false is part of the numeric contract (lp_device.cuh); -ffp-contract=off keeps the host code that plans a
+// single robot's velocity samples (plan_samples) on the arithmetic the kernels use. There is no CPU path in this file.
+// -DB200LP_COUNT=1 / -DB200LP_CHECKS=1 give the counting and the checking build (never timed).
 #include <cuda_runtime.h>
 #include <nvtx3/nvToolsExt.h>  // header-only NVTX 3: ranges cost a null-pointer test unless a profiler injects its library
 

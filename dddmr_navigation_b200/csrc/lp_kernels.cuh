@@ -1,8 +1,12 @@
 // lp_kernels.cuh — the sm_100a kernels of the rollout-and-score path.
 //
-//   grid build : bounds_kernel -> hist_kernel -> scan (3 kernels) -> scatter_kernel
-//   plan cycle : prep_kernel (velocity sampling + trajectory list) -> plan_kernel (fused rollout,
-//                obstacle query, critics, block argmin, last-block final argmin)
+//   grid build : bounds_pack_kernel (clouds not packed on the host) -> hist_kernel (per upload piece; leaves every point's
+//                rank inside its cell) -> scan_kernel (one launch, decoupled look-back) -> scatter_kernel -> sat_y / sat_z
+//   plan cycle : prep_kernel (velocity samples, trajectory list in the reference's order, forward simulation, pure-pursuit
+//                terms) -> cull_kernel (float pre-cull of every pose against the summed-volume table, work lists) ->
+//                plan_kernel (persistent warps: cuboid geometry, obstacle sweep, critics, ordered sum; for one robot also
+//                the argmin and — for sample shards — the cross-GPU exchange) -> argmin_kernel (fleets)
+//   shared map : share_* kernels (one upload for all ranks of a peer group, rows pushed over NVLink)
 //   read-back  : poses_kernel, count_radius_kernel (diagnostics / parity / roofline accounting)
 //   either side: prune_kernel, blocked_kernel here; the lidar observation producer in lp_observe.cuh
 #pragma once
